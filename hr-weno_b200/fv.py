@@ -1,0 +1,83 @@
+"""The example `rhs` routines (example1:72-109, example2:73-129) as one fused device operator."""
+from __future__ import annotations
+
+import ctypes as C
+
+import numpy as np
+
+from . import _abi
+
+
+def make_desc(
+    n,
+    k=3,
+    eps=1e-6,
+    rows=1,
+    flux_model=_abi.FLUX_BURGERS,
+    flux_scheme=_abi.SCHEME_GODUNOV,
+    flux_coef=(1.0, 1.0),
+    alpha=1.0,
+    bc=_abi.BC_COPY_NEIGHBOUR,
+    width=None,
+    linear=None,
+    mode=_abi.MODE_STRICT,
+    rank=0,
+    nranks=1,
+    global_n=0,
+    global_offset=0,
+):
+    """Build a hrweno_fv_desc.  `width` = list of per-axis width arrays, or `linear` = (xmin, xmax)."""
+    n = (int(n),) if np.isscalar(n) else tuple(int(x) for x in n)
+    d = _abi.FvDesc()
+    d.abi_version = _abi.ABI_VERSION
+    d.ndim = len(n)
+    d.n[0] = n[0]
+    d.n[1] = n[1] if len(n) > 1 else 1
+    d.rows = rows
+    d.k, d.eps = k, eps
+    d.flux_model, d.flux_scheme, d.bc, d.mode = flux_model, flux_scheme, bc, mode
+    d.flux_coef[0], d.flux_coef[1] = flux_coef
+    d.alpha = alpha
+    keep = []
+    if linear is not None:
+        d.grid_kind = _abi.GRID_LINEAR
+        d.xmin, d.xmax = linear
+    else:
+        d.grid_kind = _abi.GRID_WIDTH_ARRAY
+        for a in range(d.ndim):
+            w = np.ascontiguousarray(width[a], dtype=np.float64)
+            keep.append(w)
+            d.width[a] = w.ctypes.data_as(_abi.c_double_p)
+    d.rank, d.nranks, d.global_n, d.global_offset = rank, nranks, global_n, global_offset
+    d._keepalive = keep
+    return d
+
+
+class FV:
+    def __init__(self, desc):
+        self.desc = desc
+        self._h = C.c_void_p()
+        _abi.check(_abi.lib().hrweno_fv_create(C.byref(self._h), C.byref(desc)))
+        self.neq = _abi.lib().hrweno_fv_neq(self._h)
+
+    def __del__(self):
+        if getattr(self, "_h", None) and self._h.value:
+            _abi.lib().hrweno_fv_destroy(self._h)
+            self._h = C.c_void_p()
+
+    def rhs(self, t, v):
+        v = np.ascontiguousarray(v, dtype=np.float64)
+        out = np.empty_like(v)
+        _abi.check(_abi.lib().hrweno_fv_rhs(self._h, t, v.ctypes.data, out.ctypes.data))
+        return out
+
+    def rhs_dev(self, t, v_ptr, out_ptr, stream=None):
+        _abi.check(_abi.lib().hrweno_fv_rhs_dev(self._h, t, v_ptr, out_ptr, stream))
+
+    def export_halo(self):
+        buf = C.create_string_buffer(_abi.IPC_HANDLE_BYTES)
+        _abi.check(_abi.lib().hrweno_fv_export_halo(self._h, buf))
+        return buf.raw
+
+    def import_halo(self, left, right):
+        _abi.check(_abi.lib().hrweno_fv_import_halo(self._h, left, right))

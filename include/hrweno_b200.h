@@ -1,0 +1,200 @@
+/*
+ * hrweno_b200.h -- C ABI of the B200-native HR-WENO finite-volume update path.
+ *
+ * The reference (HugoMVale/HR-WENO) is pure Fortran and has no FFI boundary of
+ * its own; its surface for this path is the set of module procedures cited
+ * below (paths relative to the reference tree).  This header is the boundary a
+ * thin ISO_C_BINDING shim (fortran/) binds so that the
+ * Fortran-side names keep working:
+ *
+ *   weno(ncells,k,eps,xedges)         src/hrweno_weno.f90:54-127   -> hrweno_weno_create
+ *   weno%reconstruct(v,vl,vr)         src/hrweno_weno.f90:129-219  -> hrweno_weno_reconstruct[_batch|_dev]
+ *   weno%cnu                          src/hrweno_weno.f90:41,221-297 -> hrweno_weno_get_cnu
+ *   godunov(f,vm,vp,x,t)              src/hrweno_fluxes.f90:47-76  -> hrweno_godunov / hrweno_flux_faces
+ *   lax_friedrichs(f,vm,vp,x,t,alpha) src/hrweno_fluxes.f90:22-45  -> hrweno_lax_friedrichs / hrweno_flux_faces
+ *   rktvd(fu,neq,order)               src/hrweno_tvdode.f90:69-95  -> hrweno_rktvd_create[_fused]
+ *   rktvd%integrate(u,t,tout,dt,itask)src/hrweno_tvdode.f90:97-178 -> hrweno_ode_integrate[_dev]
+ *   mstvd(fu,neq)                     src/hrweno_tvdode.f90:180-201-> hrweno_mstvd_create[_fused]
+ *   mstvd%integrate(u,t,tout,dt)      src/hrweno_tvdode.f90:203-271-> hrweno_ode_integrate[_dev]
+ *   example rhs (1D)                  example/example1_burgers_1d_fv.f90:72-109 -> hrweno_fv_* (ndim=1)
+ *   example rhs (2D, split)           example/example2_pbe_2d_fv.f90:73-129     -> hrweno_fv_* (ndim=2)
+ *
+ * Conventions: plain pointers and sizes only; every entry point returns an
+ * int status (0 = ok) unless it is a pure value function; the message of the
+ * last failure on the calling thread is available from hrweno_last_error().
+ * "host" pointers are ordinary CPU memory; "dev" pointers are CUDA device
+ * memory on the current device, and `stream` is a cudaStream_t passed as
+ * void* (NULL = legacy default stream).  All arithmetic is IEEE fp64
+ * (rk = real64, src/hrweno_kinds.F90:16).
+ *
+ * There is no CPU fallback: every compute entry point runs CUDA kernels and
+ * fails with HRWENO_ECUDA when no device is usable.
+ */
+#ifndef HRWENO_B200_H
+#define HRWENO_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define HRWENO_ABI_VERSION 1
+
+/* ---- status codes --------------------------------------------------------- */
+enum hrweno_status {
+   HRWENO_OK = 0,
+   HRWENO_EINVAL = 1, /* invalid argument: the reference would `error stop` (weno.f90:75-108, tvdode.f90:83,89) */
+   HRWENO_ECUDA = 2,  /* CUDA runtime failure or no device */
+   HRWENO_ENOMEM = 3,
+   HRWENO_ESTATE = 4, /* object in error state (istate < 1, tvdode.f90:126,228) */
+   HRWENO_ECOMM = 5   /* multi-GPU halo exchange failure / timeout */
+};
+
+/* ---- enums for the fused finite-volume path ------------------------------- */
+enum hrweno_flux_model {
+   HRWENO_FLUX_BURGERS = 0, /* f(v) = (v**2)/2          example1:120 */
+   HRWENO_FLUX_LINEAR = 1   /* f(v) = a*v (a=1: f = v)  example2:140,153 */
+};
+enum hrweno_flux_scheme {
+   HRWENO_SCHEME_GODUNOV = 0,       /* fluxes.f90:67-74 */
+   HRWENO_SCHEME_LAX_FRIEDRICHS = 1 /* fluxes.f90:43, alpha supplied by the caller */
+};
+enum hrweno_bc {
+   HRWENO_BC_COPY_NEIGHBOUR = 0, /* fedges(0)=fedges(1), fedges(nc)=fedges(nc-1)   example1:103-104 */
+   HRWENO_BC_ZERO_FLUX = 1       /* fedges(0)=fedges(nc)=0                          example2:117-120 */
+};
+enum hrweno_grid_kind {
+   HRWENO_GRID_WIDTH_ARRAY = 0, /* width(:) arrays streamed from memory (any grid1 kind) */
+   HRWENO_GRID_LINEAR = 1       /* 1D only: width recomputed on device bit-identically to grid1%linear
+                                   (grids.f90:76-79,247): edges(i)=xmin+rx*i, width=edges(i)-edges(i-1) */
+};
+enum hrweno_mode {
+   HRWENO_MODE_STRICT = 0, /* reference operation order, no FMA contraction: bit-identical to the oracle */
+   HRWENO_MODE_FAST = 1    /* same formulas, division-light weights and FMA contraction; within the
+                              north-star tolerances (1e-12 normwise per output time, few ULP reconstruct) */
+};
+
+/* ---- opaque handles ------------------------------------------------------- */
+typedef struct hrweno_weno hrweno_weno; /* type(weno)          weno.f90:23-46 */
+typedef struct hrweno_fv hrweno_fv;     /* the example `rhs`: reconstruct + flux + divergence */
+typedef struct hrweno_ode hrweno_ode;   /* type(rktvd)/type(mstvd)  tvdode.f90:14-48 */
+
+/* ---- library -------------------------------------------------------------- */
+int hrweno_abi_version(void);
+const char *hrweno_last_error(void); /* thread-local, never NULL */
+int hrweno_device_count(void);       /* number of usable CUDA devices (0 if none) */
+
+/* ---- WENO reconstruction (src/hrweno_weno.f90) ---------------------------- */
+
+/* weno_init (weno.f90:54-127).  Validation mirrors the reference: ncells > 0,
+ * 1 <= k <= 3, eps > epsilon(1d0).  xedges == NULL selects the uniform-grid
+ * tables c1/c2/c3 (weno.f90:12-21); otherwise xedges[0..ncells] are the cell
+ * edges and cnu(0:k-1,-1:k-1,1:ncells) is computed per weno_calc_cnu
+ * (weno.f90:221-297, Shu eq. 2.20). */
+int hrweno_weno_create(hrweno_weno **out, int64_t ncells, int k, double eps, const double *xedges);
+void hrweno_weno_destroy(hrweno_weno *w);
+int hrweno_weno_info(const hrweno_weno *w, int64_t *ncells, int *k, double *eps, int *uniform_grid);
+/* copy of cnu in the reference's column-major order cnu(j,r,i): index j + k*((r+1) + (k+1)*(i-1)) */
+int hrweno_weno_get_cnu(const hrweno_weno *w, double *cnu_host);
+
+/* weno_reconstruct (weno.f90:129-219): v(ncells) -> vl(ncells), vr(ncells), host memory.
+ * Re-entrant for one handle (the reference procedure is pure with intent(in) self). */
+int hrweno_weno_reconstruct(const hrweno_weno *w, const double *v, double *vl, double *vr);
+/* `rows` independent rows of ncells cells; element (row, i) of v at v[row*ldv + i*incv]
+ * (incv > 1 expresses the strided sections of example2:107); outputs at [row*ldo + i]. */
+int hrweno_weno_reconstruct_batch(const hrweno_weno *w, int64_t rows, const double *v, int64_t ldv,
+                                  int64_t incv, double *vl, double *vr, int64_t ldo);
+/* same, device pointers, asynchronous on `stream` */
+int hrweno_weno_reconstruct_dev(const hrweno_weno *w, int64_t rows, const double *v_dev, int64_t ldv,
+                                int64_t incv, double *vl_dev, double *vr_dev, int64_t ldo, void *stream);
+
+/* ---- numerical fluxes (src/hrweno_fluxes.f90) ------------------------------ */
+
+/* flux callback: abstract interface `flux(u, x(:), t)` (fluxes.f90:12-18) */
+typedef double (*hrweno_flux_fn)(void *ctx, double u, const double *x, int nx, double t);
+/* pointwise host helpers with a user callback, exactly the reference signatures */
+double hrweno_lax_friedrichs(hrweno_flux_fn f, void *ctx, double vm, double vp, const double *x, int nx,
+                             double t, double alpha);
+double hrweno_godunov(hrweno_flux_fn f, void *ctx, double vm, double vp, const double *x, int nx, double t);
+/* closed-set device evaluation over n faces: h[i] = scheme(model; vm[i], vp[i]) (host pointers) */
+int hrweno_flux_faces(int flux_scheme, int flux_model, double flux_coef, double alpha, int64_t n,
+                      const double *vm, const double *vp, double *h);
+
+/* ---- fused finite-volume right-hand side ---------------------------------- */
+typedef struct hrweno_fv_desc {
+   int32_t abi_version; /* HRWENO_ABI_VERSION */
+   int32_t ndim;        /* 1 or 2 */
+   int64_t n[2];        /* cells per dimension; n[0] is the contiguous axis; storage u[(j)*n[0]+i] (example2:50) */
+   int64_t rows;        /* ndim==1: number of independent 1D problems stored row after row (>=1) */
+   int32_t k;           /* 1..3, order 2k-1 */
+   int32_t flux_model;  /* enum hrweno_flux_model */
+   int32_t flux_scheme; /* enum hrweno_flux_scheme */
+   int32_t bc;          /* enum hrweno_bc */
+   int32_t grid_kind;   /* enum hrweno_grid_kind */
+   int32_t mode;        /* enum hrweno_mode */
+   double eps;          /* WENO smoothing factor (> epsilon) */
+   double flux_coef[2]; /* LINEAR: a per dimension */
+   double alpha;        /* LAX_FRIEDRICHS: max|f'(v)|, caller supplied (fluxes.f90:40) */
+   double xmin, xmax;   /* GRID_LINEAR: domain of the *global* grid */
+   const double *width[2]; /* GRID_WIDTH_ARRAY: host arrays width[d][0..n[d]-1] (copied) */
+   /* slab decomposition across GPUs (one process per GPU).  The decomposed axis is the
+      slowest one (axis 0 for ndim==1, axis 1 for ndim==2).  nranks <= 1: single GPU. */
+   int32_t rank, nranks;
+   int64_t global_n;      /* global number of cells along the decomposed axis */
+   int64_t global_offset; /* global index of this slab's first cell along that axis */
+} hrweno_fv_desc;
+
+int hrweno_fv_create(hrweno_fv **out, const hrweno_fv_desc *desc);
+void hrweno_fv_destroy(hrweno_fv *fv);
+int64_t hrweno_fv_neq(const hrweno_fv *fv); /* local number of unknowns */
+/* one evaluation of the example `rhs` (example1:72-109 / example2:73-129): vdot = L(v), host memory */
+int hrweno_fv_rhs(hrweno_fv *fv, double t, const double *v, double *vdot);
+int hrweno_fv_rhs_dev(hrweno_fv *fv, double t, const double *v_dev, double *vdot_dev, void *stream);
+
+/* multi-GPU plumbing: each rank exports a 64-byte CUDA IPC handle of its halo mailbox and
+ * imports the handles of its left/right neighbours (NULL at a physical boundary). */
+#define HRWENO_IPC_HANDLE_BYTES 64
+int hrweno_fv_export_halo(hrweno_fv *fv, void *handle_out);
+int hrweno_fv_import_halo(hrweno_fv *fv, const void *left_handle, const void *right_handle);
+
+/* ---- TVD time integrators (src/hrweno_tvdode.f90) -------------------------- */
+
+/* integrand callback `fu(t, u(:), udot(:))` (tvdode.f90:50-57).  u and udot are DEVICE pointers
+ * (the state is device resident); the callback must enqueue its work on `stream`. */
+typedef void (*hrweno_rhs_fn)(void *ctx, double t, int64_t neq, const double *u_dev, double *udot_dev,
+                              void *stream);
+
+/* rktvd_init (tvdode.f90:69-95): neq >= 1, 1 <= order <= 3 */
+int hrweno_rktvd_create(hrweno_ode **out, hrweno_rhs_fn fu, void *ctx, int64_t neq, int order);
+/* mstvd_init (tvdode.f90:180-201) */
+int hrweno_mstvd_create(hrweno_ode **out, hrweno_rhs_fn fu, void *ctx, int64_t neq);
+/* same integrators with the rhs, flux and stage combination fused into one kernel per stage */
+int hrweno_rktvd_create_fused(hrweno_ode **out, hrweno_fv *fv, int order);
+int hrweno_mstvd_create_fused(hrweno_ode **out, hrweno_fv *fv);
+void hrweno_ode_destroy(hrweno_ode *ode);
+
+/* rktvd_integrate / mstvd_integrate (tvdode.f90:97-178, 203-271).  Semantics reproduced
+ * exactly: returns immediately when istate < 1 or is_done(t,tout,dt) (strict '>' test,
+ * tvdode.f90:282); t is advanced by repeated t = t + dt; itask = 1 integrate past tout,
+ * itask = 2 one single step (ignored by mstvd, which has no itask).  u is host memory. */
+int hrweno_ode_integrate(hrweno_ode *ode, double *u, double *t, double tout, double dt, int itask);
+/* device-resident u; asynchronous w.r.t. the host except for the scalar bookkeeping */
+int hrweno_ode_integrate_dev(hrweno_ode *ode, double *u_dev, double *t, double tout, double dt, int itask,
+                             void *stream);
+/* public fields of type(tvdode) (tvdode.f90:18-29) */
+int64_t hrweno_ode_fevals(const hrweno_ode *ode); /* keeps the reference's count, incl. mstvd's 12 for the start-up */
+int hrweno_ode_istate(const hrweno_ode *ode);
+int hrweno_ode_order(const hrweno_ode *ode);
+int64_t hrweno_ode_neq(const hrweno_ode *ode);
+/* number of kernels launched by this object so far (bench bookkeeping) */
+int64_t hrweno_ode_launches(const hrweno_ode *ode);
+
+/* ---- pinned host memory helpers (so host-buffer calls reach PCIe speed) ---- */
+int hrweno_host_alloc(void **out, int64_t bytes);
+void hrweno_host_free(void *p);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* HRWENO_B200_H */

@@ -1,0 +1,235 @@
+"""Independent NumPy restatement of the reference path (TEST INFRASTRUCTURE).
+
+Written separately from oracle/hrweno_oracle.c (vectorised over cells instead of a
+per-cell routine) so that the two can be compared bit for bit: every NumPy ufunc call
+is one correctly rounded IEEE fp64 operation per element, no FMA contraction, which is
+the arithmetic model of the reference's gfortran/x86-64 build.  Parity status is the
+one stated in hrweno_oracle.h: pinned to the reference's own test tolerances only.
+
+Citations are into /root/reference.
+"""
+from __future__ import annotations
+
+import math
+
+import numpy as np
+
+# src/hrweno_weno.f90:12-21 -- c[k][r+1] is the column c(:, r)
+D = {1: np.array([1.0]), 2: np.array([2.0 / 3, 1.0 / 3]), 3: np.array([0.3, 0.6, 0.1])}
+C = {
+    1: np.array([[1.0], [1.0]]),
+    2: np.array([[3.0 / 2, -1.0 / 2], [1.0 / 2, 1.0 / 2], [-1.0 / 2, 3.0 / 2]]),
+    3: np.array(
+        [
+            [11.0 / 6, -7.0 / 6, 1.0 / 3],
+            [1.0 / 3, 5.0 / 6, -1.0 / 6],
+            [-1.0 / 6, 5.0 / 6, 1.0 / 3],
+            [1.0 / 3, -7.0 / 6, 11.0 / 6],
+        ]
+    ),
+}
+
+
+def calc_cnu(xedges, k):
+    """src/hrweno_weno.f90:221-297; returns cnu[i-1, r+1, j]."""
+    xedges = np.asarray(xedges, dtype=np.float64)
+    nc = len(xedges) - 1
+    ng = k + 1
+    xext = {}
+    for i in range(nc + 1):
+        xext[i] = float(xedges[i])
+    dx = xext[1] - xext[0]
+    for i in range(-1, -ng - 1, -1):
+        xext[i] = xext[i + 1] - dx
+    dx = xext[nc] - xext[nc - 1]
+    for i in range(nc + 1, nc + ng + 1):
+        xext[i] = xext[i - 1] + dx
+    xl = lambda m: xext[m - 1]  # noqa: E731
+    xr = lambda m: xext[m]  # noqa: E731
+    cnu = np.zeros((nc, k + 1, k))
+    for i in range(1, nc + 1):
+        for r in range(-1, k):
+            for j in range(k):
+                sum2 = 0.0
+                for m in range(j + 1, k + 1):
+                    prod2 = 1.0
+                    for l in range(k + 1):
+                        if l == m:
+                            continue
+                        prod2 = prod2 * (xl(i - r + m) - xl(i - r + l))
+                    sum1 = 0.0
+                    for l in range(k + 1):
+                        if l == m:
+                            continue
+                        prod1 = 1.0
+                        for q in range(k + 1):
+                            if q == m or q == l:
+                                continue
+                            prod1 = prod1 * (xr(i) - xl(i - r + q))
+                        sum1 = sum1 + prod1
+                    sum2 = sum2 + sum1 / prod2
+                cnu[i - 1, r + 1, j] = sum2 * (xr(i - r + j) - xl(i - r + j))
+    return cnu
+
+
+def reconstruct(v, k=3, eps=1e-6, cnu=None):
+    """src/hrweno_weno.f90:129-219, vectorised over cells; returns (vl, vr)."""
+    v = np.asarray(v, dtype=np.float64)
+    nc = v.shape[-1]
+    g = k - 1
+    pad = [(0, 0)] * (v.ndim - 1) + [(g, g)]
+    vext = np.pad(v, pad, mode="edge")  # :171-173
+
+    def s(off):  # vext(i+off) for all cells i
+        return vext[..., g + off : g + off + nc]
+
+    d = D[k]
+    vrr, vlr = [], []
+    for r in range(k):
+        sr = np.zeros_like(v)
+        sl = np.zeros_like(v)
+        for j in range(k):
+            if cnu is None:
+                cr, cl = C[k][r + 1][j], C[k][r][j]
+            else:
+                cr, cl = cnu[:, r + 1, j], cnu[:, r, j]
+            sr = sr + cr * s(-r + j)  # :179
+            sl = sl + cl * s(-r + j)  # :180
+        vrr.append(sr)
+        vlr.append(sl)
+    if k == 1:
+        beta = [np.zeros_like(v)]
+    elif k == 2:
+        beta = [(s(1) - s(0)) ** 2, (s(0) - s(-1)) ** 2]
+    else:
+        beta = [
+            13.0 / 12 * ((s(0) - 2 * s(1)) + s(2)) ** 2 + 1.0 / 4 * ((3 * s(0) - 4 * s(1)) + s(2)) ** 2,
+            13.0 / 12 * ((s(-1) - 2 * s(0)) + s(1)) ** 2 + 1.0 / 4 * (s(-1) - s(1)) ** 2,
+            13.0 / 12 * ((s(-2) - 2 * s(-1)) + s(0)) ** 2 + 1.0 / 4 * ((s(-2) - 4 * s(-1)) + 3 * s(0)) ** 2,
+        ]
+    den = [(eps + b) ** 2 for b in beta]
+    alfa = [d[r] / den[r] for r in range(k)]
+    alfat = [d[k - 1 - r] / den[r] for r in range(k)]
+    sa = np.zeros_like(v)
+    sat = np.zeros_like(v)
+    for r in range(k):
+        sa = sa + alfa[r]
+        sat = sat + alfat[r]
+    vr = np.zeros_like(v)
+    vl = np.zeros_like(v)
+    for r in range(k):
+        vr = vr + (alfa[r] / sa) * vrr[r]
+        vl = vl + (alfat[r] / sat) * vlr[r]
+    return vl, vr
+
+
+def flux_model(model, coef, v):
+    if model == "burgers":
+        return (v * v) / 2  # example1:120
+    return coef * v  # example2:140,153
+
+
+def face_flux(scheme, model, coef, alpha, vm, vp):
+    fm = flux_model(model, coef, vm)
+    fp = flux_model(model, coef, vp)
+    if scheme == "lax_friedrichs":
+        return (fm + fp - alpha * (vp - vm)) / 2  # fluxes.f90:43
+    return np.where(vm <= vp, np.minimum(fm, fp), np.maximum(fm, fp))  # fluxes.f90:70-74
+
+
+def grid_linear(xmin, xmax, n):
+    """src/hrweno_grids.f90:76-79, 246-247 -> (edges, center, width)."""
+    rx = (xmax - xmin) / n
+    edges = xmin + rx * np.arange(n + 1, dtype=np.float64)
+    return edges, (edges[:-1] + edges[1:]) / 2, edges[1:] - edges[:-1]
+
+
+def _faces(vl, vr, scheme, model, coef, alpha, bc):
+    """faces along the last axis: returns f[..., 0:nc+1]."""
+    inner = face_flux(scheme, model, coef, alpha, vr[..., :-1], vl[..., 1:])
+    if bc == "copy":
+        lo, hi = inner[..., :1], inner[..., -1:]
+    else:
+        lo = np.zeros_like(inner[..., :1])
+        hi = lo
+    return np.concatenate([lo, inner, hi], axis=-1)
+
+
+def rhs1d(v, width, k=3, eps=1e-6, scheme="godunov", model="burgers", coef=1.0, alpha=1.0, bc="copy"):
+    """example/example1_burgers_1d_fv.f90:72-109 (rows of independent problems allowed)."""
+    vl, vr = reconstruct(v, k, eps)
+    f = _faces(vl, vr, scheme, model, coef, alpha, bc)
+    return -(f[..., 1:] - f[..., :-1]) / width
+
+
+def rhs2d(v, w1, w2, k=3, eps=1e-6, scheme="godunov", model="linear", coef=(1.0, 1.0), alpha=1.0, bc="zero"):
+    """example/example2_pbe_2d_fv.f90:73-129; v[j, i] with i (x1) contiguous."""
+    vl1, vr1 = reconstruct(v, k, eps)
+    f1 = _faces(vl1, vr1, scheme, model, coef[0], alpha, bc)
+    vt = np.ascontiguousarray(v.T)
+    vl2, vr2 = reconstruct(vt, k, eps)
+    f2 = _faces(vl2, vr2, scheme, model, coef[1], alpha, bc)
+    t1 = -(f1[:, 1:] - f1[:, :-1]) / w1[None, :]
+    t2 = ((f2[:, 1:] - f2[:, :-1]) / w2[None, :]).T
+    return t1 - t2
+
+
+def is_done(t, tout, dt):
+    return (t - tout) * math.copysign(1.0, dt) > 0.0  # tvdode.f90:282
+
+
+class RK:
+    """src/hrweno_tvdode.f90:69-178."""
+
+    def __init__(self, fu, order):
+        self.fu, self.order, self.fevals, self.istate = fu, order, 0, 1
+
+    def integrate(self, u, t, tout, dt, itask=1):
+        if self.istate < 1 or is_done(t, tout, dt):
+            return u, t
+        fu = self.fu
+        while True:
+            if self.order == 1:
+                u = u + dt * fu(t, u)
+            elif self.order == 2:
+                ui = u + dt * fu(t, u)
+                u = (u + ui + dt * fu(t + dt, ui)) / 2
+            else:
+                ui = u + dt * fu(t, u)
+                ui = (3 * u + ui + dt * fu(t + dt, ui)) / 4
+                u = (u + 2 * ui + (2 * dt) * fu(t + dt / 2, ui)) / 3
+            t = t + dt
+            self.fevals += self.order
+            if is_done(t, tout, dt) or itask == 2:
+                break
+        self.istate = 2
+        return u, t
+
+
+class MS:
+    """src/hrweno_tvdode.f90:180-271."""
+
+    def __init__(self, fu):
+        self.fu, self.order, self.fevals, self.istate = fu, 3, 0, 1
+        self.uold, self.udotold = [None] * 4, [None] * 4
+
+    def integrate(self, u, t, tout, dt):
+        if self.istate < 1 or is_done(t, tout, dt):
+            return u, t
+        if self.istate == 1:
+            start = RK(self.fu, 3)
+            for c in (3, 2, 1, 0):
+                self.uold[c] = u
+                self.udotold[c] = self.fu(t, u)
+                u, t = start.integrate(u, t, t + 2 * dt, dt, itask=2)
+            self.fevals = start.fevals
+            self.istate = 2
+        while not is_done(t, tout, dt):
+            udot = self.fu(t, u)
+            ui = (25 * u + (50 * dt) * udot + 7 * self.uold[3] + (10 * dt) * self.udotold[3]) / 32
+            t = t + dt
+            self.fevals += 1
+            self.udotold = [udot] + self.udotold[:3]
+            self.uold = [u] + self.uold[:3]
+            u = ui
+        return u, t
