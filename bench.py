@@ -1,0 +1,299 @@
+#!/usr/bin/env python
+"""bench.py -- WENO5 + Godunov + RK3-TVD cell-updates/s on B200 (BASELINE.json metric).
+
+Workload (configs[2] of BASELINE.json, SURVEY 8d "cfg3"): 1D inviscid Burgers, k=3, eps=1e-6,
+rktvd order 3, 2^28 cells per GPU on a linear grid over [-5,5], initial data = example1's clipped
+ramp + 1e-3*N(0,1) (default_rng(12345)), dt = 0.1*dx.  One "step" = one RK3 time step = 3 fused
+stage kernels over all cells; one cell-update = one cell-stage.
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl reference] [--mode strict|fast]
+
+N > 1 is launched by torchrun (one rank per GPU); weak scaling: 2^28 cells per GPU, slab
+decomposition along x with k halo cells per stage.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+import __graft_entry__ as graft  # noqa: E402
+
+RK3_BYTES_PER_CELL_STEP = 64.0  # 16 + 24 + 24
+XMIN, XMAX = -5.0, 5.0
+
+
+def make_ic(n, offset=0, n_global=None, seed=12345):
+    """example1's ramp (example1:128-131) at the cell centres of grid1%linear plus a seeded perturbation"""
+    n_global = n_global or n
+    rx = (XMAX - XMIN) / n_global
+    i = np.arange(offset, offset + n + 1, dtype=np.float64)
+    edges = XMIN + rx * i
+    x = (edges[:-1] + edges[1:]) / 2
+    u = np.clip(1.0 + (-1.5 / 6.0) * (x + 4.0), -0.5, 1.0)
+    rng = np.random.default_rng(seed + offset // max(n, 1))
+    u += 1e-3 * rng.standard_normal(n)
+    return u
+
+
+class ClockSampler(threading.Thread):
+    """nvidia-smi clocks / throttle reasons during the timed region (B200_PROFILING.md recipe)"""
+
+    Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index):
+        super().__init__(daemon=True)
+        self.index, self.rows, self._stop_evt = index, [], threading.Event()
+
+    def run(self):
+        while not self._stop_evt.is_set():
+            try:
+                out = subprocess.run(
+                    ["nvidia-smi", f"--id={self.index}", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits"],
+                    capture_output=True, text=True, timeout=5).stdout.strip()
+                if out:
+                    self.rows.append([c.strip() for c in out.split(",")])
+            except Exception:
+                pass
+            self._stop_evt.wait(0.2)
+
+    def stop(self):
+        self._stop_evt.set()
+        self.join(timeout=6)
+        sm = sorted(float(r[0]) for r in self.rows if r and r[0].replace(".", "").isdigit())
+        reasons = set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for r in self.rows:
+            for nm, val in zip(names, r[3:7]):
+                if val.lower().startswith("active"):
+                    reasons.add(nm)
+        return {
+            "sm_mhz": sm[len(sm) // 2] if sm else None,
+            "sm_max_mhz": float(self.rows[0][1]) if self.rows else None,
+            "power_w_max": max((float(r[2]) for r in self.rows if r[2].replace(".", "").isdigit()), default=None),
+            "reasons": sorted(reasons),
+            "samples": len(self.rows),
+        }
+
+
+def peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        return json.load(open(p))["hbm_gbs"], "measured (MEASURED_PEAKS.json)"
+    return 6650.0, "fallback (B200_PROFILING.md)"
+
+
+def run_reference(args, rank, world):
+    """--impl reference: the CPU restatement of the reference path (no Fortran compiler exists in this image,
+    so oracle/_ref cannot be built; kind = "port") on all host threads, bounded sample per step."""
+    if rank != 0:
+        return
+    pkg = graft.load_package()
+    ref = graft.load_oracle()
+    cores = ref.max_threads()
+    ref.set_threads(cores)
+    n = 1 << 24
+    u = make_ic(n)
+    dt = 0.1 * (XMAX - XMIN) / n
+    fv = ref.FV(pkg.fv.make_desc(n, k=3, eps=1e-6, linear=(XMIN, XMAX)))
+    ode = ref.rktvd(fv, 3)
+    t = 0.0
+    for _ in range(args.warmup):
+        t = ode.integrate(u, t, 1e9, dt, itask=2)
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        t = ode.integrate(u, t, 1e9, dt, itask=2)
+    el = time.perf_counter() - t0
+    value = n * 3 * args.steps / el
+    sample = f"2^24 cells x {args.steps} RK3 steps per run (1/16 of the 2^28-cell workload), OpenMP over cells"
+    print(json.dumps({
+        "impl": "reference", "metric": "WENO5+RK3 cell-updates/s", "value": value, "unit": "cell-updates/s",
+        "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * el / args.steps,
+        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+        "config": {"workload": "cfg3: 1D Burgers WENO5+Godunov+RK3, linear grid [-5,5], ramp+1e-3*N(0,1) IC, dt=0.1dx",
+                   "cells_per_step": n, "note": "C restatement of the reference (oracle), not gfortran"},
+        "cpu_baseline": {"value": value, "unit": "cell-updates/s", "cores": cores, "kind": "port", "sample": sample},
+        "e2e": {"value": value, "unit": "cell-updates/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+    }))
+
+
+def cpu_baseline_leg(pkg):
+    """the oracle on ONE host core (the shipped reference is serial), bounded sample"""
+    ref = graft.load_oracle()
+    ref.set_threads(1)
+    n, steps = 1 << 22, 10
+    u = make_ic(n)
+    dt = 0.1 * (XMAX - XMIN) / n
+    ode = ref.rktvd(ref.FV(pkg.fv.make_desc(n, k=3, eps=1e-6, linear=(XMIN, XMAX))), 3)
+    t = ode.integrate(u, 0.0, 1e9, dt, itask=2)
+    t0 = time.perf_counter()
+    for _ in range(steps):
+        t = ode.integrate(u, t, 1e9, dt, itask=2)
+    el = time.perf_counter() - t0
+    return {"value": n * 3 * steps / el, "unit": "cell-updates/s", "cores": 1, "kind": "port",
+            "sample": f"2^22 cells x {steps} RK3 steps, 1 thread (C restatement of the reference, not gfortran)"}
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="b200")
+    ap.add_argument("--mode", default=os.environ.get("HRWENO_BENCH_MODE", "strict"), choices=["strict", "fast"])
+    ap.add_argument("--log2-cells", type=int, default=28)
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+
+    if args.impl == "reference":
+        run_reference(args, rank, world)
+        return
+
+    import torch
+    import torch.distributed as dist
+
+    pkg = graft.load_package()
+    torch.cuda.set_device(local_rank)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+    lib = pkg.lib()
+    assert lib.hrweno_device_count() >= 1, "no CUDA device: there is no CPU fallback"
+
+    n = 1 << args.log2_cells  # cells per GPU (weak scaling)
+    n_global = n * world
+    dt = 0.1 * (XMAX - XMIN) / n_global
+    mode = pkg._abi.MODE_STRICT if args.mode == "strict" else pkg._abi.MODE_FAST
+    desc = pkg.fv.make_desc(n, k=3, eps=1e-6, linear=(XMIN, XMAX), mode=mode, rank=rank, nranks=world,
+                            global_n=n_global, global_offset=rank * n)
+    fv = pkg.fv.FV(desc)
+    if world > 1:
+        handles = [None] * world
+        dist.all_gather_object(handles, fv.export_halo())
+        fv.import_halo(handles[rank - 1] if rank > 0 else None, handles[rank + 1] if rank < world - 1 else None)
+    ode = pkg.hrweno_tvdode.rktvd(fv, n, 3)
+
+    u_host = torch.from_numpy(make_ic(n, rank * n, n_global)).pin_memory()
+    u_dev = u_host.cuda(non_blocking=False)
+    stream = torch.cuda.current_stream().cuda_stream
+    t = 0.0
+    BIG = 1e30
+
+    def run_steps(k):
+        nonlocal t
+        # K steps in ONE integrate call: tout chosen so that exactly k steps are taken (strict is_done test)
+        tt = t
+        for _ in range(k - 1):
+            tt = tt + dt
+        t = ode.integrate_dev(u_dev.data_ptr(), t, tt, dt, 1, stream)
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    run_steps(args.warmup)
+    barrier()
+
+    # ---- value: device-resident, K steps in one C-ABI call ------------------------------------------
+    sampler = ClockSampler(local_rank)
+    sampler.start()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    launches0 = ode.launches
+    barrier()
+    e0.record()
+    run_steps(args.steps)
+    e1.record()
+    barrier()
+    ms = e0.elapsed_time(e1)
+    launches = ode.launches - launches0
+    # stage-kernel-only time: T(K steps) - T(1 step) removes the pack/unpack copies of the call
+    e2, e3 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e2.record()
+    run_steps(1)
+    e3.record()
+    torch.cuda.synchronize()
+    ms1 = e2.elapsed_time(e3)
+    clocks = sampler.stop()
+    if world > 1:
+        tmax = torch.tensor([ms, ms1], device="cuda", dtype=torch.float64)
+        dist.all_reduce(tmax, op=dist.ReduceOp.MAX)
+        ms, ms1 = float(tmax[0]), float(tmax[1])
+
+    # ---- e2e: host (pinned) u through the host-pointer C-ABI call, copies inside the timed region -----
+    t_e2e = 0.0
+    u_np = u_host.numpy()
+
+    def e2e_call(k):
+        nonlocal t_e2e
+        tt = t_e2e
+        for _ in range(k - 1):
+            tt = tt + dt
+        t_e2e = ode.integrate(u_np, t_e2e, tt, dt)
+
+    e2e_call(1)
+    barrier()
+    w0 = time.perf_counter()
+    e2e_call(args.steps)
+    barrier()
+    e2e_s = time.perf_counter() - w0
+    if world > 1:
+        tm = torch.tensor([e2e_s], device="cuda", dtype=torch.float64)
+        dist.all_reduce(tm, op=dist.ReduceOp.MAX)
+        e2e_s = float(tm[0])
+
+    if rank != 0:
+        if world > 1:
+            dist.destroy_process_group()
+        return
+
+    K = args.steps
+    value = n_global * 3 * K / (ms * 1e-3)
+    stage_ms = (ms - ms1) / (3 * (K - 1)) if K > 1 else ms / 3
+    peak, peak_src = peaks()
+    achieved = n * (RK3_BYTES_PER_CELL_STEP / 3) / (stage_ms * 1e-3) / 1e9
+    line = {
+        "metric": "WENO5+RK3 cell-updates/s", "value": value, "unit": "cell-updates/s", "n_gpus": world, "steps": K,
+        "warmup": args.warmup, "ms_per_step": ms / K, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+        "dtype": "f64", "data": "synthetic",
+        "config": {
+            "workload": "cfg3: 1D Burgers WENO5(k=3,eps=1e-6)+Godunov+rktvd(3), 2^%d cells per GPU, linear grid [-5,5], "
+                        "ramp+1e-3*N(0,1) IC (rng 12345), dt=0.1dx" % args.log2_cells,
+            "cells_per_gpu": n, "mode": args.mode, "parallelism": "slab x%d (halo k=3 per stage)" % world if world > 1 else "1 GPU",
+            "l2": "state vectors are 2 GiB each, far larger than the 126 MB L2 (no flush needed)",
+            "unit_note": "one cell-update = one cell-stage (rhs + stage combination); cell-steps/s = value/3",
+        },
+        "cell_steps_per_s": value / 3,
+        "gpu_launches": int(launches),
+        "clocks": clocks,
+        "roofline": {
+            "bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": None,
+            "kernel": "fv1d_stage_kernel<K=3> (average of the 3 RK3 stage instantiations)",
+            "algorithmic_bytes_per_launch": n * RK3_BYTES_PER_CELL_STEP / 3, "avg_launch_ms": stage_ms, "peak_source": peak_src,
+        },
+        "e2e": {
+            "value": n_global * 3 * K / e2e_s, "unit": "cell-updates/s",
+            "h2d_bytes_per_step": n * 8 / K, "d2h_bytes_per_step": n * 8 / K,
+            "note": "one hrweno_ode_integrate call with a pinned host u advancing K steps: H2D u, 3K fused stages, D2H u",
+        },
+    }
+    if not args.no_cpu_baseline:
+        line["cpu_baseline"] = cpu_baseline_leg(pkg)
+    print(json.dumps(line))
+    if world > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

@@ -1,0 +1,100 @@
+// internal.hpp -- C++ objects behind the opaque C handles.
+#pragma once
+
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include <mutex>
+#include <string>
+#include <vector>
+
+#include "common.cuh"
+
+namespace hrw {
+
+// stage combinations fused behind the right-hand side L(v)  (tvdode.f90:141,149-167,257)
+enum Combine {
+   C_RHS = 0,       // out = L(v)                                          example rhs
+   C_EULER = 1,     // out = v + dt*L(v)                                   RK1, first stage of RK2/RK3
+   C_RK2_FINAL = 2, // out = ((a + v) + dt*L(v))/2          a = u^n        tvdode.f90:152
+   C_RK3_S2 = 3,    // out = ((3a + v) + dt*L(v))/4         a = u^n        tvdode.f90:165
+   C_RK3_S3 = 4,    // out = ((a + 2v) + (2dt)*L(v))/3      a = u^n        tvdode.f90:167
+   C_MS = 5         // out = ((((25v) + (50dt)L(v)) + 7a) + (10dt)b)/32, out2 = L(v);  a = u^{n-4}, b = L^{n-4}   :257
+};
+
+struct StageArgs {
+   const double *vin;  // stage input  (padded layout, pointer at cell 0 of row 0)
+   const double *a;    // pointwise operand (padded layout) or nullptr
+   const double *b;    // second pointwise operand or nullptr
+   double *out;        // result, pointer at cell 0 of row 0
+   double *out2;       // C_MS: L(v) (padded layout)
+   int64_t ld_out;     // row pitch of out (padded pitch, or n for a caller's dense array)
+   int out_dense;      // 1: out is a caller's dense array: no ghost writes, no alignment assumptions
+   double c0, c1;      // dt-like coefficients: (dt) | (2dt) | (50dt, 10dt)
+};
+
+struct Fv {
+   hrweno_fv_desc d{};
+   int64_t n0 = 0, n1 = 1;      // cells along x1 (contiguous) and x2
+   int64_t rows = 1;             // 1D: independent rows
+   int64_t neq = 0;
+   int64_t pitch = 0;            // padded row pitch (doubles)
+   int64_t nrows_alloc = 0;      // rows (1D) or n1 + 2*PAD2 (2D)
+   double *d_width[2] = {nullptr, nullptr};
+   double rx = 0.0;              // GRID_LINEAR: (xmax-xmin)/global_n
+   // scratch for hrweno_fv_rhs[_dev]
+   double *d_scratch_in = nullptr, *d_scratch_out = nullptr;
+   cudaStream_t stream = nullptr;
+   std::mutex mtx;
+   int64_t launches = 0;
+   // geometry helpers
+   size_t state_doubles() const; // doubles of one padded state vector
+   double *cell0(double *base) const; // pointer at cell 0 of row 0 inside a padded allocation
+   const double *cell0(const double *base) const;
+   int alloc_state(double **out) const;
+   ~Fv();
+};
+
+int fv_create(Fv **out, const hrweno_fv_desc *desc);
+// dense caller array <-> padded state (fills ghost cells of physical boundaries)
+int fv_pack(Fv *fv, const double *dense_dev, double *padded_cell0, cudaStream_t st);
+int fv_unpack(Fv *fv, const double *padded_cell0, double *dense_dev, cudaStream_t st);
+// one fused stage: reconstruct + face fluxes + divergence + combination
+int fv_stage(Fv *fv, int combine, const StageArgs &args, cudaStream_t st);
+
+struct Weno {
+   int64_t ncells = 0;
+   int k = 3;
+   double eps = 1e-6;
+   bool uniform = true;
+   std::vector<double> cnu_host;
+   double *d_cnu = nullptr;
+   // cached device buffers for the host-pointer entry points
+   double *d_buf = nullptr;
+   size_t buf_doubles = 0;
+   std::mutex mtx;
+   ~Weno();
+};
+
+int weno_reconstruct_launch(const Weno *w, int64_t rows, const double *v, int64_t ldv, int64_t incv, double *vl,
+                            double *vr, int64_t ldo, cudaStream_t st);
+
+struct Ode {
+   bool is_ms = false;
+   bool fused = false;
+   Fv *fv = nullptr;
+   hrweno_rhs_fn fu = nullptr;
+   void *ctx = nullptr;
+   int64_t neq = 0;
+   int order = 3;
+   int64_t fevals = 0;
+   int istate = 0;
+   int64_t launches = 0;
+   // device state (padded layout for the fused path, dense for the callback path)
+   std::vector<double *> bufs;
+   int ring = 0; // mstvd: index of the slot holding u^n inside the u ring
+   cudaStream_t stream = nullptr;
+   ~Ode();
+};
+
+} // namespace hrw

@@ -1,0 +1,320 @@
+// ode.cu -- rktvd / mstvd drivers (src/hrweno_tvdode.f90).
+//
+// The time loop, `t = t + dt` accumulation, the strict is_done test and the fevals/istate
+// bookkeeping run on the host in fp64 exactly as the reference does (tvdode.f90:126-176, 228-268,
+// 282); every stage is one fused device kernel (fused path) or one user rhs call plus one combine
+// kernel (callback path).  mstvd keeps its history in rings addressed by the step number instead of
+// the reference's two eoshift copies per step (tvdode.f90:262-263).
+#include <cmath>
+#include <new>
+
+#include "internal.hpp"
+
+namespace hrw {
+
+static inline bool is_done(double t, double tout, double dt) { return (t - tout) * std::copysign(1.0, dt) > 0.0; }
+
+Ode::~Ode() {
+   for (double *p : bufs) cudaFree(p);
+   if (stream) cudaStreamDestroy(stream);
+}
+
+// ------------------------------------------------------------------------------------------------
+// K6: stage combinations on dense vectors for the callback path (tvdode.f90:141,149-167,257)
+// ------------------------------------------------------------------------------------------------
+template <int COMBINE>
+__global__ void combine_kernel(int64_t n, const double *__restrict__ v, const double *__restrict__ L,
+                               const double *__restrict__ a, const double *__restrict__ b, double *__restrict__ out,
+                               double c0, double c1) {
+   for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
+      const double l = L[i], x = v[i];
+      double o;
+      if (COMBINE == C_EULER)
+         o = __dadd_rn(x, __dmul_rn(c0, l));
+      else if (COMBINE == C_RK2_FINAL)
+         o = __dmul_rn(__dadd_rn(__dadd_rn(a[i], x), __dmul_rn(c0, l)), 0.5);
+      else if (COMBINE == C_RK3_S2)
+         o = __dmul_rn(__dadd_rn(__dadd_rn(__dmul_rn(3.0, a[i]), x), __dmul_rn(c0, l)), 0.25);
+      else if (COMBINE == C_RK3_S3)
+         o = __ddiv_rn(__dadd_rn(__fma_rn(2.0, x, a[i]), __dmul_rn(c0, l)), 3.0);
+      else
+         o = __dmul_rn(__dadd_rn(__dadd_rn(__dadd_rn(__dmul_rn(25.0, x), __dmul_rn(c0, l)), __dmul_rn(7.0, a[i])),
+                                 __dmul_rn(c1, b[i])),
+                       0.03125);
+      out[i] = o;
+   }
+}
+
+static int launch_combine(int combine, int64_t n, const double *v, const double *L, const double *a, const double *b,
+                          double *out, double c0, double c1, cudaStream_t st) {
+   int64_t blocks = (n + 255) / 256;
+   if (blocks > 148 * 16) blocks = 148 * 16;
+   const unsigned g = (unsigned)blocks;
+   switch (combine) {
+   case C_EULER: combine_kernel<C_EULER><<<g, 256, 0, st>>>(n, v, L, a, b, out, c0, c1); break;
+   case C_RK2_FINAL: combine_kernel<C_RK2_FINAL><<<g, 256, 0, st>>>(n, v, L, a, b, out, c0, c1); break;
+   case C_RK3_S2: combine_kernel<C_RK3_S2><<<g, 256, 0, st>>>(n, v, L, a, b, out, c0, c1); break;
+   case C_RK3_S3: combine_kernel<C_RK3_S3><<<g, 256, 0, st>>>(n, v, L, a, b, out, c0, c1); break;
+   default: combine_kernel<C_MS><<<g, 256, 0, st>>>(n, v, L, a, b, out, c0, c1); break;
+   }
+   HRW_CUDA(cudaGetLastError());
+   return HRWENO_OK;
+}
+
+// ------------------------------------------------------------------------------------------------
+// creation
+// ------------------------------------------------------------------------------------------------
+static int ode_alloc(Ode *o) {
+   size_t n_bufs, doubles;
+   if (o->fused) {
+      n_bufs = o->is_ms ? 5 + 4 + 2 : 3;
+      doubles = o->fv->state_doubles();
+   } else {
+      // callback path: dense vectors.  RK: u, ui, udot.  MS: u ring (5), udot ring (4), ui, udot.
+      n_bufs = o->is_ms ? 5 + 4 + 2 : 3;
+      doubles = (size_t)o->neq;
+   }
+   for (size_t i = 0; i < n_bufs; ++i) {
+      double *p = nullptr;
+      HRW_CUDA(cudaMalloc(&p, doubles * sizeof(double)));
+      o->bufs.push_back(p);
+      HRW_CUDA(cudaMemset(p, 0, doubles * sizeof(double)));
+   }
+   // dense staging vector for the host-pointer entry point
+   double *p = nullptr;
+   HRW_CUDA(cudaMalloc(&p, (size_t)o->neq * sizeof(double)));
+   o->bufs.push_back(p);
+   HRW_CUDA(cudaStreamCreateWithFlags(&o->stream, cudaStreamNonBlocking));
+   return HRWENO_OK;
+}
+
+int ode_create(Ode **out, bool is_ms, Fv *fv, hrweno_rhs_fn fu, void *ctx, int64_t neq, int order) {
+   if (!out) return fail(HRWENO_EINVAL, "ode create: null argument");
+   if (!fv && !fu) return fail(HRWENO_EINVAL, "ode create: no integrand");
+   if (fv) neq = fv->neq;
+   if (!(neq > 0)) return fail(HRWENO_EINVAL, "Invalid input 'neq'. Valid range: neq >= 1."); // tvdode.f90:83,192
+   if (!(order >= 1 && order <= 3))
+      return fail(HRWENO_EINVAL, "Invalid input 'order' in 'rktvd'. Valid range: 1 <= k <= 3."); // :89
+   int ndev = 0;
+   if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev < 1)
+      return fail(HRWENO_ECUDA, "no CUDA device (this library has no CPU fallback)");
+   Ode *o = new (std::nothrow) Ode();
+   if (!o) return fail(HRWENO_ENOMEM, "out of host memory");
+   o->is_ms = is_ms;
+   o->fused = fv != nullptr;
+   o->fv = fv;
+   o->fu = fu;
+   o->ctx = ctx;
+   o->neq = neq;
+   o->order = is_ms ? 3 : order; // tvdode.f90:195
+   const int st = ode_alloc(o);
+   if (st != HRWENO_OK) {
+      delete o;
+      return st;
+   }
+   o->istate = 1; // tvdode.f90:93,199
+   *out = o;
+   return HRWENO_OK;
+}
+
+// ------------------------------------------------------------------------------------------------
+// one RK step  src -> dst  (dst may equal src); t1, t2 are temporaries.  Fused: padded states.
+// ------------------------------------------------------------------------------------------------
+static int rk_step_fused(Ode *o, int order, double *src, double *dst, double *t1, double *t2, double dt, cudaStream_t st) {
+   Fv *fv = o->fv;
+   StageArgs a{};
+   a.ld_out = fv->pitch;
+   a.out_dense = 0;
+   auto c0 = [&](double *p) { return fv->cell0(p); };
+   if (order == 1) { // u = u + dt*udot  (needs dst != src: the stencil reads src)
+      a.vin = c0(src);
+      a.out = c0(dst);
+      a.c0 = dt;
+      HRW_TRY(fv_stage(fv, C_EULER, a, st));
+      o->launches += 1;
+      return HRWENO_OK;
+   }
+   a.vin = c0(src);
+   a.out = c0(t1);
+   a.c0 = dt;
+   HRW_TRY(fv_stage(fv, C_EULER, a, st)); // ui = u + dt*udot
+   if (order == 2) {
+      a.vin = c0(t1);
+      a.a = c0(src);
+      a.out = c0(dst);
+      HRW_TRY(fv_stage(fv, C_RK2_FINAL, a, st)); // u = (u + ui + dt*udot)/2
+      o->launches += 2;
+      return HRWENO_OK;
+   }
+   a.vin = c0(t1);
+   a.a = c0(src);
+   a.out = c0(t2);
+   HRW_TRY(fv_stage(fv, C_RK3_S2, a, st)); // ui = (3*u + ui + dt*udot)/4
+   a.vin = c0(t2);
+   a.a = c0(src);
+   a.out = c0(dst);
+   a.c0 = 2 * dt;
+   HRW_TRY(fv_stage(fv, C_RK3_S3, a, st)); // u = (u + 2*ui + 2*dt*udot)/3
+   o->launches += 3;
+   return HRWENO_OK;
+}
+
+// callback path: dense vectors; ui and udot are work vectors (tvdode.f90:30-31)
+static int rk_step_cb(Ode *o, int order, double t, double *u, double *ui, double *udot, double dt, cudaStream_t st) {
+   const int64_t n = o->neq;
+   o->fu(o->ctx, t, n, u, udot, st);
+   if (order == 1) {
+      HRW_TRY(launch_combine(C_EULER, n, u, udot, nullptr, nullptr, u, dt, 0, st));
+      o->launches += 1;
+      return HRWENO_OK;
+   }
+   HRW_TRY(launch_combine(C_EULER, n, u, udot, nullptr, nullptr, ui, dt, 0, st));
+   o->fu(o->ctx, t + dt, n, ui, udot, st);
+   if (order == 2) {
+      HRW_TRY(launch_combine(C_RK2_FINAL, n, ui, udot, u, nullptr, u, dt, 0, st));
+      o->launches += 2;
+      return HRWENO_OK;
+   }
+   HRW_TRY(launch_combine(C_RK3_S2, n, ui, udot, u, nullptr, ui, dt, 0, st));
+   o->fu(o->ctx, t + dt / 2, n, ui, udot, st);
+   HRW_TRY(launch_combine(C_RK3_S3, n, ui, udot, u, nullptr, u, 2 * dt, 0, st));
+   o->launches += 3;
+   return HRWENO_OK;
+}
+
+// ------------------------------------------------------------------------------------------------
+// rktvd_integrate (tvdode.f90:97-178)
+// ------------------------------------------------------------------------------------------------
+static int rk_integrate(Ode *o, double *u_dev, double *t, double tout, double dt, int itask, cudaStream_t st) {
+   if (o->istate < 1) return HRWENO_OK;          // :126
+   if (is_done(*t, tout, dt)) return HRWENO_OK;   // :127
+   if (o->fused) {
+      Fv *fv = o->fv;
+      double *U = o->bufs[0], *T1 = o->bufs[1], *T2 = o->bufs[2];
+      HRW_TRY(fv_pack(fv, u_dev, fv->cell0(U), st));
+      o->launches++;
+      for (;;) {
+         if (o->order == 1) {
+            HRW_TRY(rk_step_fused(o, 1, U, T1, nullptr, nullptr, dt, st));
+            std::swap(U, T1);
+         } else {
+            HRW_TRY(rk_step_fused(o, o->order, U, U, T1, T2, dt, st));
+         }
+         *t = *t + dt;
+         o->fevals += o->order;
+         if (is_done(*t, tout, dt) || itask == 2) break;
+      }
+      HRW_TRY(fv_unpack(fv, fv->cell0(U), u_dev, st));
+      o->launches++;
+      o->bufs[0] = U;
+      o->bufs[1] = T1;
+   } else {
+      for (;;) {
+         HRW_TRY(rk_step_cb(o, o->order, *t, u_dev, o->bufs[1], o->bufs[2], dt, st));
+         *t = *t + dt;
+         o->fevals += o->order;
+         if (is_done(*t, tout, dt) || itask == 2) break;
+      }
+   }
+   if (o->istate == 1) o->istate = 2; // :176
+   return HRWENO_OK;
+}
+
+// ------------------------------------------------------------------------------------------------
+// mstvd_integrate (tvdode.f90:203-271).  Step number n = o->ring: u^n lives in uring[n % 5],
+// L(u^n) in lring[n % 4]; u^{n-4} and L^{n-4} are read and overwritten in place by u^{n+1}, L^n.
+// ------------------------------------------------------------------------------------------------
+static int ms_integrate(Ode *o, double *u_dev, double *t, double tout, double dt, cudaStream_t st) {
+   if (o->istate < 1) return HRWENO_OK;        // :228
+   if (is_done(*t, tout, dt)) return HRWENO_OK; // :229
+   double **uring = &o->bufs[0], **lring = &o->bufs[5];
+   double *T1 = o->bufs[9], *T2 = o->bufs[10];
+   Fv *fv = o->fv;
+   const int64_t n = o->neq;
+   int &step = o->ring;
+   // the caller's u is the current state (it may have been edited between calls, like the reference's inout u)
+   if (o->fused) {
+      HRW_TRY(fv_pack(fv, u_dev, fv->cell0(uring[step % 5]), st));
+      o->launches++;
+   } else {
+      HRW_CUDA(cudaMemcpyAsync(uring[step % 5], u_dev, (size_t)n * sizeof(double), cudaMemcpyDeviceToDevice, st));
+   }
+   if (o->istate == 1) { // :236-249: four RK3 single steps; uold(:,i) = u, udotold(:,i) = fu(t,u)
+      for (int i = 0; i < 4; ++i) {
+         double *U = uring[step % 5], *Un = uring[(step + 1) % 5];
+         if (o->fused) {
+            StageArgs a{};
+            a.vin = fv->cell0(U);
+            a.out = fv->cell0(lring[step % 4]);
+            a.ld_out = fv->pitch;
+            HRW_TRY(fv_stage(fv, C_RHS, a, st));
+            o->launches++;
+            HRW_TRY(rk_step_fused(o, 3, U, Un, T1, T2, dt, st));
+         } else {
+            o->fu(o->ctx, *t, n, U, lring[step % 4], st);
+            HRW_CUDA(cudaMemcpyAsync(Un, U, (size_t)n * sizeof(double), cudaMemcpyDeviceToDevice, st));
+            HRW_TRY(rk_step_cb(o, 3, *t, Un, T1, T2, dt, st));
+         }
+         *t = *t + dt;
+         step++;
+      }
+      o->fevals = 12; // :246: fevals = ode_start%fevals (the four extra fu calls are not counted)
+      o->istate = 2;
+   }
+   const double c50 = 50 * dt, c10 = 10 * dt;
+   for (;;) { // :252-268
+      if (is_done(*t, tout, dt)) break;
+      double *U = uring[step % 5], *Uo4 = uring[(step + 1) % 5], *Lo4 = lring[step % 4];
+      if (o->fused) {
+         StageArgs a{};
+         a.vin = fv->cell0(U);
+         a.a = fv->cell0(Uo4);
+         a.b = fv->cell0(Lo4);
+         a.out = fv->cell0(Uo4);
+         a.out2 = fv->cell0(Lo4);
+         a.ld_out = fv->pitch;
+         a.c0 = c50;
+         a.c1 = c10;
+         HRW_TRY(fv_stage(fv, C_MS, a, st));
+         o->launches++;
+      } else {
+         o->fu(o->ctx, *t, n, U, T1, st); // udot
+         HRW_TRY(launch_combine(C_MS, n, U, T1, Uo4, Lo4, Uo4, c50, c10, st));
+         HRW_CUDA(cudaMemcpyAsync(Lo4, T1, (size_t)n * sizeof(double), cudaMemcpyDeviceToDevice, st));
+         o->launches++;
+      }
+      *t = *t + dt;
+      o->fevals += 1;
+      step++;
+   }
+   if (o->fused) {
+      HRW_TRY(fv_unpack(fv, fv->cell0(uring[step % 5]), u_dev, st));
+      o->launches++;
+   } else {
+      HRW_CUDA(cudaMemcpyAsync(u_dev, uring[step % 5], (size_t)n * sizeof(double), cudaMemcpyDeviceToDevice, st));
+   }
+   // keep the step counter small: only its residues mod 5 and mod 4 matter
+   step %= 20;
+   return HRWENO_OK;
+}
+
+int ode_integrate_dev(Ode *o, double *u_dev, double *t, double tout, double dt, int itask, cudaStream_t st) {
+   if (!o || !u_dev || !t) return fail(HRWENO_EINVAL, "integrate: null argument");
+   if (o->is_ms) return ms_integrate(o, u_dev, t, tout, dt, st);
+   return rk_integrate(o, u_dev, t, tout, dt, itask, st);
+}
+
+int ode_integrate_host(Ode *o, double *u, double *t, double tout, double dt, int itask) {
+   if (!o || !u || !t) return fail(HRWENO_EINVAL, "integrate: null argument");
+   if (o->istate < 1) return HRWENO_OK;
+   if (is_done(*t, tout, dt)) return HRWENO_OK;
+   double *d = o->bufs.back();
+   const size_t bytes = (size_t)o->neq * sizeof(double);
+   HRW_CUDA(cudaMemcpyAsync(d, u, bytes, cudaMemcpyHostToDevice, o->stream));
+   HRW_TRY(ode_integrate_dev(o, d, t, tout, dt, itask, o->stream));
+   HRW_CUDA(cudaMemcpyAsync(u, d, bytes, cudaMemcpyDeviceToHost, o->stream));
+   HRW_CUDA(cudaStreamSynchronize(o->stream));
+   return HRWENO_OK;
+}
+
+} // namespace hrw

@@ -1,0 +1,224 @@
+// weno_core.cuh -- WENO reconstruction of a run of R consecutive cells held in registers.
+//
+// Restates weno_reconstruct (src/hrweno_weno.f90:174-216) for the uniform-grid tables
+// (weno.f90:12-21).  A thread owns R consecutive cells and holds the window
+//     w[0 .. R+2(K-1)-1] = vext(i0-(K-1)) .. vext(i0+R-1+(K-1))
+// so that everything the reference recomputes per cell but that is *the same expression* for
+// neighbouring cells is evaluated once (bit-identical by construction):
+//   * the coefficient*value products c(j,r)*vext(m) (5 distinct coefficients for k=3),
+//   * vlr(r)_i == vrr(r-1)_{i-1},
+//   * the second-difference term 13/12*(a-2b+c)**2 shared by beta0_{i-1}, beta1_i, beta2_{i+1},
+//   * (eps+beta_r)**2 shared by alfa_r and alfatilde_r, and alfa_1 == alfatilde_1 (d(1) both).
+// sum() in the reference accumulates from 0; "0 + x" is dropped here (it can only turn -0 into +0).
+#pragma once
+
+#include "common.cuh"
+
+namespace hrw {
+
+template <int K, int R>
+struct Window {
+   static constexpr int G = K - 1;       // reconstruct ghost width (weno.f90:163)
+   static constexpr int N = R + 2 * G;   // window length
+};
+
+// ---------------------------------------------------------------------------------------- k = 1
+template <int R, class M>
+__device__ __forceinline__ void weno_run_k1(const double *w, double, double *vl, double *vr) {
+   // vrr = 1*v, beta = 0, alfa = 1/eps**2, w = alfa/alfa = 1  ->  vl = vr = v   (weno.f90:186)
+#pragma unroll
+   for (int j = 0; j < R; ++j) {
+      vl[j] = w[j];
+      vr[j] = w[j];
+   }
+}
+
+// ---------------------------------------------------------------------------------------- k = 2
+template <int R, class M>
+__device__ __forceinline__ void weno_run_k2(const double *w, double eps, double *vl, double *vr) {
+   constexpr int N = R + 2;
+   // c2 (weno.f90:17-18): c(:,-1) = [3/2,-1/2], c(:,0) = [1/2,1/2], c(:,1) = [-1/2,3/2]
+   double h[N], q[N]; // h = v/2 (exact), q = 3/2*v
+#pragma unroll
+   for (int j = 0; j < N; ++j) {
+      h[j] = M::mul(0.5, w[j]);
+      q[j] = M::mul(1.5, w[j]);
+   }
+   double dsq[N - 1]; // (v[j+1]-v[j])**2   (weno.f90:190-191)
+#pragma unroll
+   for (int j = 0; j < N - 1; ++j) {
+      const double d = M::sub(w[j + 1], w[j]);
+      dsq[j] = M::mul(d, d);
+   }
+   double a0[R + 1]; // a0[j] = vrr(0) of cell j-1 (window index j) = vlr(1) of cell j
+#pragma unroll
+   for (int j = 0; j < R + 1; ++j) a0[j] = M::add(h[j], h[j + 1]);
+   const double d0 = 2.0 / 3, d1 = 1.0 / 3;
+#pragma unroll
+   for (int j = 0; j < R; ++j) {
+      const int c = j + 1; // window index of the cell
+      const double vrr0 = a0[c];
+      const double vrr1 = M::sub(q[c], h[c - 1]); // -1/2*v[c-1] + 3/2*v[c]
+      const double vlr0 = M::sub(q[c], h[c + 1]); //  3/2*v[c] - 1/2*v[c+1]
+      const double vlr1 = a0[c - 1];
+      const double e0 = M::add(eps, dsq[c]), e1 = M::add(eps, dsq[c - 1]);
+      const double den0 = M::mul(e0, e0), den1 = M::mul(e1, e1);
+      if constexpr (M::strict) {
+         const double al0 = M::div(d0, den0), al1 = M::div(d1, den1);
+         const double at0 = M::div(d1, den0), at1 = M::div(d0, den1);
+         const double s = M::add(al0, al1), st = M::add(at0, at1);
+         vr[j] = M::add(M::mul(M::div(al0, s), vrr0), M::mul(M::div(al1, s), vrr1));
+         vl[j] = M::add(M::mul(M::div(at0, st), vlr0), M::mul(M::div(at1, st), vlr1));
+      } else {
+         // alfa_r ~ d_r * prod_{s != r} den_s ; one reciprocal per side
+         const double al0 = d0 * den1, al1 = d1 * den0;
+         const double at0 = d1 * den1, at1 = d0 * den0;
+         vr[j] = fma(al0, vrr0, al1 * vrr1) * fast_rcp(al0 + al1);
+         vl[j] = fma(at0, vlr0, at1 * vlr1) * fast_rcp(at0 + at1);
+      }
+   }
+}
+
+// ---------------------------------------------------------------------------------------- k = 3
+template <int R, class M>
+__device__ __forceinline__ void weno_run_k3(const double *w, double eps, double *vl, double *vr) {
+   constexpr int N = R + 4;
+   // c3 (weno.f90:19-21): c(:,-1) = [11/6,-7/6,1/3], c(:,0) = [1/3,5/6,-1/6],
+   //                      c(:,1) = [-1/6,5/6,1/3],   c(:,2) = [1/3,-7/6,11/6]
+   const double C13 = 1.0 / 3, C56 = 5.0 / 6, C16 = -1.0 / 6, C76 = -7.0 / 6, C116 = 11.0 / 6;
+   double p13[N], p56[N], p16[N], p76[N], p116[N], t3[N];
+#pragma unroll
+   for (int j = 0; j < N; ++j) {
+      p13[j] = M::mul(C13, w[j]);
+      p56[j] = M::mul(C56, w[j]);
+      p16[j] = M::mul(C16, w[j]);
+      p76[j] = M::mul(C76, w[j]);
+      p116[j] = M::mul(C116, w[j]);
+      t3[j] = M::mul(3.0, w[j]);
+   }
+   // m2[j] = 13/12 * ((v[j-1] - 2 v[j]) + v[j+1])**2, j = 1..N-2   (weno.f90:195,198,201)
+   double m2[N];
+#pragma unroll
+   for (int j = 1; j < N - 1; ++j) {
+      const double d2 = M::add(M::fma_exact(-2.0, w[j], w[j - 1]), w[j + 1]);
+      m2[j] = M::mul(13.0 / 12, M::mul(d2, d2));
+   }
+   // A0[j] = vrr(0) of the cell at window index j = (1/3 v[j] + 5/6 v[j+1]) - 1/6 v[j+2]; also vlr(1) of cell j+1
+   // A1[j] = vrr(1) of the cell at window index j = (-1/6 v[j-1] + 5/6 v[j]) + 1/3 v[j+1]; also vlr(2) of cell j+1
+   double A0[N], A1[N];
+#pragma unroll
+   for (int j = 1; j < R + 2; ++j) {
+      A0[j] = M::add(M::add(p13[j], p56[j + 1]), p16[j + 2]);
+      A1[j] = M::add(M::add(p16[j - 1], p56[j]), p13[j + 1]);
+   }
+#pragma unroll
+   for (int j = 0; j < R; ++j) {
+      const int c = j + 2; // window index of the cell
+      const double vrr0 = A0[c], vrr1 = A1[c];
+      const double vrr2 = M::add(M::add(p13[c - 2], p76[c - 1]), p116[c]);
+      const double vlr0 = M::add(M::add(p116[c], p76[c + 1]), p13[c + 2]);
+      const double vlr1 = A0[c - 1], vlr2 = A1[c - 1];
+      // beta (weno.f90:195-202); 1/4*x is exact so the final add may be fused
+      const double b0 = M::add(M::fma_exact(-4.0, w[c + 1], t3[c]), w[c + 2]);
+      const double b1 = M::sub(w[c - 1], w[c + 1]);
+      const double b2 = M::add(M::fma_exact(-4.0, w[c - 1], w[c - 2]), t3[c]);
+      const double beta0 = M::fma_exact(0.25, M::mul(b0, b0), m2[c + 1]);
+      const double beta1 = M::fma_exact(0.25, M::mul(b1, b1), m2[c]);
+      const double beta2 = M::fma_exact(0.25, M::mul(b2, b2), m2[c - 1]);
+      const double e0 = M::add(eps, beta0), e1 = M::add(eps, beta1), e2 = M::add(eps, beta2);
+      const double den0 = M::mul(e0, e0), den1 = M::mul(e1, e1), den2 = M::mul(e2, e2);
+      if constexpr (M::strict) {
+         // alfa = d/(eps+beta)**2, alfatilde = d(k-1:0:-1)/(eps+beta)**2   (weno.f90:207-208), d3 = [0.3,0.6,0.1]
+         const double al0 = M::div(0.3, den0), al1 = M::div(0.6, den1), al2 = M::div(0.1, den2);
+         const double at0 = M::div(0.1, den0), at2 = M::div(0.3, den2); // at1 == al1
+         const double s = M::add(M::add(al0, al1), al2);
+         const double st = M::add(M::add(at0, al1), at2);
+         // w = alfa/sum(alfa); vr = sum(w*vrr)   (weno.f90:209-214)
+         vr[j] = M::add(M::add(M::mul(M::div(al0, s), vrr0), M::mul(M::div(al1, s), vrr1)), M::mul(M::div(al2, s), vrr2));
+         vl[j] = M::add(M::add(M::mul(M::div(at0, st), vlr0), M::mul(M::div(al1, st), vlr1)), M::mul(M::div(at2, st), vlr2));
+      } else {
+         // division-light weights: alfa_r ~ d_r * prod_{s != r} den_s, one reciprocal per side
+         const double p0 = den1 * den2, p1 = den0 * den2, p2 = den0 * den1;
+         const double al0 = 0.3 * p0, al1 = 0.6 * p1, al2 = 0.1 * p2;
+         const double at0 = 0.1 * p0, at2 = 0.3 * p2;
+         const double s = (al0 + al1) + al2, st = (at0 + al1) + at2;
+         vr[j] = fma(al2, vrr2, fma(al1, vrr1, al0 * vrr0)) * fast_rcp(s);
+         vl[j] = fma(at2, vlr2, fma(al1, vlr1, at0 * vlr0)) * fast_rcp(st);
+      }
+   }
+}
+
+template <int K, int R, class M>
+__device__ __forceinline__ void weno_run(const double *w, double eps, double *vl, double *vr) {
+   if constexpr (K == 1)
+      weno_run_k1<R, M>(w, eps, vl, vr);
+   else if constexpr (K == 2)
+      weno_run_k2<R, M>(w, eps, vl, vr);
+   else
+      weno_run_k3<R, M>(w, eps, vl, vr);
+}
+
+// ------------------------------------------------------------------------------------------------
+// One cell with per-cell coefficients (non-uniform grid: ci = cnu(:,:,i), weno.f90:177).  Literal.
+// ci[j + K*(r+1)] = c(j,r); ve points at vext(i).
+// ------------------------------------------------------------------------------------------------
+template <int K, class M>
+__device__ __forceinline__ void weno_cell_nonuniform(const double *ci, const double *ve /* [-(K-1)..K-1] */,
+                                                     double eps, double &vl, double &vr) {
+   double vrr[K], vlr[K], beta[K];
+#pragma unroll
+   for (int r = 0; r < K; ++r) {
+      double sr = M::mul(ci[K * (r + 1)], ve[-r]);
+      double sl = M::mul(ci[K * r], ve[-r]);
+#pragma unroll
+      for (int j = 1; j < K; ++j) {
+         sr = M::mad(ci[j + K * (r + 1)], ve[-r + j], sr);
+         sl = M::mad(ci[j + K * r], ve[-r + j], sl);
+      }
+      vrr[r] = sr;
+      vlr[r] = sl;
+   }
+   if constexpr (K == 1) {
+      beta[0] = 0.0;
+   } else if constexpr (K == 2) {
+      const double a = M::sub(ve[1], ve[0]), b = M::sub(ve[0], ve[-1]);
+      beta[0] = M::mul(a, a);
+      beta[K - 1] = M::mul(b, b);
+   } else {
+      double a = M::add(M::fma_exact(-2.0, ve[1], ve[0]), ve[2]);
+      double b = M::add(M::fma_exact(-4.0, ve[1], M::mul(3.0, ve[0])), ve[2]);
+      beta[0] = M::fma_exact(0.25, M::mul(b, b), M::mul(13.0 / 12, M::mul(a, a)));
+      a = M::add(M::fma_exact(-2.0, ve[0], ve[-1]), ve[1]);
+      b = M::sub(ve[-1], ve[1]);
+      beta[1] = M::fma_exact(0.25, M::mul(b, b), M::mul(13.0 / 12, M::mul(a, a)));
+      a = M::add(M::fma_exact(-2.0, ve[-1], ve[-(K - 1)]), ve[0]);
+      b = M::add(M::fma_exact(-4.0, ve[-1], ve[-(K - 1)]), M::mul(3.0, ve[0]));
+      beta[K - 1] = M::fma_exact(0.25, M::mul(b, b), M::mul(13.0 / 12, M::mul(a, a)));
+   }
+   const double d1[1] = {1.0}, d2[2] = {2.0 / 3, 1.0 / 3}, d3[3] = {0.3, 0.6, 0.1};
+   const double *d = K == 1 ? d1 : (K == 2 ? d2 : d3);
+   double al[K], at[K];
+#pragma unroll
+   for (int r = 0; r < K; ++r) {
+      const double e = M::add(eps, beta[r]);
+      const double den = M::mul(e, e);
+      al[r] = M::div(d[r], den);
+      at[r] = M::div(d[K - 1 - r], den);
+   }
+   double s = al[0], st = at[0];
+#pragma unroll
+   for (int r = 1; r < K; ++r) {
+      s = M::add(s, al[r]);
+      st = M::add(st, at[r]);
+   }
+   double xr = M::mul(M::div(al[0], s), vrr[0]), xl = M::mul(M::div(at[0], st), vlr[0]);
+#pragma unroll
+   for (int r = 1; r < K; ++r) {
+      xr = M::add(xr, M::mul(M::div(al[r], s), vrr[r]));
+      xl = M::add(xl, M::mul(M::div(at[r], st), vlr[r]));
+   }
+   vr = xr;
+   vl = xl;
+}
+
+} // namespace hrw

@@ -1,0 +1,263 @@
+"""GPU parity: the CUDA path through the C ABI against the CPU oracle on the same inputs.
+
+Bar (north star): strict mode is bit-identical to the oracle (0 ULP; -0 == +0 allowed);
+fast mode is within 1e-12 normwise at every output time and a few ULP for reconstruct-only.
+"""
+import numpy as np
+import pytest
+
+from conftest import ex1_ic, ex2_ic, normwise, pulse
+
+pytestmark = pytest.mark.gpu
+
+SIZES_1D = [2, 3, 5, 30, 100, 1015, 1016, 1017, 2033, 5000]
+
+
+# ---- reconstruct (weno.f90:129-219) --------------------------------------------------------------
+@pytest.mark.parametrize("k", [1, 2, 3])
+def test_reconstruct_reference_test_uniform(gpu_lib, pkg, ref, k):
+    """test/test_hrweno.f90:29-67 through the reference-shaped API, plus bitwise vs the oracle"""
+    v = pulse(30)
+    w = pkg.hrweno_weno.weno(30, k, eps=1e-6)
+    vl, vr = w.reconstruct(v)
+    assert np.max(np.abs(vl - v)) <= 1e-6 and np.max(np.abs(vr - v)) <= 1e-6
+    rl, rr = ref.reconstruct(v, k, 1e-6)
+    assert np.array_equal(vl, rl) and np.array_equal(vr, rr)
+
+
+@pytest.mark.parametrize("k", [1, 2, 3])
+@pytest.mark.parametrize("nc", [1, 2, 3, 7, 257, 4096, 100003])
+def test_reconstruct_bitwise(gpu_lib, pkg, ref, k, nc):
+    rng = np.random.default_rng(100 * k + nc % 97)
+    v = rng.standard_normal(nc)
+    w = pkg.hrweno_weno.weno(nc, k, 1e-6)
+    vl, vr = w.reconstruct(v)
+    rl, rr = ref.reconstruct(v, k, 1e-6)
+    assert np.array_equal(vl, rl) and np.array_equal(vr, rr)
+
+
+@pytest.mark.parametrize("k", [1, 2, 3])
+def test_reconstruct_nonuniform(gpu_lib, pkg, ref, k):
+    """test/test_hrweno.f90:69-161: cnu on a uniform grid equals the tables; cubic grid pulse"""
+    nc = 30
+    xe = np.array([0.0 + 3.0 * i / nc for i in range(nc + 1)])
+    w = pkg.hrweno_weno.weno(nc, k, 1e-6, xedges=xe)
+    tab = {1: pkg.hrweno_weno.c1, 2: pkg.hrweno_weno.c2, 3: pkg.hrweno_weno.c3}[k]
+    for i in range(nc):
+        np.testing.assert_allclose(w.cnu[i], tab.T, rtol=1e-5)
+    assert np.array_equal(w.cnu, ref.calc_cnu(xe, k))
+    xe = np.array([i / nc for i in range(nc + 1)]) ** 3
+    w = pkg.hrweno_weno.weno(nc, k, xedges=xe)
+    v = pulse(nc)
+    vl, vr = w.reconstruct(v)
+    assert np.max(np.abs(vl - v)) <= 1e-6 and np.max(np.abs(vr - v)) <= 1e-6
+    rl, rr = ref.reconstruct(v, k, 1e-6, cnu=ref.calc_cnu(xe, k))
+    assert np.array_equal(vl, rl) and np.array_equal(vr, rr)
+    rng = np.random.default_rng(k)
+    v = rng.standard_normal(nc)
+    vl, vr = w.reconstruct(v)
+    rl, rr = ref.reconstruct(v, k, 1e-6, cnu=ref.calc_cnu(xe, k))
+    assert np.array_equal(vl, rl) and np.array_equal(vr, rr)
+
+
+def test_reconstruct_strided_and_batched(gpu_lib, pkg, ref):
+    """the sections of example2:98,107: contiguous rows and stride-nc1 columns"""
+    rng = np.random.default_rng(5)
+    n1, n2 = 37, 23
+    m = rng.standard_normal((n2, n1))
+    w1, w2 = pkg.hrweno_weno.weno(n1, 3, 1e-6), pkg.hrweno_weno.weno(n2, 3, 1e-6)
+    vl, vr = w1.reconstruct(m)  # all rows in one call
+    for j in range(n2):
+        rl, rr = ref.reconstruct(m[j], 3, 1e-6)
+        assert np.array_equal(vl[j], rl) and np.array_equal(vr[j], rr)
+    for i in (0, 5, n1 - 1):
+        vl, vr = w2.reconstruct(m[:, i])  # strided view
+        rl, rr = ref.reconstruct(np.ascontiguousarray(m[:, i]), 3, 1e-6)
+        assert np.array_equal(vl, rl) and np.array_equal(vr, rr)
+
+
+# ---- fluxes (fluxes.f90) -----------------------------------------------------------------------------
+def test_fluxes_reference_test(gpu_lib, pkg):
+    """test/test_fluxes.f90:27-71 (rtol 1e-8) for the pointwise helpers and the device face kernel"""
+    f = lambda u, x, t: u * x[0] * t  # noqa: E731
+    x, t, vm = [3.0], 5.0, 2.0
+    for vm_, vp_ in [(vm, vm), (vm, -2 * vm), (-vm, 2 * vm)]:
+        href = f(vm_, x, t)
+        assert pkg.hrweno_fluxes.godunov(f, vm_, vp_, x, t) == pytest.approx(href, rel=1e-8)
+        assert pkg.hrweno_fluxes.lax_friedrichs(f, vm_, vp_, x, t, x[0] * t) == pytest.approx(href, rel=1e-8)
+        for scheme in (0, 1):
+            h = pkg.hrweno_fluxes.flux_faces(scheme, 1, [vm_], [vp_], coef=15.0, alpha=15.0)
+            assert h[0] == pytest.approx(href, rel=1e-8)
+
+
+@pytest.mark.parametrize("scheme", [0, 1])
+@pytest.mark.parametrize("model", [0, 1])
+def test_flux_faces_bitwise(gpu_lib, pkg, ref, scheme, model):
+    rng = np.random.default_rng(9)
+    vm, vp = rng.standard_normal(1000), rng.standard_normal(1000)
+    vp[:100] = vm[:100]
+    h = pkg.hrweno_fluxes.flux_faces(scheme, model, vm, vp, coef=1.7, alpha=1.3)
+    assert np.array_equal(h, ref.face_flux(scheme, model, 1.7, 1.3, vm, vp))
+
+
+# ---- fused rhs, 1D (example1:72-109) --------------------------------------------------------------
+@pytest.mark.parametrize("k", [1, 2, 3])
+@pytest.mark.parametrize("nc", SIZES_1D)
+def test_rhs1d_bitwise_sizes(gpu_lib, pkg, ref, k, nc):
+    rng = np.random.default_rng(nc)
+    g = pkg.hrweno_grids.grid1().linear(-5.0, 5.0, nc)
+    v = ex1_ic(g.center) + 1e-3 * rng.standard_normal(nc)
+    d = pkg.fv.make_desc(nc, k=k, width=[g.width])
+    assert np.array_equal(pkg.fv.FV(d).rhs(0.0, v), ref.FV(d).rhs(0.0, v))
+
+
+@pytest.mark.parametrize("scheme,model,bc", [(0, 0, 0), (1, 0, 0), (0, 1, 1), (1, 1, 1), (0, 0, 1), (1, 1, 0)])
+@pytest.mark.parametrize("k", [1, 2, 3])
+def test_rhs1d_bitwise_variants_batched(gpu_lib, pkg, ref, k, scheme, model, bc):
+    rng = np.random.default_rng(11)
+    nc, rows = 1500, 7
+    g = pkg.hrweno_grids.grid1().geometric(0.0, 4.0, 1.001, nc)
+    v = ex1_ic(np.linspace(-5, 5, nc))[None, :] + 1e-3 * rng.standard_normal((rows, nc))
+    d = pkg.fv.make_desc(nc, k=k, rows=rows, flux_model=model, flux_scheme=scheme, flux_coef=(1.7, 1.0),
+                         alpha=1.3, bc=bc, width=[g.width])
+    assert np.array_equal(pkg.fv.FV(d).rhs(0.0, v), ref.FV(d).rhs(0.0, v))
+
+
+def test_rhs1d_linear_grid_analytic_width_is_bitwise(gpu_lib, pkg, ref):
+    """GRID_LINEAR recomputes grid1%linear's width on the device (grids.f90:76-79,247)"""
+    rng = np.random.default_rng(2)
+    for nc, (a, b) in [(100, (-5.0, 5.0)), (4097, (0.0, 10.0)), (1000, (-1.3, 7.7))]:
+        g = pkg.hrweno_grids.grid1().linear(a, b, nc)
+        v = ex1_ic(g.center) + 1e-3 * rng.standard_normal(nc)
+        got = pkg.fv.FV(pkg.fv.make_desc(nc, linear=(a, b))).rhs(0.0, v)
+        want = ref.FV(pkg.fv.make_desc(nc, width=[g.width])).rhs(0.0, v)
+        assert np.array_equal(got, want)
+
+
+# ---- integrators (tvdode.f90) ---------------------------------------------------------------------
+@pytest.mark.parametrize("order", [1, 2, 3])
+@pytest.mark.parametrize("k", [1, 2, 3])
+def test_rktvd_fused_bitwise(gpu_lib, pkg, ref, k, order):
+    nc = 300
+    g = pkg.hrweno_grids.grid1().linear(-5.0, 5.0, nc)
+    kw = dict(n=nc, k=k, width=[g.width])
+    ode = pkg.hrweno_tvdode.rktvd(pkg.fv.FV(pkg.fv.make_desc(**kw)), nc, order)
+    rode = ref.rktvd(ref.FV(pkg.fv.make_desc(**kw)), order)
+    u, ur, t, tr = ex1_ic(g.center), ex1_ic(g.center), 0.0, 0.0
+    for tout in (0.0, 0.05, 0.05, 0.2):  # includes t == tout (steps once) and an already-done call
+        t = ode.integrate(u, t, tout, 5e-3)
+        tr = rode.integrate(ur, tr, tout, 5e-3)
+        assert t == tr and np.array_equal(u, ur)
+    t, tr = ode.integrate(u, t, 9.0, 5e-3, itask=2), rode.integrate(ur, tr, 9.0, 5e-3, itask=2)
+    assert t == tr and np.array_equal(u, ur)
+    assert ode.fevals == rode.fevals and ode.istate == rode.istate == 2
+
+
+def test_config1_example1_every_output_time(gpu_lib, pkg, ref):
+    """configs[0]: example1 as shipped (Godunov, example1:99) -- and with Lax-Friedrichs alpha=1 as
+    BASELINE.json words it (example1:98).  Bitwise at all 101 output times."""
+    nc = 100
+    g = pkg.hrweno_grids.grid1().linear(-5.0, 5.0, nc)
+    for scheme in (0, 1):
+        kw = dict(n=nc, k=3, eps=1e-6, flux_scheme=scheme, alpha=1.0, width=[g.width])
+        ode = pkg.hrweno_tvdode.rktvd(pkg.fv.FV(pkg.fv.make_desc(**kw)), nc, 3)
+        rode = ref.rktvd(ref.FV(pkg.fv.make_desc(**kw)), 3)
+        u, ur, t, tr = ex1_ic(g.center), ex1_ic(g.center), 0.0, 0.0
+        for ii in range(101):
+            tout = 12.0 * ii / 100
+            t = ode.integrate(u, t, tout, 1e-2)
+            tr = rode.integrate(ur, tr, tout, 1e-2)
+            assert t == tr and np.array_equal(u, ur), f"output {ii}: normwise {normwise(u, ur):.3e}"
+        assert ode.fevals == 3603 and repr(t) == "12.009999999999788"
+
+
+def test_mstvd_fused_1d_bitwise(gpu_lib, pkg, ref):
+    nc = 500
+    g = pkg.hrweno_grids.grid1().linear(-5.0, 5.0, nc)
+    kw = dict(n=nc, k=3, width=[g.width])
+    ode = pkg.hrweno_tvdode.mstvd(pkg.fv.FV(pkg.fv.make_desc(**kw)), nc)
+    rode = ref.mstvd(ref.FV(pkg.fv.make_desc(**kw)))
+    u, ur, t, tr = ex1_ic(g.center), ex1_ic(g.center), 0.0, 0.0
+    for tout in (0.0, 0.1, 0.1, 0.25, 0.6):
+        t = ode.integrate(u, t, tout, 4e-3)
+        tr = rode.integrate(ur, tr, tout, 4e-3)
+        assert t == tr and np.array_equal(u, ur)
+    assert ode.fevals == rode.fevals
+
+
+@pytest.mark.parametrize("k", [1, 2, 3])
+def test_fast_mode_within_north_star_tolerance(gpu_lib, pkg, ref, k):
+    """fast mode: 1e-12 normwise at every output time (tolerance from BASELINE.json north_star)"""
+    nc = 100
+    g = pkg.hrweno_grids.grid1().linear(-5.0, 5.0, nc)
+    kw = dict(n=nc, k=k, eps=1e-6, width=[g.width])
+    ode = pkg.hrweno_tvdode.rktvd(pkg.fv.FV(pkg.fv.make_desc(mode=pkg._abi.MODE_FAST, **kw)), nc, 3)
+    rode = ref.rktvd(ref.FV(pkg.fv.make_desc(**kw)), 3)
+    u, ur, t, tr = ex1_ic(g.center), ex1_ic(g.center), 0.0, 0.0
+    worst = 0.0
+    for ii in range(101):
+        tout = 12.0 * ii / 100
+        t = ode.integrate(u, t, tout, 1e-2)
+        tr = rode.integrate(ur, tr, tout, 1e-2)
+        assert t == tr
+        worst = max(worst, normwise(u, ur))
+    assert worst <= 1e-12, worst
+
+
+def test_generic_callback_integrators_device_resident(gpu_lib, pkg, ref):
+    """rktvd(fu, neq, order) / mstvd(fu, neq) with a user rhs working on device memory (tvdode.f90:50-57)"""
+    nc = 200
+    g = pkg.hrweno_grids.grid1().linear(-5.0, 5.0, nc)
+    kw = dict(n=nc, k=3, width=[g.width])
+    fv = pkg.fv.FV(pkg.fv.make_desc(**kw))
+    calls = []
+
+    def fu(t, neq, u_ptr, udot_ptr, stream):
+        calls.append(t)
+        fv.rhs_dev(t, u_ptr, udot_ptr, stream)
+
+    for make, rmake in [
+        (lambda: pkg.hrweno_tvdode.rktvd(fu, nc, 3), lambda: ref.rktvd(ref.FV(pkg.fv.make_desc(**kw)), 3)),
+        (lambda: pkg.hrweno_tvdode.mstvd(fu, nc), lambda: ref.mstvd(ref.FV(pkg.fv.make_desc(**kw)))),
+    ]:
+        ode, rode = make(), rmake()
+        u, ur, t, tr = ex1_ic(g.center), ex1_ic(g.center), 0.0, 0.0
+        for tout in (0.0, 0.1, 0.3):
+            t = ode.integrate(u, t, tout, 5e-3)
+            tr = rode.integrate(ur, tr, tout, 5e-3)
+            assert t == tr and np.array_equal(u, ur)
+        assert ode.fevals == rode.fevals
+    assert calls[:3] == [0.0, 0.005, 0.0025]  # stage times t, t+dt, t+dt/2 (tvdode.f90:162-166)
+
+
+def test_reference_tvdode_tests_through_gpu_path(gpu_lib, pkg, ref):
+    """test/test_tvdode.f90 with the linear test ODE evaluated by a device rhs (a*u as LINEAR flux is not
+    applicable, so the callback scales on the device through the combine path): use the oracle numbers."""
+    a = np.array([-1.0 + float(ii - 1) * 4 / 9 for ii in range(1, 11)])
+    torch = pytest.importorskip("torch")
+    a_dev = torch.tensor(a, dtype=torch.float64, device="cuda")
+
+    def fu(t, neq, u_ptr, udot_ptr, stream):
+        # udot = a*u enqueued on the integrator's stream (torch only as a device-array convenience here)
+        n = int(neq)
+        with torch.cuda.stream(torch.cuda.ExternalStream(int(stream))):
+            _as_tensor(torch, udot_ptr, n).copy_(a_dev * _as_tensor(torch, u_ptr, n))
+
+    t0, tout = -1.3, 1.5
+    for order, rtol, dt in [(1, 2e-2, (tout - t0) / 3000), (2, 1e-3, (tout - t0) / 3000), (3, 1e-3, (tout - t0) / 3000)]:
+        ode = pkg.hrweno_tvdode.rktvd(fu, 10, order)
+        u = np.full(10, 0.1)
+        t = ode.integrate(u, t0, tout, dt)
+        np.testing.assert_allclose(u, 0.1 * np.exp(a * (t - t0)), rtol=rtol)
+        ur = np.full(10, 0.1)
+        tr = ref.rktvd("test_ode", order, neq=10).integrate(ur, t0, tout, dt)
+        assert t == tr and np.array_equal(u, ur)
+
+
+def _as_tensor(torch, ptr, n):
+    """wrap a raw device pointer as a torch tensor (test helper)"""
+
+    class _Holder:
+        __cuda_array_interface__ = {"shape": (n,), "typestr": "<f8", "data": (int(ptr), False), "version": 2}
+
+    return torch.as_tensor(_Holder(), device="cuda")
