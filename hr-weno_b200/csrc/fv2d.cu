@@ -1,6 +1,262 @@
-// fv2d.cu -- placeholder until the tile kernel lands
+// fv2d.cu -- fused 2D dimension-split finite-volume stage (example2:73-129).
+//
+// One CTA owns a TX x TY tile of cells.  The tile plus a 4-cell frame is staged in shared memory once
+// (coalesced 16-B loads along x1); both sweeps read it from there, so the stride-nc1 column gathers of
+// the reference (example2:107) never touch HBM.
+//   phase A: reconstruction along x1 for every tile row and along x2 for every tile column.  Work items
+//            are runs of R=4 consecutive cells of a line (row or column) -- the same register-window
+//            routine as the 1D kernel, addressed by (base, stride) so x1- and x2-items share one code
+//            path and one item list.  Each line gets one extra run at either end (tile overlap) so the
+//            faces on the tile edge see vr / vl of the neighbouring tile's cells without recomputation
+//            inside the tile.
+//   phase B: thread = (x, run of R cells along x2): Godunov / Lax-Friedrichs flux at the x1- and x2-faces,
+//            boundary constraints (example2:117-120), vdot = -(df1)/w1 - (df2)/w2 (example2:123-127),
+//            stage combination, coalesced stores along x1.
 #include "fv2d.cuh"
 
 namespace hrw {
-int fv2d_stage(Fv *, int, const StageArgs &, cudaStream_t) { return fail(HRWENO_EINVAL, "2D fused stage not built yet"); }
+
+struct Fv2dGeom {
+   int64_t n0, n1;   // cells along x1 (contiguous) and x2 (local slab)
+   int64_t pitch;    // padded row pitch
+   int tiles_x, tiles_y;
+   const double *w1, *w2; // widths (device, padded)
+   double eps;
+   FluxCfg flux1, flux2;
+   int bc;
+   int phys_lo, phys_hi; // x2 ends are physical boundaries (x1 ends always are)
+};
+
+template <int TX, int TY>
+struct Tile2d {
+   static constexpr int R = 4, H = 4;
+   static constexpr int SP = TX + 2 * H;         // tile pitch
+   static constexpr int SROWS = TY + 2 * H;
+   static constexpr int XP = TX + 2 * R;         // pitch of the x1-sweep vl/vr arrays (cells x0-R .. x0+TX+R-1)
+   static constexpr int YROWS = TY + 2 * R;      // rows of the x2-sweep vl/vr arrays
+   static constexpr int RUNS_X = TX / R + 2, NRX = RUNS_X * TY;
+   static constexpr int RUNS_Y = TY / R + 2, NRY = RUNS_Y * TX;
+   static constexpr int GR = 2;                  // zero guard rows above/below the staged tile (read by the
+                                                 // unused outer cells of the overlap runs of the x2-sweep)
+   static constexpr int OFF_V = GR * SP;
+   static constexpr int OFF_VLX = OFF_V + (SROWS + GR) * SP;
+   static constexpr int OFF_VRX = OFF_VLX + TY * XP;
+   static constexpr int OFF_VLY = OFF_VRX + TY * XP;
+   static constexpr int OFF_VRY = OFF_VLY + YROWS * TX;
+   static constexpr int TOTAL = OFF_VRY + YROWS * TX;
+   static constexpr size_t BYTES = (size_t)TOTAL * sizeof(double);
+};
+
+template <int K, int COMBINE, class M, int TX, int TY, int NT>
+__global__ void __launch_bounds__(NT) fv2d_stage_kernel(const Fv2dGeom g, const StageArgs s) {
+   using T = Tile2d<TX, TY>;
+   constexpr int R = T::R, H = T::H;
+   extern __shared__ __align__(16) double smem[];
+   double *s_v = smem + T::OFF_V;
+   double *s_vlx = smem + T::OFF_VLX, *s_vrx = smem + T::OFF_VRX;
+   double *s_vly = smem + T::OFF_VLY, *s_vry = smem + T::OFF_VRY;
+
+   const int tid = threadIdx.x;
+   const int64_t x0 = (int64_t)blockIdx.x * TX;
+   const int64_t y0 = (int64_t)blockIdx.y * TY;
+
+   // ---- stage tile + frame: rows y0-H .. y0+TY+H-1, columns x0-H .. x0+TX+H-1 -----------------------
+   for (int idx = tid; idx < (T::SROWS + 2 * T::GR) * (T::SP / 2); idx += NT) {
+      const int ry = idx / (T::SP / 2) - T::GR;
+      const int cx = (idx - (ry + T::GR) * (T::SP / 2)) * 2;
+      const int64_t gy = y0 - H + ry, gx = x0 - H + cx;
+      double2 t = make_double2(0.0, 0.0);
+      if (ry >= 0 && ry < T::SROWS && gy >= -PAD2 && gy < g.n1 + PAD2 && gx >= -PAD && gx + 1 < g.n0 + PAD)
+         t = *reinterpret_cast<const double2 *>(s.vin + gy * g.pitch + gx);
+      *reinterpret_cast<double2 *>(&s_v[ry * T::SP + cx]) = t;
+   }
+   __syncthreads();
+
+   // ---- phase A: reconstruction items ------------------------------------------------------------------
+   for (int it = tid; it < T::NRX + T::NRY; it += NT) {
+      const double *base;
+      int stride, oidx, ostride;
+      double *ovl, *ovr;
+      if (it < T::NRX) { // x1-sweep: row ly, run rx in [-1, TX/R]
+         const int ly = it / T::RUNS_X;
+         const int rx = it - ly * T::RUNS_X - 1;
+         base = s_v + (ly + H) * T::SP + (H + rx * R); // first cell of the run
+         stride = 1;
+         oidx = ly * T::XP + (rx + 1) * R;
+         ostride = 1;
+         ovl = s_vlx;
+         ovr = s_vrx;
+      } else { // x2-sweep: column lx, run ry in [-1, TY/R]
+         const int q = it - T::NRX;
+         const int ryi = q / TX;
+         const int lx = q - ryi * TX;
+         const int ry = ryi - 1;
+         base = s_v + (H + ry * R) * T::SP + (lx + H);
+         stride = T::SP;
+         oidx = (ryi * R) * TX + lx;
+         ostride = TX;
+         ovl = s_vly;
+         ovr = s_vry;
+      }
+      double w[R + 4];
+#pragma unroll
+      for (int j = 0; j < R + 4; ++j) w[j] = base[(j - 2) * stride];
+      double vl[R], vr[R];
+      weno_run<K, R, M>(w + (2 - (K - 1)), g.eps, vl, vr);
+#pragma unroll
+      for (int j = 0; j < R; ++j) {
+         ovl[oidx + j * ostride] = vl[j];
+         ovr[oidx + j * ostride] = vr[j];
+      }
+   }
+   __syncthreads();
+
+   // ---- phase B: fluxes, divergence, combination ---------------------------------------------------------
+   const bool copy = g.bc == HRWENO_BC_COPY_NEIGHBOUR;
+   for (int it = tid; it < TX * (TY / R); it += NT) {
+      const int ryi = it / TX;
+      const int lx = it - ryi * TX;
+      const int ly0 = ryi * R;
+      const int64_t gx = x0 + lx, gy0 = y0 + ly0;
+      if (gx >= g.n0 || gy0 >= g.n1) continue;
+
+      // x2-faces gy0 .. gy0+R of column gx: face f lies between rows f-1 and f
+      double F2[R + 1];
+#pragma unroll
+      for (int j = 0; j <= R; ++j) {
+         // vr of row (ly0+j-1), vl of row (ly0+j); array row index = local row + R
+         const double vm = s_vry[(ly0 + j - 1 + R) * TX + lx];
+         const double vp = s_vly[(ly0 + j + R) * TX + lx];
+         F2[j] = face_flux<M>(g.flux2, vm, vp);
+      }
+      if (g.phys_lo && gy0 == 0) F2[0] = copy ? F2[1] : 0.0;
+      if (g.phys_hi) {
+#pragma unroll
+         for (int j = 1; j <= R; ++j)
+            if (gy0 + j == g.n1) F2[j] = copy ? F2[j - 1] : 0.0;
+      }
+      const double w1 = __ldg(g.w1 + gx);
+#pragma unroll
+      for (int j = 0; j < R; ++j) {
+         const int64_t gy = gy0 + j;
+         if (gy >= g.n1) break;
+         const int ly = ly0 + j;
+         // x1-faces gx and gx+1 of row gy
+         const double *vlx = s_vlx + ly * T::XP + R + lx, *vrx = s_vrx + ly * T::XP + R + lx;
+         double Fl = face_flux<M>(g.flux1, vrx[-1], vlx[0]);
+         double Fr = face_flux<M>(g.flux1, vrx[0], vlx[1]);
+         if (copy) {
+            // fedges(0) = fedges(1), fedges(nc) = fedges(nc-1): needs the flux one face further in
+            if (gx == 0) Fl = Fr;
+            if (gx == g.n0 - 1) Fr = Fl;
+         } else {
+            if (gx == 0) Fl = 0.0;
+            if (gx == g.n0 - 1) Fr = 0.0;
+         }
+         const double w2 = __ldg(g.w2 + gy);
+         // vdot = -(f1(i)-f1(i-1))/w1(i) - (f2(j)-f2(j-1))/w2(j)   (example2:123-127)
+         const double L = M::sub(-M::div(M::sub(Fr, Fl), w1), M::div(M::sub(F2[j + 1], F2[j]), w2));
+         const double v = s_v[(ly + H) * T::SP + lx + H];
+         const int64_t off = gy * g.pitch + gx;
+         double o;
+         if (COMBINE == C_RHS) {
+            o = L;
+         } else if (COMBINE == C_EULER) {
+            o = M::add(v, M::mul(s.c0, L));
+         } else if (COMBINE == C_RK2_FINAL) {
+            o = M::mul(M::add(M::add(s.a[off], v), M::mul(s.c0, L)), 0.5);
+         } else if (COMBINE == C_RK3_S2) {
+            o = M::mul(M::add(M::add(M::mul(3.0, s.a[off]), v), M::mul(s.c0, L)), 0.25);
+         } else if (COMBINE == C_RK3_S3) {
+            o = M::div(M::add(M::fma_exact(2.0, v, s.a[off]), M::mul(s.c0, L)), 3.0);
+         } else {
+            o = M::mul(M::add(M::add(M::add(M::mul(25.0, v), M::mul(s.c0, L)), M::mul(7.0, s.a[off])), M::mul(s.c1, s.b[off])),
+                       0.03125);
+            s.out2[off] = L;
+         }
+         if (s.out_dense) {
+            s.out[gy * s.ld_out + gx] = o;
+         } else {
+            s.out[off] = o;
+            if (COMBINE != C_RHS) {
+               // ghost cells of the result at physical boundaries (edge replicas, weno.f90:172-173)
+               if (gx == 0) {
+#pragma unroll
+                  for (int q = 1; q <= K; ++q) s.out[off - q] = o;
+               }
+               if (gx == g.n0 - 1) {
+#pragma unroll
+                  for (int q = 1; q <= K; ++q) s.out[off + q] = o;
+               }
+               if (g.phys_lo && gy == 0) {
+#pragma unroll
+                  for (int q = 1; q <= K; ++q) s.out[off - q * g.pitch] = o;
+               }
+               if (g.phys_hi && gy == g.n1 - 1) {
+#pragma unroll
+                  for (int q = 1; q <= K; ++q) s.out[off + q * g.pitch] = o;
+               }
+            }
+         }
+      }
+   }
+}
+
+constexpr int TX2 = 64, TY2 = 32, NT2 = 256;
+
+template <int K, int COMBINE, class M>
+static int launch2d(const Fv2dGeom &g, const StageArgs &a, cudaStream_t st) {
+   using T = Tile2d<TX2, TY2>;
+   auto kern = fv2d_stage_kernel<K, COMBINE, M, TX2, TY2, NT2>;
+   static bool configured = false; // one flag per instantiation
+   if (!configured) {
+      HRW_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)T::BYTES));
+      configured = true;
+   }
+   dim3 grid((unsigned)g.tiles_x, (unsigned)g.tiles_y);
+   kern<<<grid, NT2, T::BYTES, st>>>(g, a);
+   HRW_CUDA(cudaGetLastError());
+   return HRWENO_OK;
+}
+
+template <int K, class M>
+static int launch2d_c(int combine, const Fv2dGeom &g, const StageArgs &a, cudaStream_t st) {
+   switch (combine) {
+   case C_RHS: return launch2d<K, C_RHS, M>(g, a, st);
+   case C_EULER: return launch2d<K, C_EULER, M>(g, a, st);
+   case C_RK2_FINAL: return launch2d<K, C_RK2_FINAL, M>(g, a, st);
+   case C_RK3_S2: return launch2d<K, C_RK3_S2, M>(g, a, st);
+   case C_RK3_S3: return launch2d<K, C_RK3_S3, M>(g, a, st);
+   default: return launch2d<K, C_MS, M>(g, a, st);
+   }
+}
+
+template <class M>
+static int launch2d_k(int k, int combine, const Fv2dGeom &g, const StageArgs &a, cudaStream_t st) {
+   if (k == 1) return launch2d_c<1, M>(combine, g, a, st);
+   if (k == 2) return launch2d_c<2, M>(combine, g, a, st);
+   return launch2d_c<3, M>(combine, g, a, st);
+}
+
+int fv2d_stage(Fv *fv, int combine, const StageArgs &args, cudaStream_t st) {
+   const hrweno_fv_desc &d = fv->d;
+   Fv2dGeom g{};
+   g.n0 = fv->n0;
+   g.n1 = fv->n1;
+   g.pitch = fv->pitch;
+   g.tiles_x = (int)((fv->n0 + TX2 - 1) / TX2);
+   g.tiles_y = (int)((fv->n1 + TY2 - 1) / TY2);
+   g.w1 = fv->d_width[0];
+   g.w2 = fv->d_width[1];
+   g.eps = d.eps;
+   g.flux1 = FluxCfg{d.flux_model, d.flux_scheme, d.flux_coef[0], d.alpha};
+   g.flux2 = FluxCfg{d.flux_model, d.flux_scheme, d.flux_coef[1], d.alpha};
+   g.bc = d.bc;
+   g.phys_lo = d.rank == 0;
+   g.phys_hi = d.rank == d.nranks - 1;
+   if (g.tiles_y > 65535) return fail(HRWENO_EINVAL, "2D grid too tall for one launch");
+   if (d.mode == HRWENO_MODE_STRICT) return launch2d_k<Strict>(d.k, combine, g, args, st);
+   return launch2d_k<Fast>(d.k, combine, g, args, st);
+}
+
 } // namespace hrw

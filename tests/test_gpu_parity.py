@@ -261,3 +261,90 @@ def _as_tensor(torch, ptr, n):
         __cuda_array_interface__ = {"shape": (n,), "typestr": "<f8", "data": (int(ptr), False), "version": 2}
 
     return torch.as_tensor(_Holder(), device="cuda")
+
+
+# ---- fused rhs, 2D dimension-split (example2:73-129) -----------------------------------------------
+@pytest.mark.parametrize("k", [1, 2, 3])
+@pytest.mark.parametrize("n1,n2", [(5, 7), (2, 2), (37, 23), (64, 32), (65, 33), (130, 70), (250, 250)])
+def test_rhs2d_bitwise_sizes(gpu_lib, pkg, ref, k, n1, n2):
+    rng = np.random.default_rng(n1 * 1000 + n2)
+    g1 = pkg.hrweno_grids.grid1().linear(0.0, 10.0, n1)
+    g2 = pkg.hrweno_grids.grid1().linear(0.0, 7.0, n2)
+    v = ex2_ic(g1.center, g2.center) + 1e-3 * rng.standard_normal((n2, n1))
+    d = pkg.fv.make_desc((n1, n2), k=k, flux_model=1, bc=1, width=[g1.width, g2.width])
+    assert np.array_equal(pkg.fv.FV(d).rhs(0.0, v), ref.FV(d).rhs(0.0, v))
+
+
+@pytest.mark.parametrize("scheme,model,bc", [(0, 0, 0), (1, 0, 0), (1, 1, 1), (0, 0, 1), (1, 1, 0)])
+def test_rhs2d_bitwise_variants(gpu_lib, pkg, ref, scheme, model, bc):
+    rng = np.random.default_rng(17)
+    n1, n2 = 150, 90
+    g1 = pkg.hrweno_grids.grid1().geometric(0.0, 4.0, 1.01, n1)
+    g2 = pkg.hrweno_grids.grid1().log(0.5, 9.0, n2)
+    v = rng.standard_normal((n2, n1))
+    d = pkg.fv.make_desc((n1, n2), k=3, flux_model=model, flux_scheme=scheme, flux_coef=(1.7, -0.6), alpha=1.3,
+                         bc=bc, width=[g1.width, g2.width])
+    assert np.array_equal(pkg.fv.FV(d).rhs(0.0, v), ref.FV(d).rhs(0.0, v))
+
+
+@pytest.mark.parametrize("order", [1, 2, 3])
+def test_rktvd_fused_2d_bitwise(gpu_lib, pkg, ref, order):
+    n1, n2 = 70, 45
+    g1 = pkg.hrweno_grids.grid1().linear(0.0, 10.0, n1)
+    g2 = pkg.hrweno_grids.grid1().linear(0.0, 10.0, n2)
+    kw = dict(n=(n1, n2), k=3, flux_model=1, bc=1, width=[g1.width, g2.width])
+    ode = pkg.hrweno_tvdode.rktvd(pkg.fv.FV(pkg.fv.make_desc(**kw)), n1 * n2, order)
+    rode = ref.rktvd(ref.FV(pkg.fv.make_desc(**kw)), order)
+    u = ex2_ic(g1.center, g2.center).reshape(-1)
+    ur = u.copy()
+    t, tr = 0.0, 0.0
+    for tout in (0.0, 0.1, 0.3):
+        t = ode.integrate(u, t, tout, 2e-2)
+        tr = rode.integrate(ur, tr, tout, 2e-2)
+        assert t == tr and np.array_equal(u, ur)
+
+
+def test_config2_example2_every_output_time(gpu_lib, pkg, ref):
+    """configs[1]: example2 as shipped (250x250, k=3, mstvd, dt=5e-3, 101 outputs to t=5): bitwise at every output"""
+    n = 250
+    g = pkg.hrweno_grids.grid1().linear(0.0, 10.0, n)
+    kw = dict(n=(n, n), k=3, eps=1e-6, flux_model=1, bc=1, width=[g.width, g.width])
+    ode = pkg.hrweno_tvdode.mstvd(pkg.fv.FV(pkg.fv.make_desc(**kw)), n * n)
+    ref.set_threads(min(16, ref.max_threads()))
+    try:
+        rode = ref.mstvd(ref.FV(pkg.fv.make_desc(**kw)))
+        u = ex2_ic(g.center, g.center).reshape(-1)
+        ur = u.copy()
+        t, tr = 0.0, 0.0
+        for ii in range(101):
+            tout = 5.0 * ii / 100
+            t = ode.integrate(u, t, tout, 5e-3)
+            tr = rode.integrate(ur, tr, tout, 5e-3)
+            assert t == tr and np.array_equal(u, ur), f"output {ii}: normwise {normwise(u, ur):.3e}"
+    finally:
+        ref.set_threads(1)
+    assert ode.fevals == 1009 and repr(t) == "5.0049999999999155"
+    assert abs(float(np.sum(u.reshape(n, n) * g.width[None, :] * g.width[:, None])) - 4.0) < 1e-12
+
+
+def test_config2_fast_mode_within_tolerance(gpu_lib, pkg, ref):
+    """fast mode on example2: 1e-12 normwise at every output time (SURVEY 7.4-1 measured 3.5e-13 drift)"""
+    n = 250
+    g = pkg.hrweno_grids.grid1().linear(0.0, 10.0, n)
+    kw = dict(n=(n, n), k=3, eps=1e-6, flux_model=1, bc=1, width=[g.width, g.width])
+    ode = pkg.hrweno_tvdode.mstvd(pkg.fv.FV(pkg.fv.make_desc(mode=pkg._abi.MODE_FAST, **kw)), n * n)
+    ref.set_threads(min(16, ref.max_threads()))
+    try:
+        rode = ref.mstvd(ref.FV(pkg.fv.make_desc(**kw)))
+        u = ex2_ic(g.center, g.center).reshape(-1)
+        ur = u.copy()
+        t, tr, worst = 0.0, 0.0, 0.0
+        for ii in range(101):
+            tout = 5.0 * ii / 100
+            t = ode.integrate(u, t, tout, 5e-3)
+            tr = rode.integrate(ur, tr, tout, 5e-3)
+            assert t == tr
+            worst = max(worst, normwise(u, ur))
+    finally:
+        ref.set_threads(1)
+    assert worst <= 1e-12, worst
