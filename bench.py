@@ -178,10 +178,7 @@ def main():
     desc = pkg.fv.make_desc(n, k=3, eps=1e-6, linear=(XMIN, XMAX), mode=mode, rank=rank, nranks=world,
                             global_n=n_global, global_offset=rank * n)
     fv = pkg.fv.FV(desc)
-    if world > 1:
-        handles = [None] * world
-        dist.all_gather_object(handles, fv.export_halo())
-        fv.import_halo(handles[rank - 1] if rank > 0 else None, handles[rank + 1] if rank < world - 1 else None)
+    pkg.slab.connect(fv, rank, world, pkg.slab.torch_all_gather(world))
     ode = pkg.hrweno_tvdode.rktvd(fv, n, 3)
 
     u_host = torch.from_numpy(make_ic(n, rank * n, n_global)).pin_memory()

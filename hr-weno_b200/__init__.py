@@ -14,6 +14,6 @@ except grid set-up, which the north star keeps on the host.
 """
 from . import _abi
 from ._abi import HrwenoError, lib
-from . import hrweno_grids, hrweno_weno, hrweno_fluxes, hrweno_tvdode, fv
+from . import hrweno_grids, hrweno_weno, hrweno_fluxes, hrweno_tvdode, fv, slab
 
-__all__ = ["_abi", "HrwenoError", "lib", "hrweno_grids", "hrweno_weno", "hrweno_fluxes", "hrweno_tvdode", "fv"]
+__all__ = ["_abi", "HrwenoError", "lib", "hrweno_grids", "hrweno_weno", "hrweno_fluxes", "hrweno_tvdode", "fv", "slab"]

@@ -92,6 +92,7 @@ PROTOTYPES = {
     "hrweno_fv_rhs_dev": (C.c_int, [C.c_void_p, C.c_double, C.c_void_p, C.c_void_p, C.c_void_p]),
     "hrweno_fv_export_halo": (C.c_int, [C.c_void_p, C.c_void_p]),
     "hrweno_fv_import_halo": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p]),
+    "hrweno_fv_halo_status": (C.c_int, [C.c_void_p]),
     "hrweno_rktvd_create": (C.c_int, [C.POINTER(C.c_void_p), RHS_FN, C.c_void_p, C.c_int64, C.c_int]),
     "hrweno_mstvd_create": (C.c_int, [C.POINTER(C.c_void_p), RHS_FN, C.c_void_p, C.c_int64]),
     "hrweno_rktvd_create_fused": (C.c_int, [C.POINTER(C.c_void_p), C.c_void_p, C.c_int]),

@@ -47,6 +47,7 @@ static int ensure_buf(Weno *w, size_t doubles) {
 static int fv_rhs_any(Fv *fv, const double *v_dev, double *vdot_dev, cudaStream_t st) {
    if (!fv->d_scratch_in) HRW_TRY(fv->alloc_state(&fv->d_scratch_in));
    HRW_TRY(fv_pack(fv, v_dev, fv->cell0(fv->d_scratch_in), st));
+   HRW_TRY(fv_exchange(fv, fv->cell0(fv->d_scratch_in), st));
    StageArgs a{};
    a.vin = fv->cell0(fv->d_scratch_in);
    a.out = vdot_dev;
@@ -194,11 +195,21 @@ int hrweno_fv_rhs(hrweno_fv *h, double t, const double *v, double *vdot) {
    HRW_TRY(fv_rhs_any(fv, din, dout, fv->stream));
    HRW_CUDA(cudaMemcpyAsync(vdot, dout, bytes, cudaMemcpyDeviceToHost, fv->stream));
    HRW_CUDA(cudaStreamSynchronize(fv->stream));
-   return HRWENO_OK;
+   return fv_halo_status(fv);
 }
 
-int hrweno_fv_export_halo(hrweno_fv *, void *) { return fail(HRWENO_ECOMM, "halo exchange not built yet"); }
-int hrweno_fv_import_halo(hrweno_fv *, const void *, const void *) { return fail(HRWENO_ECOMM, "halo exchange not built yet"); }
+int hrweno_fv_export_halo(hrweno_fv *h, void *handle_out) {
+   if (!h) return fail(HRWENO_EINVAL, "null fv handle");
+   return fv_halo_export(reinterpret_cast<Fv *>(h), handle_out);
+}
+int hrweno_fv_import_halo(hrweno_fv *h, const void *left_handle, const void *right_handle) {
+   if (!h) return fail(HRWENO_EINVAL, "null fv handle");
+   return fv_halo_import(reinterpret_cast<Fv *>(h), left_handle, right_handle);
+}
+int hrweno_fv_halo_status(hrweno_fv *h) {
+   if (!h) return fail(HRWENO_EINVAL, "null fv handle");
+   return fv_halo_status(reinterpret_cast<Fv *>(h));
+}
 
 // ---- integrators -----------------------------------------------------------------------------------
 int hrweno_rktvd_create(hrweno_ode **out, hrweno_rhs_fn fu, void *ctx, int64_t neq, int order) {

@@ -28,6 +28,7 @@ int Fv::alloc_state(double **out) const {
 }
 
 Fv::~Fv() {
+   fv_halo_free(this);
    cudaFree(d_width[0]);
    cudaFree(d_width[1]);
    cudaFree(d_scratch_in);

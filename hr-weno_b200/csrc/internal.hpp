@@ -33,8 +33,24 @@ struct StageArgs {
    double c0, c1;      // dt-like coefficients: (dt) | (2dt) | (50dt, 10dt)
 };
 
+// Halo exchange between slab neighbours over NVLink peer memory (CUDA IPC), one process per GPU.
+// Every rank owns a mailbox; its neighbours store their boundary cells straight into it (peer stores)
+// and then publish a sequence number; the owner's receive kernel spins on that number and moves the
+// cells into the ghost region of the state vector.  No host synchronisation, no NCCL call per stage.
+struct Halo {
+   static constexpr int NSLOTS = 4;
+   static constexpr size_t HDR_BYTES = 2048; // flags[2][NSLOTS] on separate 128-B lines + error word
+   size_t halo_doubles = 0;                  // doubles per side per slot
+   size_t bytes = 0;
+   unsigned char *mbox = nullptr;            // my mailbox (device memory, cudaMalloc'ed so it can be IPC-exported)
+   unsigned char *peer[2] = {nullptr, nullptr}; // left / right neighbour's mailbox mapped into this process
+   unsigned long long seq = 0;               // number of exchanges done (identical on all ranks: SPMD)
+   bool ready = false;
+};
+
 struct Fv {
    hrweno_fv_desc d{};
+   Halo halo;
    int64_t n0 = 0, n1 = 1;      // cells along x1 (contiguous) and x2
    int64_t rows = 1;             // 1D: independent rows
    int64_t neq = 0;
@@ -61,6 +77,12 @@ int fv_pack(Fv *fv, const double *dense_dev, double *padded_cell0, cudaStream_t 
 int fv_unpack(Fv *fv, const double *padded_cell0, double *dense_dev, cudaStream_t st);
 // one fused stage: reconstruct + face fluxes + divergence + combination
 int fv_stage(Fv *fv, int combine, const StageArgs &args, cudaStream_t st);
+// fill the slab-interface ghost cells of a padded state from the neighbouring ranks (no-op on one GPU)
+int fv_exchange(Fv *fv, double *padded_cell0, cudaStream_t st);
+int fv_halo_export(Fv *fv, void *handle_out);
+int fv_halo_import(Fv *fv, const void *left, const void *right);
+int fv_halo_status(Fv *fv);
+void fv_halo_free(Fv *fv);
 
 struct Weno {
    int64_t ncells = 0;

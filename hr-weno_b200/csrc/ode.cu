@@ -131,6 +131,7 @@ static int rk_step_fused(Ode *o, int order, double *src, double *dst, double *t1
       a.out = c0(dst);
       a.c0 = dt;
       HRW_TRY(fv_stage(fv, C_EULER, a, st));
+      HRW_TRY(fv_exchange(fv, c0(dst), st));
       o->launches += 1;
       return HRWENO_OK;
    }
@@ -138,11 +139,13 @@ static int rk_step_fused(Ode *o, int order, double *src, double *dst, double *t1
    a.out = c0(t1);
    a.c0 = dt;
    HRW_TRY(fv_stage(fv, C_EULER, a, st)); // ui = u + dt*udot
+   HRW_TRY(fv_exchange(fv, c0(t1), st));
    if (order == 2) {
       a.vin = c0(t1);
       a.a = c0(src);
       a.out = c0(dst);
       HRW_TRY(fv_stage(fv, C_RK2_FINAL, a, st)); // u = (u + ui + dt*udot)/2
+      HRW_TRY(fv_exchange(fv, c0(dst), st));
       o->launches += 2;
       return HRWENO_OK;
    }
@@ -150,11 +153,13 @@ static int rk_step_fused(Ode *o, int order, double *src, double *dst, double *t1
    a.a = c0(src);
    a.out = c0(t2);
    HRW_TRY(fv_stage(fv, C_RK3_S2, a, st)); // ui = (3*u + ui + dt*udot)/4
+   HRW_TRY(fv_exchange(fv, c0(t2), st));
    a.vin = c0(t2);
    a.a = c0(src);
    a.out = c0(dst);
    a.c0 = 2 * dt;
    HRW_TRY(fv_stage(fv, C_RK3_S3, a, st)); // u = (u + 2*ui + 2*dt*udot)/3
+   HRW_TRY(fv_exchange(fv, c0(dst), st));
    o->launches += 3;
    return HRWENO_OK;
 }
@@ -192,6 +197,7 @@ static int rk_integrate(Ode *o, double *u_dev, double *t, double tout, double dt
       Fv *fv = o->fv;
       double *U = o->bufs[0], *T1 = o->bufs[1], *T2 = o->bufs[2];
       HRW_TRY(fv_pack(fv, u_dev, fv->cell0(U), st));
+      HRW_TRY(fv_exchange(fv, fv->cell0(U), st));
       o->launches++;
       for (;;) {
          if (o->order == 1) {
@@ -235,6 +241,7 @@ static int ms_integrate(Ode *o, double *u_dev, double *t, double tout, double dt
    // the caller's u is the current state (it may have been edited between calls, like the reference's inout u)
    if (o->fused) {
       HRW_TRY(fv_pack(fv, u_dev, fv->cell0(uring[step % 5]), st));
+      HRW_TRY(fv_exchange(fv, fv->cell0(uring[step % 5]), st));
       o->launches++;
    } else {
       HRW_CUDA(cudaMemcpyAsync(uring[step % 5], u_dev, (size_t)n * sizeof(double), cudaMemcpyDeviceToDevice, st));
@@ -276,6 +283,7 @@ static int ms_integrate(Ode *o, double *u_dev, double *t, double tout, double dt
          a.c0 = c50;
          a.c1 = c10;
          HRW_TRY(fv_stage(fv, C_MS, a, st));
+         HRW_TRY(fv_exchange(fv, fv->cell0(Uo4), st));
          o->launches++;
       } else {
          o->fu(o->ctx, *t, n, U, T1, st); // udot
@@ -314,6 +322,7 @@ int ode_integrate_host(Ode *o, double *u, double *t, double tout, double dt, int
    HRW_TRY(ode_integrate_dev(o, d, t, tout, dt, itask, o->stream));
    HRW_CUDA(cudaMemcpyAsync(u, d, bytes, cudaMemcpyDeviceToHost, o->stream));
    HRW_CUDA(cudaStreamSynchronize(o->stream));
+   if (o->fused) HRW_TRY(fv_halo_status(o->fv));
    return HRWENO_OK;
 }
 

@@ -157,6 +157,8 @@ int hrweno_fv_rhs_dev(hrweno_fv *fv, double t, const double *v_dev, double *vdot
 #define HRWENO_IPC_HANDLE_BYTES 64
 int hrweno_fv_export_halo(hrweno_fv *fv, void *handle_out);
 int hrweno_fv_import_halo(hrweno_fv *fv, const void *left_handle, const void *right_handle);
+/* synchronises the device and reports HRWENO_ECOMM if a halo wait timed out (a neighbour rank died) */
+int hrweno_fv_halo_status(hrweno_fv *fv);
 
 /* ---- TVD time integrators (src/hrweno_tvdode.f90) -------------------------- */
 
