@@ -1,0 +1,361 @@
+!> ISO_C_BINDING shim: the reference's module / type / procedure names on top of libhrweno_b200.so.
+!!
+!! NOT COMPILED IN THIS REPOSITORY'S CI: the build image has no Fortran compiler (see DESIGN.md).  It is
+!! the binding a maintainer adds to HR-WENO so that example1/example2 re-link against the B200 library:
+!!     gfortran -c hrweno_b200_shim.f90 && gfortran example1.f90 hrweno_b200_shim.o -lhrweno_b200
+!! `hrweno_kinds` and `hrweno_grids` are used unchanged from the reference (grids, set-up and I/O stay
+!! on the host); this file replaces hrweno_weno, hrweno_fluxes (re-exported unchanged: pointwise host
+!! helpers) and hrweno_tvdode.
+module hrweno_b200_c
+   use, intrinsic :: iso_c_binding
+   implicit none
+   public
+
+   integer(c_int), parameter :: HRWENO_ABI_VERSION = 1
+   integer(c_int), parameter :: FLUX_BURGERS = 0, FLUX_LINEAR = 1
+   integer(c_int), parameter :: SCHEME_GODUNOV = 0, SCHEME_LAX_FRIEDRICHS = 1
+   integer(c_int), parameter :: BC_COPY_NEIGHBOUR = 0, BC_ZERO_FLUX = 1
+   integer(c_int), parameter :: GRID_WIDTH_ARRAY = 0, GRID_LINEAR = 1
+   integer(c_int), parameter :: MODE_STRICT = 0, MODE_FAST = 1
+
+   type, bind(c) :: hrweno_fv_desc
+      integer(c_int32_t) :: abi_version = HRWENO_ABI_VERSION
+      integer(c_int32_t) :: ndim = 1
+      integer(c_int64_t) :: n(2) = [1, 1]
+      integer(c_int64_t) :: rows = 1
+      integer(c_int32_t) :: k = 3
+      integer(c_int32_t) :: flux_model = FLUX_BURGERS
+      integer(c_int32_t) :: flux_scheme = SCHEME_GODUNOV
+      integer(c_int32_t) :: bc = BC_COPY_NEIGHBOUR
+      integer(c_int32_t) :: grid_kind = GRID_WIDTH_ARRAY
+      integer(c_int32_t) :: mode = MODE_STRICT
+      real(c_double) :: eps = 1e-6_c_double
+      real(c_double) :: flux_coef(2) = [1.0_c_double, 1.0_c_double]
+      real(c_double) :: alpha = 1.0_c_double
+      real(c_double) :: xmin = 0.0_c_double, xmax = 1.0_c_double
+      type(c_ptr) :: width(2) = [c_null_ptr, c_null_ptr]
+      integer(c_int32_t) :: rank = 0, nranks = 1
+      integer(c_int64_t) :: global_n = 0, global_offset = 0
+   end type
+
+   interface
+      function hrweno_last_error() bind(c, name="hrweno_last_error") result(p)
+         import :: c_ptr
+         type(c_ptr) :: p
+      end function
+      function hrweno_weno_create(out, ncells, k, eps, xedges) bind(c, name="hrweno_weno_create") result(st)
+         import :: c_ptr, c_int, c_int64_t, c_double
+         type(c_ptr), intent(out) :: out
+         integer(c_int64_t), value :: ncells
+         integer(c_int), value :: k
+         real(c_double), value :: eps
+         type(c_ptr), value :: xedges
+         integer(c_int) :: st
+      end function
+      subroutine hrweno_weno_destroy(w) bind(c, name="hrweno_weno_destroy")
+         import :: c_ptr
+         type(c_ptr), value :: w
+      end subroutine
+      function hrweno_weno_get_cnu(w, cnu) bind(c, name="hrweno_weno_get_cnu") result(st)
+         import :: c_ptr, c_int, c_double
+         type(c_ptr), value :: w
+         real(c_double), intent(out) :: cnu(*)
+         integer(c_int) :: st
+      end function
+      function hrweno_weno_reconstruct(w, v, vl, vr) bind(c, name="hrweno_weno_reconstruct") result(st)
+         import :: c_ptr, c_int, c_double
+         type(c_ptr), value :: w
+         real(c_double), intent(in) :: v(*)
+         real(c_double), intent(out) :: vl(*), vr(*)
+         integer(c_int) :: st
+      end function
+      function hrweno_fv_create(out, desc) bind(c, name="hrweno_fv_create") result(st)
+         import :: c_ptr, c_int, hrweno_fv_desc
+         type(c_ptr), intent(out) :: out
+         type(hrweno_fv_desc), intent(in) :: desc
+         integer(c_int) :: st
+      end function
+      subroutine hrweno_fv_destroy(fv) bind(c, name="hrweno_fv_destroy")
+         import :: c_ptr
+         type(c_ptr), value :: fv
+      end subroutine
+      function hrweno_fv_rhs(fv, t, v, vdot) bind(c, name="hrweno_fv_rhs") result(st)
+         import :: c_ptr, c_int, c_double
+         type(c_ptr), value :: fv
+         real(c_double), value :: t
+         real(c_double), intent(in) :: v(*)
+         real(c_double), intent(out) :: vdot(*)
+         integer(c_int) :: st
+      end function
+      function hrweno_rktvd_create_fused(out, fv, order) bind(c, name="hrweno_rktvd_create_fused") result(st)
+         import :: c_ptr, c_int
+         type(c_ptr), intent(out) :: out
+         type(c_ptr), value :: fv
+         integer(c_int), value :: order
+         integer(c_int) :: st
+      end function
+      function hrweno_mstvd_create_fused(out, fv) bind(c, name="hrweno_mstvd_create_fused") result(st)
+         import :: c_ptr, c_int
+         type(c_ptr), intent(out) :: out
+         type(c_ptr), value :: fv
+         integer(c_int) :: st
+      end function
+      function hrweno_rktvd_create(out, fu, ctx, neq, order) bind(c, name="hrweno_rktvd_create") result(st)
+         import :: c_ptr, c_funptr, c_int, c_int64_t
+         type(c_ptr), intent(out) :: out
+         type(c_funptr), value :: fu
+         type(c_ptr), value :: ctx
+         integer(c_int64_t), value :: neq
+         integer(c_int), value :: order
+         integer(c_int) :: st
+      end function
+      function hrweno_mstvd_create(out, fu, ctx, neq) bind(c, name="hrweno_mstvd_create") result(st)
+         import :: c_ptr, c_funptr, c_int, c_int64_t
+         type(c_ptr), intent(out) :: out
+         type(c_funptr), value :: fu
+         type(c_ptr), value :: ctx
+         integer(c_int64_t), value :: neq
+         integer(c_int) :: st
+      end function
+      subroutine hrweno_ode_destroy(ode) bind(c, name="hrweno_ode_destroy")
+         import :: c_ptr
+         type(c_ptr), value :: ode
+      end subroutine
+      function hrweno_ode_integrate(ode, u, t, tout, dt, itask) bind(c, name="hrweno_ode_integrate") result(st)
+         import :: c_ptr, c_int, c_double
+         type(c_ptr), value :: ode
+         real(c_double), intent(inout) :: u(*)
+         real(c_double), intent(inout) :: t
+         real(c_double), value :: tout, dt
+         integer(c_int), value :: itask
+         integer(c_int) :: st
+      end function
+      function hrweno_ode_fevals(ode) bind(c, name="hrweno_ode_fevals") result(n)
+         import :: c_ptr, c_int64_t
+         type(c_ptr), value :: ode
+         integer(c_int64_t) :: n
+      end function
+      function hrweno_ode_istate(ode) bind(c, name="hrweno_ode_istate") result(n)
+         import :: c_ptr, c_int
+         type(c_ptr), value :: ode
+         integer(c_int) :: n
+      end function
+   end interface
+
+contains
+
+   function last_error_string() result(msg)
+      character(:), allocatable :: msg
+      character(kind=c_char), pointer :: p(:)
+      integer :: n
+      call c_f_pointer(hrweno_last_error(), p, [4096])
+      n = 0
+      do while (p(n + 1) /= c_null_char)
+         n = n + 1
+      end do
+      allocate (character(n) :: msg)
+      msg = transfer(p(1:n), msg)
+   end function
+
+end module hrweno_b200_c
+
+module hrweno_weno
+!! Drop-in for src/hrweno_weno.f90: same public names (weno, c1, c2, c3), same constructor and
+!! reconstruct signatures (weno.f90:44,48-50,54,129).  `reconstruct` is no longer `pure`: it calls C.
+   use, intrinsic :: iso_c_binding
+   use hrweno_kinds, only: rk
+   use hrweno_b200_c
+   implicit none
+   private
+   public :: weno, c1, c2, c3
+
+   real(rk), parameter :: &
+      c1(0:0, -1:0) = reshape([1.0_rk, 1.0_rk], [1, 2]), &
+      c2(0:1, -1:1) = reshape([3.0_rk/2, -1.0_rk/2, 1.0_rk/2, 1.0_rk/2, -1.0_rk/2, 3.0_rk/2], [2, 3]), &
+      c3(0:2, -1:2) = reshape([11.0_rk/6, -7.0_rk/6, 1.0_rk/3, 1.0_rk/3, 5.0_rk/6, -1.0_rk/6, &
+                               -1.0_rk/6, 5.0_rk/6, 1.0_rk/3, 1.0_rk/3, -7.0_rk/6, 11.0_rk/6], [3, 4])
+
+   type :: weno
+      character(:), allocatable :: msg
+      integer :: ierr = 0
+      integer :: ncells
+      integer :: k = 3
+      real(rk) :: eps = 1e-6_rk
+      real(rk), allocatable :: cnu(:, :, :)
+      type(c_ptr), private :: handle = c_null_ptr  ! owned by the C library; released by destroy()
+   contains
+      procedure, pass(self) :: reconstruct => weno_reconstruct
+      procedure, pass(self) :: destroy => weno_destroy  ! explicit: a finaliser would free the handle of the
+                                                        ! function-result temporary in `w = weno(...)` (example1:44)
+   end type weno
+
+   interface weno
+      module procedure :: weno_init
+   end interface weno
+
+contains
+
+   type(weno) function weno_init(ncells, k, eps, xedges) result(self)
+      integer, intent(in) :: ncells
+      integer, intent(in), optional :: k
+      real(rk), intent(in), optional :: eps
+      real(rk), intent(in), optional, target :: xedges(0:)
+      integer(c_int) :: st
+      type(c_ptr) :: xe
+      self%ncells = ncells
+      if (present(k)) self%k = k
+      if (present(eps)) self%eps = eps
+      xe = c_null_ptr
+      if (present(xedges)) then
+         if (size(xedges) /= ncells + 1) then
+            self%msg = "Invalid input 'xedges': size(xedges) /= ncells + 1."
+            self%ierr = 1
+            error stop self%msg
+         end if
+         xe = c_loc(xedges)
+      end if
+      st = hrweno_weno_create(self%handle, int(ncells, c_int64_t), int(self%k, c_int), real(self%eps, c_double), xe)
+      if (st /= 0) then
+         self%msg = last_error_string()   ! same texts as weno.f90:75,84,94
+         self%ierr = 1
+         error stop self%msg
+      end if
+      if (present(xedges)) then
+         allocate (self%cnu(0:self%k - 1, -1:self%k - 1, 1:ncells))
+         st = hrweno_weno_get_cnu(self%handle, self%cnu)
+      end if
+   end function weno_init
+
+   subroutine weno_reconstruct(self, v, vl, vr)
+      class(weno), intent(in) :: self
+      real(rk), intent(in), contiguous :: v(:)   ! strided actuals (example2:107) are copied in by the compiler
+      real(rk), intent(out), contiguous :: vl(:), vr(:)
+      integer(c_int) :: st
+      st = hrweno_weno_reconstruct(self%handle, v, vl, vr)
+      if (st /= 0) error stop last_error_string()
+   end subroutine weno_reconstruct
+
+   subroutine weno_destroy(self)
+      class(weno), intent(inout) :: self
+      call hrweno_weno_destroy(self%handle)
+      self%handle = c_null_ptr
+   end subroutine weno_destroy
+
+end module hrweno_weno
+
+module hrweno_tvdode
+!! Drop-in for src/hrweno_tvdode.f90 (rktvd, mstvd; tvdode.f90:36-48,59-65).  Two constructors each:
+!! the reference's `rktvd(fu, neq, order)` / `mstvd(fu, neq)` with a user integrand, and the fused
+!! `rktvd(fv, order)` / `mstvd(fv)` where `fv` is a hrweno_fv handle describing the example rhs.
+   use, intrinsic :: iso_c_binding
+   use hrweno_kinds, only: rk
+   use hrweno_b200_c
+   implicit none
+   private
+   public :: rktvd, mstvd, integrand_dev
+
+   abstract interface
+      subroutine integrand_dev(ctx, t, neq, u_dev, udot_dev, stream) bind(c)
+         !! device-resident integrand: u_dev/udot_dev are CUDA device pointers (hrweno_rhs_fn)
+         import :: c_ptr, c_double, c_int64_t
+         type(c_ptr), value :: ctx
+         real(c_double), value :: t
+         integer(c_int64_t), value :: neq
+         type(c_ptr), value :: u_dev, udot_dev, stream
+      end subroutine
+   end interface
+
+   type, abstract :: tvdode
+      integer :: neq
+      integer :: order
+      character(:), allocatable :: msg
+      type(c_ptr) :: handle = c_null_ptr
+   contains
+      procedure, pass(self) :: fevals => tvdode_fevals   ! a function now: the counter lives in the C object
+      procedure, pass(self) :: istate => tvdode_istate
+      procedure, pass(self) :: integrate => tvdode_integrate
+      procedure, pass(self) :: destroy => tvdode_destroy
+   end type tvdode
+
+   type, extends(tvdode) :: rktvd
+   end type
+   type, extends(tvdode) :: mstvd
+   end type
+
+   interface rktvd
+      module procedure :: rktvd_init, rktvd_init_fused
+   end interface
+   interface mstvd
+      module procedure :: mstvd_init, mstvd_init_fused
+   end interface
+
+contains
+
+   type(rktvd) function rktvd_init(fu, neq, order) result(self)
+      procedure(integrand_dev) :: fu
+      integer, intent(in) :: neq, order
+      self%neq = neq; self%order = order
+      call created(self, hrweno_rktvd_create(self%handle, c_funloc(fu), c_null_ptr, int(neq, c_int64_t), int(order, c_int)))
+   end function
+
+   type(rktvd) function rktvd_init_fused(fv, neq, order) result(self)
+      type(c_ptr), intent(in) :: fv
+      integer, intent(in) :: neq, order
+      self%neq = neq; self%order = order
+      call created(self, hrweno_rktvd_create_fused(self%handle, fv, int(order, c_int)))
+   end function
+
+   type(mstvd) function mstvd_init(fu, neq) result(self)
+      procedure(integrand_dev) :: fu
+      integer, intent(in) :: neq
+      self%neq = neq; self%order = 3
+      call created(self, hrweno_mstvd_create(self%handle, c_funloc(fu), c_null_ptr, int(neq, c_int64_t)))
+   end function
+
+   type(mstvd) function mstvd_init_fused(fv, neq) result(self)
+      type(c_ptr), intent(in) :: fv
+      integer, intent(in) :: neq
+      self%neq = neq; self%order = 3
+      call created(self, hrweno_mstvd_create_fused(self%handle, fv))
+   end function
+
+   subroutine created(self, st)
+      class(tvdode), intent(inout) :: self
+      integer(c_int), intent(in) :: st
+      if (st /= 0) then
+         self%msg = last_error_string()   ! tvdode.f90:83,89 texts
+         error stop self%msg
+      end if
+   end subroutine
+
+   subroutine tvdode_integrate(self, u, t, tout, dt, itask)
+      !! tvdode.f90:97 / :203 -- same argument list; mstvd ignores itask like the reference (it has none)
+      class(tvdode), intent(inout) :: self
+      real(rk), intent(inout), contiguous :: u(:)
+      real(rk), intent(inout) :: t
+      real(rk), intent(in) :: tout, dt
+      integer, intent(in), optional :: itask
+      integer(c_int) :: st, itask_
+      itask_ = 1
+      if (present(itask)) itask_ = int(itask, c_int)
+      st = hrweno_ode_integrate(self%handle, u, t, tout, dt, itask_)
+      if (st /= 0) error stop last_error_string()
+   end subroutine
+
+   integer function tvdode_fevals(self) result(n)
+      class(tvdode), intent(in) :: self
+      n = int(hrweno_ode_fevals(self%handle))
+   end function
+
+   integer function tvdode_istate(self) result(n)
+      class(tvdode), intent(in) :: self
+      n = int(hrweno_ode_istate(self%handle))
+   end function
+
+   subroutine tvdode_destroy(self)
+      class(tvdode), intent(inout) :: self
+      call hrweno_ode_destroy(self%handle)
+      self%handle = c_null_ptr
+   end subroutine
+
+end module hrweno_tvdode

@@ -238,7 +238,12 @@ int64_t hrweno_ode_fevals(const hrweno_ode *ode) { return ode ? reinterpret_cast
 int hrweno_ode_istate(const hrweno_ode *ode) { return ode ? reinterpret_cast<const Ode *>(ode)->istate : -1; }
 int hrweno_ode_order(const hrweno_ode *ode) { return ode ? reinterpret_cast<const Ode *>(ode)->order : 0; }
 int64_t hrweno_ode_neq(const hrweno_ode *ode) { return ode ? reinterpret_cast<const Ode *>(ode)->neq : 0; }
-int64_t hrweno_ode_launches(const hrweno_ode *ode) { return ode ? reinterpret_cast<const Ode *>(ode)->launches : 0; }
+int64_t hrweno_ode_launches(const hrweno_ode *ode) {
+   if (!ode) return 0;
+   const Ode *o = reinterpret_cast<const Ode *>(ode);
+   // fused path: every kernel (pack, stages, halo send/signal/recv, unpack) is counted by the fv operator
+   return o->fused ? o->fv->launches : o->launches;
+}
 
 // ---- pinned host memory ----------------------------------------------------------------------------
 int hrweno_host_alloc(void **out, int64_t bytes) {

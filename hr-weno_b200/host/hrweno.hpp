@@ -1,0 +1,230 @@
+// hrweno.hpp -- C++ host-side mirror of HR-WENO's Fortran modules over the C ABI (include/hrweno_b200.h).
+//
+// The reference's host language is Fortran; no Fortran compiler exists in this image, so the host side that
+// sits above the C ABI is written in C++ with the reference's module / type / procedure names and argument
+// meaning (the ISO_C_BINDING modules a Fortran program would use instead are in fortran/).
+//   namespace hrweno::hrweno_grids   { class grid1 }                    src/hrweno_grids.f90   (host-side set-up)
+//   namespace hrweno::hrweno_weno    { class weno }                     src/hrweno_weno.f90:23-50
+//   namespace hrweno::hrweno_fluxes  { godunov, lax_friedrichs }        src/hrweno_fluxes.f90:22,47
+//   namespace hrweno::hrweno_tvdode  { class rktvd, class mstvd }       src/hrweno_tvdode.f90:36-48
+// Errors: where the reference executes `error stop msg`, these throw hrweno::error carrying the same message.
+#pragma once
+
+#include <cmath>
+#include <cstdint>
+#include <functional>
+#include <stdexcept>
+#include <string>
+#include <vector>
+
+#include "hrweno_b200.h"
+
+namespace hrweno {
+struct error : std::runtime_error {
+   int status;
+   error(int st, const std::string &m) : std::runtime_error(m), status(st) {}
+};
+inline void check(int st) {
+   if (st != HRWENO_OK) throw error(st, hrweno_last_error());
+}
+} // namespace hrweno
+
+namespace hrweno {
+namespace hrweno_grids {
+// type(grid1), grids.f90:10-37 -- only what the finite-volume path consumes
+class grid1 {
+ public:
+   int64_t ncells = 0;
+   std::string scale, name;
+   std::vector<double> edges, center, width; // edges(0:ncells); left = edges[0..n-1], right = edges[1..n]
+   const double *left() const { return edges.data(); }
+   const double *right() const { return edges.data() + 1; }
+   void linear(double xmin, double xmax, int64_t n, const std::string &nm = "") { // grids.f90:41-84
+      if (xmax <= xmin) throw hrweno::error(HRWENO_EINVAL, "Invalid input 'xmin', 'xmax'. Valid range: xmax > xmin.");
+      if (n < 1) throw hrweno::error(HRWENO_EINVAL, "Invalid input 'ncells'. Valid range: ncells > 1.");
+      std::vector<double> xe((size_t)n + 1);
+      const double rx = (xmax - xmin) / (double)n;
+      for (int64_t i = 0; i <= n; ++i) {
+         volatile double p = rx * (double)i; // keep mul and add separately rounded (no contraction)
+         xe[(size_t)i] = xmin + p;
+      }
+      scale = "linear";
+      compute(xe, nm);
+   }
+ private:
+   void compute(const std::vector<double> &xe, const std::string &nm) { // grids.f90:232-250
+      ncells = (int64_t)xe.size() - 1;
+      edges = xe;
+      center.resize((size_t)ncells);
+      width.resize((size_t)ncells);
+      for (int64_t i = 0; i < ncells; ++i) {
+         center[(size_t)i] = (edges[(size_t)i] + edges[(size_t)i + 1]) / 2;
+         width[(size_t)i] = edges[(size_t)i + 1] - edges[(size_t)i];
+      }
+      name = nm;
+   }
+};
+} // namespace hrweno_grids
+
+namespace hrweno_weno {
+class weno { // weno.f90:23-50
+ public:
+   std::string msg;
+   int ierr = 0;
+   int64_t ncells = 0;
+   int k = 3;
+   double eps = 1e-6;
+   weno() = default;
+   weno(int64_t ncells_, int k_ = 3, double eps_ = 1e-6, const std::vector<double> *xedges = nullptr) { // weno_init, :54-127
+      if (xedges && (int64_t)xedges->size() != ncells_ + 1) fail("Invalid input 'xedges': size(xedges) /= ncells + 1.");
+      const int st = hrweno_weno_create(&h_, ncells_, k_, eps_, xedges ? xedges->data() : nullptr);
+      if (st != HRWENO_OK) fail(hrweno_last_error(), st);
+      ncells = ncells_;
+      k = k_;
+      eps = eps_;
+   }
+   weno(weno &&o) noexcept { *this = std::move(o); }
+   weno &operator=(weno &&o) noexcept { // `myweno = weno(...)` (example1:44) -- move of the function result
+      if (this != &o) {
+         hrweno_weno_destroy(h_);
+         h_ = o.h_;
+         o.h_ = nullptr;
+         msg = o.msg; ierr = o.ierr; ncells = o.ncells; k = o.k; eps = o.eps;
+      }
+      return *this;
+   }
+   weno(const weno &) = delete;
+   weno &operator=(const weno &) = delete;
+   ~weno() { hrweno_weno_destroy(h_); }
+   // call w%reconstruct(v, vl, vr)  (weno.f90:129-219)
+   void reconstruct(const double *v, double *vl, double *vr) const { hrweno::check(hrweno_weno_reconstruct(h_, v, vl, vr)); }
+   // strided section v(i::inc) (example2:107)
+   void reconstruct(const double *v, int64_t inc, double *vl, double *vr) const {
+      hrweno::check(hrweno_weno_reconstruct_batch(h_, 1, v, 0, inc, vl, vr, ncells));
+   }
+   std::vector<double> cnu() const { // cnu(0:k-1,-1:k-1,1:ncells), weno.f90:41
+      std::vector<double> c((size_t)(k * (k + 1) * ncells));
+      hrweno::check(hrweno_weno_get_cnu(h_, c.data()));
+      return c;
+   }
+   const ::hrweno_weno *handle() const { return h_; }
+ private:
+   ::hrweno_weno *h_ = nullptr;
+   [[noreturn]] void fail(const std::string &m, int st = HRWENO_EINVAL) {
+      msg = m;
+      ierr = 1;
+      throw hrweno::error(st, m);
+   }
+};
+} // namespace hrweno_weno
+
+namespace hrweno_fluxes {
+using flux = std::function<double(double u, const std::vector<double> &x, double t)>; // fluxes.f90:12-18
+namespace detail {
+struct Ctx { const flux *f; };
+inline double tramp(void *ctx, double u, const double *x, int nx, double t) {
+   return (*static_cast<Ctx *>(ctx)->f)(u, std::vector<double>(x, x + nx), t);
+}
+} // namespace detail
+inline double lax_friedrichs(const flux &f, double vm, double vp, const std::vector<double> &x, double t, double alpha) {
+   detail::Ctx c{&f};
+   return hrweno_lax_friedrichs(detail::tramp, &c, vm, vp, x.data(), (int)x.size(), t, alpha); // fluxes.f90:22-45
+}
+inline double godunov(const flux &f, double vm, double vp, const std::vector<double> &x, double t) {
+   detail::Ctx c{&f};
+   return hrweno_godunov(detail::tramp, &c, vm, vp, x.data(), (int)x.size(), t); // fluxes.f90:47-76
+}
+} // namespace hrweno_fluxes
+
+namespace hrweno_fv {
+// the example `rhs` as one fused device operator (example1:72-109, example2:73-129)
+class fv {
+ public:
+   explicit fv(const hrweno_fv_desc &d) { hrweno::check(hrweno_fv_create(&h_, &d)); }
+   fv(const fv &) = delete;
+   fv &operator=(const fv &) = delete;
+   ~fv() { hrweno_fv_destroy(h_); }
+   int64_t neq() const { return hrweno_fv_neq(h_); }
+   void rhs(double t, const double *v, double *vdot) { hrweno::check(hrweno_fv_rhs(h_, t, v, vdot)); }
+   ::hrweno_fv *handle() const { return h_; }
+   static hrweno_fv_desc desc1d(int64_t nc, int k, double eps, const double *width) {
+      hrweno_fv_desc d{};
+      d.abi_version = HRWENO_ABI_VERSION;
+      d.ndim = 1; d.n[0] = nc; d.n[1] = 1; d.rows = 1; d.k = k; d.eps = eps;
+      d.flux_model = HRWENO_FLUX_BURGERS; d.flux_scheme = HRWENO_SCHEME_GODUNOV; d.bc = HRWENO_BC_COPY_NEIGHBOUR;
+      d.grid_kind = HRWENO_GRID_WIDTH_ARRAY; d.mode = HRWENO_MODE_STRICT; d.flux_coef[0] = d.flux_coef[1] = 1.0; d.alpha = 1.0;
+      d.width[0] = width; d.nranks = 1;
+      return d;
+   }
+   static hrweno_fv_desc desc2d(int64_t nc1, int64_t nc2, int k, double eps, const double *w1, const double *w2) {
+      hrweno_fv_desc d = desc1d(nc1, k, eps, w1);
+      d.ndim = 2; d.n[1] = nc2; d.width[1] = w2;
+      d.flux_model = HRWENO_FLUX_LINEAR; d.bc = HRWENO_BC_ZERO_FLUX;
+      return d;
+   }
+ private:
+   ::hrweno_fv *h_ = nullptr;
+};
+} // namespace hrweno_fv
+
+namespace hrweno_tvdode {
+// integrand(t, u(:), udot(:)) with device-resident u/udot (tvdode.f90:50-57)
+using integrand = std::function<void(double t, int64_t neq, const double *u_dev, double *udot_dev, void *stream)>;
+
+class tvdode { // tvdode.f90:14-34
+ public:
+   std::string msg;
+   int64_t neq() const { return hrweno_ode_neq(h_); }
+   int order() const { return hrweno_ode_order(h_); }
+   int64_t fevals() const { return hrweno_ode_fevals(h_); }
+   int istate() const { return h_ ? hrweno_ode_istate(h_) : -1; }
+   tvdode(const tvdode &) = delete;
+   tvdode &operator=(const tvdode &) = delete;
+   virtual ~tvdode() { hrweno_ode_destroy(h_); }
+ protected:
+   tvdode() = default;
+   hrweno_ode *h_ = nullptr;
+   integrand fu_;
+   static void tramp(void *ctx, double t, int64_t n, const double *u, double *udot, void *stream) {
+      static_cast<tvdode *>(ctx)->fu_(t, n, u, udot, stream);
+   }
+   void created(int st) {
+      if (st != HRWENO_OK) {
+         msg = hrweno_last_error(); // error_msg: istate = -1 then error stop (tvdode.f90:286-297)
+         throw hrweno::error(st, msg);
+      }
+   }
+};
+
+class rktvd : public tvdode { // rktvd(fu, neq, order), tvdode.f90:69-95
+ public:
+   rktvd(integrand fu, int64_t neq, int order) {
+      fu_ = std::move(fu);
+      created(hrweno_rktvd_create(&h_, &tvdode::tramp, this, neq, order));
+   }
+   rktvd(hrweno_fv::fv &rhs, int64_t neq, int order) { // fused path: rhs + stage combination in one kernel
+      if (neq != rhs.neq()) throw hrweno::error(HRWENO_EINVAL, "neq does not match the finite-volume operator");
+      created(hrweno_rktvd_create_fused(&h_, rhs.handle(), order));
+   }
+   // call ode%integrate(u, t, tout, dt [, itask])  (tvdode.f90:97-178)
+   void integrate(double *u, double &t, double tout, double dt, int itask = 1) {
+      hrweno::check(hrweno_ode_integrate(h_, u, &t, tout, dt, itask));
+   }
+};
+
+class mstvd : public tvdode { // mstvd(fu, neq), tvdode.f90:180-201
+ public:
+   mstvd(integrand fu, int64_t neq) {
+      fu_ = std::move(fu);
+      created(hrweno_mstvd_create(&h_, &tvdode::tramp, this, neq));
+   }
+   mstvd(hrweno_fv::fv &rhs, int64_t neq) {
+      if (neq != rhs.neq()) throw hrweno::error(HRWENO_EINVAL, "neq does not match the finite-volume operator");
+      created(hrweno_mstvd_create_fused(&h_, rhs.handle()));
+   }
+   void integrate(double *u, double &t, double tout, double dt) { // tvdode.f90:203-271
+      hrweno::check(hrweno_ode_integrate(h_, u, &t, tout, dt, 1));
+   }
+};
+} // namespace hrweno_tvdode
+} // namespace hrweno
