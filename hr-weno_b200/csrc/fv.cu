@@ -192,7 +192,17 @@ constexpr int R1 = 4, NT1 = 256;
 
 template <int K, int COMBINE, class M>
 static void launch1d(const Fv1dGeom &g, const StageArgs &a, int64_t rows, cudaStream_t st) {
-   const int64_t blocks = rows * g.tiles_per_row;
+   // persistent grid: SMs x resident CTAs of this instantiation (queried once), never more than there are tiles
+   static int resident = 0;
+   if (resident == 0) {
+      int dev = 0, sms = 0, per_sm = 0;
+      cudaGetDevice(&dev);
+      cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+      cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, fv1d_stage_kernel<K, COMBINE, M, R1, NT1>, NT1, 0);
+      resident = (sms > 0 ? sms : 148) * (per_sm > 0 ? per_sm : 1);
+   }
+   int64_t blocks = rows * g.tiles_per_row;
+   if (blocks > resident) blocks = resident;
    fv1d_stage_kernel<K, COMBINE, M, R1, NT1><<<(unsigned)blocks, NT1, 0, st>>>(g, a);
 }
 
@@ -229,6 +239,7 @@ int fv_stage(Fv *fv, int combine, const StageArgs &args, cudaStream_t st) {
    g.n = fv->n0;
    g.ld = fv->pitch;
    g.tiles_per_row = (fv->n0 + (NT1 - 2) * R1 - 1) / ((NT1 - 2) * R1);
+   g.rows = fv->rows;
    g.width = fv->d_width[0];
    g.xmin = d.xmin;
    g.rx = fv->rx;

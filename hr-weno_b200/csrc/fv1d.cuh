@@ -22,6 +22,7 @@ struct Fv1dGeom {
    int64_t n;             // cells per row
    int64_t ld;            // padded row pitch of vin / a / b / out2
    int64_t tiles_per_row;
+   int64_t rows;          // independent rows (batched ensemble)
    const double *width;   // GRID_WIDTH_ARRAY: device array (padded to a multiple of 4, >= n+4)
    double xmin, rx;       // GRID_LINEAR
    int64_t goff;          // global index of local cell 0 (slab decomposition)
@@ -32,182 +33,240 @@ struct Fv1dGeom {
    int phys_left, phys_right; // the row ends are physical boundaries (not slab interfaces)
 };
 
+// ---- TMA bulk copy + mbarrier (PTX; SASS: UBLKCP / SYNCS) ----------------------------------------------
+__device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void mbar_init(unsigned long long *bar, int count) {
+   asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
+}
+__device__ __forceinline__ void mbar_expect_tx(unsigned long long *bar, uint32_t bytes) {
+   asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(unsigned long long *bar, uint32_t parity) {
+   uint32_t done;
+   do {
+      asm volatile(
+         "{\n"
+         ".reg .pred p;\n"
+         "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n"
+         "selp.u32 %0, 1, 0, p;\n"
+         "}\n"
+         : "=r"(done)
+         : "r"(smem_u32(bar)), "r"(parity)
+         : "memory");
+   } while (!done);
+}
+// global -> shared bulk copy of `bytes` (multiple of 16, both addresses 16-B aligned), completion on `bar`
+__device__ __forceinline__ void tma_bulk_g2s(void *dst_smem, const void *src_gmem, uint32_t bytes, unsigned long long *bar) {
+   asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(smem_u32(dst_smem)),
+                "l"(src_gmem), "r"(bytes), "r"(smem_u32(bar))
+                : "memory");
+}
+
+// Persistent kernel: grid = SMs x resident CTAs; every CTA walks tiles blockIdx.x, +gridDim.x, ...  The tile of
+// iteration i+1 is fetched by one TMA bulk copy into the other shared-memory buffer while iteration i computes.
 template <int K, int COMBINE, class M, int R, int NT>
 __global__ void __launch_bounds__(NT) fv1d_stage_kernel(const Fv1dGeom g, const StageArgs s) {
    constexpr int P = 4;              // tile halo in shared memory (>= K-1, keeps 32-B alignment)
-   constexpr int TILE = (NT - 2) * R; // cells written per CTA
+   constexpr int TILE = (NT - 2) * R; // cells written per CTA and tile
    constexpr int SM_N = NT * R + 2 * P;
    constexpr int WN = R + 4;         // aligned register window (superset for K < 3)
-   __shared__ __align__(16) double s_v[SM_N];
-   __shared__ double s_vr[NT];
-   __shared__ double s_vl[NT];
+   __shared__ __align__(128) double s_v[2][SM_N];
+   __shared__ double s_vr[2][NT];
+   __shared__ double s_vl[2][NT];
+   __shared__ __align__(8) unsigned long long s_bar[2];
 
    const int tid = threadIdx.x;
-   const int64_t row = blockIdx.x / g.tiles_per_row;
-   const int64_t tile = blockIdx.x - row * g.tiles_per_row;
-   const int64_t c0 = tile * TILE;
-   const int64_t i0 = c0 + (int64_t)(tid - 1) * R; // first owned cell (thread 0: the run left of the tile)
-   const double *vrow = s.vin + row * g.ld;
-   const bool active = tid >= 1 && tid <= NT - 2 && i0 < g.n;
-   const bool full = i0 + R <= g.n;
+   const int64_t total_tiles = g.tiles_per_row * g.rows;
 
-   // pointwise operands: issue the global loads before waiting on the tile
-   double av[R], bv[R];
-   if (COMBINE == C_RK2_FINAL || COMBINE == C_RK3_S2 || COMBINE == C_RK3_S3 || COMBINE == C_MS) {
-      if (active) {
-         const double *ap = s.a + row * g.ld + i0;
-         if (full) {
-#pragma unroll
-            for (int j = 0; j < R; j += 2) {
-               const double2 t = __ldg(reinterpret_cast<const double2 *>(ap + j));
-               av[j] = t.x;
-               av[j + 1] = t.y;
-            }
-         } else {
-#pragma unroll
-            for (int j = 0; j < R; ++j) av[j] = (i0 + j < g.n) ? ap[j] : 0.0;
-         }
-         if (COMBINE == C_MS) {
-            const double *bp = s.b + row * g.ld + i0;
+   // one elected thread issues the bulk copy of a tile: cells [c0-R-P, c0-R-P+SM_N) clipped to the padded row
+   auto issue = [&](int64_t tile_id, int buf) {
+      const int64_t row = tile_id / g.tiles_per_row;
+      const int64_t c0 = (tile_id - row * g.tiles_per_row) * TILE;
+      const int64_t ts = c0 - R - P;
+      const int64_t lo = ts < -PAD ? (int64_t)-PAD : ts;
+      int64_t hi = ts + SM_N;
+      if (hi > g.ld - PAD) hi = g.ld - PAD;
+      const uint32_t bytes = (uint32_t)((hi - lo) * (int64_t)sizeof(double));
+      mbar_expect_tx(&s_bar[buf], bytes);
+      tma_bulk_g2s(&s_v[buf][lo - ts], s.vin + row * g.ld + lo, bytes, &s_bar[buf]);
+   };
+
+   for (int idx = tid; idx < 2 * SM_N; idx += NT) (&s_v[0][0])[idx] = 0.0; // parts a clipped copy never writes
+   asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); // order the generic-proxy zero fill before async-proxy writes
+   if (tid == 0) {
+      mbar_init(&s_bar[0], 1);
+      mbar_init(&s_bar[1], 1);
+      asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+   }
+   __syncthreads();
+   if (tid == 0 && (int64_t)blockIdx.x < total_tiles) issue(blockIdx.x, 0);
+
+   int it = 0;
+   for (int64_t tile_id = blockIdx.x; tile_id < total_tiles; tile_id += gridDim.x, ++it) {
+      const int buf = it & 1;
+      // prefetch the next tile into the other buffer: every thread finished reading it before the exchange
+      // barrier of the previous iteration, which this thread has passed
+      if (tid == 0 && tile_id + gridDim.x < total_tiles) issue(tile_id + gridDim.x, buf ^ 1);
+
+      const int64_t row = tile_id / g.tiles_per_row;
+      const int64_t c0 = (tile_id - row * g.tiles_per_row) * TILE;
+      const int64_t i0 = c0 + (int64_t)(tid - 1) * R; // first owned cell (thread 0: the run left of the tile)
+      const bool active = tid >= 1 && tid <= NT - 2 && i0 < g.n;
+      const bool full = i0 + R <= g.n;
+
+      // pointwise operands: issue the global loads before waiting on the tile
+      double av[R], bv[R];
+      if (COMBINE == C_RK2_FINAL || COMBINE == C_RK3_S2 || COMBINE == C_RK3_S3 || COMBINE == C_MS) {
+         if (active) {
+            const double *ap = s.a + row * g.ld + i0;
             if (full) {
 #pragma unroll
                for (int j = 0; j < R; j += 2) {
-                  const double2 t = __ldg(reinterpret_cast<const double2 *>(bp + j));
-                  bv[j] = t.x;
-                  bv[j + 1] = t.y;
+                  const double2 t = __ldg(reinterpret_cast<const double2 *>(ap + j));
+                  av[j] = t.x;
+                  av[j + 1] = t.y;
                }
             } else {
 #pragma unroll
-               for (int j = 0; j < R; ++j) bv[j] = (i0 + j < g.n) ? bp[j] : 0.0;
+               for (int j = 0; j < R; ++j) av[j] = (i0 + j < g.n) ? ap[j] : 0.0;
+            }
+            if (COMBINE == C_MS) {
+               const double *bp = s.b + row * g.ld + i0;
+               if (full) {
+#pragma unroll
+                  for (int j = 0; j < R; j += 2) {
+                     const double2 t = __ldg(reinterpret_cast<const double2 *>(bp + j));
+                     bv[j] = t.x;
+                     bv[j + 1] = t.y;
+                  }
+               } else {
+#pragma unroll
+                  for (int j = 0; j < R; ++j) bv[j] = (i0 + j < g.n) ? bp[j] : 0.0;
+               }
             }
          }
       }
-   }
 
-   // stage the tile: cells [c0-R-P, c0-R-P+SM_N) of the padded row
-   const int64_t ts = c0 - R - P;
-   for (int idx = 2 * tid; idx < SM_N; idx += 2 * NT) {
-      const int64_t gi = ts + idx;
-      double2 t = make_double2(0.0, 0.0);
-      if (gi >= -PAD && gi + 1 < g.n + PAD) t = *reinterpret_cast<const double2 *>(vrow + gi);
-      *reinterpret_cast<double2 *>(&s_v[idx]) = t;
-   }
-   __syncthreads();
+      mbar_wait(&s_bar[buf], (uint32_t)((it >> 1) & 1));
 
-   // register window: cells i0-2 .. i0+R+1
-   double w[WN];
+      // register window: cells i0-2 .. i0+R+1
+      double w[WN];
 #pragma unroll
-   for (int j = 0; j < WN; j += 2) {
-      const double2 t = *reinterpret_cast<const double2 *>(&s_v[tid * R + P - 2 + j]);
-      w[j] = t.x;
-      w[j + 1] = t.y;
-   }
-   double vl[R], vr[R];
-   weno_run<K, R, M>(w + (2 - (K - 1)), g.eps, vl, vr);
-
-   s_vr[tid] = vr[R - 1];
-   s_vl[tid] = vl[0];
-   __syncthreads();
-   if (!active) return;
-   const double vr_left = s_vr[tid - 1];
-   const double vl_right = s_vl[tid + 1];
-
-   // numerical flux at the R+1 faces i0 .. i0+R (face f lies between cells f-1 and f)
-   double F[R + 1];
-   F[0] = face_flux<M>(g.flux, vr_left, vl[0]);
-#pragma unroll
-   for (int j = 1; j < R; ++j) F[j] = face_flux<M>(g.flux, vr[j - 1], vl[j]);
-   F[R] = face_flux<M>(g.flux, vr[R - 1], vl_right);
-   // problem-specific constraints at the domain boundaries (example1:103-104, example2:117-120)
-   const bool copy = g.bc == HRWENO_BC_COPY_NEIGHBOUR;
-   if (g.phys_left && i0 == 0) F[0] = copy ? F[1] : 0.0;
-   if (g.phys_right) {
-#pragma unroll
-      for (int j = 1; j <= R; ++j)
-         if (i0 + j == g.n) F[j] = copy ? F[j - 1] : 0.0;
-   }
-
-   // cell widths
-   double wd[R];
-   if (g.grid_kind == HRWENO_GRID_LINEAR) {
-      // grids.f90:76-79,247: edges(i) = xmin + rx*i ; width = edges(i) - edges(i-1)
-      const double base = (double)(g.goff + i0);
-      double el = M::add(g.xmin, M::mul(g.rx, base));
-#pragma unroll
-      for (int j = 0; j < R; ++j) {
-         const double er = M::add(g.xmin, M::mul(g.rx, base + (double)(j + 1)));
-         wd[j] = M::sub(er, el);
-         el = er;
+      for (int j = 0; j < WN; j += 2) {
+         const double2 t = *reinterpret_cast<const double2 *>(&s_v[buf][tid * R + P - 2 + j]);
+         w[j] = t.x;
+         w[j + 1] = t.y;
       }
-   } else {
-#pragma unroll
-      for (int j = 0; j < R; j += 2) {
-         const double2 t = __ldg(reinterpret_cast<const double2 *>(g.width + i0 + j));
-         wd[j] = t.x;
-         wd[j + 1] = t.y;
-      }
-   }
+      double vl[R], vr[R];
+      weno_run<K, R, M>(w + (2 - (K - 1)), g.eps, vl, vr);
 
-   double res[R], lres[R];
-#pragma unroll
-   for (int j = 0; j < R; ++j) {
-      // vdot = -(fedges(i) - fedges(i-1))/width   (example1:107)
-      const double L = -M::div(M::sub(F[j + 1], F[j]), wd[j]);
-      const double v = w[2 + j];
-      double o;
-      if (COMBINE == C_RHS) {
-         o = L;
-      } else if (COMBINE == C_EULER) {
-         o = M::add(v, M::mul(s.c0, L)); // u + dt*udot
-      } else if (COMBINE == C_RK2_FINAL) {
-         o = M::mul(M::add(M::add(av[j], v), M::mul(s.c0, L)), 0.5); // (u + ui + dt*udot)/2
-      } else if (COMBINE == C_RK3_S2) {
-         o = M::mul(M::add(M::add(M::mul(3.0, av[j]), v), M::mul(s.c0, L)), 0.25); // (3*u + ui + dt*udot)/4
-      } else if (COMBINE == C_RK3_S3) {
-         // (u + 2*ui + 2*dt*udot)/3 ; 2*ui is exact
-         o = M::div(M::add(M::fma_exact(2.0, v, av[j]), M::mul(s.c0, L)), 3.0);
-      } else {
-         // (25*u + 50*dt*udot + 7*uold(:,4) + 10*dt*udotold(:,4))/32 ; /32 is exact
-         o = M::mul(M::add(M::add(M::add(M::mul(25.0, v), M::mul(s.c0, L)), M::mul(7.0, av[j])), M::mul(s.c1, bv[j])),
-                    0.03125);
-         lres[j] = L;
-      }
-      res[j] = o;
-   }
+      // exchange arrays are double buffered by iteration parity: a slot is rewritten two iterations later, after
+      // the barrier of the iteration in between, which every reader of the old value has passed
+      s_vr[buf][tid] = vr[R - 1];
+      s_vl[buf][tid] = vl[0];
+      __syncthreads();
+      if (!active) continue;
+      const double vr_left = s_vr[buf][tid - 1];
+      const double vl_right = s_vl[buf][tid + 1];
 
-   double *orow = s.out + row * s.ld_out + i0;
-   if (full && !s.out_dense) {
+      // numerical flux at the R+1 faces i0 .. i0+R (face f lies between cells f-1 and f)
+      double F[R + 1];
+      F[0] = face_flux<M>(g.flux, vr_left, vl[0]);
 #pragma unroll
-      for (int j = 0; j < R; j += 2) *reinterpret_cast<double2 *>(orow + j) = make_double2(res[j], res[j + 1]);
-   } else {
-#pragma unroll
-      for (int j = 0; j < R; ++j)
-         if (i0 + j < g.n) orow[j] = res[j];
-   }
-   if (COMBINE == C_MS) {
-      double *lrow = s.out2 + row * g.ld + i0;
-      if (full) {
-#pragma unroll
-         for (int j = 0; j < R; j += 2) *reinterpret_cast<double2 *>(lrow + j) = make_double2(lres[j], lres[j + 1]);
-      } else {
-#pragma unroll
-         for (int j = 0; j < R; ++j)
-            if (i0 + j < g.n) lrow[j] = lres[j];
-      }
-   }
-   // ghost cells of the result at physical boundaries: edge replicas (weno.f90:172-173)
-   if (!s.out_dense && COMBINE != C_RHS) {
-      if (g.phys_left && i0 == 0) {
-#pragma unroll
-         for (int q = 1; q <= K; ++q) orow[-q] = res[0];
-      }
+      for (int j = 1; j < R; ++j) F[j] = face_flux<M>(g.flux, vr[j - 1], vl[j]);
+      F[R] = face_flux<M>(g.flux, vr[R - 1], vl_right);
+      // problem-specific constraints at the domain boundaries (example1:103-104, example2:117-120)
+      const bool copy = g.bc == HRWENO_BC_COPY_NEIGHBOUR;
+      if (g.phys_left && i0 == 0) F[0] = copy ? F[1] : 0.0;
       if (g.phys_right) {
 #pragma unroll
-         for (int j = 0; j < R; ++j)
-            if (i0 + j == g.n - 1) {
+         for (int j = 1; j <= R; ++j)
+            if (i0 + j == g.n) F[j] = copy ? F[j - 1] : 0.0;
+      }
+
+      // cell widths
+      double wd[R];
+      if (g.grid_kind == HRWENO_GRID_LINEAR) {
+         // grids.f90:76-79,247: edges(i) = xmin + rx*i ; width = edges(i) - edges(i-1)
+         const double base = (double)(g.goff + i0);
+         double el = M::add(g.xmin, M::mul(g.rx, base));
 #pragma unroll
-               for (int q = 1; q <= K; ++q) orow[j + q] = res[j];
-            }
+         for (int j = 0; j < R; ++j) {
+            const double er = M::add(g.xmin, M::mul(g.rx, base + (double)(j + 1)));
+            wd[j] = M::sub(er, el);
+            el = er;
+         }
+      } else {
+#pragma unroll
+         for (int j = 0; j < R; j += 2) {
+            const double2 t = __ldg(reinterpret_cast<const double2 *>(g.width + i0 + j));
+            wd[j] = t.x;
+            wd[j + 1] = t.y;
+         }
+      }
+
+      double res[R], lres[R];
+#pragma unroll
+      for (int j = 0; j < R; ++j) {
+         // vdot = -(fedges(i) - fedges(i-1))/width   (example1:107)
+         const double L = -M::div(M::sub(F[j + 1], F[j]), wd[j]);
+         const double v = w[2 + j];
+         double o;
+         if (COMBINE == C_RHS) {
+            o = L;
+         } else if (COMBINE == C_EULER) {
+            o = M::add(v, M::mul(s.c0, L)); // u + dt*udot
+         } else if (COMBINE == C_RK2_FINAL) {
+            o = M::mul(M::add(M::add(av[j], v), M::mul(s.c0, L)), 0.5); // (u + ui + dt*udot)/2
+         } else if (COMBINE == C_RK3_S2) {
+            o = M::mul(M::add(M::add(M::mul(3.0, av[j]), v), M::mul(s.c0, L)), 0.25); // (3*u + ui + dt*udot)/4
+         } else if (COMBINE == C_RK3_S3) {
+            // (u + 2*ui + 2*dt*udot)/3 ; 2*ui is exact
+            o = div3<M>(M::add(M::fma_exact(2.0, v, av[j]), M::mul(s.c0, L)));
+         } else {
+            // (25*u + 50*dt*udot + 7*uold(:,4) + 10*dt*udotold(:,4))/32 ; /32 is exact
+            o = M::mul(M::add(M::add(M::add(M::mul(25.0, v), M::mul(s.c0, L)), M::mul(7.0, av[j])), M::mul(s.c1, bv[j])),
+                       0.03125);
+            lres[j] = L;
+         }
+         res[j] = o;
+      }
+
+      double *orow = s.out + row * s.ld_out + i0;
+      if (full && !s.out_dense) {
+#pragma unroll
+         for (int j = 0; j < R; j += 2) *reinterpret_cast<double2 *>(orow + j) = make_double2(res[j], res[j + 1]);
+      } else {
+#pragma unroll
+         for (int j = 0; j < R; ++j)
+            if (i0 + j < g.n) orow[j] = res[j];
+      }
+      if (COMBINE == C_MS) {
+         double *lrow = s.out2 + row * g.ld + i0;
+         if (full) {
+#pragma unroll
+            for (int j = 0; j < R; j += 2) *reinterpret_cast<double2 *>(lrow + j) = make_double2(lres[j], lres[j + 1]);
+         } else {
+#pragma unroll
+            for (int j = 0; j < R; ++j)
+               if (i0 + j < g.n) lrow[j] = lres[j];
+         }
+      }
+      // ghost cells of the result at physical boundaries: edge replicas (weno.f90:172-173)
+      if (!s.out_dense && COMBINE != C_RHS) {
+         if (g.phys_left && i0 == 0) {
+#pragma unroll
+            for (int q = 1; q <= K; ++q) orow[-q] = res[0];
+         }
+         if (g.phys_right) {
+#pragma unroll
+            for (int j = 0; j < R; ++j)
+               if (i0 + j == g.n - 1) {
+#pragma unroll
+                  for (int q = 1; q <= K; ++q) orow[j + q] = res[j];
+               }
+         }
       }
    }
 }

@@ -22,6 +22,28 @@ struct Window {
    static constexpr int N = R + 2 * G;   // window length
 };
 
+// fallbacks with the compiler's own division (taken only when an exact_div range check fails: operands
+// near the overflow/underflow thresholds); same formulas as the strict branches below.
+static __device__ __noinline__ void weno_weights_slow_k2(double den0, double den1, double vrr0, double vrr1, double vlr0,
+                                                  double vlr1, double &vl, double &vr) {
+   const double d0 = 2.0 / 3, d1 = 1.0 / 3;
+   const double al0 = __ddiv_rn(d0, den0), al1 = __ddiv_rn(d1, den1);
+   const double at0 = __ddiv_rn(d1, den0), at1 = __ddiv_rn(d0, den1);
+   const double s = __dadd_rn(al0, al1), st = __dadd_rn(at0, at1);
+   vr = __dadd_rn(__dmul_rn(__ddiv_rn(al0, s), vrr0), __dmul_rn(__ddiv_rn(al1, s), vrr1));
+   vl = __dadd_rn(__dmul_rn(__ddiv_rn(at0, st), vlr0), __dmul_rn(__ddiv_rn(at1, st), vlr1));
+}
+
+static __device__ __noinline__ void weno_weights_slow_k3(double den0, double den1, double den2, double vrr0, double vrr1,
+                                                  double vrr2, double vlr0, double vlr1, double vlr2, double &vl, double &vr) {
+   const double al0 = __ddiv_rn(0.3, den0), al1 = __ddiv_rn(0.6, den1), al2 = __ddiv_rn(0.1, den2);
+   const double at0 = __ddiv_rn(0.1, den0), at2 = __ddiv_rn(0.3, den2);
+   const double s = __dadd_rn(__dadd_rn(al0, al1), al2);
+   const double st = __dadd_rn(__dadd_rn(at0, al1), at2);
+   vr = __dadd_rn(__dadd_rn(__dmul_rn(__ddiv_rn(al0, s), vrr0), __dmul_rn(__ddiv_rn(al1, s), vrr1)), __dmul_rn(__ddiv_rn(al2, s), vrr2));
+   vl = __dadd_rn(__dadd_rn(__dmul_rn(__ddiv_rn(at0, st), vlr0), __dmul_rn(__ddiv_rn(al1, st), vlr1)), __dmul_rn(__ddiv_rn(at2, st), vlr2));
+}
+
 // ---------------------------------------------------------------------------------------- k = 1
 template <int R, class M>
 __device__ __forceinline__ void weno_run_k1(const double *w, double, double *vl, double *vr) {
@@ -64,11 +86,15 @@ __device__ __forceinline__ void weno_run_k2(const double *w, double eps, double 
       const double e0 = M::add(eps, dsq[c]), e1 = M::add(eps, dsq[c - 1]);
       const double den0 = M::mul(e0, e0), den1 = M::mul(e1, e1);
       if constexpr (M::strict) {
-         const double al0 = M::div(d0, den0), al1 = M::div(d1, den1);
-         const double at0 = M::div(d1, den0), at1 = M::div(d0, den1);
+         bool ok = true;
+         const double r0 = exact_recip(den0), r1 = exact_recip(den1);
+         const double al0 = exact_div(d0, den0, r0, ok), al1 = exact_div(d1, den1, r1, ok);
+         const double at0 = exact_div(d1, den0, r0, ok), at1 = exact_div(d0, den1, r1, ok);
          const double s = M::add(al0, al1), st = M::add(at0, at1);
-         vr[j] = M::add(M::mul(M::div(al0, s), vrr0), M::mul(M::div(al1, s), vrr1));
-         vl[j] = M::add(M::mul(M::div(at0, st), vlr0), M::mul(M::div(at1, st), vlr1));
+         const double rs = exact_recip(s), rst = exact_recip(st);
+         vr[j] = M::add(M::mul(exact_div(al0, s, rs, ok), vrr0), M::mul(exact_div(al1, s, rs, ok), vrr1));
+         vl[j] = M::add(M::mul(exact_div(at0, st, rst, ok), vlr0), M::mul(exact_div(at1, st, rst, ok), vlr1));
+         if (!ok) weno_weights_slow_k2(den0, den1, vrr0, vrr1, vlr0, vlr1, vl[j], vr[j]);
       } else {
          // alfa_r ~ d_r * prod_{s != r} den_s ; one reciprocal per side
          const double al0 = d0 * den1, al1 = d1 * den0;
@@ -129,13 +155,20 @@ __device__ __forceinline__ void weno_run_k3(const double *w, double eps, double 
       const double den0 = M::mul(e0, e0), den1 = M::mul(e1, e1), den2 = M::mul(e2, e2);
       if constexpr (M::strict) {
          // alfa = d/(eps+beta)**2, alfatilde = d(k-1:0:-1)/(eps+beta)**2   (weno.f90:207-208), d3 = [0.3,0.6,0.1]
-         const double al0 = M::div(0.3, den0), al1 = M::div(0.6, den1), al2 = M::div(0.1, den2);
-         const double at0 = M::div(0.1, den0), at2 = M::div(0.3, den2); // at1 == al1
+         // IEEE quotients with the reciprocal refinement shared per denominator (common.cuh: exact_div)
+         bool ok = true;
+         const double r0 = exact_recip(den0), r1 = exact_recip(den1), r2 = exact_recip(den2);
+         const double al0 = exact_div(0.3, den0, r0, ok), al1 = exact_div(0.6, den1, r1, ok), al2 = exact_div(0.1, den2, r2, ok);
+         const double at0 = exact_div(0.1, den0, r0, ok), at2 = exact_div(0.3, den2, r2, ok); // at1 == al1
          const double s = M::add(M::add(al0, al1), al2);
          const double st = M::add(M::add(at0, al1), at2);
+         const double rs = exact_recip(s), rst = exact_recip(st);
          // w = alfa/sum(alfa); vr = sum(w*vrr)   (weno.f90:209-214)
-         vr[j] = M::add(M::add(M::mul(M::div(al0, s), vrr0), M::mul(M::div(al1, s), vrr1)), M::mul(M::div(al2, s), vrr2));
-         vl[j] = M::add(M::add(M::mul(M::div(at0, st), vlr0), M::mul(M::div(al1, st), vlr1)), M::mul(M::div(at2, st), vlr2));
+         vr[j] = M::add(M::add(M::mul(exact_div(al0, s, rs, ok), vrr0), M::mul(exact_div(al1, s, rs, ok), vrr1)),
+                        M::mul(exact_div(al2, s, rs, ok), vrr2));
+         vl[j] = M::add(M::add(M::mul(exact_div(at0, st, rst, ok), vlr0), M::mul(exact_div(al1, st, rst, ok), vlr1)),
+                        M::mul(exact_div(at2, st, rst, ok), vlr2));
+         if (!ok) weno_weights_slow_k3(den0, den1, den2, vrr0, vrr1, vrr2, vlr0, vlr1, vlr2, vl[j], vr[j]);
       } else {
          // division-light weights: alfa_r ~ d_r * prod_{s != r} den_s, one reciprocal per side
          const double p0 = den1 * den2, p1 = den0 * den2, p2 = den0 * den1;
