@@ -10,7 +10,7 @@ import os
 
 PKG_DIR = os.path.dirname(os.path.abspath(__file__))
 REPO_ROOT = os.path.dirname(PKG_DIR)
-LIB_PATH = os.path.join(PKG_DIR, "lib", "libhrweno_b200.so")
+LIB_PATH = os.environ.get("HRWENO_B200_LIB") or os.path.join(PKG_DIR, "lib", "libhrweno_b200.so")  # override: tuning variants
 
 ABI_VERSION = 1
 OK, EINVAL, ECUDA, ENOMEM, ESTATE, ECOMM = range(6)

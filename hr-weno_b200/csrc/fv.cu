@@ -31,6 +31,8 @@ Fv::~Fv() {
    fv_halo_free(this);
    cudaFree(d_width[0]);
    cudaFree(d_width[1]);
+   cudaFree(d_wtab);
+   cudaFree(d_widx);
    cudaFree(d_scratch_in);
    cudaFree(d_scratch_out);
    if (stream) cudaStreamDestroy(stream);
@@ -42,6 +44,97 @@ static int upload_width(const double *host, int64_t n, double **dev) {
    HRW_CUDA(cudaMalloc(dev, tmp.size() * sizeof(double)));
    HRW_CUDA(cudaMemcpy(*dev, tmp.data(), tmp.size() * sizeof(double), cudaMemcpyHostToDevice));
    return HRWENO_OK;
+}
+
+// refined reciprocals of the dictionary widths, computed with the very sequence the kernels' divisions use
+__global__ void wtab_recip_kernel(double2 *tab, int count) {
+   const int i = threadIdx.x;
+   if (i < 256) {
+      double2 e = tab[i];
+      if (i >= count) e.x = 1.0;
+      e.y = exact_recip(e.x);
+      tab[i] = e;
+   }
+}
+
+// 1D widths.  The cell widths of the local slab -- grid1%linear's own arithmetic for GRID_LINEAR (grids.f90:76-79,247:
+// edges(i) = xmin + rx*i, width = edges(i) - edges(i-1), separately rounded) or the caller's array -- are deduplicated
+// into a dictionary when they take at most 256 distinct values (a linear grid takes a handful: the roundings of the
+// edges), else streamed as an array.
+static int setup_width_1d(Fv *fv, const hrweno_fv_desc *desc) {
+   const int64_t n = fv->n0;
+   std::vector<double> tab;
+   std::vector<unsigned char> idx((size_t)n + PAD, 0);
+   bool dict = true;
+   int last = 0;
+   double el = 0.0;
+   const bool linear = desc->grid_kind == HRWENO_GRID_LINEAR;
+   if (linear) {
+      fv->rx = (desc->xmax - desc->xmin) / (double)fv->d.global_n; // grids.f90:76
+      volatile double p = fv->rx * (double)fv->d.global_offset;
+      el = desc->xmin + p;
+   }
+   for (int64_t i = 0; i < n && dict; ++i) {
+      double wv;
+      if (linear) {
+         volatile double p = fv->rx * (double)(fv->d.global_offset + i + 1); // grids.f90:78 (mul and add rounded separately)
+         const double er = desc->xmin + p;
+         wv = er - el; // grids.f90:247
+         el = er;
+      } else {
+         wv = desc->width[0][i];
+      }
+      if (!(wv > 0x1p-200 && wv < 0x1p200)) { // outside the range the shared-reciprocal division is proven for
+         dict = false;
+         break;
+      }
+      int found = -1;
+      if (!tab.empty() && tab[(size_t)last] == wv) {
+         found = last;
+      } else {
+         for (size_t q = 0; q < tab.size(); ++q)
+            if (tab[q] == wv) {
+               found = (int)q;
+               break;
+            }
+      }
+      if (found < 0) {
+         if (tab.size() == 256) {
+            dict = false;
+            break;
+         }
+         tab.push_back(wv);
+         found = (int)tab.size() - 1;
+      }
+      last = found;
+      idx[(size_t)i] = (unsigned char)found;
+   }
+   if (dict) {
+      std::vector<double2> t2(256, make_double2(1.0, 1.0));
+      for (size_t q = 0; q < tab.size(); ++q) t2[q].x = tab[q];
+      HRW_CUDA(cudaMalloc(&fv->d_wtab, 256 * sizeof(double2)));
+      HRW_CUDA(cudaMemcpy(fv->d_wtab, t2.data(), 256 * sizeof(double2), cudaMemcpyHostToDevice));
+      wtab_recip_kernel<<<1, 256>>>(fv->d_wtab, (int)tab.size());
+      HRW_CUDA(cudaGetLastError());
+      HRW_CUDA(cudaMalloc(&fv->d_widx, idx.size()));
+      HRW_CUDA(cudaMemcpy(fv->d_widx, idx.data(), idx.size(), cudaMemcpyHostToDevice));
+      fv->width_dict = true;
+      return HRWENO_OK;
+   }
+   // array mode
+   if (linear) {
+      std::vector<double> wv((size_t)n);
+      volatile double p0 = fv->rx * (double)fv->d.global_offset;
+      double e0 = desc->xmin + p0;
+      for (int64_t i = 0; i < n; ++i) {
+         volatile double p = fv->rx * (double)(fv->d.global_offset + i + 1);
+         const double er = desc->xmin + p;
+         wv[(size_t)i] = er - e0;
+         e0 = er;
+      }
+      return upload_width(wv.data(), n, &fv->d_width[0]);
+   }
+   return upload_width(desc->width[0], n, &fv->d_width[0]);
 }
 
 int fv_create(Fv **out, const hrweno_fv_desc *desc) {
@@ -93,8 +186,8 @@ int fv_create(Fv **out, const hrweno_fv_desc *desc) {
       fv->d.global_n = desc->ndim == 1 ? fv->n0 : fv->n1;
    }
    int st = HRWENO_OK;
-   if (desc->grid_kind == HRWENO_GRID_LINEAR) {
-      fv->rx = (desc->xmax - desc->xmin) / (double)fv->d.global_n; // grids.f90:76
+   if (desc->ndim == 1) {
+      st = setup_width_1d(fv, desc);
    } else {
       for (int a = 0; a < desc->ndim && st == HRWENO_OK; ++a) st = upload_width(desc->width[a], desc->n[a], &fv->d_width[a]);
    }
@@ -188,44 +281,23 @@ int fv_unpack(Fv *fv, const double *padded0, double *dense, cudaStream_t st) {
 // ------------------------------------------------------------------------------------------------
 // stage dispatch
 // ------------------------------------------------------------------------------------------------
-constexpr int R1 = 4, NT1 = 256;
+int fv1d_launch_k1_m0(int, int, int, const Fv1dGeom &, const StageArgs &, cudaStream_t);
+int fv1d_launch_k2_m0(int, int, int, const Fv1dGeom &, const StageArgs &, cudaStream_t);
+int fv1d_launch_k3_m0(int, int, int, const Fv1dGeom &, const StageArgs &, cudaStream_t);
+int fv1d_launch_k1_m1(int, int, int, const Fv1dGeom &, const StageArgs &, cudaStream_t);
+int fv1d_launch_k2_m1(int, int, int, const Fv1dGeom &, const StageArgs &, cudaStream_t);
+int fv1d_launch_k3_m1(int, int, int, const Fv1dGeom &, const StageArgs &, cudaStream_t);
+int fv1d_tile_cells();
 
-template <int K, int COMBINE, class M>
-static void launch1d(const Fv1dGeom &g, const StageArgs &a, int64_t rows, cudaStream_t st) {
-   // persistent grid: SMs x resident CTAs of this instantiation (queried once), never more than there are tiles
-   static int resident = 0;
-   if (resident == 0) {
-      int dev = 0, sms = 0, per_sm = 0;
-      cudaGetDevice(&dev);
-      cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
-      cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, fv1d_stage_kernel<K, COMBINE, M, R1, NT1>, NT1, 0);
-      resident = (sms > 0 ? sms : 148) * (per_sm > 0 ? per_sm : 1);
+int fv1d_launch(int k, int mode, int combine, int fk, int wk, const Fv1dGeom &g, const StageArgs &a, cudaStream_t st) {
+   if (mode == HRWENO_MODE_STRICT) {
+      if (k == 1) return fv1d_launch_k1_m0(combine, fk, wk, g, a, st);
+      if (k == 2) return fv1d_launch_k2_m0(combine, fk, wk, g, a, st);
+      return fv1d_launch_k3_m0(combine, fk, wk, g, a, st);
    }
-   int64_t blocks = rows * g.tiles_per_row;
-   if (blocks > resident) blocks = resident;
-   fv1d_stage_kernel<K, COMBINE, M, R1, NT1><<<(unsigned)blocks, NT1, 0, st>>>(g, a);
-}
-
-template <int K, class M>
-static void launch1d_c(int combine, const Fv1dGeom &g, const StageArgs &a, int64_t rows, cudaStream_t st) {
-   switch (combine) {
-   case C_RHS: launch1d<K, C_RHS, M>(g, a, rows, st); break;
-   case C_EULER: launch1d<K, C_EULER, M>(g, a, rows, st); break;
-   case C_RK2_FINAL: launch1d<K, C_RK2_FINAL, M>(g, a, rows, st); break;
-   case C_RK3_S2: launch1d<K, C_RK3_S2, M>(g, a, rows, st); break;
-   case C_RK3_S3: launch1d<K, C_RK3_S3, M>(g, a, rows, st); break;
-   default: launch1d<K, C_MS, M>(g, a, rows, st); break;
-   }
-}
-
-template <class M>
-static void launch1d_k(int k, int combine, const Fv1dGeom &g, const StageArgs &a, int64_t rows, cudaStream_t st) {
-   if (k == 1)
-      launch1d_c<1, M>(combine, g, a, rows, st);
-   else if (k == 2)
-      launch1d_c<2, M>(combine, g, a, rows, st);
-   else
-      launch1d_c<3, M>(combine, g, a, rows, st);
+   if (k == 1) return fv1d_launch_k1_m1(combine, fk, wk, g, a, st);
+   if (k == 2) return fv1d_launch_k2_m1(combine, fk, wk, g, a, st);
+   return fv1d_launch_k3_m1(combine, fk, wk, g, a, st);
 }
 
 int fv_stage(Fv *fv, int combine, const StageArgs &args, cudaStream_t st) {
@@ -236,26 +308,22 @@ int fv_stage(Fv *fv, int combine, const StageArgs &args, cudaStream_t st) {
       return HRWENO_OK;
    }
    Fv1dGeom g{};
+   const int tile = fv1d_tile_cells();
    g.n = fv->n0;
    g.ld = fv->pitch;
-   g.tiles_per_row = (fv->n0 + (NT1 - 2) * R1 - 1) / ((NT1 - 2) * R1);
+   g.tiles_per_row = (fv->n0 + tile - 1) / tile;
    g.rows = fv->rows;
    g.width = fv->d_width[0];
-   g.xmin = d.xmin;
-   g.rx = fv->rx;
-   g.goff = d.global_offset;
+   g.wtab = fv->d_wtab;
+   g.widx = fv->d_widx;
    g.eps = d.eps;
    g.flux = FluxCfg{d.flux_model, d.flux_scheme, d.flux_coef[0], d.alpha};
    g.bc = d.bc;
-   g.grid_kind = d.grid_kind;
    g.phys_left = d.rank == 0;
    g.phys_right = d.rank == d.nranks - 1;
-   if (d.mode == HRWENO_MODE_STRICT)
-      launch1d_k<Strict>(d.k, combine, g, args, fv->rows, st);
-   else
-      launch1d_k<Fast>(d.k, combine, g, args, fv->rows, st);
+   const int fk = (d.flux_model == HRWENO_FLUX_BURGERS && d.flux_scheme == HRWENO_SCHEME_GODUNOV) ? FK_BURGERS_GODUNOV : FK_GENERIC;
+   HRW_TRY(fv1d_launch(d.k, d.mode, combine, fk, fv->width_dict ? WK_DICT : WK_ARRAY, g, args, st));
    fv->launches++;
-   HRW_CUDA(cudaGetLastError());
    return HRWENO_OK;
 }
 

@@ -9,27 +9,40 @@
 // provide those neighbour values (tiles overlap by one thread-run on each side: 2/NT redundant work)
 // so no thread ever reconstructs a cell twice.
 //
-// HBM traffic per cell: read v once (tile staged in shared memory with 16-B vector loads), read the
-// pointwise operands a/b once, write out once -- the algorithmic 16/24/24 B of an RK3 step.
+// The kernel is persistent (grid = SMs x resident CTAs); the tile of the next iteration is fetched by one
+// TMA bulk copy (cp.async.bulk + mbarrier) into the other shared-memory buffer while this one computes.
+//
+// Measured on B200 (tools/microbench/fp64_issue.cu, profiles/): a warp-wide DFMA/DMUL/DADD holds the SMSP
+// issue port for 2 cycles and every other instruction costs ~0.8 cycles on top, so this kernel is bound by
+// instruction issue, not by HBM or latency.  Hence: the hot path is specialised at compile time (flux, width
+// source), boundary handling lives in a cold path only edge threads take, the 1/2 of Burgers' flux and the
+// sign of the divergence are folded into the (exact, power-of-two scaled) stage coefficient, and widths come
+// from a small dictionary (value + refined reciprocal) indexed by one byte per cell.
 #pragma once
 
 #include "internal.hpp"
 #include "weno_core.cuh"
 
+#ifndef HRW_MINB
+#define HRW_MINB 2 // resident CTAs per SM the register allocation is tuned for
+#endif
+
 namespace hrw {
+
+enum FluxKind { FK_BURGERS_GODUNOV = 0, FK_GENERIC = 1 };
+enum WidthKind { WK_DICT = 0, WK_ARRAY = 1 };
 
 struct Fv1dGeom {
    int64_t n;             // cells per row
    int64_t ld;            // padded row pitch of vin / a / b / out2
    int64_t tiles_per_row;
    int64_t rows;          // independent rows (batched ensemble)
-   const double *width;   // GRID_WIDTH_ARRAY: device array (padded to a multiple of 4, >= n+4)
-   double xmin, rx;       // GRID_LINEAR
-   int64_t goff;          // global index of local cell 0 (slab decomposition)
+   const double *width;   // WK_ARRAY: device array (padded, >= n + 16)
+   const double2 *wtab;   // WK_DICT: 256 entries {width, refined reciprocal (exact_recip)}
+   const unsigned char *widx; // WK_DICT: one byte per cell (padded, >= n + 16)
    double eps;
    FluxCfg flux;
    int bc;
-   int grid_kind;
    int phys_left, phys_right; // the row ends are physical boundaries (not slab interfaces)
 };
 
@@ -63,10 +76,191 @@ __device__ __forceinline__ void tma_bulk_g2s(void *dst_smem, const void *src_gme
                 : "memory");
 }
 
-// Persistent kernel: grid = SMs x resident CTAs; every CTA walks tiles blockIdx.x, +gridDim.x, ...  The tile of
-// iteration i+1 is fetched by one TMA bulk copy into the other shared-memory buffer while iteration i computes.
-template <int K, int COMBINE, class M, int R, int NT>
-__global__ void __launch_bounds__(NT) fv1d_stage_kernel(const Fv1dGeom g, const StageArgs s) {
+// ---- numerical flux at one face ---------------------------------------------------------------------------
+// FK_BURGERS_GODUNOV returns TWICE the reference's value: godunov (fluxes.f90:67-74) of f = (v**2)/2 (example1:120)
+// is  vm<=vp ? min(fm,fp) : max(fm,fp)  and  min(x/2, y/2) = min(x,y)/2 exactly, so the selection is done on the
+// squares and the exact factor 1/2 is folded into the stage coefficient by the caller.
+template <int FK, class M>
+__device__ __forceinline__ double face_flux_k(const FluxCfg &c, double vm, double vp) {
+   if constexpr (FK == FK_BURGERS_GODUNOV) {
+      const double qm = M::mul(vm, vm), qp = M::mul(vp, vp);
+      const bool up = vm <= vp, lt = qm < qp;
+      return (up == lt) ? qm : qp; // up: the smaller square, else the larger one (ties: equal values)
+   } else {
+      return face_flux<M>(c, vm, vp);
+   }
+}
+
+// one thread's share of a tile after the reconstruction: fluxes, divergence, combination, stores.
+// EDGE = false: interior thread -- all R cells exist, no physical boundary touches its faces (hot path).
+// EDGE = true : everything else (row ends, partial runs): boundary constraints, ghost cells, scalar accesses.
+template <int K, int COMBINE, class M, int FK, int WK, int R, bool EDGE>
+__device__ __forceinline__ void fv1d_finish(const Fv1dGeom &g, const StageArgs &s, const double2 *s_wtab, int64_t row, int64_t i0,
+                                            const double *w /* window, cell j at w[2+j] */, const double *vl, const double *vr,
+                                            double vr_left, double vl_right, double cL, double lscale) {
+   // numerical flux at the R+1 faces i0 .. i0+R (face f lies between cells f-1 and f)
+   double F[R + 1];
+   F[0] = face_flux_k<FK, M>(g.flux, vr_left, vl[0]);
+#pragma unroll
+   for (int j = 1; j < R; ++j) F[j] = face_flux_k<FK, M>(g.flux, vr[j - 1], vl[j]);
+   F[R] = face_flux_k<FK, M>(g.flux, vr[R - 1], vl_right);
+   if constexpr (EDGE) {
+      // problem-specific constraints at the domain boundaries (example1:103-104, example2:117-120)
+      const bool copy = g.bc == HRWENO_BC_COPY_NEIGHBOUR;
+      if (g.phys_left && i0 == 0) F[0] = copy ? F[1] : 0.0;
+      if (g.phys_right) {
+#pragma unroll
+         for (int j = 1; j <= R; ++j)
+            if (i0 + j == g.n) F[j] = copy ? F[j - 1] : 0.0;
+      }
+   }
+
+   // pointwise operands
+   double av[R], bv[R];
+   constexpr bool NEED_A = COMBINE == C_RK2_FINAL || COMBINE == C_RK3_S2 || COMBINE == C_RK3_S3 || COMBINE == C_MS;
+   if constexpr (NEED_A) {
+      const double *ap = s.a + row * g.ld + i0;
+      if constexpr (!EDGE) {
+#pragma unroll
+         for (int j = 0; j < R; j += 2) {
+            const double2 t = __ldg(reinterpret_cast<const double2 *>(ap + j));
+            av[j] = t.x;
+            av[j + 1] = t.y;
+         }
+      } else {
+#pragma unroll
+         for (int j = 0; j < R; ++j) av[j] = (i0 + j < g.n) ? ap[j] : 0.0;
+      }
+      if constexpr (COMBINE == C_MS) {
+         const double *bp = s.b + row * g.ld + i0;
+         if constexpr (!EDGE) {
+#pragma unroll
+            for (int j = 0; j < R; j += 2) {
+               const double2 t = __ldg(reinterpret_cast<const double2 *>(bp + j));
+               bv[j] = t.x;
+               bv[j + 1] = t.y;
+            }
+         } else {
+#pragma unroll
+            for (int j = 0; j < R; ++j) bv[j] = (i0 + j < g.n) ? bp[j] : 0.0;
+         }
+      }
+   }
+
+   // widths: {w, refined reciprocal of w}
+   double wd[R], wr[R];
+   if constexpr (WK == WK_DICT) {
+      static_assert(R % 4 == 0, "dictionary indices are fetched four at a time");
+#pragma unroll
+      for (int j = 0; j < R; j += 4) {
+         const uint32_t idx4 = __ldg(reinterpret_cast<const uint32_t *>(g.widx + i0 + j));
+#pragma unroll
+         for (int q = 0; q < 4; ++q) {
+            const double2 e = s_wtab[(idx4 >> (8 * q)) & 0xffu];
+            wd[j + q] = e.x;
+            wr[j + q] = e.y;
+         }
+      }
+   } else {
+#pragma unroll
+      for (int j = 0; j < R; j += 2) {
+         const double2 t = __ldg(reinterpret_cast<const double2 *>(g.width + i0 + j));
+         wd[j] = t.x;
+         wd[j + 1] = t.y;
+      }
+#pragma unroll
+      for (int j = 0; j < R; ++j) wr[j] = M::strict ? exact_recip(wd[j]) : fast_rcp(wd[j]);
+   }
+
+   double res[R], lres[R];
+   bool ok = true;
+#pragma unroll
+   for (int j = 0; j < R; ++j) {
+      // vdot = -(fedges(i) - fedges(i-1))/width (example1:107); q = (df)/width here, sign and the flux's 1/2 are in cL/lscale
+      const double dF = M::sub(F[j + 1], F[j]);
+      double q;
+      if constexpr (M::strict)
+         q = exact_div_q(dF, wd[j], wr[j], ok);
+      else
+         q = dF * wr[j];
+      const double v = w[2 + j];
+      double o;
+      if constexpr (COMBINE == C_RHS) {
+         o = M::mul(lscale, q);
+      } else if constexpr (COMBINE == C_EULER) {
+         o = M::add(v, M::mul(cL, q)); // u + dt*udot
+      } else if constexpr (COMBINE == C_RK2_FINAL) {
+         o = M::mul(M::add(M::add(av[j], v), M::mul(cL, q)), 0.5); // (u + ui + dt*udot)/2
+      } else if constexpr (COMBINE == C_RK3_S2) {
+         o = M::mul(M::add(M::add(M::mul(3.0, av[j]), v), M::mul(cL, q)), 0.25); // (3*u + ui + dt*udot)/4
+      } else if constexpr (COMBINE == C_RK3_S3) {
+         // (u + 2*ui + 2*dt*udot)/3 ; 2*ui is exact
+         o = div3<M>(M::add(M::fma_exact(2.0, v, av[j]), M::mul(cL, q)));
+      } else {
+         // (25*u + 50*dt*udot + 7*uold(:,4) + 10*dt*udotold(:,4))/32 ; /32 is exact
+         o = M::mul(M::add(M::add(M::add(M::mul(25.0, v), M::mul(cL, q)), M::mul(7.0, av[j])), M::mul(s.c1, bv[j])), 0.03125);
+         lres[j] = M::mul(lscale, q);
+      }
+      res[j] = o;
+   }
+   if constexpr (M::strict) {
+      if (!ok) { // a quotient in the denormal range: redo this run with the compiler's division (cold)
+#pragma unroll
+         for (int j = 0; j < R; ++j) {
+            const double q = __ddiv_rn(__dsub_rn(F[j + 1], F[j]), wd[j]);
+            const double v = w[2 + j];
+            if constexpr (COMBINE == C_RHS) res[j] = __dmul_rn(lscale, q);
+            if constexpr (COMBINE == C_EULER) res[j] = __dadd_rn(v, __dmul_rn(cL, q));
+            if constexpr (COMBINE == C_RK2_FINAL) res[j] = __dmul_rn(__dadd_rn(__dadd_rn(av[j], v), __dmul_rn(cL, q)), 0.5);
+            if constexpr (COMBINE == C_RK3_S2) res[j] = __dmul_rn(__dadd_rn(__dadd_rn(__dmul_rn(3.0, av[j]), v), __dmul_rn(cL, q)), 0.25);
+            if constexpr (COMBINE == C_RK3_S3) res[j] = __ddiv_rn(__dadd_rn(__fma_rn(2.0, v, av[j]), __dmul_rn(cL, q)), 3.0);
+            if constexpr (COMBINE == C_MS) {
+               res[j] = __dmul_rn(__dadd_rn(__dadd_rn(__dadd_rn(__dmul_rn(25.0, v), __dmul_rn(cL, q)), __dmul_rn(7.0, av[j])), __dmul_rn(s.c1, bv[j])), 0.03125);
+               lres[j] = __dmul_rn(lscale, q);
+            }
+         }
+      }
+   }
+
+   double *orow = s.out + row * s.ld_out + i0;
+   if constexpr (!EDGE) {
+#pragma unroll
+      for (int j = 0; j < R; j += 2) *reinterpret_cast<double2 *>(orow + j) = make_double2(res[j], res[j + 1]);
+      if constexpr (COMBINE == C_MS) {
+         double *lrow = s.out2 + row * g.ld + i0;
+#pragma unroll
+         for (int j = 0; j < R; j += 2) *reinterpret_cast<double2 *>(lrow + j) = make_double2(lres[j], lres[j + 1]);
+      }
+   } else {
+#pragma unroll
+      for (int j = 0; j < R; ++j)
+         if (i0 + j < g.n) orow[j] = res[j];
+      if constexpr (COMBINE == C_MS) {
+         double *lrow = s.out2 + row * g.ld + i0;
+#pragma unroll
+         for (int j = 0; j < R; ++j)
+            if (i0 + j < g.n) lrow[j] = lres[j];
+      }
+      // ghost cells of the result at physical boundaries: edge replicas (weno.f90:172-173)
+      if (!s.out_dense && COMBINE != C_RHS) {
+         if (g.phys_left && i0 == 0) {
+#pragma unroll
+            for (int q = 1; q <= K; ++q) orow[-q] = res[0];
+         }
+         if (g.phys_right) {
+#pragma unroll
+            for (int j = 0; j < R; ++j)
+               if (i0 + j == g.n - 1) {
+#pragma unroll
+                  for (int q = 1; q <= K; ++q) orow[j + q] = res[j];
+               }
+         }
+      }
+   }
+}
+
+template <int K, int COMBINE, class M, int FK, int WK, int R, int NT>
+__global__ void __launch_bounds__(NT, HRW_MINB) fv1d_stage_kernel(const Fv1dGeom g, const StageArgs s) {
    constexpr int P = 4;              // tile halo in shared memory (>= K-1, keeps 32-B alignment)
    constexpr int TILE = (NT - 2) * R; // cells written per CTA and tile
    constexpr int SM_N = NT * R + 2 * P;
@@ -74,6 +268,7 @@ __global__ void __launch_bounds__(NT) fv1d_stage_kernel(const Fv1dGeom g, const 
    __shared__ __align__(128) double s_v[2][SM_N];
    __shared__ double s_vr[2][NT];
    __shared__ double s_vl[2][NT];
+   __shared__ __align__(16) double2 s_wtab[WK == WK_DICT ? 256 : 1];
    __shared__ __align__(8) unsigned long long s_bar[2];
 
    const int tid = threadIdx.x;
@@ -93,6 +288,8 @@ __global__ void __launch_bounds__(NT) fv1d_stage_kernel(const Fv1dGeom g, const 
    };
 
    for (int idx = tid; idx < 2 * SM_N; idx += NT) (&s_v[0][0])[idx] = 0.0; // parts a clipped copy never writes
+   if constexpr (WK == WK_DICT)
+      for (int idx = tid; idx < 256; idx += NT) s_wtab[idx] = g.wtab[idx];
    asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); // order the generic-proxy zero fill before async-proxy writes
    if (tid == 0) {
       mbar_init(&s_bar[0], 1);
@@ -101,6 +298,11 @@ __global__ void __launch_bounds__(NT) fv1d_stage_kernel(const Fv1dGeom g, const 
    }
    __syncthreads();
    if (tid == 0 && (int64_t)blockIdx.x < total_tiles) issue(blockIdx.x, 0);
+
+   // stage coefficient with the sign of the divergence and, for Burgers/Godunov, the flux's exact 1/2 folded in:
+   // dt*L = dt*(-(1/2) q) = (-dt/2)*q bit for bit (power-of-two scaling commutes with rounding)
+   const double lscale = FK == FK_BURGERS_GODUNOV ? -0.5 : -1.0;
+   const double cL = lscale * s.c0;
 
    int it = 0;
    for (int64_t tile_id = blockIdx.x; tile_id < total_tiles; tile_id += gridDim.x, ++it) {
@@ -112,41 +314,6 @@ __global__ void __launch_bounds__(NT) fv1d_stage_kernel(const Fv1dGeom g, const 
       const int64_t row = tile_id / g.tiles_per_row;
       const int64_t c0 = (tile_id - row * g.tiles_per_row) * TILE;
       const int64_t i0 = c0 + (int64_t)(tid - 1) * R; // first owned cell (thread 0: the run left of the tile)
-      const bool active = tid >= 1 && tid <= NT - 2 && i0 < g.n;
-      const bool full = i0 + R <= g.n;
-
-      // pointwise operands: issue the global loads before waiting on the tile
-      double av[R], bv[R];
-      if (COMBINE == C_RK2_FINAL || COMBINE == C_RK3_S2 || COMBINE == C_RK3_S3 || COMBINE == C_MS) {
-         if (active) {
-            const double *ap = s.a + row * g.ld + i0;
-            if (full) {
-#pragma unroll
-               for (int j = 0; j < R; j += 2) {
-                  const double2 t = __ldg(reinterpret_cast<const double2 *>(ap + j));
-                  av[j] = t.x;
-                  av[j + 1] = t.y;
-               }
-            } else {
-#pragma unroll
-               for (int j = 0; j < R; ++j) av[j] = (i0 + j < g.n) ? ap[j] : 0.0;
-            }
-            if (COMBINE == C_MS) {
-               const double *bp = s.b + row * g.ld + i0;
-               if (full) {
-#pragma unroll
-                  for (int j = 0; j < R; j += 2) {
-                     const double2 t = __ldg(reinterpret_cast<const double2 *>(bp + j));
-                     bv[j] = t.x;
-                     bv[j + 1] = t.y;
-                  }
-               } else {
-#pragma unroll
-                  for (int j = 0; j < R; ++j) bv[j] = (i0 + j < g.n) ? bp[j] : 0.0;
-               }
-            }
-         }
-      }
 
       mbar_wait(&s_bar[buf], (uint32_t)((it >> 1) & 1));
 
@@ -166,108 +333,16 @@ __global__ void __launch_bounds__(NT) fv1d_stage_kernel(const Fv1dGeom g, const 
       s_vr[buf][tid] = vr[R - 1];
       s_vl[buf][tid] = vl[0];
       __syncthreads();
-      if (!active) continue;
+      if (tid == 0 || tid == NT - 1 || i0 >= g.n) continue;
       const double vr_left = s_vr[buf][tid - 1];
       const double vl_right = s_vl[buf][tid + 1];
 
-      // numerical flux at the R+1 faces i0 .. i0+R (face f lies between cells f-1 and f)
-      double F[R + 1];
-      F[0] = face_flux<M>(g.flux, vr_left, vl[0]);
-#pragma unroll
-      for (int j = 1; j < R; ++j) F[j] = face_flux<M>(g.flux, vr[j - 1], vl[j]);
-      F[R] = face_flux<M>(g.flux, vr[R - 1], vl_right);
-      // problem-specific constraints at the domain boundaries (example1:103-104, example2:117-120)
-      const bool copy = g.bc == HRWENO_BC_COPY_NEIGHBOUR;
-      if (g.phys_left && i0 == 0) F[0] = copy ? F[1] : 0.0;
-      if (g.phys_right) {
-#pragma unroll
-         for (int j = 1; j <= R; ++j)
-            if (i0 + j == g.n) F[j] = copy ? F[j - 1] : 0.0;
-      }
-
-      // cell widths
-      double wd[R];
-      if (g.grid_kind == HRWENO_GRID_LINEAR) {
-         // grids.f90:76-79,247: edges(i) = xmin + rx*i ; width = edges(i) - edges(i-1)
-         const double base = (double)(g.goff + i0);
-         double el = M::add(g.xmin, M::mul(g.rx, base));
-#pragma unroll
-         for (int j = 0; j < R; ++j) {
-            const double er = M::add(g.xmin, M::mul(g.rx, base + (double)(j + 1)));
-            wd[j] = M::sub(er, el);
-            el = er;
-         }
-      } else {
-#pragma unroll
-         for (int j = 0; j < R; j += 2) {
-            const double2 t = __ldg(reinterpret_cast<const double2 *>(g.width + i0 + j));
-            wd[j] = t.x;
-            wd[j + 1] = t.y;
-         }
-      }
-
-      double res[R], lres[R];
-#pragma unroll
-      for (int j = 0; j < R; ++j) {
-         // vdot = -(fedges(i) - fedges(i-1))/width   (example1:107)
-         const double L = -M::div(M::sub(F[j + 1], F[j]), wd[j]);
-         const double v = w[2 + j];
-         double o;
-         if (COMBINE == C_RHS) {
-            o = L;
-         } else if (COMBINE == C_EULER) {
-            o = M::add(v, M::mul(s.c0, L)); // u + dt*udot
-         } else if (COMBINE == C_RK2_FINAL) {
-            o = M::mul(M::add(M::add(av[j], v), M::mul(s.c0, L)), 0.5); // (u + ui + dt*udot)/2
-         } else if (COMBINE == C_RK3_S2) {
-            o = M::mul(M::add(M::add(M::mul(3.0, av[j]), v), M::mul(s.c0, L)), 0.25); // (3*u + ui + dt*udot)/4
-         } else if (COMBINE == C_RK3_S3) {
-            // (u + 2*ui + 2*dt*udot)/3 ; 2*ui is exact
-            o = div3<M>(M::add(M::fma_exact(2.0, v, av[j]), M::mul(s.c0, L)));
-         } else {
-            // (25*u + 50*dt*udot + 7*uold(:,4) + 10*dt*udotold(:,4))/32 ; /32 is exact
-            o = M::mul(M::add(M::add(M::add(M::mul(25.0, v), M::mul(s.c0, L)), M::mul(7.0, av[j])), M::mul(s.c1, bv[j])),
-                       0.03125);
-            lres[j] = L;
-         }
-         res[j] = o;
-      }
-
-      double *orow = s.out + row * s.ld_out + i0;
-      if (full && !s.out_dense) {
-#pragma unroll
-         for (int j = 0; j < R; j += 2) *reinterpret_cast<double2 *>(orow + j) = make_double2(res[j], res[j + 1]);
-      } else {
-#pragma unroll
-         for (int j = 0; j < R; ++j)
-            if (i0 + j < g.n) orow[j] = res[j];
-      }
-      if (COMBINE == C_MS) {
-         double *lrow = s.out2 + row * g.ld + i0;
-         if (full) {
-#pragma unroll
-            for (int j = 0; j < R; j += 2) *reinterpret_cast<double2 *>(lrow + j) = make_double2(lres[j], lres[j + 1]);
-         } else {
-#pragma unroll
-            for (int j = 0; j < R; ++j)
-               if (i0 + j < g.n) lrow[j] = lres[j];
-         }
-      }
-      // ghost cells of the result at physical boundaries: edge replicas (weno.f90:172-173)
-      if (!s.out_dense && COMBINE != C_RHS) {
-         if (g.phys_left && i0 == 0) {
-#pragma unroll
-            for (int q = 1; q <= K; ++q) orow[-q] = res[0];
-         }
-         if (g.phys_right) {
-#pragma unroll
-            for (int j = 0; j < R; ++j)
-               if (i0 + j == g.n - 1) {
-#pragma unroll
-                  for (int q = 1; q <= K; ++q) orow[j + q] = res[j];
-               }
-         }
-      }
+      // a caller's dense output array carries no alignment guarantee: scalar stores (edge path) for every thread
+      const bool edge = s.out_dense || (i0 + R > g.n) || (i0 == 0) || (i0 + R == g.n);
+      if (!edge)
+         fv1d_finish<K, COMBINE, M, FK, WK, R, false>(g, s, s_wtab, row, i0, w, vl, vr, vr_left, vl_right, cL, lscale);
+      else
+         fv1d_finish<K, COMBINE, M, FK, WK, R, true>(g, s, s_wtab, row, i0, w, vl, vr, vr_left, vl_right, cL, lscale);
    }
 }
 

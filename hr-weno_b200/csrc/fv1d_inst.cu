@@ -1,0 +1,68 @@
+// fv1d_inst.cu -- instantiations of the 1D stage kernel for one (k, mode) pair; the Makefile compiles this file
+// six times (-DHRW_INST_K=1..3 -DHRW_INST_MODE=0|1) so the 144 specialisations build in parallel.
+#include "fv1d.cuh"
+
+#ifndef HRW_R1
+#define HRW_R1 4
+#endif
+#ifndef HRW_NT1
+#define HRW_NT1 256
+#endif
+
+namespace hrw {
+
+constexpr int IK = HRW_INST_K;
+#if HRW_INST_MODE == 0
+using IM = Strict;
+#else
+using IM = Fast;
+#endif
+constexpr int R1 = HRW_R1, NT1 = HRW_NT1;
+
+template <int COMBINE, int FK, int WK>
+static int launch(const Fv1dGeom &g, const StageArgs &a, cudaStream_t st) {
+   auto kern = fv1d_stage_kernel<IK, COMBINE, IM, FK, WK, R1, NT1>;
+   // persistent grid: SMs x resident CTAs of this specialisation (queried once), never more than there are tiles
+   static int resident = 0;
+   if (resident == 0) {
+      int dev = 0, sms = 0, per_sm = 0;
+      cudaGetDevice(&dev);
+      cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+      cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, NT1, 0);
+      resident = (sms > 0 ? sms : 148) * (per_sm > 0 ? per_sm : 1);
+   }
+   int64_t blocks = g.rows * g.tiles_per_row;
+   if (blocks > resident) blocks = resident;
+   kern<<<(unsigned)blocks, NT1, 0, st>>>(g, a);
+   HRW_CUDA(cudaGetLastError());
+   return HRWENO_OK;
+}
+
+template <int COMBINE>
+static int launch_c(int fk, int wk, const Fv1dGeom &g, const StageArgs &a, cudaStream_t st) {
+   if (fk == FK_BURGERS_GODUNOV) {
+      if (wk == WK_DICT) return launch<COMBINE, FK_BURGERS_GODUNOV, WK_DICT>(g, a, st);
+      return launch<COMBINE, FK_BURGERS_GODUNOV, WK_ARRAY>(g, a, st);
+   }
+   if (wk == WK_DICT) return launch<COMBINE, FK_GENERIC, WK_DICT>(g, a, st);
+   return launch<COMBINE, FK_GENERIC, WK_ARRAY>(g, a, st);
+}
+
+#define HRW_CAT2(a, b, c, d) a##b##c##d
+#define HRW_CAT(a, b, c, d) HRW_CAT2(a, b, c, d)
+int HRW_CAT(fv1d_launch_k, HRW_INST_K, _m, HRW_INST_MODE)(int combine, int fk, int wk, const Fv1dGeom &g, const StageArgs &a, cudaStream_t st) {
+   switch (combine) {
+   case C_RHS: return launch_c<C_RHS>(fk, wk, g, a, st);
+   case C_EULER: return launch_c<C_EULER>(fk, wk, g, a, st);
+   case C_RK2_FINAL: return launch_c<C_RK2_FINAL>(fk, wk, g, a, st);
+   case C_RK3_S2: return launch_c<C_RK3_S2>(fk, wk, g, a, st);
+   case C_RK3_S3: return launch_c<C_RK3_S3>(fk, wk, g, a, st);
+   default: return launch_c<C_MS>(fk, wk, g, a, st);
+   }
+}
+
+#if HRW_INST_K == 3 && HRW_INST_MODE == 0
+int fv1d_tile_cells() { return (NT1 - 2) * R1; } // defined by one of the six objects
+#endif
+
+} // namespace hrw

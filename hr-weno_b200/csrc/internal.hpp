@@ -57,6 +57,10 @@ struct Fv {
    int64_t pitch = 0;            // padded row pitch (doubles)
    int64_t nrows_alloc = 0;      // rows (1D) or n1 + 2*PAD2 (2D)
    double *d_width[2] = {nullptr, nullptr};
+   // 1D width dictionary: <= 256 distinct widths {w, refined reciprocal} + one byte per cell (fv1d.cuh)
+   double2 *d_wtab = nullptr;
+   unsigned char *d_widx = nullptr;
+   bool width_dict = false;
    double rx = 0.0;              // GRID_LINEAR: (xmax-xmin)/global_n
    // scratch for hrweno_fv_rhs[_dev]
    double *d_scratch_in = nullptr, *d_scratch_out = nullptr;
@@ -77,6 +81,9 @@ int fv_pack(Fv *fv, const double *dense_dev, double *padded_cell0, cudaStream_t 
 int fv_unpack(Fv *fv, const double *padded_cell0, double *dense_dev, cudaStream_t st);
 // one fused stage: reconstruct + face fluxes + divergence + combination
 int fv_stage(Fv *fv, int combine, const StageArgs &args, cudaStream_t st);
+struct Fv1dGeom;
+// fv1d_inst.cu, compiled once per (k, mode): launches the 1D stage kernel specialised for (combine, flux kind, width kind)
+int fv1d_launch(int k, int mode, int combine, int flux_kind, int width_kind, const Fv1dGeom &g, const StageArgs &a, cudaStream_t st);
 // fill the slab-interface ghost cells of a padded state from the neighbouring ranks (no-op on one GPU)
 int fv_exchange(Fv *fv, double *padded_cell0, cudaStream_t st);
 int fv_halo_export(Fv *fv, void *handle_out);

@@ -22,26 +22,37 @@ struct Window {
    static constexpr int N = R + 2 * G;   // window length
 };
 
-// fallbacks with the compiler's own division (taken only when an exact_div range check fails: operands
-// near the overflow/underflow thresholds); same formulas as the strict branches below.
-static __device__ __noinline__ void weno_weights_slow_k2(double den0, double den1, double vrr0, double vrr1, double vlr0,
-                                                  double vlr1, double &vl, double &vr) {
+// fallbacks with the compiler's own division (taken only when the range test of the strict branches fails:
+// eps+beta >= 2^256); same formulas.  Returned by value {vl, vr} so nothing is forced onto the stack.
+static __device__ __noinline__ double2 weno_weights_slow_k2(double den0, double den1, double vrr0, double vrr1, double vlr0, double vlr1) {
    const double d0 = 2.0 / 3, d1 = 1.0 / 3;
    const double al0 = __ddiv_rn(d0, den0), al1 = __ddiv_rn(d1, den1);
    const double at0 = __ddiv_rn(d1, den0), at1 = __ddiv_rn(d0, den1);
    const double s = __dadd_rn(al0, al1), st = __dadd_rn(at0, at1);
-   vr = __dadd_rn(__dmul_rn(__ddiv_rn(al0, s), vrr0), __dmul_rn(__ddiv_rn(al1, s), vrr1));
-   vl = __dadd_rn(__dmul_rn(__ddiv_rn(at0, st), vlr0), __dmul_rn(__ddiv_rn(at1, st), vlr1));
+   double2 r;
+   r.y = __dadd_rn(__dmul_rn(__ddiv_rn(al0, s), vrr0), __dmul_rn(__ddiv_rn(al1, s), vrr1));
+   r.x = __dadd_rn(__dmul_rn(__ddiv_rn(at0, st), vlr0), __dmul_rn(__ddiv_rn(at1, st), vlr1));
+   return r;
 }
 
-static __device__ __noinline__ void weno_weights_slow_k3(double den0, double den1, double den2, double vrr0, double vrr1,
-                                                  double vrr2, double vlr0, double vlr1, double vlr2, double &vl, double &vr) {
+static __device__ __noinline__ double2 weno_weights_slow_k3(double den0, double den1, double den2, double vrr0, double vrr1, double vrr2,
+                                                            double vlr0, double vlr1, double vlr2) {
    const double al0 = __ddiv_rn(0.3, den0), al1 = __ddiv_rn(0.6, den1), al2 = __ddiv_rn(0.1, den2);
    const double at0 = __ddiv_rn(0.1, den0), at2 = __ddiv_rn(0.3, den2);
    const double s = __dadd_rn(__dadd_rn(al0, al1), al2);
    const double st = __dadd_rn(__dadd_rn(at0, al1), at2);
-   vr = __dadd_rn(__dadd_rn(__dmul_rn(__ddiv_rn(al0, s), vrr0), __dmul_rn(__ddiv_rn(al1, s), vrr1)), __dmul_rn(__ddiv_rn(al2, s), vrr2));
-   vl = __dadd_rn(__dadd_rn(__dmul_rn(__ddiv_rn(at0, st), vlr0), __dmul_rn(__ddiv_rn(al1, st), vlr1)), __dmul_rn(__ddiv_rn(at2, st), vlr2));
+   double2 r;
+   r.y = __dadd_rn(__dadd_rn(__dmul_rn(__ddiv_rn(al0, s), vrr0), __dmul_rn(__ddiv_rn(al1, s), vrr1)), __dmul_rn(__ddiv_rn(al2, s), vrr2));
+   r.x = __dadd_rn(__dadd_rn(__dmul_rn(__ddiv_rn(at0, st), vlr0), __dmul_rn(__ddiv_rn(al1, st), vlr1)), __dmul_rn(__ddiv_rn(at2, st), vlr2));
+   return r;
+}
+
+// strict branches: every quotient of the weights stays in the range where the compiler's division takes its
+// fast path (normal quotient, divisor < 2^1016) as long as eps+beta < 2^256 (eps > 2^-52 is validated at
+// creation): den < 2^512, alfa > 2^-516, sum(alfa) <= 1/eps^2 < 2^105, w > 2^-621.  One integer test per cell.
+__device__ __forceinline__ bool weights_in_range(double e0, double e1, double e2) {
+   const uint32_t h0 = (uint32_t)__double2hiint(e0), h1 = (uint32_t)__double2hiint(e1), h2 = (uint32_t)__double2hiint(e2);
+   return max(max(h0, h1), h2) < 0x4ff00000u;
 }
 
 // ---------------------------------------------------------------------------------------- k = 1
@@ -86,21 +97,24 @@ __device__ __forceinline__ void weno_run_k2(const double *w, double eps, double 
       const double e0 = M::add(eps, dsq[c]), e1 = M::add(eps, dsq[c - 1]);
       const double den0 = M::mul(e0, e0), den1 = M::mul(e1, e1);
       if constexpr (M::strict) {
-         bool ok = true;
          const double r0 = exact_recip(den0), r1 = exact_recip(den1);
-         const double al0 = exact_div(d0, den0, r0, ok), al1 = exact_div(d1, den1, r1, ok);
-         const double at0 = exact_div(d1, den0, r0, ok), at1 = exact_div(d0, den1, r1, ok);
+         const double al0 = exact_div_nc(d0, den0, r0), al1 = exact_div_nc(d1, den1, r1);
+         const double at0 = exact_div_nc(d1, den0, r0), at1 = exact_div_nc(d0, den1, r1);
          const double s = M::add(al0, al1), st = M::add(at0, at1);
          const double rs = exact_recip(s), rst = exact_recip(st);
-         vr[j] = M::add(M::mul(exact_div(al0, s, rs, ok), vrr0), M::mul(exact_div(al1, s, rs, ok), vrr1));
-         vl[j] = M::add(M::mul(exact_div(at0, st, rst, ok), vlr0), M::mul(exact_div(at1, st, rst, ok), vlr1));
-         if (!ok) weno_weights_slow_k2(den0, den1, vrr0, vrr1, vlr0, vlr1, vl[j], vr[j]);
+         vr[j] = M::add(M::mul(exact_div_nc(al0, s, rs), vrr0), M::mul(exact_div_nc(al1, s, rs), vrr1));
+         vl[j] = M::add(M::mul(exact_div_nc(at0, st, rst), vlr0), M::mul(exact_div_nc(at1, st, rst), vlr1));
+         if (!weights_in_range(e0, e1, e1)) {
+            const double2 r = weno_weights_slow_k2(den0, den1, vrr0, vrr1, vlr0, vlr1);
+            vl[j] = r.x;
+            vr[j] = r.y;
+         }
       } else {
          // alfa_r ~ d_r * prod_{s != r} den_s ; one reciprocal per side
          const double al0 = d0 * den1, al1 = d1 * den0;
          const double at0 = d1 * den1, at1 = d0 * den0;
-         vr[j] = fma(al0, vrr0, al1 * vrr1) * fast_rcp(al0 + al1);
-         vl[j] = fma(at0, vlr0, at1 * vlr1) * fast_rcp(at0 + at1);
+         vr[j] = fma(al0, vrr0, al1 * vrr1) * rcp3(al0 + al1);
+         vl[j] = fma(at0, vlr0, at1 * vlr1) * rcp3(at0 + at1);
       }
    }
 }
@@ -156,19 +170,22 @@ __device__ __forceinline__ void weno_run_k3(const double *w, double eps, double 
       if constexpr (M::strict) {
          // alfa = d/(eps+beta)**2, alfatilde = d(k-1:0:-1)/(eps+beta)**2   (weno.f90:207-208), d3 = [0.3,0.6,0.1]
          // IEEE quotients with the reciprocal refinement shared per denominator (common.cuh: exact_div)
-         bool ok = true;
          const double r0 = exact_recip(den0), r1 = exact_recip(den1), r2 = exact_recip(den2);
-         const double al0 = exact_div(0.3, den0, r0, ok), al1 = exact_div(0.6, den1, r1, ok), al2 = exact_div(0.1, den2, r2, ok);
-         const double at0 = exact_div(0.1, den0, r0, ok), at2 = exact_div(0.3, den2, r2, ok); // at1 == al1
+         const double al0 = exact_div_nc(0.3, den0, r0), al1 = exact_div_nc(0.6, den1, r1), al2 = exact_div_nc(0.1, den2, r2);
+         const double at0 = exact_div_nc(0.1, den0, r0), at2 = exact_div_nc(0.3, den2, r2); // at1 == al1
          const double s = M::add(M::add(al0, al1), al2);
          const double st = M::add(M::add(at0, al1), at2);
          const double rs = exact_recip(s), rst = exact_recip(st);
          // w = alfa/sum(alfa); vr = sum(w*vrr)   (weno.f90:209-214)
-         vr[j] = M::add(M::add(M::mul(exact_div(al0, s, rs, ok), vrr0), M::mul(exact_div(al1, s, rs, ok), vrr1)),
-                        M::mul(exact_div(al2, s, rs, ok), vrr2));
-         vl[j] = M::add(M::add(M::mul(exact_div(at0, st, rst, ok), vlr0), M::mul(exact_div(al1, st, rst, ok), vlr1)),
-                        M::mul(exact_div(at2, st, rst, ok), vlr2));
-         if (!ok) weno_weights_slow_k3(den0, den1, den2, vrr0, vrr1, vrr2, vlr0, vlr1, vlr2, vl[j], vr[j]);
+         vr[j] = M::add(M::add(M::mul(exact_div_nc(al0, s, rs), vrr0), M::mul(exact_div_nc(al1, s, rs), vrr1)),
+                        M::mul(exact_div_nc(al2, s, rs), vrr2));
+         vl[j] = M::add(M::add(M::mul(exact_div_nc(at0, st, rst), vlr0), M::mul(exact_div_nc(al1, st, rst), vlr1)),
+                        M::mul(exact_div_nc(at2, st, rst), vlr2));
+         if (!weights_in_range(e0, e1, e2)) {
+            const double2 r = weno_weights_slow_k3(den0, den1, den2, vrr0, vrr1, vrr2, vlr0, vlr1, vlr2);
+            vl[j] = r.x;
+            vr[j] = r.y;
+         }
       } else {
          // division-light weights: alfa_r ~ d_r * prod_{s != r} den_s, one reciprocal per side
          const double p0 = den1 * den2, p1 = den0 * den2, p2 = den0 * den1;
@@ -181,12 +198,61 @@ __device__ __forceinline__ void weno_run_k3(const double *w, double eps, double 
    }
 }
 
+// ------------------------------------------------------------------------------------ k = 3, fast mode
+// Same scheme, fewest fp64 instructions (the kernel is bound by instruction issue): FMA chains for the
+// candidates; smoothness indicators scaled by 4 (beta' = 4*beta, eps' = 4*eps: every weight ratio is unchanged)
+// so that beta' = b*b + (13/3)*d2*d2 is one FMA per indicator; weights in the division-light form
+//   alfa_r ~ d_r * prod_{s != r} (eps+beta_s)^2   with d = (3,6,1)/10 and the common 1/10 dropped,
+// one reciprocal per side (MUFU seed + one cubic step).  Not bit-identical to the reference order: parity is
+// the north-star tolerance (1e-12 normwise per output time, a few ULP per reconstruction).
+template <int R>
+__device__ __forceinline__ void weno_run_k3_fast(const double *w, double eps, double *vl, double *vr) {
+   constexpr int N = R + 4;
+   const double C13 = 1.0 / 3, C56 = 5.0 / 6, C16 = -1.0 / 6, C76 = -7.0 / 6, C116 = 11.0 / 6;
+   const double eps4 = 4.0 * eps;
+   double m2[N]; // (13/3) * (v[j-1] - 2 v[j] + v[j+1])**2
+#pragma unroll
+   for (int j = 1; j < N - 1; ++j) {
+      const double d2 = fma(-2.0, w[j], w[j - 1]) + w[j + 1];
+      m2[j] = (13.0 / 3) * (d2 * d2);
+   }
+   double A0[N], A1[N];
+#pragma unroll
+   for (int j = 1; j < R + 2; ++j) {
+      A0[j] = fma(C16, w[j + 2], fma(C56, w[j + 1], C13 * w[j]));
+      A1[j] = fma(C13, w[j + 1], fma(C56, w[j], C16 * w[j - 1]));
+   }
+#pragma unroll
+   for (int j = 0; j < R; ++j) {
+      const int c = j + 2;
+      const double vrr0 = A0[c], vrr1 = A1[c];
+      const double vrr2 = fma(C116, w[c], fma(C76, w[c - 1], C13 * w[c - 2]));
+      const double vlr0 = fma(C13, w[c + 2], fma(C76, w[c + 1], C116 * w[c]));
+      const double vlr1 = A0[c - 1], vlr2 = A1[c - 1];
+      const double t3 = 3.0 * w[c];
+      const double b0 = fma(-4.0, w[c + 1], t3) + w[c + 2];
+      const double b1 = w[c - 1] - w[c + 1];
+      const double b2 = fma(-4.0, w[c - 1], w[c - 2]) + t3;
+      const double e0 = eps4 + fma(b0, b0, m2[c + 1]);
+      const double e1 = eps4 + fma(b1, b1, m2[c]);
+      const double e2 = eps4 + fma(b2, b2, m2[c - 1]);
+      const double den0 = e0 * e0, den1 = e1 * e1, den2 = e2 * e2;
+      const double P0 = den1 * den2, P2 = den0 * den1;
+      const double Q1 = 6.0 * (den0 * den2), T0 = 3.0 * P0, T2 = 3.0 * P2;
+      const double s = (T0 + Q1) + P2, st = (P0 + Q1) + T2;
+      vr[j] = fma(P2, vrr2, fma(Q1, vrr1, T0 * vrr0)) * rcp3(s);
+      vl[j] = fma(T2, vlr2, fma(Q1, vlr1, P0 * vlr0)) * rcp3(st);
+   }
+}
+
 template <int K, int R, class M>
 __device__ __forceinline__ void weno_run(const double *w, double eps, double *vl, double *vr) {
    if constexpr (K == 1)
       weno_run_k1<R, M>(w, eps, vl, vr);
    else if constexpr (K == 2)
       weno_run_k2<R, M>(w, eps, vl, vr);
+   else if constexpr (!M::strict)
+      weno_run_k3_fast<R>(w, eps, vl, vr);
    else
       weno_run_k3<R, M>(w, eps, vl, vr);
 }
