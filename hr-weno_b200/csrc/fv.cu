@@ -156,6 +156,8 @@ int fv_create(Fv **out, const hrweno_fv_desc *desc) {
    if (desc->bc == HRWENO_BC_COPY_NEIGHBOUR)
       for (int a = 0; a < desc->ndim; ++a)
          if (desc->n[a] < 2) return fail(HRWENO_EINVAL, "hrweno_fv_create: copy-neighbour boundary needs ncells >= 2");
+   for (int a = 0; a < desc->ndim; ++a)
+      if (desc->n[a] > 2000000000LL) return fail(HRWENO_EINVAL, "hrweno_fv_create: more than 2e9 cells along one axis of one slab");
    if (desc->grid_kind == HRWENO_GRID_LINEAR) {
       if (desc->ndim != 1) return fail(HRWENO_EINVAL, "hrweno_fv_create: GRID_LINEAR is 1D only (pass width arrays)");
       if (!(desc->xmax > desc->xmin)) return fail(HRWENO_EINVAL, "Invalid input 'xmin', 'xmax'. Valid range: xmax > xmin."); // grids.f90:66

@@ -94,10 +94,20 @@ __device__ __forceinline__ double face_flux_k(const FluxCfg &c, double vm, doubl
 // one thread's share of a tile after the reconstruction: fluxes, divergence, combination, stores.
 // EDGE = false: interior thread -- all R cells exist, no physical boundary touches its faces (hot path).
 // EDGE = true : everything else (row ends, partial runs): boundary constraints, ghost cells, scalar accesses.
+// operands an interior thread fetches from global memory at the top of the iteration, so that their latency
+// hides behind the reconstruction
+template <int R>
+struct Prefetched {
+   double av[R], bv[R];
+   uint32_t idx4[R / 4 > 0 ? R / 4 : 1];
+   double wd[R];
+};
+
 template <int K, int COMBINE, class M, int FK, int WK, int R, bool EDGE>
-__device__ __forceinline__ void fv1d_finish(const Fv1dGeom &g, const StageArgs &s, const double2 *s_wtab, int64_t row, int64_t i0,
+__device__ __forceinline__ void fv1d_finish(const Fv1dGeom &g, const StageArgs &s, const double2 *s_wtab, int64_t row, int i0,
                                             const double *w /* window, cell j at w[2+j] */, const double *vl, const double *vr,
-                                            double vr_left, double vl_right, double cL, double lscale) {
+                                            double vr_left, double vl_right, double cL, double lscale, const Prefetched<R> &pf) {
+   const int n = (int)g.n;
    // numerical flux at the R+1 faces i0 .. i0+R (face f lies between cells f-1 and f)
    double F[R + 1];
    F[0] = face_flux_k<FK, M>(g.flux, vr_left, vl[0]);
@@ -111,63 +121,54 @@ __device__ __forceinline__ void fv1d_finish(const Fv1dGeom &g, const StageArgs &
       if (g.phys_right) {
 #pragma unroll
          for (int j = 1; j <= R; ++j)
-            if (i0 + j == g.n) F[j] = copy ? F[j - 1] : 0.0;
+            if (i0 + j == n) F[j] = copy ? F[j - 1] : 0.0;
       }
    }
 
-   // pointwise operands
-   double av[R], bv[R];
+   // pointwise operands and widths {w, refined reciprocal of w}
+   double av[R], bv[R], wd[R], wr[R];
    constexpr bool NEED_A = COMBINE == C_RK2_FINAL || COMBINE == C_RK3_S2 || COMBINE == C_RK3_S3 || COMBINE == C_MS;
-   if constexpr (NEED_A) {
-      const double *ap = s.a + row * g.ld + i0;
-      if constexpr (!EDGE) {
+   uint32_t idx4[R / 4 > 0 ? R / 4 : 1];
+   if constexpr (!EDGE) {
 #pragma unroll
-         for (int j = 0; j < R; j += 2) {
-            const double2 t = __ldg(reinterpret_cast<const double2 *>(ap + j));
-            av[j] = t.x;
-            av[j + 1] = t.y;
+      for (int j = 0; j < R; ++j) {
+         av[j] = pf.av[j];
+         bv[j] = pf.bv[j];
+         wd[j] = pf.wd[j];
+      }
+#pragma unroll
+      for (int j = 0; j < (R / 4 > 0 ? R / 4 : 1); ++j) idx4[j] = pf.idx4[j];
+   } else {
+      if constexpr (NEED_A) {
+         const double *ap = s.a + row * g.ld + i0;
+#pragma unroll
+         for (int j = 0; j < R; ++j) av[j] = (i0 + j < n) ? ap[j] : 0.0;
+         if constexpr (COMBINE == C_MS) {
+            const double *bp = s.b + row * g.ld + i0;
+#pragma unroll
+            for (int j = 0; j < R; ++j) bv[j] = (i0 + j < n) ? bp[j] : 0.0;
          }
+      }
+      if constexpr (WK == WK_DICT) {
+#pragma unroll
+         for (int j = 0; j < R; j += 4) idx4[j / 4] = __ldg(reinterpret_cast<const uint32_t *>(g.widx + i0 + j));
       } else {
 #pragma unroll
-         for (int j = 0; j < R; ++j) av[j] = (i0 + j < g.n) ? ap[j] : 0.0;
-      }
-      if constexpr (COMBINE == C_MS) {
-         const double *bp = s.b + row * g.ld + i0;
-         if constexpr (!EDGE) {
-#pragma unroll
-            for (int j = 0; j < R; j += 2) {
-               const double2 t = __ldg(reinterpret_cast<const double2 *>(bp + j));
-               bv[j] = t.x;
-               bv[j + 1] = t.y;
-            }
-         } else {
-#pragma unroll
-            for (int j = 0; j < R; ++j) bv[j] = (i0 + j < g.n) ? bp[j] : 0.0;
-         }
+         for (int j = 0; j < R; ++j) wd[j] = __ldg(g.width + i0 + j);
       }
    }
-
-   // widths: {w, refined reciprocal of w}
-   double wd[R], wr[R];
    if constexpr (WK == WK_DICT) {
       static_assert(R % 4 == 0, "dictionary indices are fetched four at a time");
 #pragma unroll
       for (int j = 0; j < R; j += 4) {
-         const uint32_t idx4 = __ldg(reinterpret_cast<const uint32_t *>(g.widx + i0 + j));
 #pragma unroll
          for (int q = 0; q < 4; ++q) {
-            const double2 e = s_wtab[(idx4 >> (8 * q)) & 0xffu];
+            const double2 e = s_wtab[(idx4[j / 4] >> (8 * q)) & 0xffu];
             wd[j + q] = e.x;
             wr[j + q] = e.y;
          }
       }
    } else {
-#pragma unroll
-      for (int j = 0; j < R; j += 2) {
-         const double2 t = __ldg(reinterpret_cast<const double2 *>(g.width + i0 + j));
-         wd[j] = t.x;
-         wd[j + 1] = t.y;
-      }
 #pragma unroll
       for (int j = 0; j < R; ++j) wr[j] = M::strict ? exact_recip(wd[j]) : fast_rcp(wd[j]);
    }
@@ -234,12 +235,12 @@ __device__ __forceinline__ void fv1d_finish(const Fv1dGeom &g, const StageArgs &
    } else {
 #pragma unroll
       for (int j = 0; j < R; ++j)
-         if (i0 + j < g.n) orow[j] = res[j];
+         if (i0 + j < n) orow[j] = res[j];
       if constexpr (COMBINE == C_MS) {
          double *lrow = s.out2 + row * g.ld + i0;
 #pragma unroll
          for (int j = 0; j < R; ++j)
-            if (i0 + j < g.n) lrow[j] = lres[j];
+            if (i0 + j < n) lrow[j] = lres[j];
       }
       // ghost cells of the result at physical boundaries: edge replicas (weno.f90:172-173)
       if (!s.out_dense && COMBINE != C_RHS) {
@@ -250,7 +251,7 @@ __device__ __forceinline__ void fv1d_finish(const Fv1dGeom &g, const StageArgs &
          if (g.phys_right) {
 #pragma unroll
             for (int j = 0; j < R; ++j)
-               if (i0 + j == g.n - 1) {
+               if (i0 + j == n - 1) {
 #pragma unroll
                   for (int q = 1; q <= K; ++q) orow[j + q] = res[j];
                }
@@ -272,19 +273,19 @@ __global__ void __launch_bounds__(NT, HRW_MINB) fv1d_stage_kernel(const Fv1dGeom
    __shared__ __align__(8) unsigned long long s_bar[2];
 
    const int tid = threadIdx.x;
-   const int64_t total_tiles = g.tiles_per_row * g.rows;
+   const int n = (int)g.n;                     // cells per row (< 2^31, validated at creation)
+   const int tpr = (int)g.tiles_per_row;
+   const int nrows = (int)g.rows;
 
    // one elected thread issues the bulk copy of a tile: cells [c0-R-P, c0-R-P+SM_N) clipped to the padded row
-   auto issue = [&](int64_t tile_id, int buf) {
-      const int64_t row = tile_id / g.tiles_per_row;
-      const int64_t c0 = (tile_id - row * g.tiles_per_row) * TILE;
-      const int64_t ts = c0 - R - P;
-      const int64_t lo = ts < -PAD ? (int64_t)-PAD : ts;
-      int64_t hi = ts + SM_N;
-      if (hi > g.ld - PAD) hi = g.ld - PAD;
-      const uint32_t bytes = (uint32_t)((hi - lo) * (int64_t)sizeof(double));
+   auto issue = [&](int row, int tcol, int buf) {
+      const int ts = tcol * TILE - R - P;
+      const int lo = ts < -PAD ? -PAD : ts;
+      int hi = ts + SM_N;
+      if (hi > (int)g.ld - PAD) hi = (int)g.ld - PAD;
+      const uint32_t bytes = (uint32_t)(hi - lo) * (uint32_t)sizeof(double);
       mbar_expect_tx(&s_bar[buf], bytes);
-      tma_bulk_g2s(&s_v[buf][lo - ts], s.vin + row * g.ld + lo, bytes, &s_bar[buf]);
+      tma_bulk_g2s(&s_v[buf][lo - ts], s.vin + (int64_t)row * g.ld + lo, bytes, &s_bar[buf]);
    };
 
    for (int idx = tid; idx < 2 * SM_N; idx += NT) (&s_v[0][0])[idx] = 0.0; // parts a clipped copy never writes
@@ -297,23 +298,67 @@ __global__ void __launch_bounds__(NT, HRW_MINB) fv1d_stage_kernel(const Fv1dGeom
       asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
    }
    __syncthreads();
-   if (tid == 0 && (int64_t)blockIdx.x < total_tiles) issue(blockIdx.x, 0);
+
+   // tiles are walked as (row, tile-in-row) pairs advanced by gridDim.x without any division in the loop
+   const int step_rows = (int)(gridDim.x / (unsigned)tpr), step_cols = (int)(gridDim.x % (unsigned)tpr);
+   int row = (int)(blockIdx.x / (unsigned)tpr), tcol = (int)(blockIdx.x % (unsigned)tpr);
+   if (tid == 0 && row < nrows) issue(row, tcol, 0);
 
    // stage coefficient with the sign of the divergence and, for Burgers/Godunov, the flux's exact 1/2 folded in:
    // dt*L = dt*(-(1/2) q) = (-dt/2)*q bit for bit (power-of-two scaling commutes with rounding)
    const double lscale = FK == FK_BURGERS_GODUNOV ? -0.5 : -1.0;
    const double cL = lscale * s.c0;
+   constexpr bool NEED_A = COMBINE == C_RK2_FINAL || COMBINE == C_RK3_S2 || COMBINE == C_RK3_S3 || COMBINE == C_MS;
 
-   int it = 0;
-   for (int64_t tile_id = blockIdx.x; tile_id < total_tiles; tile_id += gridDim.x, ++it) {
+   for (int it = 0; row < nrows; ++it) {
       const int buf = it & 1;
+      int nrow = row + step_rows, ntcol = tcol + step_cols;
+      if (ntcol >= tpr) {
+         ntcol -= tpr;
+         ++nrow;
+      }
       // prefetch the next tile into the other buffer: every thread finished reading it before the exchange
       // barrier of the previous iteration, which this thread has passed
-      if (tid == 0 && tile_id + gridDim.x < total_tiles) issue(tile_id + gridDim.x, buf ^ 1);
+      if (tid == 0 && nrow < nrows) issue(nrow, ntcol, buf ^ 1);
 
-      const int64_t row = tile_id / g.tiles_per_row;
-      const int64_t c0 = (tile_id - row * g.tiles_per_row) * TILE;
-      const int64_t i0 = c0 + (int64_t)(tid - 1) * R; // first owned cell (thread 0: the run left of the tile)
+      const int i0 = tcol * TILE + (tid - 1) * R; // first owned cell (thread 0: the run left of the tile)
+      // a caller's dense output array carries no alignment guarantee: scalar stores (edge path) for every thread
+      const bool skip = tid == 0 || tid == NT - 1 || i0 >= n;
+      const bool edge = s.out_dense || (i0 + R >= n) || (i0 == 0);
+
+      // interior threads: start the global loads of the pointwise operands and the width indices now
+      Prefetched<R> pf;
+      if (!skip && !edge) {
+         if constexpr (NEED_A) {
+            const double *ap = s.a + (int64_t)row * g.ld + i0;
+#pragma unroll
+            for (int j = 0; j < R; j += 2) {
+               const double2 t = __ldg(reinterpret_cast<const double2 *>(ap + j));
+               pf.av[j] = t.x;
+               pf.av[j + 1] = t.y;
+            }
+            if constexpr (COMBINE == C_MS) {
+               const double *bp = s.b + (int64_t)row * g.ld + i0;
+#pragma unroll
+               for (int j = 0; j < R; j += 2) {
+                  const double2 t = __ldg(reinterpret_cast<const double2 *>(bp + j));
+                  pf.bv[j] = t.x;
+                  pf.bv[j + 1] = t.y;
+               }
+            }
+         }
+         if constexpr (WK == WK_DICT) {
+#pragma unroll
+            for (int j = 0; j < R; j += 4) pf.idx4[j / 4] = __ldg(reinterpret_cast<const uint32_t *>(g.widx + i0 + j));
+         } else {
+#pragma unroll
+            for (int j = 0; j < R; j += 2) {
+               const double2 t = __ldg(reinterpret_cast<const double2 *>(g.width + i0 + j));
+               pf.wd[j] = t.x;
+               pf.wd[j + 1] = t.y;
+            }
+         }
+      }
 
       mbar_wait(&s_bar[buf], (uint32_t)((it >> 1) & 1));
 
@@ -333,16 +378,16 @@ __global__ void __launch_bounds__(NT, HRW_MINB) fv1d_stage_kernel(const Fv1dGeom
       s_vr[buf][tid] = vr[R - 1];
       s_vl[buf][tid] = vl[0];
       __syncthreads();
-      if (tid == 0 || tid == NT - 1 || i0 >= g.n) continue;
-      const double vr_left = s_vr[buf][tid - 1];
-      const double vl_right = s_vl[buf][tid + 1];
-
-      // a caller's dense output array carries no alignment guarantee: scalar stores (edge path) for every thread
-      const bool edge = s.out_dense || (i0 + R > g.n) || (i0 == 0) || (i0 + R == g.n);
-      if (!edge)
-         fv1d_finish<K, COMBINE, M, FK, WK, R, false>(g, s, s_wtab, row, i0, w, vl, vr, vr_left, vl_right, cL, lscale);
-      else
-         fv1d_finish<K, COMBINE, M, FK, WK, R, true>(g, s, s_wtab, row, i0, w, vl, vr, vr_left, vl_right, cL, lscale);
+      if (!skip) {
+         const double vr_left = s_vr[buf][tid - 1];
+         const double vl_right = s_vl[buf][tid + 1];
+         if (!edge)
+            fv1d_finish<K, COMBINE, M, FK, WK, R, false>(g, s, s_wtab, row, i0, w, vl, vr, vr_left, vl_right, cL, lscale, pf);
+         else
+            fv1d_finish<K, COMBINE, M, FK, WK, R, true>(g, s, s_wtab, row, i0, w, vl, vr, vr_left, vl_right, cL, lscale, pf);
+      }
+      row = nrow;
+      tcol = ntcol;
    }
 }
 
