@@ -31,6 +31,8 @@ Fv::~Fv() {
    fv_halo_free(this);
    cudaFree(d_width[0]);
    cudaFree(d_width[1]);
+   cudaFree(d_rwidth[0]);
+   cudaFree(d_rwidth[1]);
    cudaFree(d_wtab);
    cudaFree(d_widx);
    cudaFree(d_scratch_in);
@@ -44,6 +46,11 @@ static int upload_width(const double *host, int64_t n, double **dev) {
    HRW_CUDA(cudaMalloc(dev, tmp.size() * sizeof(double)));
    HRW_CUDA(cudaMemcpy(*dev, tmp.data(), tmp.size() * sizeof(double), cudaMemcpyHostToDevice));
    return HRWENO_OK;
+}
+
+__global__ void recip_array_kernel(const double *w, double *rw, int64_t n) {
+   const int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+   if (i < n) rw[i] = exact_recip(w[i]);
 }
 
 // refined reciprocals of the dictionary widths, computed with the very sequence the kernels' divisions use
@@ -191,7 +198,22 @@ int fv_create(Fv **out, const hrweno_fv_desc *desc) {
    if (desc->ndim == 1) {
       st = setup_width_1d(fv, desc);
    } else {
-      for (int a = 0; a < desc->ndim && st == HRWENO_OK; ++a) st = upload_width(desc->width[a], desc->n[a], &fv->d_width[a]);
+      for (int a = 0; a < desc->ndim && st == HRWENO_OK; ++a) {
+         for (int64_t i = 0; i < desc->n[a]; ++i)
+            if (!(desc->width[a][i] > 0x1p-200 && desc->width[a][i] < 0x1p200)) st = fail(HRWENO_EINVAL, "hrweno_fv_create: cell width outside (2^-200, 2^200)");
+         if (st == HRWENO_OK) st = upload_width(desc->width[a], desc->n[a], &fv->d_width[a]);
+         if (st == HRWENO_OK) {
+            const int64_t np = desc->n[a] + PAD;
+            cudaError_t e = cudaMalloc(&fv->d_rwidth[a], (size_t)np * sizeof(double));
+            if (e != cudaSuccess) {
+               st = cuda_fail(e, "cudaMalloc", __FILE__, __LINE__);
+            } else {
+               recip_array_kernel<<<(unsigned)((np + 255) / 256), 256>>>(fv->d_width[a], fv->d_rwidth[a], np);
+               e = cudaGetLastError();
+               if (e != cudaSuccess) st = cuda_fail(e, "recip_array_kernel", __FILE__, __LINE__);
+            }
+         }
+      }
    }
    if (st == HRWENO_OK) {
       cudaError_t e = cudaStreamCreateWithFlags(&fv->stream, cudaStreamNonBlocking);

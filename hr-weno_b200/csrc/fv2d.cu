@@ -20,7 +20,8 @@ struct Fv2dGeom {
    int64_t n0, n1;   // cells along x1 (contiguous) and x2 (local slab)
    int64_t pitch;    // padded row pitch
    int tiles_x, tiles_y;
-   const double *w1, *w2; // widths (device, padded)
+   const double *w1, *w2;   // widths (device, padded)
+   const double *rw1, *rw2; // their refined reciprocals (exact_recip)
    double eps;
    FluxCfg flux1, flux2;
    int bc;
@@ -135,7 +136,22 @@ __global__ void __launch_bounds__(NT) fv2d_stage_kernel(const Fv2dGeom g, const 
          for (int j = 1; j <= R; ++j)
             if (gy0 + j == g.n1) F2[j] = copy ? F2[j - 1] : 0.0;
       }
-      const double w1 = __ldg(g.w1 + gx);
+      const double w1 = __ldg(g.w1 + gx), rw1 = __ldg(g.rw1 + gx);
+      // pointwise operands first: out may alias a (and out2 alias b) element for element in the multistep stage, so
+      // loads issued after the first store could not be hoisted by the compiler and would serialise on DRAM latency
+      double av[R], bv[R], w2v[R], rw2v[R];
+#pragma unroll
+      for (int j = 0; j < R; ++j) {
+         const int64_t gy = gy0 + j;
+         const bool in = gy < g.n1;
+         const int64_t off = gy * g.pitch + gx;
+         av[j] = 0.0;
+         bv[j] = 0.0;
+         if (COMBINE == C_RK2_FINAL || COMBINE == C_RK3_S2 || COMBINE == C_RK3_S3 || COMBINE == C_MS) av[j] = in ? s.a[off] : 0.0;
+         if (COMBINE == C_MS) bv[j] = in ? s.b[off] : 0.0;
+         w2v[j] = __ldg(g.w2 + (in ? gy : gy0));
+         rw2v[j] = __ldg(g.rw2 + (in ? gy : gy0));
+      }
 #pragma unroll
       for (int j = 0; j < R; ++j) {
          const int64_t gy = gy0 + j;
@@ -153,9 +169,18 @@ __global__ void __launch_bounds__(NT) fv2d_stage_kernel(const Fv2dGeom g, const 
             if (gx == 0) Fl = 0.0;
             if (gx == g.n0 - 1) Fr = 0.0;
          }
-         const double w2 = __ldg(g.w2 + gy);
+         const double w2 = w2v[j];
          // vdot = -(f1(i)-f1(i-1))/w1(i) - (f2(j)-f2(j-1))/w2(j)   (example2:123-127)
-         const double L = M::sub(-M::div(M::sub(Fr, Fl), w1), M::div(M::sub(F2[j + 1], F2[j]), w2));
+         double L;
+         if constexpr (M::strict) {
+            // IEEE quotients from the precomputed refined reciprocals (common.cuh: exact_div_q), cold fallback
+            bool ok = true;
+            const double d1 = M::sub(Fr, Fl), d2 = M::sub(F2[j + 1], F2[j]);
+            L = M::sub(-exact_div_q(d1, w1, rw1, ok), exact_div_q(d2, w2, rw2v[j], ok));
+            if (!ok) L = M::sub(-M::div(d1, w1), M::div(d2, w2));
+         } else {
+            L = fma(-(F2[j + 1] - F2[j]), rw2v[j], -((Fr - Fl) * rw1));
+         }
          const double v = s_v[(ly + H) * T::SP + lx + H];
          const int64_t off = gy * g.pitch + gx;
          double o;
@@ -164,13 +189,13 @@ __global__ void __launch_bounds__(NT) fv2d_stage_kernel(const Fv2dGeom g, const 
          } else if (COMBINE == C_EULER) {
             o = M::add(v, M::mul(s.c0, L));
          } else if (COMBINE == C_RK2_FINAL) {
-            o = M::mul(M::add(M::add(s.a[off], v), M::mul(s.c0, L)), 0.5);
+            o = M::mul(M::add(M::add(av[j], v), M::mul(s.c0, L)), 0.5);
          } else if (COMBINE == C_RK3_S2) {
-            o = M::mul(M::add(M::add(M::mul(3.0, s.a[off]), v), M::mul(s.c0, L)), 0.25);
+            o = M::mul(M::add(M::add(M::mul(3.0, av[j]), v), M::mul(s.c0, L)), 0.25);
          } else if (COMBINE == C_RK3_S3) {
-            o = M::div(M::add(M::fma_exact(2.0, v, s.a[off]), M::mul(s.c0, L)), 3.0);
+            o = div3<M>(M::add(M::fma_exact(2.0, v, av[j]), M::mul(s.c0, L)));
          } else {
-            o = M::mul(M::add(M::add(M::add(M::mul(25.0, v), M::mul(s.c0, L)), M::mul(7.0, s.a[off])), M::mul(s.c1, s.b[off])),
+            o = M::mul(M::add(M::add(M::add(M::mul(25.0, v), M::mul(s.c0, L)), M::mul(7.0, av[j])), M::mul(s.c1, bv[j])),
                        0.03125);
             s.out2[off] = L;
          }
@@ -248,6 +273,8 @@ int fv2d_stage(Fv *fv, int combine, const StageArgs &args, cudaStream_t st) {
    g.tiles_y = (int)((fv->n1 + TY2 - 1) / TY2);
    g.w1 = fv->d_width[0];
    g.w2 = fv->d_width[1];
+   g.rw1 = fv->d_rwidth[0];
+   g.rw2 = fv->d_rwidth[1];
    g.eps = d.eps;
    g.flux1 = FluxCfg{d.flux_model, d.flux_scheme, d.flux_coef[0], d.alpha};
    g.flux2 = FluxCfg{d.flux_model, d.flux_scheme, d.flux_coef[1], d.alpha};

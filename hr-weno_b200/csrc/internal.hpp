@@ -57,6 +57,7 @@ struct Fv {
    int64_t pitch = 0;            // padded row pitch (doubles)
    int64_t nrows_alloc = 0;      // rows (1D) or n1 + 2*PAD2 (2D)
    double *d_width[2] = {nullptr, nullptr};
+   double *d_rwidth[2] = {nullptr, nullptr}; // 2D: refined reciprocals of the widths (exact_recip), same padding
    // 1D width dictionary: <= 256 distinct widths {w, refined reciprocal} + one byte per cell (fv1d.cuh)
    double2 *d_wtab = nullptr;
    unsigned char *d_widx = nullptr;

@@ -61,9 +61,12 @@ class FV:
         self.neq = _abi.lib().hrweno_fv_neq(self._h)
 
     def __del__(self):
-        if getattr(self, "_h", None) and self._h.value:
-            _abi.lib().hrweno_fv_destroy(self._h)
-            self._h = C.c_void_p()
+        try:
+            if getattr(self, "_h", None) and self._h.value:
+                _abi.lib().hrweno_fv_destroy(self._h)
+                self._h = C.c_void_p()
+        except Exception:  # interpreter shutdown: module globals are already gone
+            pass
 
     def rhs(self, t, v):
         v = np.ascontiguousarray(v, dtype=np.float64)

@@ -16,9 +16,12 @@ class _tvdode:
         self.msg = ""
 
     def __del__(self):
-        if getattr(self, "_h", None) and self._h.value:
-            _abi.lib().hrweno_ode_destroy(self._h)
-            self._h = C.c_void_p()
+        try:
+            if getattr(self, "_h", None) and self._h.value:
+                _abi.lib().hrweno_ode_destroy(self._h)
+                self._h = C.c_void_p()
+        except Exception:  # interpreter shutdown: module globals are already gone
+            pass
 
     def _created(self, st):
         if st != _abi.OK:

@@ -51,9 +51,12 @@ class weno:
         self.uniform_grid = xedges is None
 
     def __del__(self):
-        if getattr(self, "_h", None) and self._h.value:
-            _abi.lib().hrweno_weno_destroy(self._h)
-            self._h = C.c_void_p()
+        try:
+            if getattr(self, "_h", None) and self._h.value:
+                _abi.lib().hrweno_weno_destroy(self._h)
+                self._h = C.c_void_p()
+        except Exception:  # interpreter shutdown: module globals are already gone
+            pass
 
     @property
     def cnu(self):

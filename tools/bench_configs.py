@@ -1,0 +1,116 @@
+#!/usr/bin/env python
+"""Throughput of the other BASELINE.json configurations on one GPU (not the bench.py line).
+
+  cfg1: example1 as shipped (100 cells): latency per integrate call / per step
+  cfg2: example2 as shipped (250x250 mstvd): time for the whole run
+  cfg4: 2D linear advection WENO5+mstvd, 16384 x 16384 (or --n2d)
+  cfg5: batched ensemble 65536 rows x 4096 cells, k in {1,2,3} x rktvd order in {1,2,3}
+"""
+import argparse
+import os
+import sys
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+sys.path.insert(0, os.path.join(ROOT, "tests"))
+import __graft_entry__ as graft  # noqa: E402
+from conftest import ex1_ic, ex2_ic  # noqa: E402
+
+import torch  # noqa: E402
+
+ap = argparse.ArgumentParser()
+ap.add_argument("--n2d", type=int, default=16384)
+ap.add_argument("--rows", type=int, default=65536)
+ap.add_argument("--mode", default="strict")
+ap.add_argument("--only", default="")
+args = ap.parse_args()
+pkg = graft.load_package()
+MODE = pkg._abi.MODE_STRICT if args.mode == "strict" else pkg._abi.MODE_FAST
+PEAK = 6538.9
+stream = torch.cuda.current_stream().cuda_stream
+
+
+def timed(fn):
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    torch.cuda.synchronize()
+    e0.record()
+    fn()
+    e1.record()
+    torch.cuda.synchronize()
+    return e0.elapsed_time(e1) * 1e-3
+
+
+def steps_to(t, dt, k):
+    tt = t
+    for _ in range(k - 1):
+        tt = tt + dt
+    return tt
+
+
+if args.only in ("", "cfg1"):
+    g = pkg.hrweno_grids.grid1().linear(-5.0, 5.0, 100)
+    ode = pkg.hrweno_tvdode.rktvd(pkg.fv.FV(pkg.fv.make_desc(100, width=[g.width], mode=MODE)), 100, 3)
+    u, t = ex1_ic(g.center), 0.0
+    t = ode.integrate(u, t, 0.0, 1e-2)
+    w0 = time.perf_counter()
+    for ii in range(1, 101):
+        t = ode.integrate(u, t, 12.0 * ii / 100, 1e-2)
+    el = time.perf_counter() - w0
+    print(f"cfg1 example1 ({args.mode}): 100 integrate calls, 1200 steps in {el*1e3:.1f} ms -> {el/1200*1e6:.1f} us/step, {el/100*1e6:.0f} us per integrate call (host u, 12 steps)")
+
+if args.only in ("", "cfg2"):
+    n = 250
+    g = pkg.hrweno_grids.grid1().linear(0.0, 10.0, n)
+    ode = pkg.hrweno_tvdode.mstvd(pkg.fv.FV(pkg.fv.make_desc((n, n), flux_model=1, bc=1, width=[g.width, g.width], mode=MODE)), n * n)
+    u, t = ex2_ic(g.center, g.center).reshape(-1), 0.0
+    w0 = time.perf_counter()
+    for ii in range(101):
+        t = ode.integrate(u, t, 5.0 * ii / 100, 5e-3)
+    el = time.perf_counter() - w0
+    print(f"cfg2 example2 ({args.mode}): 101 integrate calls, 1001 steps in {el*1e3:.1f} ms -> {el/1001*1e6:.1f} us/step ({62500*1013/el:.3e} cell-rhs/s)")
+
+if args.only in ("", "cfg4"):
+    n = args.n2d
+    g = pkg.hrweno_grids.grid1().linear(0.0, 10.0, n)
+    fv = pkg.fv.FV(pkg.fv.make_desc((n, n), flux_model=1, bc=1, width=[g.width, g.width], mode=MODE))
+    ode = pkg.hrweno_tvdode.mstvd(fv, n * n)
+    c = g.center
+    rng = np.random.default_rng(12345)
+    u = ex2_ic(c, c)
+    u += 1e-3 * rng.standard_normal(u.shape)
+    ud = torch.from_numpy(u.reshape(-1)).cuda()
+    dt = 0.125 * 10.0 / n
+    t = ode.integrate_dev(ud.data_ptr(), 0.0, steps_to(0.0, dt, 6), dt, 1, stream)  # start-up (4 RK3) + 2 MS steps
+    K = 20
+    el = timed(lambda: ode.integrate_dev(ud.data_ptr(), t, steps_to(t, dt, K), dt, 1, stream))
+    cells = n * n
+    gbs = cells * 40.0 * K / el / 1e9
+    print(f"cfg4 2D {n}x{n} WENO5+mstvd ({args.mode}): {K} steps in {el*1e3:.1f} ms -> {cells*K/el:.3e} cell-steps/s, {gbs:.0f} GB/s algorithmic (40 B/cell-step) = {gbs/PEAK:.3f} of measured HBM peak")
+    del ode, fv, ud
+
+if args.only in ("", "cfg5"):
+    rows, nc = args.rows, 4096
+    g = pkg.hrweno_grids.grid1().linear(-5.0, 5.0, nc)
+    rng = np.random.default_rng(2024)
+    va, vb = rng.uniform(0.5, 1.5, rows), rng.uniform(-1.0, 0.0, rows)
+    xa, xb = rng.uniform(-4.5, -3.0, rows), rng.uniform(1.0, 3.0, rows)
+    x = g.center[None, :]
+    u0 = np.clip(va[:, None] + (vb - va)[:, None] / (xb - xa)[:, None] * (x - xa[:, None]), np.minimum(va, vb)[:, None], np.maximum(va, vb)[:, None])
+    ud0 = torch.from_numpy(u0.reshape(-1)).cuda()
+    dt = 0.1 * 10.0 / nc
+    bytes_step = {1: 16.0, 2: 40.0, 3: 64.0}
+    for k in (1, 2, 3):
+        for order in (1, 2, 3):
+            fv = pkg.fv.FV(pkg.fv.make_desc(nc, k=k, rows=rows, width=[g.width], mode=MODE))
+            ode = pkg.hrweno_tvdode.rktvd(fv, rows * nc, order)
+            ud = ud0.clone()
+            t = ode.integrate_dev(ud.data_ptr(), 0.0, steps_to(0.0, dt, 3), dt, 1, stream)
+            K = 10
+            el = timed(lambda: ode.integrate_dev(ud.data_ptr(), t, steps_to(t, dt, K), dt, 1, stream))
+            cells = rows * nc
+            gbs = cells * bytes_step[order] * K / el / 1e9
+            print(f"cfg5 ensemble {rows}x{nc} k={k} rktvd{order} ({args.mode}): {cells*order*K/el:.3e} cell-stages/s, {gbs:.0f} GB/s algorithmic = {gbs/PEAK:.3f} of peak")
+            del ode, fv, ud
