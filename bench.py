@@ -149,7 +149,8 @@ def main():
     ap.add_argument("--steps", type=int, default=20)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200")
-    ap.add_argument("--mode", default=os.environ.get("HRWENO_BENCH_MODE", "strict"), choices=["strict", "fast"])
+    ap.add_argument("--mode", default=os.environ.get("HRWENO_BENCH_MODE", "fast"), choices=["strict", "fast"])
+    ap.add_argument("--single-mode", action="store_true", help="skip the short measurement of the other arithmetic mode")
     ap.add_argument("--log2-cells", type=int, default=28)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     args = ap.parse_args()
@@ -174,117 +175,139 @@ def main():
     n = 1 << args.log2_cells  # cells per GPU (weak scaling)
     n_global = n * world
     dt = 0.1 * (XMAX - XMIN) / n_global
-    mode = pkg._abi.MODE_STRICT if args.mode == "strict" else pkg._abi.MODE_FAST
-    desc = pkg.fv.make_desc(n, k=3, eps=1e-6, linear=(XMIN, XMAX), mode=mode, rank=rank, nranks=world,
-                            global_n=n_global, global_offset=rank * n)
-    fv = pkg.fv.FV(desc)
-    pkg.slab.connect(fv, rank, world, pkg.slab.torch_all_gather(world))
-    ode = pkg.hrweno_tvdode.rktvd(fv, n, 3)
-
     u_host = torch.from_numpy(make_ic(n, rank * n, n_global)).pin_memory()
-    u_dev = u_host.cuda(non_blocking=False)
     stream = torch.cuda.current_stream().cuda_stream
-    t = 0.0
-    BIG = 1e30
-
-    def run_steps(k):
-        nonlocal t
-        # K steps in ONE integrate call: tout chosen so that exactly k steps are taken (strict is_done test)
-        tt = t
-        for _ in range(k - 1):
-            tt = tt + dt
-        t = ode.integrate_dev(u_dev.data_ptr(), t, tt, dt, 1, stream)
+    gather = pkg.slab.torch_all_gather(world)
 
     def barrier():
         if world > 1:
             dist.barrier()
         torch.cuda.synchronize()
 
-    run_steps(args.warmup)
-    barrier()
-
-    # ---- value: device-resident, K steps in one C-ABI call ------------------------------------------
-    sampler = ClockSampler(local_rank)
-    sampler.start()
-    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    launches0 = ode.launches
-    barrier()
-    e0.record()
-    run_steps(args.steps)
-    e1.record()
-    barrier()
-    ms = e0.elapsed_time(e1)
-    launches = ode.launches - launches0
-    # stage-kernel-only time: T(K steps) - T(1 step) removes the pack/unpack copies of the call
-    e2, e3 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    e2.record()
-    run_steps(1)
-    e3.record()
-    torch.cuda.synchronize()
-    ms1 = e2.elapsed_time(e3)
-    clocks = sampler.stop()
-    if world > 1:
-        tmax = torch.tensor([ms, ms1], device="cuda", dtype=torch.float64)
+    def allmax(*vals):
+        if world == 1:
+            return vals
+        tmax = torch.tensor(vals, device="cuda", dtype=torch.float64)
         dist.all_reduce(tmax, op=dist.ReduceOp.MAX)
-        ms, ms1 = float(tmax[0]), float(tmax[1])
+        return tuple(float(x) for x in tmax)
 
-    # ---- e2e: host (pinned) u through the host-pointer C-ABI call, copies inside the timed region -----
-    t_e2e = 0.0
-    u_np = u_host.numpy()
+    def measure(mode_name, steps, warmup, with_e2e):
+        """one full measurement in one arithmetic mode: device-resident K steps, stage-kernel time, e2e"""
+        mode = pkg._abi.MODE_STRICT if mode_name == "strict" else pkg._abi.MODE_FAST
+        desc = pkg.fv.make_desc(n, k=3, eps=1e-6, linear=(XMIN, XMAX), mode=mode, rank=rank, nranks=world,
+                                global_n=n_global, global_offset=rank * n)
+        fv = pkg.fv.FV(desc)
+        pkg.slab.connect(fv, rank, world, gather)
+        ode = pkg.hrweno_tvdode.rktvd(fv, n, 3)
+        u_dev = u_host.cuda(non_blocking=False)
+        state = {"t": 0.0, "te": 0.0}
 
-    def e2e_call(k):
-        nonlocal t_e2e
-        tt = t_e2e
-        for _ in range(k - 1):
-            tt = tt + dt
-        t_e2e = ode.integrate(u_np, t_e2e, tt, dt)
+        def run_steps(k):
+            # k steps in ONE integrate call: tout = t after k-1 steps, the strict is_done test then takes exactly k
+            tt = state["t"]
+            for _ in range(k - 1):
+                tt = tt + dt
+            state["t"] = ode.integrate_dev(u_dev.data_ptr(), state["t"], tt, dt, 1, stream)
 
-    e2e_call(1)
-    barrier()
-    w0 = time.perf_counter()
-    e2e_call(args.steps)
-    barrier()
-    e2e_s = time.perf_counter() - w0
-    if world > 1:
-        tm = torch.tensor([e2e_s], device="cuda", dtype=torch.float64)
-        dist.all_reduce(tm, op=dist.ReduceOp.MAX)
-        e2e_s = float(tm[0])
+        run_steps(warmup)
+        barrier()
+        sampler = ClockSampler(local_rank)
+        sampler.start()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        launches0 = ode.launches
+        barrier()
+        e0.record()
+        run_steps(steps)
+        e1.record()
+        barrier()
+        ms = e0.elapsed_time(e1)
+        launches = ode.launches - launches0
+        # stage-kernel-only time: T(K steps) - T(1 step) removes the pack/unpack copies of the call
+        e2, e3 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e2.record()
+        run_steps(1)
+        e3.record()
+        torch.cuda.synchronize()
+        ms1 = e2.elapsed_time(e3)
+        clocks = sampler.stop()
+        ms, ms1 = allmax(ms, ms1)
+        out = {"ms": ms, "ms1": ms1, "launches": int(launches), "clocks": clocks}
+        if with_e2e:
+            # host (pinned) u through the host-pointer C-ABI call, copies inside the timed region
+            u_np = u_host.numpy()
+
+            def e2e_call(k):
+                tt = state["te"]
+                for _ in range(k - 1):
+                    tt = tt + dt
+                state["te"] = ode.integrate(u_np, state["te"], tt, dt)
+
+            e2e_call(1)
+            barrier()
+            w0 = time.perf_counter()
+            e2e_call(steps)
+            barrier()
+            (out["e2e_s"],) = allmax(time.perf_counter() - w0)
+        del ode, fv, u_dev
+        torch.cuda.empty_cache()
+        return out
+
+    K = args.steps
+    main_m = measure(args.mode, K, args.warmup, True)
+    other = "strict" if args.mode == "fast" else "fast"
+    other_m = measure(other, max(2, min(K, 5)), 3, False) if not args.single_mode else None
 
     if rank != 0:
         if world > 1:
             dist.destroy_process_group()
         return
 
-    K = args.steps
-    value = n_global * 3 * K / (ms * 1e-3)
-    stage_ms = (ms - ms1) / (3 * (K - 1)) if K > 1 else ms / 3
     peak, peak_src = peaks()
-    achieved = n * (RK3_BYTES_PER_CELL_STEP / 3) / (stage_ms * 1e-3) / 1e9
+
+    def derive(m, k):
+        stage_ms = (m["ms"] - m["ms1"]) / (3 * (k - 1)) if k > 1 else m["ms"] / 3
+        achieved = n * (RK3_BYTES_PER_CELL_STEP / 3) / (stage_ms * 1e-3) / 1e9
+        return n_global * 3 * k / (m["ms"] * 1e-3), stage_ms, achieved
+
+    value, stage_ms, achieved = derive(main_m, K)
+    traffic = None
+    tp = os.path.join(ROOT, "profiles", "traffic.json")
+    if os.path.exists(tp):
+        tj = json.load(open(tp)).get(args.mode, {})
+        if tj.get("log2_cells") == args.log2_cells:
+            traffic = tj.get("dram_bytes_per_launch")
     line = {
         "metric": "WENO5+RK3 cell-updates/s", "value": value, "unit": "cell-updates/s", "n_gpus": world, "steps": K,
-        "warmup": args.warmup, "ms_per_step": ms / K, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+        "warmup": args.warmup, "ms_per_step": main_m["ms"] / K, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
         "dtype": "f64", "data": "synthetic",
         "config": {
             "workload": "cfg3: 1D Burgers WENO5(k=3,eps=1e-6)+Godunov+rktvd(3), 2^%d cells per GPU, linear grid [-5,5], "
                         "ramp+1e-3*N(0,1) IC (rng 12345), dt=0.1dx" % args.log2_cells,
-            "cells_per_gpu": n, "mode": args.mode, "parallelism": "slab x%d (halo k=3 per stage)" % world if world > 1 else "1 GPU",
+            "cells_per_gpu": n, "mode": args.mode,
+            "parity": "strict = bit-identical to the oracle; fast = within 1e-12 normwise per output time (tests/test_gpu_parity.py)",
+            "parallelism": "slab x%d (halo k=3 per stage over NVLink peer memory)" % world if world > 1 else "1 GPU",
             "l2": "state vectors are 2 GiB each, far larger than the 126 MB L2 (no flush needed)",
             "unit_note": "one cell-update = one cell-stage (rhs + stage combination); cell-steps/s = value/3",
         },
         "cell_steps_per_s": value / 3,
-        "gpu_launches": int(launches),
-        "clocks": clocks,
+        "gpu_launches": main_m["launches"],
+        "clocks": main_m["clocks"],
         "roofline": {
-            "bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": None,
-            "kernel": "fv1d_stage_kernel<K=3> (average of the 3 RK3 stage instantiations)",
+            "bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": traffic,
+            "kernel": "fv1d_stage_kernel<K=3> (average of the 3 RK3 stage instantiations; 16/24/24 algorithmic B per cell)",
             "algorithmic_bytes_per_launch": n * RK3_BYTES_PER_CELL_STEP / 3, "avg_launch_ms": stage_ms, "peak_source": peak_src,
+            "note": "fp64 WENO5 is bound by fp64 instruction issue on B200, not by HBM (DESIGN.md section 5)",
         },
         "e2e": {
-            "value": n_global * 3 * K / e2e_s, "unit": "cell-updates/s",
+            "value": n_global * 3 * K / main_m["e2e_s"], "unit": "cell-updates/s",
             "h2d_bytes_per_step": n * 8 / K, "d2h_bytes_per_step": n * 8 / K,
-            "note": "one hrweno_ode_integrate call with a pinned host u advancing K steps: H2D u, 3K fused stages, D2H u",
+            "note": "one hrweno_ode_integrate call with a pinned host u advancing K steps: H2D u (8n B), 3K fused stages, D2H u (8n B)",
         },
     }
+    if other_m is not None:
+        ko = max(2, min(K, 5))
+        v2, sm2, ach2 = derive(other_m, ko)
+        line["other_mode"] = {"mode": other, "value": v2, "steps": ko, "avg_launch_ms": sm2, "roofline_frac": ach2 / peak}
     if not args.no_cpu_baseline:
         line["cpu_baseline"] = cpu_baseline_leg(pkg)
     print(json.dumps(line))
