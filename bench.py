@@ -45,43 +45,71 @@ def make_ic(n, offset=0, n_global=None, seed=12345):
 
 
 class ClockSampler(threading.Thread):
-    """nvidia-smi clocks / throttle reasons during the timed region (B200_PROFILING.md recipe)"""
+    """SM clock / power / throttle reasons sampled DURING the timed region (NVML every 5 ms; the nvidia-smi query
+    of B200_PROFILING.md once as a cross-check)."""
 
-    Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
-         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+    REASONS = {0x8: "hw_slowdown", 0x40: "hw_thermal_slowdown", 0x20: "sw_thermal_slowdown", 0x4: "sw_power_cap"}
 
     def __init__(self, index):
         super().__init__(daemon=True)
-        self.index, self.rows, self._stop_evt = index, [], threading.Event()
+        self.index, self.sm, self.power, self.bits, self._stop_evt = index, [], [], 0, threading.Event()
+        self.sm_max, self.err = None, None
+        try:
+            import pynvml
+
+            pynvml.nvmlInit()
+            vis = os.environ.get("CUDA_VISIBLE_DEVICES")
+            phys = int(vis.split(",")[index]) if vis and vis.split(",")[index].isdigit() else index
+            self.nv, self.h = pynvml, pynvml.nvmlDeviceGetHandleByIndex(phys)
+            self.sm_max = float(pynvml.nvmlDeviceGetMaxClockInfo(self.h, pynvml.NVML_CLOCK_SM))
+        except Exception as e:  # NVML missing: fall back to nvidia-smi sampling
+            self.nv, self.err = None, repr(e)
+
+    def _smi_once(self):
+        q = "clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown," \
+            "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap"
+        try:
+            out = subprocess.run(["nvidia-smi", f"--id={self.index}", f"--query-gpu={q}", "--format=csv,noheader,nounits"],
+                                 capture_output=True, text=True, timeout=5).stdout.strip()
+            r = [c.strip() for c in out.split(",")]
+            self.sm.append(float(r[0]))
+            self.sm_max = self.sm_max or float(r[1])
+            self.power.append(float(r[2]))
+            for bit, val in zip((0x8, 0x40, 0x20, 0x4), r[3:7]):
+                if val.lower().startswith("active"):
+                    self.bits |= bit
+        except Exception:
+            pass
 
     def run(self):
         while not self._stop_evt.is_set():
-            try:
-                out = subprocess.run(
-                    ["nvidia-smi", f"--id={self.index}", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits"],
-                    capture_output=True, text=True, timeout=5).stdout.strip()
-                if out:
-                    self.rows.append([c.strip() for c in out.split(",")])
-            except Exception:
-                pass
-            self._stop_evt.wait(0.2)
+            if self.nv is not None:
+                try:
+                    self.sm.append(float(self.nv.nvmlDeviceGetClockInfo(self.h, self.nv.NVML_CLOCK_SM)))
+                    self.power.append(self.nv.nvmlDeviceGetPowerUsage(self.h) / 1000.0)
+                    self.bits |= int(self.nv.nvmlDeviceGetCurrentClocksEventReasons(self.h))
+                except Exception:
+                    try:
+                        self.bits |= int(self.nv.nvmlDeviceGetCurrentClocksThrottleReasons(self.h))
+                    except Exception:
+                        pass
+                self._stop_evt.wait(0.005)
+            else:
+                self._smi_once()
+                self._stop_evt.wait(0.05)
 
     def stop(self):
         self._stop_evt.set()
         self.join(timeout=6)
-        sm = sorted(float(r[0]) for r in self.rows if r and r[0].replace(".", "").isdigit())
-        reasons = set()
-        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
-        for r in self.rows:
-            for nm, val in zip(names, r[3:7]):
-                if val.lower().startswith("active"):
-                    reasons.add(nm)
+        sm = sorted(self.sm)
         return {
             "sm_mhz": sm[len(sm) // 2] if sm else None,
-            "sm_max_mhz": float(self.rows[0][1]) if self.rows else None,
-            "power_w_max": max((float(r[2]) for r in self.rows if r[2].replace(".", "").isdigit()), default=None),
-            "reasons": sorted(reasons),
-            "samples": len(self.rows),
+            "sm_min_mhz": sm[0] if sm else None,
+            "sm_max_mhz": self.sm_max,
+            "power_w_max": max(self.power, default=None),
+            "reasons": sorted(name for bit, name in self.REASONS.items() if self.bits & bit),
+            "samples": len(sm),
+            "source": "nvml 5 ms" if self.nv is not None else "nvidia-smi",
         }
 
 
