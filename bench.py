@@ -86,14 +86,12 @@ class ClockSampler(threading.Thread):
             if self.nv is not None:
                 try:
                     self.sm.append(float(self.nv.nvmlDeviceGetClockInfo(self.h, self.nv.NVML_CLOCK_SM)))
-                    self.power.append(self.nv.nvmlDeviceGetPowerUsage(self.h) / 1000.0)
-                    self.bits |= int(self.nv.nvmlDeviceGetCurrentClocksEventReasons(self.h))
-                except Exception:
-                    try:
-                        self.bits |= int(self.nv.nvmlDeviceGetCurrentClocksThrottleReasons(self.h))
-                    except Exception:
-                        pass
-                self._stop_evt.wait(0.005)
+                    self.bits |= int(self.nv.nvmlDeviceGetCurrentClocksThrottleReasons(self.h))
+                    if len(self.sm) % 8 == 1:  # the power query is slow: every 8th sample
+                        self.power.append(self.nv.nvmlDeviceGetPowerUsage(self.h) / 1000.0)
+                except Exception as e:
+                    self.err = repr(e)
+                self._stop_evt.wait(0.002)
             else:
                 self._smi_once()
                 self._stop_evt.wait(0.05)

@@ -186,7 +186,14 @@ __device__ __forceinline__ void fv1d_finish(const Fv1dGeom &g, const StageArgs &
          q = dF * wr[j];
       const double v = w[2 + j];
       double o;
-      if constexpr (COMBINE == C_RHS) {
+      constexpr bool FOLD = !M::strict && WK == WK_DICT && (COMBINE == C_EULER || COMBINE == C_RK2_FINAL || COMBINE == C_RK3_S2 || COMBINE == C_RK3_S3);
+      if constexpr (FOLD) {
+         // wr already carries the stage coefficient: q == dt*L
+         if constexpr (COMBINE == C_EULER) o = v + q;
+         if constexpr (COMBINE == C_RK2_FINAL) o = ((av[j] + v) + q) * 0.5;
+         if constexpr (COMBINE == C_RK3_S2) o = (fma(3.0, av[j], v) + q) * 0.25;
+         if constexpr (COMBINE == C_RK3_S3) o = div3<M>(fma(2.0, v, av[j]) + q);
+      } else if constexpr (COMBINE == C_RHS) {
          o = M::mul(lscale, q);
       } else if constexpr (COMBINE == C_EULER) {
          o = M::add(v, M::mul(cL, q)); // u + dt*udot
@@ -289,8 +296,18 @@ __global__ void __launch_bounds__(NT, HRW_MINB) fv1d_stage_kernel(const Fv1dGeom
    };
 
    for (int idx = tid; idx < 2 * SM_N; idx += NT) (&s_v[0][0])[idx] = 0.0; // parts a clipped copy never writes
+   // stage coefficient with the sign of the divergence and, for Burgers/Godunov, the flux's exact 1/2 folded in:
+   // dt*L = dt*(-(1/2) q) = (-dt/2)*q bit for bit (power-of-two scaling commutes with rounding)
+   const double lscale = FK == FK_BURGERS_GODUNOV ? -0.5 : -1.0;
+   const double cL = lscale * s.c0;
+   // fast mode with a width dictionary: the table carries cL/w, so (dt*L) is one multiply of the flux difference
+   constexpr bool FOLD = !M::strict && WK == WK_DICT && (COMBINE == C_EULER || COMBINE == C_RK2_FINAL || COMBINE == C_RK3_S2 || COMBINE == C_RK3_S3);
    if constexpr (WK == WK_DICT)
-      for (int idx = tid; idx < 256; idx += NT) s_wtab[idx] = g.wtab[idx];
+      for (int idx = tid; idx < 256; idx += NT) {
+         double2 e = g.wtab[idx];
+         if constexpr (FOLD) e.y *= cL;
+         s_wtab[idx] = e;
+      }
    asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); // order the generic-proxy zero fill before async-proxy writes
    if (tid == 0) {
       mbar_init(&s_bar[0], 1);
@@ -304,10 +321,6 @@ __global__ void __launch_bounds__(NT, HRW_MINB) fv1d_stage_kernel(const Fv1dGeom
    int row = (int)(blockIdx.x / (unsigned)tpr), tcol = (int)(blockIdx.x % (unsigned)tpr);
    if (tid == 0 && row < nrows) issue(row, tcol, 0);
 
-   // stage coefficient with the sign of the divergence and, for Burgers/Godunov, the flux's exact 1/2 folded in:
-   // dt*L = dt*(-(1/2) q) = (-dt/2)*q bit for bit (power-of-two scaling commutes with rounding)
-   const double lscale = FK == FK_BURGERS_GODUNOV ? -0.5 : -1.0;
-   const double cL = lscale * s.c0;
    constexpr bool NEED_A = COMBINE == C_RK2_FINAL || COMBINE == C_RK3_S2 || COMBINE == C_RK3_S3 || COMBINE == C_MS;
 
    for (int it = 0; row < nrows; ++it) {

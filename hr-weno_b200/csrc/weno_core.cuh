@@ -208,34 +208,40 @@ __device__ __forceinline__ void weno_run_k3(const double *w, double eps, double 
 template <int R>
 __device__ __forceinline__ void weno_run_k3_fast(const double *w, double eps, double *vl, double *vr) {
    constexpr int N = R + 4;
-   const double C13 = 1.0 / 3, C56 = 5.0 / 6, C16 = -1.0 / 6, C76 = -7.0 / 6, C116 = 11.0 / 6;
+   const double C13 = 1.0 / 3, C56 = 5.0 / 6, C16 = -1.0 / 6;
    const double eps4 = 4.0 * eps;
-   double m2[N]; // (13/3) * (v[j-1] - 2 v[j] + v[j+1])**2
+   // second differences d2[j] = v[j-1] - 2 v[j] + v[j+1]; m2e[j] = eps' + (13/3) d2^2; third differences D3[j] = d2[j+1] - d2[j]
+   double d2[N], m2e[N], D3[N];
 #pragma unroll
    for (int j = 1; j < N - 1; ++j) {
-      const double d2 = fma(-2.0, w[j], w[j - 1]) + w[j + 1];
-      m2[j] = (13.0 / 3) * (d2 * d2);
+      d2[j] = fma(-2.0, w[j], w[j - 1]) + w[j + 1];
+      m2e[j] = fma((13.0 / 3) * d2[j], d2[j], eps4);
    }
-   double A0[N], A1[N];
+#pragma unroll
+   for (int j = 1; j < N - 2; ++j) D3[j] = d2[j + 1] - d2[j];
+   // the three candidates of a side differ by multiples of a third difference (Shu eq. 2.11 coefficients):
+   //   vrr1 = (-v[c-1] + 5 v[c] + 2 v[c+1])/6,  vrr0 = vrr1 - D3[c]/6,  vrr2 = vrr1 - D3[c-1]/3,
+   //   vlr1 = vrr0 of cell c-1,  vlr2 = vrr1 of cell c-1,  vlr0 = vlr1 + D3[c]/3
+   double V1[N], V0[N];
 #pragma unroll
    for (int j = 1; j < R + 2; ++j) {
-      A0[j] = fma(C16, w[j + 2], fma(C56, w[j + 1], C13 * w[j]));
-      A1[j] = fma(C13, w[j + 1], fma(C56, w[j], C16 * w[j - 1]));
+      V1[j] = fma(C13, w[j + 1], fma(C56, w[j], C16 * w[j - 1]));
+      V0[j] = fma(C16, D3[j], V1[j]);
    }
 #pragma unroll
    for (int j = 0; j < R; ++j) {
       const int c = j + 2;
-      const double vrr0 = A0[c], vrr1 = A1[c];
-      const double vrr2 = fma(C116, w[c], fma(C76, w[c - 1], C13 * w[c - 2]));
-      const double vlr0 = fma(C13, w[c + 2], fma(C76, w[c + 1], C116 * w[c]));
-      const double vlr1 = A0[c - 1], vlr2 = A1[c - 1];
+      const double vrr0 = V0[c], vrr1 = V1[c];
+      const double vrr2 = fma(-C13, D3[c - 1], vrr1);
+      const double vlr1 = V0[c - 1], vlr2 = V1[c - 1];
+      const double vlr0 = fma(C13, D3[c], vlr1);
       const double t3 = 3.0 * w[c];
       const double b0 = fma(-4.0, w[c + 1], t3) + w[c + 2];
       const double b1 = w[c - 1] - w[c + 1];
       const double b2 = fma(-4.0, w[c - 1], w[c - 2]) + t3;
-      const double e0 = eps4 + fma(b0, b0, m2[c + 1]);
-      const double e1 = eps4 + fma(b1, b1, m2[c]);
-      const double e2 = eps4 + fma(b2, b2, m2[c - 1]);
+      const double e0 = fma(b0, b0, m2e[c + 1]);
+      const double e1 = fma(b1, b1, m2e[c]);
+      const double e2 = fma(b2, b2, m2e[c - 1]);
       const double den0 = e0 * e0, den1 = e1 * e1, den2 = e2 * e2;
       const double P0 = den1 * den2, P2 = den0 * den1;
       const double Q1 = 6.0 * (den0 * den2), T0 = 3.0 * P0, T2 = 3.0 * P2;
