@@ -48,7 +48,149 @@ struct Tile2d {
    static constexpr size_t BYTES = (size_t)TOTAL * sizeof(double);
 };
 
-template <int K, int COMBINE, class M, int TX, int TY, int NT>
+// UPW = 1: linear flux f = a*v with a >= 0 in both directions and the Godunov rule.  Then vm <= vp implies
+// a*vm <= a*vp (rounding is monotone), so godunov (fluxes.f90:70-74) returns f(vm) = a*vr(i) in every case and
+// vl never influences the result (SURVEY 3.2 notes this for example2): the left-side reconstruction is skipped.
+// The result is bit-identical to evaluating both sides.
+template <int UPW, class M>
+__device__ __forceinline__ double face2d(const FluxCfg &c, double vm, double vp) {
+   if constexpr (UPW) {
+      return M::mul(c.coef, vm);
+   } else {
+      return face_flux<M>(c, vm, vp);
+   }
+}
+
+// phase B for one thread = (column lx, run of R rows).  INTERIOR: the tile touches no domain edge and is complete.
+template <int K, int COMBINE, class M, int UPW, int TX, int TY, bool INTERIOR>
+__device__ __forceinline__ void fv2d_phase_b(const Fv2dGeom &g, const StageArgs &s, const double *s_v, const double *s_vlx,
+                                             const double *s_vrx, const double *s_vly, const double *s_vry, int64_t x0, int64_t y0,
+                                             int lx, int ly0) {
+   using T = Tile2d<TX, TY>;
+   constexpr int R = T::R, H = T::H;
+   const int64_t gx = x0 + lx, gy0 = y0 + ly0;
+   if constexpr (!INTERIOR) {
+      if (gx >= g.n0 || gy0 >= g.n1) return;
+   }
+   const bool copy = g.bc == HRWENO_BC_COPY_NEIGHBOUR;
+   // x2-faces gy0 .. gy0+R of column gx: face f lies between rows f-1 and f; array row index = local row + R
+   double F2[R + 1];
+#pragma unroll
+   for (int j = 0; j <= R; ++j) {
+      const double vm = s_vry[(ly0 + j - 1 + R) * TX + lx];
+      const double vp = UPW ? 0.0 : s_vly[(ly0 + j + R) * TX + lx];
+      F2[j] = face2d<UPW, M>(g.flux2, vm, vp);
+   }
+   if constexpr (!INTERIOR) {
+      if (g.phys_lo && gy0 == 0) F2[0] = copy ? F2[1] : 0.0;
+      if (g.phys_hi) {
+#pragma unroll
+         for (int j = 1; j <= R; ++j)
+            if (gy0 + j == g.n1) F2[j] = copy ? F2[j - 1] : 0.0;
+      }
+   }
+   const double w1 = __ldg(g.w1 + gx), rw1 = __ldg(g.rw1 + gx);
+   // pointwise operands first: out may alias a (and out2 alias b) element for element in the multistep stage, so
+   // loads issued after the first store could not be hoisted by the compiler and would serialise on DRAM latency
+   constexpr bool NEED_A = COMBINE == C_RK2_FINAL || COMBINE == C_RK3_S2 || COMBINE == C_RK3_S3 || COMBINE == C_MS;
+   double av[R], bv[R], w2v[R], rw2v[R];
+#pragma unroll
+   for (int j = 0; j < R; ++j) {
+      const int64_t gy = gy0 + j;
+      const bool in = INTERIOR || gy < g.n1;
+      const int64_t off = gy * g.pitch + gx;
+      av[j] = 0.0;
+      bv[j] = 0.0;
+      if constexpr (NEED_A) av[j] = in ? s.a[off] : 0.0;
+      if constexpr (COMBINE == C_MS) bv[j] = in ? s.b[off] : 0.0;
+      w2v[j] = __ldg(g.w2 + (in ? gy : gy0));
+      rw2v[j] = __ldg(g.rw2 + (in ? gy : gy0));
+   }
+   double res[R], lres[R];
+#pragma unroll
+   for (int j = 0; j < R; ++j) {
+      const int ly = ly0 + j;
+      // x1-faces gx and gx+1 of row gy
+      const double *vlx = s_vlx + ly * T::XP + R + lx, *vrx = s_vrx + ly * T::XP + R + lx;
+      double Fl = face2d<UPW, M>(g.flux1, vrx[-1], UPW ? 0.0 : vlx[0]);
+      double Fr = face2d<UPW, M>(g.flux1, vrx[0], UPW ? 0.0 : vlx[1]);
+      if constexpr (!INTERIOR) {
+         if (copy) { // fedges(0) = fedges(1), fedges(nc) = fedges(nc-1)
+            if (gx == 0) Fl = Fr;
+            if (gx == g.n0 - 1) Fr = Fl;
+         } else {
+            if (gx == 0) Fl = 0.0;
+            if (gx == g.n0 - 1) Fr = 0.0;
+         }
+      }
+      // vdot = -(f1(i)-f1(i-1))/w1(i) - (f2(j)-f2(j-1))/w2(j)   (example2:123-127)
+      double L;
+      if constexpr (M::strict) {
+         // IEEE quotients from the precomputed refined reciprocals (common.cuh: exact_div_q), cold fallback
+         bool ok = true;
+         const double d1 = M::sub(Fr, Fl), d2 = M::sub(F2[j + 1], F2[j]);
+         L = M::sub(-exact_div_q(d1, w1, rw1, ok), exact_div_q(d2, w2v[j], rw2v[j], ok));
+         if (!ok) L = M::sub(-M::div(d1, w1), M::div(d2, w2v[j]));
+      } else {
+         L = fma(-(F2[j + 1] - F2[j]), rw2v[j], -((Fr - Fl) * rw1));
+      }
+      const double v = s_v[(ly + H) * T::SP + lx + H];
+      double o;
+      if constexpr (COMBINE == C_RHS) {
+         o = L;
+      } else if constexpr (COMBINE == C_EULER) {
+         o = M::add(v, M::mul(s.c0, L));
+      } else if constexpr (COMBINE == C_RK2_FINAL) {
+         o = M::mul(M::add(M::add(av[j], v), M::mul(s.c0, L)), 0.5);
+      } else if constexpr (COMBINE == C_RK3_S2) {
+         o = M::mul(M::add(M::add(M::mul(3.0, av[j]), v), M::mul(s.c0, L)), 0.25);
+      } else if constexpr (COMBINE == C_RK3_S3) {
+         o = div3<M>(M::add(M::fma_exact(2.0, v, av[j]), M::mul(s.c0, L)));
+      } else {
+         o = M::mul(M::add(M::add(M::add(M::mul(25.0, v), M::mul(s.c0, L)), M::mul(7.0, av[j])), M::mul(s.c1, bv[j])), 0.03125);
+         lres[j] = L;
+      }
+      res[j] = o;
+   }
+#pragma unroll
+   for (int j = 0; j < R; ++j) {
+      const int64_t gy = gy0 + j;
+      if constexpr (!INTERIOR) {
+         if (gy >= g.n1) break;
+      }
+      const int64_t off = gy * g.pitch + gx;
+      const double o = res[j];
+      if constexpr (COMBINE == C_MS) s.out2[off] = lres[j];
+      if constexpr (INTERIOR) {
+         s.out[off] = o;
+      } else if (s.out_dense) {
+         s.out[gy * s.ld_out + gx] = o;
+      } else {
+         s.out[off] = o;
+         if (COMBINE != C_RHS) {
+            // ghost cells of the result at physical boundaries (edge replicas, weno.f90:172-173)
+            if (gx == 0) {
+#pragma unroll
+               for (int q = 1; q <= K; ++q) s.out[off - q] = o;
+            }
+            if (gx == g.n0 - 1) {
+#pragma unroll
+               for (int q = 1; q <= K; ++q) s.out[off + q] = o;
+            }
+            if (g.phys_lo && gy == 0) {
+#pragma unroll
+               for (int q = 1; q <= K; ++q) s.out[off - q * g.pitch] = o;
+            }
+            if (g.phys_hi && gy == g.n1 - 1) {
+#pragma unroll
+               for (int q = 1; q <= K; ++q) s.out[off + q * g.pitch] = o;
+            }
+         }
+      }
+   }
+}
+
+template <int K, int COMBINE, class M, int UPW, int TX, int TY, int NT>
 __global__ void __launch_bounds__(NT) fv2d_stage_kernel(const Fv2dGeom g, const StageArgs s) {
    using T = Tile2d<TX, TY>;
    constexpr int R = T::R, H = T::H;
@@ -106,133 +248,30 @@ __global__ void __launch_bounds__(NT) fv2d_stage_kernel(const Fv2dGeom g, const 
       weno_run<K, R, M>(w + (2 - (K - 1)), g.eps, vl, vr);
 #pragma unroll
       for (int j = 0; j < R; ++j) {
-         ovl[oidx + j * ostride] = vl[j];
+         if constexpr (!UPW) ovl[oidx + j * ostride] = vl[j]; // upwind: the left side is never used and is eliminated
          ovr[oidx + j * ostride] = vr[j];
       }
    }
    __syncthreads();
 
    // ---- phase B: fluxes, divergence, combination ---------------------------------------------------------
-   const bool copy = g.bc == HRWENO_BC_COPY_NEIGHBOUR;
+   const bool interior = !s.out_dense && x0 > 0 && x0 + TX < g.n0 && y0 > 0 && y0 + TY < g.n1;
    for (int it = tid; it < TX * (TY / R); it += NT) {
       const int ryi = it / TX;
       const int lx = it - ryi * TX;
-      const int ly0 = ryi * R;
-      const int64_t gx = x0 + lx, gy0 = y0 + ly0;
-      if (gx >= g.n0 || gy0 >= g.n1) continue;
-
-      // x2-faces gy0 .. gy0+R of column gx: face f lies between rows f-1 and f
-      double F2[R + 1];
-#pragma unroll
-      for (int j = 0; j <= R; ++j) {
-         // vr of row (ly0+j-1), vl of row (ly0+j); array row index = local row + R
-         const double vm = s_vry[(ly0 + j - 1 + R) * TX + lx];
-         const double vp = s_vly[(ly0 + j + R) * TX + lx];
-         F2[j] = face_flux<M>(g.flux2, vm, vp);
-      }
-      if (g.phys_lo && gy0 == 0) F2[0] = copy ? F2[1] : 0.0;
-      if (g.phys_hi) {
-#pragma unroll
-         for (int j = 1; j <= R; ++j)
-            if (gy0 + j == g.n1) F2[j] = copy ? F2[j - 1] : 0.0;
-      }
-      const double w1 = __ldg(g.w1 + gx), rw1 = __ldg(g.rw1 + gx);
-      // pointwise operands first: out may alias a (and out2 alias b) element for element in the multistep stage, so
-      // loads issued after the first store could not be hoisted by the compiler and would serialise on DRAM latency
-      double av[R], bv[R], w2v[R], rw2v[R];
-#pragma unroll
-      for (int j = 0; j < R; ++j) {
-         const int64_t gy = gy0 + j;
-         const bool in = gy < g.n1;
-         const int64_t off = gy * g.pitch + gx;
-         av[j] = 0.0;
-         bv[j] = 0.0;
-         if (COMBINE == C_RK2_FINAL || COMBINE == C_RK3_S2 || COMBINE == C_RK3_S3 || COMBINE == C_MS) av[j] = in ? s.a[off] : 0.0;
-         if (COMBINE == C_MS) bv[j] = in ? s.b[off] : 0.0;
-         w2v[j] = __ldg(g.w2 + (in ? gy : gy0));
-         rw2v[j] = __ldg(g.rw2 + (in ? gy : gy0));
-      }
-#pragma unroll
-      for (int j = 0; j < R; ++j) {
-         const int64_t gy = gy0 + j;
-         if (gy >= g.n1) break;
-         const int ly = ly0 + j;
-         // x1-faces gx and gx+1 of row gy
-         const double *vlx = s_vlx + ly * T::XP + R + lx, *vrx = s_vrx + ly * T::XP + R + lx;
-         double Fl = face_flux<M>(g.flux1, vrx[-1], vlx[0]);
-         double Fr = face_flux<M>(g.flux1, vrx[0], vlx[1]);
-         if (copy) {
-            // fedges(0) = fedges(1), fedges(nc) = fedges(nc-1): needs the flux one face further in
-            if (gx == 0) Fl = Fr;
-            if (gx == g.n0 - 1) Fr = Fl;
-         } else {
-            if (gx == 0) Fl = 0.0;
-            if (gx == g.n0 - 1) Fr = 0.0;
-         }
-         const double w2 = w2v[j];
-         // vdot = -(f1(i)-f1(i-1))/w1(i) - (f2(j)-f2(j-1))/w2(j)   (example2:123-127)
-         double L;
-         if constexpr (M::strict) {
-            // IEEE quotients from the precomputed refined reciprocals (common.cuh: exact_div_q), cold fallback
-            bool ok = true;
-            const double d1 = M::sub(Fr, Fl), d2 = M::sub(F2[j + 1], F2[j]);
-            L = M::sub(-exact_div_q(d1, w1, rw1, ok), exact_div_q(d2, w2, rw2v[j], ok));
-            if (!ok) L = M::sub(-M::div(d1, w1), M::div(d2, w2));
-         } else {
-            L = fma(-(F2[j + 1] - F2[j]), rw2v[j], -((Fr - Fl) * rw1));
-         }
-         const double v = s_v[(ly + H) * T::SP + lx + H];
-         const int64_t off = gy * g.pitch + gx;
-         double o;
-         if (COMBINE == C_RHS) {
-            o = L;
-         } else if (COMBINE == C_EULER) {
-            o = M::add(v, M::mul(s.c0, L));
-         } else if (COMBINE == C_RK2_FINAL) {
-            o = M::mul(M::add(M::add(av[j], v), M::mul(s.c0, L)), 0.5);
-         } else if (COMBINE == C_RK3_S2) {
-            o = M::mul(M::add(M::add(M::mul(3.0, av[j]), v), M::mul(s.c0, L)), 0.25);
-         } else if (COMBINE == C_RK3_S3) {
-            o = div3<M>(M::add(M::fma_exact(2.0, v, av[j]), M::mul(s.c0, L)));
-         } else {
-            o = M::mul(M::add(M::add(M::add(M::mul(25.0, v), M::mul(s.c0, L)), M::mul(7.0, av[j])), M::mul(s.c1, bv[j])),
-                       0.03125);
-            s.out2[off] = L;
-         }
-         if (s.out_dense) {
-            s.out[gy * s.ld_out + gx] = o;
-         } else {
-            s.out[off] = o;
-            if (COMBINE != C_RHS) {
-               // ghost cells of the result at physical boundaries (edge replicas, weno.f90:172-173)
-               if (gx == 0) {
-#pragma unroll
-                  for (int q = 1; q <= K; ++q) s.out[off - q] = o;
-               }
-               if (gx == g.n0 - 1) {
-#pragma unroll
-                  for (int q = 1; q <= K; ++q) s.out[off + q] = o;
-               }
-               if (g.phys_lo && gy == 0) {
-#pragma unroll
-                  for (int q = 1; q <= K; ++q) s.out[off - q * g.pitch] = o;
-               }
-               if (g.phys_hi && gy == g.n1 - 1) {
-#pragma unroll
-                  for (int q = 1; q <= K; ++q) s.out[off + q * g.pitch] = o;
-               }
-            }
-         }
-      }
+      if (interior)
+         fv2d_phase_b<K, COMBINE, M, UPW, TX, TY, true>(g, s, s_v, s_vlx, s_vrx, s_vly, s_vry, x0, y0, lx, ryi * R);
+      else
+         fv2d_phase_b<K, COMBINE, M, UPW, TX, TY, false>(g, s, s_v, s_vlx, s_vrx, s_vly, s_vry, x0, y0, lx, ryi * R);
    }
 }
 
 constexpr int TX2 = 64, TY2 = 32, NT2 = 256;
 
-template <int K, int COMBINE, class M>
-static int launch2d(const Fv2dGeom &g, const StageArgs &a, cudaStream_t st) {
+template <int K, int COMBINE, class M, int UPW>
+static int launch2d_u(const Fv2dGeom &g, const StageArgs &a, cudaStream_t st) {
    using T = Tile2d<TX2, TY2>;
-   auto kern = fv2d_stage_kernel<K, COMBINE, M, TX2, TY2, NT2>;
+   auto kern = fv2d_stage_kernel<K, COMBINE, M, UPW, TX2, TY2, NT2>;
    static bool configured = false; // one flag per instantiation
    if (!configured) {
       HRW_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)T::BYTES));
@@ -242,6 +281,12 @@ static int launch2d(const Fv2dGeom &g, const StageArgs &a, cudaStream_t st) {
    kern<<<grid, NT2, T::BYTES, st>>>(g, a);
    HRW_CUDA(cudaGetLastError());
    return HRWENO_OK;
+}
+
+template <int K, int COMBINE, class M>
+static int launch2d(const Fv2dGeom &g, const StageArgs &a, cudaStream_t st) {
+   const bool upw = g.flux1.model == HRWENO_FLUX_LINEAR && g.flux1.scheme == HRWENO_SCHEME_GODUNOV && g.flux1.coef >= 0.0 && g.flux2.coef >= 0.0;
+   return upw ? launch2d_u<K, COMBINE, M, 1>(g, a, st) : launch2d_u<K, COMBINE, M, 0>(g, a, st);
 }
 
 template <int K, class M>
