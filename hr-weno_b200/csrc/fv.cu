@@ -340,7 +340,7 @@ int fv_stage(Fv *fv, int combine, const StageArgs &args, cudaStream_t st) {
    g.width = fv->d_width[0];
    g.wtab = fv->d_wtab;
    g.widx = fv->d_widx;
-   g.eps = d.eps;
+   g.kc = make_wenok(d.eps);
    g.flux = FluxCfg{d.flux_model, d.flux_scheme, d.flux_coef[0], d.alpha};
    g.bc = d.bc;
    g.phys_left = d.rank == 0;

@@ -40,7 +40,7 @@ struct Fv1dGeom {
    const double *width;   // WK_ARRAY: device array (padded, >= n + 16)
    const double2 *wtab;   // WK_DICT: 256 entries {width, refined reciprocal (exact_recip)}
    const unsigned char *widx; // WK_DICT: one byte per cell (padded, >= n + 16)
-   double eps;
+   WenoK kc;              // eps and the WENO tables (parameter-bank operands)
    FluxCfg flux;
    int bc;
    int phys_left, phys_right; // the row ends are physical boundaries (not slab interfaces)
@@ -384,7 +384,7 @@ __global__ void __launch_bounds__(NT, HRW_MINB) fv1d_stage_kernel(const Fv1dGeom
          w[j + 1] = t.y;
       }
       double vl[R], vr[R];
-      weno_run<K, R, M>(w + (2 - (K - 1)), g.eps, vl, vr);
+      weno_run<K, R, M>(w + (2 - (K - 1)), g.kc, vl, vr);
 
       // exchange arrays are double buffered by iteration parity: a slot is rewritten two iterations later, after
       // the barrier of the iteration in between, which every reader of the old value has passed

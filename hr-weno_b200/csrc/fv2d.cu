@@ -22,7 +22,7 @@ struct Fv2dGeom {
    int tiles_x, tiles_y;
    const double *w1, *w2;   // widths (device, padded)
    const double *rw1, *rw2; // their refined reciprocals (exact_recip)
-   double eps;
+   WenoK kc;
    FluxCfg flux1, flux2;
    int bc;
    int phys_lo, phys_hi; // x2 ends are physical boundaries (x1 ends always are)
@@ -245,7 +245,7 @@ __global__ void __launch_bounds__(NT) fv2d_stage_kernel(const Fv2dGeom g, const 
 #pragma unroll
       for (int j = 0; j < R + 4; ++j) w[j] = base[(j - 2) * stride];
       double vl[R], vr[R];
-      weno_run<K, R, M>(w + (2 - (K - 1)), g.eps, vl, vr);
+      weno_run<K, R, M>(w + (2 - (K - 1)), g.kc, vl, vr);
 #pragma unroll
       for (int j = 0; j < R; ++j) {
          if constexpr (!UPW) ovl[oidx + j * ostride] = vl[j]; // upwind: the left side is never used and is eliminated
@@ -320,7 +320,7 @@ int fv2d_stage(Fv *fv, int combine, const StageArgs &args, cudaStream_t st) {
    g.w2 = fv->d_width[1];
    g.rw1 = fv->d_rwidth[0];
    g.rw2 = fv->d_rwidth[1];
-   g.eps = d.eps;
+   g.kc = make_wenok(d.eps);
    g.flux1 = FluxCfg{d.flux_model, d.flux_scheme, d.flux_coef[0], d.alpha};
    g.flux2 = FluxCfg{d.flux_model, d.flux_scheme, d.flux_coef[1], d.alpha};
    g.bc = d.bc;

@@ -93,7 +93,8 @@ int weno_create(Weno **out, int64_t ncells, int k, double eps, const double *xed
 template <int K, class M>
 __global__ void __launch_bounds__(256)
    recon_kernel(const double *__restrict__ v, int64_t ldv, int64_t incv, double *__restrict__ vl, double *__restrict__ vr,
-                int64_t ldo, int64_t n, int64_t rows, double eps, const double *__restrict__ cnu, int cell_fastest) {
+                int64_t ldo, int64_t n, int64_t rows, const WenoK kc, const double *__restrict__ cnu, int cell_fastest) {
+   const double eps = kc.eps;
    const int64_t total = rows * n;
    for (int64_t idx = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; idx < total; idx += (int64_t)gridDim.x * blockDim.x) {
       int64_t row, i;
@@ -119,7 +120,7 @@ __global__ void __launch_bounds__(256)
          for (int q = 0; q < K * (K + 1); ++q) ci[q] = __ldg(cnu + (size_t)i * (K * (K + 1)) + q);
          weno_cell_nonuniform<K, M>(ci, w + (K - 1), eps, l, r);
       } else {
-         weno_run<K, 1, M>(w, eps, &l, &r);
+         weno_run<K, 1, M>(w, kc, &l, &r);
       }
       vl[row * ldo + i] = l;
       vr[row * ldo + i] = r;
@@ -134,13 +135,13 @@ int weno_reconstruct_launch(const Weno *w, int64_t rows, const double *v, int64_
    const int cf = incv == 1;
    switch (w->k) {
    case 1:
-      recon_kernel<1, Strict><<<(unsigned)blocks, 256, 0, st>>>(v, ldv, incv, vl, vr, ldo, w->ncells, rows, w->eps, w->d_cnu, cf);
+      recon_kernel<1, Strict><<<(unsigned)blocks, 256, 0, st>>>(v, ldv, incv, vl, vr, ldo, w->ncells, rows, make_wenok(w->eps), w->d_cnu, cf);
       break;
    case 2:
-      recon_kernel<2, Strict><<<(unsigned)blocks, 256, 0, st>>>(v, ldv, incv, vl, vr, ldo, w->ncells, rows, w->eps, w->d_cnu, cf);
+      recon_kernel<2, Strict><<<(unsigned)blocks, 256, 0, st>>>(v, ldv, incv, vl, vr, ldo, w->ncells, rows, make_wenok(w->eps), w->d_cnu, cf);
       break;
    default:
-      recon_kernel<3, Strict><<<(unsigned)blocks, 256, 0, st>>>(v, ldv, incv, vl, vr, ldo, w->ncells, rows, w->eps, w->d_cnu, cf);
+      recon_kernel<3, Strict><<<(unsigned)blocks, 256, 0, st>>>(v, ldv, incv, vl, vr, ldo, w->ncells, rows, make_wenok(w->eps), w->d_cnu, cf);
    }
    HRW_CUDA(cudaGetLastError());
    return HRWENO_OK;

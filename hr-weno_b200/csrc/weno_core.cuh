@@ -57,7 +57,7 @@ __device__ __forceinline__ bool weights_in_range(double e0, double e1, double e2
 
 // ---------------------------------------------------------------------------------------- k = 1
 template <int R, class M>
-__device__ __forceinline__ void weno_run_k1(const double *w, double, double *vl, double *vr) {
+__device__ __forceinline__ void weno_run_k1(const double *w, const WenoK &, double *vl, double *vr) {
    // vrr = 1*v, beta = 0, alfa = 1/eps**2, w = alfa/alfa = 1  ->  vl = vr = v   (weno.f90:186)
 #pragma unroll
    for (int j = 0; j < R; ++j) {
@@ -68,7 +68,8 @@ __device__ __forceinline__ void weno_run_k1(const double *w, double, double *vl,
 
 // ---------------------------------------------------------------------------------------- k = 2
 template <int R, class M>
-__device__ __forceinline__ void weno_run_k2(const double *w, double eps, double *vl, double *vr) {
+__device__ __forceinline__ void weno_run_k2(const double *w, const WenoK &kc, double *vl, double *vr) {
+   const double eps = kc.eps;
    constexpr int N = R + 2;
    // c2 (weno.f90:17-18): c(:,-1) = [3/2,-1/2], c(:,0) = [1/2,1/2], c(:,1) = [-1/2,3/2]
    double h[N], q[N]; // h = v/2 (exact), q = 3/2*v
@@ -86,7 +87,7 @@ __device__ __forceinline__ void weno_run_k2(const double *w, double eps, double 
    double a0[R + 1]; // a0[j] = vrr(0) of cell j-1 (window index j) = vlr(1) of cell j
 #pragma unroll
    for (int j = 0; j < R + 1; ++j) a0[j] = M::add(h[j], h[j + 1]);
-   const double d0 = 2.0 / 3, d1 = 1.0 / 3;
+   const double d0 = kc.d23, d1 = kc.d13;
 #pragma unroll
    for (int j = 0; j < R; ++j) {
       const int c = j + 1; // window index of the cell
@@ -121,11 +122,12 @@ __device__ __forceinline__ void weno_run_k2(const double *w, double eps, double 
 
 // ---------------------------------------------------------------------------------------- k = 3
 template <int R, class M>
-__device__ __forceinline__ void weno_run_k3(const double *w, double eps, double *vl, double *vr) {
+__device__ __forceinline__ void weno_run_k3(const double *w, const WenoK &kc, double *vl, double *vr) {
+   const double eps = kc.eps;
    constexpr int N = R + 4;
    // c3 (weno.f90:19-21): c(:,-1) = [11/6,-7/6,1/3], c(:,0) = [1/3,5/6,-1/6],
    //                      c(:,1) = [-1/6,5/6,1/3],   c(:,2) = [1/3,-7/6,11/6]
-   const double C13 = 1.0 / 3, C56 = 5.0 / 6, C16 = -1.0 / 6, C76 = -7.0 / 6, C116 = 11.0 / 6;
+   const double C13 = kc.c13, C56 = kc.c56, C16 = kc.c16m, C76 = kc.c76m, C116 = kc.c116;
    double p13[N], p56[N], p16[N], p76[N], p116[N], t3[N];
 #pragma unroll
    for (int j = 0; j < N; ++j) {
@@ -141,7 +143,7 @@ __device__ __forceinline__ void weno_run_k3(const double *w, double eps, double 
 #pragma unroll
    for (int j = 1; j < N - 1; ++j) {
       const double d2 = M::add(M::fma_exact(-2.0, w[j], w[j - 1]), w[j + 1]);
-      m2[j] = M::mul(13.0 / 12, M::mul(d2, d2));
+      m2[j] = M::mul(kc.k1312, M::mul(d2, d2));
    }
    // A0[j] = vrr(0) of the cell at window index j = (1/3 v[j] + 5/6 v[j+1]) - 1/6 v[j+2]; also vlr(1) of cell j+1
    // A1[j] = vrr(1) of the cell at window index j = (-1/6 v[j-1] + 5/6 v[j]) + 1/3 v[j+1]; also vlr(2) of cell j+1
@@ -171,8 +173,8 @@ __device__ __forceinline__ void weno_run_k3(const double *w, double eps, double 
          // alfa = d/(eps+beta)**2, alfatilde = d(k-1:0:-1)/(eps+beta)**2   (weno.f90:207-208), d3 = [0.3,0.6,0.1]
          // IEEE quotients with the reciprocal refinement shared per denominator (common.cuh: exact_div)
          const double r0 = exact_recip(den0), r1 = exact_recip(den1), r2 = exact_recip(den2);
-         const double al0 = exact_div_nc(0.3, den0, r0), al1 = exact_div_nc(0.6, den1, r1), al2 = exact_div_nc(0.1, den2, r2);
-         const double at0 = exact_div_nc(0.1, den0, r0), at2 = exact_div_nc(0.3, den2, r2); // at1 == al1
+         const double al0 = exact_div_nc(kc.d03, den0, r0), al1 = exact_div_nc(kc.d06, den1, r1), al2 = exact_div_nc(kc.d01, den2, r2);
+         const double at0 = exact_div_nc(kc.d01, den0, r0), at2 = exact_div_nc(kc.d03, den2, r2); // at1 == al1
          const double s = M::add(M::add(al0, al1), al2);
          const double st = M::add(M::add(at0, al1), at2);
          const double rs = exact_recip(s), rst = exact_recip(st);
@@ -206,16 +208,16 @@ __device__ __forceinline__ void weno_run_k3(const double *w, double eps, double 
 // one reciprocal per side (MUFU seed + one cubic step).  Not bit-identical to the reference order: parity is
 // the north-star tolerance (1e-12 normwise per output time, a few ULP per reconstruction).
 template <int R>
-__device__ __forceinline__ void weno_run_k3_fast(const double *w, double eps, double *vl, double *vr) {
+__device__ __forceinline__ void weno_run_k3_fast(const double *w, const WenoK &kc, double *vl, double *vr) {
    constexpr int N = R + 4;
-   const double C13 = 1.0 / 3, C56 = 5.0 / 6, C16 = -1.0 / 6;
-   const double eps4 = 4.0 * eps;
+   const double C13 = kc.c13, C56 = kc.c56, C16 = kc.c16m;
+   const double eps4 = kc.eps4;
    // second differences d2[j] = v[j-1] - 2 v[j] + v[j+1]; m2e[j] = eps' + (13/3) d2^2; third differences D3[j] = d2[j+1] - d2[j]
    double d2[N], m2e[N], D3[N];
 #pragma unroll
    for (int j = 1; j < N - 1; ++j) {
       d2[j] = fma(-2.0, w[j], w[j - 1]) + w[j + 1];
-      m2e[j] = fma((13.0 / 3) * d2[j], d2[j], eps4);
+      m2e[j] = fma(kc.k133 * d2[j], d2[j], eps4);
    }
 #pragma unroll
    for (int j = 1; j < N - 2; ++j) D3[j] = d2[j + 1] - d2[j];
@@ -252,15 +254,15 @@ __device__ __forceinline__ void weno_run_k3_fast(const double *w, double eps, do
 }
 
 template <int K, int R, class M>
-__device__ __forceinline__ void weno_run(const double *w, double eps, double *vl, double *vr) {
+__device__ __forceinline__ void weno_run(const double *w, const WenoK &kc, double *vl, double *vr) {
    if constexpr (K == 1)
-      weno_run_k1<R, M>(w, eps, vl, vr);
+      weno_run_k1<R, M>(w, kc, vl, vr);
    else if constexpr (K == 2)
-      weno_run_k2<R, M>(w, eps, vl, vr);
+      weno_run_k2<R, M>(w, kc, vl, vr);
    else if constexpr (!M::strict)
-      weno_run_k3_fast<R>(w, eps, vl, vr);
+      weno_run_k3_fast<R>(w, kc, vl, vr);
    else
-      weno_run_k3<R, M>(w, eps, vl, vr);
+      weno_run_k3<R, M>(w, kc, vl, vr);
 }
 
 // ------------------------------------------------------------------------------------------------
