@@ -216,27 +216,28 @@ __global__ void __launch_bounds__(NT) fv2d_stage_kernel(const Fv2dGeom g, const 
    __syncthreads();
 
    // ---- phase A: reconstruction items ------------------------------------------------------------------
-   for (int it = tid; it < T::NRX + T::NRY; it += NT) {
+   // regular items: runs of R cells inside the tile, x1-lines first, then x2-lines (one code path, (base, stride) addressing)
+   constexpr int NXR = (TX / R) * TY, NYR = TX * (TY / R);
+   for (int it = tid; it < NXR + NYR; it += NT) {
       const double *base;
       int stride, oidx, ostride;
       double *ovl, *ovr;
-      if (it < T::NRX) { // x1-sweep: row ly, run rx in [-1, TX/R]
-         const int ly = it / T::RUNS_X;
-         const int rx = it - ly * T::RUNS_X - 1;
+      if (it < NXR) { // x1-sweep: row ly, run rx
+         const int ly = it / (TX / R);
+         const int rx = it - ly * (TX / R);
          base = s_v + (ly + H) * T::SP + (H + rx * R); // first cell of the run
          stride = 1;
          oidx = ly * T::XP + (rx + 1) * R;
          ostride = 1;
          ovl = s_vlx;
          ovr = s_vrx;
-      } else { // x2-sweep: column lx, run ry in [-1, TY/R]
-         const int q = it - T::NRX;
-         const int ryi = q / TX;
-         const int lx = q - ryi * TX;
-         const int ry = ryi - 1;
+      } else { // x2-sweep: column lx, run ry
+         const int q = it - NXR;
+         const int ry = q / TX;
+         const int lx = q - ry * TX;
          base = s_v + (H + ry * R) * T::SP + (lx + H);
          stride = T::SP;
-         oidx = (ryi * R) * TX + lx;
+         oidx = ((ry + 1) * R) * TX + lx;
          ostride = TX;
          ovl = s_vly;
          ovr = s_vry;
@@ -251,6 +252,34 @@ __global__ void __launch_bounds__(NT) fv2d_stage_kernel(const Fv2dGeom g, const 
          if constexpr (!UPW) ovl[oidx + j * ostride] = vl[j]; // upwind: the left side is never used and is eliminated
          ovr[oidx + j * ostride] = vr[j];
       }
+   }
+   // halo items: the faces on the tile edge need vr of the cell just below/left of the tile and (unless upwind) vl of the
+   // cell just above/right of it: single-cell reconstructions, grouped after the regular items so that whole warps take them
+   constexpr int NHALO = UPW ? (TY + TX) : 2 * (TY + TX);
+   for (int it = tid; it < NHALO; it += NT) {
+      const bool high = it >= TY + TX; // high side: vl of cell index T (only when !UPW)
+      const int q = high ? it - (TY + TX) : it;
+      const double *base;
+      int stride;
+      double *dst;
+      if (q < TY) { // x1 line q
+         const int cx = high ? TX : -1;
+         base = s_v + (q + H) * T::SP + (H + cx);
+         stride = 1;
+         dst = (high ? s_vlx : s_vrx) + q * T::XP + R + cx;
+      } else { // x2 line
+         const int lx = q - TY;
+         const int cy = high ? TY : -1;
+         base = s_v + (H + cy) * T::SP + (lx + H);
+         stride = T::SP;
+         dst = (high ? s_vly : s_vry) + (cy + R) * TX + lx;
+      }
+      double w[5];
+#pragma unroll
+      for (int j = 0; j < 5; ++j) w[j] = base[(j - 2) * stride];
+      double vl1[1], vr1[1];
+      weno_run<K, 1, M>(w + (2 - (K - 1)), g.kc, vl1, vr1);
+      *dst = high ? vl1[0] : vr1[0];
    }
    __syncthreads();
 

@@ -348,3 +348,24 @@ def test_config2_fast_mode_within_tolerance(gpu_lib, pkg, ref):
     finally:
         ref.set_threads(1)
     assert worst <= 1e-12, worst
+
+
+def test_fast_mode_rhs_within_a_few_ulp(gpu_lib, pkg, ref):
+    """one rhs evaluation in fast mode against the oracle: a few ULP of the quantities it differences (north star:
+    'a few ULP' per reconstruction; the divergence divides O(ulp) flux differences by the cell width)"""
+    rng = np.random.default_rng(4)
+    nc = 4000
+    g = pkg.hrweno_grids.grid1().linear(-5.0, 5.0, nc)
+    v = ex1_ic(g.center) + 1e-3 * rng.standard_normal(nc)
+    for k in (1, 2, 3):
+        got = pkg.fv.FV(pkg.fv.make_desc(nc, k=k, width=[g.width], mode=pkg._abi.MODE_FAST)).rhs(0.0, v)
+        want = ref.FV(pkg.fv.make_desc(nc, k=k, width=[g.width])).rhs(0.0, v)
+        scale = 0.5 * np.max(v * v) / g.width.min()  # magnitude of f/width: the rhs is a difference of two such terms
+        assert np.max(np.abs(got - want)) <= 16 * np.finfo(float).eps * scale
+    n1, n2 = 130, 70
+    g1, g2 = pkg.hrweno_grids.grid1().linear(0.0, 10.0, n1), pkg.hrweno_grids.grid1().linear(0.0, 7.0, n2)
+    v2 = ex2_ic(g1.center, g2.center) + 1e-3 * rng.standard_normal((n2, n1))
+    kw = dict(n=(n1, n2), k=3, flux_model=1, bc=1, width=[g1.width, g2.width])
+    got = pkg.fv.FV(pkg.fv.make_desc(mode=pkg._abi.MODE_FAST, **kw)).rhs(0.0, v2)
+    want = ref.FV(pkg.fv.make_desc(**kw)).rhs(0.0, v2)
+    assert np.max(np.abs(got - want)) <= 16 * np.finfo(float).eps * np.max(np.abs(v2)) / min(g1.width.min(), g2.width.min())
