@@ -28,7 +28,7 @@ struct Fv2dGeom {
    int phys_lo, phys_hi; // x2 ends are physical boundaries (x1 ends always are)
 };
 
-template <int TX, int TY>
+template <int TX, int TY, int UPW = 0>
 struct Tile2d {
    static constexpr int R = 4, H = 4;
    static constexpr int SP = TX + 2 * H;         // tile pitch
@@ -41,9 +41,10 @@ struct Tile2d {
                                                  // unused outer cells of the overlap runs of the x2-sweep)
    static constexpr int OFF_V = GR * SP;
    static constexpr int OFF_VLX = OFF_V + (SROWS + GR) * SP;
-   static constexpr int OFF_VRX = OFF_VLX + TY * XP;
+   // upwind specialisation: the left-side arrays are never touched and get no storage (more CTAs per SM)
+   static constexpr int OFF_VRX = OFF_VLX + (UPW ? 0 : TY * XP);
    static constexpr int OFF_VLY = OFF_VRX + TY * XP;
-   static constexpr int OFF_VRY = OFF_VLY + YROWS * TX;
+   static constexpr int OFF_VRY = OFF_VLY + (UPW ? 0 : YROWS * TX);
    static constexpr int TOTAL = OFF_VRY + YROWS * TX;
    static constexpr size_t BYTES = (size_t)TOTAL * sizeof(double);
 };
@@ -66,7 +67,7 @@ template <int K, int COMBINE, class M, int UPW, int TX, int TY, bool INTERIOR>
 __device__ __forceinline__ void fv2d_phase_b(const Fv2dGeom &g, const StageArgs &s, const double *s_v, const double *s_vlx,
                                              const double *s_vrx, const double *s_vly, const double *s_vry, int64_t x0, int64_t y0,
                                              int lx, int ly0) {
-   using T = Tile2d<TX, TY>;
+   using T = Tile2d<TX, TY, UPW>;
    constexpr int R = T::R, H = T::H;
    const int64_t gx = x0 + lx, gy0 = y0 + ly0;
    if constexpr (!INTERIOR) {
@@ -192,7 +193,7 @@ __device__ __forceinline__ void fv2d_phase_b(const Fv2dGeom &g, const StageArgs 
 
 template <int K, int COMBINE, class M, int UPW, int TX, int TY, int NT>
 __global__ void __launch_bounds__(NT) fv2d_stage_kernel(const Fv2dGeom g, const StageArgs s) {
-   using T = Tile2d<TX, TY>;
+   using T = Tile2d<TX, TY, UPW>;
    constexpr int R = T::R, H = T::H;
    extern __shared__ __align__(16) double smem[];
    double *s_v = smem + T::OFF_V;
@@ -299,7 +300,7 @@ constexpr int TX2 = 64, TY2 = 32, NT2 = 256;
 
 template <int K, int COMBINE, class M, int UPW>
 static int launch2d_u(const Fv2dGeom &g, const StageArgs &a, cudaStream_t st) {
-   using T = Tile2d<TX2, TY2>;
+   using T = Tile2d<TX2, TY2, UPW>;
    auto kern = fv2d_stage_kernel<K, COMBINE, M, UPW, TX2, TY2, NT2>;
    static bool configured = false; // one flag per instantiation
    if (!configured) {
