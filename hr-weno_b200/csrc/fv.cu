@@ -305,23 +305,23 @@ int fv_unpack(Fv *fv, const double *padded0, double *dense, cudaStream_t st) {
 // ------------------------------------------------------------------------------------------------
 // stage dispatch
 // ------------------------------------------------------------------------------------------------
-int fv1d_launch_k1_m0(int, int, int, const Fv1dGeom &, const StageArgs &, cudaStream_t);
-int fv1d_launch_k2_m0(int, int, int, const Fv1dGeom &, const StageArgs &, cudaStream_t);
-int fv1d_launch_k3_m0(int, int, int, const Fv1dGeom &, const StageArgs &, cudaStream_t);
-int fv1d_launch_k1_m1(int, int, int, const Fv1dGeom &, const StageArgs &, cudaStream_t);
-int fv1d_launch_k2_m1(int, int, int, const Fv1dGeom &, const StageArgs &, cudaStream_t);
-int fv1d_launch_k3_m1(int, int, int, const Fv1dGeom &, const StageArgs &, cudaStream_t);
-int fv1d_tile_cells();
+int fv1d_launch_k1_m0(int, int, int, int, const Fv1dGeom &, const StageArgs &, cudaStream_t);
+int fv1d_launch_k2_m0(int, int, int, int, const Fv1dGeom &, const StageArgs &, cudaStream_t);
+int fv1d_launch_k3_m0(int, int, int, int, const Fv1dGeom &, const StageArgs &, cudaStream_t);
+int fv1d_launch_k1_m1(int, int, int, int, const Fv1dGeom &, const StageArgs &, cudaStream_t);
+int fv1d_launch_k2_m1(int, int, int, int, const Fv1dGeom &, const StageArgs &, cudaStream_t);
+int fv1d_launch_k3_m1(int, int, int, int, const Fv1dGeom &, const StageArgs &, cudaStream_t);
+int fv1d_tile_cells(int half_tile);
 
-int fv1d_launch(int k, int mode, int combine, int fk, int wk, const Fv1dGeom &g, const StageArgs &a, cudaStream_t st) {
+int fv1d_launch(int k, int mode, int combine, int fk, int wk, int half_tile, const Fv1dGeom &g, const StageArgs &a, cudaStream_t st) {
    if (mode == HRWENO_MODE_STRICT) {
-      if (k == 1) return fv1d_launch_k1_m0(combine, fk, wk, g, a, st);
-      if (k == 2) return fv1d_launch_k2_m0(combine, fk, wk, g, a, st);
-      return fv1d_launch_k3_m0(combine, fk, wk, g, a, st);
+      if (k == 1) return fv1d_launch_k1_m0(combine, fk, wk, half_tile, g, a, st);
+      if (k == 2) return fv1d_launch_k2_m0(combine, fk, wk, half_tile, g, a, st);
+      return fv1d_launch_k3_m0(combine, fk, wk, half_tile, g, a, st);
    }
-   if (k == 1) return fv1d_launch_k1_m1(combine, fk, wk, g, a, st);
-   if (k == 2) return fv1d_launch_k2_m1(combine, fk, wk, g, a, st);
-   return fv1d_launch_k3_m1(combine, fk, wk, g, a, st);
+   if (k == 1) return fv1d_launch_k1_m1(combine, fk, wk, half_tile, g, a, st);
+   if (k == 2) return fv1d_launch_k2_m1(combine, fk, wk, half_tile, g, a, st);
+   return fv1d_launch_k3_m1(combine, fk, wk, half_tile, g, a, st);
 }
 
 int fv_stage(Fv *fv, int combine, const StageArgs &args, cudaStream_t st) {
@@ -332,7 +332,16 @@ int fv_stage(Fv *fv, int combine, const StageArgs &args, cudaStream_t st) {
       return HRWENO_OK;
    }
    Fv1dGeom g{};
-   const int tile = fv1d_tile_cells();
+   const int fk = (d.flux_model == HRWENO_FLUX_BURGERS && d.flux_scheme == HRWENO_SCHEME_GODUNOV) ? FK_BURGERS_GODUNOV : FK_GENERIC;
+   // tile = (threads - 2) * R cells.  The half-size tile exists for Burgers/Godunov with a width dictionary; it is used
+   // when it covers the row with fewer (partly idle) thread runs, e.g. 4096-cell rows: 9 x 504 instead of 5 x 1016
+   int half_tile = 0;
+   if (fk == FK_BURGERS_GODUNOV && fv->width_dict) {
+      const int64_t t0 = fv1d_tile_cells(0), t1 = fv1d_tile_cells(1);
+      const double slots0 = (double)((fv->n0 + t0 - 1) / t0) * (double)(t0 + 8), slots1 = (double)((fv->n0 + t1 - 1) / t1) * (double)(t1 + 8);
+      half_tile = slots1 < 0.97 * slots0;
+   }
+   const int tile = fv1d_tile_cells(half_tile);
    g.n = fv->n0;
    g.ld = fv->pitch;
    g.tiles_per_row = (fv->n0 + tile - 1) / tile;
@@ -345,8 +354,7 @@ int fv_stage(Fv *fv, int combine, const StageArgs &args, cudaStream_t st) {
    g.bc = d.bc;
    g.phys_left = d.rank == 0;
    g.phys_right = d.rank == d.nranks - 1;
-   const int fk = (d.flux_model == HRWENO_FLUX_BURGERS && d.flux_scheme == HRWENO_SCHEME_GODUNOV) ? FK_BURGERS_GODUNOV : FK_GENERIC;
-   HRW_TRY(fv1d_launch(d.k, d.mode, combine, fk, fv->width_dict ? WK_DICT : WK_ARRAY, g, args, st));
+   HRW_TRY(fv1d_launch(d.k, d.mode, combine, fk, fv->width_dict ? WK_DICT : WK_ARRAY, half_tile, g, args, st));
    fv->launches++;
    return HRWENO_OK;
 }

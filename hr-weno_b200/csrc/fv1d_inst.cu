@@ -19,28 +19,30 @@ using IM = Fast;
 #endif
 constexpr int R1 = HRW_R1, NT1 = HRW_NT1;
 
-template <int COMBINE, int FK, int WK>
+template <int COMBINE, int FK, int WK, int NT = NT1>
 static int launch(const Fv1dGeom &g, const StageArgs &a, cudaStream_t st) {
-   auto kern = fv1d_stage_kernel<IK, COMBINE, IM, FK, WK, R1, NT1>;
+   auto kern = fv1d_stage_kernel<IK, COMBINE, IM, FK, WK, R1, NT>;
    // persistent grid: SMs x resident CTAs of this specialisation (queried once), never more than there are tiles
    static int resident = 0;
    if (resident == 0) {
       int dev = 0, sms = 0, per_sm = 0;
       cudaGetDevice(&dev);
       cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
-      cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, NT1, 0);
+      cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, NT, 0);
       resident = (sms > 0 ? sms : 148) * (per_sm > 0 ? per_sm : 1);
    }
    int64_t blocks = g.rows * g.tiles_per_row;
    if (blocks > resident) blocks = resident;
-   kern<<<(unsigned)blocks, NT1, 0, st>>>(g, a);
+   kern<<<(unsigned)blocks, NT, 0, st>>>(g, a);
    HRW_CUDA(cudaGetLastError());
    return HRWENO_OK;
 }
 
 template <int COMBINE>
-static int launch_c(int fk, int wk, const Fv1dGeom &g, const StageArgs &a, cudaStream_t st) {
+static int launch_c(int fk, int wk, int half_tile, const Fv1dGeom &g, const StageArgs &a, cudaStream_t st) {
    if (fk == FK_BURGERS_GODUNOV) {
+      // short rows (batched ensembles): the half-size tile wastes fewer thread runs at the row ends
+      if (wk == WK_DICT && half_tile) return launch<COMBINE, FK_BURGERS_GODUNOV, WK_DICT, NT1 / 2>(g, a, st);
       if (wk == WK_DICT) return launch<COMBINE, FK_BURGERS_GODUNOV, WK_DICT>(g, a, st);
       return launch<COMBINE, FK_BURGERS_GODUNOV, WK_ARRAY>(g, a, st);
    }
@@ -50,19 +52,19 @@ static int launch_c(int fk, int wk, const Fv1dGeom &g, const StageArgs &a, cudaS
 
 #define HRW_CAT2(a, b, c, d) a##b##c##d
 #define HRW_CAT(a, b, c, d) HRW_CAT2(a, b, c, d)
-int HRW_CAT(fv1d_launch_k, HRW_INST_K, _m, HRW_INST_MODE)(int combine, int fk, int wk, const Fv1dGeom &g, const StageArgs &a, cudaStream_t st) {
+int HRW_CAT(fv1d_launch_k, HRW_INST_K, _m, HRW_INST_MODE)(int combine, int fk, int wk, int half_tile, const Fv1dGeom &g, const StageArgs &a, cudaStream_t st) {
    switch (combine) {
-   case C_RHS: return launch_c<C_RHS>(fk, wk, g, a, st);
-   case C_EULER: return launch_c<C_EULER>(fk, wk, g, a, st);
-   case C_RK2_FINAL: return launch_c<C_RK2_FINAL>(fk, wk, g, a, st);
-   case C_RK3_S2: return launch_c<C_RK3_S2>(fk, wk, g, a, st);
-   case C_RK3_S3: return launch_c<C_RK3_S3>(fk, wk, g, a, st);
-   default: return launch_c<C_MS>(fk, wk, g, a, st);
+   case C_RHS: return launch_c<C_RHS>(fk, wk, half_tile, g, a, st);
+   case C_EULER: return launch_c<C_EULER>(fk, wk, half_tile, g, a, st);
+   case C_RK2_FINAL: return launch_c<C_RK2_FINAL>(fk, wk, half_tile, g, a, st);
+   case C_RK3_S2: return launch_c<C_RK3_S2>(fk, wk, half_tile, g, a, st);
+   case C_RK3_S3: return launch_c<C_RK3_S3>(fk, wk, half_tile, g, a, st);
+   default: return launch_c<C_MS>(fk, wk, half_tile, g, a, st);
    }
 }
 
 #if HRW_INST_K == 3 && HRW_INST_MODE == 0
-int fv1d_tile_cells() { return (NT1 - 2) * R1; } // defined by one of the six objects
+int fv1d_tile_cells(int half_tile) { return ((half_tile ? NT1 / 2 : NT1) - 2) * R1; } // defined by one of the six objects
 #endif
 
 } // namespace hrw

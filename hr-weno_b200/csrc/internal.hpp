@@ -84,7 +84,8 @@ int fv_unpack(Fv *fv, const double *padded_cell0, double *dense_dev, cudaStream_
 int fv_stage(Fv *fv, int combine, const StageArgs &args, cudaStream_t st);
 struct Fv1dGeom;
 // fv1d_inst.cu, compiled once per (k, mode): launches the 1D stage kernel specialised for (combine, flux kind, width kind)
-int fv1d_launch(int k, int mode, int combine, int flux_kind, int width_kind, const Fv1dGeom &g, const StageArgs &a, cudaStream_t st);
+int fv1d_launch(int k, int mode, int combine, int flux_kind, int width_kind, int half_tile, const Fv1dGeom &g, const StageArgs &a,
+                cudaStream_t st);
 // fill the slab-interface ghost cells of a padded state from the neighbouring ranks (no-op on one GPU)
 int fv_exchange(Fv *fv, double *padded_cell0, cudaStream_t st);
 int fv_halo_export(Fv *fv, void *handle_out);
