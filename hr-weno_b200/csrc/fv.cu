@@ -324,6 +324,25 @@ int fv1d_launch(int k, int mode, int combine, int fk, int wk, int half_tile, con
    return fv1d_launch_k3_m1(combine, fk, wk, half_tile, g, a, st);
 }
 
+static int fv1d_flux_kind(const hrweno_fv_desc &d) {
+   return (d.flux_model == HRWENO_FLUX_BURGERS && d.flux_scheme == HRWENO_SCHEME_GODUNOV) ? FK_BURGERS_GODUNOV : FK_GENERIC;
+}
+
+// tile = (threads - 2) * R cells.  The half-size tile exists for Burgers/Godunov with a width dictionary; it is used
+// when it covers the row with fewer (partly idle) thread runs, e.g. 4096-cell rows: 9 x 504 instead of 5 x 1016
+static int fv1d_half_tile(const Fv *fv) {
+   if (fv1d_flux_kind(fv->d) != FK_BURGERS_GODUNOV || !fv->width_dict) return 0;
+   const int64_t t0 = fv1d_tile_cells(0), t1 = fv1d_tile_cells(1);
+   const double slots0 = (double)((fv->n0 + t0 - 1) / t0) * (double)(t0 + 8), slots1 = (double)((fv->n0 + t1 - 1) / t1) * (double)(t1 + 8);
+   return slots1 < 0.97 * slots0;
+}
+
+void fv_tiling_1d(const Fv *fv, int *tile_cells, int *tiles_per_row) {
+   const int tile = fv1d_tile_cells(fv1d_half_tile(fv));
+   *tile_cells = tile;
+   *tiles_per_row = (int)((fv->n0 + tile - 1) / tile);
+}
+
 int fv_stage(Fv *fv, int combine, const StageArgs &args, cudaStream_t st) {
    const hrweno_fv_desc &d = fv->d;
    if (d.ndim == 2) {
@@ -332,20 +351,15 @@ int fv_stage(Fv *fv, int combine, const StageArgs &args, cudaStream_t st) {
       return HRWENO_OK;
    }
    Fv1dGeom g{};
-   const int fk = (d.flux_model == HRWENO_FLUX_BURGERS && d.flux_scheme == HRWENO_SCHEME_GODUNOV) ? FK_BURGERS_GODUNOV : FK_GENERIC;
-   // tile = (threads - 2) * R cells.  The half-size tile exists for Burgers/Godunov with a width dictionary; it is used
-   // when it covers the row with fewer (partly idle) thread runs, e.g. 4096-cell rows: 9 x 504 instead of 5 x 1016
-   int half_tile = 0;
-   if (fk == FK_BURGERS_GODUNOV && fv->width_dict) {
-      const int64_t t0 = fv1d_tile_cells(0), t1 = fv1d_tile_cells(1);
-      const double slots0 = (double)((fv->n0 + t0 - 1) / t0) * (double)(t0 + 8), slots1 = (double)((fv->n0 + t1 - 1) / t1) * (double)(t1 + 8);
-      half_tile = slots1 < 0.97 * slots0;
-   }
+   const int fk = fv1d_flux_kind(d);
+   const int half_tile = fv1d_half_tile(fv);
    const int tile = fv1d_tile_cells(half_tile);
    g.n = fv->n0;
    g.ld = fv->pitch;
    g.tiles_per_row = (fv->n0 + tile - 1) / tile;
    g.rows = fv->rows;
+   g.tile_begin = args.tile_begin;
+   g.tile_end = args.tile_end > 0 ? args.tile_end : (int)(g.tiles_per_row * g.rows);
    g.width = fv->d_width[0];
    g.wtab = fv->d_wtab;
    g.widx = fv->d_widx;

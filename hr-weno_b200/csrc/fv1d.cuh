@@ -37,6 +37,7 @@ struct Fv1dGeom {
    int64_t ld;            // padded row pitch of vin / a / b / out2
    int64_t tiles_per_row;
    int64_t rows;          // independent rows (batched ensemble)
+   int tile_begin, tile_end; // linear tile range (row-major over (row, tile)) this launch covers
    const double *width;   // WK_ARRAY: device array (padded, >= n + 16)
    const double2 *wtab;   // WK_DICT: 256 entries {width, refined reciprocal (exact_recip)}
    const unsigned char *widx; // WK_DICT: one byte per cell (padded, >= n + 16)
@@ -282,7 +283,6 @@ __global__ void __launch_bounds__(NT, HRW_MINB) fv1d_stage_kernel(const Fv1dGeom
    const int tid = threadIdx.x;
    const int n = (int)g.n;                     // cells per row (< 2^31, validated at creation)
    const int tpr = (int)g.tiles_per_row;
-   const int nrows = (int)g.rows;
 
    // one elected thread issues the bulk copy of a tile: cells [c0-R-P, c0-R-P+SM_N) clipped to the padded row
    auto issue = [&](int row, int tcol, int buf) {
@@ -318,12 +318,13 @@ __global__ void __launch_bounds__(NT, HRW_MINB) fv1d_stage_kernel(const Fv1dGeom
 
    // tiles are walked as (row, tile-in-row) pairs advanced by gridDim.x without any division in the loop
    const int step_rows = (int)(gridDim.x / (unsigned)tpr), step_cols = (int)(gridDim.x % (unsigned)tpr);
-   int row = (int)(blockIdx.x / (unsigned)tpr), tcol = (int)(blockIdx.x % (unsigned)tpr);
-   if (tid == 0 && row < nrows) issue(row, tcol, 0);
+   int lin = g.tile_begin + (int)blockIdx.x; // linear tile id; this launch owns [tile_begin, tile_end)
+   int row = lin / tpr, tcol = lin % tpr;
+   if (tid == 0 && lin < g.tile_end) issue(row, tcol, 0);
 
    constexpr bool NEED_A = COMBINE == C_RK2_FINAL || COMBINE == C_RK3_S2 || COMBINE == C_RK3_S3 || COMBINE == C_MS;
 
-   for (int it = 0; row < nrows; ++it) {
+   for (int it = 0; lin < g.tile_end; ++it, lin += (int)gridDim.x) {
       const int buf = it & 1;
       int nrow = row + step_rows, ntcol = tcol + step_cols;
       if (ntcol >= tpr) {
@@ -332,7 +333,7 @@ __global__ void __launch_bounds__(NT, HRW_MINB) fv1d_stage_kernel(const Fv1dGeom
       }
       // prefetch the next tile into the other buffer: every thread finished reading it before the exchange
       // barrier of the previous iteration, which this thread has passed
-      if (tid == 0 && nrow < nrows) issue(nrow, ntcol, buf ^ 1);
+      if (tid == 0 && lin + (int)gridDim.x < g.tile_end) issue(nrow, ntcol, buf ^ 1);
 
       const int i0 = tcol * TILE + (tid - 1) * R; // first owned cell (thread 0: the run left of the tile)
       // a caller's dense output array carries no alignment guarantee: scalar stores (edge path) for every thread

@@ -31,8 +31,9 @@ static int launch(const Fv1dGeom &g, const StageArgs &a, cudaStream_t st) {
       cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, NT, 0);
       resident = (sms > 0 ? sms : 148) * (per_sm > 0 ? per_sm : 1);
    }
-   int64_t blocks = g.rows * g.tiles_per_row;
+   int64_t blocks = g.tile_end - g.tile_begin;
    if (blocks > resident) blocks = resident;
+   if (blocks < 1) return HRWENO_OK;
    kern<<<(unsigned)blocks, NT, 0, st>>>(g, a);
    HRW_CUDA(cudaGetLastError());
    return HRWENO_OK;

@@ -31,6 +31,7 @@ struct StageArgs {
    int64_t ld_out;     // row pitch of out (padded pitch, or n for a caller's dense array)
    int out_dense;      // 1: out is a caller's dense array: no ghost writes, no alignment assumptions
    double c0, c1;      // dt-like coefficients: (dt) | (2dt) | (50dt, 10dt)
+   int tile_begin = 0, tile_end = 0; // 1D only: restrict the launch to a range of tiles (0,0 = the whole state)
 };
 
 // Halo exchange between slab neighbours over NVLink peer memory (CUDA IPC), one process per GPU.
@@ -82,6 +83,8 @@ int fv_pack(Fv *fv, const double *dense_dev, double *padded_cell0, cudaStream_t 
 int fv_unpack(Fv *fv, const double *padded_cell0, double *dense_dev, cudaStream_t st);
 // one fused stage: reconstruct + face fluxes + divergence + combination
 int fv_stage(Fv *fv, int combine, const StageArgs &args, cudaStream_t st);
+// 1D tiling of the current configuration: cells per tile and tiles per row
+void fv_tiling_1d(const Fv *fv, int *tile_cells, int *tiles_per_row);
 struct Fv1dGeom;
 // fv1d_inst.cu, compiled once per (k, mode): launches the 1D stage kernel specialised for (combine, flux kind, width kind)
 int fv1d_launch(int k, int mode, int combine, int flux_kind, int width_kind, int half_tile, const Fv1dGeom &g, const StageArgs &a,
@@ -125,6 +128,9 @@ struct Ode {
    std::vector<double *> bufs;
    int ring = 0; // mstvd: index of the slot holding u^n inside the u ring
    cudaStream_t stream = nullptr;
+   // chunk pipeline of the host-pointer entry point (ode.cu: rk_integrate_pipelined)
+   cudaStream_t s_in = nullptr, s_out = nullptr;
+   std::vector<cudaEvent_t> ev_in, ev_fin;
    ~Ode();
 };
 

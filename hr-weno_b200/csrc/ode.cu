@@ -5,7 +5,9 @@
 // 282); every stage is one fused device kernel (fused path) or one user rhs call plus one combine
 // kernel (callback path).  mstvd keeps its history in rings addressed by the step number instead of
 // the reference's two eoshift copies per step (tvdode.f90:262-263).
+#include <algorithm>
 #include <cmath>
+#include <cstdlib>
 #include <new>
 
 #include "internal.hpp"
@@ -16,6 +18,10 @@ static inline bool is_done(double t, double tout, double dt) { return (t - tout)
 
 Ode::~Ode() {
    for (double *p : bufs) cudaFree(p);
+   for (cudaEvent_t e : ev_in) cudaEventDestroy(e);
+   for (cudaEvent_t e : ev_fin) cudaEventDestroy(e);
+   if (s_in) cudaStreamDestroy(s_in);
+   if (s_out) cudaStreamDestroy(s_out);
    if (stream) cudaStreamDestroy(stream);
 }
 
@@ -312,10 +318,149 @@ int ode_integrate_dev(Ode *o, double *u_dev, double *t, double tout, double dt, 
    return rk_integrate(o, u_dev, t, tout, dt, itask, st);
 }
 
+// ------------------------------------------------------------------------------------------------
+// Host-pointer rktvd_integrate for one large 1D row: a time-skewed chunk pipeline.
+// The row is cut into C chunks of whole tiles.  Chunk c is copied host->device on its own stream straight into the
+// padded state; stage g of chunk c (a launch restricted to that chunk's tiles) needs stage g-1 of chunks c-1, c, c+1,
+// hence chunk c+g+1 to have arrived.  Launching the tasks (c, g) diagonal by diagonal (d = c + g, g ascending inside a
+// diagonal) on ONE compute stream satisfies every read-after-write and write-after-read dependency of the RK buffers by
+// stream order alone, and lets the early chunks run many stages ahead while the late ones are still on the PCIe bus;
+// chunk c goes back to the host as soon as its last stage is done.  Arithmetic and results are those of the plain path.
+// ------------------------------------------------------------------------------------------------
+__global__ void fill_ghost_kernel(double *cell0, int64_t n, int k, int left, int right) {
+   const int q = threadIdx.x;
+   if (q < k) {
+      if (left) cell0[-1 - q] = cell0[0];      // weno.f90:172
+      if (right) cell0[n + q] = cell0[n - 1];  // weno.f90:173
+   }
+}
+
+static int rk_integrate_pipelined(Ode *o, double *u, double *t, double tout, double dt, int itask, bool *done) {
+   *done = false;
+   Fv *fv = o->fv;
+   if (!o->fused || o->is_ms || fv->d.ndim != 1 || fv->rows != 1 || fv->d.nranks > 1) return HRWENO_OK;
+   int tile = 0, tpr = 0;
+   fv_tiling_1d(fv, &tile, &tpr);
+   int chunk_tiles = 148 * 48; // a multiple of every resident-CTA count in use (148 x 1,2,3,4,6,8): no ragged last wave;
+                               // 7.2 M cells per chunk measured best on B200 (profiles/r1_variant_sweeps.txt)
+   if (const char *e = std::getenv("HRWENO_PIPE_CHUNK_TILES")) chunk_tiles = std::atoi(e);
+   if (chunk_tiles < 1) return HRWENO_OK; // pipeline disabled
+   const int C = (tpr + chunk_tiles - 1) / chunk_tiles;
+   if (C < 4) return HRWENO_OK;
+   // number of steps this call takes (tvdode.f90:161-171: step, then test)
+   int64_t nsteps = 0;
+   double tt = *t;
+   for (;;) {
+      tt = tt + dt;
+      ++nsteps;
+      if (is_done(tt, tout, dt) || itask == 2) break;
+   }
+   const int order = o->order;
+   const int64_t G = (int64_t)order * nsteps;
+   if (G + C > 2000000) return HRWENO_OK;
+   const int64_t n = fv->n0;
+   if (!o->s_in) HRW_CUDA(cudaStreamCreateWithFlags(&o->s_in, cudaStreamNonBlocking));
+   if (!o->s_out) HRW_CUDA(cudaStreamCreateWithFlags(&o->s_out, cudaStreamNonBlocking));
+   while ((int)o->ev_in.size() < C) {
+      cudaEvent_t e;
+      HRW_CUDA(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
+      o->ev_in.push_back(e);
+      HRW_CUDA(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
+      o->ev_fin.push_back(e);
+   }
+   double *B[3] = {fv->cell0(o->bufs[0]), fv->cell0(o->bufs[1]), fv->cell0(o->bufs[2])}; // U, T1, T2 at cell 0
+   const int k = fv->d.k;
+   const int64_t chunk_cells = (int64_t)chunk_tiles * tile;
+   auto c_lo = [&](int c) { return (int64_t)c * chunk_cells; };
+   auto c_hi = [&](int c) { return std::min<int64_t>(n, (int64_t)(c + 1) * chunk_cells); };
+   cudaStream_t cs = o->stream;
+   // host -> device, chunk by chunk, straight into the padded state (one row: dense offset == padded offset)
+   for (int c = 0; c < C; ++c) {
+      HRW_CUDA(cudaMemcpyAsync(B[0] + c_lo(c), u + c_lo(c), (size_t)(c_hi(c) - c_lo(c)) * sizeof(double), cudaMemcpyHostToDevice, o->s_in));
+      HRW_CUDA(cudaEventRecord(o->ev_in[c], o->s_in));
+   }
+   int waited = -1; // highest chunk whose arrival the compute stream already waits for
+   auto need = [&](int c) -> int {
+      if (c > C - 1) c = C - 1;
+      while (waited < c) {
+         ++waited;
+         HRW_CUDA(cudaStreamWaitEvent(cs, o->ev_in[waited], 0));
+         if (waited == 0) fill_ghost_kernel<<<1, 32, 0, cs>>>(B[0], n, k, 1, 0);
+         if (waited == C - 1) fill_ghost_kernel<<<1, 32, 0, cs>>>(B[0], n, k, 0, 1);
+         if (waited == 0 || waited == C - 1) fv->launches++;
+      }
+      return HRWENO_OK;
+   };
+   const int fin_buf = order == 1 ? (int)(nsteps & 1) : 0; // RK1 ping-pongs U <-> T1
+   for (int64_t d = 0; d <= (int64_t)(C - 1) + (G - 1); ++d) {
+      if (d + 1 <= C - 1 || waited < C - 1) HRW_TRY(need((int)std::min<int64_t>(d + 1, C - 1)));
+      const int64_t g_lo = std::max<int64_t>(0, d - (C - 1)), g_hi = std::min<int64_t>(d, G - 1);
+      for (int64_t g = g_lo; g <= g_hi; ++g) {
+         const int c = (int)(d - g);
+         const int64_t step = g / order;
+         const int j = (int)(g - step * order);
+         StageArgs a{};
+         a.ld_out = fv->pitch;
+         a.tile_begin = c * chunk_tiles;
+         a.tile_end = std::min(tpr, (c + 1) * chunk_tiles);
+         int combine;
+         if (order == 1) {
+            combine = C_EULER;
+            a.vin = B[step & 1];
+            a.out = B[(step & 1) ^ 1];
+            a.c0 = dt;
+         } else if (j == 0) {
+            combine = C_EULER; // ui = u + dt*udot
+            a.vin = B[0];
+            a.out = B[1];
+            a.c0 = dt;
+         } else if (order == 2) {
+            combine = C_RK2_FINAL; // u = (u + ui + dt*udot)/2
+            a.vin = B[1];
+            a.a = B[0];
+            a.out = B[0];
+            a.c0 = dt;
+         } else if (j == 1) {
+            combine = C_RK3_S2; // ui = (3*u + ui + dt*udot)/4
+            a.vin = B[1];
+            a.a = B[0];
+            a.out = B[2];
+            a.c0 = dt;
+         } else {
+            combine = C_RK3_S3; // u = (u + 2*ui + 2*dt*udot)/3
+            a.vin = B[2];
+            a.a = B[0];
+            a.out = B[0];
+            a.c0 = 2 * dt;
+         }
+         HRW_TRY(fv_stage(fv, combine, a, cs));
+         if (g == G - 1) { // chunk c is final: device -> host on the output stream
+            HRW_CUDA(cudaEventRecord(o->ev_fin[c], cs));
+            HRW_CUDA(cudaStreamWaitEvent(o->s_out, o->ev_fin[c], 0));
+            HRW_CUDA(cudaMemcpyAsync(u + c_lo(c), B[fin_buf] + c_lo(c), (size_t)(c_hi(c) - c_lo(c)) * sizeof(double), cudaMemcpyDeviceToHost,
+                                     o->s_out));
+         }
+      }
+   }
+   HRW_CUDA(cudaStreamSynchronize(o->s_out));
+   HRW_CUDA(cudaStreamSynchronize(cs));
+   if (order == 1 && (nsteps & 1)) std::swap(o->bufs[0], o->bufs[1]);
+   *t = tt;
+   o->fevals += (int64_t)order * nsteps;
+   if (o->istate == 1) o->istate = 2;
+   *done = true;
+   return HRWENO_OK;
+}
+
 int ode_integrate_host(Ode *o, double *u, double *t, double tout, double dt, int itask) {
    if (!o || !u || !t) return fail(HRWENO_EINVAL, "integrate: null argument");
    if (o->istate < 1) return HRWENO_OK;
    if (is_done(*t, tout, dt)) return HRWENO_OK;
+   if (o->fused) {
+      bool done = false;
+      HRW_TRY(rk_integrate_pipelined(o, u, t, tout, dt, itask, &done));
+      if (done) return HRWENO_OK;
+   }
    double *d = o->bufs.back();
    const size_t bytes = (size_t)o->neq * sizeof(double);
    HRW_CUDA(cudaMemcpyAsync(d, u, bytes, cudaMemcpyHostToDevice, o->stream));

@@ -369,3 +369,30 @@ def test_fast_mode_rhs_within_a_few_ulp(gpu_lib, pkg, ref):
     got = pkg.fv.FV(pkg.fv.make_desc(mode=pkg._abi.MODE_FAST, **kw)).rhs(0.0, v2)
     want = ref.FV(pkg.fv.make_desc(**kw)).rhs(0.0, v2)
     assert np.max(np.abs(got - want)) <= 16 * np.finfo(float).eps * np.max(np.abs(v2)) / min(g1.width.min(), g2.width.min())
+
+
+@pytest.mark.parametrize("order", [1, 2, 3])
+def test_host_integrate_chunk_pipeline_bitwise(gpu_lib, pkg, ref, order, monkeypatch):
+    """the host-pointer integrate of a large 1D row runs as a time-skewed chunk pipeline (ode.cu); forced here at a
+    small size with one tile per chunk: results must equal the oracle's bit for bit, call after call"""
+    monkeypatch.setenv("HRWENO_PIPE_CHUNK_TILES", "1")
+    nc = 7 * 1016 + 333  # 8 chunks of one tile, the last one partial
+    g = pkg.hrweno_grids.grid1().linear(-5.0, 5.0, nc)
+    rng = np.random.default_rng(order)
+    u0 = ex1_ic(g.center) + 1e-3 * rng.standard_normal(nc)
+    for kw in (dict(n=nc, k=3, linear=(-5.0, 5.0)), dict(n=nc, k=2, flux_scheme=1, alpha=1.2, width=[g.width])):
+        rkw = dict(kw)
+        rkw.pop("linear", None)
+        rkw["width"] = [g.width]
+        ode = pkg.hrweno_tvdode.rktvd(pkg.fv.FV(pkg.fv.make_desc(**kw)), nc, order)
+        rode = ref.rktvd(ref.FV(pkg.fv.make_desc(**rkw)), order)
+        launches0 = ode.launches
+        u, ur, t, tr = u0.copy(), u0.copy(), 0.0, 0.0
+        dt = 0.2 * 10.0 / nc
+        for tout in (0.0, 7 * dt, 7 * dt, 20 * dt):
+            t = ode.integrate(u, t, tout, dt)
+            tr = rode.integrate(ur, tr, tout, dt)
+            assert t == tr and np.array_equal(u, ur)
+        t, tr = ode.integrate(u, t, 1e9, dt, itask=2), rode.integrate(ur, tr, 1e9, dt, itask=2)
+        assert t == tr and np.array_equal(u, ur) and ode.fevals == rode.fevals
+        assert ode.launches - launches0 > 8 * order * 20  # one launch per (chunk, stage): the pipeline was taken
