@@ -53,7 +53,7 @@ static int fv_rhs_any(Fv *fv, const double *v_dev, double *vdot_dev, cudaStream_
    a.out = vdot_dev;
    a.ld_out = fv->n0;
    a.out_dense = 1;
-   return fv_stage(fv, C_RHS, a, st);
+   return fv_stage_halo(fv, C_RHS, a, false, st);
 }
 
 } // namespace hrw

@@ -343,7 +343,7 @@ void fv_tiling_1d(const Fv *fv, int *tile_cells, int *tiles_per_row) {
    *tiles_per_row = (int)((fv->n0 + tile - 1) / tile);
 }
 
-int fv_stage(Fv *fv, int combine, const StageArgs &args, cudaStream_t st) {
+static int fv_stage_impl(Fv *fv, int combine, const StageArgs &args, const HaloIO *io, cudaStream_t st) {
    const hrweno_fv_desc &d = fv->d;
    if (d.ndim == 2) {
       HRW_TRY(fv2d_stage(fv, combine, args, st));
@@ -368,8 +368,21 @@ int fv_stage(Fv *fv, int combine, const StageArgs &args, cudaStream_t st) {
    g.bc = d.bc;
    g.phys_left = d.rank == 0;
    g.phys_right = d.rank == d.nranks - 1;
+   if (io) g.halo = *io;
    HRW_TRY(fv1d_launch(d.k, d.mode, combine, fk, fv->width_dict ? WK_DICT : WK_ARRAY, half_tile, g, args, st));
    fv->launches++;
+   return HRWENO_OK;
+}
+
+int fv_stage(Fv *fv, int combine, const StageArgs &args, cudaStream_t st) { return fv_stage_impl(fv, combine, args, nullptr, st); }
+
+int fv_stage_halo(Fv *fv, int combine, const StageArgs &args, bool halo_out, cudaStream_t st) {
+   if (fv->d.nranks <= 1) return fv_stage_impl(fv, combine, args, nullptr, st);
+   HaloIO io;
+   HRW_TRY(fv_halo_io(fv, args.vin, args.out, halo_out && !args.out_dense, &io));
+   if (io.edge_first) return fv_stage_impl(fv, combine, args, &io, st); // halo traffic inside the stage kernel
+   HRW_TRY(fv_stage_impl(fv, combine, args, nullptr, st));
+   if (halo_out && !args.out_dense) HRW_TRY(fv_exchange(fv, args.out, st));
    return HRWENO_OK;
 }
 

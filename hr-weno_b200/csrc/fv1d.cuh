@@ -45,6 +45,7 @@ struct Fv1dGeom {
    FluxCfg flux;
    int bc;
    int phys_left, phys_right; // the row ends are physical boundaries (not slab interfaces)
+   HaloIO halo;               // slab-interface halo traffic fused into this launch (all null on one GPU)
 };
 
 // ---- TMA bulk copy + mbarrier (PTX; SASS: UBLKCP / SYNCS) ----------------------------------------------
@@ -320,7 +321,10 @@ __global__ void __launch_bounds__(NT, HRW_MINB) fv1d_stage_kernel(const Fv1dGeom
    const int step_rows = (int)(gridDim.x / (unsigned)tpr), step_cols = (int)(gridDim.x % (unsigned)tpr);
    int lin = g.tile_begin + (int)blockIdx.x; // linear tile id; this launch owns [tile_begin, tile_end)
    int row = lin / tpr, tcol = lin % tpr;
-   if (tid == 0 && lin < g.tile_end) issue(row, tcol, 0);
+   // slabs: the two edge tiles are walked first (logical tile 1 <-> last tile), so the boundary cells reach the
+   // neighbour GPU while the bulk of the stage is still being computed
+   auto remap = [&](int tc) { return (!g.halo.edge_first || tpr < 3) ? tc : (tc == 1 ? tpr - 1 : (tc == tpr - 1 ? 1 : tc)); };
+   if (tid == 0 && lin < g.tile_end) issue(row, remap(tcol), 0);
 
    constexpr bool NEED_A = COMBINE == C_RK2_FINAL || COMBINE == C_RK3_S2 || COMBINE == C_RK3_S3 || COMBINE == C_MS;
 
@@ -333,9 +337,10 @@ __global__ void __launch_bounds__(NT, HRW_MINB) fv1d_stage_kernel(const Fv1dGeom
       }
       // prefetch the next tile into the other buffer: every thread finished reading it before the exchange
       // barrier of the previous iteration, which this thread has passed
-      if (tid == 0 && lin + (int)gridDim.x < g.tile_end) issue(nrow, ntcol, buf ^ 1);
+      if (tid == 0 && lin + (int)gridDim.x < g.tile_end) issue(nrow, remap(ntcol), buf ^ 1);
 
-      const int i0 = tcol * TILE + (tid - 1) * R; // first owned cell (thread 0: the run left of the tile)
+      const int ptc = remap(tcol);               // physical tile of this iteration
+      const int i0 = ptc * TILE + (tid - 1) * R; // first owned cell (thread 0: the run left of the tile)
       // a caller's dense output array carries no alignment guarantee: scalar stores (edge path) for every thread
       const bool skip = tid == 0 || tid == NT - 1 || i0 >= n;
       const bool edge = s.out_dense || (i0 + R >= n) || (i0 == 0);
@@ -376,6 +381,36 @@ __global__ void __launch_bounds__(NT, HRW_MINB) fv1d_stage_kernel(const Fv1dGeom
 
       mbar_wait(&s_bar[buf], (uint32_t)((it >> 1) & 1));
 
+      // slab interface: the ghost cells of an edge tile come from this GPU's mailbox (stored there by the neighbour's
+      // previous stage); wait for the sequence number, then patch them into the staged tile
+      if (g.halo.seq_in) {
+         const bool rl = ptc == 0 && g.halo.recv_left, rr = ptc == tpr - 1 && g.halo.recv_right;
+         if (rl || rr) { // CTA-uniform
+            if (tid < 32) {
+               if (tid == 0) {
+                  const long long t0 = clock64();
+                  for (int side = 0; side < 2; ++side) {
+                     const unsigned long long *f = side == 0 ? (rl ? g.halo.rflag_left : nullptr) : (rr ? g.halo.rflag_right : nullptr);
+                     if (!f) continue;
+                     while (*reinterpret_cast<const volatile unsigned long long *>(f) < g.halo.seq_in) {
+                        if (*reinterpret_cast<volatile unsigned int *>(g.halo.err) != 0) break;
+                        if (clock64() - t0 > g.halo.timeout_cycles) {
+                           atomicExch(g.halo.err, 1u);
+                           break;
+                        }
+                     }
+                  }
+                  __threadfence_system();
+               }
+               __syncwarp();
+               const int ts = ptc * TILE - R - P;
+               if (rl && tid < K) s_v[buf][(-K + tid) - ts] = __ldcv(g.halo.recv_left + tid);
+               if (rr && tid < K) s_v[buf][(n + tid) - ts] = __ldcv(g.halo.recv_right + tid);
+            }
+            __syncthreads();
+         }
+      }
+
       // register window: cells i0-2 .. i0+R+1
       double w[WN];
 #pragma unroll
@@ -399,6 +434,28 @@ __global__ void __launch_bounds__(NT, HRW_MINB) fv1d_stage_kernel(const Fv1dGeom
             fv1d_finish<K, COMBINE, M, FK, WK, R, false>(g, s, s_wtab, row, i0, w, vl, vr, vr_left, vl_right, cL, lscale, pf);
          else
             fv1d_finish<K, COMBINE, M, FK, WK, R, true>(g, s, s_wtab, row, i0, w, vl, vr, vr_left, vl_right, cL, lscale, pf);
+      }
+      // slab interface: the CTA that just wrote the first / last k cells of the slab stores them into the neighbour's
+      // mailbox over NVLink and publishes the sequence number (release: fence, then flag)
+      if (g.halo.seq_out) {
+         const bool sl = ptc == 0 && g.halo.send_left, sr = ptc == tpr - 1 && g.halo.send_right;
+         if (sl || sr) { // CTA-uniform
+            __syncthreads(); // every store of this tile has been issued
+            if (tid == 0) {
+               const double *orow = s.out + (int64_t)row * s.ld_out;
+               if (sl) {
+#pragma unroll
+                  for (int q = 0; q < K; ++q) g.halo.send_left[q] = __ldcg(orow + q);
+               }
+               if (sr) {
+#pragma unroll
+                  for (int q = 0; q < K; ++q) g.halo.send_right[q] = __ldcg(orow + (n - K + q));
+               }
+               __threadfence_system();
+               if (sl) *reinterpret_cast<volatile unsigned long long *>(g.halo.sflag_left) = g.halo.seq_out;
+               if (sr) *reinterpret_cast<volatile unsigned long long *>(g.halo.sflag_right) = g.halo.seq_out;
+            }
+         }
       }
       row = nrow;
       tcol = ntcol;

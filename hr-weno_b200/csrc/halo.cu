@@ -142,6 +142,7 @@ int fv_halo_status(Fv *fv) {
 int fv_exchange(Fv *fv, double *cell0, cudaStream_t st) {
    if (fv->d.nranks <= 1) return HRWENO_OK;
    Halo &h = fv->halo;
+   if (h.pending_buf == cell0) h.pending_buf = nullptr; // ghosts are about to be in place
    if (!h.ready) return fail(HRWENO_ECOMM, "slab decomposition needs hrweno_fv_export_halo / hrweno_fv_import_halo first");
    const unsigned long long seq = ++h.seq;
    const int slot = (int)(seq % Halo::NSLOTS);
@@ -167,6 +168,53 @@ int fv_exchange(Fv *fv, double *cell0, cudaStream_t st) {
                                             ffr, seq, reinterpret_cast<unsigned int *>(h.mbox + ERR_OFF), timeout_cycles);
    fv->launches += 3;
    HRW_CUDA(cudaGetLastError());
+   return HRWENO_OK;
+}
+
+// Build the in-kernel halo description for one fused stage (see HaloIO).  Returns with io->edge_first == 0 when the
+// configuration is not eligible (then the caller uses fv_exchange after the stage).
+int fv_halo_io(Fv *fv, const double *vin_cell0, const double *out_cell0, bool halo_out, HaloIO *io) {
+   *io = HaloIO{};
+   Halo &h = fv->halo;
+   if (fv->d.nranks <= 1 || fv->d.ndim != 1 || fv->rows != 1) return HRWENO_OK;
+   if (!h.ready) return fail(HRWENO_ECOMM, "slab decomposition needs hrweno_fv_export_halo / hrweno_fv_import_halo first");
+   // the k boundary cells must lie inside one tile on either side (the CTA that sends them must have written them)
+   int tile = 0, tpr = 0;
+   fv_tiling_1d(fv, &tile, &tpr);
+   if (fv->n0 - (int64_t)(tpr - 1) * tile < fv->d.k || fv->n0 < fv->d.k) return HRWENO_OK;
+   const size_t hd = h.halo_doubles;
+   io->edge_first = 1;
+   io->err = reinterpret_cast<unsigned int *>(h.mbox + ERR_OFF);
+   io->timeout_cycles = 60LL * 1900000000LL;
+   if (h.pending_buf == vin_cell0 && h.pending_seq != 0) { // the input's ghost cells sit in my mailbox
+      const int slot = (int)(h.pending_seq % Halo::NSLOTS);
+      io->seq_in = h.pending_seq;
+      if (h.peer[0]) {
+         io->recv_left = reinterpret_cast<const double *>(slot_ptr(h.mbox, hd, 0, slot));
+         io->rflag_left = reinterpret_cast<const unsigned long long *>(h.mbox + flag_off(0, slot));
+      }
+      if (h.peer[1]) {
+         io->recv_right = reinterpret_cast<const double *>(slot_ptr(h.mbox, hd, 1, slot));
+         io->rflag_right = reinterpret_cast<const unsigned long long *>(h.mbox + flag_off(1, slot));
+      }
+   }
+   if (halo_out) {
+      const unsigned long long seq = ++h.seq;
+      const int slot = (int)(seq % Halo::NSLOTS);
+      io->seq_out = seq;
+      if (h.peer[0]) { // I am my left neighbour's right neighbour: its side 1 ("from right")
+         io->send_left = reinterpret_cast<double *>(slot_ptr(h.peer[0], hd, 1, slot));
+         io->sflag_left = reinterpret_cast<unsigned long long *>(h.peer[0] + flag_off(1, slot));
+      }
+      if (h.peer[1]) {
+         io->send_right = reinterpret_cast<double *>(slot_ptr(h.peer[1], hd, 0, slot));
+         io->sflag_right = reinterpret_cast<unsigned long long *>(h.peer[1] + flag_off(0, slot));
+      }
+      h.pending_buf = out_cell0;
+      h.pending_seq = seq;
+   } else if (h.pending_buf == out_cell0) {
+      h.pending_buf = nullptr; // overwritten without a send (its ghost cells are not needed)
+   }
    return HRWENO_OK;
 }
 

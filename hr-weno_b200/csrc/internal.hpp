@@ -34,6 +34,21 @@ struct StageArgs {
    int tile_begin = 0, tile_end = 0; // 1D only: restrict the launch to a range of tiles (0,0 = the whole state)
 };
 
+// Halo traffic fused into the 1D stage kernel (one slab per GPU, rows == 1).  The CTA that computed the first / last
+// k cells of the slab stores them into the neighbour's mailbox over NVLink and publishes seq_out; the CTA that owns an
+// edge tile of the NEXT stage waits for seq_in and patches the ghost cells of its shared-memory tile from its own
+// mailbox.  Edge tiles are walked first, so the transfer overlaps the bulk of the stage.  nullptr = side not used.
+struct HaloIO {
+   double *send_left = nullptr, *send_right = nullptr;                      // peer mailbox slots for this stage's output
+   unsigned long long *sflag_left = nullptr, *sflag_right = nullptr;        // peer flags to publish
+   const double *recv_left = nullptr, *recv_right = nullptr;                // my mailbox slots with the input's ghost cells
+   const unsigned long long *rflag_left = nullptr, *rflag_right = nullptr;  // my flags to wait on
+   unsigned long long seq_out = 0, seq_in = 0;
+   unsigned int *err = nullptr;
+   long long timeout_cycles = 0;
+   int edge_first = 0; // walk tile 0 and the last tile first
+};
+
 // Halo exchange between slab neighbours over NVLink peer memory (CUDA IPC), one process per GPU.
 // Every rank owns a mailbox; its neighbours store their boundary cells straight into it (peer stores)
 // and then publish a sequence number; the owner's receive kernel spins on that number and moves the
@@ -47,6 +62,9 @@ struct Halo {
    unsigned char *peer[2] = {nullptr, nullptr}; // left / right neighbour's mailbox mapped into this process
    unsigned long long seq = 0;               // number of exchanges done (identical on all ranks: SPMD)
    bool ready = false;
+   // which padded state has its slab-interface ghost cells in a mailbox slot (sequence number) instead of in place
+   const double *pending_buf = nullptr;
+   unsigned long long pending_seq = 0;
 };
 
 struct Fv {
@@ -91,6 +109,10 @@ int fv1d_launch(int k, int mode, int combine, int flux_kind, int width_kind, int
                 cudaStream_t st);
 // fill the slab-interface ghost cells of a padded state from the neighbouring ranks (no-op on one GPU)
 int fv_exchange(Fv *fv, double *padded_cell0, cudaStream_t st);
+// stage + halo: fused into the kernel where supported (1D, one row, slabs), else fv_stage followed by fv_exchange.
+// `halo_out`: the result will be a stencil input (its ghost cells must reach the neighbours).
+int fv_stage_halo(Fv *fv, int combine, const StageArgs &args, bool halo_out, cudaStream_t st);
+int fv_halo_io(Fv *fv, const double *vin_cell0, const double *out_cell0, bool halo_out, HaloIO *io);
 int fv_halo_export(Fv *fv, void *handle_out);
 int fv_halo_import(Fv *fv, const void *left, const void *right);
 int fv_halo_status(Fv *fv);

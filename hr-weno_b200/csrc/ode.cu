@@ -136,36 +136,31 @@ static int rk_step_fused(Ode *o, int order, double *src, double *dst, double *t1
       a.vin = c0(src);
       a.out = c0(dst);
       a.c0 = dt;
-      HRW_TRY(fv_stage(fv, C_EULER, a, st));
-      HRW_TRY(fv_exchange(fv, c0(dst), st));
+      HRW_TRY(fv_stage_halo(fv, C_EULER, a, true, st));
       o->launches += 1;
       return HRWENO_OK;
    }
    a.vin = c0(src);
    a.out = c0(t1);
    a.c0 = dt;
-   HRW_TRY(fv_stage(fv, C_EULER, a, st)); // ui = u + dt*udot
-   HRW_TRY(fv_exchange(fv, c0(t1), st));
+   HRW_TRY(fv_stage_halo(fv, C_EULER, a, true, st)); // ui = u + dt*udot
    if (order == 2) {
       a.vin = c0(t1);
       a.a = c0(src);
       a.out = c0(dst);
-      HRW_TRY(fv_stage(fv, C_RK2_FINAL, a, st)); // u = (u + ui + dt*udot)/2
-      HRW_TRY(fv_exchange(fv, c0(dst), st));
+      HRW_TRY(fv_stage_halo(fv, C_RK2_FINAL, a, true, st)); // u = (u + ui + dt*udot)/2
       o->launches += 2;
       return HRWENO_OK;
    }
    a.vin = c0(t1);
    a.a = c0(src);
    a.out = c0(t2);
-   HRW_TRY(fv_stage(fv, C_RK3_S2, a, st)); // ui = (3*u + ui + dt*udot)/4
-   HRW_TRY(fv_exchange(fv, c0(t2), st));
+   HRW_TRY(fv_stage_halo(fv, C_RK3_S2, a, true, st)); // ui = (3*u + ui + dt*udot)/4
    a.vin = c0(t2);
    a.a = c0(src);
    a.out = c0(dst);
    a.c0 = 2 * dt;
-   HRW_TRY(fv_stage(fv, C_RK3_S3, a, st)); // u = (u + 2*ui + 2*dt*udot)/3
-   HRW_TRY(fv_exchange(fv, c0(dst), st));
+   HRW_TRY(fv_stage_halo(fv, C_RK3_S3, a, true, st)); // u = (u + 2*ui + 2*dt*udot)/3
    o->launches += 3;
    return HRWENO_OK;
 }
@@ -260,7 +255,7 @@ static int ms_integrate(Ode *o, double *u_dev, double *t, double tout, double dt
             a.vin = fv->cell0(U);
             a.out = fv->cell0(lring[step % 4]);
             a.ld_out = fv->pitch;
-            HRW_TRY(fv_stage(fv, C_RHS, a, st));
+            HRW_TRY(fv_stage_halo(fv, C_RHS, a, false, st));
             o->launches++;
             HRW_TRY(rk_step_fused(o, 3, U, Un, T1, T2, dt, st));
          } else {
@@ -288,8 +283,7 @@ static int ms_integrate(Ode *o, double *u_dev, double *t, double tout, double dt
          a.ld_out = fv->pitch;
          a.c0 = c50;
          a.c1 = c10;
-         HRW_TRY(fv_stage(fv, C_MS, a, st));
-         HRW_TRY(fv_exchange(fv, fv->cell0(Uo4), st));
+         HRW_TRY(fv_stage_halo(fv, C_MS, a, true, st));
          o->launches++;
       } else {
          o->fu(o->ctx, *t, n, U, T1, st); // udot
