@@ -13,6 +13,7 @@
 //            boundary constraints (example2:117-120), vdot = -(df1)/w1 - (df2)/w2 (example2:123-127),
 //            stage combination, coalesced stores along x1.
 #include "fv2d.cuh"
+#include "fv1d.cuh" // TMA bulk copy + mbarrier helpers
 
 namespace hrw {
 
@@ -37,10 +38,10 @@ struct Tile2d {
    static constexpr int YROWS = TY + 2 * R;      // rows of the x2-sweep vl/vr arrays
    static constexpr int RUNS_X = TX / R + 2, NRX = RUNS_X * TY;
    static constexpr int RUNS_Y = TY / R + 2, NRY = RUNS_Y * TX;
-   static constexpr int GR = 2;                  // zero guard rows above/below the staged tile (read by the
-                                                 // unused outer cells of the overlap runs of the x2-sweep)
-   static constexpr int OFF_V = GR * SP;
-   static constexpr int OFF_VLX = OFF_V + (SROWS + GR) * SP;
+   // two staged-tile buffers: the next tile is fetched by TMA row copies while this one is being computed
+   static constexpr int OFF_V = 0;
+   static constexpr int TILE_DOUBLES = SROWS * SP;
+   static constexpr int OFF_VLX = OFF_V + 2 * TILE_DOUBLES;
    // upwind specialisation: the left-side arrays are never touched and get no storage (more CTAs per SM)
    static constexpr int OFF_VRX = OFF_VLX + (UPW ? 0 : TY * XP);
    static constexpr int OFF_VLY = OFF_VRX + TY * XP;
@@ -200,21 +201,50 @@ __global__ void __launch_bounds__(NT) fv2d_stage_kernel(const Fv2dGeom g, const 
    double *s_vlx = smem + T::OFF_VLX, *s_vrx = smem + T::OFF_VRX;
    double *s_vly = smem + T::OFF_VLY, *s_vry = smem + T::OFF_VRY;
 
+   __shared__ __align__(8) unsigned long long s_bar[2];
    const int tid = threadIdx.x;
-   const int64_t x0 = (int64_t)blockIdx.x * TX;
-   const int64_t y0 = (int64_t)blockIdx.y * TY;
+   const int total_tiles = g.tiles_x * g.tiles_y;
 
-   // ---- stage tile + frame: rows y0-H .. y0+TY+H-1, columns x0-H .. x0+TX+H-1 -----------------------
-   for (int idx = tid; idx < (T::SROWS + 2 * T::GR) * (T::SP / 2); idx += NT) {
-      const int ry = idx / (T::SP / 2) - T::GR;
-      const int cx = (idx - (ry + T::GR) * (T::SP / 2)) * 2;
-      const int64_t gy = y0 - H + ry, gx = x0 - H + cx;
-      double2 t = make_double2(0.0, 0.0);
-      if (ry >= 0 && ry < T::SROWS && gy >= -PAD2 && gy < g.n1 + PAD2 && gx >= -PAD && gx + 1 < g.n0 + PAD)
-         t = *reinterpret_cast<const double2 *>(s.vin + gy * g.pitch + gx);
-      *reinterpret_cast<double2 *>(&s_v[ry * T::SP + cx]) = t;
+   // warp 0 fetches a tile + frame (rows y0-H .. y0+TY+H-1, columns x0-H .. x0+TX+H-1, clipped to the padded state)
+   // with one TMA bulk copy per row, all completing on the buffer's mbarrier
+   auto issue = [&](int tile_id, int buf) {
+      const int ty = tile_id / g.tiles_x, tx = tile_id - ty * g.tiles_x;
+      const int x0 = tx * TX, y0 = ty * TY;
+      int hi = x0 - H + T::SP;
+      if (hi > (int)g.pitch - PAD) hi = (int)g.pitch - PAD;
+      const uint32_t row_bytes = (uint32_t)(hi - (x0 - H)) * (uint32_t)sizeof(double);
+      int r_lo = -PAD2 - (y0 - H), r_hi = (int)g.n1 + PAD2 - (y0 - H); // valid tile rows [r_lo, r_hi)
+      r_lo = r_lo < 0 ? 0 : r_lo;
+      r_hi = r_hi > T::SROWS ? T::SROWS : r_hi;
+      const int lane = tid;
+      if (lane == 0) mbar_expect_tx(&s_bar[buf], row_bytes * (uint32_t)(r_hi - r_lo));
+      __syncwarp();
+      double *dst = s_v + buf * T::TILE_DOUBLES;
+      for (int r = r_lo + lane; r < r_hi; r += 32)
+         tma_bulk_g2s(dst + r * T::SP, s.vin + (int64_t)(y0 - H + r) * g.pitch + (x0 - H), row_bytes, &s_bar[buf]);
+   };
+
+   for (int idx = tid; idx < 2 * T::TILE_DOUBLES; idx += NT) s_v[idx] = 0.0; // parts a clipped copy never writes
+   asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+   if (tid == 0) {
+      mbar_init(&s_bar[0], 1);
+      mbar_init(&s_bar[1], 1);
+      asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
    }
    __syncthreads();
+   if (tid < 32 && (int)blockIdx.x < total_tiles) issue(blockIdx.x, 0);
+
+   int it_n = 0;
+   for (int tile_id = blockIdx.x; tile_id < total_tiles; tile_id += gridDim.x, ++it_n) {
+   const int buf = it_n & 1;
+   // every thread is past phase B of the previous tile: its staged tile and its vl/vr arrays may be overwritten
+   __syncthreads();
+   if (tid < 32 && tile_id + (int)gridDim.x < total_tiles) issue(tile_id + gridDim.x, buf ^ 1);
+   const int ty_ = tile_id / g.tiles_x, tx_ = tile_id - ty_ * g.tiles_x;
+   const int64_t x0 = (int64_t)tx_ * TX;
+   const int64_t y0 = (int64_t)ty_ * TY;
+   double *s_vt = s_v + buf * T::TILE_DOUBLES; // this tile
+   mbar_wait(&s_bar[buf], (uint32_t)((it_n >> 1) & 1));
 
    // ---- phase A: reconstruction items ------------------------------------------------------------------
    // regular items: runs of R cells inside the tile, x1-lines first, then x2-lines (one code path, (base, stride) addressing)
@@ -226,7 +256,7 @@ __global__ void __launch_bounds__(NT) fv2d_stage_kernel(const Fv2dGeom g, const 
       if (it < NXR) { // x1-sweep: row ly, run rx
          const int ly = it / (TX / R);
          const int rx = it - ly * (TX / R);
-         base = s_v + (ly + H) * T::SP + (H + rx * R); // first cell of the run
+         base = s_vt + (ly + H) * T::SP + (H + rx * R); // first cell of the run
          stride = 1;
          oidx = ly * T::XP + (rx + 1) * R;
          ostride = 1;
@@ -236,7 +266,7 @@ __global__ void __launch_bounds__(NT) fv2d_stage_kernel(const Fv2dGeom g, const 
          const int q = it - NXR;
          const int ry = q / TX;
          const int lx = q - ry * TX;
-         base = s_v + (H + ry * R) * T::SP + (lx + H);
+         base = s_vt + (H + ry * R) * T::SP + (lx + H);
          stride = T::SP;
          oidx = ((ry + 1) * R) * TX + lx;
          ostride = TX;
@@ -265,13 +295,13 @@ __global__ void __launch_bounds__(NT) fv2d_stage_kernel(const Fv2dGeom g, const 
       double *dst;
       if (q < TY) { // x1 line q
          const int cx = high ? TX : -1;
-         base = s_v + (q + H) * T::SP + (H + cx);
+         base = s_vt + (q + H) * T::SP + (H + cx);
          stride = 1;
          dst = (high ? s_vlx : s_vrx) + q * T::XP + R + cx;
       } else { // x2 line
          const int lx = q - TY;
          const int cy = high ? TY : -1;
-         base = s_v + (H + cy) * T::SP + (lx + H);
+         base = s_vt + (H + cy) * T::SP + (lx + H);
          stride = T::SP;
          dst = (high ? s_vly : s_vry) + (cy + R) * TX + lx;
       }
@@ -290,10 +320,11 @@ __global__ void __launch_bounds__(NT) fv2d_stage_kernel(const Fv2dGeom g, const 
       const int ryi = it / TX;
       const int lx = it - ryi * TX;
       if (interior)
-         fv2d_phase_b<K, COMBINE, M, UPW, TX, TY, true>(g, s, s_v, s_vlx, s_vrx, s_vly, s_vry, x0, y0, lx, ryi * R);
+         fv2d_phase_b<K, COMBINE, M, UPW, TX, TY, true>(g, s, s_vt, s_vlx, s_vrx, s_vly, s_vry, x0, y0, lx, ryi * R);
       else
-         fv2d_phase_b<K, COMBINE, M, UPW, TX, TY, false>(g, s, s_v, s_vlx, s_vrx, s_vly, s_vry, x0, y0, lx, ryi * R);
+         fv2d_phase_b<K, COMBINE, M, UPW, TX, TY, false>(g, s, s_vt, s_vlx, s_vrx, s_vly, s_vry, x0, y0, lx, ryi * R);
    }
+   } // tile loop
 }
 
 constexpr int TX2 = 64, TY2 = 32, NT2 = 256;
@@ -307,8 +338,17 @@ static int launch2d_u(const Fv2dGeom &g, const StageArgs &a, cudaStream_t st) {
       HRW_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)T::BYTES));
       configured = true;
    }
-   dim3 grid((unsigned)g.tiles_x, (unsigned)g.tiles_y);
-   kern<<<grid, NT2, T::BYTES, st>>>(g, a);
+   // persistent grid: SMs x resident CTAs of this instantiation, never more than there are tiles
+   static int resident = 0;
+   if (resident == 0) {
+      int dev = 0, sms = 0, per_sm = 0;
+      cudaGetDevice(&dev);
+      cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+      cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, NT2, T::BYTES);
+      resident = (sms > 0 ? sms : 148) * (per_sm > 0 ? per_sm : 1);
+   }
+   const int64_t tiles = (int64_t)g.tiles_x * g.tiles_y;
+   kern<<<(unsigned)(tiles < resident ? tiles : resident), NT2, T::BYTES, st>>>(g, a);
    HRW_CUDA(cudaGetLastError());
    return HRWENO_OK;
 }
@@ -356,7 +396,7 @@ int fv2d_stage(Fv *fv, int combine, const StageArgs &args, cudaStream_t st) {
    g.bc = d.bc;
    g.phys_lo = d.rank == 0;
    g.phys_hi = d.rank == d.nranks - 1;
-   if (g.tiles_y > 65535) return fail(HRWENO_EINVAL, "2D grid too tall for one launch");
+   if ((int64_t)g.tiles_x * g.tiles_y > 2000000000LL) return fail(HRWENO_EINVAL, "2D grid too large for one launch");
    if (d.mode == HRWENO_MODE_STRICT) return launch2d_k<Strict>(d.k, combine, g, args, st);
    return launch2d_k<Fast>(d.k, combine, g, args, st);
 }
