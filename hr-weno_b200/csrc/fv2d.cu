@@ -21,6 +21,7 @@ struct Fv2dGeom {
    int64_t n0, n1;   // cells along x1 (contiguous) and x2 (local slab)
    int64_t pitch;    // padded row pitch
    int tiles_x, tiles_y;
+   int small_tiles;  // 32x16 tiles instead of 64x32
    const double *w1, *w2;   // widths (device, padded)
    const double *rw1, *rw2; // their refined reciprocals (exact_recip)
    WenoK kc;
@@ -327,10 +328,11 @@ __global__ void __launch_bounds__(NT) fv2d_stage_kernel(const Fv2dGeom g, const 
    } // tile loop
 }
 
-constexpr int TX2 = 64, TY2 = 32, NT2 = 256;
+constexpr int TX2 = 64, TY2 = 32, NT2 = 256;   // large grids
+constexpr int TX2S = 32, TY2S = 16, NT2S = 128; // small grids (e.g. example2's 250x250): enough tiles to occupy every SM
 
-template <int K, int COMBINE, class M, int UPW>
-static int launch2d_u(const Fv2dGeom &g, const StageArgs &a, cudaStream_t st) {
+template <int K, int COMBINE, class M, int UPW, int TX2, int TY2, int NT2>
+static int launch2d_t(const Fv2dGeom &g, const StageArgs &a, cudaStream_t st) {
    using T = Tile2d<TX2, TY2, UPW>;
    auto kern = fv2d_stage_kernel<K, COMBINE, M, UPW, TX2, TY2, NT2>;
    static bool configured = false; // one flag per instantiation
@@ -351,6 +353,12 @@ static int launch2d_u(const Fv2dGeom &g, const StageArgs &a, cudaStream_t st) {
    kern<<<(unsigned)(tiles < resident ? tiles : resident), NT2, T::BYTES, st>>>(g, a);
    HRW_CUDA(cudaGetLastError());
    return HRWENO_OK;
+}
+
+template <int K, int COMBINE, class M, int UPW>
+static int launch2d_u(const Fv2dGeom &g, const StageArgs &a, cudaStream_t st) {
+   if (g.small_tiles) return launch2d_t<K, COMBINE, M, UPW, TX2S, TY2S, NT2S>(g, a, st);
+   return launch2d_t<K, COMBINE, M, UPW, TX2, TY2, NT2>(g, a, st);
 }
 
 template <int K, int COMBINE, class M>
@@ -386,6 +394,11 @@ int fv2d_stage(Fv *fv, int combine, const StageArgs &args, cudaStream_t st) {
    g.pitch = fv->pitch;
    g.tiles_x = (int)((fv->n0 + TX2 - 1) / TX2);
    g.tiles_y = (int)((fv->n1 + TY2 - 1) / TY2);
+   g.small_tiles = (int64_t)g.tiles_x * g.tiles_y < 2 * 148; // fewer large tiles than two per SM: use the small ones
+   if (g.small_tiles) {
+      g.tiles_x = (int)((fv->n0 + TX2S - 1) / TX2S);
+      g.tiles_y = (int)((fv->n1 + TY2S - 1) / TY2S);
+   }
    g.w1 = fv->d_width[0];
    g.w2 = fv->d_width[1];
    g.rw1 = fv->d_rwidth[0];
