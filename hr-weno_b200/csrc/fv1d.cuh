@@ -281,6 +281,9 @@ __global__ void __launch_bounds__(NT, HRW_MINB) fv1d_stage_kernel(const Fv1dGeom
    __shared__ __align__(16) double2 s_wtab[WK == WK_DICT ? 256 : 1];
    __shared__ __align__(8) unsigned long long s_bar[2];
 
+   // let the next kernel of the stream be scheduled as soon as SM resources free up (it waits for this grid to
+   // complete before reading or writing global data, see griddepcontrol.wait below)
+   asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
    const int tid = threadIdx.x;
    const int n = (int)g.n;                     // cells per row (< 2^31, validated at creation)
    const int tpr = (int)g.tiles_per_row;
@@ -319,6 +322,9 @@ __global__ void __launch_bounds__(NT, HRW_MINB) fv1d_stage_kernel(const Fv1dGeom
 
    // tiles are walked as (row, tile-in-row) pairs advanced by gridDim.x without any division in the loop
    const int step_rows = (int)(gridDim.x / (unsigned)tpr), step_cols = (int)(gridDim.x % (unsigned)tpr);
+   // everything above touched only shared memory and creation-time constants; from here on this grid reads and writes
+   // state vectors produced by earlier kernels of the stream
+   asm volatile("griddepcontrol.wait;" ::: "memory");
    int lin = g.tile_begin + (int)blockIdx.x; // linear tile id; this launch owns [tile_begin, tile_end)
    int row = lin / tpr, tcol = lin % tpr;
    // slabs: the two edge tiles are walked first (logical tile 1 <-> last tile), so the boundary cells reach the

@@ -34,8 +34,19 @@ static int launch(const Fv1dGeom &g, const StageArgs &a, cudaStream_t st) {
    int64_t blocks = g.tile_end - g.tile_begin;
    if (blocks > resident) blocks = resident;
    if (blocks < 1) return HRWENO_OK;
-   kern<<<(unsigned)blocks, NT, 0, st>>>(g, a);
-   HRW_CUDA(cudaGetLastError());
+   // programmatic dependent launch: this grid may be scheduled while the previous kernel of the stream drains; the kernel
+   // itself waits (griddepcontrol.wait) before it touches anything an earlier kernel wrote
+   cudaLaunchConfig_t cfg = {};
+   cfg.gridDim = dim3((unsigned)blocks);
+   cfg.blockDim = dim3(NT);
+   cfg.dynamicSmemBytes = 0;
+   cfg.stream = st;
+   cudaLaunchAttribute attr[1];
+   attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+   attr[0].val.programmaticStreamSerializationAllowed = 1;
+   cfg.attrs = attr;
+   cfg.numAttrs = 1;
+   HRW_CUDA(cudaLaunchKernelEx(&cfg, kern, g, a));
    return HRWENO_OK;
 }
 

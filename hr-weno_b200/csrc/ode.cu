@@ -339,7 +339,10 @@ static int rk_integrate_pipelined(Ode *o, double *u, double *t, double tout, dou
                                // 7.2 M cells per chunk measured best on B200 (profiles/r1_variant_sweeps.txt)
    if (const char *e = std::getenv("HRWENO_PIPE_CHUNK_TILES")) chunk_tiles = std::atoi(e);
    if (chunk_tiles < 1) return HRWENO_OK; // pipeline disabled
-   const int C = (tpr + chunk_tiles - 1) / chunk_tiles;
+   // chunk c covers tiles [cb[c], cb[c+1])  (smaller first chunks to shorten the ramp were tried: no measurable gain)
+   std::vector<int> cb(1, 0);
+   while (cb.back() < tpr) cb.push_back(std::min(tpr, cb.back() + chunk_tiles));
+   const int C = (int)cb.size() - 1;
    if (C < 4) return HRWENO_OK;
    // number of steps this call takes (tvdode.f90:161-171: step, then test)
    int64_t nsteps = 0;
@@ -364,9 +367,8 @@ static int rk_integrate_pipelined(Ode *o, double *u, double *t, double tout, dou
    }
    double *B[3] = {fv->cell0(o->bufs[0]), fv->cell0(o->bufs[1]), fv->cell0(o->bufs[2])}; // U, T1, T2 at cell 0
    const int k = fv->d.k;
-   const int64_t chunk_cells = (int64_t)chunk_tiles * tile;
-   auto c_lo = [&](int c) { return (int64_t)c * chunk_cells; };
-   auto c_hi = [&](int c) { return std::min<int64_t>(n, (int64_t)(c + 1) * chunk_cells); };
+   auto c_lo = [&](int c) { return (int64_t)cb[c] * tile; };
+   auto c_hi = [&](int c) { return std::min<int64_t>(n, (int64_t)cb[c + 1] * tile); };
    cudaStream_t cs = o->stream;
    // host -> device, chunk by chunk, straight into the padded state (one row: dense offset == padded offset)
    for (int c = 0; c < C; ++c) {
@@ -395,8 +397,8 @@ static int rk_integrate_pipelined(Ode *o, double *u, double *t, double tout, dou
          const int j = (int)(g - step * order);
          StageArgs a{};
          a.ld_out = fv->pitch;
-         a.tile_begin = c * chunk_tiles;
-         a.tile_end = std::min(tpr, (c + 1) * chunk_tiles);
+         a.tile_begin = cb[c];
+         a.tile_end = cb[c + 1];
          int combine;
          if (order == 1) {
             combine = C_EULER;
