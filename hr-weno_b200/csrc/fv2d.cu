@@ -203,6 +203,7 @@ __global__ void __launch_bounds__(NT) fv2d_stage_kernel(const Fv2dGeom g, const 
    double *s_vly = smem + T::OFF_VLY, *s_vry = smem + T::OFF_VRY;
 
    __shared__ __align__(8) unsigned long long s_bar[2];
+   asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); // the next kernel may be scheduled as SMs free up
    const int tid = threadIdx.x;
    const int total_tiles = g.tiles_x * g.tiles_y;
 
@@ -233,6 +234,7 @@ __global__ void __launch_bounds__(NT) fv2d_stage_kernel(const Fv2dGeom g, const 
       asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
    }
    __syncthreads();
+   asm volatile("griddepcontrol.wait;" ::: "memory"); // state vectors written by earlier kernels are complete from here on
    if (tid < 32 && (int)blockIdx.x < total_tiles) issue(blockIdx.x, 0);
 
    int it_n = 0;
@@ -350,8 +352,18 @@ static int launch2d_t(const Fv2dGeom &g, const StageArgs &a, cudaStream_t st) {
       resident = (sms > 0 ? sms : 148) * (per_sm > 0 ? per_sm : 1);
    }
    const int64_t tiles = (int64_t)g.tiles_x * g.tiles_y;
-   kern<<<(unsigned)(tiles < resident ? tiles : resident), NT2, T::BYTES, st>>>(g, a);
-   HRW_CUDA(cudaGetLastError());
+   // programmatic dependent launch, as for the 1D kernel (fv1d_inst.cu)
+   cudaLaunchConfig_t cfg = {};
+   cfg.gridDim = dim3((unsigned)(tiles < resident ? tiles : resident));
+   cfg.blockDim = dim3(NT2);
+   cfg.dynamicSmemBytes = T::BYTES;
+   cfg.stream = st;
+   cudaLaunchAttribute attr[1];
+   attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+   attr[0].val.programmaticStreamSerializationAllowed = 1;
+   cfg.attrs = attr;
+   cfg.numAttrs = 1;
+   HRW_CUDA(cudaLaunchKernelEx(&cfg, kern, g, a));
    return HRWENO_OK;
 }
 
