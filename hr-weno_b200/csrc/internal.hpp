@@ -103,6 +103,9 @@ int fv_unpack(Fv *fv, const double *padded_cell0, double *dense_dev, cudaStream_
 int fv_stage(Fv *fv, int combine, const StageArgs &args, cudaStream_t st);
 // 1D tiling of the current configuration: cells per tile and tiles per row
 void fv_tiling_1d(const Fv *fv, int *tile_cells, int *tiles_per_row);
+// fv1d_small.cu: whole integrate call of a small 1D problem (<= 1024 cells) in one single-CTA launch
+bool fv_small_eligible(const Fv *fv);
+int fv_small_integrate(Fv *fv, double *u_dev, int order, long long nsteps, double dt, cudaStream_t st);
 struct Fv1dGeom;
 // fv1d_inst.cu, compiled once per (k, mode): launches the 1D stage kernel specialised for (combine, flux kind, width kind)
 int fv1d_launch(int k, int mode, int combine, int flux_kind, int width_kind, int half_tile, const Fv1dGeom &g, const StageArgs &a,

@@ -194,6 +194,21 @@ static int rk_step_cb(Ode *o, int order, double t, double *u, double *ui, double
 static int rk_integrate(Ode *o, double *u_dev, double *t, double tout, double dt, int itask, cudaStream_t st) {
    if (o->istate < 1) return HRWENO_OK;          // :126
    if (is_done(*t, tout, dt)) return HRWENO_OK;   // :127
+   if (o->fused && fv_small_eligible(o->fv)) {
+      // small problem: count the steps exactly as the loop below would take them, then one single-CTA launch
+      long long nsteps = 0;
+      double tt = *t;
+      for (;;) {
+         tt = tt + dt;
+         ++nsteps;
+         if (is_done(tt, tout, dt) || itask == 2) break;
+      }
+      HRW_TRY(fv_small_integrate(o->fv, u_dev, o->order, nsteps, dt, st));
+      *t = tt;
+      o->fevals += (int64_t)o->order * nsteps;
+      if (o->istate == 1) o->istate = 2;
+      return HRWENO_OK;
+   }
    if (o->fused) {
       Fv *fv = o->fv;
       double *U = o->bufs[0], *T1 = o->bufs[1], *T2 = o->bufs[2];

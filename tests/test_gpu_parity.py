@@ -396,3 +396,22 @@ def test_host_integrate_chunk_pipeline_bitwise(gpu_lib, pkg, ref, order, monkeyp
         t, tr = ode.integrate(u, t, 1e9, dt, itask=2), rode.integrate(ur, tr, 1e9, dt, itask=2)
         assert t == tr and np.array_equal(u, ur) and ode.fevals == rode.fevals
         assert ode.launches - launches0 > 8 * order * 20  # one launch per (chunk, stage): the pipeline was taken
+
+
+@pytest.mark.parametrize("order", [1, 2, 3])
+@pytest.mark.parametrize("k", [2, 3])
+def test_rktvd_fused_tiled_path_bitwise(gpu_lib, pkg, ref, k, order):
+    """more than 1024 cells: the tiled persistent kernel (the <=1024-cell case takes the single-launch kernel)"""
+    nc = 2500
+    g = pkg.hrweno_grids.grid1().linear(-5.0, 5.0, nc)
+    rng = np.random.default_rng(k * 10 + order)
+    u0 = ex1_ic(g.center) + 1e-3 * rng.standard_normal(nc)
+    kw = dict(n=nc, k=k, width=[g.width])
+    ode = pkg.hrweno_tvdode.rktvd(pkg.fv.FV(pkg.fv.make_desc(**kw)), nc, order)
+    rode = ref.rktvd(ref.FV(pkg.fv.make_desc(**kw)), order)
+    u, ur, t, tr = u0.copy(), u0.copy(), 0.0, 0.0
+    for tout in (0.0, 0.01, 0.03):
+        t = ode.integrate(u, t, tout, 5e-4)
+        tr = rode.integrate(ur, tr, tout, 5e-4)
+        assert t == tr and np.array_equal(u, ur)
+    assert ode.fevals == rode.fevals
