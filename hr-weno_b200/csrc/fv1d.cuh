@@ -190,11 +190,11 @@ __device__ __forceinline__ void fv1d_finish(const Fv1dGeom &g, const StageArgs &
       double o;
       constexpr bool FOLD = !M::strict && WK == WK_DICT && (COMBINE == C_EULER || COMBINE == C_RK2_FINAL || COMBINE == C_RK3_S2 || COMBINE == C_RK3_S3);
       if constexpr (FOLD) {
-         // wr already carries the stage coefficient: q == dt*L
-         if constexpr (COMBINE == C_EULER) o = v + q;
-         if constexpr (COMBINE == C_RK2_FINAL) o = ((av[j] + v) + q) * 0.5;
-         if constexpr (COMBINE == C_RK3_S2) o = (fma(3.0, av[j], v) + q) * 0.25;
-         if constexpr (COMBINE == C_RK3_S3) o = div3<M>(fma(2.0, v, av[j]) + q);
+         // wr already carries the stage coefficient (dF*wr == dt*L), so the product rides in the combination's FMA
+         if constexpr (COMBINE == C_EULER) o = fma(dF, wr[j], v);
+         if constexpr (COMBINE == C_RK2_FINAL) o = fma(dF, wr[j], av[j] + v) * 0.5;
+         if constexpr (COMBINE == C_RK3_S2) o = fma(0.75, av[j], 0.25 * fma(dF, wr[j], v));
+         if constexpr (COMBINE == C_RK3_S3) o = div3<M>(fma(dF, wr[j], fma(2.0, v, av[j])));
       } else if constexpr (COMBINE == C_RHS) {
          o = M::mul(lscale, q);
       } else if constexpr (COMBINE == C_EULER) {

@@ -6,9 +6,10 @@
 //   phase A: reconstruction along x1 for every tile row and along x2 for every tile column.  Work items
 //            are runs of R=4 consecutive cells of a line (row or column) -- the same register-window
 //            routine as the 1D kernel, addressed by (base, stride) so x1- and x2-items share one code
-//            path and one item list.  Each line gets one extra run at either end (tile overlap) so the
-//            faces on the tile edge see vr / vl of the neighbouring tile's cells without recomputation
-//            inside the tile.
+//            path.  The faces on the tile edge need vr / vl of the neighbouring tile's cells: single-cell
+//            "halo items".  x1-results go to shared memory (the consumer is a different thread); an
+//            x2-item (column lx, run ry) is owned by the thread that later does phase B for the same
+//            cells, so its vl / vr stay in registers and only the run-end values are exchanged.
 //   phase B: thread = (x, run of R cells along x2): Godunov / Lax-Friedrichs flux at the x1- and x2-faces,
 //            boundary constraints (example2:117-120), vdot = -(df1)/w1 - (df2)/w2 (example2:123-127),
 //            stage combination, coalesced stores along x1.
@@ -36,18 +37,18 @@ struct Tile2d {
    static constexpr int SP = TX + 2 * H;         // tile pitch
    static constexpr int SROWS = TY + 2 * H;
    static constexpr int XP = TX + 2 * R;         // pitch of the x1-sweep vl/vr arrays (cells x0-R .. x0+TX+R-1)
-   static constexpr int YROWS = TY + 2 * R;      // rows of the x2-sweep vl/vr arrays
-   static constexpr int RUNS_X = TX / R + 2, NRX = RUNS_X * TY;
-   static constexpr int RUNS_Y = TY / R + 2, NRY = RUNS_Y * TX;
+   static constexpr int RY = TY / R;             // x2-runs per column
    // two staged-tile buffers: the next tile is fetched by TMA row copies while this one is being computed
    static constexpr int OFF_V = 0;
    static constexpr int TILE_DOUBLES = SROWS * SP;
    static constexpr int OFF_VLX = OFF_V + 2 * TILE_DOUBLES;
    // upwind specialisation: the left-side arrays are never touched and get no storage (more CTAs per SM)
    static constexpr int OFF_VRX = OFF_VLX + (UPW ? 0 : TY * XP);
-   static constexpr int OFF_VLY = OFF_VRX + TY * XP;
-   static constexpr int OFF_VRY = OFF_VLY + (UPW ? 0 : YROWS * TX);
-   static constexpr int TOTAL = OFF_VRY + YROWS * TX;
+   // x2-sweep exchange: vr of the cell below each run (slot 0: the cell below the tile) and vl of the cell above it
+   // (slot RY: the cell above the tile); slot s of column lx at [s * TX + lx]
+   static constexpr int OFF_VRE = OFF_VRX + TY * XP;
+   static constexpr int OFF_VLE = OFF_VRE + (RY + 1) * TX;
+   static constexpr int TOTAL = OFF_VLE + (UPW ? 0 : (RY + 1) * TX);
    static constexpr size_t BYTES = (size_t)TOTAL * sizeof(double);
 };
 
@@ -67,8 +68,8 @@ __device__ __forceinline__ double face2d(const FluxCfg &c, double vm, double vp)
 // phase B for one thread = (column lx, run of R rows).  INTERIOR: the tile touches no domain edge and is complete.
 template <int K, int COMBINE, class M, int UPW, int TX, int TY, bool INTERIOR>
 __device__ __forceinline__ void fv2d_phase_b(const Fv2dGeom &g, const StageArgs &s, const double *s_v, const double *s_vlx,
-                                             const double *s_vrx, const double *s_vly, const double *s_vry, int64_t x0, int64_t y0,
-                                             int lx, int ly0) {
+                                             const double *s_vrx, const double *vmY /* vr below face j, j = 0..R */,
+                                             const double *vpY /* vl above face j */, int64_t x0, int64_t y0, int lx, int ly0) {
    using T = Tile2d<TX, TY, UPW>;
    constexpr int R = T::R, H = T::H;
    const int64_t gx = x0 + lx, gy0 = y0 + ly0;
@@ -76,14 +77,10 @@ __device__ __forceinline__ void fv2d_phase_b(const Fv2dGeom &g, const StageArgs 
       if (gx >= g.n0 || gy0 >= g.n1) return;
    }
    const bool copy = g.bc == HRWENO_BC_COPY_NEIGHBOUR;
-   // x2-faces gy0 .. gy0+R of column gx: face f lies between rows f-1 and f; array row index = local row + R
+   // x2-faces gy0 .. gy0+R of column gx: face f lies between rows f-1 and f
    double F2[R + 1];
 #pragma unroll
-   for (int j = 0; j <= R; ++j) {
-      const double vm = s_vry[(ly0 + j - 1 + R) * TX + lx];
-      const double vp = UPW ? 0.0 : s_vly[(ly0 + j + R) * TX + lx];
-      F2[j] = face2d<UPW, M>(g.flux2, vm, vp);
-   }
+   for (int j = 0; j <= R; ++j) F2[j] = face2d<UPW, M>(g.flux2, vmY[j], UPW ? 0.0 : vpY[j]);
    if constexpr (!INTERIOR) {
       if (g.phys_lo && gy0 == 0) F2[0] = copy ? F2[1] : 0.0;
       if (g.phys_hi) {
@@ -193,14 +190,20 @@ __device__ __forceinline__ void fv2d_phase_b(const Fv2dGeom &g, const StageArgs 
    }
 }
 
+// resident CTAs per SM the registers are capped for: 3 tiles of the upwind fast variant fit in shared memory, 2 otherwise
+template <class M, int UPW, int NT>
+constexpr int fv2d_min_blocks() {
+   return ((UPW && !M::strict) ? 3 : 2) * (256 / NT);
+}
+
 template <int K, int COMBINE, class M, int UPW, int TX, int TY, int NT>
-__global__ void __launch_bounds__(NT) fv2d_stage_kernel(const Fv2dGeom g, const StageArgs s) {
+__global__ void __launch_bounds__(NT, fv2d_min_blocks<M, UPW, NT>()) fv2d_stage_kernel(const Fv2dGeom g, const StageArgs s) {
    using T = Tile2d<TX, TY, UPW>;
    constexpr int R = T::R, H = T::H;
    extern __shared__ __align__(16) double smem[];
    double *s_v = smem + T::OFF_V;
    double *s_vlx = smem + T::OFF_VLX, *s_vrx = smem + T::OFF_VRX;
-   double *s_vly = smem + T::OFF_VLY, *s_vry = smem + T::OFF_VRY;
+   double *s_vre = smem + T::OFF_VRE, *s_vle = smem + T::OFF_VLE;
 
    __shared__ __align__(8) unsigned long long s_bar[2];
    asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); // the next kernel may be scheduled as SMs free up
@@ -250,45 +253,28 @@ __global__ void __launch_bounds__(NT) fv2d_stage_kernel(const Fv2dGeom g, const 
    mbar_wait(&s_bar[buf], (uint32_t)((it_n >> 1) & 1));
 
    // ---- phase A: reconstruction items ------------------------------------------------------------------
-   // regular items: runs of R cells inside the tile, x1-lines first, then x2-lines (one code path, (base, stride) addressing)
+   // x1-sweep: runs of R cells of a tile row -> shared memory (phase B reads them from other threads)
    constexpr int NXR = (TX / R) * TY, NYR = TX * (TY / R);
-   for (int it = tid; it < NXR + NYR; it += NT) {
-      const double *base;
-      int stride, oidx, ostride;
-      double *ovl, *ovr;
-      if (it < NXR) { // x1-sweep: row ly, run rx
-         const int ly = it / (TX / R);
-         const int rx = it - ly * (TX / R);
-         base = s_vt + (ly + H) * T::SP + (H + rx * R); // first cell of the run
-         stride = 1;
-         oidx = ly * T::XP + (rx + 1) * R;
-         ostride = 1;
-         ovl = s_vlx;
-         ovr = s_vrx;
-      } else { // x2-sweep: column lx, run ry
-         const int q = it - NXR;
-         const int ry = q / TX;
-         const int lx = q - ry * TX;
-         base = s_vt + (H + ry * R) * T::SP + (lx + H);
-         stride = T::SP;
-         oidx = ((ry + 1) * R) * TX + lx;
-         ostride = TX;
-         ovl = s_vly;
-         ovr = s_vry;
-      }
+   constexpr int YI = NYR / NT; // x2-items (= phase-B items) per thread
+   static_assert(NYR % NT == 0, "every thread owns the same number of x2-runs");
+   for (int it = tid; it < NXR; it += NT) {
+      const int ly = it / (TX / R);
+      const int rx = it - ly * (TX / R);
+      const double *base = s_vt + (ly + H) * T::SP + (H + rx * R); // first cell of the run
+      const int oidx = ly * T::XP + (rx + 1) * R;
       double w[R + 4];
 #pragma unroll
-      for (int j = 0; j < R + 4; ++j) w[j] = base[(j - 2) * stride];
+      for (int j = 0; j < R + 4; ++j) w[j] = base[j - 2];
       double vl[R], vr[R];
       weno_run<K, R, M>(w + (2 - (K - 1)), g.kc, vl, vr);
 #pragma unroll
       for (int j = 0; j < R; ++j) {
-         if constexpr (!UPW) ovl[oidx + j * ostride] = vl[j]; // upwind: the left side is never used and is eliminated
-         ovr[oidx + j * ostride] = vr[j];
+         if constexpr (!UPW) s_vlx[oidx + j] = vl[j]; // upwind: the left side is never used and is eliminated
+         s_vrx[oidx + j] = vr[j];
       }
    }
    // halo items: the faces on the tile edge need vr of the cell just below/left of the tile and (unless upwind) vl of the
-   // cell just above/right of it: single-cell reconstructions, grouped after the regular items so that whole warps take them
+   // cell just above/right of it: single-cell reconstructions, grouped so that whole warps take them
    constexpr int NHALO = UPW ? (TY + TX) : 2 * (TY + TX);
    for (int it = tid; it < NHALO; it += NT) {
       const bool high = it >= TY + TX; // high side: vl of cell index T (only when !UPW)
@@ -306,7 +292,7 @@ __global__ void __launch_bounds__(NT) fv2d_stage_kernel(const Fv2dGeom g, const 
          const int cy = high ? TY : -1;
          base = s_vt + (H + cy) * T::SP + (lx + H);
          stride = T::SP;
-         dst = (high ? s_vly : s_vry) + (cy + R) * TX + lx;
+         dst = high ? s_vle + T::RY * TX + lx : s_vre + lx;
       }
       double w[5];
 #pragma unroll
@@ -315,17 +301,43 @@ __global__ void __launch_bounds__(NT) fv2d_stage_kernel(const Fv2dGeom g, const 
       weno_run<K, 1, M>(w + (2 - (K - 1)), g.kc, vl1, vr1);
       *dst = high ? vl1[0] : vr1[0];
    }
+   // x2-sweep: item (column lx, run ry) is also this thread's phase-B item, so vl / vr stay in registers; the values the
+   // neighbouring run needs (vr of its cell below, vl of its cell above) go through the exchange arrays
+   double vlY[YI][R], vrY[YI][R];
+#pragma unroll
+   for (int q = 0; q < YI; ++q) {
+      const int it = tid + q * NT;
+      const int ry = it / TX;
+      const int lx = it - ry * TX;
+      const double *base = s_vt + (H + ry * R) * T::SP + (lx + H);
+      double w[R + 4];
+#pragma unroll
+      for (int j = 0; j < R + 4; ++j) w[j] = base[(j - 2) * T::SP];
+      weno_run<K, R, M>(w + (2 - (K - 1)), g.kc, vlY[q], vrY[q]);
+      s_vre[(ry + 1) * TX + lx] = vrY[q][R - 1];
+      if constexpr (!UPW) s_vle[ry * TX + lx] = vlY[q][0];
+   }
    __syncthreads();
 
    // ---- phase B: fluxes, divergence, combination ---------------------------------------------------------
    const bool interior = !s.out_dense && x0 > 0 && x0 + TX < g.n0 && y0 > 0 && y0 + TY < g.n1;
-   for (int it = tid; it < TX * (TY / R); it += NT) {
-      const int ryi = it / TX;
-      const int lx = it - ryi * TX;
+#pragma unroll
+   for (int q = 0; q < YI; ++q) {
+      const int it = tid + q * NT;
+      const int ry = it / TX;
+      const int lx = it - ry * TX;
+      double vmY[R + 1], vpY[R + 1];
+      vmY[0] = s_vre[ry * TX + lx];
+#pragma unroll
+      for (int j = 0; j < R; ++j) {
+         vmY[j + 1] = vrY[q][j];
+         vpY[j] = UPW ? 0.0 : vlY[q][j];
+      }
+      vpY[R] = UPW ? 0.0 : s_vle[(ry + 1) * TX + lx];
       if (interior)
-         fv2d_phase_b<K, COMBINE, M, UPW, TX, TY, true>(g, s, s_vt, s_vlx, s_vrx, s_vly, s_vry, x0, y0, lx, ryi * R);
+         fv2d_phase_b<K, COMBINE, M, UPW, TX, TY, true>(g, s, s_vt, s_vlx, s_vrx, vmY, vpY, x0, y0, lx, ry * R);
       else
-         fv2d_phase_b<K, COMBINE, M, UPW, TX, TY, false>(g, s, s_vt, s_vlx, s_vrx, s_vly, s_vry, x0, y0, lx, ryi * R);
+         fv2d_phase_b<K, COMBINE, M, UPW, TX, TY, false>(g, s, s_vt, s_vlx, s_vrx, vmY, vpY, x0, y0, lx, ry * R);
    }
    } // tile loop
 }

@@ -201,55 +201,86 @@ __device__ __forceinline__ void weno_run_k3(const double *w, const WenoK &kc, do
 }
 
 // ------------------------------------------------------------------------------------ k = 3, fast mode
-// Same scheme, fewest fp64 instructions (the kernel is bound by instruction issue): FMA chains for the
-// candidates; smoothness indicators scaled by 4 (beta' = 4*beta, eps' = 4*eps: every weight ratio is unchanged)
-// so that beta' = b*b + (13/3)*d2*d2 is one FMA per indicator; weights in the division-light form
-//   alfa_r ~ d_r * prod_{s != r} (eps+beta_s)^2   with d = (3,6,1)/10 and the common 1/10 dropped,
-// one reciprocal per side (MUFU seed + one cubic step).  Not bit-identical to the reference order: parity is
-// the north-star tolerance (1e-12 normwise per output time, a few ULP per reconstruction).
+// Same scheme, fewest fp64 instructions (the kernel is bound by instruction issue).
+// Everything is written in differences of the cell averages, d1[j] = v[j+1] - v[j], d2[j] = d1[j] - d1[j-1],
+// D3[j] = d2[j+1] - d2[j] (each one instruction, shared by neighbouring cells):
+//   * smoothness indicators scaled by 4 (beta' = 4*beta, eps' = 4*eps leaves every weight ratio unchanged):
+//       beta'_0 = (d1[c+1] - 3 d1[c])^2 + (13/3) d2[c+1]^2,   beta'_1 = (d1[c-1] + d1[c])^2 + (13/3) d2[c]^2,
+//       beta'_2 = (d1[c-2] - 3 d1[c-1])^2 + (13/3) d2[c-1]^2                                    (weno.f90:195-202)
+//   * the three candidates of a side differ by multiples of a third difference (c3, weno.f90:19-21):
+//       vrr1 = v[c] + (d1[c-1] + 2 d1[c])/6,   vrr0 = vrr1 - D3[c]/6,   vrr2 = vrr1 - D3[c-1]/3,
+//       vlr1 = vrr0 of cell c-1,   vlr2 = vlr1 + D3[c-1]/6,   vlr0 = vlr1 + D3[c]/3
+//   * division-light weights alfa_r ~ d_r * P_r with P_r = prod_{s != r} (eps'+beta'_s)^2, d = (3,6,1)/10
+//     (weno.f90:207-214), so the convex combination is the central candidate plus a weighted sum of two third
+//     differences, one reciprocal per side (MUFU seed + one cubic step):
+//       vr = vrr1 - (1.5 X + Y)/(9 P0 + 18 P1 + 3 P2),   vl = vlr1 + (X + 1.5 Y)/(3 P0 + 18 P1 + 9 P2),
+//       X = P0*D3[c],  Y = P2*D3[c-1].
+// Not bit-identical to the reference order (and less cancellation than it): parity is the north-star tolerance
+// (1e-12 normwise per output time, a few ULP per reconstruction; oracle/np_oracle.py: reconstruct_fast restates it).
 template <int R>
 __device__ __forceinline__ void weno_run_k3_fast(const double *w, const WenoK &kc, double *vl, double *vr) {
    constexpr int N = R + 4;
-   const double C13 = kc.c13, C56 = kc.c56, C16 = kc.c16m;
+   const double C13 = kc.c13, C16 = kc.c16;
    const double eps4 = kc.eps4;
-   // second differences d2[j] = v[j-1] - 2 v[j] + v[j+1]; m2e[j] = eps' + (13/3) d2^2; third differences D3[j] = d2[j+1] - d2[j]
-   double d2[N], m2e[N], D3[N];
+   double d1[N], d2[N], m2e[N], D3[N];
+#pragma unroll
+   for (int j = 0; j < N - 1; ++j) d1[j] = w[j + 1] - w[j];
 #pragma unroll
    for (int j = 1; j < N - 1; ++j) {
-      d2[j] = fma(-2.0, w[j], w[j - 1]) + w[j + 1];
+      d2[j] = d1[j] - d1[j - 1];
       m2e[j] = fma(kc.k133 * d2[j], d2[j], eps4);
    }
 #pragma unroll
    for (int j = 1; j < N - 2; ++j) D3[j] = d2[j + 1] - d2[j];
-   // the three candidates of a side differ by multiples of a third difference (Shu eq. 2.11 coefficients):
-   //   vrr1 = (-v[c-1] + 5 v[c] + 2 v[c+1])/6,  vrr0 = vrr1 - D3[c]/6,  vrr2 = vrr1 - D3[c-1]/3,
-   //   vlr1 = vrr0 of cell c-1,  vlr2 = vrr1 of cell c-1,  vlr0 = vlr1 + D3[c]/3
+   // V1[j] = vrr1 of the cell at window index j, V0[j] = its vrr0 (= vlr1 of cell j+1)
    double V1[N], V0[N];
 #pragma unroll
    for (int j = 1; j < R + 2; ++j) {
-      V1[j] = fma(C13, w[j + 1], fma(C56, w[j], C16 * w[j - 1]));
-      V0[j] = fma(C16, D3[j], V1[j]);
+      V1[j] = fma(C13, d1[j], fma(C16, d1[j - 1], w[j]));
+      V0[j] = fma(-C16, D3[j], V1[j]);
    }
 #pragma unroll
    for (int j = 0; j < R; ++j) {
       const int c = j + 2;
-      const double vrr0 = V0[c], vrr1 = V1[c];
-      const double vrr2 = fma(-C13, D3[c - 1], vrr1);
-      const double vlr1 = V0[c - 1], vlr2 = V1[c - 1];
-      const double vlr0 = fma(C13, D3[c], vlr1);
-      const double t3 = 3.0 * w[c];
-      const double b0 = fma(-4.0, w[c + 1], t3) + w[c + 2];
-      const double b1 = w[c - 1] - w[c + 1];
-      const double b2 = fma(-4.0, w[c - 1], w[c - 2]) + t3;
+      const double b0 = fma(-3.0, d1[c], d1[c + 1]);
+      const double b1 = d1[c - 1] + d1[c];
+      const double b2 = fma(-3.0, d1[c - 1], d1[c - 2]);
       const double e0 = fma(b0, b0, m2e[c + 1]);
       const double e1 = fma(b1, b1, m2e[c]);
       const double e2 = fma(b2, b2, m2e[c - 1]);
-      const double den0 = e0 * e0, den1 = e1 * e1, den2 = e2 * e2;
-      const double P0 = den1 * den2, P2 = den0 * den1;
-      const double Q1 = 6.0 * (den0 * den2), T0 = 3.0 * P0, T2 = 3.0 * P2;
-      const double s = (T0 + Q1) + P2, st = (P0 + Q1) + T2;
-      vr[j] = fma(P2, vrr2, fma(Q1, vrr1, T0 * vrr0)) * rcp3(s);
-      vl[j] = fma(T2, vlr2, fma(Q1, vlr1, P0 * vlr0)) * rcp3(st);
+      const double f0 = e1 * e2, f1 = e0 * e2, f2 = e0 * e1;
+      const double P0 = f0 * f0, P2 = f2 * f2;
+      const double Q = (18.0 * f1) * f1;
+      const double X = P0 * D3[c], Y = P2 * D3[c - 1];
+      const double A = fma(3.0, P0 + P2, Q);
+      const double sr = fma(6.0, P0, A), sl = fma(6.0, P2, A);
+      vr[j] = fma(-fma(1.5, X, Y), rcp3(sr), V1[c]);
+      vl[j] = fma(fma(1.5, Y, X), rcp3(sl), V0[c - 1]);
+   }
+}
+
+// ------------------------------------------------------------------------------------ k = 2, fast mode
+// Difference form of the third-order scheme (c2, d2 of weno.f90:13,17-18):
+//   vrr0 = v[c] + d1[c]/2,  vrr1 = vrr0 - d2[c]/2,  alfa ~ (2 den1, den0):  vr = vrr0 - (den0*d2[c]/2)/(2 den1 + den0)
+//   vlr1 = v[c] - d1[c-1]/2, vlr0 = vlr1 - d2[c]/2, alfat ~ (den1, 2 den0): vl = vlr1 - (den1*d2[c]/2)/(den1 + 2 den0)
+// with den0 = (eps + d1[c]^2)^2, den1 = (eps + d1[c-1]^2)^2 (weno.f90:190-191,207-214).
+template <int R>
+__device__ __forceinline__ void weno_run_k2_fast(const double *w, const WenoK &kc, double *vl, double *vr) {
+   constexpr int N = R + 2;
+   double d1[N], den[N];
+#pragma unroll
+   for (int j = 0; j < N - 1; ++j) {
+      d1[j] = w[j + 1] - w[j];
+      const double e = fma(d1[j], d1[j], kc.eps);
+      den[j] = e * e;
+   }
+#pragma unroll
+   for (int j = 0; j < R; ++j) {
+      const int c = j + 1;
+      const double h = 0.5 * (d1[c] - d1[c - 1]); // d2[c]/2
+      const double den0 = den[c], den1 = den[c - 1];
+      vr[j] = fma(-(den0 * h), rcp3(fma(2.0, den1, den0)), fma(0.5, d1[c], w[c]));
+      vl[j] = fma(-(den1 * h), rcp3(fma(2.0, den0, den1)), fma(-0.5, d1[c - 1], w[c]));
    }
 }
 
@@ -257,6 +288,8 @@ template <int K, int R, class M>
 __device__ __forceinline__ void weno_run(const double *w, const WenoK &kc, double *vl, double *vr) {
    if constexpr (K == 1)
       weno_run_k1<R, M>(w, kc, vl, vr);
+   else if constexpr (K == 2 && !M::strict)
+      weno_run_k2_fast<R>(w, kc, vl, vr);
    else if constexpr (K == 2)
       weno_run_k2<R, M>(w, kc, vl, vr);
    else if constexpr (!M::strict)

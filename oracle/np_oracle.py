@@ -233,3 +233,51 @@ class MS:
             self.uold = [u] + self.uold[:3]
             u = ui
         return u, t
+
+
+def reconstruct_fast(v, k=3, eps=1e-6):
+    """Algebra check of the FAST-mode device formulas (hr-weno_b200/csrc/weno_core.cuh: weno_run_k3_fast,
+    weno_run_k2_fast): the same scheme as `reconstruct` (weno.f90:174-216) rewritten in differences of the cell
+    averages with division-light weights.  Separately rounded NumPy operations stand in for the device FMAs, so
+    this agrees with the kernel to rounding, not bit for bit; tests hold it to a few ULP of `reconstruct`."""
+    v = np.asarray(v, dtype=np.float64)
+    nc = v.shape[-1]
+    if k == 1:
+        return v.copy(), v.copy()
+    g = k - 1
+    pad = [(0, 0)] * (v.ndim - 1) + [(g, g)]
+    vext = np.pad(v, pad, mode="edge")
+
+    def s(off):
+        return vext[..., g + off : g + off + nc]
+
+    def d1(off):  # v[c+off+1] - v[c+off]
+        return s(off + 1) - s(off)
+
+    if k == 2:
+        den0 = (eps + d1(0) ** 2) ** 2
+        den1 = (eps + d1(-1) ** 2) ** 2
+        h = 0.5 * (d1(0) - d1(-1))
+        vr = (s(0) + 0.5 * d1(0)) - (den0 * h) / (2 * den1 + den0)
+        vl = (s(0) - 0.5 * d1(-1)) - (den1 * h) / (2 * den0 + den1)
+        return vl, vr
+
+    def d2(off):
+        return d1(off) - d1(off - 1)
+
+    def d3(off):
+        return d2(off + 1) - d2(off)
+
+    eps4 = 4.0 * eps
+    e0 = (d1(1) - 3 * d1(0)) ** 2 + ((13.0 / 3) * d2(1) ** 2 + eps4)
+    e1 = (d1(-1) + d1(0)) ** 2 + ((13.0 / 3) * d2(0) ** 2 + eps4)
+    e2 = (d1(-2) - 3 * d1(-1)) ** 2 + ((13.0 / 3) * d2(-1) ** 2 + eps4)
+    p0, p1, p2 = (e1 * e2) ** 2, (e0 * e2) ** 2, (e0 * e1) ** 2
+    # the third differences that straddle the domain edge use replicated ghosts, as vext does
+    x, y = p0 * d3(0), p2 * d3(-1)
+    a = 3 * (p0 + p2) + 18 * p1
+    vrr1 = s(0) + (d1(-1) + 2 * d1(0)) / 6
+    vlr1 = s(0) - (2 * d1(-1) + d1(0)) / 6
+    vr = vrr1 - (1.5 * x + y) / (6 * p0 + a)
+    vl = vlr1 + (x + 1.5 * y) / (6 * p2 + a)
+    return vl, vr
