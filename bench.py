@@ -87,7 +87,7 @@ class ClockSampler(threading.Thread):
                 try:
                     self.sm.append(float(self.nv.nvmlDeviceGetClockInfo(self.h, self.nv.NVML_CLOCK_SM)))
                     self.bits |= int(self.nv.nvmlDeviceGetCurrentClocksThrottleReasons(self.h))
-                    if len(self.sm) % 8 == 1:  # the power query is slow: every 8th sample
+                    if len(self.sm) % 16 == 8:  # the power query is slow (tens of ms on some boxes): rarely, never first
                         self.power.append(self.nv.nvmlDeviceGetPowerUsage(self.h) / 1000.0)
                 except Exception as e:
                     self.err = repr(e)

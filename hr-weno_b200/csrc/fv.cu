@@ -71,7 +71,7 @@ __global__ void wtab_recip_kernel(double2 *tab, int count) {
 static int setup_width_1d(Fv *fv, const hrweno_fv_desc *desc) {
    const int64_t n = fv->n0;
    std::vector<double> tab;
-   std::vector<unsigned char> idx((size_t)n + PAD, 0);
+   std::vector<unsigned char> idx((size_t)n + 2048, 0); // the stage kernel stages a whole tile of indices (<= 1056 B from a 16-B boundary below n)
    bool dict = true;
    int last = 0;
    double el = 0.0;
@@ -311,7 +311,8 @@ int fv1d_launch_k3_m0(int, int, int, int, const Fv1dGeom &, const StageArgs &, c
 int fv1d_launch_k1_m1(int, int, int, int, const Fv1dGeom &, const StageArgs &, cudaStream_t);
 int fv1d_launch_k2_m1(int, int, int, int, const Fv1dGeom &, const StageArgs &, cudaStream_t);
 int fv1d_launch_k3_m1(int, int, int, int, const Fv1dGeom &, const StageArgs &, cudaStream_t);
-int fv1d_tile_cells(int half_tile);
+int fv1d_tile_cells(int mode, int half_tile);
+int fv1d_tile_slots(int mode, int half_tile);
 
 int fv1d_launch(int k, int mode, int combine, int fk, int wk, int half_tile, const Fv1dGeom &g, const StageArgs &a, cudaStream_t st) {
    if (mode == HRWENO_MODE_STRICT) {
@@ -332,13 +333,14 @@ static int fv1d_flux_kind(const hrweno_fv_desc &d) {
 // when it covers the row with fewer (partly idle) thread runs, e.g. 4096-cell rows: 9 x 504 instead of 5 x 1016
 static int fv1d_half_tile(const Fv *fv) {
    if (fv1d_flux_kind(fv->d) != FK_BURGERS_GODUNOV || !fv->width_dict) return 0;
-   const int64_t t0 = fv1d_tile_cells(0), t1 = fv1d_tile_cells(1);
-   const double slots0 = (double)((fv->n0 + t0 - 1) / t0) * (double)(t0 + 8), slots1 = (double)((fv->n0 + t1 - 1) / t1) * (double)(t1 + 8);
+   const int64_t t0 = fv1d_tile_cells(fv->d.mode, 0), t1 = fv1d_tile_cells(fv->d.mode, 1);
+   const double slots0 = (double)((fv->n0 + t0 - 1) / t0) * (double)fv1d_tile_slots(fv->d.mode, 0);
+   const double slots1 = (double)((fv->n0 + t1 - 1) / t1) * (double)fv1d_tile_slots(fv->d.mode, 1);
    return slots1 < 0.97 * slots0;
 }
 
 void fv_tiling_1d(const Fv *fv, int *tile_cells, int *tiles_per_row) {
-   const int tile = fv1d_tile_cells(fv1d_half_tile(fv));
+   const int tile = fv1d_tile_cells(fv->d.mode, fv1d_half_tile(fv));
    *tile_cells = tile;
    *tiles_per_row = (int)((fv->n0 + tile - 1) / tile);
 }
@@ -353,7 +355,7 @@ static int fv_stage_impl(Fv *fv, int combine, const StageArgs &args, const HaloI
    Fv1dGeom g{};
    const int fk = fv1d_flux_kind(d);
    const int half_tile = fv1d_half_tile(fv);
-   const int tile = fv1d_tile_cells(half_tile);
+   const int tile = fv1d_tile_cells(d.mode, half_tile);
    g.n = fv->n0;
    g.ld = fv->pitch;
    g.tiles_per_row = (fv->n0 + tile - 1) / tile;

@@ -26,6 +26,15 @@
 #ifndef HRW_MINB
 #define HRW_MINB 2 // resident CTAs per SM the register allocation is tuned for
 #endif
+#ifndef HRW_STAGE_A
+#define HRW_STAGE_A 0 // 1: the pointwise operand a travels with the tile's bulk copies (measured slower: profiles/r1_variant_sweeps.txt)
+#endif
+#ifndef HRW_STAGE_W
+#define HRW_STAGE_W 1 // 1: the width indices of the tile travel with the tile's bulk copies (0: global loads per thread)
+#endif
+#ifndef HRW_SPLIT_BAR
+#define HRW_SPLIT_BAR 0 // neighbour exchange: 0 = __syncthreads, 1 = mbarrier arrive per thread / wait late, 2 = one arrive per warp
+#endif
 
 namespace hrw {
 
@@ -53,6 +62,33 @@ __device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)_
 
 __device__ __forceinline__ void mbar_init(unsigned long long *bar, int count) {
    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
+}
+// split-phase CTA barrier: every thread arrives once per phase (release), waits later (acquire) with mbar_wait
+__device__ __forceinline__ void mbar_arrive(uint32_t bar) {
+   asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
+}
+// overloads on 32-bit shared-window addresses: a persistent loop converts its barrier / buffer pointers once
+__device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes) {
+   asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
+   uint32_t done;
+   do {
+      asm volatile(
+         "{\n"
+         ".reg .pred p;\n"
+         "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n"
+         "selp.u32 %0, 1, 0, p;\n"
+         "}\n"
+         : "=r"(done)
+         : "r"(bar), "r"(parity)
+         : "memory");
+   } while (!done);
+}
+__device__ __forceinline__ void tma_bulk_g2s(uint32_t dst_smem, const void *src_gmem, uint32_t bytes, uint32_t bar) {
+   asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(dst_smem), "l"(src_gmem),
+                "r"(bytes), "r"(bar)
+                : "memory");
 }
 __device__ __forceinline__ void mbar_expect_tx(unsigned long long *bar, uint32_t bytes) {
    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
@@ -105,17 +141,24 @@ struct Prefetched {
    double wd[R];
 };
 
+// The values of the neighbouring thread runs (vr of the cell left of the run, vl of the cell right of it) are published
+// through shared memory behind a split-phase barrier: every thread has arrived before this call; the wait sits after the
+// faces and cells that need no neighbour (R-1 of R+1 faces, R-2 of R cells), so warps that run ahead do not idle.
 template <int K, int COMBINE, class M, int FK, int WK, int R, bool EDGE>
 __device__ __forceinline__ void fv1d_finish(const Fv1dGeom &g, const StageArgs &s, const double2 *s_wtab, int64_t row, int i0,
                                             const double *w /* window, cell j at w[2+j] */, const double *vl, const double *vr,
-                                            double vr_left, double vl_right, double cL, double lscale, const Prefetched<R> &pf) {
+                                            const double *p_vr_left, const double *p_vl_right, uint32_t xbar, uint32_t xparity,
+                                            double cL, double lscale, const Prefetched<R> &pf) {
    const int n = (int)g.n;
    // numerical flux at the R+1 faces i0 .. i0+R (face f lies between cells f-1 and f)
    double F[R + 1];
-   F[0] = face_flux_k<FK, M>(g.flux, vr_left, vl[0]);
 #pragma unroll
    for (int j = 1; j < R; ++j) F[j] = face_flux_k<FK, M>(g.flux, vr[j - 1], vl[j]);
-   F[R] = face_flux_k<FK, M>(g.flux, vr[R - 1], vl_right);
+   if constexpr (EDGE) {
+      if constexpr (HRW_SPLIT_BAR != 0) mbar_wait(xbar, xparity);
+      F[0] = face_flux_k<FK, M>(g.flux, *p_vr_left, vl[0]);
+      F[R] = face_flux_k<FK, M>(g.flux, vr[R - 1], *p_vl_right);
+   }
    if constexpr (EDGE) {
       // problem-specific constraints at the domain boundaries (example1:103-104, example2:117-120)
       const bool copy = g.bc == HRWENO_BC_COPY_NEIGHBOUR;
@@ -177,8 +220,7 @@ __device__ __forceinline__ void fv1d_finish(const Fv1dGeom &g, const StageArgs &
 
    double res[R], lres[R];
    bool ok = true;
-#pragma unroll
-   for (int j = 0; j < R; ++j) {
+   auto cell = [&](int j) {
       // vdot = -(fedges(i) - fedges(i-1))/width (example1:107); q = (df)/width here, sign and the flux's 1/2 are in cL/lscale
       const double dF = M::sub(F[j + 1], F[j]);
       double q;
@@ -212,6 +254,18 @@ __device__ __forceinline__ void fv1d_finish(const Fv1dGeom &g, const StageArgs &
          lres[j] = M::mul(lscale, q);
       }
       res[j] = o;
+   };
+   if constexpr (EDGE) {
+#pragma unroll
+      for (int j = 0; j < R; ++j) cell(j);
+   } else {
+#pragma unroll
+      for (int j = 1; j < R - 1; ++j) cell(j);
+      if constexpr (HRW_SPLIT_BAR != 0) mbar_wait(xbar, xparity);
+      F[0] = face_flux_k<FK, M>(g.flux, *p_vr_left, vl[0]);
+      F[R] = face_flux_k<FK, M>(g.flux, vr[R - 1], *p_vl_right);
+      cell(0);
+      cell(R - 1);
    }
    if constexpr (M::strict) {
       if (!ok) { // a quotient in the denormal range: redo this run with the compiler's division (cold)
@@ -275,19 +329,31 @@ __global__ void __launch_bounds__(NT, HRW_MINB) fv1d_stage_kernel(const Fv1dGeom
    constexpr int TILE = (NT - 2) * R; // cells written per CTA and tile
    constexpr int SM_N = NT * R + 2 * P;
    constexpr int WN = R + 4;         // aligned register window (superset for K < 3)
+   constexpr bool NEED_A = COMBINE == C_RK2_FINAL || COMBINE == C_RK3_S2 || COMBINE == C_RK3_S3 || COMBINE == C_MS;
+   // the pointwise operand a and the width indices of the tile travel with the tile's bulk copies (one iteration ahead),
+   // so interior threads read them from shared memory instead of waiting for global loads
+   constexpr bool STAGE_A = NEED_A && HRW_STAGE_A;
+   constexpr bool STAGE_W = WK == WK_DICT && HRW_STAGE_W;
+   constexpr int WROW = ((TILE + 15) / 16) * 16 + 16; // staged index bytes per tile: from the 16-B boundary at or below its first cell
    __shared__ __align__(128) double s_v[2][SM_N];
+   __shared__ __align__(128) double s_a[STAGE_A ? 2 : 1][STAGE_A ? TILE : 2];
+   __shared__ __align__(16) unsigned char s_wi[STAGE_W ? 2 : 1][STAGE_W ? WROW : 16];
    __shared__ double s_vr[2][NT];
    __shared__ double s_vl[2][NT];
    __shared__ __align__(16) double2 s_wtab[WK == WK_DICT ? 256 : 1];
-   __shared__ __align__(8) unsigned long long s_bar[2];
+   __shared__ __align__(8) unsigned long long s_bar[3]; // [0], [1]: tile buffers (TMA complete_tx); [2]: neighbour exchange
 
    // let the next kernel of the stream be scheduled as soon as SM resources free up (it waits for this grid to
    // complete before reading or writing global data, see griddepcontrol.wait below)
    asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
-   const int tid = threadIdx.x;
+   int tid = threadIdx.x;
+   asm volatile("" : "+r"(tid)); // keep the thread index in a register: re-reading SR_TID.X inside the tile loop stalls
    const int n = (int)g.n;                     // cells per row (< 2^31, validated at creation)
    const int tpr = (int)g.tiles_per_row;
 
+   const uint32_t bar_u32 = smem_u32(&s_bar[0]), sv_u32 = smem_u32(&s_v[0][0]);
+   const uint32_t sa_u32 = smem_u32(&s_a[0][0]), sw_u32 = smem_u32(&s_wi[0][0]);
+   const uint32_t xbar_u32 = bar_u32 + 16u;
    // one elected thread issues the bulk copy of a tile: cells [c0-R-P, c0-R-P+SM_N) clipped to the padded row
    auto issue = [&](int row, int tcol, int buf) {
       const int ts = tcol * TILE - R - P;
@@ -295,8 +361,17 @@ __global__ void __launch_bounds__(NT, HRW_MINB) fv1d_stage_kernel(const Fv1dGeom
       int hi = ts + SM_N;
       if (hi > (int)g.ld - PAD) hi = (int)g.ld - PAD;
       const uint32_t bytes = (uint32_t)(hi - lo) * (uint32_t)sizeof(double);
-      mbar_expect_tx(&s_bar[buf], bytes);
-      tma_bulk_g2s(&s_v[buf][lo - ts], s.vin + (int64_t)row * g.ld + lo, bytes, &s_bar[buf]);
+      const int c0 = tcol * TILE; // first cell the tile writes
+      uint32_t abytes = 0;
+      if constexpr (STAGE_A) {
+         int ahi = c0 + TILE;
+         if (ahi > (int)g.ld - PAD) ahi = (int)g.ld - PAD;
+         abytes = (uint32_t)(ahi - c0) * (uint32_t)sizeof(double);
+      }
+      mbar_expect_tx(bar_u32 + 8u * buf, bytes + abytes + (STAGE_W ? (uint32_t)WROW : 0u));
+      tma_bulk_g2s(sv_u32 + (uint32_t)(buf * SM_N + (lo - ts)) * 8u, s.vin + (int64_t)row * g.ld + lo, bytes, bar_u32 + 8u * buf);
+      if constexpr (STAGE_A) tma_bulk_g2s(sa_u32 + (uint32_t)(buf * TILE) * 8u, s.a + (int64_t)row * g.ld + c0, abytes, bar_u32 + 8u * buf);
+      if constexpr (STAGE_W) tma_bulk_g2s(sw_u32 + (uint32_t)(buf * WROW), g.widx + (c0 & ~15), (uint32_t)WROW, bar_u32 + 8u * buf);
    };
 
    for (int idx = tid; idx < 2 * SM_N; idx += NT) (&s_v[0][0])[idx] = 0.0; // parts a clipped copy never writes
@@ -316,6 +391,7 @@ __global__ void __launch_bounds__(NT, HRW_MINB) fv1d_stage_kernel(const Fv1dGeom
    if (tid == 0) {
       mbar_init(&s_bar[0], 1);
       mbar_init(&s_bar[1], 1);
+      mbar_init(&s_bar[2], HRW_SPLIT_BAR == 2 ? NT / 32 : NT);
       asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
    }
    __syncthreads();
@@ -331,8 +407,6 @@ __global__ void __launch_bounds__(NT, HRW_MINB) fv1d_stage_kernel(const Fv1dGeom
    // neighbour GPU while the bulk of the stage is still being computed
    auto remap = [&](int tc) { return (!g.halo.edge_first || tpr < 3) ? tc : (tc == 1 ? tpr - 1 : (tc == tpr - 1 ? 1 : tc)); };
    if (tid == 0 && lin < g.tile_end) issue(row, remap(tcol), 0);
-
-   constexpr bool NEED_A = COMBINE == C_RK2_FINAL || COMBINE == C_RK3_S2 || COMBINE == C_RK3_S3 || COMBINE == C_MS;
 
    for (int it = 0; lin < g.tile_end; ++it, lin += (int)gridDim.x) {
       const int buf = it & 1;
@@ -351,10 +425,10 @@ __global__ void __launch_bounds__(NT, HRW_MINB) fv1d_stage_kernel(const Fv1dGeom
       const bool skip = tid == 0 || tid == NT - 1 || i0 >= n;
       const bool edge = s.out_dense || (i0 + R >= n) || (i0 == 0);
 
-      // interior threads: start the global loads of the pointwise operands and the width indices now
+      // interior threads: start the global loads of the operands that are not staged with the tile now
       Prefetched<R> pf;
       if (!skip && !edge) {
-         if constexpr (NEED_A) {
+         if constexpr (NEED_A && !STAGE_A) {
             const double *ap = s.a + (int64_t)row * g.ld + i0;
 #pragma unroll
             for (int j = 0; j < R; j += 2) {
@@ -362,20 +436,21 @@ __global__ void __launch_bounds__(NT, HRW_MINB) fv1d_stage_kernel(const Fv1dGeom
                pf.av[j] = t.x;
                pf.av[j + 1] = t.y;
             }
-            if constexpr (COMBINE == C_MS) {
-               const double *bp = s.b + (int64_t)row * g.ld + i0;
+         }
+         if constexpr (COMBINE == C_MS) {
+            const double *bp = s.b + (int64_t)row * g.ld + i0;
 #pragma unroll
-               for (int j = 0; j < R; j += 2) {
-                  const double2 t = __ldg(reinterpret_cast<const double2 *>(bp + j));
-                  pf.bv[j] = t.x;
-                  pf.bv[j + 1] = t.y;
-               }
+            for (int j = 0; j < R; j += 2) {
+               const double2 t = __ldg(reinterpret_cast<const double2 *>(bp + j));
+               pf.bv[j] = t.x;
+               pf.bv[j + 1] = t.y;
             }
          }
-         if constexpr (WK == WK_DICT) {
+         if constexpr (WK == WK_DICT && !STAGE_W) {
 #pragma unroll
             for (int j = 0; j < R; j += 4) pf.idx4[j / 4] = __ldg(reinterpret_cast<const uint32_t *>(g.widx + i0 + j));
-         } else {
+         }
+         if constexpr (WK != WK_DICT) {
 #pragma unroll
             for (int j = 0; j < R; j += 2) {
                const double2 t = __ldg(reinterpret_cast<const double2 *>(g.width + i0 + j));
@@ -385,7 +460,24 @@ __global__ void __launch_bounds__(NT, HRW_MINB) fv1d_stage_kernel(const Fv1dGeom
          }
       }
 
-      mbar_wait(&s_bar[buf], (uint32_t)((it >> 1) & 1));
+      mbar_wait(bar_u32 + 8u * buf, (uint32_t)((it >> 1) & 1));
+
+      // staged operands of this thread's run (threads 0 and NT-1 own no cells: their slots are never used)
+      if (!skip && !edge) {
+         if constexpr (STAGE_A) {
+#pragma unroll
+            for (int j = 0; j < R; j += 2) {
+               const double2 t = *reinterpret_cast<const double2 *>(&s_a[buf][(tid - 1) * R + j]);
+               pf.av[j] = t.x;
+               pf.av[j + 1] = t.y;
+            }
+         }
+         if constexpr (STAGE_W) {
+            const int woff = (ptc * TILE) & 15;
+#pragma unroll
+            for (int j = 0; j < R; j += 4) pf.idx4[j / 4] = *reinterpret_cast<const uint32_t *>(&s_wi[buf][woff + (tid - 1) * R + j]);
+         }
+      }
 
       // slab interface: the ghost cells of an edge tile come from this GPU's mailbox (stored there by the neighbour's
       // previous stage); wait for the sequence number, then patch them into the staged tile
@@ -432,14 +524,22 @@ __global__ void __launch_bounds__(NT, HRW_MINB) fv1d_stage_kernel(const Fv1dGeom
       // the barrier of the iteration in between, which every reader of the old value has passed
       s_vr[buf][tid] = vr[R - 1];
       s_vl[buf][tid] = vl[0];
-      __syncthreads();
+      // HRW_SPLIT_BAR: arrive now, wait inside fv1d_finish after the work that needs no neighbour
+      if constexpr (HRW_SPLIT_BAR == 1) mbar_arrive(xbar_u32);
+      if constexpr (HRW_SPLIT_BAR == 2) {
+         __syncwarp();
+         if ((tid & 31) == 0) mbar_arrive(xbar_u32);
+      }
+      if constexpr (HRW_SPLIT_BAR == 0) __syncthreads();
+      const uint32_t xpar = (uint32_t)(it & 1);
       if (!skip) {
-         const double vr_left = s_vr[buf][tid - 1];
-         const double vl_right = s_vl[buf][tid + 1];
+         const double *p_vr_left = &s_vr[buf][tid - 1], *p_vl_right = &s_vl[buf][tid + 1];
          if (!edge)
-            fv1d_finish<K, COMBINE, M, FK, WK, R, false>(g, s, s_wtab, row, i0, w, vl, vr, vr_left, vl_right, cL, lscale, pf);
+            fv1d_finish<K, COMBINE, M, FK, WK, R, false>(g, s, s_wtab, row, i0, w, vl, vr, p_vr_left, p_vl_right, xbar_u32, xpar, cL, lscale, pf);
          else
-            fv1d_finish<K, COMBINE, M, FK, WK, R, true>(g, s, s_wtab, row, i0, w, vl, vr, vr_left, vl_right, cL, lscale, pf);
+            fv1d_finish<K, COMBINE, M, FK, WK, R, true>(g, s, s_wtab, row, i0, w, vl, vr, p_vr_left, p_vl_right, xbar_u32, xpar, cL, lscale, pf);
+      } else {
+         if constexpr (HRW_SPLIT_BAR != 0) mbar_wait(xbar_u32, xpar); // every thread passes every phase: it bounds how far a warp can run ahead
       }
       // slab interface: the CTA that just wrote the first / last k cells of the slab stores them into the neighbour's
       // mailbox over NVLink and publishes the sequence number (release: fence, then flag)

@@ -2,11 +2,19 @@
 // six times (-DHRW_INST_K=1..3 -DHRW_INST_MODE=0|1) so the 144 specialisations build in parallel.
 #include "fv1d.cuh"
 
-#ifndef HRW_R1
-#define HRW_R1 4
+// cells per thread run / threads per CTA, per arithmetic mode (profiles/r1_variant_sweeps.txt): the fast kernel has the
+// registers for runs of 8 (fewer shared differences recomputed at run ends, half the per-tile overhead per cell)
+#ifndef HRW_R1_STRICT
+#define HRW_R1_STRICT 4
 #endif
-#ifndef HRW_NT1
-#define HRW_NT1 256
+#ifndef HRW_NT1_STRICT
+#define HRW_NT1_STRICT 256
+#endif
+#ifndef HRW_R1_FAST
+#define HRW_R1_FAST 8
+#endif
+#ifndef HRW_NT1_FAST
+#define HRW_NT1_FAST 128
 #endif
 
 namespace hrw {
@@ -14,10 +22,11 @@ namespace hrw {
 constexpr int IK = HRW_INST_K;
 #if HRW_INST_MODE == 0
 using IM = Strict;
+constexpr int R1 = HRW_R1_STRICT, NT1 = HRW_NT1_STRICT;
 #else
 using IM = Fast;
+constexpr int R1 = HRW_R1_FAST, NT1 = HRW_NT1_FAST;
 #endif
-constexpr int R1 = HRW_R1, NT1 = HRW_NT1;
 
 template <int COMBINE, int FK, int WK, int NT = NT1>
 static int launch(const Fv1dGeom &g, const StageArgs &a, cudaStream_t st) {
@@ -76,7 +85,17 @@ int HRW_CAT(fv1d_launch_k, HRW_INST_K, _m, HRW_INST_MODE)(int combine, int fk, i
 }
 
 #if HRW_INST_K == 3 && HRW_INST_MODE == 0
-int fv1d_tile_cells(int half_tile) { return ((half_tile ? NT1 / 2 : NT1) - 2) * R1; } // defined by one of the six objects
+// defined by one of the six objects
+int fv1d_tile_cells(int mode, int half_tile) {
+   const int r = mode == HRWENO_MODE_STRICT ? HRW_R1_STRICT : HRW_R1_FAST;
+   const int nt = mode == HRWENO_MODE_STRICT ? HRW_NT1_STRICT : HRW_NT1_FAST;
+   return ((half_tile ? nt / 2 : nt) - 2) * r;
+}
+int fv1d_tile_slots(int mode, int half_tile) { // thread runs x cells per run, including the two overlap runs
+   const int r = mode == HRWENO_MODE_STRICT ? HRW_R1_STRICT : HRW_R1_FAST;
+   const int nt = mode == HRWENO_MODE_STRICT ? HRW_NT1_STRICT : HRW_NT1_FAST;
+   return (half_tile ? nt / 2 : nt) * r;
+}
 #endif
 
 } // namespace hrw
