@@ -342,7 +342,12 @@ __global__ void __launch_bounds__(NT, fv2d_min_blocks<M, UPW, NT>()) fv2d_stage_
    } // tile loop
 }
 
-constexpr int TX2 = 64, TY2 = 32, NT2 = 256;   // large grids
+#ifndef HRW_TX2
+#define HRW_TX2 64
+#define HRW_TY2 32
+#define HRW_NT2 256
+#endif
+constexpr int TX2 = HRW_TX2, TY2 = HRW_TY2, NT2 = HRW_NT2;   // large grids
 constexpr int TX2S = 32, TY2S = 16, NT2S = 128; // small grids (e.g. example2's 250x250): enough tiles to occupy every SM
 
 template <int K, int COMBINE, class M, int UPW, int TX2, int TY2, int NT2>
