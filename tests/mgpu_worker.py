@@ -85,6 +85,31 @@ def main():
                 print(f"[rank {rank}] FAIL 2D {n1}x{n2g} {kind} tout={tout}: max|d|={np.max(np.abs(u - want)):.3e}", flush=True)
         dist.barrier()
 
+    # ---- FAST mode: the slab result must equal the single-domain FAST result bit for bit (per-cell arithmetic does
+    # not depend on the decomposition) and stay within the north-star tolerance of the oracle ----------------------------
+    FAST = pkg._abi.MODE_FAST
+    for nglob, k, order in [(40000, 3, 3), (30011, 2, 2)]:
+        off, n = pkg.slab.partition(nglob, world, rank)
+        g = pkg.hrweno_grids.grid1().linear(-5.0, 5.0, nglob)
+        rng = np.random.default_rng(nglob)
+        u0 = ex1_ic(g.center) + 1e-3 * rng.standard_normal(nglob)
+        common = dict(k=k, eps=1e-6, linear=(-5.0, 5.0), mode=FAST)
+        fv = pkg.fv.FV(pkg.fv.make_desc(n, rank=rank, nranks=world, global_n=nglob, global_offset=off, **common))
+        pkg.slab.connect(fv, rank, world, gather)
+        ode = pkg.hrweno_tvdode.rktvd(fv, n, order)
+        gode = pkg.hrweno_tvdode.rktvd(pkg.fv.FV(pkg.fv.make_desc(nglob, **common)), nglob, order)  # whole domain on this GPU
+        rode = ref.rktvd(ref.FV(pkg.fv.make_desc(nglob, width=[g.width], k=k, eps=1e-6)), order)
+        u, ug, ur = np.ascontiguousarray(u0[off:off + n]), u0.copy(), u0.copy()
+        dt = 0.2 * 10.0 / nglob
+        t = ode.integrate(u, 0.0, 25 * dt, dt)
+        tg = gode.integrate(ug, 0.0, 25 * dt, dt)
+        rode.integrate(ur, 0.0, 25 * dt, dt)
+        drift = np.max(np.abs(u - ur[off:off + n])) / np.max(np.abs(ur))
+        if not (t == tg and np.array_equal(u, ug[off:off + n]) and drift < 1e-12):
+            fails += 1
+            print(f"[rank {rank}] FAIL 1D fast n={nglob} k={k}: slab vs single-domain max|d|={np.max(np.abs(u - ug[off:off + n])):.3e}, drift {drift:.3e}", flush=True)
+        dist.barrier()
+
     tot = torch.tensor([fails], device="cuda")
     dist.all_reduce(tot)
     if rank == 0:
