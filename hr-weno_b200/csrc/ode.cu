@@ -390,30 +390,33 @@ static int rk_integrate_pipelined(Ode *o, double *u, double *t, double tout, dou
       HRW_CUDA(cudaMemcpyAsync(B[0] + c_lo(c), u + c_lo(c), (size_t)(c_hi(c) - c_lo(c)) * sizeof(double), cudaMemcpyHostToDevice, o->s_in));
       HRW_CUDA(cudaEventRecord(o->ev_in[c], o->s_in));
    }
-   int waited = -1; // highest chunk whose arrival the compute stream already waits for
-   auto need = [&](int c) -> int {
-      if (c > C - 1) c = C - 1;
-      while (waited < c) {
-         ++waited;
-         HRW_CUDA(cudaStreamWaitEvent(cs, o->ev_in[waited], 0));
-         if (waited == 0) fill_ghost_kernel<<<1, 32, 0, cs>>>(B[0], n, k, 1, 0);
-         if (waited == C - 1) fill_ghost_kernel<<<1, 32, 0, cs>>>(B[0], n, k, 0, 1);
-         if (waited == 0 || waited == C - 1) fv->launches++;
-      }
-      return HRWENO_OK;
+   // Time-skewed chunks: stage g of chunk c covers tiles [L(c,g), L(c+1,g)) with L(c,g) = cb[c] - (g+1) for the inner
+   // boundaries (one tile further left per stage; L(0,g) = 0, L(C,g) = tpr).  A stage needs its input k cells beyond
+   // either end of its range: on the right that stays inside the range the same chunk wrote one stage earlier, on the
+   // left inside what chunk c-1 wrote.  So chunk c depends on chunks <= c only: all of its stages run as soon as it has
+   // arrived, in plain chunk-major stream order, while later chunks are still on the bus, and its final range goes back
+   // to the host right after its last stage.  Nothing a later task reads is overwritten early: a buffer is rewritten
+   // `order` stages later, i.e. at least two tiles further left (one for RK1/RK2, still more than k cells).
+   auto Lb = [&](int c, int64_t g) -> int {
+      if (c <= 0) return 0;
+      if (c >= C) return tpr;
+      const int64_t v = (int64_t)cb[c] - (g + 1);
+      return (int)(v < 0 ? 0 : v);
    };
    const int fin_buf = order == 1 ? (int)(nsteps & 1) : 0; // RK1 ping-pongs U <-> T1
-   for (int64_t d = 0; d <= (int64_t)(C - 1) + (G - 1); ++d) {
-      if (d + 1 <= C - 1 || waited < C - 1) HRW_TRY(need((int)std::min<int64_t>(d + 1, C - 1)));
-      const int64_t g_lo = std::max<int64_t>(0, d - (C - 1)), g_hi = std::min<int64_t>(d, G - 1);
-      for (int64_t g = g_lo; g <= g_hi; ++g) {
-         const int c = (int)(d - g);
+   for (int c = 0; c < C; ++c) {
+      HRW_CUDA(cudaStreamWaitEvent(cs, o->ev_in[c], 0));
+      if (c == 0) fill_ghost_kernel<<<1, 32, 0, cs>>>(B[0], n, k, 1, 0);
+      if (c == C - 1) fill_ghost_kernel<<<1, 32, 0, cs>>>(B[0], n, k, 0, 1);
+      if (c == 0 || c == C - 1) fv->launches++;
+      for (int64_t g = 0; g < G; ++g) {
          const int64_t step = g / order;
          const int j = (int)(g - step * order);
          StageArgs a{};
          a.ld_out = fv->pitch;
-         a.tile_begin = cb[c];
-         a.tile_end = cb[c + 1];
+         a.tile_begin = Lb(c, g);
+         a.tile_end = Lb(c + 1, g);
+         if (a.tile_end <= a.tile_begin) continue; // the skew has moved this chunk's range out of the domain
          int combine;
          if (order == 1) {
             combine = C_EULER;
@@ -445,12 +448,13 @@ static int rk_integrate_pipelined(Ode *o, double *u, double *t, double tout, dou
             a.c0 = 2 * dt;
          }
          HRW_TRY(fv_stage(fv, combine, a, cs));
-         if (g == G - 1) { // chunk c is final: device -> host on the output stream
-            HRW_CUDA(cudaEventRecord(o->ev_fin[c], cs));
-            HRW_CUDA(cudaStreamWaitEvent(o->s_out, o->ev_fin[c], 0));
-            HRW_CUDA(cudaMemcpyAsync(u + c_lo(c), B[fin_buf] + c_lo(c), (size_t)(c_hi(c) - c_lo(c)) * sizeof(double), cudaMemcpyDeviceToHost,
-                                     o->s_out));
-         }
+      }
+      // the cells chunk c finished with its last stage: device -> host on the output stream
+      const int64_t f_lo = (int64_t)Lb(c, G - 1) * tile, f_hi = std::min<int64_t>(n, (int64_t)Lb(c + 1, G - 1) * tile);
+      if (f_hi > f_lo) {
+         HRW_CUDA(cudaEventRecord(o->ev_fin[c], cs));
+         HRW_CUDA(cudaStreamWaitEvent(o->s_out, o->ev_fin[c], 0));
+         HRW_CUDA(cudaMemcpyAsync(u + f_lo, B[fin_buf] + f_lo, (size_t)(f_hi - f_lo) * sizeof(double), cudaMemcpyDeviceToHost, o->s_out));
       }
    }
    HRW_CUDA(cudaStreamSynchronize(o->s_out));
