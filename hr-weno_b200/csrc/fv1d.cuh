@@ -32,8 +32,10 @@
 #ifndef HRW_STAGE_W
 #define HRW_STAGE_W 1 // 1: the width indices of the tile travel with the tile's bulk copies (0: global loads per thread)
 #endif
-#ifndef HRW_SPLIT_BAR
-#define HRW_SPLIT_BAR 0 // neighbour exchange: 0 = __syncthreads, 1 = mbarrier arrive per thread / wait late, 2 = one arrive per warp
+#ifndef HRW_WARP_TILES
+#define HRW_WARP_TILES 0 // 1: every warp overlaps its neighbours by one thread run and exchanges by shuffles (no CTA barrier per
+                         // tile).  Measured (profiles/r1_variant_sweeps.txt): the barrier stall disappears but 11 % more instructions
+                         // (30 of 32 lanes useful) and late tile prefetches eat the gain; kept as an option, off.
 #endif
 
 namespace hrw {
@@ -63,7 +65,21 @@ __device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)_
 __device__ __forceinline__ void mbar_init(unsigned long long *bar, int count) {
    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
 }
-// split-phase CTA barrier: every thread arrives once per phase (release), waits later (acquire) with mbar_wait
+// non-blocking phase test
+__device__ __forceinline__ bool mbar_test(uint32_t bar, uint32_t parity) {
+   uint32_t done;
+   asm volatile(
+      "{\n"
+      ".reg .pred p;\n"
+      "mbarrier.test_wait.parity.shared::cta.b64 p, [%1], %2;\n"
+      "selp.u32 %0, 1, 0, p;\n"
+      "}\n"
+      : "=r"(done)
+      : "r"(bar), "r"(parity)
+      : "memory");
+   return done != 0;
+}
+// arrival on a consumer-release barrier (release semantics), waited for with mbar_wait / mbar_test
 __device__ __forceinline__ void mbar_arrive(uint32_t bar) {
    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
 }
@@ -141,24 +157,17 @@ struct Prefetched {
    double wd[R];
 };
 
-// The values of the neighbouring thread runs (vr of the cell left of the run, vl of the cell right of it) are published
-// through shared memory behind a split-phase barrier: every thread has arrived before this call; the wait sits after the
-// faces and cells that need no neighbour (R-1 of R+1 faces, R-2 of R cells), so warps that run ahead do not idle.
 template <int K, int COMBINE, class M, int FK, int WK, int R, bool EDGE>
 __device__ __forceinline__ void fv1d_finish(const Fv1dGeom &g, const StageArgs &s, const double2 *s_wtab, int64_t row, int i0,
                                             const double *w /* window, cell j at w[2+j] */, const double *vl, const double *vr,
-                                            const double *p_vr_left, const double *p_vl_right, uint32_t xbar, uint32_t xparity,
-                                            double cL, double lscale, const Prefetched<R> &pf) {
+                                            double vr_left, double vl_right, double cL, double lscale, const Prefetched<R> &pf) {
    const int n = (int)g.n;
    // numerical flux at the R+1 faces i0 .. i0+R (face f lies between cells f-1 and f)
    double F[R + 1];
+   F[0] = face_flux_k<FK, M>(g.flux, vr_left, vl[0]);
 #pragma unroll
    for (int j = 1; j < R; ++j) F[j] = face_flux_k<FK, M>(g.flux, vr[j - 1], vl[j]);
-   if constexpr (EDGE) {
-      if constexpr (HRW_SPLIT_BAR != 0) mbar_wait(xbar, xparity);
-      F[0] = face_flux_k<FK, M>(g.flux, *p_vr_left, vl[0]);
-      F[R] = face_flux_k<FK, M>(g.flux, vr[R - 1], *p_vl_right);
-   }
+   F[R] = face_flux_k<FK, M>(g.flux, vr[R - 1], vl_right);
    if constexpr (EDGE) {
       // problem-specific constraints at the domain boundaries (example1:103-104, example2:117-120)
       const bool copy = g.bc == HRWENO_BC_COPY_NEIGHBOUR;
@@ -220,7 +229,8 @@ __device__ __forceinline__ void fv1d_finish(const Fv1dGeom &g, const StageArgs &
 
    double res[R], lres[R];
    bool ok = true;
-   auto cell = [&](int j) {
+#pragma unroll
+   for (int j = 0; j < R; ++j) {
       // vdot = -(fedges(i) - fedges(i-1))/width (example1:107); q = (df)/width here, sign and the flux's 1/2 are in cL/lscale
       const double dF = M::sub(F[j + 1], F[j]);
       double q;
@@ -254,18 +264,6 @@ __device__ __forceinline__ void fv1d_finish(const Fv1dGeom &g, const StageArgs &
          lres[j] = M::mul(lscale, q);
       }
       res[j] = o;
-   };
-   if constexpr (EDGE) {
-#pragma unroll
-      for (int j = 0; j < R; ++j) cell(j);
-   } else {
-#pragma unroll
-      for (int j = 1; j < R - 1; ++j) cell(j);
-      if constexpr (HRW_SPLIT_BAR != 0) mbar_wait(xbar, xparity);
-      F[0] = face_flux_k<FK, M>(g.flux, *p_vr_left, vl[0]);
-      F[R] = face_flux_k<FK, M>(g.flux, vr[R - 1], *p_vl_right);
-      cell(0);
-      cell(R - 1);
    }
    if constexpr (M::strict) {
       if (!ok) { // a quotient in the denormal range: redo this run with the compiler's division (cold)
@@ -326,22 +324,30 @@ __device__ __forceinline__ void fv1d_finish(const Fv1dGeom &g, const StageArgs &
 template <int K, int COMBINE, class M, int FK, int WK, int R, int NT>
 __global__ void __launch_bounds__(NT, HRW_MINB) fv1d_stage_kernel(const Fv1dGeom g, const StageArgs s) {
    constexpr int P = 4;              // tile halo in shared memory (>= K-1, keeps 32-B alignment)
-   constexpr int TILE = (NT - 2) * R; // cells written per CTA and tile
-   constexpr int SM_N = NT * R + 2 * P;
+   // Thread runs per tile.  HRW_WARP_TILES: each warp covers 30 runs; its lanes 0 and 31 recompute the neighbouring warps'
+   // edge runs (as threads 0 and NT-1 do for the neighbouring tiles), so vr/vl of the adjacent run arrive by warp shuffles
+   // and the tile loop needs no CTA barrier: warps drift apart by up to one tile and hide each other's stalls.
+   constexpr bool WT = HRW_WARP_TILES != 0;
+   constexpr int WARPS = NT / 32;
+   constexpr int RUNS = WT ? WARPS * 30 : NT - 2; // runs that write cells
+   constexpr int TILE = RUNS * R;                 // cells written per CTA and tile
+   constexpr int SM_N = (RUNS + 2) * R + 2 * P;
    constexpr int WN = R + 4;         // aligned register window (superset for K < 3)
    constexpr bool NEED_A = COMBINE == C_RK2_FINAL || COMBINE == C_RK3_S2 || COMBINE == C_RK3_S3 || COMBINE == C_MS;
-   // the pointwise operand a and the width indices of the tile travel with the tile's bulk copies (one iteration ahead),
-   // so interior threads read them from shared memory instead of waiting for global loads
+   // the width indices of the tile travel with the tile's bulk copies (one iteration ahead), so interior threads read them
+   // from shared memory instead of waiting for global loads (the same for operand a measured slower: HRW_STAGE_A)
    constexpr bool STAGE_A = NEED_A && HRW_STAGE_A;
    constexpr bool STAGE_W = WK == WK_DICT && HRW_STAGE_W;
    constexpr int WROW = ((TILE + 15) / 16) * 16 + 16; // staged index bytes per tile: from the 16-B boundary at or below its first cell
    __shared__ __align__(128) double s_v[2][SM_N];
    __shared__ __align__(128) double s_a[STAGE_A ? 2 : 1][STAGE_A ? TILE : 2];
    __shared__ __align__(16) unsigned char s_wi[STAGE_W ? 2 : 1][STAGE_W ? WROW : 16];
-   __shared__ double s_vr[2][NT];
-   __shared__ double s_vl[2][NT];
+   __shared__ double s_vr[WT ? 1 : 2][WT ? 1 : NT];
+   __shared__ double s_vl[WT ? 1 : 2][WT ? 1 : NT];
+   (void)s_vr;
+   (void)s_vl;
    __shared__ __align__(16) double2 s_wtab[WK == WK_DICT ? 256 : 1];
-   __shared__ __align__(8) unsigned long long s_bar[3]; // [0], [1]: tile buffers (TMA complete_tx); [2]: neighbour exchange
+   __shared__ __align__(8) unsigned long long s_bar[4]; // [0], [1]: tile buffer full (TMA complete_tx); [2], [3]: tile buffer consumed
 
    // let the next kernel of the stream be scheduled as soon as SM resources free up (it waits for this grid to
    // complete before reading or writing global data, see griddepcontrol.wait below)
@@ -353,7 +359,8 @@ __global__ void __launch_bounds__(NT, HRW_MINB) fv1d_stage_kernel(const Fv1dGeom
 
    const uint32_t bar_u32 = smem_u32(&s_bar[0]), sv_u32 = smem_u32(&s_v[0][0]);
    const uint32_t sa_u32 = smem_u32(&s_a[0][0]), sw_u32 = smem_u32(&s_wi[0][0]);
-   const uint32_t xbar_u32 = bar_u32 + 16u;
+   const int lane = tid & 31;
+   const int slot = WT ? (tid >> 5) * 30 + lane : tid; // run index within the staged tile (0 = the run left of the tile)
    // one elected thread issues the bulk copy of a tile: cells [c0-R-P, c0-R-P+SM_N) clipped to the padded row
    auto issue = [&](int row, int tcol, int buf) {
       const int ts = tcol * TILE - R - P;
@@ -391,7 +398,8 @@ __global__ void __launch_bounds__(NT, HRW_MINB) fv1d_stage_kernel(const Fv1dGeom
    if (tid == 0) {
       mbar_init(&s_bar[0], 1);
       mbar_init(&s_bar[1], 1);
-      mbar_init(&s_bar[2], HRW_SPLIT_BAR == 2 ? NT / 32 : NT);
+      mbar_init(&s_bar[2], WARPS);
+      mbar_init(&s_bar[3], WARPS);
       asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
    }
    __syncthreads();
@@ -415,18 +423,40 @@ __global__ void __launch_bounds__(NT, HRW_MINB) fv1d_stage_kernel(const Fv1dGeom
          ntcol -= tpr;
          ++nrow;
       }
-      // prefetch the next tile into the other buffer: every thread finished reading it before the exchange
-      // barrier of the previous iteration, which this thread has passed
-      if (tid == 0 && lin + (int)gridDim.x < g.tile_end) issue(nrow, remap(ntcol), buf ^ 1);
+      // prefetch the next tile into the other buffer once every warp has taken the previous tile out of it: with the
+      // exchange barrier, every thread passed last iteration's barrier after its loads; with warp tiles, each warp
+      // arrives on the buffer's "consumed" barrier after its loads
+      // The producer (thread 0) never blocks its warp early: it tests the "consumed" barrier here, again after the
+      // reconstruction, and waits only at the end of the iteration.
+      bool pending = tid == 0 && lin + (int)gridDim.x < g.tile_end;
+      auto try_issue = [&](bool block) {
+         if (!pending) return;
+         if (WT && it > 0) {
+            const uint32_t eb = bar_u32 + 16u + 8u * (buf ^ 1), ep = (uint32_t)(((it - 1) >> 1) & 1);
+            if (block)
+               mbar_wait(eb, ep);
+            else if (!mbar_test(eb, ep))
+               return;
+         }
+         issue(nrow, remap(ntcol), buf ^ 1);
+         pending = false;
+      };
+      try_issue(false);
 
-      const int ptc = remap(tcol);               // physical tile of this iteration
-      const int i0 = ptc * TILE + (tid - 1) * R; // first owned cell (thread 0: the run left of the tile)
+      const int ptc = remap(tcol);                // physical tile of this iteration
+      const int i0 = ptc * TILE + (slot - 1) * R; // first owned cell (slot 0: the run left of the tile)
       // a caller's dense output array carries no alignment guarantee: scalar stores (edge path) for every thread
-      const bool skip = tid == 0 || tid == NT - 1 || i0 >= n;
+      const bool skip = (WT ? (lane == 0 || lane == 31) : (tid == 0 || tid == NT - 1)) || i0 >= n;
       const bool edge = s.out_dense || (i0 + R >= n) || (i0 == 0);
 
       // interior threads: start the global loads of the operands that are not staged with the tile now
       Prefetched<R> pf;
+#pragma unroll
+      for (int q = 0; q < (R / 4 > 0 ? R / 4 : 1); ++q) pf.idx4[q] = 0u;
+      if constexpr (STAGE_A) {
+#pragma unroll
+         for (int j = 0; j < R; ++j) pf.av[j] = 0.0;
+      }
       if (!skip && !edge) {
          if constexpr (NEED_A && !STAGE_A) {
             const double *ap = s.a + (int64_t)row * g.ld + i0;
@@ -462,12 +492,12 @@ __global__ void __launch_bounds__(NT, HRW_MINB) fv1d_stage_kernel(const Fv1dGeom
 
       mbar_wait(bar_u32 + 8u * buf, (uint32_t)((it >> 1) & 1));
 
-      // staged operands of this thread's run (threads 0 and NT-1 own no cells: their slots are never used)
+      // staged operands of this thread's run (overlap runs own no cells: their slots are never used)
       if (!skip && !edge) {
          if constexpr (STAGE_A) {
 #pragma unroll
             for (int j = 0; j < R; j += 2) {
-               const double2 t = *reinterpret_cast<const double2 *>(&s_a[buf][(tid - 1) * R + j]);
+               const double2 t = *reinterpret_cast<const double2 *>(&s_a[buf][(slot - 1) * R + j]);
                pf.av[j] = t.x;
                pf.av[j + 1] = t.y;
             }
@@ -475,7 +505,7 @@ __global__ void __launch_bounds__(NT, HRW_MINB) fv1d_stage_kernel(const Fv1dGeom
          if constexpr (STAGE_W) {
             const int woff = (ptc * TILE) & 15;
 #pragma unroll
-            for (int j = 0; j < R; j += 4) pf.idx4[j / 4] = *reinterpret_cast<const uint32_t *>(&s_wi[buf][woff + (tid - 1) * R + j]);
+            for (int j = 0; j < R; j += 4) pf.idx4[j / 4] = *reinterpret_cast<const uint32_t *>(&s_wi[buf][woff + (slot - 1) * R + j]);
          }
       }
 
@@ -513,34 +543,50 @@ __global__ void __launch_bounds__(NT, HRW_MINB) fv1d_stage_kernel(const Fv1dGeom
       double w[WN];
 #pragma unroll
       for (int j = 0; j < WN; j += 2) {
-         const double2 t = *reinterpret_cast<const double2 *>(&s_v[buf][tid * R + P - 2 + j]);
+         const double2 t = *reinterpret_cast<const double2 *>(&s_v[buf][slot * R + P - 2 + j]);
          w[j] = t.x;
          w[j + 1] = t.y;
       }
+      if constexpr (WT) {
+         // this warp has its part of the tile in registers (the empty asm makes the loads' results a dependency of what
+         // follows): release the buffer, one arrival per warp
+#pragma unroll
+         for (int j = 0; j < WN; ++j) asm volatile("" : "+d"(w[j]));
+         if constexpr (STAGE_W) {
+#pragma unroll
+            for (int q = 0; q < (R / 4 > 0 ? R / 4 : 1); ++q) asm volatile("" : "+r"(pf.idx4[q]));
+         }
+         if constexpr (STAGE_A) {
+#pragma unroll
+            for (int j = 0; j < R; ++j) asm volatile("" : "+d"(pf.av[j]));
+         }
+         __syncwarp();
+         if (lane == 0) mbar_arrive(bar_u32 + 16u + 8u * buf);
+      }
       double vl[R], vr[R];
       weno_run<K, R, M>(w + (2 - (K - 1)), g.kc, vl, vr);
+      try_issue(false);
 
-      // exchange arrays are double buffered by iteration parity: a slot is rewritten two iterations later, after
-      // the barrier of the iteration in between, which every reader of the old value has passed
-      s_vr[buf][tid] = vr[R - 1];
-      s_vl[buf][tid] = vl[0];
-      // HRW_SPLIT_BAR: arrive now, wait inside fv1d_finish after the work that needs no neighbour
-      if constexpr (HRW_SPLIT_BAR == 1) mbar_arrive(xbar_u32);
-      if constexpr (HRW_SPLIT_BAR == 2) {
-         __syncwarp();
-         if ((tid & 31) == 0) mbar_arrive(xbar_u32);
-      }
-      if constexpr (HRW_SPLIT_BAR == 0) __syncthreads();
-      const uint32_t xpar = (uint32_t)(it & 1);
-      if (!skip) {
-         const double *p_vr_left = &s_vr[buf][tid - 1], *p_vl_right = &s_vl[buf][tid + 1];
-         if (!edge)
-            fv1d_finish<K, COMBINE, M, FK, WK, R, false>(g, s, s_wtab, row, i0, w, vl, vr, p_vr_left, p_vl_right, xbar_u32, xpar, cL, lscale, pf);
-         else
-            fv1d_finish<K, COMBINE, M, FK, WK, R, true>(g, s, s_wtab, row, i0, w, vl, vr, p_vr_left, p_vl_right, xbar_u32, xpar, cL, lscale, pf);
+      double vr_left, vl_right;
+      if constexpr (WT) {
+         vr_left = __shfl_up_sync(0xffffffffu, vr[R - 1], 1);
+         vl_right = __shfl_down_sync(0xffffffffu, vl[0], 1);
       } else {
-         if constexpr (HRW_SPLIT_BAR != 0) mbar_wait(xbar_u32, xpar); // every thread passes every phase: it bounds how far a warp can run ahead
+         // exchange arrays are double buffered by iteration parity: a slot is rewritten two iterations later, after
+         // the barrier of the iteration in between, which every reader of the old value has passed
+         s_vr[buf][tid] = vr[R - 1];
+         s_vl[buf][tid] = vl[0];
+         __syncthreads();
+         vr_left = s_vr[buf][tid > 0 ? tid - 1 : 0];
+         vl_right = s_vl[buf][tid < NT - 1 ? tid + 1 : tid];
       }
+      if (!skip) {
+         if (!edge)
+            fv1d_finish<K, COMBINE, M, FK, WK, R, false>(g, s, s_wtab, row, i0, w, vl, vr, vr_left, vl_right, cL, lscale, pf);
+         else
+            fv1d_finish<K, COMBINE, M, FK, WK, R, true>(g, s, s_wtab, row, i0, w, vl, vr, vr_left, vl_right, cL, lscale, pf);
+      }
+      try_issue(true);
       // slab interface: the CTA that just wrote the first / last k cells of the slab stores them into the neighbour's
       // mailbox over NVLink and publishes the sequence number (release: fence, then flag)
       if (g.halo.seq_out) {

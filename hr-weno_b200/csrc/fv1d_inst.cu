@@ -88,10 +88,11 @@ int HRW_CAT(fv1d_launch_k, HRW_INST_K, _m, HRW_INST_MODE)(int combine, int fk, i
 // defined by one of the six objects
 int fv1d_tile_cells(int mode, int half_tile) {
    const int r = mode == HRWENO_MODE_STRICT ? HRW_R1_STRICT : HRW_R1_FAST;
-   const int nt = mode == HRWENO_MODE_STRICT ? HRW_NT1_STRICT : HRW_NT1_FAST;
-   return ((half_tile ? nt / 2 : nt) - 2) * r;
+   int nt = mode == HRWENO_MODE_STRICT ? HRW_NT1_STRICT : HRW_NT1_FAST;
+   if (half_tile) nt /= 2;
+   return (HRW_WARP_TILES ? (nt / 32) * 30 : nt - 2) * r;
 }
-int fv1d_tile_slots(int mode, int half_tile) { // thread runs x cells per run, including the two overlap runs
+int fv1d_tile_slots(int mode, int half_tile) { // thread runs x cells per run, including the overlap runs
    const int r = mode == HRWENO_MODE_STRICT ? HRW_R1_STRICT : HRW_R1_FAST;
    const int nt = mode == HRWENO_MODE_STRICT ? HRW_NT1_STRICT : HRW_NT1_FAST;
    return (half_tile ? nt / 2 : nt) * r;
