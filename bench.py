@@ -188,6 +188,17 @@ def main():
         run_reference(args, rank, world)
         return
 
+    # stdout carries exactly ONE JSON line: everything libraries print while the job runs (NCCL's version banner, ...)
+    # goes to stderr; the descriptor is restored just before the line is printed
+    sys.stdout.flush()
+    saved_stdout = os.dup(1)
+    os.dup2(2, 1)
+
+    def emit(line):
+        sys.stdout.flush()
+        os.dup2(saved_stdout, 1)
+        print(json.dumps(line), flush=True)
+
     import torch
     import torch.distributed as dist
 
@@ -336,7 +347,7 @@ def main():
         line["other_mode"] = {"mode": other, "value": v2, "steps": ko, "avg_launch_ms": sm2, "roofline_frac": ach2 / peak}
     if not args.no_cpu_baseline:
         line["cpu_baseline"] = cpu_baseline_leg(pkg)
-    print(json.dumps(line))
+    emit(line)
     if world > 1:
         dist.destroy_process_group()
 
