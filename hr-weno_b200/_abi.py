@@ -67,6 +67,7 @@ PROTOTYPES = {
         [C.c_void_p, C.POINTER(C.c_int64), C.POINTER(C.c_int), C.POINTER(C.c_double), C.POINTER(C.c_int)],
     ),
     "hrweno_weno_get_cnu": (C.c_int, [C.c_void_p, C.c_void_p]),
+    "hrweno_weno_set_mode": (C.c_int, [C.c_void_p, C.c_int]),
     "hrweno_weno_reconstruct": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),
     "hrweno_weno_reconstruct_batch": (
         C.c_int,

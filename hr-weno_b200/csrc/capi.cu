@@ -92,6 +92,14 @@ int hrweno_weno_info(const hrweno_weno *h, int64_t *ncells, int *k, double *eps,
    return HRWENO_OK;
 }
 
+int hrweno_weno_set_mode(hrweno_weno *h, int mode) {
+   Weno *w = reinterpret_cast<Weno *>(h);
+   if (!w) return fail(HRWENO_EINVAL, "null weno handle");
+   if (mode != HRWENO_MODE_STRICT && mode != HRWENO_MODE_FAST) return fail(HRWENO_EINVAL, "invalid mode");
+   w->mode = mode;
+   return HRWENO_OK;
+}
+
 int hrweno_weno_get_cnu(const hrweno_weno *h, double *cnu_host) {
    const Weno *w = reinterpret_cast<const Weno *>(h);
    if (!w || !cnu_host) return fail(HRWENO_EINVAL, "null argument");

@@ -126,6 +126,7 @@ struct Weno {
    int k = 3;
    double eps = 1e-6;
    bool uniform = true;
+   int mode = HRWENO_MODE_STRICT; // arithmetic of the uniform-table reconstruct kernel (hrweno_weno_set_mode)
    std::vector<double> cnu_host;
    double *d_cnu = nullptr;
    // cached device buffers for the host-pointer entry points

@@ -127,8 +127,96 @@ __global__ void __launch_bounds__(256)
    }
 }
 
+// ------------------------------------------------------------------------------------------------
+// K1r: uniform tables, contiguous rows (incv == 1).  A thread reconstructs a run of R = 4 consecutive cells from a
+// register window, so the products and differences neighbouring cells share are computed once (weno_core.cuh);
+// 16-B loads and stores when the caller's pointers and pitches allow it, clamped scalar accesses at row ends.
+// ------------------------------------------------------------------------------------------------
+template <int K, class M, bool VEC>
+__global__ void __launch_bounds__(256)
+   recon_run_kernel(const double *__restrict__ v, int64_t ldv, double *__restrict__ vl, double *__restrict__ vr, int64_t ldo, int64_t n,
+                    int64_t rows, const WenoK kc) {
+   constexpr int R = 4;
+   const int64_t runs_per_row = (n + R - 1) / R;
+   const int64_t total = rows * runs_per_row;
+   for (int64_t idx = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; idx < total; idx += (int64_t)gridDim.x * blockDim.x) {
+      const int64_t row = idx / runs_per_row;
+      const int64_t i0 = (idx - row * runs_per_row) * R;
+      const double *vrow = v + row * ldv;
+      double w[R + 4]; // cells i0-2 .. i0+R+1; only [JLO, JHI) is needed for this K (even bounds: 16-B loads)
+      constexpr int JLO = (2 - (K - 1)) & ~1, JHI = (R + 2 + (K - 1) + 1) & ~1;
+#pragma unroll
+      for (int j = 0; j < R + 4; ++j) w[j] = 0.0;
+      const bool inner = i0 >= 2 && i0 + R + 2 <= n;
+      if (VEC && inner) {
+#pragma unroll
+         for (int j = JLO; j < JHI; j += 2) {
+            const double2 t = __ldg(reinterpret_cast<const double2 *>(vrow + i0 - 2 + j));
+            w[j] = t.x;
+            w[j + 1] = t.y;
+         }
+      } else {
+#pragma unroll
+         for (int j = JLO; j < JHI; ++j) {
+            int64_t ii = i0 - 2 + j;
+            ii = ii < 0 ? 0 : (ii > n - 1 ? n - 1 : ii); // edge replicas (weno.f90:171-173)
+            w[j] = __ldg(vrow + ii);
+         }
+      }
+      double l[R], r[R];
+      weno_run<K, R, M>(w + (2 - (K - 1)), kc, l, r);
+      double *pl = vl + row * ldo + i0, *pr = vr + row * ldo + i0;
+      if (VEC && i0 + R <= n) {
+#pragma unroll
+         for (int j = 0; j < R; j += 2) {
+            *reinterpret_cast<double2 *>(pl + j) = make_double2(l[j], l[j + 1]);
+            *reinterpret_cast<double2 *>(pr + j) = make_double2(r[j], r[j + 1]);
+         }
+      } else {
+#pragma unroll
+         for (int j = 0; j < R; ++j)
+            if (i0 + j < n) {
+               pl[j] = l[j];
+               pr[j] = r[j];
+            }
+      }
+   }
+}
+
+template <int K, class M>
+static void launch_run(const Weno *w, int64_t rows, const double *v, int64_t ldv, double *vl, double *vr, int64_t ldo, cudaStream_t st) {
+   const int64_t total = rows * ((w->ncells + 3) / 4);
+   int64_t blocks = (total + 255) / 256;
+   if (blocks > 148 * 32) blocks = 148 * 32;
+   const bool vec = ((reinterpret_cast<uintptr_t>(v) | reinterpret_cast<uintptr_t>(vl) | reinterpret_cast<uintptr_t>(vr)) & 15u) == 0 &&
+                    (rows == 1 || ((ldv | ldo) & 1) == 0);
+   if (vec)
+      recon_run_kernel<K, M, true><<<(unsigned)blocks, 256, 0, st>>>(v, ldv, vl, vr, ldo, w->ncells, rows, make_wenok(w->eps));
+   else
+      recon_run_kernel<K, M, false><<<(unsigned)blocks, 256, 0, st>>>(v, ldv, vl, vr, ldo, w->ncells, rows, make_wenok(w->eps));
+}
+
+template <class M>
+static void launch_run_k(const Weno *w, int64_t rows, const double *v, int64_t ldv, double *vl, double *vr, int64_t ldo, cudaStream_t st) {
+   if (w->k == 1)
+      launch_run<1, M>(w, rows, v, ldv, vl, vr, ldo, st);
+   else if (w->k == 2)
+      launch_run<2, M>(w, rows, v, ldv, vl, vr, ldo, st);
+   else
+      launch_run<3, M>(w, rows, v, ldv, vl, vr, ldo, st);
+}
+
 int weno_reconstruct_launch(const Weno *w, int64_t rows, const double *v, int64_t ldv, int64_t incv, double *vl,
                             double *vr, int64_t ldo, cudaStream_t st) {
+   if (w->uniform && incv == 1) { // the common case: contiguous rows, uniform tables
+      if (w->mode == HRWENO_MODE_FAST)
+         launch_run_k<Fast>(w, rows, v, ldv, vl, vr, ldo, st);
+      else
+         launch_run_k<Strict>(w, rows, v, ldv, vl, vr, ldo, st);
+      HRW_CUDA(cudaGetLastError());
+      return HRWENO_OK;
+   }
+   // strided sections (example2:107) and per-cell coefficient tables: one cell per thread, reference order
    const int64_t total = rows * w->ncells;
    int64_t blocks = (total + 255) / 256;
    if (blocks > 148 * 32) blocks = 148 * 32;

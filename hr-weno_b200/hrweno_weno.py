@@ -30,7 +30,7 @@ class weno:
     ``error stop`` after setting ierr = 1 and msg.
     """
 
-    def __init__(self, ncells, k=3, eps=1e-6, xedges=None):
+    def __init__(self, ncells, k=3, eps=1e-6, xedges=None, mode=None):
         self.msg = ""
         self.ierr = 0
         self._h = C.c_void_p()
@@ -49,6 +49,8 @@ class weno:
             raise _abi.HrwenoError(st, self.msg)
         self.ncells, self.k, self.eps = int(ncells), int(k), float(eps)
         self.uniform_grid = xedges is None
+        if mode is not None:  # extension: arithmetic mode of the uniform-table kernel (strict by default)
+            _abi.check(_abi.lib().hrweno_weno_set_mode(self._h, int(mode)))
 
     def __del__(self):
         try:

@@ -95,6 +95,10 @@ int hrweno_device_count(void);       /* number of usable CUDA devices (0 if none
 int hrweno_weno_create(hrweno_weno **out, int64_t ncells, int k, double eps, const double *xedges);
 void hrweno_weno_destroy(hrweno_weno *w);
 int hrweno_weno_info(const hrweno_weno *w, int64_t *ncells, int *k, double *eps, int *uniform_grid);
+/* Extension (no counterpart in the reference): arithmetic of reconstruct on uniform tables, HRWENO_MODE_STRICT
+ * (default; bit-identical to the reference's operation order) or HRWENO_MODE_FAST (same scheme in difference form,
+ * a few ULP of max|v|).  Non-uniform (cnu) and strided reconstructions always run in the reference order. */
+int hrweno_weno_set_mode(hrweno_weno *w, int mode);
 /* copy of cnu in the reference's column-major order cnu(j,r,i): index j + k*((r+1) + (k+1)*(i-1)) */
 int hrweno_weno_get_cnu(const hrweno_weno *w, double *cnu_host);
 

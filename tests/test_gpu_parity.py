@@ -60,6 +60,43 @@ def test_reconstruct_nonuniform(gpu_lib, pkg, ref, k):
     assert np.array_equal(vl, rl) and np.array_equal(vr, rr)
 
 
+@pytest.mark.parametrize("k", [1, 2, 3])
+def test_reconstruct_fast_mode_within_a_few_ulp(gpu_lib, pkg, ref, k):
+    """north star: reconstruction-only results at identical inputs within a few ULP (fast mode, difference form)"""
+    rng = np.random.default_rng(40 + k)
+    for nc in (1, 2, 5, 6, 1001, 65536):
+        x = np.linspace(-5, 5, nc)
+        v = np.clip(1.0 - 0.25 * (x + 4.0), -0.5, 1.0) + 1e-3 * rng.standard_normal(nc)
+        vl, vr = pkg.hrweno_weno.weno(nc, k, 1e-6, mode=pkg._abi.MODE_FAST).reconstruct(v)
+        rl, rr = ref.reconstruct(v, k, 1e-6)
+        tol = 4 * np.finfo(float).eps * np.max(np.abs(v))
+        assert np.max(np.abs(vl - rl)) <= tol and np.max(np.abs(vr - rr)) <= tol
+
+
+@pytest.mark.parametrize("k", [2, 3])
+def test_reconstruct_dev_unaligned_pointers_and_odd_pitches(gpu_lib, pkg, ref, k):
+    """device-pointer entry: the 16-B vector path needs aligned pointers and even pitches; anything else must take the
+    scalar path and give the same bits"""
+    import torch
+
+    rng = np.random.default_rng(k)
+    rows, nc = 5, 1003
+    w = pkg.hrweno_weno.weno(nc, k, 1e-6)
+    for ldv, ldo, shift in [(nc, nc, 0), (nc + 1, nc + 1, 0), (nc + 5, nc + 3, 1), (nc + 1, nc + 1, 1)]:
+        m = rng.standard_normal((rows, ldv))
+        buf = torch.zeros(rows * ldv + 2, dtype=torch.float64, device="cuda")
+        buf[shift:shift + rows * ldv] = torch.from_numpy(m.reshape(-1)).cuda()
+        ol = torch.zeros(rows * ldo + 2, dtype=torch.float64, device="cuda")
+        orr = torch.zeros(rows * ldo + 2, dtype=torch.float64, device="cuda")
+        w.reconstruct_dev(buf.data_ptr() + 8 * shift, ol.data_ptr() + 8 * shift, orr.data_ptr() + 8 * shift, rows=rows, ldv=ldv, ldo=ldo)
+        torch.cuda.synchronize()
+        gl = ol[shift:shift + rows * ldo].cpu().numpy().reshape(rows, ldo)[:, :nc]
+        gr = orr[shift:shift + rows * ldo].cpu().numpy().reshape(rows, ldo)[:, :nc]
+        for j in range(rows):
+            rl, rr = ref.reconstruct(m[j, :nc], k, 1e-6)
+            assert np.array_equal(gl[j], rl) and np.array_equal(gr[j], rr), (ldv, ldo, shift, j)
+
+
 def test_reconstruct_strided_and_batched(gpu_lib, pkg, ref):
     """the sections of example2:98,107: contiguous rows and stride-nc1 columns"""
     rng = np.random.default_rng(5)

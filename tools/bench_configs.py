@@ -92,6 +92,19 @@ if args.only in ("", "cfg4"):
     print(f"cfg4 2D {n}x{n} WENO5+mstvd ({args.mode}): {K} steps in {el*1e3:.1f} ms -> {cells*K/el:.3e} cell-steps/s, {gbs:.0f} GB/s algorithmic (40 B/cell-step) = {gbs/PEAK:.3f} of measured HBM peak")
     del ode, fv, ud
 
+if args.only in ("", "recon"):
+    # reconstruct-only (K1r): w%reconstruct on device arrays, 2^27 cells, 24 algorithmic B/cell (R v, W vl, W vr)
+    n = 1 << 27
+    v = torch.from_numpy(np.random.default_rng(1).standard_normal(n)).cuda()
+    vl, vr = torch.empty_like(v), torch.empty_like(v)
+    for k in (1, 2, 3):
+        w = pkg.hrweno_weno.weno(n, k, 1e-6, mode=MODE)
+        w.reconstruct_dev(v.data_ptr(), vl.data_ptr(), vr.data_ptr(), stream=stream)
+        el = timed(lambda: [w.reconstruct_dev(v.data_ptr(), vl.data_ptr(), vr.data_ptr(), stream=stream) for _ in range(10)]) / 10
+        gbs = n * 24.0 / el / 1e9
+        print(f"reconstruct-only 2^27 cells k={k} ({args.mode}): {n/el:.3e} cells/s, {gbs:.0f} GB/s algorithmic (24 B/cell) = {gbs/PEAK:.3f} of peak")
+    del v, vl, vr
+
 if args.only in ("", "cfg5"):
     rows, nc = args.rows, 4096
     g = pkg.hrweno_grids.grid1().linear(-5.0, 5.0, nc)
