@@ -190,10 +190,13 @@ __device__ __forceinline__ void fv2d_phase_b(const Fv2dGeom &g, const StageArgs 
    }
 }
 
+#ifndef HRW_MINB2_BIG
+#define HRW_MINB2_BIG 2 // resident 512-thread CTAs per SM the registers are capped for (64 registers)
+#endif
 // resident CTAs per SM the registers are capped for: 3 tiles of the upwind fast variant fit in shared memory, 2 otherwise
 template <class M, int UPW, int NT>
 constexpr int fv2d_min_blocks() {
-   return ((UPW && !M::strict) ? 3 : 2) * (256 / NT);
+   return NT > 256 ? HRW_MINB2_BIG : ((UPW && !M::strict) ? 3 : 2) * (256 / NT);
 }
 
 template <int K, int COMBINE, class M, int UPW, int TX, int TY, int NT>
@@ -264,7 +267,11 @@ __global__ void __launch_bounds__(NT, fv2d_min_blocks<M, UPW, NT>()) fv2d_stage_
       const int oidx = ly * T::XP + (rx + 1) * R;
       double w[R + 4];
 #pragma unroll
-      for (int j = 0; j < R + 4; ++j) w[j] = base[j - 2];
+      for (int j = 0; j < R + 4; j += 2) { // base - 2 is 16-B aligned: even tile pitch, even frame, runs of 4
+         const double2 t = *reinterpret_cast<const double2 *>(base + j - 2);
+         w[j] = t.x;
+         w[j + 1] = t.y;
+      }
       double vl[R], vr[R];
       weno_run<K, R, M>(w + (2 - (K - 1)), g.kc, vl, vr);
 #pragma unroll
@@ -348,6 +355,7 @@ __global__ void __launch_bounds__(NT, fv2d_min_blocks<M, UPW, NT>()) fv2d_stage_
 #define HRW_NT2 256
 #endif
 constexpr int TX2 = HRW_TX2, TY2 = HRW_TY2, NT2 = HRW_NT2;   // large grids
+constexpr int NT2F = 2 * HRW_NT2;                            // threads per tile in fast mode
 constexpr int TX2S = 32, TY2S = 16, NT2S = 128; // small grids (e.g. example2's 250x250): enough tiles to occupy every SM
 
 template <int K, int COMBINE, class M, int UPW, int TX2, int TY2, int NT2>
@@ -387,6 +395,9 @@ static int launch2d_t(const Fv2dGeom &g, const StageArgs &a, cudaStream_t st) {
 template <int K, int COMBINE, class M, int UPW>
 static int launch2d_u(const Fv2dGeom &g, const StageArgs &a, cudaStream_t st) {
    if (g.small_tiles) return launch2d_t<K, COMBINE, M, UPW, TX2S, TY2S, NT2S>(g, a, st);
+   // fast mode: 512 threads per tile (one x1-run and one x2-run each, 64 registers, 32 resident warps per SM instead of 24):
+   // +6 % on cfg4; strict mode needs its 112-128 registers and keeps 256 threads (profiles/r1_variant_sweeps.txt)
+   if constexpr (!M::strict) return launch2d_t<K, COMBINE, M, UPW, TX2, TY2, NT2F>(g, a, st);
    return launch2d_t<K, COMBINE, M, UPW, TX2, TY2, NT2>(g, a, st);
 }
 
