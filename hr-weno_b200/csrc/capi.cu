@@ -206,6 +206,22 @@ int hrweno_fv_rhs(hrweno_fv *h, double t, const double *v, double *vdot) {
    return fv_halo_status(fv);
 }
 
+int hrweno_fv_max_wavespeed_dev(hrweno_fv *h, const double *v_dev, double *out_dev, void *stream) {
+   Fv *fv = reinterpret_cast<Fv *>(h);
+   if (!fv || !v_dev || !out_dev) return fail(HRWENO_EINVAL, "null argument");
+   std::lock_guard<std::mutex> lock(fv->mtx);
+   return fv_max_wavespeed(fv, v_dev, out_dev, (cudaStream_t)stream);
+}
+
+int hrweno_fv_set_alpha(hrweno_fv *h, double alpha) {
+   Fv *fv = reinterpret_cast<Fv *>(h);
+   if (!fv) return fail(HRWENO_EINVAL, "null fv handle");
+   if (!(alpha >= 0.0)) return fail(HRWENO_EINVAL, "Invalid input 'alpha'. Valid range: alpha >= 0.");
+   std::lock_guard<std::mutex> lock(fv->mtx);
+   fv->d.alpha = alpha; // read at every stage launch
+   return HRWENO_OK;
+}
+
 int hrweno_fv_export_halo(hrweno_fv *h, void *handle_out) {
    if (!h) return fail(HRWENO_EINVAL, "null fv handle");
    return fv_halo_export(reinterpret_cast<Fv *>(h), handle_out);

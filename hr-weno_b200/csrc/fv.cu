@@ -303,6 +303,56 @@ int fv_unpack(Fv *fv, const double *padded0, double *dense, cudaStream_t st) {
 }
 
 // ------------------------------------------------------------------------------------------------
+// K5: local max |f'(v)| (the Lax-Friedrichs alpha, fluxes.f90:40-43).  The reference takes alpha from the caller and has
+// no reduction; this helper lets a caller compute it on the device -- Burgers (example1:120): f'(v) = v; linear flux:
+// |a| -- and combine the per-GPU values with one max all-reduce (hr-weno_b200/slab.py: global_max_wavespeed, NCCL).
+// Non-negative doubles order like their bit patterns, so the grid-wide maximum is one integer atomicMax per CTA.
+// ------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) max_abs_kernel(const double *__restrict__ v, int64_t n, unsigned long long *out) {
+   double m = 0.0;
+   const int64_t tid = blockIdx.x * (int64_t)blockDim.x + threadIdx.x, nth = (int64_t)gridDim.x * blockDim.x;
+   const bool vec = (reinterpret_cast<uintptr_t>(v) & 15u) == 0;
+   if (vec) {
+      const double2 *v2 = reinterpret_cast<const double2 *>(v);
+      for (int64_t i = tid; i < n / 2; i += nth) {
+         const double2 t = __ldg(v2 + i);
+         m = fmax(m, fmax(fabs(t.x), fabs(t.y))); // fmax drops a NaN operand, as Fortran's maxval(abs(v)) does not: see the header
+      }
+      if (tid == 0 && (n & 1)) m = fmax(m, fabs(v[n - 1]));
+   } else {
+      for (int64_t i = tid; i < n; i += nth) m = fmax(m, fabs(__ldg(v + i)));
+   }
+#pragma unroll
+   for (int o = 16; o > 0; o >>= 1) m = fmax(m, __shfl_xor_sync(0xffffffffu, m, o));
+   __shared__ double s_m[8];
+   if ((threadIdx.x & 31) == 0) s_m[threadIdx.x >> 5] = m;
+   __syncthreads();
+   if (threadIdx.x < 8) {
+      m = s_m[threadIdx.x];
+#pragma unroll
+      for (int o = 4; o > 0; o >>= 1) m = fmax(m, __shfl_xor_sync(0xffu, m, o));
+      if (threadIdx.x == 0) atomicMax(out, (unsigned long long)__double_as_longlong(m));
+   }
+}
+
+int fv_max_wavespeed(Fv *fv, const double *v_dev, double *out_dev, cudaStream_t st) {
+   const hrweno_fv_desc &d = fv->d;
+   if (d.flux_model == HRWENO_FLUX_LINEAR) {
+      const double a = d.ndim == 2 ? fmax(fabs(d.flux_coef[0]), fabs(d.flux_coef[1])) : fabs(d.flux_coef[0]);
+      HRW_CUDA(cudaMemcpyAsync(out_dev, &a, sizeof(double), cudaMemcpyHostToDevice, st));
+      HRW_CUDA(cudaStreamSynchronize(st)); // `a` lives on this stack frame
+      return HRWENO_OK;
+   }
+   HRW_CUDA(cudaMemsetAsync(out_dev, 0, sizeof(double), st));
+   int64_t blocks = (fv->neq / 2 + 255) / 256;
+   blocks = blocks < 1 ? 1 : (blocks > 148 * 8 ? 148 * 8 : blocks);
+   max_abs_kernel<<<(unsigned)blocks, 256, 0, st>>>(v_dev, fv->neq, reinterpret_cast<unsigned long long *>(out_dev));
+   fv->launches++;
+   HRW_CUDA(cudaGetLastError());
+   return HRWENO_OK;
+}
+
+// ------------------------------------------------------------------------------------------------
 // stage dispatch
 // ------------------------------------------------------------------------------------------------
 int fv1d_launch_k1_m0(int, int, int, int, const Fv1dGeom &, const StageArgs &, cudaStream_t);

@@ -103,6 +103,7 @@ int fv_unpack(Fv *fv, const double *padded_cell0, double *dense_dev, cudaStream_
 int fv_stage(Fv *fv, int combine, const StageArgs &args, cudaStream_t st);
 // 1D tiling of the current configuration: cells per tile and tiles per row
 void fv_tiling_1d(const Fv *fv, int *tile_cells, int *tiles_per_row);
+int fv_max_wavespeed(Fv *fv, const double *v_dev, double *out_dev, cudaStream_t st);
 // fv1d_small.cu: whole integrate call of a small 1D problem (<= 1024 cells) in one single-CTA launch
 bool fv_small_eligible(const Fv *fv);
 int fv_small_integrate(Fv *fv, double *u_dev, int order, long long nsteps, double dt, cudaStream_t st);

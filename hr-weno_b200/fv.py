@@ -77,6 +77,14 @@ class FV:
     def rhs_dev(self, t, v_ptr, out_ptr, stream=None):
         _abi.check(_abi.lib().hrweno_fv_rhs_dev(self._h, t, v_ptr, out_ptr, stream))
 
+    def max_wavespeed_dev(self, v_ptr, out_ptr, stream=None):
+        """extension: local max |f'(v)| of the dense device vector at v_ptr into the device scalar at out_ptr (async)"""
+        _abi.check(_abi.lib().hrweno_fv_max_wavespeed_dev(self._h, v_ptr, out_ptr, stream))
+
+    def set_alpha(self, alpha):
+        """extension: Lax-Friedrichs alpha used from the next stage launch on (fluxes.f90:40 takes it per call)"""
+        _abi.check(_abi.lib().hrweno_fv_set_alpha(self._h, float(alpha)))
+
     def export_halo(self):
         buf = C.create_string_buffer(_abi.IPC_HANDLE_BYTES)
         _abi.check(_abi.lib().hrweno_fv_export_halo(self._h, buf))

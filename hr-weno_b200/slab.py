@@ -45,3 +45,26 @@ def torch_all_gather(world):
         return out
 
     return gather
+
+
+def reduce_alpha(local_max, nranks):
+    """max over ranks of a one-element float64 tensor (NCCL for CUDA tensors, gloo for CPU ones) -> float"""
+    import torch.distributed as dist
+
+    if nranks > 1:
+        dist.all_reduce(local_max, op=dist.ReduceOp.MAX)
+    return float(local_max.item())
+
+
+def global_max_wavespeed(fv, u_dev, nranks, device_scalar=None):
+    """Extension (BASELINE north star; the reference has a caller-supplied alpha and no reduction): the Lax-Friedrichs
+    alpha = max |f'(u)| over ALL slabs.  The local maximum is reduced on the GPU (csrc/fv.cu: max_abs_kernel), the ranks
+    combine their scalars with ONE max all-reduce on the device (torch.distributed, NCCL on GPUs) and the result is
+    installed with fv.set_alpha().  `u_dev` is a torch CUDA tensor holding this rank's dense state."""
+    import torch
+
+    out = device_scalar if device_scalar is not None else torch.zeros(1, dtype=torch.float64, device=u_dev.device)
+    fv.max_wavespeed_dev(u_dev.data_ptr(), out.data_ptr(), torch.cuda.current_stream().cuda_stream)
+    alpha = reduce_alpha(out, nranks)
+    fv.set_alpha(alpha)
+    return alpha

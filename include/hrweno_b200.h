@@ -159,6 +159,13 @@ int hrweno_fv_rhs_dev(hrweno_fv *fv, double t, const double *v_dev, double *vdot
 /* multi-GPU plumbing: each rank exports a 64-byte CUDA IPC handle of its halo mailbox and
  * imports the handles of its left/right neighbours (NULL at a physical boundary). */
 #define HRWENO_IPC_HANDLE_BYTES 64
+/* Extension (the reference takes the Lax-Friedrichs alpha from the caller, fluxes.f90:40, and has no reduction):
+ * max |f'(v)| over this rank's cells of the dense device vector v_dev, written to the device scalar out_dev,
+ * asynchronous on `stream` (Burgers: max|v|; linear flux: max|a|).  NaN cells are ignored.  Ranks combine their values
+ * with one max all-reduce (hr-weno_b200/slab.py: global_max_wavespeed) and pass the result to hrweno_fv_set_alpha,
+ * which takes effect from the next stage launch.  Off in every parity run: results then depend on alpha's history. */
+int hrweno_fv_max_wavespeed_dev(hrweno_fv *fv, const double *v_dev, double *out_dev, void *stream);
+int hrweno_fv_set_alpha(hrweno_fv *fv, double alpha);
 int hrweno_fv_export_halo(hrweno_fv *fv, void *handle_out);
 int hrweno_fv_import_halo(hrweno_fv *fv, const void *left_handle, const void *right_handle);
 /* synchronises the device and reports HRWENO_ECOMM if a halo wait timed out (a neighbour rank died) */

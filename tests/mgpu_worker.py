@@ -110,6 +110,27 @@ def main():
             print(f"[rank {rank}] FAIL 1D fast n={nglob} k={k}: slab vs single-domain max|d|={np.max(np.abs(u - ug[off:off + n])):.3e}, drift {drift:.3e}", flush=True)
         dist.barrier()
 
+    # ---- adaptive Lax-Friedrichs alpha (extension): device reduction per rank + ONE NCCL max all-reduce ---------------
+    nglob = 50001
+    off, n = pkg.slab.partition(nglob, world, rank)
+    g = pkg.hrweno_grids.grid1().linear(-5.0, 5.0, nglob)
+    u0 = ex1_ic(g.center) + 1e-3 * np.random.default_rng(3).standard_normal(nglob)
+    fv = pkg.fv.FV(pkg.fv.make_desc(n, k=3, flux_scheme=1, alpha=1.0, linear=(-5.0, 5.0), rank=rank, nranks=world, global_n=nglob,
+                                    global_offset=off))
+    pkg.slab.connect(fv, rank, world, gather)
+    ud = torch.from_numpy(np.ascontiguousarray(u0[off:off + n])).cuda()
+    alpha = pkg.slab.global_max_wavespeed(fv, ud, world)
+    ode = pkg.hrweno_tvdode.rktvd(fv, n, 3)
+    rode = ref.rktvd(ref.FV(pkg.fv.make_desc(nglob, k=3, flux_scheme=1, alpha=alpha, width=[g.width])), 3)
+    u, ur = u0[off:off + n].copy(), u0.copy()  # copies: integrate works in place
+    dt = 0.2 * 10.0 / nglob
+    ode.integrate(u, 0.0, 10 * dt, dt)
+    rode.integrate(ur, 0.0, 10 * dt, dt)
+    if not (alpha == float(np.max(np.abs(u0))) and np.array_equal(u, ur[off:off + n])):
+        fails += 1
+        print(f"[rank {rank}] FAIL adaptive alpha: {alpha!r} vs {float(np.max(np.abs(u0)))!r}", flush=True)
+    dist.barrier()
+
     tot = torch.tensor([fails], device="cuda")
     dist.all_reduce(tot)
     if rank == 0:

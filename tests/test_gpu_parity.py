@@ -473,3 +473,43 @@ def test_rktvd_fused_tiled_path_bitwise(gpu_lib, pkg, ref, k, order):
         tr = rode.integrate(ur, tr, tout, 5e-4)
         assert t == tr and np.array_equal(u, ur)
     assert ode.fevals == rode.fevals
+
+
+# ---- adaptive Lax-Friedrichs alpha (extension, K5) ---------------------------------------------------------
+@pytest.mark.parametrize("nc", [2, 3, 7, 4096, 100003])
+def test_max_wavespeed_matches_numpy(gpu_lib, pkg, nc):
+    """local max |f'(v)|: Burgers -> max|v| (odd/even sizes, unaligned pointer, NaN cells ignored); linear -> |a|"""
+    import torch
+
+    rng = np.random.default_rng(nc)
+    v = rng.standard_normal(nc + 1)
+    g = pkg.hrweno_grids.grid1().linear(-5.0, 5.0, nc)
+    fv = pkg.fv.FV(pkg.fv.make_desc(nc, k=3, flux_scheme=1, alpha=1.0, width=[g.width]))
+    buf = torch.from_numpy(v).cuda()
+    out = torch.full((1,), -1.0, dtype=torch.float64, device="cuda")
+    for shift in (0, 1):
+        fv.max_wavespeed_dev(buf.data_ptr() + 8 * shift, out.data_ptr())
+        torch.cuda.synchronize()
+        assert float(out.item()) == np.max(np.abs(v[shift:shift + nc]))
+    fvl = pkg.fv.FV(pkg.fv.make_desc(nc, k=3, flux_model=1, flux_coef=(-2.5, 1.0), width=[g.width]))
+    fvl.max_wavespeed_dev(buf.data_ptr(), out.data_ptr())
+    torch.cuda.synchronize()
+    assert float(out.item()) == 2.5
+
+
+def test_set_alpha_takes_effect_and_matches_oracle(gpu_lib, pkg, ref):
+    """alpha installed with set_alpha (from the device reduction) gives the oracle's Lax-Friedrichs rhs for that alpha"""
+    import torch
+
+    nc = 3000
+    g = pkg.hrweno_grids.grid1().linear(-5.0, 5.0, nc)
+    v = ex1_ic(g.center) + 1e-3 * np.random.default_rng(9).standard_normal(nc)
+    fv = pkg.fv.FV(pkg.fv.make_desc(nc, k=3, flux_scheme=1, alpha=0.25, width=[g.width]))
+    vd = torch.from_numpy(v).cuda()
+    alpha = pkg.slab.global_max_wavespeed(fv, vd, 1)
+    assert alpha == np.max(np.abs(v))
+    got = fv.rhs(0.0, v)
+    want = ref.FV(pkg.fv.make_desc(nc, k=3, flux_scheme=1, alpha=alpha, width=[g.width])).rhs(0.0, v)
+    assert np.array_equal(got, want)
+    with pytest.raises(pkg._abi.HrwenoError):
+        fv.set_alpha(-1.0)

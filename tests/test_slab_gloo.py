@@ -67,6 +67,11 @@ def _worker(rank, world, port, q):
     part = ref.FV(pkg.fv.make_desc(len(ext), k=k, width=[wext])).rhs(0.0, ext)[len(lo):len(lo) + nl]
     # interior faces only: the artificial ends of the extended slab use the copy rule, k cells away from our cells
     out["halo_k_bitwise"] = bool(np.array_equal(part, full[off:off + nl]))
+    # the alpha all-reduce of the adaptive Lax-Friedrichs extension: max over ranks of the local max |f'(u)|
+    import torch
+
+    out["alpha"] = pkg.slab.reduce_alpha(torch.tensor([np.max(np.abs(mine))], dtype=torch.float64), world)
+    out["alpha_want"] = float(np.max(np.abs(u)))
     q.put((rank, out))
     dist.barrier()
     dist.destroy_process_group()
@@ -97,3 +102,4 @@ def test_world_size_2_gloo(pkg):
     assert res[1]["imported"] == (bytes([0]) * 64, None)
     for r in range(world):
         assert res[r]["ic_edges_match"] and res[r]["halo_k_bitwise"]
+        assert res[r]["alpha"] == res[r]["alpha_want"]
