@@ -109,6 +109,23 @@ module hrweno_b200_c
          integer(c_int), value :: order
          integer(c_int) :: st
       end function
+      function hrweno_rktvd_create_host(out, fu, ctx, neq, order) bind(c, name="hrweno_rktvd_create_host") result(st)
+         import :: c_ptr, c_funptr, c_int, c_int64_t
+         type(c_ptr), intent(out) :: out
+         type(c_funptr), value :: fu
+         type(c_ptr), value :: ctx
+         integer(c_int64_t), value :: neq
+         integer(c_int), value :: order
+         integer(c_int) :: st
+      end function
+      function hrweno_mstvd_create_host(out, fu, ctx, neq) bind(c, name="hrweno_mstvd_create_host") result(st)
+         import :: c_ptr, c_funptr, c_int, c_int64_t
+         type(c_ptr), intent(out) :: out
+         type(c_funptr), value :: fu
+         type(c_ptr), value :: ctx
+         integer(c_int64_t), value :: neq
+         integer(c_int) :: st
+      end function
       function hrweno_mstvd_create(out, fu, ctx, neq) bind(c, name="hrweno_mstvd_create") result(st)
          import :: c_ptr, c_funptr, c_int, c_int64_t
          type(c_ptr), intent(out) :: out
@@ -244,15 +261,33 @@ contains
 end module hrweno_weno
 
 module hrweno_tvdode
-!! Drop-in for src/hrweno_tvdode.f90 (rktvd, mstvd; tvdode.f90:36-48,59-65).  Two constructors each:
-!! the reference's `rktvd(fu, neq, order)` / `mstvd(fu, neq)` with a user integrand, and the fused
-!! `rktvd(fv, order)` / `mstvd(fv)` where `fv` is a hrweno_fv handle describing the example rhs.
+!! Drop-in for src/hrweno_tvdode.f90 (rktvd, mstvd; tvdode.f90:36-48,59-65).  Constructors:
+!!  * the reference's own `rktvd(fu, neq, order)` / `mstvd(fu, neq)` with the reference's HOST integrand
+!!    `fu(t, u(:), udot(:))` (tvdode.f90:50-57): an unmodified program (its rhs calling w%reconstruct and godunov)
+!!    links and runs; the state and the stage combinations live on the GPU, u/udot are staged around every call;
+!!  * the fused `rktvd(fv, neq, order)` / `mstvd(fv, neq)` where `fv` is a hrweno_fv handle describing the example rhs
+!!    (one kernel per stage, the fast path);
+!!  * `rktvd_dev(fu_dev, neq, order)` / `mstvd_dev(fu_dev, neq)` for an integrand that works on device pointers.
    use, intrinsic :: iso_c_binding
    use hrweno_kinds, only: rk
    use hrweno_b200_c
    implicit none
    private
-   public :: rktvd, mstvd, integrand_dev
+   public :: rktvd, mstvd, rktvd_dev, mstvd_dev, integrand, integrand_dev
+
+   abstract interface
+      subroutine integrand(t, u, udot)
+         !! the reference's interface, unchanged (tvdode.f90:50-57)
+         import :: rk
+         real(rk), intent(in) :: t, u(:)
+         real(rk), intent(out) :: udot(:)
+      end subroutine
+   end interface
+
+   type :: integrand_holder
+      !! keeps the user's procedure alive behind the C callback's context pointer
+      procedure(integrand), pointer, nopass :: fu => null()
+   end type
 
    abstract interface
       subroutine integrand_dev(ctx, t, neq, u_dev, udot_dev, stream) bind(c)
@@ -270,6 +305,7 @@ module hrweno_tvdode
       integer :: order
       character(:), allocatable :: msg
       type(c_ptr) :: handle = c_null_ptr
+      type(integrand_holder), pointer :: holder => null()
    contains
       procedure, pass(self) :: fevals => tvdode_fevals   ! a function now: the counter lives in the C object
       procedure, pass(self) :: istate => tvdode_istate
@@ -291,7 +327,30 @@ module hrweno_tvdode
 
 contains
 
+   subroutine host_trampoline(ctx, t, neq, u, udot) bind(c)
+      !! hrweno_rhs_host_fn: hands the library's pinned staging arrays to the user's assumed-shape integrand
+      type(c_ptr), value :: ctx
+      real(c_double), value :: t
+      integer(c_int64_t), value :: neq
+      real(c_double), intent(in) :: u(*)
+      real(c_double), intent(out) :: udot(*)
+      type(integrand_holder), pointer :: h
+      call c_f_pointer(ctx, h)
+      call h%fu(real(t, rk), u(1:neq), udot(1:neq))
+   end subroutine
+
    type(rktvd) function rktvd_init(fu, neq, order) result(self)
+      !! tvdode.f90:69-95, same argument list
+      procedure(integrand) :: fu
+      integer, intent(in) :: neq, order
+      self%neq = neq; self%order = order
+      allocate (self%holder)
+      self%holder%fu => fu
+      call created(self, hrweno_rktvd_create_host(self%handle, c_funloc(host_trampoline), c_loc(self%holder), &
+                                                  int(neq, c_int64_t), int(order, c_int)))
+   end function
+
+   type(rktvd) function rktvd_dev(fu, neq, order) result(self)
       procedure(integrand_dev) :: fu
       integer, intent(in) :: neq, order
       self%neq = neq; self%order = order
@@ -306,6 +365,16 @@ contains
    end function
 
    type(mstvd) function mstvd_init(fu, neq) result(self)
+      !! tvdode.f90:180-201, same argument list
+      procedure(integrand) :: fu
+      integer, intent(in) :: neq
+      self%neq = neq; self%order = 3
+      allocate (self%holder)
+      self%holder%fu => fu
+      call created(self, hrweno_mstvd_create_host(self%handle, c_funloc(host_trampoline), c_loc(self%holder), int(neq, c_int64_t)))
+   end function
+
+   type(mstvd) function mstvd_dev(fu, neq) result(self)
       procedure(integrand_dev) :: fu
       integer, intent(in) :: neq
       self%neq = neq; self%order = 3
@@ -356,6 +425,7 @@ contains
       class(tvdode), intent(inout) :: self
       call hrweno_ode_destroy(self%handle)
       self%handle = c_null_ptr
+      if (associated(self%holder)) deallocate (self%holder)
    end subroutine
 
 end module hrweno_tvdode

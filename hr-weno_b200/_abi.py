@@ -54,6 +54,7 @@ class FvDesc(C.Structure):
 
 FLUX_FN = C.CFUNCTYPE(C.c_double, C.c_void_p, C.c_double, c_double_p, C.c_int, C.c_double)
 RHS_FN = C.CFUNCTYPE(None, C.c_void_p, C.c_double, C.c_int64, C.c_void_p, C.c_void_p, C.c_void_p)
+RHS_HOST_FN = C.CFUNCTYPE(None, C.c_void_p, C.c_double, C.c_int64, c_double_p, c_double_p)
 
 # name -> (restype, argtypes); this table is also what the symbol-export test walks
 PROTOTYPES = {
@@ -98,6 +99,8 @@ PROTOTYPES = {
     "hrweno_fv_halo_status": (C.c_int, [C.c_void_p]),
     "hrweno_rktvd_create": (C.c_int, [C.POINTER(C.c_void_p), RHS_FN, C.c_void_p, C.c_int64, C.c_int]),
     "hrweno_mstvd_create": (C.c_int, [C.POINTER(C.c_void_p), RHS_FN, C.c_void_p, C.c_int64]),
+    "hrweno_rktvd_create_host": (C.c_int, [C.POINTER(C.c_void_p), RHS_HOST_FN, C.c_void_p, C.c_int64, C.c_int]),
+    "hrweno_mstvd_create_host": (C.c_int, [C.POINTER(C.c_void_p), RHS_HOST_FN, C.c_void_p, C.c_int64]),
     "hrweno_rktvd_create_fused": (C.c_int, [C.POINTER(C.c_void_p), C.c_void_p, C.c_int]),
     "hrweno_mstvd_create_fused": (C.c_int, [C.POINTER(C.c_void_p), C.c_void_p]),
     "hrweno_ode_destroy": (None, [C.c_void_p]),

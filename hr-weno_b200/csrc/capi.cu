@@ -24,6 +24,7 @@ int cuda_fail(cudaError_t e, const char *what, const char *file, int line) {
 
 int weno_create(Weno **out, int64_t ncells, int k, double eps, const double *xedges);
 int ode_create(Ode **out, bool is_ms, Fv *fv, hrweno_rhs_fn fu, void *ctx, int64_t neq, int order);
+int ode_create_host(Ode **out, bool is_ms, hrweno_rhs_host_fn fu, void *ctx, int64_t neq, int order);
 int ode_integrate_dev(Ode *o, double *u_dev, double *t, double tout, double dt, int itask, cudaStream_t st);
 int ode_integrate_host(Ode *o, double *u, double *t, double tout, double dt, int itask);
 
@@ -241,6 +242,12 @@ int hrweno_rktvd_create(hrweno_ode **out, hrweno_rhs_fn fu, void *ctx, int64_t n
 }
 int hrweno_mstvd_create(hrweno_ode **out, hrweno_rhs_fn fu, void *ctx, int64_t neq) {
    return ode_create(reinterpret_cast<Ode **>(out), true, nullptr, fu, ctx, neq, 3);
+}
+int hrweno_rktvd_create_host(hrweno_ode **out, hrweno_rhs_host_fn fu, void *ctx, int64_t neq, int order) {
+   return ode_create_host(reinterpret_cast<Ode **>(out), false, fu, ctx, neq, order);
+}
+int hrweno_mstvd_create_host(hrweno_ode **out, hrweno_rhs_host_fn fu, void *ctx, int64_t neq) {
+   return ode_create_host(reinterpret_cast<Ode **>(out), true, fu, ctx, neq, 3);
 }
 int hrweno_rktvd_create_fused(hrweno_ode **out, hrweno_fv *fv, int order) {
    if (!fv) return fail(HRWENO_EINVAL, "null fv handle");

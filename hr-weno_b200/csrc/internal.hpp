@@ -146,6 +146,12 @@ struct Ode {
    Fv *fv = nullptr;
    hrweno_rhs_fn fu = nullptr;
    void *ctx = nullptr;
+   // the reference's integrand as it is: a HOST procedure on host arrays (tvdode.f90:50-57), reached through an
+   // adapter that stages u and udot in pinned memory around every call
+   hrweno_rhs_host_fn fu_host = nullptr;
+   void *ctx_host = nullptr;
+   double *h_u = nullptr, *h_udot = nullptr;
+   int cb_status = HRWENO_OK;
    int64_t neq = 0;
    int order = 3;
    int64_t fevals = 0;

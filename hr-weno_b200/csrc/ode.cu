@@ -17,6 +17,8 @@ namespace hrw {
 static inline bool is_done(double t, double tout, double dt) { return (t - tout) * std::copysign(1.0, dt) > 0.0; }
 
 Ode::~Ode() {
+   cudaFreeHost(h_u);
+   cudaFreeHost(h_udot);
    for (double *p : bufs) cudaFree(p);
    for (cudaEvent_t e : ev_in) cudaEventDestroy(e);
    for (cudaEvent_t e : ev_fin) cudaEventDestroy(e);
@@ -321,10 +323,44 @@ static int ms_integrate(Ode *o, double *u_dev, double *t, double tout, double dt
    return HRWENO_OK;
 }
 
+// host integrand behind the device-callback machinery: D2H u, the user's procedure, H2D udot.  The stage combinations
+// (K6) and the state stay on the device; what runs on the host is the caller's own code, as in the reference.
+static void host_integrand_adapter(void *ctx, double t, int64_t neq, const double *u_dev, double *udot_dev, void *stream) {
+   Ode *o = static_cast<Ode *>(ctx);
+   cudaStream_t st = static_cast<cudaStream_t>(stream);
+   const size_t bytes = (size_t)neq * sizeof(double);
+   cudaError_t e = cudaMemcpyAsync(o->h_u, u_dev, bytes, cudaMemcpyDeviceToHost, st);
+   if (e == cudaSuccess) e = cudaStreamSynchronize(st);
+   if (e == cudaSuccess) {
+      o->fu_host(o->ctx_host, t, neq, o->h_u, o->h_udot);
+      e = cudaMemcpyAsync(udot_dev, o->h_udot, bytes, cudaMemcpyHostToDevice, st);
+   }
+   if (e != cudaSuccess && o->cb_status == HRWENO_OK) o->cb_status = cuda_fail(e, "host integrand staging", __FILE__, __LINE__);
+}
+
+int ode_create_host(Ode **out, bool is_ms, hrweno_rhs_host_fn fu, void *ctx, int64_t neq, int order) {
+   if (!fu) return fail(HRWENO_EINVAL, "ode create: no integrand");
+   HRW_TRY(ode_create(out, is_ms, nullptr, host_integrand_adapter, nullptr, neq, order));
+   Ode *o = *out;
+   o->ctx = o; // the adapter's context is the object itself
+   o->fu_host = fu;
+   o->ctx_host = ctx;
+   const size_t bytes = (size_t)neq * sizeof(double);
+   cudaError_t e = cudaMallocHost(&o->h_u, bytes);
+   if (e == cudaSuccess) e = cudaMallocHost(&o->h_udot, bytes);
+   if (e != cudaSuccess) {
+      delete o;
+      *out = nullptr;
+      return cuda_fail(e, "pinned staging for the host integrand", __FILE__, __LINE__);
+   }
+   return HRWENO_OK;
+}
+
 int ode_integrate_dev(Ode *o, double *u_dev, double *t, double tout, double dt, int itask, cudaStream_t st) {
    if (!o || !u_dev || !t) return fail(HRWENO_EINVAL, "integrate: null argument");
-   if (o->is_ms) return ms_integrate(o, u_dev, t, tout, dt, st);
-   return rk_integrate(o, u_dev, t, tout, dt, itask, st);
+   const int s = o->is_ms ? ms_integrate(o, u_dev, t, tout, dt, st) : rk_integrate(o, u_dev, t, tout, dt, itask, st);
+   if (s == HRWENO_OK && o->cb_status != HRWENO_OK) return o->cb_status; // a host-integrand staging copy failed
+   return s;
 }
 
 // ------------------------------------------------------------------------------------------------

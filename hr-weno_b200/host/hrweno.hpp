@@ -170,6 +170,8 @@ class fv {
 namespace hrweno_tvdode {
 // integrand(t, u(:), udot(:)) with device-resident u/udot (tvdode.f90:50-57)
 using integrand = std::function<void(double t, int64_t neq, const double *u_dev, double *udot_dev, void *stream)>;
+// the reference's integrand as it is: host arrays (the library stages u and udot in pinned memory around every call)
+using host_integrand = std::function<void(double t, int64_t neq, const double *u, double *udot)>;
 
 class tvdode { // tvdode.f90:14-34
  public:
@@ -185,6 +187,10 @@ class tvdode { // tvdode.f90:14-34
    tvdode() = default;
    hrweno_ode *h_ = nullptr;
    integrand fu_;
+   host_integrand fu_host_;
+   static void tramp_host(void *ctx, double t, int64_t n, const double *u, double *udot) {
+      static_cast<tvdode *>(ctx)->fu_host_(t, n, u, udot);
+   }
    static void tramp(void *ctx, double t, int64_t n, const double *u, double *udot, void *stream) {
       static_cast<tvdode *>(ctx)->fu_(t, n, u, udot, stream);
    }
@@ -202,6 +208,10 @@ class rktvd : public tvdode { // rktvd(fu, neq, order), tvdode.f90:69-95
       fu_ = std::move(fu);
       created(hrweno_rktvd_create(&h_, &tvdode::tramp, this, neq, order));
    }
+   rktvd(host_integrand fu, int64_t neq, int order) { // the reference's own call: a host integrand
+      fu_host_ = std::move(fu);
+      created(hrweno_rktvd_create_host(&h_, &tvdode::tramp_host, this, neq, order));
+   }
    rktvd(hrweno_fv::fv &rhs, int64_t neq, int order) { // fused path: rhs + stage combination in one kernel
       if (neq != rhs.neq()) throw hrweno::error(HRWENO_EINVAL, "neq does not match the finite-volume operator");
       created(hrweno_rktvd_create_fused(&h_, rhs.handle(), order));
@@ -214,6 +224,10 @@ class rktvd : public tvdode { // rktvd(fu, neq, order), tvdode.f90:69-95
 
 class mstvd : public tvdode { // mstvd(fu, neq), tvdode.f90:180-201
  public:
+   mstvd(host_integrand fu, int64_t neq) { // the reference's own call: a host integrand
+      fu_host_ = std::move(fu);
+      created(hrweno_mstvd_create_host(&h_, &tvdode::tramp_host, this, neq));
+   }
    mstvd(integrand fu, int64_t neq) {
       fu_ = std::move(fu);
       created(hrweno_mstvd_create(&h_, &tvdode::tramp, this, neq));

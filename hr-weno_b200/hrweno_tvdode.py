@@ -70,17 +70,32 @@ def _wrap_rhs(fu):
     return _abi.RHS_FN(cb)
 
 
-class rktvd(_tvdode):
-    """``rktvd(fu, neq, order)`` (tvdode.f90:69-95).  `fu` is either an FV operator (fused path) or a
-    callable fu(t, neq, u_dev_ptr, udot_dev_ptr, stream) working on device memory."""
+def _wrap_host_rhs(fu):
+    """the reference's integrand `fu(t, u(:), udot(:))` (tvdode.f90:50-57) on host arrays: fu(t, u, udot) fills udot"""
 
-    def __init__(self, fu, neq, order):
+    def cb(_ctx, t, neq, u_ptr, udot_ptr):
+        u = np.ctypeslib.as_array(u_ptr, shape=(neq,))
+        udot = np.ctypeslib.as_array(udot_ptr, shape=(neq,))
+        fu(t, u, udot)
+
+    return _abi.RHS_HOST_FN(cb)
+
+
+class rktvd(_tvdode):
+    """``rktvd(fu, neq, order)`` (tvdode.f90:69-95).  `fu` is an FV operator (fused path), a host integrand
+    fu(t, u, udot) on NumPy arrays as in the reference (``host=True``), or a callable
+    fu(t, neq, u_dev_ptr, udot_dev_ptr, stream) working on device memory."""
+
+    def __init__(self, fu, neq, order, host=False):
         super().__init__()
         if isinstance(fu, FV):
             if neq != fu.neq:
                 raise _abi.HrwenoError(_abi.EINVAL, "neq does not match the FV operator")
             self._fv = fu
             self._created(_abi.lib().hrweno_rktvd_create_fused(C.byref(self._h), fu._h, order))
+        elif host:
+            self._cb = _wrap_host_rhs(fu)
+            self._created(_abi.lib().hrweno_rktvd_create_host(C.byref(self._h), self._cb, None, neq, order))
         else:
             self._cb = _wrap_rhs(fu)
             self._created(_abi.lib().hrweno_rktvd_create(C.byref(self._h), self._cb, None, neq, order))
@@ -89,13 +104,16 @@ class rktvd(_tvdode):
 class mstvd(_tvdode):
     """``mstvd(fu, neq)`` (tvdode.f90:180-201)"""
 
-    def __init__(self, fu, neq):
+    def __init__(self, fu, neq, host=False):
         super().__init__()
         if isinstance(fu, FV):
             if neq != fu.neq:
                 raise _abi.HrwenoError(_abi.EINVAL, "neq does not match the FV operator")
             self._fv = fu
             self._created(_abi.lib().hrweno_mstvd_create_fused(C.byref(self._h), fu._h))
+        elif host:
+            self._cb = _wrap_host_rhs(fu)
+            self._created(_abi.lib().hrweno_mstvd_create_host(C.byref(self._h), self._cb, None, neq))
         else:
             self._cb = _wrap_rhs(fu)
             self._created(_abi.lib().hrweno_mstvd_create(C.byref(self._h), self._cb, None, neq))

@@ -178,6 +178,13 @@ int hrweno_fv_halo_status(hrweno_fv *fv);
 typedef void (*hrweno_rhs_fn)(void *ctx, double t, int64_t neq, const double *u_dev, double *udot_dev,
                               void *stream);
 
+/* the reference's integrand exactly as it is (tvdode.f90:50-57): a HOST procedure on HOST arrays.  The state and the
+ * stage combinations stay on the device; u is copied to pinned host memory before every call and udot back after it,
+ * so a reference program runs unchanged (its rhs calling weno%reconstruct and godunov), only slower than the fused path. */
+typedef void (*hrweno_rhs_host_fn)(void *ctx, double t, int64_t neq, const double *u, double *udot);
+int hrweno_rktvd_create_host(hrweno_ode **out, hrweno_rhs_host_fn fu, void *ctx, int64_t neq, int order);
+int hrweno_mstvd_create_host(hrweno_ode **out, hrweno_rhs_host_fn fu, void *ctx, int64_t neq);
+
 /* rktvd_init (tvdode.f90:69-95): neq >= 1, 1 <= order <= 3 */
 int hrweno_rktvd_create(hrweno_ode **out, hrweno_rhs_fn fu, void *ctx, int64_t neq, int order);
 /* mstvd_init (tvdode.f90:180-201) */

@@ -513,3 +513,66 @@ def test_set_alpha_takes_effect_and_matches_oracle(gpu_lib, pkg, ref):
     assert np.array_equal(got, want)
     with pytest.raises(pkg._abi.HrwenoError):
         fv.set_alpha(-1.0)
+
+
+# ---- the reference's host integrand, unchanged (tvdode.f90:50-57) --------------------------------------------
+A_TVD = np.array([-1.0 + float(ii - 1) * 4 / 9 for ii in range(1, 11)])  # test_tvdode.f90:15
+
+
+@pytest.mark.parametrize("order,rtol", [(1, 2e-2), (2, 1e-3), (3, 1e-3)])
+def test_rktvd_host_integrand_reference_test(gpu_lib, pkg, order, rtol):
+    """test/test_tvdode.f90:31-70 as written there: u' = a*u with the HOST integrand `fu(t, u, udot)`, nu = 10,
+    t0 = -1.3, tout = 1.5, dt = (tout-t0)/3000, through rktvd(fu, nu, order); the reference's tolerances, and bitwise
+    against the NumPy driver of the same steps (3001 steps)"""
+    from oracle import np_oracle
+
+    def fu(t, u, udot):
+        udot[:] = A_TVD * u
+
+    t0, tout = -1.3, 1.5
+    dt = (tout - t0) / 3000
+    ode = pkg.hrweno_tvdode.rktvd(fu, 10, order, host=True)
+    u = np.full(10, 0.1)
+    t = ode.integrate(u, t0, tout, dt)
+    np.testing.assert_allclose(u, 0.1 * np.exp(A_TVD * (t - t0)), rtol=rtol)
+    ur, tr = np_oracle.RK(lambda t_, u_: A_TVD * u_, order).integrate(np.full(10, 0.1), t0, tout, dt)
+    assert t == tr and np.array_equal(u, ur) and ode.fevals == 3001 * order
+
+
+def test_mstvd_host_integrand_reference_test(gpu_lib, pkg):
+    """test/test_tvdode.f90:72-104: mstvd(fu, nu) with the host integrand, dt = 1e-3, rtol 1e-3; bitwise vs the NumPy driver"""
+    from oracle import np_oracle
+
+    def fu(t, u, udot):
+        udot[:] = A_TVD * u
+
+    ode = pkg.hrweno_tvdode.mstvd(fu, 10, host=True)
+    u = np.full(10, 0.1)
+    t = ode.integrate(u, -1.3, 1.5, 1e-3)
+    np.testing.assert_allclose(u, 0.1 * np.exp(A_TVD * (t + 1.3)), rtol=1e-3)
+    ur, tr = np_oracle.MS(lambda t_, u_: A_TVD * u_).integrate(np.full(10, 0.1), -1.3, 1.5, 1e-3)
+    assert t == tr and np.array_equal(u, ur)
+
+
+def test_example1_with_unchanged_host_rhs_equals_fused(gpu_lib, pkg, ref):
+    """example1 as a reference user writes it: a HOST rhs calling w%reconstruct and godunov per face (example1:72-109),
+    handed to rktvd(rhs, nc, 3).  Must equal the fused path (and so the oracle) bit for bit."""
+    nc = 100
+    g = pkg.hrweno_grids.grid1().linear(-5.0, 5.0, nc)
+    w = pkg.hrweno_weno.weno(nc, 3, 1e-6)
+    flux = lambda v, x, t: (v ** 2) / 2  # noqa: E731  example1:120
+
+    def rhs(t, v, vdot):
+        vl, vr = w.reconstruct(np.ascontiguousarray(v))
+        fed = np.empty(nc + 1)
+        for i in range(1, nc):
+            fed[i] = pkg.hrweno_fluxes.godunov(flux, vr[i - 1], vl[i], [g.right[i - 1]], t)
+        fed[0], fed[nc] = fed[1], fed[nc - 1]
+        vdot[:] = -(fed[1:] - fed[:-1]) / g.width
+
+    ode = pkg.hrweno_tvdode.rktvd(rhs, nc, 3, host=True)
+    fused = pkg.hrweno_tvdode.rktvd(pkg.fv.FV(pkg.fv.make_desc(nc, k=3, eps=1e-6, width=[g.width])), nc, 3)
+    u, uf, t, tf = ex1_ic(g.center), ex1_ic(g.center), 0.0, 0.0
+    for tout in (0.05, 0.12):
+        t, tf = ode.integrate(u, t, tout, 1e-2), fused.integrate(uf, tf, tout, 1e-2)
+        assert t == tf and np.array_equal(u, uf)
