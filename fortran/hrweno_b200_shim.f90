@@ -87,6 +87,22 @@ module hrweno_b200_c
          real(c_double), intent(out) :: vdot(*)
          integer(c_int) :: st
       end function
+      ! weno(ncells,k,eps,xedges) inside the fused operator: per-cell tables for the sweep along `axis` (0-based)
+      function hrweno_fv_set_xedges(fv, axis, xedges) bind(c, name="hrweno_fv_set_xedges") result(st)
+         import :: c_ptr, c_int, c_double
+         type(c_ptr), value :: fv
+         integer(c_int), value :: axis
+         real(c_double), intent(in) :: xedges(*)
+         integer(c_int) :: st
+      end function
+      ! x-dependent flux f = (model(v)*cross(c))*face(f) along `axis`; pass c_null_ptr for an absent factor
+      function hrweno_fv_set_flux_coef(fv, axis, face_coef, cross_coef) bind(c, name="hrweno_fv_set_flux_coef") result(st)
+         import :: c_ptr, c_int
+         type(c_ptr), value :: fv
+         integer(c_int), value :: axis
+         type(c_ptr), value :: face_coef, cross_coef
+         integer(c_int) :: st
+      end function
       function hrweno_rktvd_create_fused(out, fv, order) bind(c, name="hrweno_rktvd_create_fused") result(st)
          import :: c_ptr, c_int
          type(c_ptr), intent(out) :: out

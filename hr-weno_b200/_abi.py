@@ -94,6 +94,8 @@ PROTOTYPES = {
     "hrweno_fv_rhs_dev": (C.c_int, [C.c_void_p, C.c_double, C.c_void_p, C.c_void_p, C.c_void_p]),
     "hrweno_fv_max_wavespeed_dev": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),
     "hrweno_fv_set_alpha": (C.c_int, [C.c_void_p, C.c_double]),
+    "hrweno_fv_set_xedges": (C.c_int, [C.c_void_p, C.c_int, C.c_void_p]),
+    "hrweno_fv_set_flux_coef": (C.c_int, [C.c_void_p, C.c_int, C.c_void_p, C.c_void_p]),
     "hrweno_fv_export_halo": (C.c_int, [C.c_void_p, C.c_void_p]),
     "hrweno_fv_import_halo": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p]),
     "hrweno_fv_halo_status": (C.c_int, [C.c_void_p]),

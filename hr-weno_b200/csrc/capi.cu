@@ -223,6 +223,16 @@ int hrweno_fv_set_alpha(hrweno_fv *h, double alpha) {
    return HRWENO_OK;
 }
 
+int hrweno_fv_set_xedges(hrweno_fv *h, int axis, const double *xedges) {
+   if (!h) return fail(HRWENO_EINVAL, "null fv handle");
+   return fv_set_xedges(reinterpret_cast<Fv *>(h), axis, xedges);
+}
+
+int hrweno_fv_set_flux_coef(hrweno_fv *h, int axis, const double *face_coef, const double *cross_coef) {
+   if (!h) return fail(HRWENO_EINVAL, "null fv handle");
+   return fv_set_flux_coef(reinterpret_cast<Fv *>(h), axis, face_coef, cross_coef);
+}
+
 int hrweno_fv_export_halo(hrweno_fv *h, void *handle_out) {
    if (!h) return fail(HRWENO_EINVAL, "null fv handle");
    return fv_halo_export(reinterpret_cast<Fv *>(h), handle_out);

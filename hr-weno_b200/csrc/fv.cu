@@ -5,6 +5,7 @@
 #include <float.h>
 
 #include <cstring>
+#include <string>
 #include <new>
 
 namespace hrw {
@@ -35,6 +36,11 @@ Fv::~Fv() {
    cudaFree(d_rwidth[1]);
    cudaFree(d_wtab);
    cudaFree(d_widx);
+   for (int a = 0; a < 2; ++a) {
+      cudaFree(d_cnu[a]);
+      cudaFree(d_fcoef[a]);
+      cudaFree(d_ccoef[a]);
+   }
    cudaFree(d_scratch_in);
    cudaFree(d_scratch_out);
    if (stream) cudaStreamDestroy(stream);
@@ -228,6 +234,69 @@ int fv_create(Fv **out, const hrweno_fv_desc *desc) {
 }
 
 // ------------------------------------------------------------------------------------------------
+// General path (fvgen.cu): non-uniform grids and x-dependent fluxes.  Both setters move the operator from the tuned
+// stage kernels to the general one; they are called after hrweno_fv_create and before the first rhs / integrate call.
+// ------------------------------------------------------------------------------------------------
+__global__ void expand_width_kernel(const double2 *__restrict__ tab, const unsigned char *__restrict__ idx, double *__restrict__ w, int64_t n) {
+   for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) w[i] = tab[idx[i]].x;
+}
+
+static int upload_doubles(const double *host, int64_t n, double **dev) {
+   cudaFree(*dev);
+   *dev = nullptr;
+   HRW_CUDA(cudaMalloc(dev, (size_t)n * sizeof(double)));
+   HRW_CUDA(cudaMemcpy(*dev, host, (size_t)n * sizeof(double), cudaMemcpyHostToDevice));
+   return HRWENO_OK;
+}
+
+static int fv_enable_general(Fv *fv, const char *who) {
+   if (fv->d.nranks > 1) return fail(HRWENO_EINVAL, std::string(who) + ": the general path runs on one GPU (nranks == 1)");
+   if (fv->d.ndim == 1 && !fv->d_width[0]) { // the 1D widths live in the dictionary: the general kernel reads a plain array
+      double *w = nullptr;
+      HRW_CUDA(cudaMalloc(&w, (size_t)(fv->n0 + PAD) * sizeof(double)));
+      int64_t blocks = (fv->n0 + 255) / 256;
+      if (blocks > 148 * 16) blocks = 148 * 16;
+      expand_width_kernel<<<(unsigned)blocks, 256>>>(fv->d_wtab, fv->d_widx, w, fv->n0);
+      cudaError_t e = cudaGetLastError();
+      if (e == cudaSuccess) e = cudaDeviceSynchronize();
+      if (e != cudaSuccess) {
+         cudaFree(w);
+         return cuda_fail(e, "expand_width_kernel", __FILE__, __LINE__);
+      }
+      fv->d_width[0] = w;
+   }
+   fv->general = true;
+   return HRWENO_OK;
+}
+
+// weno(ncells, k, eps, xedges) for the sweep along `axis` (weno.f90:100-112): cnu on the host, once (weno.f90:225-228)
+int fv_set_xedges(Fv *fv, int axis, const double *xedges) {
+   if (!xedges) return fail(HRWENO_EINVAL, "hrweno_fv_set_xedges: null argument");
+   if (axis < 0 || axis >= fv->d.ndim) return fail(HRWENO_EINVAL, "hrweno_fv_set_xedges: invalid axis");
+   std::lock_guard<std::mutex> lock(fv->mtx);
+   HRW_TRY(fv_enable_general(fv, "hrweno_fv_set_xedges"));
+   const int64_t n = axis == 0 ? fv->n0 : fv->n1;
+   std::vector<double> cnu;
+   weno_calc_cnu_host(n, fv->d.k, xedges, cnu);
+   return upload_doubles(cnu.data(), (int64_t)cnu.size(), &fv->d_cnu[axis]);
+}
+
+// f(v, x) = (model(v)*cross[i_other])*face[i_face] for the faces along `axis`; nullptr = factor absent
+int fv_set_flux_coef(Fv *fv, int axis, const double *face, const double *cross) {
+   if (axis < 0 || axis >= fv->d.ndim) return fail(HRWENO_EINVAL, "hrweno_fv_set_flux_coef: invalid axis");
+   if (cross && fv->d.ndim != 2) return fail(HRWENO_EINVAL, "hrweno_fv_set_flux_coef: a cross coefficient needs ndim == 2");
+   std::lock_guard<std::mutex> lock(fv->mtx);
+   HRW_TRY(fv_enable_general(fv, "hrweno_fv_set_flux_coef"));
+   const int64_t n = axis == 0 ? fv->n0 : fv->n1, nother = axis == 0 ? fv->n1 : fv->n0;
+   cudaFree(fv->d_fcoef[axis]);
+   cudaFree(fv->d_ccoef[axis]);
+   fv->d_fcoef[axis] = fv->d_ccoef[axis] = nullptr;
+   if (face) HRW_TRY(upload_doubles(face, n + 1, &fv->d_fcoef[axis]));
+   if (cross) HRW_TRY(upload_doubles(cross, nother, &fv->d_ccoef[axis]));
+   return HRWENO_OK;
+}
+
+// ------------------------------------------------------------------------------------------------
 // dense <-> padded copies.  pack also writes the ghost cells of physical boundaries.
 // ------------------------------------------------------------------------------------------------
 __global__ void pack_kernel(const double *__restrict__ dense, double *__restrict__ padded0, int64_t n, int64_t rows,
@@ -337,6 +406,8 @@ __global__ void __launch_bounds__(256) max_abs_kernel(const double *__restrict__
 
 int fv_max_wavespeed(Fv *fv, const double *v_dev, double *out_dev, cudaStream_t st) {
    const hrweno_fv_desc &d = fv->d;
+   if (fv->d_fcoef[0] || fv->d_fcoef[1] || fv->d_ccoef[0] || fv->d_ccoef[1])
+      return fail(HRWENO_EINVAL, "hrweno_fv_max_wavespeed_dev: not available with x-dependent flux coefficients");
    if (d.flux_model == HRWENO_FLUX_LINEAR) {
       const double a = d.ndim == 2 ? fmax(fabs(d.flux_coef[0]), fabs(d.flux_coef[1])) : fabs(d.flux_coef[0]);
       HRW_CUDA(cudaMemcpyAsync(out_dev, &a, sizeof(double), cudaMemcpyHostToDevice, st));
@@ -397,6 +468,11 @@ void fv_tiling_1d(const Fv *fv, int *tile_cells, int *tiles_per_row) {
 
 static int fv_stage_impl(Fv *fv, int combine, const StageArgs &args, const HaloIO *io, cudaStream_t st) {
    const hrweno_fv_desc &d = fv->d;
+   if (fv->general) { // non-uniform grid and/or x-dependent flux: the general kernel, reference operation order
+      HRW_TRY(fvgen_stage(fv, combine, args, st));
+      fv->launches++;
+      return HRWENO_OK;
+   }
    if (d.ndim == 2) {
       HRW_TRY(fv2d_stage(fv, combine, args, st));
       fv->launches++;

@@ -146,7 +146,7 @@ static int launch_small_k(const SmallArgs &a, int k, int order, int fk, cudaStre
 }
 
 bool fv_small_eligible(const Fv *fv) {
-   return fv->d.ndim == 1 && fv->rows == 1 && fv->d.nranks <= 1 && fv->n0 >= 2 && fv->n0 <= 1024;
+   return !fv->general && fv->d.ndim == 1 && fv->rows == 1 && fv->d.nranks <= 1 && fv->n0 >= 2 && fv->n0 <= 1024;
 }
 
 // nsteps RK steps of order `order` on the dense device vector u, in one launch

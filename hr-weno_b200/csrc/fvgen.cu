@@ -1,0 +1,208 @@
+// fvgen.cu -- general fused finite-volume stage (kernel K7): non-uniform grids and x-dependent fluxes.
+//
+// The tuned stage kernels (fv1d.cuh, fv2d.cu) are specialised for what the two shipped examples run: the uniform-grid
+// tables c1/c2/c3 (weno.f90:12-21) and fluxes that do not depend on x.  The reference API reaches further:
+//   * `weno(ncells, k, eps, xedges)` selects the per-cell tables cnu(:,:,i) (weno.f90:100-112, 177, 221-297), which
+//     is what a population balance on a geometric or logarithmic grid1 (grids.f90:138-230) needs;
+//   * the abstract flux `f(u, x(:), t)` (fluxes.f90:12-18) receives the face coordinates -- example2 passes
+//     `[gx(1)%right(i), gx(2)%center(j)]` / `[gx(1)%center(i), gx(2)%right(j)]` (example2:100-101,109-110) and hints at
+//     the growth terms `v*x(1)**2`, `v*x(1)*x(2)` (example2:140,153).
+// This kernel covers both behind the same fused stage interface (StageArgs, Combine): one pass reads the stage input,
+// reconstructs along x1 (and x2) with per-cell or uniform tables, evaluates the numerical flux with per-face and
+// per-cross-cell coefficients, forms -(df1)/w1 [- (df2)/w2] and applies the RK / multistep combination.  Arithmetic is
+// ALWAYS the reference's operation order (Strict policy: separately rounded IEEE operations, __ddiv_rn), i.e.
+// bit-identical to the oracle; the reconstruction of a cell is the code path of recon_kernel (weno.cu).
+//
+// Decomposition: CTA = 256 threads = one tile of 256x1 cells (1D rows) or 32x8 cells (2D).  Phase A reconstructs the
+// tile plus a one-cell frame along the sweep direction (vl, vr -> shared memory; windows are read straight from global
+// memory with the cell index clamped to the row, which IS the edge replication of weno.f90:171-173, so no ghost cell
+// of the padded layout is read or written).  Phase B: each thread owns one cell: two faces per direction from shared
+// memory, boundary rule, divergence, combination, store.  HBM-bound by the 8k(k+1) B/cell of coefficient traffic per
+// non-uniform axis (96 B/cell at k=3) on top of the stage's 16-40 B/cell.
+// Single GPU only (nranks == 1): per-cell tables of a slab would need the neighbour's edges.
+#include "fv2d.cuh"
+#include "internal.hpp"
+#include "weno_core.cuh"
+
+namespace hrw {
+
+struct GenGeom {
+   int64_t n0, n1;  // cells along x1; rows (1D) or cells along x2 (2D)
+   int64_t ld;      // pitch of the padded state vectors (vin, a, b, out2)
+   int bc;
+   const double *cnu0, *cnu1; // per-cell tables or nullptr (uniform tables)
+   const double *w0, *w1;     // cell widths
+   const double *fc0, *fc1;   // face coefficient along the axis, index 0..n like edges(0:n), or nullptr
+   const double *cc0, *cc1;   // cross coefficient: cc0[j] for x1 faces of row j, cc1[i] for x2 faces of column i, or nullptr
+   WenoK kc;
+   FluxCfg fx0, fx1;
+};
+
+// reconstruct cell i of the strided row base[ii*inc], ii = 0..n-1 (same code path as recon_kernel, weno.cu)
+template <int K>
+__device__ __forceinline__ void gen_recon(const double *base, int64_t inc, int64_t i, int64_t n, const double *cnu, const WenoK &kc,
+                                          double &l, double &r) {
+   double w[2 * K - 1];
+#pragma unroll
+   for (int o = -(K - 1); o <= K - 1; ++o) {
+      int64_t ii = i + o;
+      ii = ii < 0 ? 0 : (ii > n - 1 ? n - 1 : ii); // edge replicas (weno.f90:171-173)
+      w[o + K - 1] = base[ii * inc];
+   }
+   if (cnu) {
+      double ci[K * (K + 1)];
+#pragma unroll
+      for (int q = 0; q < K * (K + 1); ++q) ci[q] = __ldg(cnu + (size_t)i * (K * (K + 1)) + q);
+      weno_cell_nonuniform<K, Strict>(ci, w + (K - 1), kc.eps, l, r);
+   } else {
+      weno_run<K, 1, Strict>(w, kc, &l, &r);
+   }
+}
+
+// f(v, x) = (model(v)*cross)*face, left to right like `v*x(1)*x(2)` (example2:153); an absent factor is not multiplied in
+__device__ __forceinline__ double gen_phys(const FluxCfg &c, double v, bool has_cc, double cc, bool has_fc, double fc) {
+   double f = phys_flux<Strict>(c, v);
+   if (has_cc) f = __dmul_rn(f, cc);
+   if (has_fc) f = __dmul_rn(f, fc);
+   return f;
+}
+
+__device__ __forceinline__ double gen_face_flux(const FluxCfg &c, double vm, double vp, bool has_cc, double cc, bool has_fc, double fc) {
+   const double fm = gen_phys(c, vm, has_cc, cc, has_fc, fc);
+   const double fp = gen_phys(c, vp, has_cc, cc, has_fc, fc);
+   if (c.scheme == HRWENO_SCHEME_LAX_FRIEDRICHS) // (f(vm) + f(vp) - alpha*(vp - vm))/2      fluxes.f90:43
+      return __dmul_rn(__dsub_rn(__dadd_rn(fm, fp), __dmul_rn(c.alpha, __dsub_rn(vp, vm))), 0.5);
+   const double lo = fm < fp ? fm : fp; // fluxes.f90:70-74
+   const double hi = fm > fp ? fm : fp;
+   return vm <= vp ? lo : hi;
+}
+
+// boundary rule on the two faces of cell i of a row of n cells: interior faces are given in fl (i > 0) and fr (i < n-1)
+__device__ __forceinline__ void gen_bc(int bc, int64_t i, int64_t n, double &fl, double &fr) {
+   const bool zero = bc == HRWENO_BC_ZERO_FLUX;
+   if (i == 0) fl = zero ? 0.0 : fr;     // fedges(0) = fedges(1) (example1:103) | 0 (example2:117,119); copy needs n >= 2
+   if (i == n - 1) fr = zero ? 0.0 : fl; // fedges(nc) = fedges(nc-1) (example1:104) | 0 (example2:118,120)
+}
+
+template <int K, bool TWO_D>
+__global__ void __launch_bounds__(256) fvgen_stage_kernel(const GenGeom g, const StageArgs a, const int combine) {
+   constexpr int TX = TWO_D ? 32 : 256, TY = TWO_D ? 8 : 1;
+   constexpr int SX = TX + 2; // x1 sweep: cells i0-1 .. i0+TX
+   __shared__ double s_l1[SX * TY], s_r1[SX * TY];
+   __shared__ double s_l2[TWO_D ? TX * (TY + 2) : 1], s_r2[TWO_D ? TX * (TY + 2) : 1]; // x2 sweep: cells j0-1 .. j0+TY
+   const int64_t tiles_x = (g.n0 + TX - 1) / TX, tiles_y = (g.n1 + TY - 1) / TY;
+   const int lx = threadIdx.x % TX, ly = threadIdx.x / TX;
+   for (int64_t tile = blockIdx.x; tile < tiles_x * tiles_y; tile += gridDim.x) {
+      const int64_t tj = tile / tiles_x;
+      const int64_t i0 = (tile - tj * tiles_x) * TX, j0 = tj * TY;
+      // ---- phase A: reconstruct the tile and its frame --------------------------------------------------------
+      for (int q = threadIdx.x; q < SX * TY; q += 256) {
+         const int iy = q / SX, ix = q - iy * SX;
+         const int64_t i = i0 - 1 + ix, j = j0 + iy;
+         if (i >= 0 && i < g.n0 && j < g.n1) {
+            double l, r;
+            gen_recon<K>(a.vin + j * g.ld, 1, i, g.n0, g.cnu0, g.kc, l, r); // example1:93, example2:98 (contiguous row)
+            s_l1[q] = l;
+            s_r1[q] = r;
+         }
+      }
+      if constexpr (TWO_D) {
+         for (int q = threadIdx.x; q < TX * (TY + 2); q += 256) {
+            const int iy = q / TX, ix = q - iy * TX;
+            const int64_t i = i0 + ix, j = j0 - 1 + iy;
+            if (i < g.n0 && j >= 0 && j < g.n1) {
+               double l, r;
+               gen_recon<K>(a.vin + i, g.ld, j, g.n1, g.cnu1, g.kc, l, r); // example2:107 (stride-nc1 column)
+               s_l2[q] = l;
+               s_r2[q] = r;
+            }
+         }
+      }
+      __syncthreads();
+      // ---- phase B: faces, divergence, combination ------------------------------------------------------------
+      const int64_t i = i0 + lx, j = j0 + ly;
+      if (i < g.n0 && j < g.n1) {
+         // x1: face f lies between cells f-1 and f: godunov(flux, vr(f-1), vl(f), [right(f-1), center2(j)])  (example1:99, example2:100)
+         const bool hc0 = g.cc0 != nullptr, hf0 = g.fc0 != nullptr;
+         const double cc0 = hc0 ? g.cc0[j] : 1.0;
+         const int c1 = lx + 1 + ly * SX; // shared index of cell (i, j) in the x1 arrays
+         double fl = 0.0, fr = 0.0;
+         if (i > 0) fl = gen_face_flux(g.fx0, s_r1[c1 - 1], s_l1[c1], hc0, cc0, hf0, hf0 ? g.fc0[i] : 1.0);
+         if (i < g.n0 - 1) fr = gen_face_flux(g.fx0, s_r1[c1], s_l1[c1 + 1], hc0, cc0, hf0, hf0 ? g.fc0[i + 1] : 1.0);
+         gen_bc(g.bc, i, g.n0, fl, fr);
+         double L = -__ddiv_rn(__dsub_rn(fr, fl), g.w0[i]); // -(fedges(i) - fedges(i-1))/width(i)   example1:107, example2:125
+         if constexpr (TWO_D) {
+            const bool hc1 = g.cc1 != nullptr, hf1 = g.fc1 != nullptr;
+            const double cc1 = hc1 ? g.cc1[i] : 1.0;
+            const int c2 = lx + (ly + 1) * TX; // shared index of cell (i, j) in the x2 arrays
+            double gl = 0.0, gr = 0.0;
+            if (j > 0) gl = gen_face_flux(g.fx1, s_r2[c2 - TX], s_l2[c2], hc1, cc1, hf1, hf1 ? g.fc1[j] : 1.0);
+            if (j < g.n1 - 1) gr = gen_face_flux(g.fx1, s_r2[c2], s_l2[c2 + TX], hc1, cc1, hf1, hf1 ? g.fc1[j + 1] : 1.0);
+            gen_bc(g.bc, j, g.n1, gl, gr);
+            L = __dsub_rn(L, __ddiv_rn(__dsub_rn(gr, gl), g.w1[j])); // ... - (fedges2(j,i) - fedges2(j-1,i))/width2(j)   example2:126
+         }
+         // stage combination (tvdode.f90:141,149-167,257), the expressions of combine_kernel (ode.cu)
+         const int64_t off = j * g.ld + i;
+         const double x = a.vin[off];
+         double o;
+         switch (combine) {
+         case C_RHS: o = L; break;
+         case C_EULER: o = __dadd_rn(x, __dmul_rn(a.c0, L)); break;
+         case C_RK2_FINAL: o = __dmul_rn(__dadd_rn(__dadd_rn(a.a[off], x), __dmul_rn(a.c0, L)), 0.5); break;
+         case C_RK3_S2: o = __dmul_rn(__dadd_rn(__dadd_rn(__dmul_rn(3.0, a.a[off]), x), __dmul_rn(a.c0, L)), 0.25); break;
+         case C_RK3_S3: o = __ddiv_rn(__dadd_rn(__fma_rn(2.0, x, a.a[off]), __dmul_rn(a.c0, L)), 3.0); break;
+         default: // C_MS
+            o = __dmul_rn(__dadd_rn(__dadd_rn(__dadd_rn(__dmul_rn(25.0, x), __dmul_rn(a.c0, L)), __dmul_rn(7.0, a.a[off])),
+                                    __dmul_rn(a.c1, a.b[off])),
+                          0.03125);
+            a.out2[off] = L; // out2 aliases b element for element: b[off] was read above
+         }
+         a.out[j * a.ld_out + i] = o; // out may alias a element for element (read above); it never aliases vin
+      }
+      __syncthreads(); // the next tile overwrites the shared arrays
+   }
+}
+
+template <int K>
+static void fvgen_launch(bool two_d, unsigned blocks, const GenGeom &g, const StageArgs &a, int combine, cudaStream_t st) {
+   if (two_d)
+      fvgen_stage_kernel<K, true><<<blocks, 256, 0, st>>>(g, a, combine);
+   else
+      fvgen_stage_kernel<K, false><<<blocks, 256, 0, st>>>(g, a, combine);
+}
+
+int fvgen_stage(Fv *fv, int combine, const StageArgs &args, cudaStream_t st) {
+   const hrweno_fv_desc &d = fv->d;
+   const bool two_d = d.ndim == 2;
+   GenGeom g{};
+   g.n0 = fv->n0;
+   g.n1 = two_d ? fv->n1 : fv->rows;
+   g.ld = fv->pitch;
+   g.bc = d.bc;
+   g.cnu0 = fv->d_cnu[0];
+   g.cnu1 = fv->d_cnu[1];
+   g.w0 = fv->d_width[0];
+   g.w1 = fv->d_width[1];
+   g.fc0 = fv->d_fcoef[0];
+   g.fc1 = fv->d_fcoef[1];
+   g.cc0 = fv->d_ccoef[0];
+   g.cc1 = fv->d_ccoef[1];
+   g.kc = make_wenok(d.eps);
+   g.fx0 = FluxCfg{d.flux_model, d.flux_scheme, d.flux_coef[0], d.alpha};
+   g.fx1 = FluxCfg{d.flux_model, d.flux_scheme, d.flux_coef[1], d.alpha};
+   if (!g.w0 || (two_d && !g.w1)) return fail(HRWENO_EINVAL, "general stage: width arrays missing");
+   const int64_t tx = two_d ? 32 : 256, ty = two_d ? 8 : 1;
+   const int64_t tiles = ((g.n0 + tx - 1) / tx) * ((g.n1 + ty - 1) / ty);
+   const int64_t cap = 148 * 8; // 8 resident CTAs of 256 threads per SM
+   const unsigned blocks = (unsigned)(tiles < cap ? tiles : cap);
+   if (d.k == 1)
+      fvgen_launch<1>(two_d, blocks, g, args, combine, st);
+   else if (d.k == 2)
+      fvgen_launch<2>(two_d, blocks, g, args, combine, st);
+   else
+      fvgen_launch<3>(two_d, blocks, g, args, combine, st);
+   HRW_CUDA(cudaGetLastError());
+   return HRWENO_OK;
+}
+
+} // namespace hrw

@@ -82,6 +82,11 @@ struct Fv {
    unsigned char *d_widx = nullptr;
    bool width_dict = false;
    double rx = 0.0;              // GRID_LINEAR: (xmax-xmin)/global_n
+   // general path (fvgen.cu, K7), switched on by hrweno_fv_set_xedges / hrweno_fv_set_flux_coef
+   bool general = false;
+   double *d_cnu[2] = {nullptr, nullptr};   // cnu(0:k-1,-1:k-1,1:n[a]) of weno(ncells,k,eps,xedges)  (weno.f90:41,100-112)
+   double *d_fcoef[2] = {nullptr, nullptr}; // face coefficient along axis a, index 0..n[a] like edges(0:n)
+   double *d_ccoef[2] = {nullptr, nullptr}; // cross coefficient for the faces of axis a, index = cell along the other axis
    // scratch for hrweno_fv_rhs[_dev]
    double *d_scratch_in = nullptr, *d_scratch_out = nullptr;
    cudaStream_t stream = nullptr;
@@ -104,6 +109,12 @@ int fv_stage(Fv *fv, int combine, const StageArgs &args, cudaStream_t st);
 // 1D tiling of the current configuration: cells per tile and tiles per row
 void fv_tiling_1d(const Fv *fv, int *tile_cells, int *tiles_per_row);
 int fv_max_wavespeed(Fv *fv, const double *v_dev, double *out_dev, cudaStream_t st);
+// fvgen.cu: general fused stage (per-cell reconstruction tables and/or x-dependent flux coefficients), reference order
+int fvgen_stage(Fv *fv, int combine, const StageArgs &args, cudaStream_t st);
+int fv_set_xedges(Fv *fv, int axis, const double *xedges);
+int fv_set_flux_coef(Fv *fv, int axis, const double *face, const double *cross);
+// weno.cu: weno_calc_cnu (weno.f90:221-297) on the host
+void weno_calc_cnu_host(int64_t nc, int k, const double *xedges, std::vector<double> &cnu);
 // fv1d_small.cu: whole integrate call of a small 1D problem (<= 1024 cells) in one single-CTA launch
 bool fv_small_eligible(const Fv *fv);
 int fv_small_integrate(Fv *fv, double *u_dev, int order, long long nsteps, double dt, cudaStream_t st);

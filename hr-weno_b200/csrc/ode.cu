@@ -383,7 +383,7 @@ __global__ void fill_ghost_kernel(double *cell0, int64_t n, int k, int left, int
 static int rk_integrate_pipelined(Ode *o, double *u, double *t, double tout, double dt, int itask, bool *done) {
    *done = false;
    Fv *fv = o->fv;
-   if (!o->fused || o->is_ms || fv->d.ndim != 1 || fv->rows != 1 || fv->d.nranks > 1) return HRWENO_OK;
+   if (!o->fused || o->is_ms || fv->general || fv->d.ndim != 1 || fv->rows != 1 || fv->d.nranks > 1) return HRWENO_OK;
    int tile = 0, tpr = 0;
    fv_tiling_1d(fv, &tile, &tpr);
    int chunk_tiles = 148 * 48; // a multiple of every resident-CTA count in use (148 x 1,2,3,4,6,8): no ragged last wave;

@@ -16,7 +16,7 @@ Weno::~Weno() {
 
 // weno_calc_cnu (weno.f90:221-297, Shu eq. 2.20).  Host side, once per object ("only called a very
 // small number of times at the start of the simulation", weno.f90:225-228); fp64, reference order.
-static void calc_cnu_host(int64_t nc, int k, const double *xedges, std::vector<double> &cnu) {
+void weno_calc_cnu_host(int64_t nc, int k, const double *xedges, std::vector<double> &cnu) {
    const int ng = k + 1;
    std::vector<double> buf((size_t)(nc + 2 * ng + 1));
    double *xext = buf.data() + ng;
@@ -73,7 +73,7 @@ int weno_create(Weno **out, int64_t ncells, int k, double eps, const double *xed
    w->eps = eps;
    w->uniform = xedges == nullptr;
    if (xedges) {
-      calc_cnu_host(ncells, k, xedges, w->cnu_host);
+      weno_calc_cnu_host(ncells, k, xedges, w->cnu_host);
       const size_t bytes = w->cnu_host.size() * sizeof(double);
       cudaError_t e = cudaMalloc(&w->d_cnu, bytes);
       if (e == cudaSuccess) e = cudaMemcpy(w->d_cnu, w->cnu_host.data(), bytes, cudaMemcpyHostToDevice);

@@ -85,6 +85,27 @@ class FV:
         """extension: Lax-Friedrichs alpha used from the next stage launch on (fluxes.f90:40 takes it per call)"""
         _abi.check(_abi.lib().hrweno_fv_set_alpha(self._h, float(alpha)))
 
+    def set_xedges(self, axis, xedges):
+        """weno(ncells, k, eps, xedges) for the sweep along `axis` (weno.f90:100-112): per-cell tables cnu"""
+        xe = np.ascontiguousarray(xedges, dtype=np.float64)
+        if xe.size != self.desc.n[axis] + 1:  # weno.f90:101-108
+            raise _abi.HrwenoError(_abi.EINVAL, "Invalid input 'xedges'. Valid range: size(xedges) = ncells + 1.")
+        _abi.check(_abi.lib().hrweno_fv_set_xedges(self._h, axis, xe.ctypes.data))
+
+    def set_flux_coef(self, axis, face=None, cross=None):
+        """x-dependent flux f = (model(v)*cross[c])*face[f] for the faces along `axis` (example2:100-101,109-110,140,153)"""
+        f = None if face is None else np.ascontiguousarray(face, dtype=np.float64)
+        c = None if cross is None else np.ascontiguousarray(cross, dtype=np.float64)
+        if f is not None and f.size != self.desc.n[axis] + 1:
+            raise _abi.HrwenoError(_abi.EINVAL, "face coefficients: size must be ncells + 1 (indexed like edges(0:n))")
+        if c is not None and (self.desc.ndim != 2 or c.size != self.desc.n[1 - axis]):
+            raise _abi.HrwenoError(_abi.EINVAL, "cross coefficients: ndim == 2 and one value per cell of the other axis")
+        _abi.check(
+            _abi.lib().hrweno_fv_set_flux_coef(
+                self._h, axis, None if f is None else f.ctypes.data, None if c is None else c.ctypes.data
+            )
+        )
+
     def export_halo(self):
         buf = C.create_string_buffer(_abi.IPC_HANDLE_BYTES)
         _abi.check(_abi.lib().hrweno_fv_export_halo(self._h, buf))

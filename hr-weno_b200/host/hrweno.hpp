@@ -146,6 +146,12 @@ class fv {
    ~fv() { hrweno_fv_destroy(h_); }
    int64_t neq() const { return hrweno_fv_neq(h_); }
    void rhs(double t, const double *v, double *vdot) { hrweno::check(hrweno_fv_rhs(h_, t, v, vdot)); }
+   // weno(ncells, k, eps, xedges) for the sweep along `axis` (weno.f90:100-112,177): xedges(0:n[axis]) = grid1%edges
+   void set_xedges(int axis, const double *xedges) { hrweno::check(hrweno_fv_set_xedges(h_, axis, xedges)); }
+   // x-dependent flux f = (model(v)*cross[c])*face[f] along `axis` (example2:100-101,109-110,140,153); nullptr = absent
+   void set_flux_coef(int axis, const double *face, const double *cross = nullptr) {
+      hrweno::check(hrweno_fv_set_flux_coef(h_, axis, face, cross));
+   }
    ::hrweno_fv *handle() const { return h_; }
    static hrweno_fv_desc desc1d(int64_t nc, int k, double eps, const double *width) {
       hrweno_fv_desc d{};

@@ -156,6 +156,22 @@ int64_t hrweno_fv_neq(const hrweno_fv *fv); /* local number of unknowns */
 int hrweno_fv_rhs(hrweno_fv *fv, double t, const double *v, double *vdot);
 int hrweno_fv_rhs_dev(hrweno_fv *fv, double t, const double *v_dev, double *vdot_dev, void *stream);
 
+/* Non-uniform grids in the fused path: the sweep along `axis` (0 = x1, 1 = x2) reconstructs with the per-cell tables
+ * cnu(:,:,i) of `weno(ncells, k, eps, xedges)` (weno.f90:100-112, 177, 221-297) instead of c1/c2/c3.  xedges[0..n[axis]]
+ * (host) are the cell edges of that axis (grid1%edges, grids.f90:232-250; any grid1 kind).  The cell widths stay the
+ * ones of the descriptor.  Call after hrweno_fv_create and before the first rhs / integrate call; from then on this
+ * operator runs the general stage kernel (reference operation order in both modes, one GPU). */
+int hrweno_fv_set_xedges(hrweno_fv *fv, int axis, const double *xedges);
+/* x-dependent fluxes in the fused path.  The reference hands the face coordinates to the flux callback
+ * (`f(u, x(:), t)`, fluxes.f90:12-18; example2:100-101 passes [right1(i), center2(j)], :109-110 [center1(i), right2(j)])
+ * and hints at the growth terms `v*x(1)**2` and `v*x(1)*x(2)` (example2:140,153).  Closed-set form of those:
+ *     f(v, x) = (model(v) * cross_coef[c]) * face_coef[f]        evaluated left to right, an absent (NULL) factor skipped
+ * for the faces along `axis`: face_coef[0..n[axis]] is indexed like edges(0:n) (face f lies between cells f-1 and f;
+ * entries 0 and n belong to the boundary rule and are not read), cross_coef[0..n[other axis]-1] by the cell index
+ * along the other axis (ndim == 2 only).  `flux1 = v*x(1)**2`: face_coef = edges1**2; `flux2 = v*x(1)*x(2)`:
+ * cross_coef = center1, face_coef = edges2.  Same calling rules as hrweno_fv_set_xedges. */
+int hrweno_fv_set_flux_coef(hrweno_fv *fv, int axis, const double *face_coef, const double *cross_coef);
+
 /* multi-GPU plumbing: each rank exports a 64-byte CUDA IPC handle of its halo mailbox and
  * imports the handles of its left/right neighbours (NULL at a physical boundary). */
 #define HRWENO_IPC_HANDLE_BYTES 64

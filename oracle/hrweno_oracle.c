@@ -250,6 +250,25 @@ double hrweno_ref_face_flux(int scheme, int model, double coef, double alpha, do
    return fm > fp ? fm : fp;
 }
 
+/* x-dependent physical flux of the commented-out growth terms of example2:140,153 (`flux1 = v*x(1)**2`,
+ * `flux2 = v*x(1)*x(2)`): f = (model(v)*cross)*face, left to right like the Fortran expression; a factor that is
+ * absent is not multiplied in. */
+static inline double flux_model_x(int model, double coef, double v, const double *cross, const double *face) {
+   double f = hrweno_ref_flux_model(model, coef, v);
+   if (cross) f = f * *cross;
+   if (face) f = f * *face;
+   return f;
+}
+
+static inline double face_flux_x(int scheme, int model, double coef, double alpha, double vm, double vp,
+                                 const double *cross, const double *face) {
+   const double fm = flux_model_x(model, coef, vm, cross, face);
+   const double fp = flux_model_x(model, coef, vp, cross, face);
+   if (scheme == HRWENO_SCHEME_LAX_FRIEDRICHS) return (fm + fp - alpha * (vp - vm)) / 2; /* fluxes.f90:43 */
+   if (vm <= vp) return fm < fp ? fm : fp;                                              /* fluxes.f90:70-74 */
+   return fm > fp ? fm : fp;
+}
+
 /* ------------------------------------------------------------------------------------------
  * grid1%linear -- src/hrweno_grids.f90:76-79 (edges), :246-247 (center, width)
  * ---------------------------------------------------------------------------------------- */
@@ -273,6 +292,9 @@ struct hrweno_ref_fv {
    hrweno_fv_desc d;
    double *w[2]; /* width arrays */
    int64_t neq;
+   double *cnu[2];   /* per-axis cnu(0:k-1,-1:k-1,1:n) of weno(ncells,k,eps,xedges) (weno.f90:100-112), or NULL */
+   double *fcoef[2]; /* per-axis face coefficient, index 0..n like edges(0:n), or NULL */
+   double *ccoef[2]; /* per-axis cross coefficient, index = cell along the other axis, or NULL */
 };
 
 int hrweno_ref_fv_create(hrweno_ref_fv **out, const hrweno_fv_desc *desc) {
@@ -299,18 +321,54 @@ int hrweno_ref_fv_create(hrweno_ref_fv **out, const hrweno_fv_desc *desc) {
 
 void hrweno_ref_fv_destroy(hrweno_ref_fv *fv) {
    if (!fv) return;
-   free(fv->w[0]);
-   free(fv->w[1]);
+   for (int a = 0; a < 2; ++a) {
+      free(fv->w[a]);
+      free(fv->cnu[a]);
+      free(fv->fcoef[a]);
+      free(fv->ccoef[a]);
+   }
    free(fv);
+}
+
+/* weno(ncells, k, eps, xedges) for the reconstruction along `axis` (weno.f90:100-112,177) */
+int hrweno_ref_fv_set_xedges(hrweno_ref_fv *fv, int axis, const double *xedges) {
+   if (!fv || !xedges || axis < 0 || axis >= fv->d.ndim) return HRWENO_EINVAL;
+   const int k = fv->d.k;
+   const int64_t n = fv->d.n[axis];
+   free(fv->cnu[axis]);
+   fv->cnu[axis] = (double *)malloc(sizeof(double) * (size_t)(n * k * (k + 1)));
+   if (!fv->cnu[axis]) return HRWENO_ENOMEM;
+   return hrweno_ref_weno_calc_cnu(n, k, xedges, fv->cnu[axis]);
+}
+
+static double *dup_doubles(const double *src, int64_t n) {
+   double *p = (double *)malloc(sizeof(double) * (size_t)n);
+   if (p) memcpy(p, src, sizeof(double) * (size_t)n);
+   return p;
+}
+
+/* f(v, x) = (model(v)*cross[i_other])*face[i_face] along `axis`; face[0..n[axis]], cross[0..n[other]-1] */
+int hrweno_ref_fv_set_flux_coef(hrweno_ref_fv *fv, int axis, const double *face, const double *cross) {
+   if (!fv || axis < 0 || axis >= fv->d.ndim) return HRWENO_EINVAL;
+   if (cross && fv->d.ndim != 2) return HRWENO_EINVAL;
+   free(fv->fcoef[axis]);
+   free(fv->ccoef[axis]);
+   fv->fcoef[axis] = face ? dup_doubles(face, fv->d.n[axis] + 1) : NULL;
+   fv->ccoef[axis] = cross ? dup_doubles(cross, fv->d.n[1 - axis]) : NULL;
+   if ((face && !fv->fcoef[axis]) || (cross && !fv->ccoef[axis])) return HRWENO_ENOMEM;
+   return HRWENO_OK;
 }
 
 int64_t hrweno_ref_fv_neq(const hrweno_ref_fv *fv) { return fv->neq; }
 
 /* faces 1..nc-1 then the boundary rule; fe[0..nc] */
 static void faces_row(const hrweno_fv_desc *d, int axis, int64_t nc, const double *vl, const double *vr,
-                      double *fe, int par) {
+                      double *fe, int par, const double *fcoef, const double *cross) {
    const double coef = d->flux_coef[axis];
-   if (par) {
+   if (fcoef || cross) { /* x-dependent flux: x = [right(i), center_other] (example2:100-101,109-110) */
+      for (int64_t i = 1; i <= nc - 1; ++i)
+         fe[i] = face_flux_x(d->flux_scheme, d->flux_model, coef, d->alpha, vr[i - 1], vl[i], cross, fcoef ? fcoef + i : NULL);
+   } else if (par) {
 #pragma omp parallel for schedule(static)
       for (int64_t i = 1; i <= nc - 1; ++i) /* example1:97-100 ; example2:99-102,108-111 */
          fe[i] = hrweno_ref_face_flux(d->flux_scheme, d->flux_model, coef, d->alpha, vr[i - 1], vl[i]);
@@ -347,8 +405,8 @@ static int rhs_1d(hrweno_ref_fv *fv, const double *v, double *vdot) {
          for (int64_t row = 0; row < d->rows; ++row) {
             const double *vrow = v + row * nc;
             double *orow = vdot + row * nc;
-            recon_row(d->k, nc, d->eps, NULL, vrow, 1, vl, vr, vext, par_cells); /* example1:93 */
-            faces_row(d, 0, nc, vl, vr, fe, par_cells);
+            recon_row(d->k, nc, d->eps, fv->cnu[0], vrow, 1, vl, vr, vext, par_cells); /* example1:93 */
+            faces_row(d, 0, nc, vl, vr, fe, par_cells, fv->fcoef[0], NULL);
             const double *w = fv->w[0];
             if (par_cells) {
 #pragma omp parallel for schedule(static)
@@ -390,13 +448,13 @@ static int rhs_2d(hrweno_ref_fv *fv, const double *v, double *vdot) {
       } else {
 #pragma omp for schedule(static) nowait
          for (int64_t j = 0; j < n2; ++j) { /* example2:97-103: contiguous rows */
-            recon_row(d->k, n1, d->eps, NULL, v + j * n1, 1, vl, vr, vext, 0);
-            faces_row(d, 0, n1, vl, vr, f1 + j * (n1 + 1), 0);
+            recon_row(d->k, n1, d->eps, fv->cnu[0], v + j * n1, 1, vl, vr, vext, 0);
+            faces_row(d, 0, n1, vl, vr, f1 + j * (n1 + 1), 0, fv->fcoef[0], fv->ccoef[0] ? fv->ccoef[0] + j : NULL);
          }
 #pragma omp for schedule(static)
          for (int64_t i = 0; i < n1; ++i) { /* example2:106-112: stride-nc1 columns */
-            recon_row(d->k, n2, d->eps, NULL, v + i, n1, vl, vr, vext, 0);
-            faces_row(d, 1, n2, vl, vr, f2 + i * (n2 + 1), 0);
+            recon_row(d->k, n2, d->eps, fv->cnu[1], v + i, n1, vl, vr, vext, 0);
+            faces_row(d, 1, n2, vl, vr, f2 + i * (n2 + 1), 0, fv->fcoef[1], fv->ccoef[1] ? fv->ccoef[1] + i : NULL);
          }
          const double *w1 = fv->w[0], *w2 = fv->w[1];
 #pragma omp for schedule(static)
@@ -415,7 +473,7 @@ static int rhs_2d(hrweno_ref_fv *fv, const double *v, double *vdot) {
 }
 
 int hrweno_ref_fv_rhs(hrweno_ref_fv *fv, double t, const double *v, double *vdot) {
-   (void)t; /* the closed-set flux models do not depend on x or t (example1:120, example2:140,153) */
+   (void)t; /* the closed-set flux models do not depend on t; x enters through the coefficient arrays only */
    if (!fv || !v || !vdot) return HRWENO_EINVAL;
    return fv->d.ndim == 1 ? rhs_1d(fv, v, vdot) : rhs_2d(fv, v, vdot);
 }

@@ -57,6 +57,10 @@ void hrweno_ref_grid_linear(double xmin, double xmax, int64_t n, double *edges, 
 int hrweno_ref_fv_create(hrweno_ref_fv **out, const hrweno_fv_desc *desc);
 void hrweno_ref_fv_destroy(hrweno_ref_fv *fv);
 int64_t hrweno_ref_fv_neq(const hrweno_ref_fv *fv);
+/* weno(ncells,k,eps,xedges): per-cell tables cnu for the sweep along `axis` (weno.f90:100-112,177,221-297) */
+int hrweno_ref_fv_set_xedges(hrweno_ref_fv *fv, int axis, const double *xedges);
+/* x-dependent flux f = (model(v)*cross[i_other])*face[i_face] (the growth terms hinted at example2:140,153) */
+int hrweno_ref_fv_set_flux_coef(hrweno_ref_fv *fv, int axis, const double *face, const double *cross);
 int hrweno_ref_fv_rhs(hrweno_ref_fv *fv, double t, const double *v, double *vdot);
 
 /* tvdode.f90:69-95, 97-178, 180-201, 203-271, 273-284 */

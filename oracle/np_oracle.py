@@ -144,9 +144,31 @@ def grid_linear(xmin, xmax, n):
     return edges, (edges[:-1] + edges[1:]) / 2, edges[1:] - edges[:-1]
 
 
-def _faces(vl, vr, scheme, model, coef, alpha, bc):
-    """faces along the last axis: returns f[..., 0:nc+1]."""
-    inner = face_flux(scheme, model, coef, alpha, vr[..., :-1], vl[..., 1:])
+def face_flux_x(scheme, model, coef, alpha, vm, vp, cross=None, face=None):
+    """x-dependent flux f = (model(v)*cross)*face (growth terms hinted at example2:140,153), absent factors skipped."""
+
+    def f(v):
+        out = flux_model(model, coef, v)
+        if cross is not None:
+            out = out * cross
+        if face is not None:
+            out = out * face
+        return out
+
+    fm, fp = f(vm), f(vp)
+    if scheme == "lax_friedrichs":
+        return (fm + fp - alpha * (vp - vm)) / 2
+    return np.where(vm <= vp, np.minimum(fm, fp), np.maximum(fm, fp))
+
+
+def _faces(vl, vr, scheme, model, coef, alpha, bc, fcoef=None, cross=None):
+    """faces along the last axis: returns f[..., 0:nc+1].  fcoef[0:nc+1] per face, cross[...] per row (broadcast)."""
+    if fcoef is None and cross is None:
+        inner = face_flux(scheme, model, coef, alpha, vr[..., :-1], vl[..., 1:])
+    else:
+        inner = face_flux_x(scheme, model, coef, alpha, vr[..., :-1], vl[..., 1:],
+                            None if cross is None else np.asarray(cross)[..., None],
+                            None if fcoef is None else np.asarray(fcoef)[1:-1])
     if bc == "copy":
         lo, hi = inner[..., :1], inner[..., -1:]
     else:
@@ -155,20 +177,24 @@ def _faces(vl, vr, scheme, model, coef, alpha, bc):
     return np.concatenate([lo, inner, hi], axis=-1)
 
 
-def rhs1d(v, width, k=3, eps=1e-6, scheme="godunov", model="burgers", coef=1.0, alpha=1.0, bc="copy"):
-    """example/example1_burgers_1d_fv.f90:72-109 (rows of independent problems allowed)."""
-    vl, vr = reconstruct(v, k, eps)
-    f = _faces(vl, vr, scheme, model, coef, alpha, bc)
+def rhs1d(v, width, k=3, eps=1e-6, scheme="godunov", model="burgers", coef=1.0, alpha=1.0, bc="copy", cnu=None,
+          fcoef=None):
+    """example/example1_burgers_1d_fv.f90:72-109 (rows of independent problems allowed).
+    cnu = calc_cnu(xedges, k) for weno(nc,k,eps,xedges); fcoef[0:nc+1] = x-dependent face coefficient."""
+    vl, vr = reconstruct(v, k, eps, cnu)
+    f = _faces(vl, vr, scheme, model, coef, alpha, bc, fcoef)
     return -(f[..., 1:] - f[..., :-1]) / width
 
 
-def rhs2d(v, w1, w2, k=3, eps=1e-6, scheme="godunov", model="linear", coef=(1.0, 1.0), alpha=1.0, bc="zero"):
-    """example/example2_pbe_2d_fv.f90:73-129; v[j, i] with i (x1) contiguous."""
-    vl1, vr1 = reconstruct(v, k, eps)
-    f1 = _faces(vl1, vr1, scheme, model, coef[0], alpha, bc)
+def rhs2d(v, w1, w2, k=3, eps=1e-6, scheme="godunov", model="linear", coef=(1.0, 1.0), alpha=1.0, bc="zero",
+          cnu=(None, None), fcoef=(None, None), ccoef=(None, None)):
+    """example/example2_pbe_2d_fv.f90:73-129; v[j, i] with i (x1) contiguous.
+    Per axis: cnu (non-uniform tables), fcoef (per face along the axis), ccoef (per cell of the other axis)."""
+    vl1, vr1 = reconstruct(v, k, eps, cnu[0])
+    f1 = _faces(vl1, vr1, scheme, model, coef[0], alpha, bc, fcoef[0], ccoef[0])
     vt = np.ascontiguousarray(v.T)
-    vl2, vr2 = reconstruct(vt, k, eps)
-    f2 = _faces(vl2, vr2, scheme, model, coef[1], alpha, bc)
+    vl2, vr2 = reconstruct(vt, k, eps, cnu[1])
+    f2 = _faces(vl2, vr2, scheme, model, coef[1], alpha, bc, fcoef[1], ccoef[1])
     t1 = -(f1[:, 1:] - f1[:, :-1]) / w1[None, :]
     t2 = ((f2[:, 1:] - f2[:, :-1]) / w2[None, :]).T
     return t1 - t2

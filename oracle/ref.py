@@ -52,6 +52,8 @@ def lib():
         "hrweno_ref_fv_destroy": (None, [vp]),
         "hrweno_ref_fv_neq": (i64, [vp]),
         "hrweno_ref_fv_rhs": (i32, [vp, dbl, vp, vp]),
+        "hrweno_ref_fv_set_xedges": (i32, [vp, i32, vp]),
+        "hrweno_ref_fv_set_flux_coef": (i32, [vp, i32, vp, vp]),
         "hrweno_ref_rktvd_create": (i32, [C.POINTER(vp), REF_RHS_FN, vp, i64, i32]),
         "hrweno_ref_mstvd_create": (i32, [C.POINTER(vp), REF_RHS_FN, vp, i64]),
         "hrweno_ref_rktvd_create_fv": (i32, [C.POINTER(vp), vp, i32]),
@@ -165,6 +167,19 @@ class FV:
         out = np.empty_like(v)
         _ok(lib().hrweno_ref_fv_rhs(self._h, t, v.ctypes.data, out.ctypes.data))
         return out
+
+    def set_xedges(self, axis, xedges):
+        xe = np.ascontiguousarray(xedges, dtype=np.float64)
+        assert xe.size == self.desc.n[axis] + 1
+        _ok(lib().hrweno_ref_fv_set_xedges(self._h, axis, xe.ctypes.data))
+
+    def set_flux_coef(self, axis, face=None, cross=None):
+        f = None if face is None else np.ascontiguousarray(face, dtype=np.float64)
+        c = None if cross is None else np.ascontiguousarray(cross, dtype=np.float64)
+        assert f is None or f.size == self.desc.n[axis] + 1
+        assert c is None or c.size == self.desc.n[1 - axis]
+        _ok(lib().hrweno_ref_fv_set_flux_coef(self._h, axis, None if f is None else f.ctypes.data,
+                                             None if c is None else c.ctypes.data))
 
 
 class _ode:
