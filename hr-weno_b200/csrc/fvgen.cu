@@ -13,11 +13,12 @@
 // ALWAYS the reference's operation order (Strict policy: separately rounded IEEE operations, __ddiv_rn), i.e.
 // bit-identical to the oracle; the reconstruction of a cell is the code path of recon_kernel (weno.cu).
 //
-// Decomposition: CTA = 256 threads = one tile of 256x1 cells (1D rows) or 32x8 cells (2D).  Phase A reconstructs the
+// Decomposition: CTA = 256 threads = one tile of 254x1 cells (1D rows) or 32x16 cells (2D).  Phase A reconstructs the
 // tile plus a one-cell frame along the sweep direction (vl, vr -> shared memory; windows are read straight from global
 // memory with the cell index clamped to the row, which IS the edge replication of weno.f90:171-173, so no ghost cell
-// of the padded layout is read or written).  Phase B: each thread owns one cell: two faces per direction from shared
-// memory, boundary rule, divergence, combination, store.  HBM-bound by the 8k(k+1) B/cell of coefficient traffic per
+// of the padded layout is read or written); the tile shapes make it whole passes over the 256 threads (1D: one pass,
+// 2D: 1120 items, 2.19 reconstructions per cell).  Phase B: a thread owns one (1D) or two (2D) cells: two faces per
+// direction from shared memory, boundary rule, divergence, combination, store.  HBM-bound by the 8k(k+1) B/cell of coefficient traffic per
 // non-uniform axis (96 B/cell at k=3) on top of the stage's 16-40 B/cell.
 // Single GPU only (nranks == 1): per-cell tables of a slab would need the neighbour's edges.
 #include "fv2d.cuh"
@@ -38,21 +39,28 @@ struct GenGeom {
    FluxCfg fx0, fx1;
 };
 
-// reconstruct cell i of the strided row base[ii*inc], ii = 0..n-1 (same code path as recon_kernel, weno.cu)
-template <int K>
+// reconstruct cell i of the strided row base[ii*inc], ii = 0..n-1 (the arithmetic of recon_kernel, weno.cu); UNIT: inc == 1
+template <int K, bool UNIT>
 __device__ __forceinline__ void gen_recon(const double *base, int64_t inc, int64_t i, int64_t n, const double *cnu, const WenoK &kc,
                                           double &l, double &r) {
+   // edge replicas (weno.f90:171-173): offsets clamped to the row, in 32 bits
+   const int lo = -(int)(i < K - 1 ? i : K - 1), hi = (int)(n - 1 - i < K - 1 ? n - 1 - i : K - 1);
+   const double *cell = base + i * inc;
    double w[2 * K - 1];
 #pragma unroll
    for (int o = -(K - 1); o <= K - 1; ++o) {
-      int64_t ii = i + o;
-      ii = ii < 0 ? 0 : (ii > n - 1 ? n - 1 : ii); // edge replicas (weno.f90:171-173)
-      w[o + K - 1] = base[ii * inc];
+      const int oo = o < lo ? lo : (o > hi ? hi : o);
+      w[o + K - 1] = UNIT ? cell[oo] : cell[(int64_t)oo * inc];
    }
    if (cnu) {
-      double ci[K * (K + 1)];
+      double ci[K * (K + 1)]; // K(K+1) is even and the table is cudaMalloc'ed: 16-B loads
+      const double2 *c2 = reinterpret_cast<const double2 *>(cnu + (size_t)i * (K * (K + 1)));
 #pragma unroll
-      for (int q = 0; q < K * (K + 1); ++q) ci[q] = __ldg(cnu + (size_t)i * (K * (K + 1)) + q);
+      for (int q = 0; q < K * (K + 1) / 2; ++q) {
+         const double2 t = __ldg(c2 + q);
+         ci[2 * q] = t.x;
+         ci[2 * q + 1] = t.y;
+      }
       weno_cell_nonuniform<K, Strict>(ci, w + (K - 1), kc.eps, l, r);
    } else {
       weno_run<K, 1, Strict>(w, kc, &l, &r);
@@ -84,44 +92,64 @@ __device__ __forceinline__ void gen_bc(int bc, int64_t i, int64_t n, double &fl,
    if (i == n - 1) fr = zero ? 0.0 : fl; // fedges(nc) = fedges(nc-1) (example1:104) | 0 (example2:118,120)
 }
 
+// tile of one CTA: 2D 32x16 cells (two per thread in phase B), 1D 254 cells (threads 1..254 own one; 0 and 255 only
+// reconstruct the frame cells), so that phase A is a whole number of full passes over the 256 threads
+constexpr int GEN_NT = 256;
+template <bool TWO_D>
+struct GenTile {
+   static constexpr int TX = TWO_D ? 32 : GEN_NT - 2, TY = TWO_D ? 16 : 1;
+   static constexpr int SX = TX + 2;                    // x1 sweep: cells i0-1 .. i0+TX
+   static constexpr int N1 = SX * TY;                   // items of the x1 sweep (2D: 544 = 17 warps; 1D: 256)
+   static constexpr int N2 = TWO_D ? TX * (TY + 2) : 0; // items of the x2 sweep: cells j0-1 .. j0+TY
+};
+
 template <int K, bool TWO_D>
-__global__ void __launch_bounds__(256) fvgen_stage_kernel(const GenGeom g, const StageArgs a, const int combine) {
-   constexpr int TX = TWO_D ? 32 : 256, TY = TWO_D ? 8 : 1;
-   constexpr int SX = TX + 2; // x1 sweep: cells i0-1 .. i0+TX
-   __shared__ double s_l1[SX * TY], s_r1[SX * TY];
-   __shared__ double s_l2[TWO_D ? TX * (TY + 2) : 1], s_r2[TWO_D ? TX * (TY + 2) : 1]; // x2 sweep: cells j0-1 .. j0+TY
+__global__ void __launch_bounds__(GEN_NT) fvgen_stage_kernel(const GenGeom g, const StageArgs a, const int combine) {
+   using T = GenTile<TWO_D>;
+   constexpr int TX = T::TX, TY = T::TY, SX = T::SX, N1 = T::N1, N2 = T::N2;
+   __shared__ double s_l1[N1], s_r1[N1];
+   __shared__ double s_l2[TWO_D ? N2 : 1], s_r2[TWO_D ? N2 : 1];
    const int64_t tiles_x = (g.n0 + TX - 1) / TX, tiles_y = (g.n1 + TY - 1) / TY;
-   const int lx = threadIdx.x % TX, ly = threadIdx.x / TX;
    for (int64_t tile = blockIdx.x; tile < tiles_x * tiles_y; tile += gridDim.x) {
       const int64_t tj = tile / tiles_x;
       const int64_t i0 = (tile - tj * tiles_x) * TX, j0 = tj * TY;
       // ---- phase A: reconstruct the tile and its frame --------------------------------------------------------
-      for (int q = threadIdx.x; q < SX * TY; q += 256) {
-         const int iy = q / SX, ix = q - iy * SX;
-         const int64_t i = i0 - 1 + ix, j = j0 + iy;
-         if (i >= 0 && i < g.n0 && j < g.n1) {
-            double l, r;
-            gen_recon<K>(a.vin + j * g.ld, 1, i, g.n0, g.cnu0, g.kc, l, r); // example1:93, example2:98 (contiguous row)
-            s_l1[q] = l;
-            s_r1[q] = r;
-         }
-      }
-      if constexpr (TWO_D) {
-         for (int q = threadIdx.x; q < TX * (TY + 2); q += 256) {
-            const int iy = q / TX, ix = q - iy * TX;
+      for (int q = threadIdx.x; q < N1 + N2; q += GEN_NT) {
+         if (q < N1) { // N1 is a multiple of 32: the branch is warp-uniform
+            const int iy = q / SX, ix = q - iy * SX;
+            const int64_t i = i0 - 1 + ix, j = j0 + iy;
+            if (i >= 0 && i < g.n0 && j < g.n1) {
+               double l, r;
+               gen_recon<K, true>(a.vin + j * g.ld, 1, i, g.n0, g.cnu0, g.kc, l, r); // example1:93, example2:98 (contiguous row)
+               s_l1[q] = l;
+               s_r1[q] = r;
+            }
+         } else if constexpr (TWO_D) {
+            const int p = q - N1;
+            const int iy = p / TX, ix = p - iy * TX;
             const int64_t i = i0 + ix, j = j0 - 1 + iy;
             if (i < g.n0 && j >= 0 && j < g.n1) {
                double l, r;
-               gen_recon<K>(a.vin + i, g.ld, j, g.n1, g.cnu1, g.kc, l, r); // example2:107 (stride-nc1 column)
-               s_l2[q] = l;
-               s_r2[q] = r;
+               gen_recon<K, false>(a.vin + i, g.ld, j, g.n1, g.cnu1, g.kc, l, r); // example2:107 (stride-nc1 column)
+               s_l2[p] = l;
+               s_r2[p] = r;
             }
          }
       }
       __syncthreads();
       // ---- phase B: faces, divergence, combination ------------------------------------------------------------
-      const int64_t i = i0 + lx, j = j0 + ly;
-      if (i < g.n0 && j < g.n1) {
+      for (int c = threadIdx.x; c < (TWO_D ? TX * TY : GEN_NT); c += GEN_NT) {
+         int lx, ly;
+         if constexpr (TWO_D) {
+            ly = c / TX;
+            lx = c - ly * TX;
+         } else {
+            ly = 0;
+            lx = c - 1; // thread t reconstructed cell i0-1+t and owns it when 1 <= t <= TX
+            if (lx < 0 || lx >= TX) continue;
+         }
+         const int64_t i = i0 + lx, j = j0 + ly;
+         if (!(i < g.n0 && j < g.n1)) continue;
          // x1: face f lies between cells f-1 and f: godunov(flux, vr(f-1), vl(f), [right(f-1), center2(j)])  (example1:99, example2:100)
          const bool hc0 = g.cc0 != nullptr, hf0 = g.fc0 != nullptr;
          const double cc0 = hc0 ? g.cc0[j] : 1.0;
@@ -150,7 +178,7 @@ __global__ void __launch_bounds__(256) fvgen_stage_kernel(const GenGeom g, const
          case C_EULER: o = __dadd_rn(x, __dmul_rn(a.c0, L)); break;
          case C_RK2_FINAL: o = __dmul_rn(__dadd_rn(__dadd_rn(a.a[off], x), __dmul_rn(a.c0, L)), 0.5); break;
          case C_RK3_S2: o = __dmul_rn(__dadd_rn(__dadd_rn(__dmul_rn(3.0, a.a[off]), x), __dmul_rn(a.c0, L)), 0.25); break;
-         case C_RK3_S3: o = __ddiv_rn(__dadd_rn(__fma_rn(2.0, x, a.a[off]), __dmul_rn(a.c0, L)), 3.0); break;
+         case C_RK3_S3: o = div3<Strict>(__dadd_rn(__fma_rn(2.0, x, a.a[off]), __dmul_rn(a.c0, L))); break; // /3: the exact division of K2/K3
          default: // C_MS
             o = __dmul_rn(__dadd_rn(__dadd_rn(__dadd_rn(__dmul_rn(25.0, x), __dmul_rn(a.c0, L)), __dmul_rn(7.0, a.a[off])),
                                     __dmul_rn(a.c1, a.b[off])),
@@ -166,9 +194,9 @@ __global__ void __launch_bounds__(256) fvgen_stage_kernel(const GenGeom g, const
 template <int K>
 static void fvgen_launch(bool two_d, unsigned blocks, const GenGeom &g, const StageArgs &a, int combine, cudaStream_t st) {
    if (two_d)
-      fvgen_stage_kernel<K, true><<<blocks, 256, 0, st>>>(g, a, combine);
+      fvgen_stage_kernel<K, true><<<blocks, GEN_NT, 0, st>>>(g, a, combine);
    else
-      fvgen_stage_kernel<K, false><<<blocks, 256, 0, st>>>(g, a, combine);
+      fvgen_stage_kernel<K, false><<<blocks, GEN_NT, 0, st>>>(g, a, combine);
 }
 
 int fvgen_stage(Fv *fv, int combine, const StageArgs &args, cudaStream_t st) {
@@ -191,9 +219,9 @@ int fvgen_stage(Fv *fv, int combine, const StageArgs &args, cudaStream_t st) {
    g.fx0 = FluxCfg{d.flux_model, d.flux_scheme, d.flux_coef[0], d.alpha};
    g.fx1 = FluxCfg{d.flux_model, d.flux_scheme, d.flux_coef[1], d.alpha};
    if (!g.w0 || (two_d && !g.w1)) return fail(HRWENO_EINVAL, "general stage: width arrays missing");
-   const int64_t tx = two_d ? 32 : 256, ty = two_d ? 8 : 1;
+   const int64_t tx = two_d ? GenTile<true>::TX : GenTile<false>::TX, ty = two_d ? GenTile<true>::TY : GenTile<false>::TY;
    const int64_t tiles = ((g.n0 + tx - 1) / tx) * ((g.n1 + ty - 1) / ty);
-   const int64_t cap = 148 * 8; // 8 resident CTAs of 256 threads per SM
+   const int64_t cap = 148 * 4; // up to 4 resident CTAs of 256 threads per SM (register-limited)
    const unsigned blocks = (unsigned)(tiles < cap ? tiles : cap);
    if (d.k == 1)
       fvgen_launch<1>(two_d, blocks, g, args, combine, st);

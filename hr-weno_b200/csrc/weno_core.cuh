@@ -299,7 +299,8 @@ __device__ __forceinline__ void weno_run(const double *w, const WenoK &kc, doubl
 }
 
 // ------------------------------------------------------------------------------------------------
-// One cell with per-cell coefficients (non-uniform grid: ci = cnu(:,:,i), weno.f90:177).  Literal.
+// One cell with per-cell coefficients (non-uniform grid: ci = cnu(:,:,i), weno.f90:177).  Reference order; in strict
+// mode the weight quotients share their reciprocal refinements (common.cuh), which leaves every bit unchanged.
 // ci[j + K*(r+1)] = c(j,r); ve points at vext(i).
 // ------------------------------------------------------------------------------------------------
 template <int K, class M>
@@ -337,25 +338,68 @@ __device__ __forceinline__ void weno_cell_nonuniform(const double *ci, const dou
    }
    const double d1[1] = {1.0}, d2[2] = {2.0 / 3, 1.0 / 3}, d3[3] = {0.3, 0.6, 0.1};
    const double *d = K == 1 ? d1 : (K == 2 ? d2 : d3);
-   double al[K], at[K];
+   double xr, xl;
+   if constexpr (M::strict && K == 1) {
+      // alfa = 1/eps**2, w = alfa/alfa = 1 exactly: vr = 1*vrr(0), vl = 1*vlr(0)   (weno.f90:186,207-214)
+      xr = vrr[0];
+      xl = vlr[0];
+   } else if constexpr (M::strict) {
+      // the eleven (k=3) IEEE quotients of weno.f90:207-210 from five refined reciprocals, as in weno_run_k2/_k3:
+      // bit-identical to the divisions while eps+beta < 2^256 (one integer range test), else the literal slow path
+      double e[K], den[K], al[K], at[K];
 #pragma unroll
-   for (int r = 0; r < K; ++r) {
-      const double e = M::add(eps, beta[r]);
-      const double den = M::mul(e, e);
-      al[r] = M::div(d[r], den);
-      at[r] = M::div(d[K - 1 - r], den);
-   }
-   double s = al[0], st = at[0];
+      for (int r = 0; r < K; ++r) {
+         e[r] = M::add(eps, beta[r]);
+         den[r] = M::mul(e[r], e[r]);
+         const double rc = exact_recip(den[r]);
+         al[r] = exact_div_nc(d[r], den[r], rc);
+         at[r] = exact_div_nc(d[K - 1 - r], den[r], rc);
+      }
+      double s = al[0], st = at[0];
 #pragma unroll
-   for (int r = 1; r < K; ++r) {
-      s = M::add(s, al[r]);
-      st = M::add(st, at[r]);
-   }
-   double xr = M::mul(M::div(al[0], s), vrr[0]), xl = M::mul(M::div(at[0], st), vlr[0]);
+      for (int r = 1; r < K; ++r) {
+         s = M::add(s, al[r]);
+         st = M::add(st, at[r]);
+      }
+      const double rs = exact_recip(s), rst = exact_recip(st);
+      xr = M::mul(exact_div_nc(al[0], s, rs), vrr[0]);
+      xl = M::mul(exact_div_nc(at[0], st, rst), vlr[0]);
 #pragma unroll
-   for (int r = 1; r < K; ++r) {
-      xr = M::add(xr, M::mul(M::div(al[r], s), vrr[r]));
-      xl = M::add(xl, M::mul(M::div(at[r], st), vlr[r]));
+      for (int r = 1; r < K; ++r) {
+         xr = M::add(xr, M::mul(exact_div_nc(al[r], s, rs), vrr[r]));
+         xl = M::add(xl, M::mul(exact_div_nc(at[r], st, rst), vlr[r]));
+      }
+      if (!weights_in_range(e[0], e[K - 1], e[K / 2])) {
+         double2 f;
+         if constexpr (K == 2)
+            f = weno_weights_slow_k2(den[0], den[1], vrr[0], vrr[1], vlr[0], vlr[1]);
+         else
+            f = weno_weights_slow_k3(den[0], den[1], den[K - 1], vrr[0], vrr[1], vrr[K - 1], vlr[0], vlr[1], vlr[K - 1]);
+         xl = f.x;
+         xr = f.y;
+      }
+   } else {
+      double al[K], at[K];
+#pragma unroll
+      for (int r = 0; r < K; ++r) {
+         const double e = M::add(eps, beta[r]);
+         const double den = M::mul(e, e);
+         al[r] = M::div(d[r], den);
+         at[r] = M::div(d[K - 1 - r], den);
+      }
+      double s = al[0], st = at[0];
+#pragma unroll
+      for (int r = 1; r < K; ++r) {
+         s = M::add(s, al[r]);
+         st = M::add(st, at[r]);
+      }
+      xr = M::mul(M::div(al[0], s), vrr[0]);
+      xl = M::mul(M::div(at[0], st), vlr[0]);
+#pragma unroll
+      for (int r = 1; r < K; ++r) {
+         xr = M::add(xr, M::mul(M::div(al[r], s), vrr[r]));
+         xl = M::add(xl, M::mul(M::div(at[r], st), vlr[r]));
+      }
    }
    vr = xr;
    vl = xl;
