@@ -95,6 +95,11 @@ __device__ __forceinline__ void gen_bc(int bc, int64_t i, int64_t n, double &fl,
 // tile of one CTA: 2D 32x16 cells (two per thread in phase B), 1D 254 cells (threads 1..254 own one; 0 and 255 only
 // reconstruct the frame cells), so that phase A is a whole number of full passes over the 256 threads
 constexpr int GEN_NT = 256;
+// resident CTAs per SM the register allocation is capped for.  The kernel is latency-bound (long dependent fp64 chains
+// of the exact divisions), so warps beat registers: measured 4 / 5 / 6 per SM -> 1D 3.10 / 3.16 / 2.82e10 cell-stages/s,
+// 2D 1.02 / 1.19 / 1.31e10 cell-steps/s (profiles/r1_variant_sweeps.txt)
+template <bool TWO_D>
+constexpr int gen_minb() { return TWO_D ? 6 : 5; }
 template <bool TWO_D>
 struct GenTile {
    static constexpr int TX = TWO_D ? 32 : GEN_NT - 2, TY = TWO_D ? 16 : 1;
@@ -104,7 +109,7 @@ struct GenTile {
 };
 
 template <int K, bool TWO_D>
-__global__ void __launch_bounds__(GEN_NT) fvgen_stage_kernel(const GenGeom g, const StageArgs a, const int combine) {
+__global__ void __launch_bounds__(GEN_NT, gen_minb<TWO_D>()) fvgen_stage_kernel(const GenGeom g, const StageArgs a, const int combine) {
    using T = GenTile<TWO_D>;
    constexpr int TX = T::TX, TY = T::TY, SX = T::SX, N1 = T::N1, N2 = T::N2;
    __shared__ double s_l1[N1], s_r1[N1];
@@ -221,7 +226,7 @@ int fvgen_stage(Fv *fv, int combine, const StageArgs &args, cudaStream_t st) {
    if (!g.w0 || (two_d && !g.w1)) return fail(HRWENO_EINVAL, "general stage: width arrays missing");
    const int64_t tx = two_d ? GenTile<true>::TX : GenTile<false>::TX, ty = two_d ? GenTile<true>::TY : GenTile<false>::TY;
    const int64_t tiles = ((g.n0 + tx - 1) / tx) * ((g.n1 + ty - 1) / ty);
-   const int64_t cap = 148 * 4; // up to 4 resident CTAs of 256 threads per SM (register-limited)
+   const int64_t cap = 148 * (two_d ? gen_minb<true>() : gen_minb<false>()); // resident CTAs of 256 threads per SM
    const unsigned blocks = (unsigned)(tiles < cap ? tiles : cap);
    if (d.k == 1)
       fvgen_launch<1>(two_d, blocks, g, args, combine, st);
