@@ -51,6 +51,61 @@ class grid1 {
       scale = "linear";
       compute(xe, nm);
    }
+   void bilinear(double xmin, double xcross, double xmax, const int64_t (&n)[2], const std::string &nm = "") { // grids.f90:86-136
+      if (xcross <= xmin) throw hrweno::error(HRWENO_EINVAL, "Invalid input 'xmin', 'xcross'. Valid range: xcross > xmin.");
+      if (xmax <= xcross) throw hrweno::error(HRWENO_EINVAL, "Invalid input 'xcross', 'xmax'. Valid range: xmax > xcross.");
+      if (n[0] < 1 || n[1] < 1) throw hrweno::error(HRWENO_EINVAL, "Invalid input 'ncells'. Valid range: ncells(i) >= 1.");
+      std::vector<double> xe((size_t)(n[0] + n[1]) + 1);
+      double rx = (xcross - xmin) / (double)n[0];
+      for (int64_t i = 0; i <= n[0]; ++i) {
+         volatile double p = rx * (double)i;
+         xe[(size_t)i] = xmin + p;
+      }
+      rx = (xmax - xcross) / (double)n[1];
+      for (int64_t i = 1; i <= n[1]; ++i) {
+         volatile double p = rx * (double)i;
+         xe[(size_t)(n[0] + i)] = xcross + p;
+      }
+      scale = "bilinear";
+      compute(xe, nm);
+   }
+   void log(double xmin, double xmax, int64_t n, const std::string &nm = "") { // grids.f90:138-180
+      if (xmin <= 0.0) throw hrweno::error(HRWENO_EINVAL, "Invalid input 'xmin'. Valid range: xmin > 0.");
+      if (!(xmax > xmin)) throw hrweno::error(HRWENO_EINVAL, "Invalid input 'xmin', 'xmax'. Valid range: xmax > xmin.");
+      if (n < 1) throw hrweno::error(HRWENO_EINVAL, "Invalid input 'ncells'. Valid range: ncells > 1.");
+      std::vector<double> xe((size_t)n + 1);
+      const double rx = std::log(xmax / xmin) / (double)n, l0 = std::log(xmin);
+      for (int64_t i = 0; i <= n; ++i) {
+         volatile double p = rx * (double)i;
+         xe[(size_t)i] = std::exp(l0 + p);
+      }
+      scale = "log";
+      compute(xe, nm);
+   }
+   void geometric(double xmin, double xmax, double ratio, int64_t n, const std::string &nm = "") { // grids.f90:182-230
+      if (xmax <= xmin) throw hrweno::error(HRWENO_EINVAL, "Invalid input 'xmin', 'xmax'. Valid range: xmax > xmin");
+      if (ratio <= 0.0) throw hrweno::error(HRWENO_EINVAL, "Invalid input 'ratio'. Valid range: ratio > 0");
+      if (n < 1) throw hrweno::error(HRWENO_EINVAL, "Invalid input 'ncells'. Valid range: ncells > 1");
+      std::vector<double> xe((size_t)n + 1);
+      const double a = (xmax - xmin) / (powi(ratio, n) - 1.0);
+      for (int64_t i = 0; i <= n; ++i) {
+         volatile double p = a * (powi(ratio, i) - 1.0);
+         xe[(size_t)i] = xmin + p;
+      }
+      scale = "geometric";
+      compute(xe, nm);
+   }
+   // real**integer as gfortran evaluates it (binary exponentiation, low bit first: libgcc __powidf2 / libgfortran pow_r8_i4)
+   static double powi(double x, int64_t m) {
+      uint64_t nn = (uint64_t)(m < 0 ? -m : m);
+      volatile double y = (nn & 1) ? x : 1.0;
+      volatile double xx = x;
+      while (nn >>= 1) {
+         xx = xx * xx;
+         if (nn & 1) y = y * xx;
+      }
+      return m < 0 ? 1.0 / y : y;
+   }
  private:
    void compute(const std::vector<double> &xe, const std::string &nm) { // grids.f90:232-250
       ncells = (int64_t)xe.size() - 1;

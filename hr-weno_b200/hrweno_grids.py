@@ -69,8 +69,21 @@ class grid1:
             raise ValueError("Invalid input 'ratio'. Valid range: ratio > 0")
         if ncells < 1:
             raise ValueError("Invalid input 'ncells'. Valid range: ncells > 1")
-        a = (xmax - xmin) / (ratio**ncells - 1.0)
-        i = np.arange(ncells + 1, dtype=np.float64)
+        a = (xmax - xmin) / (float(_powi(ratio, np.array([ncells]))[0]) - 1.0)
         self.scale = "geometric"
-        self._compute(xmin + a * (ratio**i - 1), name)
+        self._compute(xmin + a * (_powi(ratio, np.arange(ncells + 1)) - 1), name)
         return self
+
+
+def _powi(x, m):
+    """real**integer as gfortran evaluates `ratio**i` (grids.f90:223-225): binary exponentiation, low bit first
+    (libgcc __powidf2 / libgfortran pow_r8_i4), vectorised over the non-negative integer exponents m"""
+    n = np.asarray(m, dtype=np.int64).copy()
+    y = np.where(n & 1, float(x), 1.0)
+    xx = float(x)
+    n >>= 1
+    while np.any(n):
+        xx = xx * xx
+        y = np.where(n & 1, y * xx, y)
+        n >>= 1
+    return y

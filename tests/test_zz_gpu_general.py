@@ -157,12 +157,13 @@ def test_pbe_growth_on_geometric_grid_mstvd_every_output(gpu_lib, pkg, ref):
     mass0 = float(np.sum(u * w))
     t, tr = 0.0, 0.0
     for ii in range(21):
-        tout = 0.2 * ii / 20
-        t = ode.integrate(u, t, tout, 1e-3)
-        tr = rode.integrate(ur, tr, tout, 1e-3)
+        tout = 0.1 * ii / 20
+        t = ode.integrate(u, t, tout, 2.5e-4)
+        tr = rode.integrate(ur, tr, tout, 2.5e-4)
         assert t == tr and np.array_equal(u, ur), f"output {ii}: normwise {normwise(u, ur):.3e}"
     assert ode.fevals == rode.fevals
     assert abs(float(np.sum(u * w)) - mass0) <= 1e-12 * mass0
+    assert u.min() > -1e-3 and u.max() < 1.0  # stable and essentially non-oscillatory at CFL 0.1
 
 
 def test_rktvd_fused_general_2d_bitwise(gpu_lib, pkg, ref):
@@ -211,3 +212,36 @@ def test_general_setters_validate(gpu_lib, pkg):
     out = torch.zeros(1, dtype=torch.float64, device="cuda")
     with pytest.raises(pkg.HrwenoError):
         fv.max_wavespeed_dev(v.data_ptr(), out.data_ptr())
+
+
+def test_example3_cpp_growth_on_geometric_grids(gpu_lib, pkg, ref, tmp_path):
+    """examples/example3_pbe_2d_growth.cpp: example2's driver with geometric grids, per-axis xedges and the growth fluxes
+    of example2:140,153, written against the C++ host mirror; final state bit-identical to the oracle on the same grids"""
+    import os
+    import subprocess
+
+    from conftest import ROOT
+
+    exe = os.path.join(ROOT, "examples", "example3_pbe_2d_growth")
+    assert os.path.exists(exe), "examples not built (python __graft_entry__.py)"
+    out = subprocess.run([exe, str(tmp_path)], capture_output=True, text=True, timeout=300)
+    assert out.returncode == 0, out.stdout + out.stderr
+    e1, e2 = np.fromfile(tmp_path / "edges1.bin"), np.fromfile(tmp_path / "edges2.bin")
+    u = np.fromfile(tmp_path / "u_final.bin")
+    n1, n2 = e1.size - 1, e2.size - 1
+    assert (n1, n2) == (80, 60)
+    # the C++ and the Python mirror of grid1%geometric agree bit for bit (tests/test_grids.py); use the program's own edges
+    assert np.array_equal(e1, pkg.hrweno_grids.grid1().geometric(0.0, 10.0, 1.02, n1).edges)
+    w1, w2, c1, c2 = e1[1:] - e1[:-1], e2[1:] - e2[:-1], (e1[:-1] + e1[1:]) / 2, (e2[:-1] + e2[1:]) / 2
+    rfv = ref.FV(pkg.fv.make_desc((n1, n2), k=3, eps=1e-6, flux_model=1, bc=1, width=[w1, w2]))
+    rfv.set_xedges(0, e1)
+    rfv.set_xedges(1, e2)
+    rfv.set_flux_coef(0, e1 * e1, None)
+    rfv.set_flux_coef(1, e2, c1)
+    rode = ref.mstvd(rfv)
+    ur, t = ex2_ic(c1, c2).reshape(-1), 0.0
+    for ii in range(21):
+        t = rode.integrate(ur, t, 0.1 * ii / 20, 2.5e-4)
+    assert ur.min() > -1e-3 and ur.max() < 1.0  # a stable, essentially non-oscillatory run (CFL 0.1)
+    assert f"fevals = {rode.fevals}" in out.stdout
+    assert np.array_equal(u, ur), f"normwise {normwise(u, ur):.3e}"
