@@ -245,3 +245,29 @@ def test_example3_cpp_growth_on_geometric_grids(gpu_lib, pkg, ref, tmp_path):
     assert ur.min() > -1e-3 and ur.max() < 1.0  # a stable, essentially non-oscillatory run (CFL 0.1)
     assert f"fevals = {rode.fevals}" in out.stdout
     assert np.array_equal(u, ur), f"normwise {normwise(u, ur):.3e}"
+
+
+@pytest.mark.parametrize("general", [False, True])
+@pytest.mark.parametrize("k", [1, 2, 3])
+def test_single_cell_rows_zero_flux(gpu_lib, pkg, ref, k, general):
+    """the smallest legal problem, ncells = 1 (weno.f90:72-76 only asks for ncells > 0): every stencil cell is an edge
+    replica and both faces are walls, so vdot = -(0 - 0)/w; 1D rows and a 1 x n / n x 1 2D grid, tuned and general path"""
+    rng = np.random.default_rng(k)
+    w = np.array([0.37])
+    for rows in (1, 4):
+        v = rng.standard_normal(rows)
+        kw = dict(n=1, rows=rows, k=k, width=[w], bc=1)
+        fv, rfv = pkg.fv.FV(pkg.fv.make_desc(**kw)), ref.FV(pkg.fv.make_desc(**kw))
+        if general:
+            fv.set_flux_coef(0, np.array([2.0, 3.0]))
+            rfv.set_flux_coef(0, np.array([2.0, 3.0]))
+        assert np.array_equal(fv.rhs(0.0, v), rfv.rhs(0.0, v))
+    g = pkg.hrweno_grids.grid1().geometric(0.0, 1.0, 1.1, 9)
+    for shape, widths, ax in (((9, 1), [g.width, w], 0), ((1, 9), [w, g.width], 1)):
+        v = rng.standard_normal(9)
+        kw = dict(n=shape, k=k, width=widths, flux_model=1, bc=1)
+        fv, rfv = pkg.fv.FV(pkg.fv.make_desc(**kw)), ref.FV(pkg.fv.make_desc(**kw))
+        if general:
+            fv.set_xedges(ax, g.edges)
+            rfv.set_xedges(ax, g.edges)
+        assert np.array_equal(fv.rhs(0.0, v), rfv.rhs(0.0, v))
