@@ -41,10 +41,11 @@ struct GenGeom {
 
 // reconstruct one cell (the arithmetic of recon_kernel, weno.cu).  `cell` points at the cell inside its row, the row is
 // strided by `inc` (UNIT: inc == 1); `i` / `n` = its index / the row length, read only when CLAMP (the tile touches a
-// domain edge); `ctab` = the cell's table cnu(:,:,i) or nullptr (uniform tables).
+// domain edge); `has_tab` (the same for every thread of the launch, so the branch stays uniform) selects the cell's
+// table cnu(:,:,i) at `ctab` or the uniform tables.
 template <int K, bool UNIT, bool CLAMP>
-__device__ __forceinline__ void gen_recon(const double *cell, int64_t inc, int64_t i, int64_t n, const double *ctab, const WenoK &kc,
-                                          double &l, double &r) {
+__device__ __forceinline__ void gen_recon(const double *cell, int64_t inc, int64_t i, int64_t n, bool has_tab, const double *ctab,
+                                          const WenoK &kc, double &l, double &r) {
    int lo = -(K - 1), hi = K - 1;
    if constexpr (CLAMP) { // edge replicas (weno.f90:171-173): offsets clamped to the row, in 32 bits
       lo = -(int)(i < K - 1 ? i : K - 1);
@@ -56,7 +57,7 @@ __device__ __forceinline__ void gen_recon(const double *cell, int64_t inc, int64
       const int oo = CLAMP ? (o < lo ? lo : (o > hi ? hi : o)) : o;
       w[o + K - 1] = UNIT ? cell[oo] : cell[(int64_t)oo * inc];
    }
-   if (ctab) {
+   if (has_tab) {
       double ci[K * (K + 1)]; // K(K+1) is even and the table is cudaMalloc'ed: 16-B loads
       const double2 *c2 = reinterpret_cast<const double2 *>(ctab);
 #pragma unroll
@@ -120,7 +121,8 @@ __device__ __forceinline__ void gen_tile(const GenGeom &g, const StageArgs &a, c
    using T = GenTile<TWO_D>;
    constexpr int TX = T::TX, TY = T::TY, SX = T::SX, N1 = T::N1, N2 = T::N2, KK = K * (K + 1);
    const double *vt = a.vin + j0 * g.ld + i0; // cell (i0, j0)
-   const double *t0 = g.cnu0 ? g.cnu0 + i0 * KK : nullptr, *t1 = g.cnu1 ? g.cnu1 + j0 * KK : nullptr;
+   const bool has0 = g.cnu0 != nullptr, has1 = g.cnu1 != nullptr;
+   const double *t0 = g.cnu0 + i0 * KK, *t1 = g.cnu1 + j0 * KK; // tables of cell i0 / j0 (dereferenced only when present)
    // ---- phase A: reconstruct the tile and its frame --------------------------------------------------------
    for (int q = threadIdx.x; q < N1 + N2; q += GEN_NT) {
       if (q < N1) { // N1 is a multiple of 32: the branch is warp-uniform
@@ -128,7 +130,7 @@ __device__ __forceinline__ void gen_tile(const GenGeom &g, const StageArgs &a, c
          const int64_t i = i0 + ix, j = j0 + iy;
          if (INTERIOR || (i >= 0 && i < g.n0 && j < g.n1)) {
             double l, r;
-            gen_recon<K, true, !INTERIOR>(vt + (int64_t)iy * g.ld + ix, 1, i, g.n0, t0 ? t0 + ix * KK : nullptr, g.kc, l,
+            gen_recon<K, true, !INTERIOR>(vt + (int64_t)iy * g.ld + ix, 1, i, g.n0, has0, t0 + ix * KK, g.kc, l,
                                           r); // example1:93, example2:98 (contiguous row)
             s_l1[q] = l;
             s_r1[q] = r;
@@ -139,7 +141,7 @@ __device__ __forceinline__ void gen_tile(const GenGeom &g, const StageArgs &a, c
          const int64_t i = i0 + ix, j = j0 + iy;
          if (INTERIOR || (i < g.n0 && j >= 0 && j < g.n1)) {
             double l, r;
-            gen_recon<K, false, !INTERIOR>(vt + (int64_t)iy * g.ld + ix, g.ld, j, g.n1, t1 ? t1 + iy * KK : nullptr, g.kc, l,
+            gen_recon<K, false, !INTERIOR>(vt + (int64_t)iy * g.ld + ix, g.ld, j, g.n1, has1, t1 + iy * KK, g.kc, l,
                                            r); // example2:107 (stride-nc1 column)
             s_l2[p] = l;
             s_r2[p] = r;
