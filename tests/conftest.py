@@ -16,9 +16,19 @@ def pytest_configure(config):
     config.addinivalue_line("markers", "slow: takes more than a few seconds")
 
 
+def _built():
+    need = [os.path.join(ROOT, "hr-weno_b200", "lib", "libhrweno_b200.so"), os.path.join(ROOT, "oracle", "libhrweno_oracle.so")]
+    need += [os.path.join(ROOT, "examples", e) for e in
+             ("example1_burgers_1d_fv", "example2_pbe_2d_fv", "example3_pbe_2d_growth", "grid_dump")]
+    return all(os.path.exists(p) for p in need)
+
+
 @pytest.fixture(scope="session")
 def pkg():
-    """the product package (hr-weno_b200 loaded as hrweno_b200); does not touch the GPU by itself"""
+    """the product package (hr-weno_b200 loaded as hrweno_b200); does not touch the GPU by itself.
+    A fresh checkout has no built artefacts (they are git-ignored): build them once (nvcc cross-compiles without a GPU)."""
+    if not _built():
+        graft.build()
     return graft.load_package()
 
 
