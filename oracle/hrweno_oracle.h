@@ -6,14 +6,23 @@
  * shipped path (hr-weno_b200/) never links or calls it.
  *
  * Parity status: the reference is Fortran and no Fortran compiler exists in this
- * image, so the reference itself cannot be run here (oracle/_ref is empty).  The
- * oracle is pinned to every assertion of the reference's own test-drive suites
- * (test/test_hrweno.f90, test_tvdode.f90, test_fluxes.f90, test_grid.f90 --
- * tolerances 1e-3..1e-8; the reference holds no golden vectors) and to an
- * independent NumPy restatement (oracle/np_oracle.py) bit for bit.  Beyond those
- * tolerances PARITY IS UNPINNED by the reference: it rests on this file following
- * the operation order of the cited source lines (gfortran, x86-64, no -ffast-math,
- * no FMA contraction; `sum()` = sequential accumulate from 0).
+ * image, so a reference BINARY cannot be run here (oracle/_ref is empty).  The oracle
+ * is pinned three ways:
+ *   1. to the reference's own SOURCE TEXT executed mechanically: tools/f90exec/f90py.py
+ *      translates the procedures of /root/reference/src and of both example programs
+ *      statement by statement into Python and runs them on IEEE binary64 (nothing
+ *      restated by hand); this file reproduces those outputs BIT FOR BIT --
+ *      reconstruct, calc_cnu, both fluxes, rktvd 1-3 / mstvd, example1 as shipped over
+ *      all 101 outputs, example2 (40x40 over all outputs, 250x250 first outputs) and
+ *      example2 with geometric grids + growth terms (fixtures tests/golden/ref_exec_*.npz,
+ *      generator tests/golden/make_ref_exec_golden.py, tests/test_reference_source_exec.py);
+ *   2. to every assertion of the reference's own test-drive suites (test/test_hrweno.f90,
+ *      test_tvdode.f90, test_fluxes.f90, test_grid.f90 -- tolerances 1e-3..1e-8; the
+ *      reference holds no golden vectors);
+ *   3. to an independent NumPy restatement (oracle/np_oracle.py) bit for bit.
+ * What remains unpinned: the output of a gfortran BINARY.  (1) is the source's operation
+ * order under IEEE evaluation without contraction or re-association -- what gfortran
+ * does on x86-64 without -ffast-math / -march=native -- not a compiler run.
  */
 #ifndef HRWENO_ORACLE_H
 #define HRWENO_ORACLE_H

@@ -1,0 +1,1137 @@
+"""f90py -- executes a subset of modern Fortran by mechanical translation to Python (TEST INFRASTRUCTURE).
+
+Purpose: the reference (HugoMVale/HR-WENO) is Fortran and no Fortran compiler exists in this image, so its
+implementation cannot be run to produce golden vectors.  This module reads the reference's own SOURCE TEXT (never
+copied into the repository) and translates, statement by statement, the procedures on the finite-volume path into
+Python functions that are then executed on IEEE binary64 floats.  Nothing about the algorithm is restated by hand:
+operation order, operator precedence and associativity, `sum()` as a sequential accumulation from zero, array sections,
+lower bounds, pointer bounds remapping, optional arguments and the control flow all come from the source lines.
+
+Arithmetic model (what a gfortran x86-64 build without -ffast-math / -march=native does): every + - * / is one
+correctly rounded binary64 operation (CPython floats and NumPy float64 element-wise operations), no FMA contraction, no
+re-association; `x**n` with an integer n is binary exponentiation (libgcc __powidf2), so `x**2 == x*x`; integer/integer
+division truncates; array expressions are evaluated element by element.
+
+Supported subset (enough for src/hrweno_{weno,fluxes,tvdode,grids}.f90 and the `rhs`/`flux`/`ic` procedures of the two
+examples): modules and programs with `contains`, derived types with default component values, type extension,
+type-bound procedures, procedure-pointer components, generic interfaces naming one module procedure, subroutines and
+functions (`result()`, `pure`/`elemental`, typed prefixes), optional and keyword arguments, explicit-shape / assumed-
+shape / automatic arrays with arbitrary lower bounds, allocatable and pointer arrays, `associate`, `do`, `do concurrent`,
+`if`, `select case`, `exit`, `cycle`, `return`, `error stop`, `allocate`, pointer assignment with bounds remapping,
+array constructors, sections with strides, and the intrinsics listed in `INTRINSICS`.
+Anything else raises `NotImplementedError` with the offending line -- it never guesses.
+"""
+from __future__ import annotations
+
+import math
+import re
+
+import numpy as np
+
+# ------------------------------------------------------------------------------------------------------------------
+# runtime
+# ------------------------------------------------------------------------------------------------------------------
+
+
+class FortranStop(RuntimeError):
+    """`error stop`"""
+
+
+class FS:
+    """array section lo:hi:step (inclusive bounds, any of them absent)"""
+
+    __slots__ = ("lo", "hi", "step")
+
+    def __init__(self, lo=None, hi=None, step=None):
+        self.lo, self.hi, self.step = lo, hi, step
+
+
+class Ref:
+    """a scalar dummy argument with intent(out) / intent(inout): passed by reference"""
+
+    __slots__ = ("v",)
+
+    def __init__(self, v=None):
+        self.v = v
+
+
+def val(x):
+    return x.v if isinstance(x, Ref) else x
+
+
+def as_ref(x):
+    return x if isinstance(x, Ref) else Ref(x)
+
+
+class FArr:
+    """Fortran array: column-major NumPy storage plus one lower bound per dimension.  Sections are views."""
+
+    __slots__ = ("a", "lb")
+
+    def __init__(self, a, lb=None):
+        self.a = a
+        self.lb = tuple(lb) if lb is not None else (1,) * a.ndim
+
+    @staticmethod
+    def alloc(bounds, dtype=np.float64):
+        shape = tuple(max(0, hi - lo + 1) for lo, hi in bounds)
+        return FArr(np.zeros(shape, dtype=dtype, order="F"), tuple(lo for lo, _ in bounds))
+
+    @staticmethod
+    def wrap(x, lb=None):
+        """dummy-argument association: assumed-shape dummies get lower bound 1 (or the declared one)"""
+        if x is None:
+            return None
+        if isinstance(x, FArr):
+            return FArr(x.a, lb if lb is not None else (1,) * x.a.ndim)
+        a = np.asarray(x)
+        if a.dtype != np.float64 and a.dtype.kind == "f":
+            a = a.astype(np.float64)
+        return FArr(a, lb if lb is not None else (1,) * a.ndim)
+
+    @staticmethod
+    def from_list(items):
+        flat = []
+        for it in items:
+            if isinstance(it, FArr):
+                flat.extend(it.a.ravel(order="F").tolist())
+            else:
+                flat.append(it)
+        return FArr(np.array(flat, dtype=np.float64), (1,))
+
+    def copy(self):
+        return FArr(np.array(self.a, order="F", copy=True), self.lb)
+
+    def rebase(self, lb):
+        return FArr(self.a, tuple(lb))
+
+    # -- indexing -------------------------------------------------------------------------------------------------
+    def _key(self, key):
+        if not isinstance(key, tuple):
+            key = (key,)
+        if len(key) != self.a.ndim:
+            raise IndexError(f"rank mismatch: {len(key)} subscripts for rank {self.a.ndim}")
+        out, is_section = [], False
+        for d, k in enumerate(key):
+            lb, n = self.lb[d], self.a.shape[d]
+            if isinstance(k, FS):
+                is_section = True
+                step = 1 if k.step is None else int(k.step)
+                lo = (lb if step > 0 else lb + n - 1) if k.lo is None else int(k.lo)
+                hi = (lb + n - 1 if step > 0 else lb) if k.hi is None else int(k.hi)
+                cnt = max(0, (hi - lo + step) // step)
+                if cnt and not (lb <= lo <= lb + n - 1 and lb <= lo + (cnt - 1) * step <= lb + n - 1):
+                    raise IndexError(f"section {lo}:{hi}:{step} outside bounds {lb}:{lb + n - 1}")
+                start = lo - lb
+                stop = start + cnt * step
+                out.append(slice(start, stop if stop >= 0 else None, step))
+            else:
+                k = int(k)
+                if not lb <= k <= lb + n - 1:
+                    raise IndexError(f"subscript {k} outside bounds {lb}:{lb + n - 1}")
+                out.append(k - lb)
+        return tuple(out), is_section
+
+    def __getitem__(self, key):
+        k, sec = self._key(key)
+        r = self.a[k]
+        if sec:
+            return FArr(r)  # a section has lower bounds 1
+        return r.item() if isinstance(r, np.generic) else r
+
+    def __setitem__(self, key, value):
+        k, _ = self._key(key)
+        self.a[k] = value.a if isinstance(value, FArr) else value
+
+    def assign(self, value):
+        if isinstance(value, FArr):
+            if value.a.shape != self.a.shape:
+                raise ValueError(f"shape mismatch in array assignment: {self.a.shape} <- {value.a.shape}")
+            self.a[...] = value.a
+        else:
+            self.a[...] = value
+
+    # -- element-wise arithmetic (each NumPy float64 operation is one correctly rounded IEEE operation) ---------------
+    @staticmethod
+    def _u(x):
+        return x.a if isinstance(x, FArr) else x
+
+    def __add__(self, o):
+        return FArr(self.a + FArr._u(o))
+
+    def __radd__(self, o):
+        return FArr(FArr._u(o) + self.a)
+
+    def __sub__(self, o):
+        return FArr(self.a - FArr._u(o))
+
+    def __rsub__(self, o):
+        return FArr(FArr._u(o) - self.a)
+
+    def __mul__(self, o):
+        return FArr(self.a * FArr._u(o))
+
+    def __rmul__(self, o):
+        return FArr(FArr._u(o) * self.a)
+
+    def __truediv__(self, o):
+        return FArr(self.a / FArr._u(o))
+
+    def __rtruediv__(self, o):
+        return FArr(FArr._u(o) / self.a)
+
+    def __neg__(self):
+        return FArr(-self.a)
+
+    def __lt__(self, o):
+        return FArr(self.a < FArr._u(o))
+
+    def __le__(self, o):
+        return FArr(self.a <= FArr._u(o))
+
+    def __gt__(self, o):
+        return FArr(self.a > FArr._u(o))
+
+    def __ge__(self, o):
+        return FArr(self.a >= FArr._u(o))
+
+    def __pos__(self):
+        return self
+
+
+def assign(cur, value):
+    """`lhs = rhs` for a whole variable: arrays are assigned in place (dummy arguments, pointer targets), an unallocated
+    allocatable is allocated to the shape of the right-hand side, scalars are rebound"""
+    if isinstance(cur, Ref):
+        cur.v = val(value)
+        return cur
+    if isinstance(cur, FArr):
+        cur.assign(value)
+        return cur
+    if isinstance(value, FArr):
+        return value.copy()
+    return val(value)
+
+
+def assign_alloc(cur, value):
+    """`lhs = rhs` where lhs is an allocatable whole array (every array component of the reference's types is): F2003
+    reallocates the left-hand side when the shapes differ (gfortran's default -frealloc-lhs)"""
+    if isinstance(cur, FArr) and isinstance(value, FArr) and cur.a.shape != value.a.shape:
+        return value.copy()
+    return assign(cur, value)
+
+
+def fdiv(a, b):
+    if isinstance(a, (int, np.integer)) and isinstance(b, (int, np.integer)) and not isinstance(a, bool):
+        q = abs(int(a)) // abs(int(b))
+        return q if (a >= 0) == (b >= 0) else -q
+    return a / b
+
+
+def fpow(x, n):
+    if isinstance(n, (int, np.integer)):
+        n = int(n)
+        if isinstance(x, (int, np.integer)):
+            return int(x) ** n
+        m = abs(n)
+        y = x if (m & 1) else 1.0
+        while m > 1:
+            m >>= 1
+            x = x * x
+            if m & 1:
+                y = y * x
+        return 1.0 / y if n < 0 else y
+    if isinstance(x, FArr):
+        return FArr(np.power(x.a, FArr._u(n)))
+    return math.pow(x, n)
+
+
+def frange(lo, hi, step=1):
+    lo, hi, step = int(lo), int(hi), int(step)
+    return range(lo, hi + (1 if step > 0 else -1), step)
+
+
+def _seq_sum(x):
+    if not isinstance(x, FArr):
+        return x
+    s = 0 if x.a.dtype.kind in "iu" else 0.0  # sum() accumulates from zero in array element order
+    for e in x.a.ravel(order="F").tolist():
+        s = s + e
+    return s
+
+
+def _size(x, dim=None):
+    return int(x.a.size if dim is None else x.a.shape[dim - 1])
+
+
+def _lbound(x, dim):
+    return x.lb[dim - 1]
+
+
+def _ubound(x, dim):
+    return x.lb[dim - 1] + x.a.shape[dim - 1] - 1
+
+
+def _sign(a, b):
+    return math.copysign(abs(a), b) if isinstance(a, float) or isinstance(b, float) else (abs(a) if b >= 0 else -abs(a))
+
+
+def _eoshift(array, shift, dim=1):
+    out = np.zeros_like(array.a)
+    ax = dim - 1
+    n = array.a.shape[ax]
+    src = [slice(None)] * array.a.ndim
+    dst = [slice(None)] * array.a.ndim
+    if shift >= 0:  # result(i) = array(i + shift)
+        src[ax], dst[ax] = slice(shift, n), slice(0, n - shift)
+    else:
+        src[ax], dst[ax] = slice(0, n + shift), slice(-shift, n)
+    out[tuple(dst)] = array.a[tuple(src)]
+    return FArr(np.asfortranarray(out), array.lb)
+
+
+def _minmax(fn):
+    def f(*args):
+        if any(isinstance(a, FArr) for a in args):
+            r = FArr._u(args[0])
+            for a in args[1:]:
+                r = fn(r, FArr._u(a))
+            return FArr(np.asarray(r, dtype=np.float64))
+        r = args[0]
+        for a in args[1:]:
+            r = a if (fn is np.minimum and a < r) or (fn is np.maximum and a > r) else r
+        return r
+
+    return f
+
+
+def _elementwise(fn):
+    return lambda x: FArr(fn(x.a)) if isinstance(x, FArr) else float(fn(x))
+
+
+INTRINSICS = {
+    "sum": _seq_sum,
+    "size": _size,
+    "lbound": _lbound,
+    "ubound": _ubound,
+    "sign": _sign,
+    "eoshift": _eoshift,
+    "min": _minmax(np.minimum),
+    "max": _minmax(np.maximum),
+    "abs": lambda x: FArr(np.abs(x.a)) if isinstance(x, FArr) else abs(x),
+    "epsilon": lambda x: float(np.finfo(np.float64).eps),
+    "any": lambda x: bool(np.any(FArr._u(x))),
+    "all": lambda x: bool(np.all(FArr._u(x))),
+    "present": lambda x: x is not None,
+    "allocated": lambda x: x is not None,
+    "associated": lambda x: x is not None,
+    "optval": lambda x, default: default if x is None else val(x),  # fortran-lang/stdlib (the reference's only use of it)
+    "real": lambda x, kind=None: float(x),
+    "int": lambda x, kind=None: int(x),
+    "exp": _elementwise(np.exp),
+    "log": _elementwise(np.log),
+    "sqrt": _elementwise(np.sqrt),
+}
+
+
+def callm(obj, name, *args, **kw):
+    """`call obj%name(...)`: a type-bound procedure (passed-object first) or a procedure-pointer component (nopass)"""
+    bound = type(obj)._bindings.get(name) if hasattr(type(obj), "_bindings") else None
+    if bound is not None:
+        return type(obj)._scope[bound](obj, *args, **kw)
+    return getattr(obj, name)(*args, **kw)
+
+
+# ------------------------------------------------------------------------------------------------------------------
+# lexical level
+# ------------------------------------------------------------------------------------------------------------------
+
+
+def logical_lines(text):
+    """comment-free logical lines (continuations joined) with the 1-based number of their first physical line"""
+    out, buf, start = [], "", None
+    for no, raw in enumerate(text.splitlines(), 1):
+        line, q, i = "", None, 0
+        while i < len(raw):  # strip the comment, respecting strings
+            ch = raw[i]
+            if q:
+                if ch == q:
+                    q = None
+            elif ch in "'\"":
+                q = ch
+            elif ch == "!":
+                break
+            line += ch
+            i += 1
+        line = line.strip()
+        if not line or line.startswith("#"):
+            continue
+        if buf:
+            line = line[1:].lstrip() if line.startswith("&") else line
+        else:
+            start = no
+        if line.endswith("&"):
+            buf += line[:-1].rstrip() + " "
+            continue
+        out.append((start, buf + line))
+        buf = ""
+    return out
+
+
+TOKEN = re.compile(
+    r"\s*(?:(?P<num>(?:\d+\.\d*|\.\d+|\d+)(?:[eEdD][+-]?\d+)?(?:_\w+)?)|(?P<str>\"[^\"]*\"|'[^']*')|"
+    r"(?P<dotop>\.(?:and|or|not|true|false|eq|ne|lt|le|gt|ge|eqv|neqv)\.)|(?P<name>[A-Za-z_]\w*)|"
+    r"(?P<op>\*\*|=>|==|/=|<=|>=|//|[-+*/<>=(),:%\[\]]))",
+    re.I,
+)
+
+
+def tokenize(s):
+    toks, pos = [], 0
+    s = s.rstrip()
+    while pos < len(s):
+        m = TOKEN.match(s, pos)
+        if not m:
+            raise NotImplementedError(f"cannot tokenize {s[pos:]!r}")
+        pos = m.end()
+        kind = m.lastgroup
+        toks.append((kind, m.group(kind)))
+    return toks
+
+
+# ------------------------------------------------------------------------------------------------------------------
+# expressions
+# ------------------------------------------------------------------------------------------------------------------
+
+
+class ExprTranslator:
+    """Fortran expression (token list) -> Python source.  Precedence (F2018 10.1.2): ** > * / > unary +- > binary +- >
+    relational > .not. > .and. > .or.; ** is right-associative, the others left-associative -- Python agrees on all of
+    it except that unary minus binds tighter than * in Python, which cannot change a rounded result."""
+
+    def __init__(self, toks, scope):
+        self.t, self.i, self.scope = toks, 0, scope
+
+    def peek(self):
+        return self.t[self.i] if self.i < len(self.t) else (None, None)
+
+    def take(self, val=None):
+        k, v = self.peek()
+        if val is not None and (v is None or v.lower() != val):
+            raise NotImplementedError(f"expected {val!r}, found {v!r} in {self.t}")
+        self.i += 1
+        return k, v
+
+    def at(self, val):
+        v = self.peek()[1]
+        return v is not None and v.lower() == val
+
+    def expr(self):
+        left = self.and_()
+        while self.at(".or."):
+            self.take()
+            left = f"({left} or {self.and_()})"
+        return left
+
+    def and_(self):
+        left = self.not_()
+        while self.at(".and."):
+            self.take()
+            left = f"({left} and {self.not_()})"
+        return left
+
+    def not_(self):
+        if self.at(".not."):
+            self.take()
+            return f"(not {self.not_()})"
+        return self.rel()
+
+    REL = {"==": "==", "/=": "!=", "<": "<", "<=": "<=", ">": ">", ">=": ">=", ".eq.": "==", ".ne.": "!=", ".lt.": "<",
+           ".le.": "<=", ".gt.": ">", ".ge.": ">="}
+
+    def rel(self):
+        left = self.add()
+        v = self.peek()[1]
+        if v is not None and v.lower() in self.REL:
+            self.take()
+            return f"({left} {self.REL[v.lower()]} {self.add()})"
+        return left
+
+    def add(self):
+        if self.at("-") or self.at("+"):
+            op = self.take()[1]
+            left = f"({op}{self.mul()})"
+        else:
+            left = self.mul()
+        while self.at("+") or self.at("-"):
+            op = self.take()[1]
+            left = f"({left} {op} {self.mul()})"
+        return left
+
+    def mul(self):
+        left = self.pow_()
+        while self.at("*") or self.at("/"):
+            op = self.take()[1]
+            right = self.pow_()
+            left = f"({left} * {right})" if op == "*" else f"fdiv({left}, {right})"
+        return left
+
+    def pow_(self):
+        base = self.primary()
+        if self.at("**"):
+            self.take()
+            if self.at("-") or self.at("+"):
+                op = self.take()[1]
+                return f"fpow({base}, {op}{self.pow_()})"
+            return f"fpow({base}, {self.pow_()})"
+        return base
+
+    def arglist(self, close):
+        """subscripts / actual arguments up to `close`; returns list of python snippets (sections as FS(...))"""
+        args = []
+        if self.at(close):
+            self.take()
+            return args
+        while True:
+            k, v = self.peek()
+            nk, nv = self.t[self.i + 1] if self.i + 1 < len(self.t) else (None, None)
+            if k == "name" and nv == "=" :  # keyword argument
+                self.take()
+                self.take()
+                args.append(f"{v.lower()}={self.arg_value()}")
+            else:
+                args.append(self.section_or_expr(close))
+            if self.at(","):
+                self.take()
+                continue
+            self.take(close)
+            return args
+
+    def arg_value(self):
+        """an actual argument: a bare by-reference scalar keeps its Ref"""
+        k, v = self.peek()
+        nv = self.t[self.i + 1][1] if self.i + 1 < len(self.t) else None
+        if k == "name" and v.lower() in self.scope.refs and nv in (",", ")"):
+            self.take()
+            return v.lower()
+        return self.expr()
+
+    def section_or_expr(self, close):
+        lo = hi = step = None
+        if not self.at(":"):
+            lo = self.arg_value()
+            if not self.at(":"):
+                return lo
+        self.take(":")
+        if not (self.at(",") or self.at(close) or self.at(":")):
+            hi = self.expr()
+        if self.at(":"):
+            self.take()
+            step = self.expr()
+        return f"FS({lo}, {hi}, {step})"
+
+    def primary(self):
+        k, v = self.take()
+        if k == "num":
+            v = re.sub(r"_\w+$", "", v)
+            v = re.sub(r"[dD]", "e", v)
+            return v
+        if k == "str":
+            return repr(v[1:-1])
+        if k == "dotop":
+            return {".true.": "True", ".false.": "False"}[v.lower()]
+        if v == "(":
+            e = self.expr()
+            self.take(")")
+            return f"({e})"
+        if v == "[":
+            items = self.arglist("]")
+            return f"FArr.from_list([{', '.join(items)}])"
+        if k != "name":
+            raise NotImplementedError(f"unexpected token {v!r} in {self.t}")
+        return self.designator(v.lower())
+
+    def designator(self, name):
+        cur = self.scope.rename(name)
+        first = True
+        while True:
+            if self.at("("):
+                self.take()
+                args = self.arglist(")")
+                if first and self.scope.is_callable(name):
+                    cur = f"{cur}({', '.join(args)})"
+                else:
+                    cur = f"{cur}[{', '.join(args)}]"
+            elif self.at("%"):
+                self.take()
+                comp = self.take()[1].lower()
+                if self.at("(") and self.scope.is_method(comp):
+                    self.take()
+                    args = self.arglist(")")
+                    cur = f"callm({cur}, {comp!r}{''.join(', ' + a for a in args)})"
+                else:
+                    cur = f"{cur}.{comp}"
+            else:
+                return cur
+            first = False
+
+
+# ------------------------------------------------------------------------------------------------------------------
+# program units
+# ------------------------------------------------------------------------------------------------------------------
+
+
+class Scope:
+    def __init__(self, unit, program):
+        self.unit, self.program = unit, program
+        self.refs = set()      # scalar dummies passed by reference: read as name.v
+        self.result = None     # (fortran name, python name) of the function result
+        self.locals = set()
+
+    def rename(self, name):
+        if self.result and name == self.result[0]:
+            return self.result[1]
+        if name in self.refs:
+            return f"{name}.v"
+        if name in PY_RESERVED:
+            return name + "_"
+        return name
+
+    def is_callable(self, name):
+        if name in self.locals and name not in self.unit["proc_dummies"]:
+            return False
+        return name in INTRINSICS or name in self.program.procs or name in self.program.generics or name in self.unit["proc_dummies"]
+
+    def is_method(self, comp):
+        return comp in self.program.methods
+
+
+PY_RESERVED = {"lambda", "from", "in", "is", "not", "pass", "def", "class", "global", "with", "as", "del", "try"}
+
+DECL = re.compile(r"^(real|integer|logical|character|type|class|procedure)\b", re.I)
+UNIT_HEAD = re.compile(
+    r"^(?P<prefix>(?:(?:pure|elemental|impure|recursive|module)\s+|(?:real|integer|logical|type|class)\s*\([^)]*\)\s+|"
+    r"(?:logical|integer|real)\s+)*)(?P<kind>subroutine|function)\s+(?P<name>\w+)\s*(?:\((?P<args>[^)]*)\))?\s*"
+    r"(?:result\s*\(\s*(?P<res>\w+)\s*\))?\s*$",
+    re.I,
+)
+
+
+def split_top(s, sep=","):
+    """split at top-level separators (not inside parentheses / brackets / strings)"""
+    out, depth, cur, q = [], 0, "", None
+    for ch in s:
+        if q:
+            cur += ch
+            if ch == q:
+                q = None
+            continue
+        if ch in "'\"":
+            q = ch
+        elif ch in "([":
+            depth += 1
+        elif ch in ")]":
+            depth -= 1
+        if ch == sep and depth == 0:
+            out.append(cur.strip())
+            cur = ""
+        else:
+            cur += ch
+    if cur.strip():
+        out.append(cur.strip())
+    return out
+
+
+class Program:
+    """all program units of a set of source files, translated into one Python namespace"""
+
+    def __init__(self):
+        self.procs = {}     # name -> unit
+        self.generics = {}  # generic interface name -> specific procedure
+        self.types = {}     # type name -> dict(parent, comps=[(name, default_src)], bindings={})
+        self.methods = set()
+        self.params = []    # module-level parameter declarations (file, line, text)
+        self.ns = {
+            "FArr": FArr, "FS": FS, "Ref": Ref, "val": val, "as_ref": as_ref, "assign": assign, "assign_alloc": assign_alloc, "fdiv": fdiv, "fpow": fpow,
+            "frange": frange, "callm": callm, "FortranStop": FortranStop, **INTRINSICS,
+        }
+        self.sources = {}
+
+    # -- parsing ----------------------------------------------------------------------------------------------------
+    def add_source(self, path, skip=()):
+        """parse one source file; procedures named in `skip` (I/O, timers) are not translated"""
+        self._skip = {x.lower() for x in skip}
+        text = open(path).read()
+        lines = logical_lines(text)
+        self.sources[path] = lines
+        i, n = 0, len(lines)
+        stack = []  # enclosing module / program / procedures
+        while i < n:
+            no, ln = lines[i]
+            low = ln.lower()
+            m = UNIT_HEAD.match(ln)
+            if re.match(r"^(module|program)\s+\w+$", low) and not low.startswith("module procedure"):
+                stack.append(("container", low.split()[1]))
+                i += 1
+            elif re.match(r"^(abstract\s+)?interface\b", low):
+                gen = low.split()[1] if len(low.split()) > 1 and not low.startswith("abstract") else None
+                i += 1
+                while not lines[i][1].lower().startswith("end interface"):
+                    mm = re.match(r"^module\s+procedure\s*(?:::)?\s*(\w+)", lines[i][1], re.I)
+                    if gen and mm:
+                        self.generics[gen] = mm.group(1).lower()
+                    i += 1
+                i += 1
+            elif re.match(r"^type\s*(,[^:]*)?(::)?\s*\w+$", low) and not low.startswith("type("):
+                i = self._parse_type(lines, i)
+            elif m:
+                i = self._parse_unit(path, lines, i, m)
+            elif low.startswith("end ") or low == "end" or low == "contains":
+                i += 1
+            else:
+                if DECL.match(ln) and "parameter" in low.split("::")[0]:
+                    self.params.append((path, no, ln))
+                i += 1
+        return self
+
+    def _parse_type(self, lines, i):
+        head = lines[i][1]
+        name = re.split(r"::|\s", head.strip())[-1].lower()
+        mext = re.search(r"extends\s*\(\s*(\w+)\s*\)", head, re.I)
+        td = {"parent": mext.group(1).lower() if mext else None, "comps": [], "bindings": {}}
+        i += 1
+        in_contains = False
+        while not re.match(r"^end\s*type", lines[i][1], re.I):
+            ln = lines[i][1]
+            if ln.lower() == "contains":
+                in_contains = True
+            elif in_contains:
+                mm = re.match(r"^procedure[^:]*::\s*(.*)$", ln, re.I)
+                if mm:
+                    for ent in split_top(mm.group(1)):
+                        if "=>" in ent:
+                            b, p = [x.strip().lower() for x in ent.split("=>")]
+                        else:
+                            b = p = ent.strip().lower()
+                        td["bindings"][b] = p
+                        self.methods.add(b)
+            else:
+                spec, ents = ln.split("::", 1)
+                for ent in split_top(ents):
+                    mm = re.match(r"^(\w+)\s*(\([^)]*\))?\s*(?:(=>|=)\s*(.*))?$", ent)
+                    cname, default = mm.group(1).lower(), mm.group(4)
+                    if mm.group(3) == "=>" or default is None:
+                        default = None
+                    td["comps"].append((cname, default))
+                    if spec.lower().startswith("procedure"):
+                        self.methods.add(cname)
+            i += 1
+        self.types[name] = td
+        return i + 1
+
+    def _parse_unit(self, path, lines, i, m):
+        name = m.group("name").lower()
+        args = [a.strip().lower() for a in (m.group("args") or "").split(",") if a.strip()]
+        unit = {"name": name, "kind": m.group("kind").lower(), "args": args, "res": (m.group("res") or name).lower(),
+                "prefix": (m.group("prefix") or "").lower(), "decls": [], "body": [], "path": path, "proc_dummies": set()}
+        i += 1
+        depth = 0
+        while True:
+            no, ln = lines[i]
+            low = ln.lower()
+            if depth == 0 and re.match(rf"^end\s*({unit['kind']})?(\s+{name})?$", low):
+                break
+            if depth == 0 and low == "contains":
+                raise NotImplementedError(f"{path}:{no}: internal procedures inside a procedure")
+            is_decl = not unit["body"] and (DECL.match(ln) and "::" in ln or low.startswith(("use ", "implicit ", "import ")))
+            if is_decl:
+                if DECL.match(ln):
+                    unit["decls"].append((no, ln))
+            else:
+                unit["body"].append((no, ln))
+            i += 1
+        if name not in self._skip:
+            self.procs[name] = unit
+        return i + 1
+
+    # -- code generation ----------------------------------------------------------------------------------------------
+    def ex(self, src, scope):
+        tr = ExprTranslator(tokenize(src), scope)
+        out = tr.expr()
+        if tr.i != len(tr.t):
+            raise NotImplementedError(f"trailing tokens in expression {src!r}")
+        return out
+
+    def _decl_entities(self, ln):
+        spec, ents = ln.split("::", 1)
+        attrs = [a.strip() for a in split_top(spec)]
+        base = attrs[0].lower()
+        info = {"base": base, "intent": None, "optional": False, "dims": None, "parameter": False, "pointer": False,
+                "allocatable": False}
+        for a in attrs[1:]:
+            al = a.lower()
+            if al.startswith("intent"):
+                info["intent"] = re.sub(r"\s", "", al)[7:-1]
+            elif al == "optional":
+                info["optional"] = True
+            elif al.startswith("dimension"):
+                info["dims"] = a[a.index("(") + 1 : a.rindex(")")]
+            elif al == "parameter":
+                info["parameter"] = True
+            elif al == "pointer":
+                info["pointer"] = True
+            elif al == "allocatable":
+                info["allocatable"] = True
+        out = []
+        for ent in split_top(ents):
+            mm = re.match(r"^(\w+)\s*(?:\((.*?)\))?\s*(?:=\s*(.*))?$", ent, re.S)
+            if not mm:
+                raise NotImplementedError(f"declaration entity {ent!r}")
+            # the dims group must be balanced: re-split by hand for nested parentheses
+            nm = mm.group(1).lower()
+            rest = ent[len(mm.group(1)) :].strip()
+            dims, init = None, None
+            if rest.startswith("("):
+                depth = 0
+                for j, ch in enumerate(rest):
+                    depth += ch == "("
+                    depth -= ch == ")"
+                    if depth == 0:
+                        dims, rest = rest[1:j], rest[j + 1 :].strip()
+                        break
+            if rest.startswith("="):
+                init = rest[1:].strip()
+            out.append((nm, dims if dims is not None else info["dims"], init, info))
+        return out
+
+    def _bounds(self, dims, scope):
+        b = []
+        for d in split_top(dims):
+            if ":" in d:
+                lo, hi = d.split(":", 1)
+                b.append((self.ex(lo, scope) if lo.strip() else None, self.ex(hi, scope) if hi.strip() else None))
+            else:
+                b.append(("1", self.ex(d, scope)))
+        return b
+
+    def gen_unit(self, unit):
+        scope = Scope(unit, self)
+        py = []
+        emit = lambda ind, s: py.append("    " * ind + s)  # noqa: E731
+        is_fn = unit["kind"] == "function"
+        args = list(unit["args"])
+        decls = {}
+        for no, ln in unit["decls"]:
+            for nm, dims, init, info in self._decl_entities(ln):
+                decls[nm] = (dims, init, info, no)
+                scope.locals.add(nm)
+                if info["base"].startswith("procedure") and nm in args:
+                    unit["proc_dummies"].add(nm)
+        res = unit["res"] if is_fn else None
+        if is_fn:
+            scope.result = (res, "res_")
+            scope.locals.add(res)
+        for a in args:  # scalar dummies with intent(out|inout) are references
+            if a in decls:
+                dims, _, info, _ = decls[a]
+                if dims is None and info["intent"] in ("out", "inout") and info["base"].startswith(("real", "integer", "logical")):
+                    scope.refs.add(a)
+        sig = ", ".join(scope.rename(a).replace(".v", "") + ("=None" if a in decls and decls[a][2]["optional"] else "") for a in args)
+        # optional dummies must come last for Python: the reference's procedures already satisfy that or are called by keyword
+        emit(0, f"def {unit['name']}({sig}):")
+        emit(1, f"# {unit['path']}:{unit['decls'][0][0] if unit['decls'] else unit['body'][0][0]}")
+        for a in args:
+            if a not in decls:
+                continue
+            dims, _, info, _ = decls[a]
+            if a in scope.refs:
+                emit(1, f"{a} = as_ref({a})")
+            elif dims is not None:
+                lbs = []
+                for lo, hi in self._bounds(dims, scope):
+                    lbs.append(lo if lo is not None else "1")
+                emit(1, f"{a} = FArr.wrap({a}, ({', '.join(lbs)},))")
+            elif info["base"].startswith(("real", "integer", "logical")):
+                emit(1, f"{a} = val({a})")
+        if is_fn:
+            rb = decls.get(res, (None, None, {"base": unit["prefix"]}, 0))[2]["base"]
+            tm = re.search(r"type\s*\(\s*(\w+)\s*\)", rb + " " + unit["prefix"])
+            emit(1, f"res_ = new_{tm.group(1).lower()}()" if tm else "res_ = None")
+        for nm, (dims, init, info, no) in decls.items():
+            if nm in args or nm == res:
+                continue
+            if info["base"].startswith(("type", "class")):
+                tm = re.search(r"\(\s*(\w+)\s*\)", info["base"])
+                emit(1, f"{scope.rename(nm)} = new_{tm.group(1).lower()}()")
+            elif dims is not None and not info["pointer"] and not info["allocatable"] and ":" not in [d.strip() for d in split_top(dims)]:
+                bs = ", ".join(f"({lo}, {hi})" for lo, hi in self._bounds(dims, scope))
+                dt = "np.int64" if info["base"].startswith("integer") else "np.float64"
+                emit(1, f"{scope.rename(nm)} = FArr.alloc([{bs}], {dt})")
+                if init is not None:
+                    emit(1, f"{scope.rename(nm)}.assign({self.ex(init, scope)})")
+            else:
+                emit(1, f"{scope.rename(nm)} = {self.ex(init, scope) if init is not None else 'None'}")
+        self._gen_body(unit, scope, emit)
+        emit(1, "return res_" if is_fn else "return None")
+        return "\n".join(py)
+
+    def _assignment(self, ln, scope):
+        """split `lhs = rhs` / `lhs => rhs` at the top-level operator"""
+        depth, q = 0, None
+        for j, ch in enumerate(ln):
+            if q:
+                q = None if ch == q else q
+                continue
+            if ch in "'\"":
+                q = ch
+            elif ch in "([":
+                depth += 1
+            elif ch in ")]":
+                depth -= 1
+            elif ch == "=" and depth == 0:
+                if ln[j + 1 : j + 2] == ">":
+                    return ln[:j].strip(), "=>", ln[j + 2 :].strip()
+                if ln[j + 1 : j + 2] == "=" or ln[j - 1] in "<>/=":
+                    continue
+                return ln[:j].strip(), "=", ln[j + 1 :].strip()
+        return None
+
+    def _gen_stmt(self, no, ln, scope, emit, ind, unit):
+        low = ln.lower()
+        ret = "return res_" if unit["kind"] == "function" else "return None"
+        if low == "return":
+            return emit(ind, ret)
+        if low == "exit":
+            return emit(ind, "break")
+        if low == "cycle":
+            return emit(ind, "continue")
+        if low.startswith("error stop"):
+            arg = ln[10:].strip()
+            return emit(ind, f"raise FortranStop({self.ex(arg, scope) if arg else repr('error stop')})")
+        if low.startswith("call "):
+            target = ln[5:].strip()
+            if "(" not in target:
+                target += "()"
+            flat, depth = "", 0  # the designator with its parenthesised groups removed: a%b(..)%c(..) -> a%b%c
+            for ch in target:
+                depth += ch == "("
+                if depth == 0:
+                    flat += ch
+                depth -= ch == ")"
+            tr = ExprTranslator(tokenize(target), CallScope(scope) if "%" not in flat else scope)
+            return emit(ind, tr.expr())
+        if low.startswith("allocate"):
+            inner = ln[ln.index("(") + 1 : ln.rindex(")")]
+            for ent in split_top(inner):
+                # the allocation shape is the last parenthesised group
+                depth, k = 0, len(ent) - 1
+                while k >= 0:
+                    depth += ent[k] == ")"
+                    depth -= ent[k] == "("
+                    if depth == 0:
+                        break
+                    k -= 1
+                target, dims = ent[:k].strip(), ent[k + 1 : -1]
+                bs = ", ".join(f"({lo}, {hi})" for lo, hi in self._bounds(dims, scope))
+                emit(ind, f"{self.ex(target, scope)} = FArr.alloc([{bs}])")
+            return None
+        if low.startswith(("deallocate", "nullify")):
+            inner = ln[ln.index("(") + 1 : ln.rindex(")")]
+            for ent in split_top(inner):
+                emit(ind, f"{self.ex(ent, scope)} = None")
+            return None
+        asg = self._assignment(ln, scope)
+        if asg is None:
+            raise NotImplementedError(f"{unit['path']}:{no}: unsupported statement {ln!r}")
+        lhs, op, rhs = asg
+        r = self.ex(rhs, scope)
+        if op == "=>":
+            mm = re.match(r"^([\w%]+)\s*\((.*)\)$", lhs)
+            if mm and ":" in mm.group(2):  # bounds remapping  p(lb:) => target
+                lbs = [self.ex(d.split(":")[0], scope) for d in split_top(mm.group(2))]
+                return emit(ind, f"{self.ex(mm.group(1), scope)} = ({r}).rebase(({', '.join(lbs)},))")
+            return emit(ind, f"{self.ex(lhs, scope)} = {r}")
+        l = self.ex(lhs, scope)
+        if l.endswith("]"):  # element or section
+            return emit(ind, f"{l} = {r}")
+        if l.endswith(".v"):
+            return emit(ind, f"{l} = val({r})")
+        if "." in l:
+            obj, comp = l.rsplit(".", 1)
+            return emit(ind, f"{l} = assign_alloc(getattr({obj}, {comp!r}, None), {r})")
+        return emit(ind, f"{l} = assign({l}, {r})")
+
+    def _gen_body(self, unit, scope, emit):
+        ind = 1
+        sel = []  # select-case stack: [tmp name, first-case flag]
+        for no, ln in unit["body"]:
+            low = ln.lower()
+            try:
+                if m := re.match(r"^if\s*\((.*)\)\s*then$", ln, re.I):
+                    emit(ind, f"if {self.ex(m.group(1), scope)}:")
+                    ind += 1
+                elif m := re.match(r"^else\s*if\s*\((.*)\)\s*then$", ln, re.I):
+                    emit(ind - 1, f"elif {self.ex(m.group(1), scope)}:")
+                elif low == "else":
+                    emit(ind - 1, "else:")
+                elif re.match(r"^end\s*if$", low):
+                    emit(ind, "pass")
+                    ind -= 1
+                elif re.match(r"^end\s*do$", low):
+                    emit(ind, "pass")
+                    ind -= 1 + self._do_stack.pop()  # a multi-index `do concurrent` opened several nested loops
+                elif low.startswith("if") and (m := self._one_line_if(ln)):
+                    emit(ind, f"if {self.ex(m[0], scope)}:")
+                    self._gen_stmt(no, m[1], scope, emit, ind + 1, unit)
+                elif low == "do":
+                    emit(ind, "while True:")
+                    self._do_stack.append(0)
+                    ind += 1
+                elif m := re.match(r"^do\s+concurrent\s*\((.*)\)$", ln, re.I):
+                    specs = split_top(m.group(1))
+                    for s in specs:
+                        var, rng = s.split("=", 1)
+                        parts = rng.split(":")
+                        a = ", ".join(self.ex(p, scope) for p in parts)
+                        emit(ind, f"for {var.strip().lower()} in frange({a}):")
+                        ind += 1
+                    self._do_stack.append(len(specs) - 1)
+                elif m := re.match(r"^do\s+(\w+)\s*=\s*(.*)$", ln, re.I):
+                    a = ", ".join(self.ex(p, scope) for p in split_top(m.group(2)))
+                    emit(ind, f"for {m.group(1).lower()} in frange({a}):")
+                    self._do_stack.append(0)
+                    ind += 1
+                elif m := re.match(r"^select\s+case\s*\((.*)\)$", ln, re.I):
+                    tmp = f"sel_{len(sel)}_{no}"
+                    emit(ind, f"{tmp} = {self.ex(m.group(1), scope)}")
+                    sel.append([tmp, True])
+                    ind += 1
+                elif m := re.match(r"^case\s*\((.*)\)$", ln, re.I):
+                    tmp, first = sel[-1]
+                    emit(ind - 1, f"{'if' if first else 'elif'} {tmp} == {self.ex(m.group(1), scope)}:")
+                    emit(ind, "pass")
+                    sel[-1][1] = False
+                elif low == "case default":
+                    emit(ind - 1, "else:" if not sel[-1][1] else "if True:")
+                    emit(ind, "pass")
+                elif re.match(r"^end\s*select$", low):
+                    sel.pop()
+                    ind -= 1
+                elif m := re.match(r"^associate\s*\((.*)\)$", ln, re.I):
+                    for s in split_top(m.group(1)):
+                        a, e = s.split("=>")
+                        scope.locals.add(a.strip().lower())
+                        emit(ind, f"{a.strip().lower()} = {self.ex(e.strip(), scope)}")
+                elif re.match(r"^end\s*associate$", low):
+                    pass
+                else:
+                    self._gen_stmt(no, ln, scope, emit, ind, unit)
+            except NotImplementedError:
+                raise
+            except Exception as e:  # pragma: no cover - translator bug: point at the line
+                raise NotImplementedError(f"{unit['path']}:{no}: {ln!r}: {type(e).__name__}: {e}") from e
+
+    _do_stack = []
+
+    @staticmethod
+    def _one_line_if(ln):
+        depth = 0
+        start = ln.index("(")
+        for j in range(start, len(ln)):
+            depth += ln[j] == "("
+            depth -= ln[j] == ")"
+            if depth == 0:
+                rest = ln[j + 1 :].strip()
+                return (ln[start + 1 : j], rest) if rest and rest.lower() != "then" else None
+        return None
+
+    def build(self):
+        """translate everything and exec it into the namespace; returns the namespace"""
+        ns = self.ns
+        ns["np"] = np
+        dummy = Scope({"proc_dummies": set()}, self)
+        # derived types -> Python classes with the declared default component values
+        for tname, td in self.types.items():
+            comps, bindings, t = [], {}, td
+            chain = []
+            while t is not None:
+                chain.append(t)
+                t = self.types.get(t["parent"]) if t["parent"] else None
+            for t in reversed(chain):
+                comps.extend(t["comps"])
+                bindings.update(t["bindings"])
+            cls = type(tname, (), {"_bindings": bindings, "_scope": ns, "_comps": comps})
+
+            def make(cls=cls, comps=comps):
+                def new():
+                    o = cls()
+                    for cname, default in comps:
+                        setattr(o, cname, eval(self.ex(default, dummy), ns) if default is not None else None)
+                    return o
+
+                return new
+
+            ns[f"new_{tname}"] = make()
+        # module-level named constants
+        for path, no, ln in self.params:
+            for nm, dims, init, info in self._decl_entities(ln):
+                if dims is not None:
+                    m = re.match(r"^reshape\s*\(\s*\[(.*)\]\s*,\s*\[(.*?)\]\s*(?:,\s*order\s*=\s*\[(.*?)\])?\s*\)$", init, re.I | re.S)
+                    bnds = [(int(eval(lo, {})), int(eval(hi, {}))) for lo, hi in self._bounds(dims, dummy)]
+                    arr = FArr.alloc(bnds)
+                    if m:
+                        vals = [eval(self.ex(v, dummy), ns) for v in split_top(m.group(1))]
+                        order = [int(x) for x in split_top(m.group(3))] if m.group(3) else list(range(1, len(bnds) + 1))
+                        shape = [int(x) for x in split_top(m.group(2))]
+                        perm_shape = [shape[o - 1] for o in order]  # element order varies fastest along order(1)
+                        tmp = np.array(vals, dtype=np.float64).reshape(perm_shape, order="F")
+                        arr.a[...] = np.transpose(tmp, np.argsort([o - 1 for o in order]))
+                    else:
+                        v = eval(self.ex(init, dummy), ns)
+                        arr.assign(v)
+                    ns[nm] = arr
+                else:
+                    ns[nm] = eval(self.ex(init, dummy), ns)
+        code = {}
+        for name, unit in self.procs.items():
+            Program._do_stack = []
+            src = self.gen_unit(unit)
+            code[name] = src
+            exec(compile(src, f"<f90py:{unit['path']}:{name}>", "exec"), ns)
+            if "elemental" in unit["prefix"]:
+                ns[name] = _elemental(ns[name])
+        for gen, spec in self.generics.items():
+            if spec in ns:
+                ns[gen] = ns[spec]
+        self.code = code
+        return ns
+
+
+class CallScope:
+    """scope view used for the target of a CALL statement: the leading name is always a procedure"""
+
+    def __init__(self, scope):
+        self._s = scope
+        self.refs = scope.refs
+
+    def rename(self, name):
+        return self._s.rename(name)
+
+    def is_callable(self, name):
+        return True if not hasattr(self, "_used") and not setattr(self, "_used", True) else self._s.is_callable(name)
+
+    def is_method(self, comp):
+        return True
+
+
+def _elemental(fn):
+    def f(x, *rest):
+        if isinstance(x, FArr):
+            out = np.empty_like(x.a)
+            flat_in, flat_out = x.a.ravel(order="K"), out.ravel(order="K")
+            for i in range(flat_in.size):
+                flat_out[i] = fn(float(flat_in[i]), *rest)
+            return FArr(out.reshape(x.a.shape), x.lb)
+        return fn(x, *rest)
+
+    return f
