@@ -1,0 +1,202 @@
+"""CPU-only: the Fortran-subset translator (tools/f90exec/f90py.py) on small snippets whose results are known by the
+language rules, so that the fixtures it produces from the reference's source (tests/golden/ref_exec_*.npz) can be trusted.
+The snippets are written here; none comes from the reference."""
+import os
+import sys
+import textwrap
+
+import numpy as np
+import pytest
+
+from conftest import ROOT
+
+sys.path.insert(0, os.path.join(ROOT, "tools", "f90exec"))
+import f90py  # noqa: E402
+from f90py import FArr, Ref, callm  # noqa: E402
+
+
+def build(tmp_path, src):
+    p = tmp_path / "snippet.f90"
+    p.write_text(textwrap.dedent(src))
+    return f90py.Program().add_source(str(p)).build()
+
+
+def test_expression_rules(tmp_path):
+    ns = build(tmp_path, """
+        module m
+        contains
+           pure real(rk) function f(a, b, c)
+              real(rk), intent(in) :: a, b, c
+              f = a - b*c**2/3 + (-a**2)    ! ** before * /, left to right, unary minus below **
+           end function
+           pure integer function idiv(i, j)
+              integer, intent(in) :: i, j
+              idiv = i/j + (-i)/j            ! integer division truncates toward zero
+           end function
+           pure real(rk) function mixed(x, n)
+              real(rk), intent(in) :: x
+              integer, intent(in) :: n
+              mixed = 13.0_rk/12*x + n/2 + x**(-2) + 2**n   ! real/int is real; int/int is int; real**int by squaring
+           end function
+           pure logical function rel(a, b)
+              real(rk), intent(in) :: a, b
+              rel = .not. (a >= b) .and. a /= b .or. a == b
+           end function
+        end module
+    """)
+    a, b, c = 0.7, 1.3, -2.9
+    assert ns["f"](a, b, c) == a - ((b * (c * c)) / 3) + (-(a * a))
+    assert ns["idiv"](7, 2) == 3 + (-3) and ns["idiv"](-7, 2) == -3 + 3
+    x = 1.1
+    assert ns["mixed"](x, 5) == ((((13.0 / 12) * x) + 2) + 1.0 / (x * x)) + 32
+    assert ns["rel"](1.0, 2.0) is True and ns["rel"](2.0, 1.0) is False and ns["rel"](1.0, 1.0) is True
+
+
+def test_sum_is_sequential_from_zero_and_sections_are_inclusive(tmp_path):
+    ns = build(tmp_path, """
+        module m
+        contains
+           subroutine s(v, out)
+              real(rk), intent(in) :: v(:)
+              real(rk), intent(out) :: out(:)
+              real(rk) :: w(-2:3)
+              w = 0.0_rk
+              w(-2:0) = v(1:3)              ! lower bound -2
+              w(1:) = v(6:4:-1)             ! negative stride
+              out(1) = sum(w)
+              out(2) = sum(w(-2:3:2)*v(1:3))
+              out(3) = w(-2) + w(3)
+              out(4) = size(w) + lbound(w, 1) + ubound(w, 1)
+           end subroutine
+        end module
+    """)
+    v = np.array([1e16, 1.0, -1e16, 3.0, 5.0, 7.0])
+    out = np.zeros(4)
+    ns["s"](v, out)
+    w = [1e16, 1.0, -1e16, 7.0, 5.0, 3.0]
+    acc = 0.0
+    for e in w:
+        acc = acc + e
+    assert out[0] == acc == 15.0  # (1e16 + 1) rounds to 1e16: a pairwise or reversed sum would give 16
+    assert out[1] == ((0.0 + w[0] * v[0]) + w[2] * v[1]) + w[4] * v[2]
+    assert out[2] == 1e16 + 3.0 and out[3] == 6 - 2 + 3
+
+
+def test_types_methods_optional_and_reference_arguments(tmp_path):
+    ns = build(tmp_path, """
+        module m
+           type :: base
+              integer :: n = 4
+              real(rk) :: scale = 2.0_rk
+              real(rk), allocatable :: a(:)
+           contains
+              procedure, pass(self) :: fill => base_fill
+           end type
+           type, extends(base) :: child
+              real(rk), allocatable :: h(:, :)
+           contains
+              procedure, pass(self) :: step => child_step
+           end type
+           interface child
+              module procedure :: child_init
+           end interface
+        contains
+           type(child) function child_init(n, scale) result(self)
+              integer, intent(in) :: n
+              real(rk), intent(in), optional :: scale
+              self%n = n
+              if (present(scale)) self%scale = scale
+              allocate (self%a(0:n - 1), self%h(n, 2))
+              call self%fill(1.0_rk)
+           end function
+           subroutine base_fill(self, x0)
+              class(base), intent(inout) :: self
+              real(rk), intent(in) :: x0
+              integer :: i
+              do concurrent(i=0:self%n - 1)
+                 self%a(i) = x0 + self%scale*i
+              end do
+           end subroutine
+           subroutine child_step(self, t, dt, mode)
+              class(child), intent(inout) :: self
+              real(rk), intent(inout) :: t
+              real(rk), intent(in) :: dt
+              integer, intent(in), optional :: mode
+              integer :: i
+              do
+                 t = t + dt
+                 self%h = eoshift(self%h, shift=-1, dim=2)
+                 self%h(:, 1) = self%a
+                 select case (optval(mode, 1))
+                 case (1)
+                    self%a = self%a/2
+                 case default
+                    self%a = -self%a
+                 end select
+                 if (t > 1.0_rk) exit
+              end do
+           end subroutine
+        end module
+    """)
+    c = ns["child"](3, scale=0.5)
+    assert c.a.lb == (0,) and np.array_equal(c.a.a, [1.0, 1.5, 2.0]) and c.h.a.shape == (3, 2)
+    t = Ref(0.0)
+    callm(c, "step", t, 0.4)
+    assert t.v == 0.4 + 0.4 + 0.4 and np.array_equal(c.a.a, np.array([1.0, 1.5, 2.0]) / 8)
+    assert np.array_equal(c.h.a[:, 0], np.array([1.0, 1.5, 2.0]) / 4) and np.array_equal(c.h.a[:, 1], np.array([1.0, 1.5, 2.0]) / 2)
+    callm(c, "step", t, 0.4, mode=2)
+    assert np.array_equal(c.a.a, -np.array([1.0, 1.5, 2.0]) / 8)
+    d = ns["child"](2)
+    assert d.scale == 2.0 and np.array_equal(d.a.a, [1.0, 3.0])
+
+
+def test_pointer_remapping_cycle_and_multi_index_concurrent(tmp_path):
+    ns = build(tmp_path, """
+        module m
+        contains
+           subroutine s(x, out)
+              real(rk), intent(in) :: x(0:)
+              real(rk), intent(out) :: out(:, :)
+              real(rk), target :: ext(-1:size(x))
+              real(rk), dimension(:), pointer :: xl
+              integer :: i, j, l
+              real(rk) :: p
+              ext(0:size(x) - 1) = x
+              ext(-1) = 2*ext(0) - ext(1)
+              ext(size(x)) = 2*ext(size(x) - 1) - ext(size(x) - 2)
+              xl(0:) => ext(lbound(ext, 1):ubound(ext, 1) - 1)    ! xl(i) = ext(i-1)
+              do concurrent(i=1:2, j=1:3)
+                 p = 1.0_rk
+                 do l = 0, 3
+                    if (l == j) cycle
+                    p = p*(xl(l) - xl(j))
+                 end do
+                 out(i, j) = p*i
+              end do
+           end subroutine
+        end module
+    """)
+    x = np.array([0.0, 1.0, 3.0])
+    out = np.zeros((2, 3), order="F")
+    ns["s"](FArr(x, (0,)), out)
+    xl = [-1.0, 0.0, 1.0, 3.0]
+    for i in (1, 2):
+        for j in (1, 2, 3):
+            p = 1.0
+            for l in range(4):
+                if l != j:
+                    p = p * (xl[l] - xl[j])
+            assert out[i - 1, j - 1] == p * i
+
+
+def test_unsupported_statements_fail_loudly(tmp_path):
+    with pytest.raises(NotImplementedError):
+        build(tmp_path, """
+            module m
+            contains
+               subroutine s(x)
+                  real(rk), intent(inout) :: x
+                  write (*, *) x
+               end subroutine
+            end module
+        """)
