@@ -124,15 +124,16 @@ def gen_grids(ns):
     return out
 
 
-def run_example1(ns, npts=100, snaps=(0, 1, 50, 100)):
-    """program example1 (example1:31-65): the driver loop is these few lines, everything it calls is translated source"""
+def run_example1(ns, npts=100, snaps=(0, 1, 50, 100), k=3, order=3):
+    """program example1 (example1:31-65): the driver loop is these few lines, everything it calls is translated source
+    (k and order are the two literals of lines 44 and 53)"""
     nc = 100
     gx = ns["new_grid1"]()
     callm(gx, "linear", -5.0, 5.0, nc)                    # example1:41
     ns["nc"], ns["gx"] = nc, gx
-    ns["myweno"] = ns["weno"](nc, 3, 1e-6)                 # example1:44
+    ns["myweno"] = ns["weno"](nc, k, 1e-6)                 # example1:44
     u = ns["ic"](gx.center)                               # example1:50
-    ode = ns["rktvd"](ns["rhs"], nc, 3)                    # example1:53
+    ode = ns["rktvd"](ns["rhs"], nc, order)                # example1:53
     time_end, dt, t = 12.0, 1e-2, Ref(0.0)                 # example1:56-58
     out, times = {}, []
     for ii in range(npts + 1):                             # example1:61-65
@@ -180,6 +181,11 @@ def run_example2(ns, n, npts, snaps, dt=5e-3, time_end=5.0, grids="linear", nonu
     return out
 
 
+# example1:98 is a stale commented alternative to line 99: `lax_friedrichs(flux, vr(i), vl(i+1), gx%r(i), t, alpha = 1.0_rk)`
+# (`gx%r` no longer exists in grid1).  BASELINE.json's first config names Lax-Friedrichs, so that line is swapped in with
+# its coordinate argument written as line 99 writes it.
+LAX_FRIEDRICHS = [("fedges(i) = godunov(flux, vr(i), vl(i + 1), [gx%right(i)], t)",
+                   "fedges(i) = lax_friedrichs(flux, vr(i), vl(i + 1), [gx%right(i)], t, alpha=1.0_rk)")]
 GROWTH = [("flux1 = v !*x(1)**2", "flux1 = v*x(1)**2"), ("flux2 = v !*x(1)*x(2)", "flux2 = v*x(1)*x(2)")]
 
 
@@ -194,6 +200,15 @@ def main():
     print(f"reconstruct / fluxes / tvdode / grids done ({time.time() - t0:.0f} s)", flush=True)
     np.savez(os.path.join(HERE, "ref_exec_example1.npz"), **run_example1(ns1))
     print(f"example1 as shipped, 101 outputs done ({time.time() - t0:.0f} s)", flush=True)
+    sweep = {}
+    for k in (1, 2, 3):  # the k x order sweep of BASELINE.json's ensemble config, on example1's problem (outputs 0..10)
+        for order in (1, 2, 3):
+            r = run_example1(load("example1_burgers_1d_fv.f90"), npts=10, snaps=(10,), k=k, order=order)
+            sweep[f"u_k{k}_o{order}"], sweep[f"t_k{k}_o{order}"], sweep[f"fevals_k{k}_o{order}"] = r["u_10"], r["times"], r["fevals"]
+    np.savez(os.path.join(HERE, "ref_exec_example1_sweep.npz"), **sweep)
+    np.savez(os.path.join(HERE, "ref_exec_example1_lf.npz"),
+             **run_example1(load("example1_burgers_1d_fv.f90", patch=LAX_FRIEDRICHS), npts=100, snaps=(0, 50, 100)))
+    print(f"example1 k x order sweep and Lax-Friedrichs variant done ({time.time() - t0:.0f} s)", flush=True)
     # example2's program with geometric grids, xedges and the growth terms its own comments hold (markers removed)
     nsg = load("example2_pbe_2d_fv.f90", patch=GROWTH)
     np.savez(os.path.join(HERE, "ref_exec_example2_growth.npz"),

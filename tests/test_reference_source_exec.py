@@ -105,6 +105,37 @@ def test_oracle_example1_equals_reference_source(pkg, ref):
     assert ode.fevals == int(g["fevals"]) == 3603 and repr(float(g["times"][-1])) == "12.009999999999788"
 
 
+def _example1_variant(pkg, make_ode, g_times, g_u, k, order, scheme=0, upto=10, snaps=None):
+    grid = pkg.hrweno_grids.grid1().linear(-5.0, 5.0, 100)
+    ode = make_ode(pkg.fv.make_desc(100, k=k, eps=1e-6, width=[grid.width], flux_scheme=scheme, alpha=1.0), order)
+    u, t = np.clip(1.0 + (-1.5 / 6.0) * (grid.center + 4.0), -0.5, 1.0), 0.0
+    for ii in range(upto + 1):
+        t = ode.integrate(u, t, 12.0 * ii / 100, 1e-2)
+        assert t == g_times[ii]
+        if snaps and ii in snaps:
+            assert np.array_equal(u, snaps[ii]), f"output {ii}: max diff {np.max(np.abs(u - snaps[ii])):.3e}"
+    if g_u is not None:
+        assert np.array_equal(u, g_u), f"k={k} order={order}: max diff {np.max(np.abs(u - g_u)):.3e}"
+    return ode
+
+
+@pytest.mark.parametrize("order", [1, 2, 3])
+@pytest.mark.parametrize("k", [1, 2, 3])
+def test_oracle_example1_k_order_sweep_equals_reference_source(pkg, ref, k, order):
+    """WENO k = 1..3 x rktvd order 1..3 (the sweep of BASELINE.json's ensemble config) on example1's problem"""
+    g = gold("example1_sweep")
+    ode = _example1_variant(pkg, lambda d, o: ref.rktvd(ref.FV(d), o), g[f"t_k{k}_o{order}"], g[f"u_k{k}_o{order}"], k, order)
+    assert ode.fevals == int(g[f"fevals_k{k}_o{order}"])
+
+
+def test_oracle_example1_lax_friedrichs_equals_reference_source(pkg, ref):
+    """BASELINE.json's first config names Lax-Friedrichs: example1 with its stale line 98 swapped in (alpha = 1)"""
+    g = gold("example1_lf")
+    snaps = {ii: g[f"u_{ii}"] for ii in (0, 50, 100)}
+    ode = _example1_variant(pkg, lambda d, o: ref.rktvd(ref.FV(d), o), g["times"], None, 3, 3, scheme=1, upto=100, snaps=snaps)
+    assert ode.fevals == int(g["fevals"]) == 3603
+
+
 def _example2(pkg, make_ode, g, n1, n2, dt, time_end, growth=False, mod=None):
     e1, e2 = g["edges1"], g["edges2"]
     w1, w2, c1, c2 = e1[1:] - e1[:-1], e2[1:] - e2[:-1], (e1[:-1] + e1[1:]) / 2, (e2[:-1] + e2[1:]) / 2

@@ -4,7 +4,7 @@ Bar: bit-identical (strict mode / the general kernel).  Sorted last on purpose (
 import numpy as np
 import pytest
 
-from test_reference_source_exec import _example1, _example2, gold
+from test_reference_source_exec import _example1, _example1_variant, _example2, gold
 
 @pytest.mark.gpu
 def test_gpu_example1_equals_reference_source(gpu_lib, pkg):
@@ -36,3 +36,21 @@ def test_gpu_reconstruct_equals_reference_source(gpu_lib, pkg, k):
         for vname in ("pulse", "rand"):
             vl, vr = w.reconstruct(g["v_" + vname])
             assert np.array_equal(vl, g[f"vl_{gname}_{vname}_k{k}"]) and np.array_equal(vr, g[f"vr_{gname}_{vname}_k{k}"])
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("order", [1, 2, 3])
+@pytest.mark.parametrize("k", [1, 2, 3])
+def test_gpu_example1_k_order_sweep_equals_reference_source(gpu_lib, pkg, k, order):
+    g = gold("example1_sweep")
+    make = lambda d, o: pkg.hrweno_tvdode.rktvd(pkg.fv.FV(d), 100, o)  # noqa: E731
+    ode = _example1_variant(pkg, make, g[f"t_k{k}_o{order}"], g[f"u_k{k}_o{order}"], k, order)
+    assert ode.fevals == int(g[f"fevals_k{k}_o{order}"])
+
+
+@pytest.mark.gpu
+def test_gpu_example1_lax_friedrichs_equals_reference_source(gpu_lib, pkg):
+    g = gold("example1_lf")
+    snaps = {ii: g[f"u_{ii}"] for ii in (0, 50, 100)}
+    make = lambda d, o: pkg.hrweno_tvdode.rktvd(pkg.fv.FV(d), 100, o)  # noqa: E731
+    _example1_variant(pkg, make, g["times"], None, 3, 3, scheme=1, upto=100, snaps=snaps)
