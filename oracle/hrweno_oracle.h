@@ -13,7 +13,8 @@
  *      statement by statement into Python and runs them on IEEE binary64 (nothing
  *      restated by hand); this file reproduces those outputs BIT FOR BIT --
  *      reconstruct, calc_cnu, both fluxes, rktvd 1-3 / mstvd, example1 as shipped over
- *      all 101 outputs, example2 (40x40 over all outputs, 250x250 first outputs) and
+ *      all 101 outputs (+ k x order sweep, Lax-Friedrichs variant), example2 (40x40 over
+ *      all outputs, 250x250 first outputs) and
  *      example2 with geometric grids + growth terms (fixtures tests/golden/ref_exec_*.npz,
  *      generator tests/golden/make_ref_exec_golden.py, tests/test_reference_source_exec.py);
  *   2. to every assertion of the reference's own test-drive suites (test/test_hrweno.f90,
