@@ -1108,20 +1108,24 @@ class Program:
 
 
 class CallScope:
-    """scope view used for the target of a CALL statement: the leading name is always a procedure"""
+    """scope view used for the target of `call name(args)`: the leading name is a procedure even if nothing declares it"""
 
     def __init__(self, scope):
         self._s = scope
         self.refs = scope.refs
+        self._first = True
 
     def rename(self, name):
         return self._s.rename(name)
 
     def is_callable(self, name):
-        return True if not hasattr(self, "_used") and not setattr(self, "_used", True) else self._s.is_callable(name)
+        if self._first:  # the designator translator asks once for the leading name, then for names inside the arguments
+            self._first = False
+            return True
+        return self._s.is_callable(name)
 
     def is_method(self, comp):
-        return True
+        return self._s.is_method(comp)
 
 
 def _elemental(fn):
