@@ -146,7 +146,7 @@ def run_reference(args, rank, world):
         "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * el / args.steps,
         "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
         "config": {"workload": "cfg3: 1D Burgers WENO5+Godunov+RK3, linear grid [-5,5], ramp+1e-3*N(0,1) IC, dt=0.1dx",
-                   "cells_per_step": n, "note": "C restatement of the reference (oracle), not gfortran"},
+                   "cells_per_step": n, "note": "C restatement of the reference (oracle, bit-identical to the executed reference source), not a gfortran build"},
         "cpu_baseline": {"value": value, "unit": "cell-updates/s", "cores": cores, "kind": "port", "sample": sample},
         "e2e": {"value": value, "unit": "cell-updates/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
     }))
@@ -321,7 +321,7 @@ def main():
             "workload": "cfg3: 1D Burgers WENO5(k=3,eps=1e-6)+Godunov+rktvd(3), 2^%d cells per GPU, linear grid [-5,5], "
                         "ramp+1e-3*N(0,1) IC (rng 12345), dt=0.1dx" % args.log2_cells,
             "cells_per_gpu": n, "mode": args.mode,
-            "parity": "strict = bit-identical to the oracle; fast = within 1e-12 normwise per output time (tests/test_gpu_parity.py)",
+            "parity": "strict = bit-identical to the oracle, which is bit-identical to the reference's source text executed by tools/f90exec (tests/test_reference_source_exec.py); fast = within 1e-12 normwise per output time (tests/test_gpu_parity.py)",
             "parallelism": "slab x%d (halo k=3 per stage over NVLink peer memory)" % world if world > 1 else "1 GPU",
             "l2": "state vectors are 2 GiB each, far larger than the 126 MB L2 (no flush needed)",
             "unit_note": "one cell-update = one cell-stage (rhs + stage combination); cell-steps/s = value/3",
