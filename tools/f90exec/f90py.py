@@ -309,7 +309,13 @@ def _elementwise(fn):
     return lambda x: FArr(fn(x.a)) if isinstance(x, FArr) else float(fn(x))
 
 
+def _reshape(x, shape):
+    shp = [int(v) for v in (shape.a.ravel().tolist() if isinstance(shape, FArr) else shape)]
+    return FArr(np.reshape(x.a, shp, order="F"))
+
+
 INTRINSICS = {
+    "reshape": _reshape,
     "sum": _seq_sum,
     "size": _size,
     "lbound": _lbound,
@@ -334,7 +340,7 @@ INTRINSICS = {
 }
 
 
-def callm(obj, name, *args, **kw):
+def callm(obj, name, /, *args, **kw):
     """`call obj%name(...)`: a type-bound procedure (passed-object first) or a procedure-pointer component (nopass)"""
     bound = type(obj)._bindings.get(name) if hasattr(type(obj), "_bindings") else None
     if bound is not None:
@@ -514,6 +520,9 @@ class ExprTranslator:
         if k == "name" and v.lower() in self.scope.refs and nv in (",", ")"):
             self.take()
             return v.lower()
+        if k == "name" and v.lower() in getattr(self.scope, "byref_tmp", ()) and nv in (",", ")"):
+            self.take()
+            return self.scope.byref_tmp[v.lower()]
         return self.expr()
 
     def section_or_expr(self, close):
@@ -545,6 +554,22 @@ class ExprTranslator:
             self.take(")")
             return f"({e})"
         if v == "[":
+            if self.at("("):  # implied do: [(expr, var = lo, hi)]
+                save = self.i
+                try:
+                    self.take("(")
+                    e = self.expr()
+                    self.take(",")
+                    var = self.take()[1].lower()
+                    self.take("=")
+                    lo = self.expr()
+                    self.take(",")
+                    hi = self.expr()
+                    self.take(")")
+                    self.take("]")
+                    return f"FArr.from_list([{e} for {var} in frange({lo}, {hi})])"
+                except NotImplementedError:
+                    self.i = save
             items = self.arglist("]")
             return f"FArr.from_list([{', '.join(items)}])"
         if k != "name":
@@ -557,8 +582,9 @@ class ExprTranslator:
         while True:
             if self.at("("):
                 self.take()
+                is_call = first and self.scope.is_callable(name)  # decided before the arguments are translated
                 args = self.arglist(")")
-                if first and self.scope.is_callable(name):
+                if is_call:
                     cur = f"{cur}({', '.join(args)})"
                 else:
                     cur = f"{cur}[{', '.join(args)}]"
@@ -587,6 +613,8 @@ class Scope:
         self.refs = set()      # scalar dummies passed by reference: read as name.v
         self.result = None     # (fortran name, python name) of the function result
         self.locals = set()
+        self.scalar_locals = set()  # non-dummy real / integer / logical scalars (passed by reference in CALLs)
+        self.byref_tmp = {}
 
     def rename(self, name):
         if self.result and name == self.result[0]:
@@ -645,7 +673,8 @@ def split_top(s, sep=","):
 class Program:
     """all program units of a set of source files, translated into one Python namespace"""
 
-    def __init__(self):
+    def __init__(self, skip_io=False):
+        self.skip_io = skip_io  # `write` / `print` statements become no-ops (test programs print diagnostics)
         self.procs = {}     # name -> unit
         self.generics = {}  # generic interface name -> specific procedure
         self.types = {}     # type name -> dict(parent, comps=[(name, default_src)], bindings={})
@@ -827,6 +856,9 @@ class Program:
                 scope.locals.add(nm)
                 if info["base"].startswith("procedure") and nm in args:
                     unit["proc_dummies"].add(nm)
+        for nm, (dims, init, info, no) in decls.items():
+            if nm not in args and dims is None and not info["parameter"] and info["base"].startswith(("real", "integer", "logical")):
+                scope.scalar_locals.add(nm)
         res = unit["res"] if is_fn else None
         if is_fn:
             scope.result = (res, "res_")
@@ -905,6 +937,8 @@ class Program:
             return emit(ind, "break")
         if low == "cycle":
             return emit(ind, "continue")
+        if self.skip_io and re.match(r"^(write\s*\(|print\b)", low):
+            return emit(ind, "pass")
         if low.startswith("error stop"):
             arg = ln[10:].strip()
             return emit(ind, f"raise FortranStop({self.ex(arg, scope) if arg else repr('error stop')})")
@@ -912,6 +946,15 @@ class Program:
             target = ln[5:].strip()
             if "(" not in target:
                 target += "()"
+            # local scalar variables given as bare actual arguments are passed by reference (the callee may define them)
+            byref = {}
+            inner = target[target.index("(") + 1 : target.rindex(")")] if "(" in target else ""
+            for a in split_top(inner):
+                a = a.strip().lower()
+                if a in scope.scalar_locals and a not in scope.refs:
+                    byref[a] = f"{a}__ref"
+                    emit(ind, f"{a}__ref = Ref({scope.rename(a)})")
+            scope.byref_tmp = byref
             flat, depth = "", 0  # the designator with its parenthesised groups removed: a%b(..)%c(..) -> a%b%c
             for ch in target:
                 depth += ch == "("
@@ -919,7 +962,11 @@ class Program:
                     flat += ch
                 depth -= ch == ")"
             tr = ExprTranslator(tokenize(target), CallScope(scope) if "%" not in flat else scope)
-            return emit(ind, tr.expr())
+            emit(ind, tr.expr())
+            for a, tmp in byref.items():
+                emit(ind, f"{scope.rename(a)} = {tmp}.v")
+            scope.byref_tmp = {}
+            return None
         if low.startswith("allocate"):
             inner = ln[ln.index("(") + 1 : ln.rindex(")")]
             for ent in split_top(inner):
@@ -1049,6 +1096,7 @@ class Program:
         """translate everything and exec it into the namespace; returns the namespace"""
         ns = self.ns
         ns["np"] = np
+        ns.setdefault("rk", 8)  # the kind parameter of hrweno_kinds (real64); only ever used as a kind argument
         dummy = Scope({"proc_dummies": set()}, self)
         # derived types -> Python classes with the declared default component values
         for tname, td in self.types.items():
@@ -1077,7 +1125,7 @@ class Program:
             for nm, dims, init, info in self._decl_entities(ln):
                 if dims is not None:
                     m = re.match(r"^reshape\s*\(\s*\[(.*)\]\s*,\s*\[(.*?)\]\s*(?:,\s*order\s*=\s*\[(.*?)\])?\s*\)$", init, re.I | re.S)
-                    bnds = [(int(eval(lo, {})), int(eval(hi, {}))) for lo, hi in self._bounds(dims, dummy)]
+                    bnds = [(int(eval(lo, ns)), int(eval(hi, ns))) for lo, hi in self._bounds(dims, dummy)]
                     arr = FArr.alloc(bnds)
                     if m:
                         vals = [eval(self.ex(v, dummy), ns) for v in split_top(m.group(1))]
@@ -1113,6 +1161,7 @@ class CallScope:
     def __init__(self, scope):
         self._s = scope
         self.refs = scope.refs
+        self.byref_tmp = scope.byref_tmp
         self._first = True
 
     def rename(self, name):
