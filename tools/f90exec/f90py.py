@@ -379,7 +379,9 @@ def logical_lines(text):
         if line.endswith("&"):
             buf += line[:-1].rstrip() + " "
             continue
-        out.append((start, buf + line))
+        for stmt in split_top(buf + line, ";"):  # `a = 1; b = 2` is two statements
+            if stmt:
+                out.append((start, stmt))
         buf = ""
     return out
 
@@ -1030,6 +1032,10 @@ class Program:
                 elif low.startswith("if") and (m := self._one_line_if(ln)):
                     emit(ind, f"if {self.ex(m[0], scope)}:")
                     self._gen_stmt(no, m[1], scope, emit, ind + 1, unit)
+                elif m := re.match(r"^do\s+while\s*\((.*)\)$", ln, re.I):
+                    emit(ind, f"while {self.ex(m.group(1), scope)}:")
+                    self._do_stack.append(0)
+                    ind += 1
                 elif low == "do":
                     emit(ind, "while True:")
                     self._do_stack.append(0)
