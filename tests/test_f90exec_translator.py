@@ -224,7 +224,7 @@ def test_fortran_shim_parses_as_far_as_the_translator_can_tell():
             assert kind is None or top[0] == kind, f"line {no}: `{ln}` closes {top}"
             continue
         for rx, kind in openers:
-            if re.match(rx, low) and not low.startswith(("module procedure", "type(", "procedure")):
+            if re.match(rx, low) and not low.startswith(("module procedure", "procedure")) and not (kind == "type" and low.startswith("type(")):
                 stack.append((kind, no, ln[:60]))
                 break
     assert not stack, f"unclosed constructs: {stack}"
