@@ -124,10 +124,9 @@ def gen_grids(ns):
     return out
 
 
-def run_example1(ns, npts=100, snaps=(0, 1, 50, 100), k=3, order=3):
+def run_example1(ns, npts=100, snaps=(0, 1, 50, 100), k=3, order=3, nc=100):
     """program example1 (example1:31-65): the driver loop is these few lines, everything it calls is translated source
-    (k and order are the two literals of lines 44 and 53)"""
-    nc = 100
+    (nc, k and order are the literals of lines 34, 44 and 53)"""
     gx = ns["new_grid1"]()
     callm(gx, "linear", -5.0, 5.0, nc)                    # example1:41
     ns["nc"], ns["gx"] = nc, gx

@@ -194,3 +194,54 @@ def test_fixtures_are_reproducible_from_the_reference_tree():
     g, live = gold("example1"), m.run_example1(ns, npts=3, snaps=(0, 1))
     assert np.array_equal(live["u_0"], g["u_0"]) and np.array_equal(live["u_1"], g["u_1"])
     assert np.array_equal(live["times"], g["times"][:4])
+
+
+@pytest.mark.skipif(not os.path.isdir(os.path.join(REFERENCE, "src")), reason="the reference tree is not on this machine")
+def test_oracle_equals_executed_reference_source_on_random_inputs(ref):
+    """beyond the frozen fixtures: random sizes (including ncells smaller than the stencil), orders, smoothing factors,
+    value scales and non-uniform grids -- reconstruct and calc_cnu of the executed source vs the C oracle, bit for bit"""
+    sys.path.insert(0, GOLD)
+    import make_ref_exec_golden as m
+    from f90py import FArr, callm
+
+    ns = m.load()
+    rng = np.random.default_rng(777)
+    for trial in range(120):
+        nc = int(rng.choice([1, 2, 3, 4, 5, 7, 16, 33]))
+        k = int(rng.integers(1, 4))
+        eps = float(10.0 ** rng.uniform(-12, -2))
+        scale = float(10.0 ** rng.uniform(-6, 6))
+        v = scale * rng.standard_normal(nc)
+        if trial % 3 == 0:
+            v[rng.integers(0, nc)] = 0.0
+        nonuniform = trial % 2 == 1 and nc >= 2
+        if nonuniform:
+            xe = np.concatenate([[0.0], np.cumsum(rng.uniform(0.1, 3.0, nc))])
+            w = ns["weno"](nc, k, eps, FArr(xe, (0,)))
+            cnu = ref.calc_cnu(xe, k)
+            assert np.array_equal(cnu, np.transpose(w.cnu.a, (2, 1, 0))), (trial, nc, k)
+        else:
+            w, cnu = ns["weno"](nc, k, eps), None
+        vl, vr = np.zeros(nc), np.zeros(nc)
+        callm(w, "reconstruct", v, vl, vr)
+        rl, rr = ref.reconstruct(v, k, eps, cnu=cnu)
+        assert np.array_equal(vl, rl) and np.array_equal(vr, rr), (trial, nc, k, eps, nonuniform)
+
+
+@pytest.mark.skipif(not os.path.isdir(os.path.join(REFERENCE, "src")), reason="the reference tree is not on this machine")
+def test_oracle_equals_executed_example1_program_on_small_and_odd_grids(pkg, ref):
+    """example1's program (grid1%linear, ic, rhs, godunov, rktvd) executed from source at grid sizes down to 2 cells,
+    every WENO order and RK order: the oracle's fused rhs + integrators, bit for bit, including t and fevals"""
+    sys.path.insert(0, GOLD)
+    import make_ref_exec_golden as m
+
+    for nc, k, order in [(2, 3, 3), (3, 2, 2), (4, 3, 1), (5, 1, 3), (7, 3, 3), (17, 2, 3), (33, 3, 2)]:
+        live = m.run_example1(m.load("example1_burgers_1d_fv.f90"), npts=4, snaps=(4,), k=k, order=order, nc=nc)
+        grid = pkg.hrweno_grids.grid1().linear(-5.0, 5.0, nc)
+        assert np.array_equal(grid.width, live["width"]) and np.array_equal(grid.center, live["center"])
+        ode = ref.rktvd(ref.FV(pkg.fv.make_desc(nc, k=k, eps=1e-6, width=[grid.width])), order)
+        u, t = np.clip(1.0 + (-1.5 / 6.0) * (grid.center + 4.0), -0.5, 1.0), 0.0
+        for ii in range(5):
+            t = ode.integrate(u, t, 12.0 * ii / 100, 1e-2)
+            assert t == live["times"][ii]
+        assert np.array_equal(u, live["u_4"]) and ode.fevals == live["fevals"], (nc, k, order)
