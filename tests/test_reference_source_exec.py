@@ -245,3 +245,17 @@ def test_oracle_equals_executed_example1_program_on_small_and_odd_grids(pkg, ref
             t = ode.integrate(u, t, 12.0 * ii / 100, 1e-2)
             assert t == live["times"][ii]
         assert np.array_equal(u, live["u_4"]) and ode.fevals == live["fevals"], (nc, k, order)
+
+
+@pytest.mark.skipif(not os.path.isdir(os.path.join(REFERENCE, "src")), reason="the reference tree is not on this machine")
+def test_oracle_equals_executed_example2_program_on_small_rectangular_grids(pkg, ref):
+    """example2's program (2D split rhs with strided column sections, zero-flux walls, mstvd start-up + multistep) executed
+    from source on small n1 /= n2 grids, with and without geometric grids + xedges + growth terms"""
+    sys.path.insert(0, GOLD)
+    import make_ref_exec_golden as m
+
+    for n1, n2, growth in [(2, 2, False), (3, 5, False), (7, 4, False), (12, 9, False), (5, 3, True), (9, 11, True)]:
+        ns = m.load("example2_pbe_2d_fv.f90", patch=m.GROWTH if growth else None)
+        kw = dict(grids="geometric", nonuniform=True, dt=2.5e-4, time_end=0.5) if growth else {}
+        live = m.run_example2(ns, n1, 2, (0, 2), n2=n2, **kw)
+        _example2(pkg, ref.mstvd, live, n1, n2, kw.get("dt", 5e-3), kw.get("time_end", 5.0), growth=growth, mod=ref)
