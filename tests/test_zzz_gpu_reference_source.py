@@ -54,3 +54,21 @@ def test_gpu_example1_lax_friedrichs_equals_reference_source(gpu_lib, pkg):
     snaps = {ii: g[f"u_{ii}"] for ii in (0, 50, 100)}
     make = lambda d, o: pkg.hrweno_tvdode.rktvd(pkg.fv.FV(d), 100, o)  # noqa: E731
     _example1_variant(pkg, make, g["times"], None, 3, 3, scheme=1, upto=100, snaps=snaps)
+
+
+@pytest.mark.gpu
+def test_gpu_fast_mode_example1_within_north_star_tolerance_of_reference_source(gpu_lib, pkg):
+    """north star: within 1e-12 relative (normwise) of the reference at every output time -- fast arithmetic mode against
+    example1 as executed from the reference's source (stored outputs 0, 1, 50, 100)"""
+    g = gold("example1")
+    d = pkg.fv.make_desc(100, k=3, eps=1e-6, width=[g["width"]], mode=pkg._abi.MODE_FAST)
+    ode = pkg.hrweno_tvdode.rktvd(pkg.fv.FV(d), 100, 3)
+    u, t = np.clip(1.0 + (-1.5 / 6.0) * (g["center"] + 4.0), -0.5, 1.0), 0.0
+    worst = 0.0
+    for ii in range(101):
+        t = ode.integrate(u, t, 12.0 * ii / 100, 1e-2)
+        assert t == g["times"][ii]
+        if f"u_{ii}" in g:
+            r = g[f"u_{ii}"]
+            worst = max(worst, float(np.max(np.abs(u - r)) / np.max(np.abs(r))))
+    assert worst <= 1e-12, f"fast-mode drift {worst:.3e}"
