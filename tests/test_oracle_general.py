@@ -111,3 +111,23 @@ def test_general_setters_validate(pkg, ref):
     assert L.hrweno_ref_fv_set_xedges(f._h, 1, g.edges.ctypes.data) == pkg._abi.EINVAL  # a 1D operator has no axis 1
     assert L.hrweno_ref_fv_set_flux_coef(f._h, 0, g.edges.ctypes.data, g.center.ctypes.data) == pkg._abi.EINVAL  # cross needs 2D
     assert L.hrweno_ref_fv_set_flux_coef(f._h, 0, g.edges.ctypes.data, None) == pkg._abi.OK
+
+
+@pytest.mark.parametrize("k", [1, 2, 3])
+def test_slab_tables_from_global_edges(ref, k):
+    """design fact for a slab decomposition of the non-uniform path: cnu(:,:,i) reads the edges
+    i-k .. i+k (weno.f90:263-292: xl(i-r+m) with r = -1..k-1, m = 0..k), so the tables of a slab [off, off+n) computed from
+    its own edges plus k-1 neighbour edges on the left and k on the right are the global tables bit for bit; one edge
+    fewer on the right and they are not"""
+    rng = np.random.default_rng(k)
+    nc = 60
+    xe = np.concatenate([[0.0], np.cumsum(rng.uniform(0.1, 2.0, nc))])
+    glob = ref.calc_cnu(xe, k)
+    for off, n in ((0, 20), (20, 20), (40, 20), (7, 3), (55, 5)):
+        lo, hi = max(0, off - (k - 1)), min(nc, off + n + k)
+        loc = ref.calc_cnu(xe[lo : hi + 1], k)
+        assert np.array_equal(loc[off - lo : off - lo + n], glob[off : off + n])
+    lo, hi = 20 - (k - 1), 40 + k - 1  # one neighbour edge too few on the right
+    loc = ref.calc_cnu(xe[lo : hi + 1], k)
+    if k >= 2:  # k = 1 reconstructs cell averages: its tables are 1 on any grid
+        assert not np.array_equal(loc[20 - lo : 20 - lo + 20], glob[20:40])
