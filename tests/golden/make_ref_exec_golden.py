@@ -3,8 +3,10 @@
 
 The reference is Fortran and no Fortran compiler exists in this image, so the reference binary cannot be run.  What can
 be done is what this script does: tools/f90exec/f90py.py translates the procedures of /root/reference/src/*.f90 and of
-the two example programs statement by statement into Python (no algorithm is restated by hand -- operation order,
-`sum()`, sections, bounds, control flow come from the source lines) and runs them on IEEE binary64.  The outputs are
+the two example programs -- their main programs included -- statement by statement into Python (no algorithm or driver
+loop is restated by hand: operation order, `sum()`, sections, bounds, control flow come from the source lines; only the
+formatted-output routine `output` is replaced by a hook that records `u` and `time`) and runs them on IEEE binary64.
+Variants patch literals of the source text (grid size, k, order, dt), listed where they are applied.  The outputs are
 committed as fixtures because /root/reference does not travel to the GPU box; tests/test_reference_source_exec.py holds
 the C oracle (and through it the CUDA path) to these fixtures bit for bit and, when /root/reference is present,
 re-executes a part of them live.
@@ -28,6 +30,7 @@ import f90py  # noqa: E402
 from f90py import FArr, Ref, callm  # noqa: E402
 
 REF = os.environ.get("HRWENO_REFERENCE", "/root/reference")
+OUT = os.environ.get("HRWENO_GOLDEN_OUT", HERE)  # where the fixtures are written (default: next to this script)
 SRC = ("src/hrweno_weno.f90", "src/hrweno_fluxes.f90", "src/hrweno_tvdode.f90", "src/hrweno_grids.f90")
 
 
@@ -124,59 +127,87 @@ def gen_grids(ns):
     return out
 
 
-def run_example1(ns, npts=100, snaps=(0, 1, 50, 100), k=3, order=3, nc=100):
-    """program example1 (example1:31-65): the driver loop is these few lines, everything it calls is translated source
-    (nc, k and order are the literals of lines 34, 44 and 53)"""
-    gx = ns["new_grid1"]()
-    callm(gx, "linear", -5.0, 5.0, nc)                    # example1:41
-    ns["nc"], ns["gx"] = nc, gx
-    ns["myweno"] = ns["weno"](nc, k, 1e-6)                 # example1:44
-    u = ns["ic"](gx.center)                               # example1:50
-    ode = ns["rktvd"](ns["rhs"], nc, order)                # example1:53
-    time_end, dt, t = 12.0, 1e-2, Ref(0.0)                 # example1:56-58
-    out, times = {}, []
-    for ii in range(npts + 1):                             # example1:61-65
-        time_out = time_end * ii / 100
-        callm(ode, "integrate", u, t, time_out, dt)
-        times.append(t.v)
+class _Stop(Exception):
+    """raised by the output hook to end a program after the outputs that are wanted"""
+
+
+def run_program(ns, main, npts, snaps, state=("u", "time")):
+    """run the example's OWN main program (translated like everything else).  The programs call `output(2)` after every
+    `integrate` (example1:64, example2:65); `output` itself is formatted file I/O and is replaced by a hook that records
+    the state -- nothing else of the program is touched.  Stops after output number `npts`."""
+    rec = {"times": [], "n": 0}
+
+    def output(action):
+        if val_int(action) != 2:
+            return
+        ii = rec["n"]
+        rec["times"].append(ns[state[1]])
         if ii in snaps:
-            out[f"u_{ii}"] = u.a.copy()
-    out.update(times=np.array(times), fevals=ode.fevals, edges=gx.edges.a.copy(), width=gx.width.a.copy(), center=gx.center.a.copy())
+            rec[f"u_{ii}"] = ns[state[0]].a.copy()
+        rec["n"] += 1
+        if ii >= npts:
+            raise _Stop
+
+    ns["output"] = output
+    try:
+        ns[main]()
+    except _Stop:
+        pass
+    out = {k: v for k, v in rec.items() if k.startswith("u_")}
+    out["times"], out["fevals"] = np.array(rec["times"]), ns["ode"].fevals
     return out
 
 
-def setup_example2(ns, n1, n2, grids="linear", nonuniform=False):
-    nc = FArr(np.array([n1, n2], dtype=np.int64))
-    gx, myweno = FArr(np.empty(2, dtype=object)), FArr(np.empty(2, dtype=object))
-    for i, n in ((1, n1), (2, n2)):
-        g = ns["new_grid1"]()
-        if grids == "linear":
-            callm(g, "linear", 0.0, 10.0, n)               # example2:38-39
-        else:
-            callm(g, "geometric", 0.0, 10.0, (1.02, 1.03)[i - 1], n)
-        gx[i] = g
-        myweno[i] = ns["weno"](n, 3, 1e-6, g.edges) if nonuniform else ns["weno"](n, 3, 1e-6)  # example2:42-43
-    ns["nc"], ns["gx"], ns["myweno"] = nc, gx, myweno
-    u = FArr(np.zeros(n1 * n2))
-    for j in range(1, n2 + 1):                             # example2:49-51
-        for i in range(1, n1 + 1):
-            u[(j - 1) * n1 + i] = ns["ic"](FArr.from_list([gx[1].center[i], gx[2].center[j]]))
-    return gx, u
+def val_int(x):
+    return int(f90py.val(x))
 
 
-def run_example2(ns, n, npts, snaps, dt=5e-3, time_end=5.0, grids="linear", nonuniform=False, n2=None):
-    """program example2 (example2:25-69)"""
+def ex1_patch(k=3, order=3, nc=100):
+    """the three literals of example1 that the sweeps vary (lines 34, 44, 53)"""
+    p = []
+    if nc != 100:
+        p.append(("integer, parameter :: nc = 100", f"integer, parameter :: nc = {nc}"))
+    if k != 3:
+        p.append(("myweno = weno(ncells=nc, k=3, eps=1e-6_rk)", f"myweno = weno(ncells=nc, k={k}, eps=1e-6_rk)"))
+    if order != 3:
+        p.append(("ode = rktvd(rhs, nc, order=3)", f"ode = rktvd(rhs, nc, order={order})"))
+    return p
+
+
+def run_example1(npts=100, snaps=(0, 1, 50, 100), k=3, order=3, nc=100, extra_patch=()):
+    """program example1_burgers_1d_fv, all of it, from the source"""
+    ns = load("example1_burgers_1d_fv.f90", patch=ex1_patch(k, order, nc) + list(extra_patch))
+    out = run_program(ns, "main_example1_burgers_1d_fv", npts, snaps)
+    gx = ns["gx"]
+    out.update(edges=gx.edges.a.copy(), width=gx.width.a.copy(), center=gx.center.a.copy())
+    return out
+
+
+def run_example2(n, npts, snaps, dt=5e-3, time_end=5.0, grids="linear", nonuniform=False, n2=None, growth=False):
+    """program example_pbe_2d_fv from the source; `n`, `dt`, `time_end` patch its literals (lines 28, 57-58); grids =
+    "geometric" swaps the two `linear` calls for `geometric` ones and hands the edges to `weno(...)` (what a user of
+    non-uniform grids writes, weno.f90:100-112); growth removes the comment markers of lines 140, 153"""
     n2 = n if n2 is None else n2
-    gx, u = setup_example2(ns, n, n2, grids, nonuniform)
-    ode = ns["mstvd"](ns["rhs"], n * n2)                   # example2:54
-    t, out, times = Ref(0.0), {}, []
-    for ii in range(npts + 1):                             # example2:61-66
-        time_out = time_end * ii / 100
-        callm(ode, "integrate", u, t, time_out, dt)
-        times.append(t.v)
-        if ii in snaps:
-            out[f"u_{ii}"] = u.a.copy()
-    out.update(times=np.array(times), fevals=ode.fevals, edges1=gx[1].edges.a.copy(), edges2=gx[2].edges.a.copy())
+    p = []
+    if (n, n2) != (250, 250):
+        p.append(("nc(2) = [250, 250]", f"nc(2) = [{n}, {n2}]"))
+    if dt != 5e-3:
+        p.append(("dt = 5e-3_rk", f"dt = {dt!r}_rk"))
+    if time_end != 5.0:
+        p.append(("time_end = 5.0_rk", f"time_end = {time_end!r}_rk"))
+    if grids == "geometric":
+        for i, ratio in ((1, 1.02), (2, 1.03)):
+            p.append((f"call gx({i})%linear(xmin=0.0_rk, xmax=10.0_rk, ncells=nc({i}))",
+                      f"call gx({i})%geometric(xmin=0.0_rk, xmax=10.0_rk, ratio={ratio!r}_rk, ncells=nc({i}))"))
+    if nonuniform:
+        for i in (1, 2):
+            p.append((f"myweno({i}) = weno(ncells=nc({i}), k=k, eps=1e-6_rk)",
+                      f"myweno({i}) = weno(ncells=nc({i}), k=k, eps=1e-6_rk, xedges=gx({i})%edges)"))
+    if growth:
+        p += GROWTH
+    ns = load("example2_pbe_2d_fv.f90", patch=p)
+    out = run_program(ns, "main_example_pbe_2d_fv", npts, snaps)
+    out.update(edges1=ns["gx"][1].edges.a.copy(), edges2=ns["gx"][2].edges.a.copy())
     return out
 
 
@@ -192,35 +223,32 @@ def main():
     quick = "--quick" in sys.argv
     t0 = time.time()
     ns1 = load("example1_burgers_1d_fv.f90")
-    np.savez(os.path.join(HERE, "ref_exec_reconstruct.npz"), **gen_reconstruct(ns1))
-    np.savez(os.path.join(HERE, "ref_exec_fluxes.npz"), **gen_fluxes(ns1))
-    np.savez(os.path.join(HERE, "ref_exec_tvdode.npz"), **gen_tvdode(ns1))
-    np.savez(os.path.join(HERE, "ref_exec_grids.npz"), **gen_grids(ns1))
+    np.savez(os.path.join(OUT, "ref_exec_reconstruct.npz"), **gen_reconstruct(ns1))
+    np.savez(os.path.join(OUT, "ref_exec_fluxes.npz"), **gen_fluxes(ns1))
+    np.savez(os.path.join(OUT, "ref_exec_tvdode.npz"), **gen_tvdode(ns1))
+    np.savez(os.path.join(OUT, "ref_exec_grids.npz"), **gen_grids(ns1))
     print(f"reconstruct / fluxes / tvdode / grids done ({time.time() - t0:.0f} s)", flush=True)
-    np.savez(os.path.join(HERE, "ref_exec_example1.npz"), **run_example1(ns1))
+    np.savez(os.path.join(OUT, "ref_exec_example1.npz"), **run_example1())
     print(f"example1 as shipped, 101 outputs done ({time.time() - t0:.0f} s)", flush=True)
     sweep = {}
     for k in (1, 2, 3):  # the k x order sweep of BASELINE.json's ensemble config, on example1's problem (outputs 0..10)
         for order in (1, 2, 3):
-            r = run_example1(load("example1_burgers_1d_fv.f90"), npts=10, snaps=(10,), k=k, order=order)
+            r = run_example1(npts=10, snaps=(10,), k=k, order=order)
             sweep[f"u_k{k}_o{order}"], sweep[f"t_k{k}_o{order}"], sweep[f"fevals_k{k}_o{order}"] = r["u_10"], r["times"], r["fevals"]
-    np.savez(os.path.join(HERE, "ref_exec_example1_sweep.npz"), **sweep)
-    np.savez(os.path.join(HERE, "ref_exec_example1_lf.npz"),
-             **run_example1(load("example1_burgers_1d_fv.f90", patch=LAX_FRIEDRICHS), npts=100, snaps=(0, 50, 100)))
+    np.savez(os.path.join(OUT, "ref_exec_example1_sweep.npz"), **sweep)
+    np.savez(os.path.join(OUT, "ref_exec_example1_lf.npz"),
+             **run_example1(npts=100, snaps=(0, 50, 100), extra_patch=LAX_FRIEDRICHS))
     print(f"example1 k x order sweep and Lax-Friedrichs variant done ({time.time() - t0:.0f} s)", flush=True)
     # example2's program with geometric grids, xedges and the growth terms its own comments hold (markers removed)
-    nsg = load("example2_pbe_2d_fv.f90", patch=GROWTH)
-    np.savez(os.path.join(HERE, "ref_exec_example2_growth.npz"),
-             **run_example2(nsg, 24, 20, (0, 10, 20), dt=2.5e-4, time_end=0.5, grids="geometric", nonuniform=True, n2=18))
+    np.savez(os.path.join(OUT, "ref_exec_example2_growth.npz"),
+             **run_example2(24, 20, (0, 10, 20), dt=2.5e-4, time_end=0.5, grids="geometric", nonuniform=True, n2=18, growth=True))
     print(f"example2 + growth on geometric 24x18 done ({time.time() - t0:.0f} s)", flush=True)
     if quick:
         return
-    ns2 = load("example2_pbe_2d_fv.f90")
-    np.savez(os.path.join(HERE, "ref_exec_example2_40.npz"), **run_example2(ns2, 40, 100, (0, 1, 50, 100)))
+    np.savez(os.path.join(OUT, "ref_exec_example2_40.npz"), **run_example2(40, 100, (0, 1, 50, 100)))
     print(f"example2 at 40x40, 101 outputs done ({time.time() - t0:.0f} s)", flush=True)
-    ns2 = load("example2_pbe_2d_fv.f90")
-    out = run_example2(ns2, 250, 1, (0, 1))
-    np.savez_compressed(os.path.join(HERE, "ref_exec_example2_250_first2.npz"), **out)
+    out = run_example2(250, 1, (0, 1))
+    np.savez_compressed(os.path.join(OUT, "ref_exec_example2_250_first2.npz"), **out)
     print(f"example2 as shipped (250x250), outputs 0 and 1 done ({time.time() - t0:.0f} s)", flush=True)
 
 

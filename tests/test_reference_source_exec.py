@@ -1,7 +1,8 @@
 """The oracle against the reference's OWN SOURCE TEXT, executed mechanically.
 
 tests/golden/ref_exec_*.npz were produced by tests/golden/make_ref_exec_golden.py: tools/f90exec/f90py.py translates
-the procedures of /root/reference/src/*.f90 and of the two example programs statement by statement into Python and runs
+the procedures of /root/reference/src/*.f90 and the two example programs (main programs included; only their formatted
+`output` routine is replaced by a recording hook) statement by statement into Python and runs
 them on IEEE binary64 (no algorithm restated by hand; see the docstrings there for the arithmetic model and its limits --
 it is the source's operation order, not a gfortran binary).  Here:
 
@@ -191,7 +192,7 @@ def test_fixtures_are_reproducible_from_the_reference_tree():
         g, live = gold(name), fn(ns)
         for key, v in live.items():
             assert np.array_equal(np.asarray(v), g[key]), (name, key)
-    g, live = gold("example1"), m.run_example1(ns, npts=3, snaps=(0, 1))
+    g, live = gold("example1"), m.run_example1(npts=3, snaps=(0, 1))
     assert np.array_equal(live["u_0"], g["u_0"]) and np.array_equal(live["u_1"], g["u_1"])
     assert np.array_equal(live["times"], g["times"][:4])
 
@@ -236,7 +237,7 @@ def test_oracle_equals_executed_example1_program_on_small_and_odd_grids(pkg, ref
     import make_ref_exec_golden as m
 
     for nc, k, order in [(2, 3, 3), (3, 2, 2), (4, 3, 1), (5, 1, 3), (7, 3, 3), (17, 2, 3), (33, 3, 2)]:
-        live = m.run_example1(m.load("example1_burgers_1d_fv.f90"), npts=4, snaps=(4,), k=k, order=order, nc=nc)
+        live = m.run_example1(npts=4, snaps=(4,), k=k, order=order, nc=nc)
         grid = pkg.hrweno_grids.grid1().linear(-5.0, 5.0, nc)
         assert np.array_equal(grid.width, live["width"]) and np.array_equal(grid.center, live["center"])
         ode = ref.rktvd(ref.FV(pkg.fv.make_desc(nc, k=k, eps=1e-6, width=[grid.width])), order)
@@ -255,7 +256,6 @@ def test_oracle_equals_executed_example2_program_on_small_rectangular_grids(pkg,
     import make_ref_exec_golden as m
 
     for n1, n2, growth in [(2, 2, False), (3, 5, False), (7, 4, False), (12, 9, False), (5, 3, True), (9, 11, True)]:
-        ns = m.load("example2_pbe_2d_fv.f90", patch=m.GROWTH if growth else None)
-        kw = dict(grids="geometric", nonuniform=True, dt=2.5e-4, time_end=0.5) if growth else {}
-        live = m.run_example2(ns, n1, 2, (0, 2), n2=n2, **kw)
+        kw = dict(grids="geometric", nonuniform=True, dt=2.5e-4, time_end=0.5, growth=True) if growth else {}
+        live = m.run_example2(n1, 2, (0, 2), n2=n2, **kw)
         _example2(pkg, ref.mstvd, live, n1, n2, kw.get("dt", 5e-3), kw.get("time_end", 5.0), growth=growth, mod=ref)

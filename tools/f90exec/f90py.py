@@ -316,6 +316,7 @@ def _reshape(x, shape):
 
 INTRINSICS = {
     "reshape": _reshape,
+    "product": lambda x: (int(np.prod(x.a)) if x.a.dtype.kind in "iu" else float(np.prod(x.a))) if isinstance(x, FArr) else x,
     "sum": _seq_sum,
     "size": _size,
     "lbound": _lbound,
@@ -701,7 +702,9 @@ class Program:
             no, ln = lines[i]
             low = ln.lower()
             m = UNIT_HEAD.match(ln)
-            if re.match(r"^(module|program)\s+\w+$", low) and not low.startswith("module procedure"):
+            if re.match(r"^program\s+\w+$", low):
+                i = self._parse_program(path, lines, i)
+            elif re.match(r"^module\s+\w+$", low) and not low.startswith("module procedure"):
                 stack.append(("container", low.split()[1]))
                 i += 1
             elif re.match(r"^(abstract\s+)?interface\b", low):
@@ -759,6 +762,28 @@ class Program:
             i += 1
         self.types[name] = td
         return i + 1
+
+    def _parse_program(self, path, lines, i):
+        """the main program: translated into `main_<name>()`, whose variables are module-level in the namespace so that
+        the internal procedures after `contains` see them by host association"""
+        name = "main_" + lines[i][1].split()[1].lower()
+        unit = {"name": name, "kind": "program", "args": [], "res": None, "prefix": "", "decls": [], "body": [], "path": path,
+                "proc_dummies": set()}
+        i += 1
+        while True:
+            no, ln = lines[i]
+            low = ln.lower()
+            if low == "contains" or re.match(r"^end\s*program", low) or low == "end":
+                break
+            if low.startswith(("use ", "use,", "implicit ")):
+                pass
+            elif not unit["body"] and DECL.match(ln) and "::" in ln:
+                unit["decls"].append((no, ln))
+            else:
+                unit["body"].append((no, ln))
+            i += 1
+        self.procs[name] = unit
+        return i + (0 if lines[i][1].lower() == "contains" else 1)
 
     def _parse_unit(self, path, lines, i, m):
         name = m.group("name").lower()
@@ -874,6 +899,8 @@ class Program:
         # optional dummies must come last for Python: the reference's procedures already satisfy that or are called by keyword
         emit(0, f"def {unit['name']}({sig}):")
         emit(1, f"# {unit['path']}:{unit['decls'][0][0] if unit['decls'] else unit['body'][0][0]}")
+        if unit["kind"] == "program" and decls:
+            emit(1, "global " + ", ".join(scope.rename(nm) for nm in decls))
         for a in args:
             if a not in decls:
                 continue
@@ -896,7 +923,11 @@ class Program:
                 continue
             if info["base"].startswith(("type", "class")):
                 tm = re.search(r"\(\s*(\w+)\s*\)", info["base"])
-                emit(1, f"{scope.rename(nm)} = new_{tm.group(1).lower()}()")
+                if dims is not None:  # an array of objects
+                    (lo, hi), = self._bounds(dims, scope)
+                    emit(1, f"{scope.rename(nm)} = FArr(np.array([new_{tm.group(1).lower()}() for _ in frange({lo}, {hi})], dtype=object), ({lo},))")
+                else:
+                    emit(1, f"{scope.rename(nm)} = new_{tm.group(1).lower()}()")
             elif dims is not None and not info["pointer"] and not info["allocatable"] and ":" not in [d.strip() for d in split_top(dims)]:
                 bs = ", ".join(f"({lo}, {hi})" for lo, hi in self._bounds(dims, scope))
                 dt = "np.int64" if info["base"].startswith("integer") else "np.float64"
