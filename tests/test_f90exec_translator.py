@@ -239,3 +239,51 @@ def test_fortran_shim_parses_as_far_as_the_translator_can_tell():
         except NotImplementedError as e:
             failed.append((name, str(e)))
     assert [n for n, _ in failed] == ["last_error_string"], failed
+
+
+def test_main_program_with_host_association_and_object_arrays(tmp_path):
+    ns = build(tmp_path, """
+        module m
+           type :: box
+              real(rk) :: w = 1.5_rk
+           contains
+              procedure, pass(self) :: grow => box_grow
+           end type
+        contains
+           subroutine box_grow(self, f)
+              class(box), intent(inout) :: self
+              real(rk), intent(in) :: f
+              self%w = self%w*f
+           end subroutine
+        end module
+        program p
+           use m
+           implicit none
+           integer, parameter :: n(2) = [3, 2], k = 2
+           real(rk) :: u(product(n)), t, dt
+           type(box) :: b(2)
+           integer :: i
+           call b(2)%grow(f=2.0_rk)
+           t = 0.0_rk; dt = 0.25_rk
+           do i = 1, size(u)
+              u(i) = i*b(2)%w
+           end do
+           do i = 0, 3
+              call advance(t, dt)
+              call output(2)
+           end do
+        contains
+           subroutine advance(tt, h)
+              real(rk), intent(inout) :: tt
+              real(rk), intent(in) :: h
+              tt = tt + h*k
+              u = u + n(1)      ! host-associated array, parameter array and named constant
+           end subroutine
+        end program
+    """)
+    seen = []
+    ns["output"] = lambda action: seen.append((ns["t"], ns["u"].a.copy()))
+    ns["main_p"]()
+    assert [s[0] for s in seen] == [0.5, 1.0, 1.5, 2.0]
+    assert np.array_equal(seen[-1][1], np.arange(1, 7) * 3.0 + 12.0)
+    assert ns["b"][1].w == 1.5 and ns["b"][2].w == 3.0

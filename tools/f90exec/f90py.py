@@ -637,6 +637,10 @@ class Scope:
         return comp in self.program.methods
 
 
+def PY_RESERVED_SAFE(name):
+    return name + "_" if name in PY_RESERVED else name
+
+
 PY_RESERVED = {"lambda", "from", "in", "is", "not", "pass", "def", "class", "global", "with", "as", "del", "try"}
 
 DECL = re.compile(r"^(real|integer|logical|character|type|class|procedure)\b", re.I)
@@ -693,6 +697,7 @@ class Program:
     def add_source(self, path, skip=()):
         """parse one source file; procedures named in `skip` (I/O, timers) are not translated"""
         self._skip = {x.lower() for x in skip}
+        self._host = set()
         text = open(path).read()
         lines = logical_lines(text)
         self.sources[path] = lines
@@ -783,13 +788,16 @@ class Program:
                 unit["body"].append((no, ln))
             i += 1
         self.procs[name] = unit
+        # internal procedures after `contains` reach the program's variables by host association
+        self._host = {nm for _, ln in unit["decls"] for nm, _, _, _ in self._decl_entities(ln)}
         return i + (0 if lines[i][1].lower() == "contains" else 1)
 
     def _parse_unit(self, path, lines, i, m):
         name = m.group("name").lower()
         args = [a.strip().lower() for a in (m.group("args") or "").split(",") if a.strip()]
         unit = {"name": name, "kind": m.group("kind").lower(), "args": args, "res": (m.group("res") or name).lower(),
-                "prefix": (m.group("prefix") or "").lower(), "decls": [], "body": [], "path": path, "proc_dummies": set()}
+                "prefix": (m.group("prefix") or "").lower(), "decls": [], "body": [], "path": path, "proc_dummies": set(),
+                "host": set(getattr(self, "_host", ()))}
         i += 1
         depth = 0
         while True:
@@ -901,6 +909,9 @@ class Program:
         emit(1, f"# {unit['path']}:{unit['decls'][0][0] if unit['decls'] else unit['body'][0][0]}")
         if unit["kind"] == "program" and decls:
             emit(1, "global " + ", ".join(scope.rename(nm) for nm in decls))
+        host = sorted(unit.get("host", set()) - set(decls) - set(args) - {unit["name"], res or ""})
+        if host:  # host-associated variables may be defined here: they live at module level of the namespace
+            emit(1, "global " + ", ".join(PY_RESERVED_SAFE(nm) for nm in host))
         for a in args:
             if a not in decls:
                 continue
