@@ -152,6 +152,42 @@ def run_reference(args, rank, world):
     }))
 
 
+PARITY_CELLS = 1 << 20
+
+
+def parity_head(n, world, total_steps, cells=None):
+    """(cells compared, cells the oracle integrates): the first 2^20 cells of rank 0's slab plus the cells whose values can
+    reach them in `total_steps` RK3 steps (k = 3 cells per stage) -- beyond that the cut is invisible"""
+    cells = cells or PARITY_CELLS
+    halo = 9 * total_steps + 32
+    if world == 1 and n <= cells + halo:
+        return n, n  # small run: the whole domain
+    m = min(cells, n - halo)
+    return (m, m + halo) if m > 0 else (0, 0)
+
+
+def parity_check_leg(pkg, u0_head, u_gpu_head, n_global, dt, calls):
+    """the oracle (reference operation order, oracle/hrweno_oracle.c) on the head of the SAME initial data for the SAME
+    steps the timed state went through; checker only, outside every timed region"""
+    ref = graft.load_oracle()
+    ref.set_threads(ref.max_threads())
+    mh, m = len(u0_head), len(u_gpu_head)
+    rx = (XMAX - XMIN) / n_global
+    edges = XMIN + rx * np.arange(mh + 1, dtype=np.float64)  # grids.f90:76-79
+    ode = ref.rktvd(ref.FV(pkg.fv.make_desc(mh, k=3, eps=1e-6, width=[edges[1:] - edges[:-1]])), 3)
+    u, t = u0_head.copy(), 0.0
+    for k in calls:
+        tt = t
+        for _ in range(k - 1):
+            tt = tt + dt
+        t = ode.integrate(u, t, tt, dt)
+    ref.set_threads(1)
+    err = float(np.max(np.abs(u[:m] - u_gpu_head)) / np.max(np.abs(u[:m])))
+    return {"cells": m, "oracle_cells": mh, "steps": int(sum(calls)), "max_normwise": err, "tolerance": 1e-12,
+            "bit_identical": bool(np.array_equal(u[:m], u_gpu_head)), "ok": bool(err <= 1e-12),
+            "what": "state after warm-up + timed steps on rank 0's first cells vs the CPU oracle on the same initial data"}
+
+
 def cpu_baseline_leg(pkg):
     """the oracle on ONE host core (the shipped reference is serial), bounded sample"""
     ref = graft.load_oracle()
@@ -238,6 +274,8 @@ def main():
         ode = pkg.hrweno_tvdode.rktvd(fv, n, 3)
         u_dev = u_host.cuda(non_blocking=False)
         state = {"t": 0.0, "te": 0.0}
+        # initial data of the cells the parity check re-integrates on the oracle (the e2e leg below advances u_host in place)
+        ic_head = u_host.numpy()[:parity_head(n, world, warmup + steps)[1]].copy() if rank == 0 else None
 
         def run_steps(k):
             # k steps in ONE integrate call: tout = t after k-1 steps, the strict is_done test then takes exactly k
@@ -259,6 +297,11 @@ def main():
         barrier()
         ms = e0.elapsed_time(e1)
         launches = ode.launches - launches0
+        # the state that was just timed (rank 0's first cells), for the parity check against the oracle after the run
+        head = None
+        if rank == 0:
+            m, _ = parity_head(n, world, warmup + steps)
+            head = u_dev[:m].cpu().numpy() if m > 0 else None
         # stage-kernel-only time: T(K steps) - T(1 step) removes the pack/unpack copies of the call
         e2, e3 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         e2.record()
@@ -268,7 +311,7 @@ def main():
         ms1 = e2.elapsed_time(e3)
         clocks = sampler.stop()
         ms, ms1 = allmax(ms, ms1)
-        out = {"ms": ms, "ms1": ms1, "launches": int(launches), "clocks": clocks}
+        out = {"ms": ms, "ms1": ms1, "launches": int(launches), "clocks": clocks, "head": head, "ic_head": ic_head, "calls": (warmup, steps)}
         if with_e2e:
             # host (pinned) u through the host-pointer C-ABI call, copies inside the timed region
             u_np = u_host.numpy()
@@ -341,10 +384,17 @@ def main():
             "note": "one hrweno_ode_integrate call with a pinned host u advancing K steps: H2D u (8n B), 3K fused stages, D2H u (8n B)",
         },
     }
+    def parity_of(m):
+        if m["head"] is None:
+            return None
+        return parity_check_leg(pkg, m["ic_head"], m["head"], n_global, dt, m["calls"])
+
+    line["parity_check"] = parity_of(main_m)
     if other_m is not None:
         ko = max(2, min(K, 5))
         v2, sm2, ach2 = derive(other_m, ko)
-        line["other_mode"] = {"mode": other, "value": v2, "steps": ko, "avg_launch_ms": sm2, "roofline_frac": ach2 / peak}
+        line["other_mode"] = {"mode": other, "value": v2, "steps": ko, "avg_launch_ms": sm2, "roofline_frac": ach2 / peak,
+                              "parity_check": parity_of(other_m)}
     if not args.no_cpu_baseline:
         line["cpu_baseline"] = cpu_baseline_leg(pkg)
     emit(line)

@@ -74,6 +74,8 @@ class weno:
         v = np.asarray(v, dtype=np.float64)
         if v.ndim == 1 and v.strides[0] != 8 and v.strides[0] % 8 == 0 and v.strides[0] > 0:
             # a strided section such as v(i::nc1) (example2:107)
+            if v.shape[0] != self.ncells:
+                raise ValueError("size(v) /= ncells")
             inc = v.strides[0] // 8
             vl, vr = np.empty(self.ncells), np.empty(self.ncells)
             base = v.__array_interface__["data"][0]

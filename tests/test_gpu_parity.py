@@ -111,6 +111,9 @@ def test_reconstruct_strided_and_batched(gpu_lib, pkg, ref):
         vl, vr = w2.reconstruct(m[:, i])  # strided view
         rl, rr = ref.reconstruct(np.ascontiguousarray(m[:, i]), 3, 1e-6)
         assert np.array_equal(vl, rl) and np.array_equal(vr, rr)
+    for bad in (m[:-1, 0], m[::2, 0], m[0, :-1]):  # size(v) /= ncells: refused before any pointer reaches the C side
+        with pytest.raises(ValueError):
+            w2.reconstruct(bad)
 
 
 # ---- fluxes (fluxes.f90) -----------------------------------------------------------------------------
