@@ -215,6 +215,9 @@ def main():
     ap.add_argument("--single-mode", action="store_true", help="skip the short measurement of the other arithmetic mode")
     ap.add_argument("--log2-cells", type=int, default=28)
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-extra-configs", action="store_true", help="skip BASELINE.json configs[3] (cfg4) and configs[4] (cfg5)")
+    ap.add_argument("--n2d", type=int, default=16384, help="cfg4 grid edge")
+    ap.add_argument("--rows", type=int, default=65536, help="cfg5 rows")
     args = ap.parse_args()
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
@@ -332,10 +335,150 @@ def main():
         torch.cuda.empty_cache()
         return out
 
+    def steps_to(t, dtx, k):
+        tt = t
+        for _ in range(k - 1):
+            tt = tt + dtx
+        return tt
+
+    def timed_max(fn):
+        """device time of fn() on the launching stream (CUDA events), barrier + synchronize on both sides, max over ranks"""
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        barrier()
+        sampler = ClockSampler(local_rank)
+        sampler.start()
+        e0.record()
+        fn()
+        e1.record()
+        barrier()
+        clocks = sampler.stop()
+        (sec,) = allmax(e0.elapsed_time(e1) * 1e-3)
+        return sec, clocks
+
+    def extra_cfg4(mode_name):
+        """BASELINE.json configs[3]: 2D linear advection (f = v in both directions, Godunov, zero-flux walls) WENO5 + mstvd
+        on an n x n grid, example2's box IC + 1e-3*N(0,1), dt = 0.125 dx, 20 multistep steps timed after the start-up.
+        N GPUs: strong scaling, slabs along x2 with k halo rows per stage over NVLink peer memory."""
+        mode = pkg._abi.MODE_STRICT if mode_name == "strict" else pkg._abi.MODE_FAST
+        n2d = args.n2d
+        off, n2 = pkg.slab.partition(n2d, world, rank)
+        g = pkg.hrweno_grids.grid1().linear(0.0, 10.0, n2d)
+        fv = pkg.fv.FV(pkg.fv.make_desc((n2d, n2), flux_model=1, bc=1, width=[g.width, g.width[off:off + n2]], mode=mode, rank=rank,
+                                        nranks=world, global_n=n2d, global_offset=off))
+        pkg.slab.connect(fv, rank, world, gather)
+        ode = pkg.hrweno_tvdode.mstvd(fv, n2d * n2)
+        c1, c2 = g.center, g.center[off:off + n2]
+        u = ((c2 >= 1.0) & (c2 <= 3.0))[:, None] & ((c1 >= 1.0) & (c1 <= 3.0))[None, :]
+        u = u.astype(np.float64)
+        u += 1e-3 * np.random.default_rng(12345 + rank).standard_normal((n2, n2d))
+        # corner block the oracle re-integrates (rank 0): 256^2 compared, + the cells that can reach them (3 per stage)
+        kw, ksteps = 6, 20
+        nstages = 12 + (kw - 4) + ksteps
+        mc, mh = 256, 256 + 3 * nstages + 16
+        chk = rank == 0 and min(n2d, n2) > mh
+        ic_blk = u[:mh, :mh].copy() if chk else None
+        ud = torch.from_numpy(u.reshape(-1)).cuda()
+        del u
+        dt2 = 0.125 * 10.0 / n2d
+        t = ode.integrate_dev(ud.data_ptr(), 0.0, steps_to(0.0, dt2, kw), dt2, 1, stream)  # start-up (4 RK3) + 2 multistep steps
+        l0 = ode.launches
+        sec, clocks = timed_max(lambda: ode.integrate_dev(ud.data_ptr(), t, steps_to(t, dt2, ksteps), dt2, 1, stream))
+        launches = ode.launches - l0
+        res = None
+        if rank == 0:
+            cells = n2d * n2d
+            gbs = cells * 40.0 * ksteps / sec / 1e9 / world
+            res = {"workload": f"cfg4: 2D linear advection WENO5+mstvd {n2d}x{n2d}, f=v, Godunov, zero-flux walls, box IC + 1e-3*N(0,1), dt=0.125dx; "
+                               f"{ksteps} multistep steps after the 4-step RK3 start-up" + (f"; strong scaling, x2 slabs on {world} GPUs" if world > 1 else ""),
+                   "mode": mode_name, "value": cells * ksteps / sec, "unit": "cell-steps/s", "ms_per_step": 1e3 * sec / ksteps, "gpu_launches": int(launches),
+                   "scaling": "strong", "clocks": clocks,
+                   "roofline": {"bound": "hbm", "achieved": gbs, "peak": peaks()[0], "unit": "GB/s", "frac": gbs / peaks()[0], "traffic": None,
+                                "kernel": "fv2d_stage_kernel<K=3, C_MS> (one launch per multistep step)", "per_gpu": True,
+                                "algorithmic_bytes_per_launch": cells * 40.0 / world, "avg_launch_ms": 1e3 * sec / ksteps}}
+            if chk:
+                ref = graft.load_oracle()
+                ref.set_threads(ref.max_threads())
+                rode = ref.mstvd(ref.FV(pkg.fv.make_desc((mh, mh), flux_model=1, bc=1, width=[g.width[:mh], g.width[:mh]])))
+                ur, tr = ic_blk.reshape(-1).copy(), 0.0
+                tr = rode.integrate(ur, tr, steps_to(0.0, dt2, kw), dt2)
+                tr = rode.integrate(ur, tr, steps_to(tr, dt2, ksteps), dt2)
+                ref.set_threads(1)
+                got = ud[: mc * n2d].cpu().numpy().reshape(mc, n2d)[:, :mc]
+                want = ur.reshape(mh, mh)[:mc, :mc]
+                err = float(np.max(np.abs(got - want)) / np.max(np.abs(want)))
+                res["parity_check"] = {"cells": mc * mc, "oracle_cells": mh * mh, "steps": kw + ksteps, "max_normwise": err, "tolerance": 1e-12,
+                                       "bit_identical": bool(np.array_equal(got, want)), "ok": bool(err <= 1e-12),
+                                       "what": "corner block of the timed state vs the CPU oracle on the same initial data"}
+        del ode, fv, ud
+        torch.cuda.empty_cache()
+        return res
+
+    def extra_cfg5(mode_name):
+        """BASELINE.json configs[4]: 65536 independent rows x 4096 cells, Burgers + Godunov, k in {1,2,3} x rktvd order in
+        {1,2,3}, 10 steps each; rows split over the GPUs, no halos."""
+        mode = pkg._abi.MODE_STRICT if mode_name == "strict" else pkg._abi.MODE_FAST
+        rows_g, nc = args.rows, 4096
+        roff, rows = pkg.slab.partition(rows_g, world, rank)
+        g = pkg.hrweno_grids.grid1().linear(-5.0, 5.0, nc)
+        rng = np.random.default_rng(2024)
+        va, vb = rng.uniform(0.5, 1.5, rows_g), rng.uniform(-1.0, 0.0, rows_g)
+        xa, xb = rng.uniform(-4.5, -3.0, rows_g), rng.uniform(1.0, 3.0, rows_g)
+        sl = slice(roff, roff + rows)
+        x = g.center[None, :]
+        u0 = np.clip(va[sl, None] + ((vb - va) / (xb - xa))[sl, None] * (x - xa[sl, None]), np.minimum(va, vb)[sl, None], np.maximum(va, vb)[sl, None])
+        ud0 = torch.from_numpy(u0.reshape(-1)).cuda()
+        dt5 = 0.1 * 10.0 / nc
+        bytes_step = {1: 16.0, 2: 40.0, 3: 64.0}
+        kw, ksteps, prow = 3, 10, 8
+        sweep, worst, launches = {}, 0.0, 0
+        for k in (1, 2, 3):
+            for order in (1, 2, 3):
+                fv = pkg.fv.FV(pkg.fv.make_desc(nc, k=k, rows=rows, width=[g.width], mode=mode))
+                ode = pkg.hrweno_tvdode.rktvd(fv, rows * nc, order)
+                ud = ud0.clone()
+                t = ode.integrate_dev(ud.data_ptr(), 0.0, steps_to(0.0, dt5, kw), dt5, 1, stream)
+                l0 = ode.launches
+                sec, clocks = timed_max(lambda: ode.integrate_dev(ud.data_ptr(), t, steps_to(t, dt5, ksteps), dt5, 1, stream))
+                launches += ode.launches - l0
+                if rank == 0:
+                    cells = rows_g * nc
+                    gbs = cells * bytes_step[order] * ksteps / sec / 1e9 / world
+                    ent = {"value": cells * order * ksteps / sec, "ms_per_step": 1e3 * sec / ksteps, "roofline_frac": gbs / peaks()[0], "achieved_gbs_per_gpu": gbs,
+                           "sm_mhz": clocks["sm_mhz"], "reasons": clocks["reasons"]}
+                    # the first rows against the oracle (rows are independent)
+                    ref = graft.load_oracle()
+                    rode = ref.rktvd(ref.FV(pkg.fv.make_desc(nc, k=k, rows=prow, width=[g.width])), order)
+                    ur = u0[:prow].reshape(-1).copy()
+                    tr = rode.integrate(ur, 0.0, steps_to(0.0, dt5, kw), dt5)
+                    tr = rode.integrate(ur, tr, steps_to(tr, dt5, ksteps), dt5)
+                    got = ud[: prow * nc].cpu().numpy()
+                    ent["parity_normwise"] = float(np.max(np.abs(got - ur)) / np.max(np.abs(ur)))
+                    worst = max(worst, ent["parity_normwise"])
+                    sweep[f"k{k}_rktvd{order}"] = ent
+                del ode, fv, ud
+        del ud0
+        torch.cuda.empty_cache()
+        if rank != 0:
+            return None
+        head = sweep["k3_rktvd3"]
+        return {"workload": f"cfg5: {rows_g} independent rows x {nc} cells, Burgers+Godunov, per-row ramp IC (rng 2024), dt=0.1dx, {ksteps} steps per (k, order); "
+                            "rows split over the GPUs, no halos; each integrate_dev call includes the dense<->padded copies of the caller's array",
+                "mode": mode_name, "unit": "cell-updates/s (cell-stages)", "value": head["value"], "value_is": "k=3, rktvd order 3", "scaling": "strong",
+                "gpu_launches": int(launches),
+                "roofline": {"bound": "hbm", "achieved": head["achieved_gbs_per_gpu"], "peak": peaks()[0], "unit": "GB/s", "frac": head["roofline_frac"],
+                             "traffic": None, "kernel": "fv1d_stage_kernel<K=3> on 4096-cell rows (half-size tiles)", "per_gpu": True,
+                             "algorithmic_bytes": "16 / 40 / 64 B per cell-step for rktvd 1 / 2 / 3"},
+                "sweep": sweep,
+                "parity_check": {"rows": prow, "steps": kw + ksteps, "max_normwise": worst, "tolerance": 1e-12, "ok": bool(worst <= 1e-12),
+                                 "what": "first rows of every (k, order) run vs the CPU oracle"}}
+
     K = args.steps
     main_m = measure(args.mode, K, args.warmup, True)
     other = "strict" if args.mode == "fast" else "fast"
     other_m = measure(other, max(2, min(K, 5)), 3, False) if not args.single_mode else None
+    extra = None
+    if not args.no_extra_configs:
+        extra = {"cfg4": extra_cfg4(args.mode), "cfg5": extra_cfg5(args.mode)}
 
     if rank != 0:
         if world > 1:
@@ -395,6 +538,8 @@ def main():
         v2, sm2, ach2 = derive(other_m, ko)
         line["other_mode"] = {"mode": other, "value": v2, "steps": ko, "avg_launch_ms": sm2, "roofline_frac": ach2 / peak,
                               "parity_check": parity_of(other_m)}
+    if extra is not None:
+        line["configs"] = extra
     if not args.no_cpu_baseline:
         line["cpu_baseline"] = cpu_baseline_leg(pkg)
     emit(line)

@@ -55,6 +55,7 @@ class FvDesc(C.Structure):
 FLUX_FN = C.CFUNCTYPE(C.c_double, C.c_void_p, C.c_double, c_double_p, C.c_int, C.c_double)
 RHS_FN = C.CFUNCTYPE(None, C.c_void_p, C.c_double, C.c_int64, C.c_void_p, C.c_void_p, C.c_void_p)
 RHS_HOST_FN = C.CFUNCTYPE(None, C.c_void_p, C.c_double, C.c_int64, c_double_p, c_double_p)
+TIME_FN = C.CFUNCTYPE(C.c_double, C.c_void_p, C.c_double)
 
 # name -> (restype, argtypes); this table is also what the symbol-export test walks
 PROTOTYPES = {
@@ -96,6 +97,7 @@ PROTOTYPES = {
     "hrweno_fv_set_alpha": (C.c_int, [C.c_void_p, C.c_double]),
     "hrweno_fv_set_xedges": (C.c_int, [C.c_void_p, C.c_int, C.c_void_p]),
     "hrweno_fv_set_flux_coef": (C.c_int, [C.c_void_p, C.c_int, C.c_void_p, C.c_void_p]),
+    "hrweno_fv_set_flux_time_fn": (C.c_int, [C.c_void_p, TIME_FN, C.c_void_p]),
     "hrweno_fv_export_halo": (C.c_int, [C.c_void_p, C.c_void_p]),
     "hrweno_fv_import_halo": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p]),
     "hrweno_fv_halo_status": (C.c_int, [C.c_void_p]),
@@ -114,11 +116,28 @@ PROTOTYPES = {
         C.c_int,
         [C.c_void_p, C.c_void_p, C.POINTER(C.c_double), C.c_double, C.c_double, C.c_int, C.c_void_p],
     ),
+    "hrweno_ode_attach": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p]),
+    "hrweno_ode_integrate_attached": (C.c_int, [C.c_void_p, C.POINTER(C.c_double), C.c_double, C.c_double, C.c_int, C.c_void_p]),
+    "hrweno_ode_fetch": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p]),
     "hrweno_ode_fevals": (C.c_int64, [C.c_void_p]),
     "hrweno_ode_istate": (C.c_int, [C.c_void_p]),
     "hrweno_ode_order": (C.c_int, [C.c_void_p]),
     "hrweno_ode_neq": (C.c_int64, [C.c_void_p]),
     "hrweno_ode_launches": (C.c_int64, [C.c_void_p]),
+    "hrweno_mgpu_create": (C.c_int, [C.POINTER(C.c_void_p), C.POINTER(FvDesc), C.c_int, C.POINTER(C.c_int)]),
+    "hrweno_mgpu_destroy": (None, [C.c_void_p]),
+    "hrweno_mgpu_ngpus": (C.c_int, [C.c_void_p]),
+    "hrweno_mgpu_slab": (C.c_int, [C.c_void_p, C.c_int, C.POINTER(C.c_int), C.POINTER(C.c_int64), C.POINTER(C.c_int64)]),
+    "hrweno_mgpu_rktvd": (C.c_int, [C.c_void_p, C.c_int]),
+    "hrweno_mgpu_mstvd": (C.c_int, [C.c_void_p]),
+    "hrweno_mgpu_integrate": (C.c_int, [C.c_void_p, C.c_void_p, C.POINTER(C.c_double), C.c_double, C.c_double, C.c_int]),
+    "hrweno_mgpu_upload": (C.c_int, [C.c_void_p, C.c_void_p]),
+    "hrweno_mgpu_integrate_resident": (C.c_int, [C.c_void_p, C.POINTER(C.c_double), C.c_double, C.c_double, C.c_int]),
+    "hrweno_mgpu_download": (C.c_int, [C.c_void_p, C.c_void_p]),
+    "hrweno_mgpu_max_wavespeed": (C.c_int, [C.c_void_p, C.POINTER(C.c_double), C.c_int]),
+    "hrweno_mgpu_set_alpha": (C.c_int, [C.c_void_p, C.c_double]),
+    "hrweno_mgpu_fevals": (C.c_int64, [C.c_void_p]),
+    "hrweno_mgpu_launches": (C.c_int64, [C.c_void_p]),
     "hrweno_host_alloc": (C.c_int, [C.POINTER(C.c_void_p), C.c_int64]),
     "hrweno_host_free": (None, [C.c_void_p]),
 }

@@ -11,6 +11,7 @@ namespace hrw {
 static thread_local std::string g_last_error;
 
 void set_error(const std::string &msg) { g_last_error = msg; }
+const char *last_error_cstr() { return g_last_error.c_str(); }
 
 int fail(int status, const std::string &msg) {
    g_last_error = msg;
@@ -27,6 +28,8 @@ int ode_create(Ode **out, bool is_ms, Fv *fv, hrweno_rhs_fn fu, void *ctx, int64
 int ode_create_host(Ode **out, bool is_ms, hrweno_rhs_host_fn fu, void *ctx, int64_t neq, int order);
 int ode_integrate_dev(Ode *o, double *u_dev, double *t, double tout, double dt, int itask, cudaStream_t st);
 int ode_integrate_host(Ode *o, double *u, double *t, double tout, double dt, int itask);
+int ode_attach(Ode *o, const double *u_dev, cudaStream_t st);
+int ode_fetch(Ode *o, double *u_dev, cudaStream_t st);
 
 // closed-set numerical flux per face (fluxes.f90:43,67-74)
 __global__ void flux_faces_kernel(FluxCfg c, int64_t n, const double *__restrict__ vm, const double *__restrict__ vp,
@@ -45,7 +48,7 @@ static int ensure_buf(Weno *w, size_t doubles) {
    return HRWENO_OK;
 }
 
-static int fv_rhs_any(Fv *fv, const double *v_dev, double *vdot_dev, cudaStream_t st) {
+static int fv_rhs_any(Fv *fv, double t, const double *v_dev, double *vdot_dev, cudaStream_t st) {
    if (!fv->d_scratch_in) HRW_TRY(fv->alloc_state(&fv->d_scratch_in));
    HRW_TRY(fv_pack(fv, v_dev, fv->cell0(fv->d_scratch_in), st));
    HRW_TRY(fv_exchange(fv, fv->cell0(fv->d_scratch_in), st));
@@ -54,6 +57,7 @@ static int fv_rhs_any(Fv *fv, const double *v_dev, double *vdot_dev, cudaStream_
    a.out = vdot_dev;
    a.ld_out = fv->n0;
    a.out_dense = 1;
+   a.t = t;
    return fv_stage_halo(fv, C_RHS, a, false, st);
 }
 
@@ -185,15 +189,13 @@ void hrweno_fv_destroy(hrweno_fv *fv) { delete reinterpret_cast<Fv *>(fv); }
 int64_t hrweno_fv_neq(const hrweno_fv *fv) { return fv ? reinterpret_cast<const Fv *>(fv)->neq : 0; }
 
 int hrweno_fv_rhs_dev(hrweno_fv *h, double t, const double *v_dev, double *vdot_dev, void *stream) {
-   (void)t; // the closed-set flux models do not depend on x or t (example1:120, example2:140,153)
-   Fv *fv = reinterpret_cast<Fv *>(h);
+   Fv *fv = reinterpret_cast<Fv *>(h); // t reaches the flux only through hrweno_fv_set_flux_time_fn (fluxes.f90:12-18)
    if (!fv || !v_dev || !vdot_dev) return fail(HRWENO_EINVAL, "null argument");
    std::lock_guard<std::mutex> lock(fv->mtx);
-   return fv_rhs_any(fv, v_dev, vdot_dev, (cudaStream_t)stream);
+   return fv_rhs_any(fv, t, v_dev, vdot_dev, (cudaStream_t)stream);
 }
 
 int hrweno_fv_rhs(hrweno_fv *h, double t, const double *v, double *vdot) {
-   (void)t;
    Fv *fv = reinterpret_cast<Fv *>(h);
    if (!fv || !v || !vdot) return fail(HRWENO_EINVAL, "null argument");
    std::lock_guard<std::mutex> lock(fv->mtx);
@@ -201,7 +203,7 @@ int hrweno_fv_rhs(hrweno_fv *h, double t, const double *v, double *vdot) {
    if (!fv->d_scratch_out) HRW_CUDA(cudaMalloc(&fv->d_scratch_out, 2 * bytes));
    double *din = fv->d_scratch_out, *dout = din + fv->neq;
    HRW_CUDA(cudaMemcpyAsync(din, v, bytes, cudaMemcpyHostToDevice, fv->stream));
-   HRW_TRY(fv_rhs_any(fv, din, dout, fv->stream));
+   HRW_TRY(fv_rhs_any(fv, t, din, dout, fv->stream));
    HRW_CUDA(cudaMemcpyAsync(vdot, dout, bytes, cudaMemcpyDeviceToHost, fv->stream));
    HRW_CUDA(cudaStreamSynchronize(fv->stream));
    return fv_halo_status(fv);
@@ -231,6 +233,11 @@ int hrweno_fv_set_xedges(hrweno_fv *h, int axis, const double *xedges) {
 int hrweno_fv_set_flux_coef(hrweno_fv *h, int axis, const double *face_coef, const double *cross_coef) {
    if (!h) return fail(HRWENO_EINVAL, "null fv handle");
    return fv_set_flux_coef(reinterpret_cast<Fv *>(h), axis, face_coef, cross_coef);
+}
+
+int hrweno_fv_set_flux_time_fn(hrweno_fv *h, hrweno_time_fn g, void *ctx) {
+   if (!h) return fail(HRWENO_EINVAL, "null fv handle");
+   return fv_set_flux_time_fn(reinterpret_cast<Fv *>(h), g, ctx);
 }
 
 int hrweno_fv_export_halo(hrweno_fv *h, void *handle_out) {
@@ -274,6 +281,15 @@ int hrweno_ode_integrate(hrweno_ode *ode, double *u, double *t, double tout, dou
 }
 int hrweno_ode_integrate_dev(hrweno_ode *ode, double *u_dev, double *t, double tout, double dt, int itask, void *stream) {
    return ode_integrate_dev(reinterpret_cast<Ode *>(ode), u_dev, t, tout, dt, itask, (cudaStream_t)stream);
+}
+int hrweno_ode_attach(hrweno_ode *ode, const double *u_dev, void *stream) {
+   return ode_attach(reinterpret_cast<Ode *>(ode), u_dev, (cudaStream_t)stream);
+}
+int hrweno_ode_integrate_attached(hrweno_ode *ode, double *t, double tout, double dt, int itask, void *stream) {
+   return ode_integrate_dev(reinterpret_cast<Ode *>(ode), nullptr, t, tout, dt, itask, (cudaStream_t)stream);
+}
+int hrweno_ode_fetch(hrweno_ode *ode, double *u_dev, void *stream) {
+   return ode_fetch(reinterpret_cast<Ode *>(ode), u_dev, (cudaStream_t)stream);
 }
 int64_t hrweno_ode_fevals(const hrweno_ode *ode) { return ode ? reinterpret_cast<const Ode *>(ode)->fevals : 0; }
 int hrweno_ode_istate(const hrweno_ode *ode) { return ode ? reinterpret_cast<const Ode *>(ode)->istate : -1; }

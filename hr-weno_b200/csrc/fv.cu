@@ -296,6 +296,14 @@ int fv_set_flux_coef(Fv *fv, int axis, const double *face, const double *cross) 
    return HRWENO_OK;
 }
 
+int fv_set_flux_time_fn(Fv *fv, hrweno_time_fn g, void *ctx) {
+   std::lock_guard<std::mutex> lock(fv->mtx);
+   if (g) HRW_TRY(fv_enable_general(fv, "hrweno_fv_set_flux_time_fn"));
+   fv->tfn = g;
+   fv->tfn_ctx = ctx;
+   return HRWENO_OK;
+}
+
 // ------------------------------------------------------------------------------------------------
 // dense <-> padded copies.  pack also writes the ghost cells of physical boundaries.
 // ------------------------------------------------------------------------------------------------

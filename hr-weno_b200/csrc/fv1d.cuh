@@ -153,9 +153,33 @@ __device__ __forceinline__ double face_flux_k(const FluxCfg &c, double vm, doubl
 template <int R>
 struct Prefetched {
    double av[R], bv[R];
-   uint32_t idx4[R / 4 > 0 ? R / 4 : 1];
+   uint32_t idx4[(R + 3) / 4];
    double wd[R];
 };
+
+// the R one-byte width indices of a run starting at p (global or shared), packed four per word.  Runs of a multiple of
+// four cells start on a 4-B boundary; other (even) run lengths start on a 2-B boundary and are assembled from the aligned
+// words around them (the index arrays are padded, fv.cu).
+template <int R>
+__device__ __forceinline__ void load_widx(const unsigned char *p, uint32_t *out) {
+   constexpr int NW = (R + 3) / 4;
+   if constexpr (R % 4 == 0) {
+#pragma unroll
+      for (int q = 0; q < NW; ++q) out[q] = reinterpret_cast<const uint32_t *>(p)[q];
+   } else {
+      static_assert(R % 2 == 0, "runs have an even number of cells");
+      constexpr int NL = (R + 2 + 3) / 4;
+      const uintptr_t a = reinterpret_cast<uintptr_t>(p);
+      const uint32_t *q = reinterpret_cast<const uint32_t *>(a & ~(uintptr_t)3);
+      const uint32_t sh = ((uint32_t)a & 3u) * 8u;
+      uint32_t wd[NL + 1];
+#pragma unroll
+      for (int i = 0; i < NL; ++i) wd[i] = q[i];
+      wd[NL] = 0u;
+#pragma unroll
+      for (int i = 0; i < NW; ++i) out[i] = __funnelshift_r(wd[i], wd[i + 1 < NL ? i + 1 : NL], sh);
+   }
+}
 
 template <int K, int COMBINE, class M, int FK, int WK, int R, bool EDGE>
 __device__ __forceinline__ void fv1d_finish(const Fv1dGeom &g, const StageArgs &s, const double2 *s_wtab, int64_t row, int i0,
@@ -182,7 +206,7 @@ __device__ __forceinline__ void fv1d_finish(const Fv1dGeom &g, const StageArgs &
    // pointwise operands and widths {w, refined reciprocal of w}
    double av[R], bv[R], wd[R], wr[R];
    constexpr bool NEED_A = COMBINE == C_RK2_FINAL || COMBINE == C_RK3_S2 || COMBINE == C_RK3_S3 || COMBINE == C_MS;
-   uint32_t idx4[R / 4 > 0 ? R / 4 : 1];
+   uint32_t idx4[(R + 3) / 4];
    if constexpr (!EDGE) {
 #pragma unroll
       for (int j = 0; j < R; ++j) {
@@ -191,7 +215,7 @@ __device__ __forceinline__ void fv1d_finish(const Fv1dGeom &g, const StageArgs &
          wd[j] = pf.wd[j];
       }
 #pragma unroll
-      for (int j = 0; j < (R / 4 > 0 ? R / 4 : 1); ++j) idx4[j] = pf.idx4[j];
+      for (int j = 0; j < (R + 3) / 4; ++j) idx4[j] = pf.idx4[j];
    } else {
       if constexpr (NEED_A) {
          const double *ap = s.a + row * g.ld + i0;
@@ -204,23 +228,18 @@ __device__ __forceinline__ void fv1d_finish(const Fv1dGeom &g, const StageArgs &
          }
       }
       if constexpr (WK == WK_DICT) {
-#pragma unroll
-         for (int j = 0; j < R; j += 4) idx4[j / 4] = __ldg(reinterpret_cast<const uint32_t *>(g.widx + i0 + j));
+         load_widx<R>(g.widx + i0, idx4);
       } else {
 #pragma unroll
          for (int j = 0; j < R; ++j) wd[j] = __ldg(g.width + i0 + j);
       }
    }
    if constexpr (WK == WK_DICT) {
-      static_assert(R % 4 == 0, "dictionary indices are fetched four at a time");
 #pragma unroll
-      for (int j = 0; j < R; j += 4) {
-#pragma unroll
-         for (int q = 0; q < 4; ++q) {
-            const double2 e = s_wtab[(idx4[j / 4] >> (8 * q)) & 0xffu];
-            wd[j + q] = e.x;
-            wr[j + q] = e.y;
-         }
+      for (int j = 0; j < R; ++j) {
+         const double2 e = s_wtab[(idx4[j / 4] >> (8 * (j % 4))) & 0xffu];
+         wd[j] = e.x;
+         wr[j] = e.y;
       }
    } else {
 #pragma unroll
@@ -338,7 +357,7 @@ __global__ void __launch_bounds__(NT, HRW_MINB) fv1d_stage_kernel(const Fv1dGeom
    // from shared memory instead of waiting for global loads (the same for operand a measured slower: HRW_STAGE_A)
    constexpr bool STAGE_A = NEED_A && HRW_STAGE_A;
    constexpr bool STAGE_W = WK == WK_DICT && HRW_STAGE_W;
-   constexpr int WROW = ((TILE + 15) / 16) * 16 + 16; // staged index bytes per tile: from the 16-B boundary at or below its first cell
+   constexpr int WROW = ((TILE + 15) / 16) * 16 + 16 + (R % 4 ? 16 : 0); // staged index bytes per tile: from the 16-B boundary at or below its first cell
    __shared__ __align__(128) double s_v[2][SM_N];
    __shared__ __align__(128) double s_a[STAGE_A ? 2 : 1][STAGE_A ? TILE : 2];
    __shared__ __align__(16) unsigned char s_wi[STAGE_W ? 2 : 1][STAGE_W ? WROW : 16];
@@ -452,7 +471,7 @@ __global__ void __launch_bounds__(NT, HRW_MINB) fv1d_stage_kernel(const Fv1dGeom
       // interior threads: start the global loads of the operands that are not staged with the tile now
       Prefetched<R> pf;
 #pragma unroll
-      for (int q = 0; q < (R / 4 > 0 ? R / 4 : 1); ++q) pf.idx4[q] = 0u;
+      for (int q = 0; q < (R + 3) / 4; ++q) pf.idx4[q] = 0u;
       if constexpr (STAGE_A) {
 #pragma unroll
          for (int j = 0; j < R; ++j) pf.av[j] = 0.0;
@@ -476,10 +495,7 @@ __global__ void __launch_bounds__(NT, HRW_MINB) fv1d_stage_kernel(const Fv1dGeom
                pf.bv[j + 1] = t.y;
             }
          }
-         if constexpr (WK == WK_DICT && !STAGE_W) {
-#pragma unroll
-            for (int j = 0; j < R; j += 4) pf.idx4[j / 4] = __ldg(reinterpret_cast<const uint32_t *>(g.widx + i0 + j));
-         }
+         if constexpr (WK == WK_DICT && !STAGE_W) load_widx<R>(g.widx + i0, pf.idx4);
          if constexpr (WK != WK_DICT) {
 #pragma unroll
             for (int j = 0; j < R; j += 2) {
@@ -504,8 +520,7 @@ __global__ void __launch_bounds__(NT, HRW_MINB) fv1d_stage_kernel(const Fv1dGeom
          }
          if constexpr (STAGE_W) {
             const int woff = (ptc * TILE) & 15;
-#pragma unroll
-            for (int j = 0; j < R; j += 4) pf.idx4[j / 4] = *reinterpret_cast<const uint32_t *>(&s_wi[buf][woff + (slot - 1) * R + j]);
+            load_widx<R>(&s_wi[buf][woff + (slot - 1) * R], pf.idx4);
          }
       }
 
@@ -554,7 +569,7 @@ __global__ void __launch_bounds__(NT, HRW_MINB) fv1d_stage_kernel(const Fv1dGeom
          for (int j = 0; j < WN; ++j) asm volatile("" : "+d"(w[j]));
          if constexpr (STAGE_W) {
 #pragma unroll
-            for (int q = 0; q < (R / 4 > 0 ? R / 4 : 1); ++q) asm volatile("" : "+r"(pf.idx4[q]));
+            for (int q = 0; q < (R + 3) / 4; ++q) asm volatile("" : "+r"(pf.idx4[q]));
          }
          if constexpr (STAGE_A) {
 #pragma unroll

@@ -11,7 +11,7 @@
 #define HRW_NT1_STRICT 256
 #endif
 #ifndef HRW_R1_FAST
-#define HRW_R1_FAST 8
+#define HRW_R1_FAST 10 // 80-B thread stride: the 16-B window loads of a quarter warp hit eight distinct bank groups (runs of 8: four-way conflicts)
 #endif
 #ifndef HRW_NT1_FAST
 #define HRW_NT1_FAST 128

@@ -15,6 +15,7 @@
 //            stage combination, coalesced stores along x1.
 #include "fv2d.cuh"
 #include "fv1d.cuh" // TMA bulk copy + mbarrier helpers
+#include "tmap.hpp"
 
 namespace hrw {
 
@@ -49,8 +50,28 @@ struct Tile2d {
    static constexpr int OFF_VRE = OFF_VRX + TY * XP;
    static constexpr int OFF_VLE = OFF_VRE + (RY + 1) * TX;
    static constexpr int TOTAL = OFF_VLE + (UPW ? 0 : (RY + 1) * TX);
-   static constexpr size_t BYTES = (size_t)TOTAL * sizeof(double);
+   // per-tile copies of the widths and their reciprocals along x1 (TX) and x2 (TY)
+   static constexpr int OFF_W1 = TOTAL, OFF_RW1 = OFF_W1 + TX, OFF_W2 = OFF_RW1 + TX, OFF_RW2 = OFF_W2 + TY;
+   // pointwise operands of the tile (a, b), fetched by TMA at the top of the tile iteration: 128-B aligned boxes of TX x TY
+   static constexpr int OFF_OPS = ((OFF_RW2 + TY + 15) / 16) * 16;
+   static constexpr int OP_DOUBLES = TX * TY;
+   static constexpr size_t bytes(int nstaged) { return (size_t)(OFF_OPS + nstaged * OP_DOUBLES) * sizeof(double); }
 };
+
+// pointwise operands the combination reads (a; b for the multistep stage) and how many of them are staged in shared memory
+// by TMA: all of them for the upwind variant; the two-sided variant has room for one next to its vl/vr arrays if two
+// CTAs are to share an SM.
+__host__ __device__ constexpr int fv2d_nops(int combine) {
+   return combine == C_MS ? 2 : ((combine == C_RK2_FINAL || combine == C_RK3_S2 || combine == C_RK3_S3) ? 1 : 0);
+}
+__host__ __device__ constexpr int fv2d_nstaged(int combine, int upw) { return upw ? fv2d_nops(combine) : (fv2d_nops(combine) > 0 ? 1 : 0); }
+
+// 2D tensor-map TMA load (SASS: UTMALDG) of one box whose first element is (c0, c1), completing on an mbarrier
+__device__ __forceinline__ void tma_tensor_2d_g2s(uint32_t dst_smem, const CUtensorMap *tm, int c0, int c1, uint32_t bar) {
+   asm volatile("cp.async.bulk.tensor.2d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3}], [%4];" ::"r"(dst_smem),
+                "l"(tm), "r"(c0), "r"(c1), "r"(bar)
+                : "memory");
+}
 
 // UPW = 1: linear flux f = a*v with a >= 0 in both directions and the Godunov rule.  Then vm <= vp implies
 // a*vm <= a*vp (rounding is monotone), so godunov (fluxes.f90:70-74) returns f(vm) = a*vr(i) in every case and
@@ -68,10 +89,12 @@ __device__ __forceinline__ double face2d(const FluxCfg &c, double vm, double vp)
 // phase B for one thread = (column lx, run of R rows).  INTERIOR: the tile touches no domain edge and is complete.
 template <int K, int COMBINE, class M, int UPW, int TX, int TY, bool INTERIOR>
 __device__ __forceinline__ void fv2d_phase_b(const Fv2dGeom &g, const StageArgs &s, const double *s_v, const double *s_vlx,
-                                             const double *s_vrx, const double *vmY /* vr below face j, j = 0..R */,
+                                             const double *s_vrx, const double *s_wd /* staged widths */, const double *s_ops,
+                                             const double *vmY /* vr below face j, j = 0..R */,
                                              const double *vpY /* vl above face j */, int64_t x0, int64_t y0, int lx, int ly0) {
    using T = Tile2d<TX, TY, UPW>;
    constexpr int R = T::R, H = T::H;
+   constexpr int NSTG = fv2d_nstaged(COMBINE, UPW);
    const int64_t gx = x0 + lx, gy0 = y0 + ly0;
    if constexpr (!INTERIOR) {
       if (gx >= g.n0 || gy0 >= g.n1) return;
@@ -89,9 +112,11 @@ __device__ __forceinline__ void fv2d_phase_b(const Fv2dGeom &g, const StageArgs 
             if (gy0 + j == g.n1) F2[j] = copy ? F2[j - 1] : 0.0;
       }
    }
-   const double w1 = __ldg(g.w1 + gx), rw1 = __ldg(g.rw1 + gx);
+   // widths of the tile's columns and rows come from the per-tile copies in shared memory
+   const double w1 = s_wd[lx], rw1 = s_wd[TX + lx];
    // pointwise operands first: out may alias a (and out2 alias b) element for element in the multistep stage, so
-   // loads issued after the first store could not be hoisted by the compiler and would serialise on DRAM latency
+   // loads issued after the first store could not be hoisted by the compiler and would serialise on DRAM latency.
+   // Staged operands were fetched by TMA at the top of the tile iteration (s_ops: a, then b, TX x TY boxes).
    constexpr bool NEED_A = COMBINE == C_RK2_FINAL || COMBINE == C_RK3_S2 || COMBINE == C_RK3_S3 || COMBINE == C_MS;
    double av[R], bv[R], w2v[R], rw2v[R];
 #pragma unroll
@@ -101,10 +126,10 @@ __device__ __forceinline__ void fv2d_phase_b(const Fv2dGeom &g, const StageArgs 
       const int64_t off = gy * g.pitch + gx;
       av[j] = 0.0;
       bv[j] = 0.0;
-      if constexpr (NEED_A) av[j] = in ? s.a[off] : 0.0;
-      if constexpr (COMBINE == C_MS) bv[j] = in ? s.b[off] : 0.0;
-      w2v[j] = __ldg(g.w2 + (in ? gy : gy0));
-      rw2v[j] = __ldg(g.rw2 + (in ? gy : gy0));
+      if constexpr (NEED_A) av[j] = NSTG >= 1 ? s_ops[(ly0 + j) * TX + lx] : (in ? s.a[off] : 0.0);
+      if constexpr (COMBINE == C_MS) bv[j] = NSTG >= 2 ? s_ops[T::OP_DOUBLES + (ly0 + j) * TX + lx] : (in ? s.b[off] : 0.0);
+      w2v[j] = s_wd[2 * TX + ly0 + j];
+      rw2v[j] = s_wd[2 * TX + TY + ly0 + j];
    }
    double res[R], lres[R];
 #pragma unroll
@@ -200,58 +225,75 @@ constexpr int fv2d_min_blocks() {
 }
 
 template <int K, int COMBINE, class M, int UPW, int TX, int TY, int NT>
-__global__ void __launch_bounds__(NT, fv2d_min_blocks<M, UPW, NT>()) fv2d_stage_kernel(const Fv2dGeom g, const StageArgs s) {
+__global__ void __launch_bounds__(NT, fv2d_min_blocks<M, UPW, NT>())
+   fv2d_stage_kernel(const Fv2dGeom g, const StageArgs s, const __grid_constant__ CUtensorMap tm_v, const __grid_constant__ CUtensorMap tm_a,
+                     const __grid_constant__ CUtensorMap tm_b) {
    using T = Tile2d<TX, TY, UPW>;
    constexpr int R = T::R, H = T::H;
-   extern __shared__ __align__(16) double smem[];
+   constexpr int NSTG = fv2d_nstaged(COMBINE, UPW);
+   extern __shared__ __align__(128) double smem[];
    double *s_v = smem + T::OFF_V;
    double *s_vlx = smem + T::OFF_VLX, *s_vrx = smem + T::OFF_VRX;
    double *s_vre = smem + T::OFF_VRE, *s_vle = smem + T::OFF_VLE;
+   double *s_wd = smem + T::OFF_W1;
+   double *s_ops = smem + T::OFF_OPS;
 
-   __shared__ __align__(8) unsigned long long s_bar[2];
+   __shared__ __align__(8) unsigned long long s_bar[3]; // [0], [1]: tile buffer full; [2]: staged operands of this tile full
    asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); // the next kernel may be scheduled as SMs free up
    const int tid = threadIdx.x;
    const int total_tiles = g.tiles_x * g.tiles_y;
 
-   // warp 0 fetches a tile + frame (rows y0-H .. y0+TY+H-1, columns x0-H .. x0+TX+H-1, clipped to the padded state)
-   // with one TMA bulk copy per row, all completing on the buffer's mbarrier
+   // one thread fetches a tile + frame (rows y0-H .. y0+TY+H-1, columns x0-H .. x0+TX+H-1) with ONE tensor-map TMA load;
+   // the parts of the box beyond the padded state arrive as zeros
    auto issue = [&](int tile_id, int buf) {
       const int ty = tile_id / g.tiles_x, tx = tile_id - ty * g.tiles_x;
-      const int x0 = tx * TX, y0 = ty * TY;
-      int hi = x0 - H + T::SP;
-      if (hi > (int)g.pitch - PAD) hi = (int)g.pitch - PAD;
-      const uint32_t row_bytes = (uint32_t)(hi - (x0 - H)) * (uint32_t)sizeof(double);
-      int r_lo = -PAD2 - (y0 - H), r_hi = (int)g.n1 + PAD2 - (y0 - H); // valid tile rows [r_lo, r_hi)
-      r_lo = r_lo < 0 ? 0 : r_lo;
-      r_hi = r_hi > T::SROWS ? T::SROWS : r_hi;
-      const int lane = tid;
-      if (lane == 0) mbar_expect_tx(&s_bar[buf], row_bytes * (uint32_t)(r_hi - r_lo));
-      __syncwarp();
-      double *dst = s_v + buf * T::TILE_DOUBLES;
-      for (int r = r_lo + lane; r < r_hi; r += 32)
-         tma_bulk_g2s(dst + r * T::SP, s.vin + (int64_t)(y0 - H + r) * g.pitch + (x0 - H), row_bytes, &s_bar[buf]);
+      mbar_expect_tx(&s_bar[buf], (uint32_t)(T::TILE_DOUBLES * sizeof(double)));
+      tma_tensor_2d_g2s(smem_u32(s_v + buf * T::TILE_DOUBLES), &tm_v, tx * TX - H + PAD, ty * TY - H + PAD2, smem_u32(&s_bar[buf]));
+   };
+   // the pointwise operands of a tile (TX x TY boxes of a and b), one tensor-map TMA load each
+   auto issue_ops = [&](int tile_id) {
+      if constexpr (NSTG > 0) {
+         const int ty = tile_id / g.tiles_x, tx = tile_id - ty * g.tiles_x;
+         mbar_expect_tx(&s_bar[2], (uint32_t)(NSTG * T::OP_DOUBLES * sizeof(double)));
+         tma_tensor_2d_g2s(smem_u32(s_ops), &tm_a, tx * TX + PAD, ty * TY + PAD2, smem_u32(&s_bar[2]));
+         if constexpr (NSTG > 1) tma_tensor_2d_g2s(smem_u32(s_ops + T::OP_DOUBLES), &tm_b, tx * TX + PAD, ty * TY + PAD2, smem_u32(&s_bar[2]));
+      }
    };
 
-   for (int idx = tid; idx < 2 * T::TILE_DOUBLES; idx += NT) s_v[idx] = 0.0; // parts a clipped copy never writes
-   asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
    if (tid == 0) {
       mbar_init(&s_bar[0], 1);
       mbar_init(&s_bar[1], 1);
+      mbar_init(&s_bar[2], 1);
       asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
    }
    __syncthreads();
    asm volatile("griddepcontrol.wait;" ::: "memory"); // state vectors written by earlier kernels are complete from here on
-   if (tid < 32 && (int)blockIdx.x < total_tiles) issue(blockIdx.x, 0);
+   if (tid == 0 && (int)blockIdx.x < total_tiles) issue(blockIdx.x, 0);
 
    int it_n = 0;
    for (int tile_id = blockIdx.x; tile_id < total_tiles; tile_id += gridDim.x, ++it_n) {
    const int buf = it_n & 1;
-   // every thread is past phase B of the previous tile: its staged tile and its vl/vr arrays may be overwritten
+   // every thread is past phase B of the previous tile: its staged tile, operands, widths and vl/vr arrays may be overwritten
    __syncthreads();
-   if (tid < 32 && tile_id + (int)gridDim.x < total_tiles) issue(tile_id + gridDim.x, buf ^ 1);
+   if (tid == 0) {
+      issue_ops(tile_id);
+      if (tile_id + (int)gridDim.x < total_tiles) issue(tile_id + gridDim.x, buf ^ 1);
+   }
    const int ty_ = tile_id / g.tiles_x, tx_ = tile_id - ty_ * g.tiles_x;
    const int64_t x0 = (int64_t)tx_ * TX;
    const int64_t y0 = (int64_t)ty_ * TY;
+   // per-tile copies of the widths (read by every thread in phase B, after the barrier below)
+   for (int i = tid; i < TX + TY; i += NT) {
+      if (i < TX) {
+         const int64_t gx = x0 + i < g.n0 ? x0 + i : g.n0 - 1;
+         s_wd[i] = __ldg(g.w1 + gx);
+         s_wd[TX + i] = __ldg(g.rw1 + gx);
+      } else {
+         const int64_t gy = y0 + (i - TX) < g.n1 ? y0 + (i - TX) : g.n1 - 1;
+         s_wd[2 * TX + (i - TX)] = __ldg(g.w2 + gy);
+         s_wd[2 * TX + TY + (i - TX)] = __ldg(g.rw2 + gy);
+      }
+   }
    double *s_vt = s_v + buf * T::TILE_DOUBLES; // this tile
    mbar_wait(&s_bar[buf], (uint32_t)((it_n >> 1) & 1));
 
@@ -325,6 +367,7 @@ __global__ void __launch_bounds__(NT, fv2d_min_blocks<M, UPW, NT>()) fv2d_stage_
       if constexpr (!UPW) s_vle[ry * TX + lx] = vlY[q][0];
    }
    __syncthreads();
+   if constexpr (NSTG > 0) mbar_wait(&s_bar[2], (uint32_t)(it_n & 1));
 
    // ---- phase B: fluxes, divergence, combination ---------------------------------------------------------
    const bool interior = !s.out_dense && x0 > 0 && x0 + TX < g.n0 && y0 > 0 && y0 + TY < g.n1;
@@ -342,9 +385,9 @@ __global__ void __launch_bounds__(NT, fv2d_min_blocks<M, UPW, NT>()) fv2d_stage_
       }
       vpY[R] = UPW ? 0.0 : s_vle[(ry + 1) * TX + lx];
       if (interior)
-         fv2d_phase_b<K, COMBINE, M, UPW, TX, TY, true>(g, s, s_vt, s_vlx, s_vrx, vmY, vpY, x0, y0, lx, ry * R);
+         fv2d_phase_b<K, COMBINE, M, UPW, TX, TY, true>(g, s, s_vt, s_vlx, s_vrx, s_wd, s_ops, vmY, vpY, x0, y0, lx, ry * R);
       else
-         fv2d_phase_b<K, COMBINE, M, UPW, TX, TY, false>(g, s, s_vt, s_vlx, s_vrx, vmY, vpY, x0, y0, lx, ry * R);
+         fv2d_phase_b<K, COMBINE, M, UPW, TX, TY, false>(g, s, s_vt, s_vlx, s_vrx, s_wd, s_ops, vmY, vpY, x0, y0, lx, ry * R);
    }
    } // tile loop
 }
@@ -359,21 +402,31 @@ constexpr int NT2F = 2 * HRW_NT2;                            // threads per tile
 constexpr int TX2S = 32, TY2S = 16, NT2S = 128; // small grids (e.g. example2's 250x250): enough tiles to occupy every SM
 
 template <int K, int COMBINE, class M, int UPW, int TX2, int TY2, int NT2>
-static int launch2d_t(const Fv2dGeom &g, const StageArgs &a, cudaStream_t st) {
+static int launch2d_t(Fv *fv, const Fv2dGeom &g, const StageArgs &a, cudaStream_t st) {
    using T = Tile2d<TX2, TY2, UPW>;
+   constexpr int NSTG = fv2d_nstaged(COMBINE, UPW);
+   constexpr size_t BYTES = T::bytes(NSTG);
    auto kern = fv2d_stage_kernel<K, COMBINE, M, UPW, TX2, TY2, NT2>;
-   static bool configured = false; // one flag per instantiation
-   if (!configured) {
-      HRW_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)T::BYTES));
-      configured = true;
+   static bool configured[64] = {}; // one flag per instantiation and device (function attributes are per device)
+   int dev = 0;
+   cudaGetDevice(&dev);
+   if (!configured[dev & 63]) {
+      HRW_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)BYTES));
+      configured[dev & 63] = true;
    }
+   // tensor maps of the stage input (tile + frame boxes) and of the staged operands (tile boxes)
+   CUtensorMap tm_v, tm_a, tm_b;
+   HRW_TRY(fv_tmap_2d(fv, a.vin, T::SP, T::SROWS, &tm_v));
+   tm_a = tm_v;
+   tm_b = tm_v;
+   if (NSTG >= 1) HRW_TRY(fv_tmap_2d(fv, a.a, TX2, TY2, &tm_a));
+   if (NSTG >= 2) HRW_TRY(fv_tmap_2d(fv, a.b, TX2, TY2, &tm_b));
    // persistent grid: SMs x resident CTAs of this instantiation, never more than there are tiles
    static int resident = 0;
    if (resident == 0) {
-      int dev = 0, sms = 0, per_sm = 0;
-      cudaGetDevice(&dev);
+      int sms = 0, per_sm = 0;
       cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
-      cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, NT2, T::BYTES);
+      cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, NT2, BYTES);
       resident = (sms > 0 ? sms : 148) * (per_sm > 0 ? per_sm : 1);
    }
    const int64_t tiles = (int64_t)g.tiles_x * g.tiles_y;
@@ -381,49 +434,49 @@ static int launch2d_t(const Fv2dGeom &g, const StageArgs &a, cudaStream_t st) {
    cudaLaunchConfig_t cfg = {};
    cfg.gridDim = dim3((unsigned)(tiles < resident ? tiles : resident));
    cfg.blockDim = dim3(NT2);
-   cfg.dynamicSmemBytes = T::BYTES;
+   cfg.dynamicSmemBytes = BYTES;
    cfg.stream = st;
    cudaLaunchAttribute attr[1];
    attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
    attr[0].val.programmaticStreamSerializationAllowed = 1;
    cfg.attrs = attr;
    cfg.numAttrs = 1;
-   HRW_CUDA(cudaLaunchKernelEx(&cfg, kern, g, a));
+   HRW_CUDA(cudaLaunchKernelEx(&cfg, kern, g, a, tm_v, tm_a, tm_b));
    return HRWENO_OK;
 }
 
 template <int K, int COMBINE, class M, int UPW>
-static int launch2d_u(const Fv2dGeom &g, const StageArgs &a, cudaStream_t st) {
-   if (g.small_tiles) return launch2d_t<K, COMBINE, M, UPW, TX2S, TY2S, NT2S>(g, a, st);
+static int launch2d_u(Fv *fv, const Fv2dGeom &g, const StageArgs &a, cudaStream_t st) {
+   if (g.small_tiles) return launch2d_t<K, COMBINE, M, UPW, TX2S, TY2S, NT2S>(fv, g, a, st);
    // fast mode: 512 threads per tile (one x1-run and one x2-run each, 64 registers, 32 resident warps per SM instead of 24):
    // +6 % on cfg4; strict mode needs its 112-128 registers and keeps 256 threads (profiles/r1_variant_sweeps.txt)
-   if constexpr (!M::strict) return launch2d_t<K, COMBINE, M, UPW, TX2, TY2, NT2F>(g, a, st);
-   return launch2d_t<K, COMBINE, M, UPW, TX2, TY2, NT2>(g, a, st);
+   if constexpr (!M::strict) return launch2d_t<K, COMBINE, M, UPW, TX2, TY2, NT2F>(fv, g, a, st);
+   return launch2d_t<K, COMBINE, M, UPW, TX2, TY2, NT2>(fv, g, a, st);
 }
 
 template <int K, int COMBINE, class M>
-static int launch2d(const Fv2dGeom &g, const StageArgs &a, cudaStream_t st) {
+static int launch2d(Fv *fv, const Fv2dGeom &g, const StageArgs &a, cudaStream_t st) {
    const bool upw = g.flux1.model == HRWENO_FLUX_LINEAR && g.flux1.scheme == HRWENO_SCHEME_GODUNOV && g.flux1.coef >= 0.0 && g.flux2.coef >= 0.0;
-   return upw ? launch2d_u<K, COMBINE, M, 1>(g, a, st) : launch2d_u<K, COMBINE, M, 0>(g, a, st);
+   return upw ? launch2d_u<K, COMBINE, M, 1>(fv, g, a, st) : launch2d_u<K, COMBINE, M, 0>(fv, g, a, st);
 }
 
 template <int K, class M>
-static int launch2d_c(int combine, const Fv2dGeom &g, const StageArgs &a, cudaStream_t st) {
+static int launch2d_c(Fv *fv, int combine, const Fv2dGeom &g, const StageArgs &a, cudaStream_t st) {
    switch (combine) {
-   case C_RHS: return launch2d<K, C_RHS, M>(g, a, st);
-   case C_EULER: return launch2d<K, C_EULER, M>(g, a, st);
-   case C_RK2_FINAL: return launch2d<K, C_RK2_FINAL, M>(g, a, st);
-   case C_RK3_S2: return launch2d<K, C_RK3_S2, M>(g, a, st);
-   case C_RK3_S3: return launch2d<K, C_RK3_S3, M>(g, a, st);
-   default: return launch2d<K, C_MS, M>(g, a, st);
+   case C_RHS: return launch2d<K, C_RHS, M>(fv, g, a, st);
+   case C_EULER: return launch2d<K, C_EULER, M>(fv, g, a, st);
+   case C_RK2_FINAL: return launch2d<K, C_RK2_FINAL, M>(fv, g, a, st);
+   case C_RK3_S2: return launch2d<K, C_RK3_S2, M>(fv, g, a, st);
+   case C_RK3_S3: return launch2d<K, C_RK3_S3, M>(fv, g, a, st);
+   default: return launch2d<K, C_MS, M>(fv, g, a, st);
    }
 }
 
 template <class M>
-static int launch2d_k(int k, int combine, const Fv2dGeom &g, const StageArgs &a, cudaStream_t st) {
-   if (k == 1) return launch2d_c<1, M>(combine, g, a, st);
-   if (k == 2) return launch2d_c<2, M>(combine, g, a, st);
-   return launch2d_c<3, M>(combine, g, a, st);
+static int launch2d_k(Fv *fv, int k, int combine, const Fv2dGeom &g, const StageArgs &a, cudaStream_t st) {
+   if (k == 1) return launch2d_c<1, M>(fv, combine, g, a, st);
+   if (k == 2) return launch2d_c<2, M>(fv, combine, g, a, st);
+   return launch2d_c<3, M>(fv, combine, g, a, st);
 }
 
 int fv2d_stage(Fv *fv, int combine, const StageArgs &args, cudaStream_t st) {
@@ -450,8 +503,8 @@ int fv2d_stage(Fv *fv, int combine, const StageArgs &args, cudaStream_t st) {
    g.phys_lo = d.rank == 0;
    g.phys_hi = d.rank == d.nranks - 1;
    if ((int64_t)g.tiles_x * g.tiles_y > 2000000000LL) return fail(HRWENO_EINVAL, "2D grid too large for one launch");
-   if (d.mode == HRWENO_MODE_STRICT) return launch2d_k<Strict>(d.k, combine, g, args, st);
-   return launch2d_k<Fast>(d.k, combine, g, args, st);
+   if (d.mode == HRWENO_MODE_STRICT) return launch2d_k<Strict>(fv, d.k, combine, g, args, st);
+   return launch2d_k<Fast>(fv, d.k, combine, g, args, st);
 }
 
 } // namespace hrw

@@ -37,6 +37,8 @@ struct GenGeom {
    const double *cc0, *cc1;   // cross coefficient: cc0[j] for x1 faces of row j, cc1[i] for x2 faces of column i, or nullptr
    WenoK kc;
    FluxCfg fx0, fx1;
+   int has_ts;  // the flux carries a time factor g(t) (fluxes.f90:12-18 passes t to the flux)
+   double ts;   // its value at this evaluation's time, computed on the host
 };
 
 // reconstruct one cell (the arithmetic of recon_kernel, weno.cu).  `cell` points at the cell inside its row, the row is
@@ -72,17 +74,23 @@ __device__ __forceinline__ void gen_recon(const double *cell, int64_t inc, int64
    }
 }
 
-// f(v, x) = (model(v)*cross)*face, left to right like `v*x(1)*x(2)` (example2:153); an absent factor is not multiplied in
-__device__ __forceinline__ double gen_phys(const FluxCfg &c, double v, bool has_cc, double cc, bool has_fc, double fc) {
+// f(v, x, t) = ((model(v)*cross)*face)*g(t), left to right like `v*x(1)*x(2)` (example2:153); an absent factor is not multiplied in
+struct GenTs {
+   bool has;
+   double v;
+};
+__device__ __forceinline__ double gen_phys(const FluxCfg &c, double v, bool has_cc, double cc, bool has_fc, double fc, const GenTs &ts) {
    double f = phys_flux<Strict>(c, v);
    if (has_cc) f = __dmul_rn(f, cc);
    if (has_fc) f = __dmul_rn(f, fc);
+   if (ts.has) f = __dmul_rn(f, ts.v);
    return f;
 }
 
-__device__ __forceinline__ double gen_face_flux(const FluxCfg &c, double vm, double vp, bool has_cc, double cc, bool has_fc, double fc) {
-   const double fm = gen_phys(c, vm, has_cc, cc, has_fc, fc);
-   const double fp = gen_phys(c, vp, has_cc, cc, has_fc, fc);
+__device__ __forceinline__ double gen_face_flux(const FluxCfg &c, double vm, double vp, bool has_cc, double cc, bool has_fc, double fc,
+                                                const GenTs &ts) {
+   const double fm = gen_phys(c, vm, has_cc, cc, has_fc, fc, ts);
+   const double fp = gen_phys(c, vp, has_cc, cc, has_fc, fc, ts);
    if (c.scheme == HRWENO_SCHEME_LAX_FRIEDRICHS) // (f(vm) + f(vp) - alpha*(vp - vm))/2      fluxes.f90:43
       return __dmul_rn(__dsub_rn(__dadd_rn(fm, fp), __dmul_rn(c.alpha, __dsub_rn(vp, vm))), 0.5);
    const double lo = fm < fp ? fm : fp; // fluxes.f90:70-74
@@ -163,12 +171,13 @@ __device__ __forceinline__ void gen_tile(const GenGeom &g, const StageArgs &a, c
       const int64_t i = i0 + lx, j = j0 + ly;
       if (!INTERIOR && !(i < g.n0 && j < g.n1)) continue;
       // x1: face f lies between cells f-1 and f: godunov(flux, vr(f-1), vl(f), [right(f-1), center2(j)])  (example1:99, example2:100)
+      const GenTs ts{g.has_ts != 0, g.ts};
       const bool hc0 = g.cc0 != nullptr, hf0 = g.fc0 != nullptr;
       const double cc0 = hc0 ? g.cc0[j] : 1.0;
       const int c1 = lx + 1 + ly * SX; // shared index of cell (i, j) in the x1 arrays
       double fl = 0.0, fr = 0.0;
-      if (INTERIOR || i > 0) fl = gen_face_flux(g.fx0, s_r1[c1 - 1], s_l1[c1], hc0, cc0, hf0, hf0 ? g.fc0[i] : 1.0);
-      if (INTERIOR || i < g.n0 - 1) fr = gen_face_flux(g.fx0, s_r1[c1], s_l1[c1 + 1], hc0, cc0, hf0, hf0 ? g.fc0[i + 1] : 1.0);
+      if (INTERIOR || i > 0) fl = gen_face_flux(g.fx0, s_r1[c1 - 1], s_l1[c1], hc0, cc0, hf0, hf0 ? g.fc0[i] : 1.0, ts);
+      if (INTERIOR || i < g.n0 - 1) fr = gen_face_flux(g.fx0, s_r1[c1], s_l1[c1 + 1], hc0, cc0, hf0, hf0 ? g.fc0[i + 1] : 1.0, ts);
       if constexpr (!INTERIOR) gen_bc(g.bc, i, g.n0, fl, fr);
       double L = -__ddiv_rn(__dsub_rn(fr, fl), g.w0[i]); // -(fedges(i) - fedges(i-1))/width(i)   example1:107, example2:125
       if constexpr (TWO_D) {
@@ -176,8 +185,8 @@ __device__ __forceinline__ void gen_tile(const GenGeom &g, const StageArgs &a, c
          const double cc1 = hc1 ? g.cc1[i] : 1.0;
          const int c2 = lx + (ly + 1) * TX; // shared index of cell (i, j) in the x2 arrays
          double gl = 0.0, gr = 0.0;
-         if (INTERIOR || j > 0) gl = gen_face_flux(g.fx1, s_r2[c2 - TX], s_l2[c2], hc1, cc1, hf1, hf1 ? g.fc1[j] : 1.0);
-         if (INTERIOR || j < g.n1 - 1) gr = gen_face_flux(g.fx1, s_r2[c2], s_l2[c2 + TX], hc1, cc1, hf1, hf1 ? g.fc1[j + 1] : 1.0);
+         if (INTERIOR || j > 0) gl = gen_face_flux(g.fx1, s_r2[c2 - TX], s_l2[c2], hc1, cc1, hf1, hf1 ? g.fc1[j] : 1.0, ts);
+         if (INTERIOR || j < g.n1 - 1) gr = gen_face_flux(g.fx1, s_r2[c2], s_l2[c2 + TX], hc1, cc1, hf1, hf1 ? g.fc1[j + 1] : 1.0, ts);
          if constexpr (!INTERIOR) gen_bc(g.bc, j, g.n1, gl, gr);
          L = __dsub_rn(L, __ddiv_rn(__dsub_rn(gr, gl), g.w1[j])); // ... - (fedges2(j,i) - fedges2(j-1,i))/width2(j)   example2:126
       }
@@ -251,6 +260,8 @@ int fvgen_stage(Fv *fv, int combine, const StageArgs &args, cudaStream_t st) {
    g.kc = make_wenok(d.eps);
    g.fx0 = FluxCfg{d.flux_model, d.flux_scheme, d.flux_coef[0], d.alpha};
    g.fx1 = FluxCfg{d.flux_model, d.flux_scheme, d.flux_coef[1], d.alpha};
+   g.has_ts = fv->tfn != nullptr;
+   g.ts = fv->tfn ? fv->tfn(fv->tfn_ctx, args.t) : 1.0; // the caller's g(t) at this evaluation's time
    if (!g.w0 || (two_d && !g.w1)) return fail(HRWENO_EINVAL, "general stage: width arrays missing");
    const int64_t tx = two_d ? GenTile<true>::TX : GenTile<false>::TX, ty = two_d ? GenTile<true>::TY : GenTile<false>::TY;
    const int64_t tiles = ((g.n0 + tx - 1) / tx) * ((g.n1 + ty - 1) / ty);

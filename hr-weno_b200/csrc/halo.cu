@@ -84,23 +84,48 @@ __global__ void halo_recv_kernel(double *__restrict__ cell0, int ndim, int64_t n
 void fv_halo_free(Fv *fv) {
    Halo &h = fv->halo;
    for (int s = 0; s < 2; ++s)
-      if (h.peer[s]) cudaIpcCloseMemHandle(h.peer[s]);
+      if (h.peer[s] && !h.local_peers) cudaIpcCloseMemHandle(h.peer[s]);
    cudaFree(h.mbox);
    h = Halo{};
 }
+
+// this rank's mailbox (allocated on the current device on first use)
+static int halo_alloc_mbox(Fv *fv) {
+   Halo &h = fv->halo;
+   if (h.mbox) return HRWENO_OK;
+   const int k = fv->d.k;
+   h.halo_doubles = fv->d.ndim == 1 ? (size_t)fv->rows * k : (size_t)k * fv->n0;
+   h.bytes = Halo::HDR_BYTES + 2 * Halo::NSLOTS * h.halo_doubles * sizeof(double);
+   if (fv->d.ndim == 1 && fv->rows == 1) { // wide slots [side][2][WIDE_H] behind the per-stage ones
+      h.bytes = (h.bytes + 255) & ~(size_t)255;
+      h.wide_off = h.bytes;
+      h.bytes += (size_t)2 * 2 * Halo::WIDE_H * sizeof(double);
+   }
+   HRW_CUDA(cudaMalloc(&h.mbox, h.bytes));
+   HRW_CUDA(cudaMemset(h.mbox, 0, h.bytes));
+   HRW_CUDA(cudaDeviceSynchronize());
+   return HRWENO_OK;
+}
+
+// slabs of ONE process (mgpu.cu): the neighbours' mailboxes are ordinary device pointers of this address space; the
+// caller has enabled peer access between the devices.  Call on every slab with its own device current.
+int fv_halo_connect_local(Fv *fv, Fv *left, Fv *right) {
+   HRW_TRY(halo_alloc_mbox(fv));
+   Halo &h = fv->halo;
+   if ((left && !left->halo.mbox) || (right && !right->halo.mbox)) return fail(HRWENO_ECOMM, "neighbour slab has no mailbox yet");
+   h.peer[0] = left ? left->halo.mbox : nullptr;
+   h.peer[1] = right ? right->halo.mbox : nullptr;
+   h.local_peers = true;
+   h.ready = true;
+   return HRWENO_OK;
+}
+int fv_halo_prepare_local(Fv *fv) { return halo_alloc_mbox(fv); }
 
 int fv_halo_export(Fv *fv, void *handle_out) {
    static_assert(sizeof(cudaIpcMemHandle_t) == HRWENO_IPC_HANDLE_BYTES, "IPC handle size");
    if (!handle_out) return fail(HRWENO_EINVAL, "null handle buffer");
    Halo &h = fv->halo;
-   if (!h.mbox) {
-      const int k = fv->d.k;
-      h.halo_doubles = fv->d.ndim == 1 ? (size_t)fv->rows * k : (size_t)k * fv->n0;
-      h.bytes = Halo::HDR_BYTES + 2 * Halo::NSLOTS * h.halo_doubles * sizeof(double);
-      HRW_CUDA(cudaMalloc(&h.mbox, h.bytes));
-      HRW_CUDA(cudaMemset(h.mbox, 0, h.bytes));
-      HRW_CUDA(cudaDeviceSynchronize());
-   }
+   HRW_TRY(halo_alloc_mbox(fv));
    cudaIpcMemHandle_t ipc;
    HRW_CUDA(cudaIpcGetMemHandle(&ipc, h.mbox));
    std::memcpy(handle_out, &ipc, sizeof(ipc));
@@ -166,6 +191,75 @@ int fv_exchange(Fv *fv, double *cell0, cudaStream_t st) {
    const long long timeout_cycles = 60LL * 1900000000LL; // ~60 s at 1.9 GHz: a dead neighbour, not a slow one
    halo_recv_kernel<<<blocks, 256, 0, st>>>(cell0, fv->d.ndim, fv->n0, fv->n1, fv->rows, fv->pitch, k, from_left, from_right, ffl,
                                             ffr, seq, reinterpret_cast<unsigned int *>(h.mbox + ERR_OFF), timeout_cycles);
+   fv->launches += 3;
+   HRW_CUDA(cudaGetLastError());
+   return HRWENO_OK;
+}
+
+// ---- wide halos: once per host-pointer integrate call (ode.cu: chunk pipeline on slabs) -------------------------------
+static constexpr size_t WIDE_FLAG_OFF = ERR_OFF + 128; // two flags on their own 128-B lines behind the error word
+static inline double *wide_slot(unsigned char *mbox, size_t wide_off, int side, int slot) {
+   return reinterpret_cast<double *>(mbox + wide_off) + ((size_t)side * 2 + slot) * Halo::WIDE_H;
+}
+
+__global__ void wide_send_kernel(const double *__restrict__ first, const double *__restrict__ last, double *__restrict__ to_left,
+                                 double *__restrict__ to_right, int h) {
+   for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < h; i += gridDim.x * blockDim.x) {
+      if (to_left) to_left[i] = first[i];
+      if (to_right) to_right[i] = last[i];
+   }
+}
+
+__global__ void wide_recv_kernel(double *__restrict__ dst_left, double *__restrict__ dst_right, const double *from_left, const double *from_right,
+                                 const unsigned long long *flag_from_left, const unsigned long long *flag_from_right, unsigned long long seq,
+                                 unsigned int *err, long long timeout_cycles, int h) {
+   __shared__ int ok;
+   if (threadIdx.x == 0) {
+      int good = *reinterpret_cast<volatile unsigned int *>(err) == 0;
+      const long long t0 = clock64();
+      for (int side = 0; side < 2 && good; ++side) {
+         const unsigned long long *f = side == 0 ? flag_from_left : flag_from_right;
+         if (!f) continue;
+         while (*reinterpret_cast<const volatile unsigned long long *>(f) < seq) {
+            if (clock64() - t0 > timeout_cycles) {
+               atomicExch(err, 1u);
+               good = 0;
+               break;
+            }
+            __nanosleep(200);
+         }
+      }
+      __threadfence_system();
+      ok = good;
+   }
+   __syncthreads();
+   if (!ok) return;
+   for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < h; i += gridDim.x * blockDim.x) {
+      if (from_left) dst_left[i] = __ldcv(from_left + i);
+      if (from_right) dst_right[i] = __ldcv(from_right + i);
+   }
+}
+
+int fv_exchange_wide(Fv *fv, double *cell0, int64_t n, cudaStream_t st) {
+   Halo &h = fv->halo;
+   if (fv->d.nranks <= 1) return HRWENO_OK;
+   if (!h.ready || !h.wide_off) return fail(HRWENO_ECOMM, "wide halo exchange: mailboxes not connected");
+   constexpr int H = Halo::WIDE_H;
+   const unsigned long long seq = ++h.wide_seq;
+   const int slot = (int)(seq & 1); // two slots: a rank is at most one call ahead of its neighbours (its receive waits for their send)
+   // I am the right neighbour of my left neighbour: my first cells go to its side 1 ("from right"), and vice versa
+   double *to_left = h.peer[0] ? wide_slot(h.peer[0], h.wide_off, 1, slot) : nullptr;
+   double *to_right = h.peer[1] ? wide_slot(h.peer[1], h.wide_off, 0, slot) : nullptr;
+   auto *fl = h.peer[0] ? reinterpret_cast<unsigned long long *>(h.peer[0] + WIDE_FLAG_OFF + 128) : nullptr;
+   auto *fr = h.peer[1] ? reinterpret_cast<unsigned long long *>(h.peer[1] + WIDE_FLAG_OFF) : nullptr;
+   wide_send_kernel<<<32, 256, 0, st>>>(cell0, cell0 + n - H, to_left, to_right, H);
+   halo_signal_kernel<<<1, 1, 0, st>>>(fl, fr, seq);
+   const double *from_left = h.peer[0] ? wide_slot(h.mbox, h.wide_off, 0, slot) : nullptr;
+   const double *from_right = h.peer[1] ? wide_slot(h.mbox, h.wide_off, 1, slot) : nullptr;
+   auto *ffl = h.peer[0] ? reinterpret_cast<const unsigned long long *>(h.mbox + WIDE_FLAG_OFF) : nullptr;
+   auto *ffr = h.peer[1] ? reinterpret_cast<const unsigned long long *>(h.mbox + WIDE_FLAG_OFF + 128) : nullptr;
+   wide_recv_kernel<<<32, 256, 0, st>>>(cell0 - H, cell0 + n, from_left, from_right, ffl, ffr, seq, reinterpret_cast<unsigned int *>(h.mbox + ERR_OFF),
+                                        60LL * 1900000000LL, H);
    fv->launches += 3;
    HRW_CUDA(cudaGetLastError());
    return HRWENO_OK;

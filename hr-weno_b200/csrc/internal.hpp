@@ -1,6 +1,7 @@
 // internal.hpp -- C++ objects behind the opaque C handles.
 #pragma once
 
+#include <cuda.h>
 #include <cuda_runtime.h>
 #include <stdint.h>
 
@@ -32,6 +33,7 @@ struct StageArgs {
    int out_dense;      // 1: out is a caller's dense array: no ghost writes, no alignment assumptions
    double c0, c1;      // dt-like coefficients: (dt) | (2dt) | (50dt, 10dt)
    int tile_begin = 0, tile_end = 0; // 1D only: restrict the launch to a range of tiles (0,0 = the whole state)
+   double t = 0.0;     // time of this right-hand-side evaluation (tvdode.f90:162,164,166,256): read by t-dependent fluxes only
 };
 
 // Halo traffic fused into the 1D stage kernel (one slab per GPU, rows == 1).  The CTA that computed the first / last
@@ -55,13 +57,19 @@ struct HaloIO {
 // cells into the ghost region of the state vector.  No host synchronisation, no NCCL call per stage.
 struct Halo {
    static constexpr int NSLOTS = 4;
-   static constexpr size_t HDR_BYTES = 2048; // flags[2][NSLOTS] on separate 128-B lines + error word
+   static constexpr size_t HDR_BYTES = 2048; // flags[2][NSLOTS] on separate 128-B lines + error word + 2 wide-halo flags
+   // wide halos (1D, one row): the WIDE_H cells next to each slab interface, exchanged ONCE per host-pointer integrate
+   // call so that every slab can run its own time-skewed chunk pipeline without per-stage traffic (ode.cu)
+   static constexpr int WIDE_H = 32768;
+   size_t wide_off = 0;                      // byte offset of the wide slots [side][2][WIDE_H] inside the mailbox (0: none)
+   unsigned long long wide_seq = 0;
    size_t halo_doubles = 0;                  // doubles per side per slot
    size_t bytes = 0;
    unsigned char *mbox = nullptr;            // my mailbox (device memory, cudaMalloc'ed so it can be IPC-exported)
    unsigned char *peer[2] = {nullptr, nullptr}; // left / right neighbour's mailbox mapped into this process
    unsigned long long seq = 0;               // number of exchanges done (identical on all ranks: SPMD)
    bool ready = false;
+   bool local_peers = false;                 // peer[] are mailboxes of slabs in this process (mgpu.cu), not IPC mappings
    // which padded state has its slab-interface ghost cells in a mailbox slot (sequence number) instead of in place
    const double *pending_buf = nullptr;
    unsigned long long pending_seq = 0;
@@ -87,11 +95,20 @@ struct Fv {
    double *d_cnu[2] = {nullptr, nullptr};   // cnu(0:k-1,-1:k-1,1:n[a]) of weno(ncells,k,eps,xedges)  (weno.f90:41,100-112)
    double *d_fcoef[2] = {nullptr, nullptr}; // face coefficient along axis a, index 0..n[a] like edges(0:n)
    double *d_ccoef[2] = {nullptr, nullptr}; // cross coefficient for the faces of axis a, index = cell along the other axis
+   hrweno_time_fn tfn = nullptr;            // time factor g(t) of the flux (hrweno_fv_set_flux_time_fn), evaluated on the host per stage
+   void *tfn_ctx = nullptr;
    // scratch for hrweno_fv_rhs[_dev]
    double *d_scratch_in = nullptr, *d_scratch_out = nullptr;
    cudaStream_t stream = nullptr;
    std::mutex mtx;
    int64_t launches = 0;
+   // TMA tensor maps of the padded 2D states, per (buffer, box shape) (tmap.cu)
+   struct TmapEntry {
+      const double *ptr;
+      uint32_t box0, box1;
+      alignas(64) CUtensorMap map;
+   };
+   std::vector<TmapEntry> tmaps;
    // geometry helpers
    size_t state_doubles() const; // doubles of one padded state vector
    double *cell0(double *base) const; // pointer at cell 0 of row 0 inside a padded allocation
@@ -113,6 +130,7 @@ int fv_max_wavespeed(Fv *fv, const double *v_dev, double *out_dev, cudaStream_t 
 int fvgen_stage(Fv *fv, int combine, const StageArgs &args, cudaStream_t st);
 int fv_set_xedges(Fv *fv, int axis, const double *xedges);
 int fv_set_flux_coef(Fv *fv, int axis, const double *face, const double *cross);
+int fv_set_flux_time_fn(Fv *fv, hrweno_time_fn g, void *ctx);
 // weno.cu: weno_calc_cnu (weno.f90:221-297) on the host
 void weno_calc_cnu_host(int64_t nc, int k, const double *xedges, std::vector<double> &cnu);
 // fv1d_small.cu: whole integrate call of a small 1D problem (<= 1024 cells) in one single-CTA launch
@@ -132,6 +150,11 @@ int fv_halo_export(Fv *fv, void *handle_out);
 int fv_halo_import(Fv *fv, const void *left, const void *right);
 int fv_halo_status(Fv *fv);
 void fv_halo_free(Fv *fv);
+// wide halo exchange of the padded state at cell0 (interior cells [0, n)): my first / last WIDE_H cells go to the
+// neighbours, theirs arrive in cells [-WIDE_H, 0) and [n, n + WIDE_H) (the caller's buffer has room for them)
+int fv_exchange_wide(Fv *fv, double *cell0, int64_t n, cudaStream_t st);
+int fv_halo_prepare_local(Fv *fv);                    // allocate this slab's mailbox on the current device
+int fv_halo_connect_local(Fv *fv, Fv *left, Fv *right); // same-process neighbours (peer access enabled by the caller)
 
 struct Weno {
    int64_t ncells = 0;
@@ -171,10 +194,15 @@ struct Ode {
    // device state (padded layout for the fused path, dense for the callback path)
    std::vector<double *> bufs;
    int ring = 0; // mstvd: index of the slot holding u^n inside the u ring
+   bool attached = false; // the current state lives inside the integrator (hrweno_ode_attach): null u in integrate
    cudaStream_t stream = nullptr;
    // chunk pipeline of the host-pointer entry point (ode.cu: rk_integrate_pipelined)
    cudaStream_t s_in = nullptr, s_out = nullptr;
    std::vector<cudaEvent_t> ev_in, ev_fin;
+   // slabs: the pipeline runs on an operator over the slab extended by the wide halos, with its own three states
+   Fv *fv_ext = nullptr;
+   std::vector<double *> ext_bufs;
+   cudaEvent_t ev_edge = nullptr;
    ~Ode();
 };
 

@@ -17,6 +17,9 @@ namespace hrw {
 static inline bool is_done(double t, double tout, double dt) { return (t - tout) * std::copysign(1.0, dt) > 0.0; }
 
 Ode::~Ode() {
+   for (double *p : ext_bufs) cudaFree(p);
+   delete fv_ext;
+   if (ev_edge) cudaEventDestroy(ev_edge);
    cudaFreeHost(h_u);
    cudaFreeHost(h_udot);
    for (double *p : bufs) cudaFree(p);
@@ -128,11 +131,12 @@ int ode_create(Ode **out, bool is_ms, Fv *fv, hrweno_rhs_fn fu, void *ctx, int64
 // ------------------------------------------------------------------------------------------------
 // one RK step  src -> dst  (dst may equal src); t1, t2 are temporaries.  Fused: padded states.
 // ------------------------------------------------------------------------------------------------
-static int rk_step_fused(Ode *o, int order, double *src, double *dst, double *t1, double *t2, double dt, cudaStream_t st) {
+static int rk_step_fused(Ode *o, int order, double t, double *src, double *dst, double *t1, double *t2, double dt, cudaStream_t st) {
    Fv *fv = o->fv;
    StageArgs a{};
    a.ld_out = fv->pitch;
    a.out_dense = 0;
+   a.t = t; // fu(t, u, udot)  tvdode.f90:138,149,162
    auto c0 = [&](double *p) { return fv->cell0(p); };
    if (order == 1) { // u = u + dt*udot  (needs dst != src: the stencil reads src)
       a.vin = c0(src);
@@ -146,6 +150,7 @@ static int rk_step_fused(Ode *o, int order, double *src, double *dst, double *t1
    a.out = c0(t1);
    a.c0 = dt;
    HRW_TRY(fv_stage_halo(fv, C_EULER, a, true, st)); // ui = u + dt*udot
+   a.t = t + dt; // fu(t + dt, ui, udot)  tvdode.f90:151,164
    if (order == 2) {
       a.vin = c0(t1);
       a.a = c0(src);
@@ -158,6 +163,7 @@ static int rk_step_fused(Ode *o, int order, double *src, double *dst, double *t1
    a.a = c0(src);
    a.out = c0(t2);
    HRW_TRY(fv_stage_halo(fv, C_RK3_S2, a, true, st)); // ui = (3*u + ui + dt*udot)/4
+   a.t = t + dt / 2; // fu(t + dt/2, ui, udot)  tvdode.f90:166
    a.vin = c0(t2);
    a.a = c0(src);
    a.out = c0(dst);
@@ -196,6 +202,8 @@ static int rk_step_cb(Ode *o, int order, double t, double *u, double *ui, double
 static int rk_integrate(Ode *o, double *u_dev, double *t, double tout, double dt, int itask, cudaStream_t st) {
    if (o->istate < 1) return HRWENO_OK;          // :126
    if (is_done(*t, tout, dt)) return HRWENO_OK;   // :127
+   const bool resident = u_dev == nullptr; // state attached to the integrator (hrweno_ode_attach): no dense <-> padded copies
+   if (resident) u_dev = o->bufs.back();   // small problems keep their (dense) state in the staging vector
    if (o->fused && fv_small_eligible(o->fv)) {
       // small problem: count the steps exactly as the loop below would take them, then one single-CTA launch
       long long nsteps = 0;
@@ -214,22 +222,26 @@ static int rk_integrate(Ode *o, double *u_dev, double *t, double tout, double dt
    if (o->fused) {
       Fv *fv = o->fv;
       double *U = o->bufs[0], *T1 = o->bufs[1], *T2 = o->bufs[2];
-      HRW_TRY(fv_pack(fv, u_dev, fv->cell0(U), st));
-      HRW_TRY(fv_exchange(fv, fv->cell0(U), st));
-      o->launches++;
+      if (!resident) {
+         HRW_TRY(fv_pack(fv, u_dev, fv->cell0(U), st));
+         HRW_TRY(fv_exchange(fv, fv->cell0(U), st));
+         o->launches++;
+      }
       for (;;) {
          if (o->order == 1) {
-            HRW_TRY(rk_step_fused(o, 1, U, T1, nullptr, nullptr, dt, st));
+            HRW_TRY(rk_step_fused(o, 1, *t, U, T1, nullptr, nullptr, dt, st));
             std::swap(U, T1);
          } else {
-            HRW_TRY(rk_step_fused(o, o->order, U, U, T1, T2, dt, st));
+            HRW_TRY(rk_step_fused(o, o->order, *t, U, U, T1, T2, dt, st));
          }
          *t = *t + dt;
          o->fevals += o->order;
          if (is_done(*t, tout, dt) || itask == 2) break;
       }
-      HRW_TRY(fv_unpack(fv, fv->cell0(U), u_dev, st));
-      o->launches++;
+      if (!resident) {
+         HRW_TRY(fv_unpack(fv, fv->cell0(U), u_dev, st));
+         o->launches++;
+      }
       o->bufs[0] = U;
       o->bufs[1] = T1;
    } else {
@@ -256,8 +268,11 @@ static int ms_integrate(Ode *o, double *u_dev, double *t, double tout, double dt
    Fv *fv = o->fv;
    const int64_t n = o->neq;
    int &step = o->ring;
+   const bool resident = u_dev == nullptr; // state attached to the integrator (hrweno_ode_attach)
    // the caller's u is the current state (it may have been edited between calls, like the reference's inout u)
-   if (o->fused) {
+   if (resident) {
+      // the ring slot of the current step already holds the state, ghost cells included
+   } else if (o->fused) {
       HRW_TRY(fv_pack(fv, u_dev, fv->cell0(uring[step % 5]), st));
       HRW_TRY(fv_exchange(fv, fv->cell0(uring[step % 5]), st));
       o->launches++;
@@ -272,9 +287,10 @@ static int ms_integrate(Ode *o, double *u_dev, double *t, double tout, double dt
             a.vin = fv->cell0(U);
             a.out = fv->cell0(lring[step % 4]);
             a.ld_out = fv->pitch;
+            a.t = *t; // fu(t, u, udotold(:,i))  tvdode.f90:242
             HRW_TRY(fv_stage_halo(fv, C_RHS, a, false, st));
             o->launches++;
-            HRW_TRY(rk_step_fused(o, 3, U, Un, T1, T2, dt, st));
+            HRW_TRY(rk_step_fused(o, 3, *t, U, Un, T1, T2, dt, st));
          } else {
             o->fu(o->ctx, *t, n, U, lring[step % 4], st);
             HRW_CUDA(cudaMemcpyAsync(Un, U, (size_t)n * sizeof(double), cudaMemcpyDeviceToDevice, st));
@@ -300,6 +316,7 @@ static int ms_integrate(Ode *o, double *u_dev, double *t, double tout, double dt
          a.ld_out = fv->pitch;
          a.c0 = c50;
          a.c1 = c10;
+         a.t = *t; // fu(t, u, udot)  tvdode.f90:256
          HRW_TRY(fv_stage_halo(fv, C_MS, a, true, st));
          o->launches++;
       } else {
@@ -312,7 +329,9 @@ static int ms_integrate(Ode *o, double *u_dev, double *t, double tout, double dt
       o->fevals += 1;
       step++;
    }
-   if (o->fused) {
+   if (resident) {
+      // stays where it is
+   } else if (o->fused) {
       HRW_TRY(fv_unpack(fv, fv->cell0(uring[step % 5]), u_dev, st));
       o->launches++;
    } else {
@@ -356,8 +375,42 @@ int ode_create_host(Ode **out, bool is_ms, hrweno_rhs_host_fn fu, void *ctx, int
    return HRWENO_OK;
 }
 
+// Device callers that keep their state inside the integrator between output times (fused path): attach packs the dense
+// vector into the library-owned padded state ONCE, integrate_attached advances it with no dense <-> padded copies (they are
+// 2 x 16 B per cell and call: 20 % of an RK1 call's traffic), fetch writes the current state to a dense vector.
+int ode_attach(Ode *o, const double *u_dev, cudaStream_t st) {
+   if (!o || !u_dev) return fail(HRWENO_EINVAL, "hrweno_ode_attach: null argument");
+   if (!o->fused) return fail(HRWENO_EINVAL, "hrweno_ode_attach: only the fused integrators keep a padded state");
+   Fv *fv = o->fv;
+   if (fv_small_eligible(fv) && !o->is_ms) {
+      HRW_CUDA(cudaMemcpyAsync(o->bufs.back(), u_dev, (size_t)o->neq * sizeof(double), cudaMemcpyDeviceToDevice, st));
+   } else {
+      double *cur = o->is_ms ? o->bufs[o->ring % 5] : o->bufs[0];
+      HRW_TRY(fv_pack(fv, u_dev, fv->cell0(cur), st));
+      HRW_TRY(fv_exchange(fv, fv->cell0(cur), st));
+      fv->launches++;
+   }
+   o->attached = true;
+   return HRWENO_OK;
+}
+
+int ode_fetch(Ode *o, double *u_dev, cudaStream_t st) {
+   if (!o || !u_dev) return fail(HRWENO_EINVAL, "hrweno_ode_fetch: null argument");
+   if (!o->attached) return fail(HRWENO_ESTATE, "hrweno_ode_fetch: no attached state (hrweno_ode_attach first)");
+   Fv *fv = o->fv;
+   if (fv_small_eligible(fv) && !o->is_ms) {
+      HRW_CUDA(cudaMemcpyAsync(u_dev, o->bufs.back(), (size_t)o->neq * sizeof(double), cudaMemcpyDeviceToDevice, st));
+   } else {
+      double *cur = o->is_ms ? o->bufs[o->ring % 5] : o->bufs[0];
+      HRW_TRY(fv_unpack(fv, fv->cell0(cur), u_dev, st));
+      fv->launches++;
+   }
+   return HRWENO_OK;
+}
+
 int ode_integrate_dev(Ode *o, double *u_dev, double *t, double tout, double dt, int itask, cudaStream_t st) {
-   if (!o || !u_dev || !t) return fail(HRWENO_EINVAL, "integrate: null argument");
+   if (!o || !t) return fail(HRWENO_EINVAL, "integrate: null argument");
+   if (!u_dev && !(o->fused && o->attached)) return fail(HRWENO_ESTATE, "integrate: null u and no attached state (hrweno_ode_attach first)");
    const int s = o->is_ms ? ms_integrate(o, u_dev, t, tout, dt, st) : rk_integrate(o, u_dev, t, tout, dt, itask, st);
    if (s == HRWENO_OK && o->cb_status != HRWENO_OK) return o->cb_status; // a host-integrand staging copy failed
    return s;
@@ -380,21 +433,54 @@ __global__ void fill_ghost_kernel(double *cell0, int64_t n, int k, int left, int
    }
 }
 
+// Slabs (one row cut over several GPUs): the per-stage halo traffic of the resident path would chain every slab's pipeline
+// to its neighbours' (the first chunk of a slab needs, stage by stage, the LAST chunk of the slab to its left).  Instead the
+// WIDE_H cells next to each interface are exchanged ONCE per call (halo.cu: fv_exchange_wide, peer stores + flags) and the
+// pipeline runs on an operator over the slab extended by those cells (same global grid indices, hence the same widths and
+// the same arithmetic per cell).  The extension's outer end has no valid neighbour data: what is computed there is wrong
+// from the first stage on, and the error moves inwards k cells per stage -- after G stages it has covered k*G <= WIDE_H
+// cells, i.e. it stops short of the slab's own cells, which therefore equal the single-domain result bit for bit.
+static int pipeline_operator(Ode *o, int64_t G, Fv **P, double **B, int64_t *HL, int64_t *HR) {
+   Fv *fv = o->fv;
+   *P = nullptr;
+   *HL = *HR = 0;
+   if (fv->d.nranks <= 1) {
+      *P = fv;
+      for (int i = 0; i < 3; ++i) B[i] = fv->cell0(o->bufs[i]);
+      return HRWENO_OK;
+   }
+   constexpr int64_t H = Halo::WIDE_H;
+   if (fv->d.grid_kind != HRWENO_GRID_LINEAR || !fv->halo.ready || !fv->halo.wide_off) return HRWENO_OK;
+   if ((int64_t)fv->d.k * G > H || fv->n0 < 4 * H) return HRWENO_OK;
+   const int64_t hl = fv->d.rank > 0 ? H : 0, hr = fv->d.rank < fv->d.nranks - 1 ? H : 0;
+   if (!o->fv_ext) {
+      hrweno_fv_desc d = fv->d; // same rank / nranks / global grid: physical-boundary flags and widths follow the global indices
+      d.n[0] = fv->n0 + hl + hr;
+      d.global_offset = fv->d.global_offset - hl;
+      if (d.n[0] > 2000000000LL) return HRWENO_OK;
+      HRW_TRY(fv_create(&o->fv_ext, &d));
+      for (int i = 0; i < 3; ++i) {
+         double *p = nullptr;
+         HRW_TRY(o->fv_ext->alloc_state(&p));
+         o->ext_bufs.push_back(p);
+      }
+      HRW_CUDA(cudaEventCreateWithFlags(&o->ev_edge, cudaEventDisableTiming));
+   }
+   *P = o->fv_ext;
+   for (int i = 0; i < 3; ++i) B[i] = o->fv_ext->cell0(o->ext_bufs[i]);
+   *HL = hl;
+   *HR = hr;
+   return HRWENO_OK;
+}
+
 static int rk_integrate_pipelined(Ode *o, double *u, double *t, double tout, double dt, int itask, bool *done) {
    *done = false;
    Fv *fv = o->fv;
-   if (!o->fused || o->is_ms || fv->general || fv->d.ndim != 1 || fv->rows != 1 || fv->d.nranks > 1) return HRWENO_OK;
-   int tile = 0, tpr = 0;
-   fv_tiling_1d(fv, &tile, &tpr);
+   if (!o->fused || o->is_ms || fv->general || fv->d.ndim != 1 || fv->rows != 1) return HRWENO_OK;
    int chunk_tiles = 148 * 48; // a multiple of every resident-CTA count in use (148 x 1,2,3,4,6,8): no ragged last wave;
                                // 7.2 M cells per chunk measured best on B200 (profiles/r1_variant_sweeps.txt)
    if (const char *e = std::getenv("HRWENO_PIPE_CHUNK_TILES")) chunk_tiles = std::atoi(e);
    if (chunk_tiles < 1) return HRWENO_OK; // pipeline disabled
-   // chunk c covers tiles [cb[c], cb[c+1])  (smaller first chunks to shorten the ramp were tried: no measurable gain)
-   std::vector<int> cb(1, 0);
-   while (cb.back() < tpr) cb.push_back(std::min(tpr, cb.back() + chunk_tiles));
-   const int C = (int)cb.size() - 1;
-   if (C < 4) return HRWENO_OK;
    // number of steps this call takes (tvdode.f90:161-171: step, then test)
    int64_t nsteps = 0;
    double tt = *t;
@@ -402,11 +488,32 @@ static int rk_integrate_pipelined(Ode *o, double *u, double *t, double tout, dou
       tt = tt + dt;
       ++nsteps;
       if (is_done(tt, tout, dt) || itask == 2) break;
+      if (nsteps > 4000000) return HRWENO_OK;
    }
    const int order = o->order;
    const int64_t G = (int64_t)order * nsteps;
+   // the operator the pipeline runs on: this one (single GPU) or the slab extended by the wide halos
+   Fv *P = nullptr;
+   double *B[3] = {nullptr, nullptr, nullptr}; // U, T1, T2 at cell 0 of P
+   int64_t HL = 0, HR = 0;
+   {
+      int tile0 = 0, tpr0 = 0;
+      fv_tiling_1d(fv, &tile0, &tpr0);
+      if ((tpr0 + chunk_tiles - 1) / chunk_tiles < 4) return HRWENO_OK; // fewer than four chunks: nothing to overlap
+   }
+   HRW_TRY(pipeline_operator(o, G, &P, B, &HL, &HR));
+   if (!P) return HRWENO_OK;
+   int tile = 0, tpr = 0;
+   fv_tiling_1d(P, &tile, &tpr);
+   // chunk c covers tiles [cb[c], cb[c+1])  (smaller first chunks to shorten the ramp were tried: no measurable gain)
+   std::vector<int> cb(1, 0);
+   while (cb.back() < tpr) cb.push_back(std::min(tpr, cb.back() + chunk_tiles));
+   const int C = (int)cb.size() - 1;
+   if (C < 4) return HRWENO_OK;
    if (G + C > 2000000) return HRWENO_OK;
-   const int64_t n = fv->n0;
+   const int64_t n = fv->n0;      // this slab's cells: u[0..n) <-> cells [HL, HL+n) of P
+   const int64_t np = P->n0;      // = HL + n + HR
+   const int64_t launches0 = P->launches;
    if (!o->s_in) HRW_CUDA(cudaStreamCreateWithFlags(&o->s_in, cudaStreamNonBlocking));
    if (!o->s_out) HRW_CUDA(cudaStreamCreateWithFlags(&o->s_out, cudaStreamNonBlocking));
    while ((int)o->ev_in.size() < C) {
@@ -416,14 +523,23 @@ static int rk_integrate_pipelined(Ode *o, double *u, double *t, double tout, dou
       HRW_CUDA(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
       o->ev_fin.push_back(e);
    }
-   double *B[3] = {fv->cell0(o->bufs[0]), fv->cell0(o->bufs[1]), fv->cell0(o->bufs[2])}; // U, T1, T2 at cell 0
    const int k = fv->d.k;
    auto c_lo = [&](int c) { return (int64_t)cb[c] * tile; };
-   auto c_hi = [&](int c) { return std::min<int64_t>(n, (int64_t)cb[c + 1] * tile); };
+   auto c_hi = [&](int c) { return std::min<int64_t>(np, (int64_t)cb[c + 1] * tile); };
    cudaStream_t cs = o->stream;
+   if (P != fv) {
+      // the cells next to the slab interfaces first, then the wide exchange with the neighbours on the compute stream
+      constexpr int64_t H = Halo::WIDE_H;
+      HRW_CUDA(cudaMemcpyAsync(B[0] + HL, u, (size_t)H * sizeof(double), cudaMemcpyHostToDevice, o->s_in));
+      HRW_CUDA(cudaMemcpyAsync(B[0] + HL + n - H, u + n - H, (size_t)H * sizeof(double), cudaMemcpyHostToDevice, o->s_in));
+      HRW_CUDA(cudaEventRecord(o->ev_edge, o->s_in));
+      HRW_CUDA(cudaStreamWaitEvent(cs, o->ev_edge, 0));
+      HRW_TRY(fv_exchange_wide(fv, B[0] + HL, n, cs));
+   }
    // host -> device, chunk by chunk, straight into the padded state (one row: dense offset == padded offset)
    for (int c = 0; c < C; ++c) {
-      HRW_CUDA(cudaMemcpyAsync(B[0] + c_lo(c), u + c_lo(c), (size_t)(c_hi(c) - c_lo(c)) * sizeof(double), cudaMemcpyHostToDevice, o->s_in));
+      const int64_t lo = std::max<int64_t>(c_lo(c), HL), hi = std::min<int64_t>(c_hi(c), HL + n);
+      if (hi > lo) HRW_CUDA(cudaMemcpyAsync(B[0] + lo, u + (lo - HL), (size_t)(hi - lo) * sizeof(double), cudaMemcpyHostToDevice, o->s_in));
       HRW_CUDA(cudaEventRecord(o->ev_in[c], o->s_in));
    }
    // Time-skewed chunks: stage g of chunk c covers tiles [L(c,g), L(c+1,g)) with L(c,g) = cb[c] - (g+1) for the inner
@@ -440,16 +556,17 @@ static int rk_integrate_pipelined(Ode *o, double *u, double *t, double tout, dou
       return (int)(v < 0 ? 0 : v);
    };
    const int fin_buf = order == 1 ? (int)(nsteps & 1) : 0; // RK1 ping-pongs U <-> T1
+   const int phys_l = P->d.rank == 0, phys_r = P->d.rank == P->d.nranks - 1;
    for (int c = 0; c < C; ++c) {
       HRW_CUDA(cudaStreamWaitEvent(cs, o->ev_in[c], 0));
-      if (c == 0) fill_ghost_kernel<<<1, 32, 0, cs>>>(B[0], n, k, 1, 0);
-      if (c == C - 1) fill_ghost_kernel<<<1, 32, 0, cs>>>(B[0], n, k, 0, 1);
-      if (c == 0 || c == C - 1) fv->launches++;
+      if (c == 0 && phys_l) fill_ghost_kernel<<<1, 32, 0, cs>>>(B[0], np, k, 1, 0);
+      if (c == C - 1 && phys_r) fill_ghost_kernel<<<1, 32, 0, cs>>>(B[0], np, k, 0, 1);
+      if ((c == 0 && phys_l) || (c == C - 1 && phys_r)) P->launches++;
       for (int64_t g = 0; g < G; ++g) {
          const int64_t step = g / order;
          const int j = (int)(g - step * order);
          StageArgs a{};
-         a.ld_out = fv->pitch;
+         a.ld_out = P->pitch;
          a.tile_begin = Lb(c, g);
          a.tile_end = Lb(c + 1, g);
          if (a.tile_end <= a.tile_begin) continue; // the skew has moved this chunk's range out of the domain
@@ -483,19 +600,26 @@ static int rk_integrate_pipelined(Ode *o, double *u, double *t, double tout, dou
             a.out = B[0];
             a.c0 = 2 * dt;
          }
-         HRW_TRY(fv_stage(fv, combine, a, cs));
+         HRW_TRY(fv_stage(P, combine, a, cs));
       }
-      // the cells chunk c finished with its last stage: device -> host on the output stream
-      const int64_t f_lo = (int64_t)Lb(c, G - 1) * tile, f_hi = std::min<int64_t>(n, (int64_t)Lb(c + 1, G - 1) * tile);
+      // the cells chunk c finished with its last stage: device -> host on the output stream (this slab's own cells only)
+      const int64_t f_lo = std::max<int64_t>((int64_t)Lb(c, G - 1) * tile, HL);
+      const int64_t f_hi = std::min<int64_t>(std::min<int64_t>(np, (int64_t)Lb(c + 1, G - 1) * tile), HL + n);
       if (f_hi > f_lo) {
          HRW_CUDA(cudaEventRecord(o->ev_fin[c], cs));
          HRW_CUDA(cudaStreamWaitEvent(o->s_out, o->ev_fin[c], 0));
-         HRW_CUDA(cudaMemcpyAsync(u + f_lo, B[fin_buf] + f_lo, (size_t)(f_hi - f_lo) * sizeof(double), cudaMemcpyDeviceToHost, o->s_out));
+         HRW_CUDA(cudaMemcpyAsync(u + (f_lo - HL), B[fin_buf] + f_lo, (size_t)(f_hi - f_lo) * sizeof(double), cudaMemcpyDeviceToHost, o->s_out));
       }
    }
    HRW_CUDA(cudaStreamSynchronize(o->s_out));
    HRW_CUDA(cudaStreamSynchronize(cs));
-   if (order == 1 && (nsteps & 1)) std::swap(o->bufs[0], o->bufs[1]);
+   if (P != fv) {
+      fv->launches += P->launches - launches0;
+      HRW_TRY(fv_halo_status(fv));
+      if (order == 1 && (nsteps & 1)) std::swap(o->ext_bufs[0], o->ext_bufs[1]);
+   } else if (order == 1 && (nsteps & 1)) {
+      std::swap(o->bufs[0], o->bufs[1]);
+   }
    *t = tt;
    o->fevals += (int64_t)order * nsteps;
    if (o->istate == 1) o->istate = 2;

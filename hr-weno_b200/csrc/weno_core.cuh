@@ -284,18 +284,97 @@ __device__ __forceinline__ void weno_run_k2_fast(const double *w, const WenoK &k
    }
 }
 
-template <int K, int R, class M>
-__device__ __forceinline__ void weno_run(const double *w, const WenoK &kc, double *vl, double *vr) {
-   if constexpr (K == 1)
-      weno_run_k1<R, M>(w, kc, vl, vr);
-   else if constexpr (K == 2 && !M::strict)
-      weno_run_k2_fast<R>(w, kc, vl, vr);
-   else if constexpr (K == 2)
-      weno_run_k2<R, M>(w, kc, vl, vr);
-   else if constexpr (!M::strict)
-      weno_run_k3_fast<R>(w, kc, vl, vr);
+// cold path of the magnitude guard below: the same fast formulas on the window scaled to magnitude ~1.  Not inlined and
+// called with scalars only (window in, results out through shared... no: through registers by value in small structs), so
+// the hot path keeps its registers.
+template <int N>
+struct WinPack {
+   double v[N];
+};
+template <int R>
+struct ResPack {
+   double vl[R], vr[R];
+};
+template <int K, int R>
+static __device__ __noinline__ ResPack<R> weno_run_fast_scaled_impl(WinPack<R + 2 * (K - 1)> win, double eps, int hi_max) {
+   constexpr int N = R + 2 * (K - 1);
+   // s = 2^-(exponent of the largest |v|): exact scaling
+   const int e = ((hi_max >> 20) & 0x7ff) - 1023;
+   const double sdn = __hiloint2double((1023 - e) << 20, 0), sup = __hiloint2double((1023 + e) << 20, 0);
+   WenoK kc = make_wenok(fmax(eps * sdn * sdn, 0x1p-200));
+   double w[N];
+#pragma unroll
+   for (int j = 0; j < N; ++j) w[j] = win.v[j] * sdn;
+   ResPack<R> r;
+   if constexpr (K == 2)
+      weno_run_k2_fast<R>(w, kc, r.vl, r.vr);
    else
-      weno_run_k3<R, M>(w, kc, vl, vr);
+      weno_run_k3_fast<R>(w, kc, r.vl, r.vr);
+#pragma unroll
+   for (int j = 0; j < R; ++j) {
+      r.vl[j] *= sup;
+      r.vr[j] *= sup;
+   }
+   return r;
+}
+template <int K, int R>
+__device__ __forceinline__ void weno_run_fast_scaled(const double *w, const WenoK &kc, float mhi, double *vl, double *vr) {
+   constexpr int N = R + 2 * (K - 1);
+   WinPack<N> win;
+#pragma unroll
+   for (int j = 0; j < N; ++j) win.v[j] = w[j];
+   const ResPack<R> r = weno_run_fast_scaled_impl<K, R>(win, kc.eps, __float_as_int(mhi));
+#pragma unroll
+   for (int j = 0; j < R; ++j) {
+      vl[j] = r.vl[j];
+      vr[j] = r.vr[j];
+   }
+}
+
+// ---- magnitude guard of the fast formulas ---------------------------------------------------------------------------
+// The division-light weights multiply smoothness terms: P = ((eps'+beta'_a)(eps'+beta'_b))^2 grows like v^8 and X = P*D3 like
+// v^9, where the reference only forms (eps+beta)^2 ~ v^4.  With |v| < 2^100 every intermediate stays below 2^930 (e <= 85 v^2,
+// P <= 5.2e7 v^8, X <= 4.2e8 v^9, the sums <= 1.6e9 v^8), far from overflow and from the flush-to-zero range of the
+// reciprocal seed.  A run whose window holds a larger value is reconstructed from the window scaled by a power of two
+// (exact; the scheme is homogeneous: vl, vr(s*v; s^2*eps) = s*vl, vr(v; eps)) in a second pass through the same code, so
+// fast mode stays finite wherever the reference does (the reference overflows from |v| ~ 1e77 on).  At those magnitudes
+// eps is far below the resolution of any non-zero smoothness indicator (>= ulp(2^100)^2 = 2^96), so the scaled eps is only
+// kept away from underflow (>= 2^-200): with all indicators exactly zero any positive eps gives the linear weights.
+// The test compares the high words of the doubles as floats (monotone in |v|; fp32 min/max, off the fp64 pipe): the float
+// patterns of finite doubles below 2^1017 are ordinary floats, beyond that the reference is not finite either.
+template <int N>
+__device__ __forceinline__ float fast_window_maxhi(const double *w) {
+   float m = 0.0f;
+#pragma unroll
+   for (int j = 0; j < N; ++j) m = fmaxf(m, fabsf(__int_as_float(__double2hiint(w[j]))));
+   return m;
+}
+constexpr int FAST_RANGE_HI = 0x46300000; // high word of 2^100 = (1023 + 100) << 20
+
+template <int K, int R, class M>
+__device__ __forceinline__ void weno_run(const double *w_in, const WenoK &kc, double *vl, double *vr) {
+   if constexpr (K == 1) {
+      weno_run_k1<R, M>(w_in, kc, vl, vr);
+   } else if constexpr (!M::strict) {
+      constexpr int N = R + 2 * (K - 1);
+      const float mhi = fast_window_maxhi<N>(w_in);
+#ifdef HRW_NO_FAST_GUARD // tuning A/B only
+      if (true) {
+#else
+      if (mhi < __int_as_float(FAST_RANGE_HI)) { // always, for data of ordinary magnitude
+#endif
+         if constexpr (K == 2)
+            weno_run_k2_fast<R>(w_in, kc, vl, vr);
+         else
+            weno_run_k3_fast<R>(w_in, kc, vl, vr);
+      } else {
+         weno_run_fast_scaled<K, R>(w_in, kc, mhi, vl, vr);
+      }
+   } else if constexpr (K == 2) {
+      weno_run_k2<R, M>(w_in, kc, vl, vr);
+   } else {
+      weno_run_k3<R, M>(w_in, kc, vl, vr);
+   }
 }
 
 // ------------------------------------------------------------------------------------------------

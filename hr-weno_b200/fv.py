@@ -106,6 +106,12 @@ class FV:
             )
         )
 
+    def set_flux_time_fn(self, g):
+        """t-dependent flux f = ((model(v)*cross)*face)*g(t) (fluxes.f90:12-18): `g(t) -> float` is called on the host once
+        per right-hand-side evaluation with that evaluation's time (tvdode.f90:162-166,256); None removes the factor"""
+        self._tfn = _abi.TIME_FN(lambda _ctx, t: float(g(t))) if g is not None else C.cast(None, _abi.TIME_FN)
+        _abi.check(_abi.lib().hrweno_fv_set_flux_time_fn(self._h, self._tfn, None))
+
     def export_halo(self):
         buf = C.create_string_buffer(_abi.IPC_HANDLE_BYTES)
         _abi.check(_abi.lib().hrweno_fv_export_halo(self._h, buf))

@@ -63,6 +63,19 @@ class _tvdode:
         return tt.value
 
 
+    # device callers that keep the state inside the integrator between output times (fused integrators)
+    def attach(self, u_ptr, stream=None):
+        _abi.check(_abi.lib().hrweno_ode_attach(self._h, u_ptr, stream))
+
+    def integrate_attached(self, t, tout, dt, itask=1, stream=None):
+        tt = C.c_double(t)
+        _abi.check(_abi.lib().hrweno_ode_integrate_attached(self._h, C.byref(tt), tout, dt, itask, stream))
+        return tt.value
+
+    def fetch(self, u_ptr, stream=None):
+        _abi.check(_abi.lib().hrweno_ode_fetch(self._h, u_ptr, stream))
+
+
 def _wrap_rhs(fu):
     def cb(_ctx, t, neq, u_ptr, udot_ptr, stream):
         fu(t, neq, u_ptr, udot_ptr, stream)

@@ -171,6 +171,15 @@ int hrweno_fv_set_xedges(hrweno_fv *fv, int axis, const double *xedges);
  * along the other axis (ndim == 2 only).  `flux1 = v*x(1)**2`: face_coef = edges1**2; `flux2 = v*x(1)*x(2)`:
  * cross_coef = center1, face_coef = edges2.  Same calling rules as hrweno_fv_set_xedges. */
 int hrweno_fv_set_flux_coef(hrweno_fv *fv, int axis, const double *face_coef, const double *cross_coef);
+/* t-dependent fluxes in the fused path.  The reference's flux receives the time of the evaluation (`f(u, x(:), t)`,
+ * fluxes.f90:12-18; the integrators call the rhs at t, t+dt and t+dt/2, tvdode.f90:162-166, and at t, :256).  Closed-set
+ * form: a separable time factor,
+ *     f(v, x, t) = ((model(v) * cross_coef[c]) * face_coef[f]) * g(t)
+ * with g a HOST function evaluated once per right-hand-side evaluation at that evaluation's time and handed to the stage
+ * kernel as a scalar, so the stage stays one fused launch (no PCIe round trip per stage, unlike the host-integrand
+ * constructors).  g == NULL removes the factor.  Same calling rules as hrweno_fv_set_xedges (general stage kernel). */
+typedef double (*hrweno_time_fn)(void *ctx, double t);
+int hrweno_fv_set_flux_time_fn(hrweno_fv *fv, hrweno_time_fn g, void *ctx);
 
 /* multi-GPU plumbing: each rank exports a 64-byte CUDA IPC handle of its halo mailbox and
  * imports the handles of its left/right neighbours (NULL at a physical boundary). */
@@ -186,6 +195,38 @@ int hrweno_fv_export_halo(hrweno_fv *fv, void *handle_out);
 int hrweno_fv_import_halo(hrweno_fv *fv, const void *left_handle, const void *right_handle);
 /* synchronises the device and reports HRWENO_ECOMM if a halo wait timed out (a neighbour rank died) */
 int hrweno_fv_halo_status(hrweno_fv *fv);
+
+/* ---- one process, N GPUs (SURVEY 8b "ngpus", 8e) ---------------------------------------------------------------
+ * The reference is a single-process program; these entry points let a Fortran / C++ host keep that shape and still use
+ * every GPU of the box.  `desc` describes the GLOBAL problem (rank / nranks / global_* are ignored): the slowest axis
+ * (x for ndim == 1 with rows == 1, x2 for ndim == 2) is cut into `ngpus` contiguous slabs, independent rows
+ * (ndim == 1, rows > 1) are dealt out without halos.  The library opens the devices (`devices` == NULL: 0..ngpus-1;
+ * ngpus <= 0: all visible), enables peer access, wires the halo mailboxes of neighbouring slabs and runs one host
+ * thread + one stream per device inside each call; the k halo cells (rows) per stage travel as peer stores over
+ * NVLink from inside the stage kernels.  Results are bit-identical to the single-GPU run of the same mode.
+ * The integrators keep the semantics of rktvd%integrate / mstvd%integrate (tvdode.f90:97-178, 203-271); u is the
+ * caller's global vector in the reference's storage order (example2:50). */
+typedef struct hrweno_mgpu hrweno_mgpu;
+int hrweno_mgpu_create(hrweno_mgpu **out, const hrweno_fv_desc *desc, int ngpus, const int *devices);
+void hrweno_mgpu_destroy(hrweno_mgpu *m);
+int hrweno_mgpu_ngpus(const hrweno_mgpu *m);
+/* slab `rank`: its device, and offset / count of its unknowns inside the global vector */
+int hrweno_mgpu_slab(const hrweno_mgpu *m, int rank, int *device, int64_t *offset, int64_t *count);
+int hrweno_mgpu_rktvd(hrweno_mgpu *m, int order); /* rktvd(fu, neq, order) with the fused rhs, tvdode.f90:69-95 */
+int hrweno_mgpu_mstvd(hrweno_mgpu *m);            /* mstvd(fu, neq), tvdode.f90:180-201 */
+/* integrate with the global HOST vector u (copied to the slabs and back inside the call) */
+int hrweno_mgpu_integrate(hrweno_mgpu *m, double *u, double *t, double tout, double dt, int itask);
+/* device-resident state between calls: upload once, integrate any number of times, download when output is due */
+int hrweno_mgpu_upload(hrweno_mgpu *m, const double *u);
+int hrweno_mgpu_integrate_resident(hrweno_mgpu *m, double *t, double tout, double dt, int itask);
+int hrweno_mgpu_download(hrweno_mgpu *m, double *u);
+/* Extension (north star: "CFL / max-wavespeed reduction"): alpha = max |f'(u)| over ALL slabs of the resident state,
+ * reduced on the GPUs (per-slab kernels, then one kernel on the first device reading its peers' partial maxima over
+ * NVLink).  install != 0 also makes it the Lax-Friedrichs alpha of every slab from the next stage on. */
+int hrweno_mgpu_max_wavespeed(hrweno_mgpu *m, double *alpha_out, int install);
+int hrweno_mgpu_set_alpha(hrweno_mgpu *m, double alpha);
+int64_t hrweno_mgpu_fevals(const hrweno_mgpu *m);
+int64_t hrweno_mgpu_launches(const hrweno_mgpu *m);
 
 /* ---- TVD time integrators (src/hrweno_tvdode.f90) -------------------------- */
 
@@ -218,6 +259,14 @@ int hrweno_ode_integrate(hrweno_ode *ode, double *u, double *t, double tout, dou
 /* device-resident u; asynchronous w.r.t. the host except for the scalar bookkeeping */
 int hrweno_ode_integrate_dev(hrweno_ode *ode, double *u_dev, double *t, double tout, double dt, int itask,
                              void *stream);
+/* Device callers that keep the state inside the integrator between output times (fused integrators only).  The
+ * reference's `u` is inout on every call (tvdode.f90:97,203); a caller that does not touch u between calls can hand it over
+ * once: attach copies the dense device vector into the library's padded state, integrate_attached advances that state
+ * with the semantics of integrate (no dense <-> padded copies, which are 2 x 16 B per cell and call), fetch writes the
+ * current state to a dense device vector.  A later hrweno_ode_integrate[_dev] with an explicit u replaces the state. */
+int hrweno_ode_attach(hrweno_ode *ode, const double *u_dev, void *stream);
+int hrweno_ode_integrate_attached(hrweno_ode *ode, double *t, double tout, double dt, int itask, void *stream);
+int hrweno_ode_fetch(hrweno_ode *ode, double *u_dev, void *stream);
 /* public fields of type(tvdode) (tvdode.f90:18-29) */
 int64_t hrweno_ode_fevals(const hrweno_ode *ode); /* keeps the reference's count, incl. mstvd's 12 for the start-up */
 int hrweno_ode_istate(const hrweno_ode *ode);

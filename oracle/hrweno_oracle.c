@@ -253,17 +253,18 @@ double hrweno_ref_face_flux(int scheme, int model, double coef, double alpha, do
 /* x-dependent physical flux of the commented-out growth terms of example2:140,153 (`flux1 = v*x(1)**2`,
  * `flux2 = v*x(1)*x(2)`): f = (model(v)*cross)*face, left to right like the Fortran expression; a factor that is
  * absent is not multiplied in. */
-static inline double flux_model_x(int model, double coef, double v, const double *cross, const double *face) {
+static inline double flux_model_x(int model, double coef, double v, const double *cross, const double *face, const double *tfac) {
    double f = hrweno_ref_flux_model(model, coef, v);
    if (cross) f = f * *cross;
    if (face) f = f * *face;
+   if (tfac) f = f * *tfac; /* separable time factor g(t): f(u, x, t), fluxes.f90:12-18 */
    return f;
 }
 
 static inline double face_flux_x(int scheme, int model, double coef, double alpha, double vm, double vp,
-                                 const double *cross, const double *face) {
-   const double fm = flux_model_x(model, coef, vm, cross, face);
-   const double fp = flux_model_x(model, coef, vp, cross, face);
+                                 const double *cross, const double *face, const double *tfac) {
+   const double fm = flux_model_x(model, coef, vm, cross, face, tfac);
+   const double fp = flux_model_x(model, coef, vp, cross, face, tfac);
    if (scheme == HRWENO_SCHEME_LAX_FRIEDRICHS) return (fm + fp - alpha * (vp - vm)) / 2; /* fluxes.f90:43 */
    if (vm <= vp) return fm < fp ? fm : fp;                                              /* fluxes.f90:70-74 */
    return fm > fp ? fm : fp;
@@ -295,6 +296,9 @@ struct hrweno_ref_fv {
    double *cnu[2];   /* per-axis cnu(0:k-1,-1:k-1,1:n) of weno(ncells,k,eps,xedges) (weno.f90:100-112), or NULL */
    double *fcoef[2]; /* per-axis face coefficient, index 0..n like edges(0:n), or NULL */
    double *ccoef[2]; /* per-axis cross coefficient, index = cell along the other axis, or NULL */
+   hrweno_time_fn tfn; /* time factor g(t) of the flux or NULL */
+   void *tfn_ctx;
+   double tfac;        /* g(t) of the evaluation in progress */
 };
 
 int hrweno_ref_fv_create(hrweno_ref_fv **out, const hrweno_fv_desc *desc) {
@@ -359,15 +363,23 @@ int hrweno_ref_fv_set_flux_coef(hrweno_ref_fv *fv, int axis, const double *face,
    return HRWENO_OK;
 }
 
+/* f(v, x, t) = ((model(v)*cross)*face)*g(t): g is called once per rhs evaluation with that evaluation's time */
+int hrweno_ref_fv_set_flux_time_fn(hrweno_ref_fv *fv, hrweno_time_fn g, void *ctx) {
+   if (!fv) return HRWENO_EINVAL;
+   fv->tfn = g;
+   fv->tfn_ctx = ctx;
+   return HRWENO_OK;
+}
+
 int64_t hrweno_ref_fv_neq(const hrweno_ref_fv *fv) { return fv->neq; }
 
 /* faces 1..nc-1 then the boundary rule; fe[0..nc] */
 static void faces_row(const hrweno_fv_desc *d, int axis, int64_t nc, const double *vl, const double *vr,
-                      double *fe, int par, const double *fcoef, const double *cross) {
+                      double *fe, int par, const double *fcoef, const double *cross, const double *tfac) {
    const double coef = d->flux_coef[axis];
-   if (fcoef || cross) { /* x-dependent flux: x = [right(i), center_other] (example2:100-101,109-110) */
+   if (fcoef || cross || tfac) { /* x/t-dependent flux: x = [right(i), center_other] (example2:100-101,109-110) */
       for (int64_t i = 1; i <= nc - 1; ++i)
-         fe[i] = face_flux_x(d->flux_scheme, d->flux_model, coef, d->alpha, vr[i - 1], vl[i], cross, fcoef ? fcoef + i : NULL);
+         fe[i] = face_flux_x(d->flux_scheme, d->flux_model, coef, d->alpha, vr[i - 1], vl[i], cross, fcoef ? fcoef + i : NULL, tfac);
    } else if (par) {
 #pragma omp parallel for schedule(static)
       for (int64_t i = 1; i <= nc - 1; ++i) /* example1:97-100 ; example2:99-102,108-111 */
@@ -406,7 +418,7 @@ static int rhs_1d(hrweno_ref_fv *fv, const double *v, double *vdot) {
             const double *vrow = v + row * nc;
             double *orow = vdot + row * nc;
             recon_row(d->k, nc, d->eps, fv->cnu[0], vrow, 1, vl, vr, vext, par_cells); /* example1:93 */
-            faces_row(d, 0, nc, vl, vr, fe, par_cells, fv->fcoef[0], NULL);
+            faces_row(d, 0, nc, vl, vr, fe, par_cells, fv->fcoef[0], NULL, fv->tfn ? &fv->tfac : NULL);
             const double *w = fv->w[0];
             if (par_cells) {
 #pragma omp parallel for schedule(static)
@@ -449,12 +461,12 @@ static int rhs_2d(hrweno_ref_fv *fv, const double *v, double *vdot) {
 #pragma omp for schedule(static) nowait
          for (int64_t j = 0; j < n2; ++j) { /* example2:97-103: contiguous rows */
             recon_row(d->k, n1, d->eps, fv->cnu[0], v + j * n1, 1, vl, vr, vext, 0);
-            faces_row(d, 0, n1, vl, vr, f1 + j * (n1 + 1), 0, fv->fcoef[0], fv->ccoef[0] ? fv->ccoef[0] + j : NULL);
+            faces_row(d, 0, n1, vl, vr, f1 + j * (n1 + 1), 0, fv->fcoef[0], fv->ccoef[0] ? fv->ccoef[0] + j : NULL, fv->tfn ? &fv->tfac : NULL);
          }
 #pragma omp for schedule(static)
          for (int64_t i = 0; i < n1; ++i) { /* example2:106-112: stride-nc1 columns */
             recon_row(d->k, n2, d->eps, fv->cnu[1], v + i, n1, vl, vr, vext, 0);
-            faces_row(d, 1, n2, vl, vr, f2 + i * (n2 + 1), 0, fv->fcoef[1], fv->ccoef[1] ? fv->ccoef[1] + i : NULL);
+            faces_row(d, 1, n2, vl, vr, f2 + i * (n2 + 1), 0, fv->fcoef[1], fv->ccoef[1] ? fv->ccoef[1] + i : NULL, fv->tfn ? &fv->tfac : NULL);
          }
          const double *w1 = fv->w[0], *w2 = fv->w[1];
 #pragma omp for schedule(static)
@@ -473,8 +485,8 @@ static int rhs_2d(hrweno_ref_fv *fv, const double *v, double *vdot) {
 }
 
 int hrweno_ref_fv_rhs(hrweno_ref_fv *fv, double t, const double *v, double *vdot) {
-   (void)t; /* the closed-set flux models do not depend on t; x enters through the coefficient arrays only */
    if (!fv || !v || !vdot) return HRWENO_EINVAL;
+   if (fv->tfn) fv->tfac = fv->tfn(fv->tfn_ctx, t); /* t enters through the separable factor g(t) only; x through the coefficient arrays */
    return fv->d.ndim == 1 ? rhs_1d(fv, v, vdot) : rhs_2d(fv, v, vdot);
 }
 

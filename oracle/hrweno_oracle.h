@@ -71,6 +71,7 @@ int64_t hrweno_ref_fv_neq(const hrweno_ref_fv *fv);
 int hrweno_ref_fv_set_xedges(hrweno_ref_fv *fv, int axis, const double *xedges);
 /* x-dependent flux f = (model(v)*cross[i_other])*face[i_face] (the growth terms hinted at example2:140,153) */
 int hrweno_ref_fv_set_flux_coef(hrweno_ref_fv *fv, int axis, const double *face, const double *cross);
+int hrweno_ref_fv_set_flux_time_fn(hrweno_ref_fv *fv, hrweno_time_fn g, void *ctx);
 int hrweno_ref_fv_rhs(hrweno_ref_fv *fv, double t, const double *v, double *vdot);
 
 /* tvdode.f90:69-95, 97-178, 180-201, 203-271, 273-284 */

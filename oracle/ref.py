@@ -54,6 +54,7 @@ def lib():
         "hrweno_ref_fv_rhs": (i32, [vp, dbl, vp, vp]),
         "hrweno_ref_fv_set_xedges": (i32, [vp, i32, vp]),
         "hrweno_ref_fv_set_flux_coef": (i32, [vp, i32, vp, vp]),
+        "hrweno_ref_fv_set_flux_time_fn": (i32, [vp, _abi.TIME_FN, vp]),
         "hrweno_ref_rktvd_create": (i32, [C.POINTER(vp), REF_RHS_FN, vp, i64, i32]),
         "hrweno_ref_mstvd_create": (i32, [C.POINTER(vp), REF_RHS_FN, vp, i64]),
         "hrweno_ref_rktvd_create_fv": (i32, [C.POINTER(vp), vp, i32]),
@@ -180,6 +181,11 @@ class FV:
         assert c is None or c.size == self.desc.n[1 - axis]
         _ok(lib().hrweno_ref_fv_set_flux_coef(self._h, axis, None if f is None else f.ctypes.data,
                                              None if c is None else c.ctypes.data))
+
+
+    def set_flux_time_fn(self, g):
+        self._tfn = _abi.TIME_FN(lambda _ctx, t: float(g(t))) if g is not None else C.cast(None, _abi.TIME_FN)
+        _ok(lib().hrweno_ref_fv_set_flux_time_fn(self._h, self._tfn, None))
 
 
 class _ode:

@@ -19,7 +19,7 @@ def pytest_configure(config):
 def _built():
     need = [os.path.join(ROOT, "hr-weno_b200", "lib", "libhrweno_b200.so"), os.path.join(ROOT, "oracle", "libhrweno_oracle.so")]
     need += [os.path.join(ROOT, "examples", e) for e in
-             ("example1_burgers_1d_fv", "example2_pbe_2d_fv", "example3_pbe_2d_growth", "grid_dump")]
+             ("example1_burgers_1d_fv", "example2_pbe_2d_fv", "example3_pbe_2d_growth", "example4_multi_gpu", "grid_dump")]
     return all(os.path.exists(p) for p in need)
 
 
