@@ -373,8 +373,16 @@ __global__ void __launch_bounds__(NT, HRW_MINB) fv1d_stage_kernel(const Fv1dGeom
    asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
    int tid = threadIdx.x;
    asm volatile("" : "+r"(tid)); // keep the thread index in a register: re-reading SR_TID.X inside the tile loop stalls
+   // Loop-invariant launch parameters the tile loop tests every iteration are pinned in registers: left to itself the
+   // compiler re-reads them from the parameter bank right in front of each use, and those LDCU round trips showed up as
+   // ~8 % of the stall samples (loop test, halo tests; profiles/r2b_k2_fast_source_hotspots.txt)
    const int n = (int)g.n;                     // cells per row (< 2^31, validated at creation)
    const int tpr = (int)g.tiles_per_row;
+   int tile_end = g.tile_end;
+   int nblk = (int)gridDim.x;
+   int lflags = (g.halo.seq_in != 0 ? 1 : 0) | (g.halo.seq_out != 0 ? 2 : 0) | (s.out_dense ? 4 : 0);
+   asm volatile("" : "+r"(tile_end), "+r"(nblk), "+r"(lflags));
+   const bool halo_in = lflags & 1, halo_out = lflags & 2, out_dense = lflags & 4;
 
    const uint32_t bar_u32 = smem_u32(&s_bar[0]), sv_u32 = smem_u32(&s_v[0][0]);
    const uint32_t sa_u32 = smem_u32(&s_a[0][0]), sw_u32 = smem_u32(&s_wi[0][0]);
@@ -424,7 +432,7 @@ __global__ void __launch_bounds__(NT, HRW_MINB) fv1d_stage_kernel(const Fv1dGeom
    __syncthreads();
 
    // tiles are walked as (row, tile-in-row) pairs advanced by gridDim.x without any division in the loop
-   const int step_rows = (int)(gridDim.x / (unsigned)tpr), step_cols = (int)(gridDim.x % (unsigned)tpr);
+   const int step_rows = (int)((unsigned)nblk / (unsigned)tpr), step_cols = (int)((unsigned)nblk % (unsigned)tpr);
    // everything above touched only shared memory and creation-time constants; from here on this grid reads and writes
    // state vectors produced by earlier kernels of the stream
    asm volatile("griddepcontrol.wait;" ::: "memory");
@@ -433,9 +441,9 @@ __global__ void __launch_bounds__(NT, HRW_MINB) fv1d_stage_kernel(const Fv1dGeom
    // slabs: the two edge tiles are walked first (logical tile 1 <-> last tile), so the boundary cells reach the
    // neighbour GPU while the bulk of the stage is still being computed
    auto remap = [&](int tc) { return (!g.halo.edge_first || tpr < 3) ? tc : (tc == 1 ? tpr - 1 : (tc == tpr - 1 ? 1 : tc)); };
-   if (tid == 0 && lin < g.tile_end) issue(row, remap(tcol), 0);
+   if (tid == 0 && lin < tile_end) issue(row, remap(tcol), 0);
 
-   for (int it = 0; lin < g.tile_end; ++it, lin += (int)gridDim.x) {
+   for (int it = 0; lin < tile_end; ++it, lin += nblk) {
       const int buf = it & 1;
       int nrow = row + step_rows, ntcol = tcol + step_cols;
       if (ntcol >= tpr) {
@@ -447,7 +455,7 @@ __global__ void __launch_bounds__(NT, HRW_MINB) fv1d_stage_kernel(const Fv1dGeom
       // arrives on the buffer's "consumed" barrier after its loads
       // The producer (thread 0) never blocks its warp early: it tests the "consumed" barrier here, again after the
       // reconstruction, and waits only at the end of the iteration.
-      bool pending = tid == 0 && lin + (int)gridDim.x < g.tile_end;
+      bool pending = tid == 0 && lin + nblk < tile_end;
       auto try_issue = [&](bool block) {
          if (!pending) return;
          if (WT && it > 0) {
@@ -466,7 +474,7 @@ __global__ void __launch_bounds__(NT, HRW_MINB) fv1d_stage_kernel(const Fv1dGeom
       const int i0 = ptc * TILE + (slot - 1) * R; // first owned cell (slot 0: the run left of the tile)
       // a caller's dense output array carries no alignment guarantee: scalar stores (edge path) for every thread
       const bool skip = (WT ? (lane == 0 || lane == 31) : (tid == 0 || tid == NT - 1)) || i0 >= n;
-      const bool edge = s.out_dense || (i0 + R >= n) || (i0 == 0);
+      const bool edge = out_dense || (i0 + R >= n) || (i0 == 0);
 
       // interior threads: start the global loads of the operands that are not staged with the tile now
       Prefetched<R> pf;
@@ -526,7 +534,7 @@ __global__ void __launch_bounds__(NT, HRW_MINB) fv1d_stage_kernel(const Fv1dGeom
 
       // slab interface: the ghost cells of an edge tile come from this GPU's mailbox (stored there by the neighbour's
       // previous stage); wait for the sequence number, then patch them into the staged tile
-      if (g.halo.seq_in) {
+      if (halo_in) {
          const bool rl = ptc == 0 && g.halo.recv_left, rr = ptc == tpr - 1 && g.halo.recv_right;
          if (rl || rr) { // CTA-uniform
             if (tid < 32) {
@@ -604,7 +612,7 @@ __global__ void __launch_bounds__(NT, HRW_MINB) fv1d_stage_kernel(const Fv1dGeom
       try_issue(true);
       // slab interface: the CTA that just wrote the first / last k cells of the slab stores them into the neighbour's
       // mailbox over NVLink and publishes the sequence number (release: fence, then flag)
-      if (g.halo.seq_out) {
+      if (halo_out) {
          const bool sl = ptc == 0 && g.halo.send_left, sr = ptc == tpr - 1 && g.halo.send_right;
          if (sl || sr) { // CTA-uniform
             __syncthreads(); // every store of this tile has been issued

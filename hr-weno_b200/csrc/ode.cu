@@ -388,7 +388,6 @@ int ode_attach(Ode *o, const double *u_dev, cudaStream_t st) {
       double *cur = o->is_ms ? o->bufs[o->ring % 5] : o->bufs[0];
       HRW_TRY(fv_pack(fv, u_dev, fv->cell0(cur), st));
       HRW_TRY(fv_exchange(fv, fv->cell0(cur), st));
-      fv->launches++;
    }
    o->attached = true;
    return HRWENO_OK;
@@ -403,7 +402,6 @@ int ode_fetch(Ode *o, double *u_dev, cudaStream_t st) {
    } else {
       double *cur = o->is_ms ? o->bufs[o->ring % 5] : o->bufs[0];
       HRW_TRY(fv_unpack(fv, fv->cell0(cur), u_dev, st));
-      fv->launches++;
    }
    return HRWENO_OK;
 }
