@@ -298,10 +298,11 @@ struct ResPack {
 template <int K, int R>
 static __device__ __noinline__ ResPack<R> weno_run_fast_scaled_impl(WinPack<R + 2 * (K - 1)> win, double eps, int hi_max) {
    constexpr int N = R + 2 * (K - 1);
-   // s = 2^-(exponent of the largest |v|): exact scaling
-   const int e = ((hi_max >> 20) & 0x7ff) - 1023;
+   // s = 2^(40 - exponent of the largest |v|): exact scaling to magnitude ~2^40 (>= 2^100 before), which keeps the products
+   // of the fast formulas below 2^400 and the scaled eps = eps*s^2 representable (not clamped) for |v| < ~1e45
+   const int e = ((hi_max >> 20) & 0x7ff) - 1023 - 40;
    const double sdn = __hiloint2double((1023 - e) << 20, 0), sup = __hiloint2double((1023 + e) << 20, 0);
-   WenoK kc = make_wenok(fmax(eps * sdn * sdn, 0x1p-200));
+   WenoK kc = make_wenok(fmax(eps * sdn * sdn, 0x1p-240));
    double w[N];
 #pragma unroll
    for (int j = 0; j < N; ++j) w[j] = win.v[j] * sdn;
@@ -338,8 +339,8 @@ __device__ __forceinline__ void weno_run_fast_scaled(const double *w, const Weno
 // reciprocal seed.  A run whose window holds a larger value is reconstructed from the window scaled by a power of two
 // (exact; the scheme is homogeneous: vl, vr(s*v; s^2*eps) = s*vl, vr(v; eps)) in a second pass through the same code, so
 // fast mode stays finite wherever the reference does (the reference overflows from |v| ~ 1e77 on).  At those magnitudes
-// eps is far below the resolution of any non-zero smoothness indicator (>= ulp(2^100)^2 = 2^96), so the scaled eps is only
-// kept away from underflow (>= 2^-200): with all indicators exactly zero any positive eps gives the linear weights.
+// the window is scaled to ~2^40 and eps by the square of the factor; the scaled eps is kept away from underflow
+// (>= 2^-240, which only binds for |v| > ~1e45 and only matters for cells whose differences are 2^-160 of that).
 // The test compares the high words of the doubles as floats (monotone in |v|; fp32 min/max, off the fp64 pipe): the float
 // patterns of finite doubles below 2^1017 are ordinary floats, beyond that the reference is not finite either.
 template <int N>

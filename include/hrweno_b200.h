@@ -72,7 +72,14 @@ enum hrweno_grid_kind {
 enum hrweno_mode {
    HRWENO_MODE_STRICT = 0, /* reference operation order, no FMA contraction: bit-identical to the oracle */
    HRWENO_MODE_FAST = 1    /* same formulas, division-light weights and FMA contraction; within the
-                              north-star tolerances (1e-12 normwise per output time, few ULP reconstruct) */
+                              north-star tolerances (1e-12 normwise per output time, few ULP reconstruct).
+                              Magnitude range: the division-light weights form products of smoothness terms
+                              that grow like v^9 where the reference forms v^4, so runs of cells are
+                              reconstructed directly while every |v| of their stencil window is < 2^100
+                              (1.3e30); windows holding larger values are rescaled by an exact power of two
+                              first (the scheme is homogeneous), so fast mode stays finite wherever the
+                              reference does (|v| up to ~1e77) at the same few-ULP accuracy.  eps must be
+                              > epsilon(1d0) as in the reference (weno.f90:92-96). */
 };
 
 /* ---- opaque handles ------------------------------------------------------- */

@@ -265,7 +265,9 @@ def reconstruct_fast(v, k=3, eps=1e-6):
     """Algebra check of the FAST-mode device formulas (hr-weno_b200/csrc/weno_core.cuh: weno_run_k3_fast,
     weno_run_k2_fast): the same scheme as `reconstruct` (weno.f90:174-216) rewritten in differences of the cell
     averages with division-light weights.  Separately rounded NumPy operations stand in for the device FMAs, so
-    this agrees with the kernel to rounding, not bit for bit; tests hold it to a few ULP of `reconstruct`."""
+    this agrees with the kernel to rounding, not bit for bit; tests hold it to a few ULP of `reconstruct`.
+    Magnitude guard as on the device (weno_core.cuh: weno_run): cells whose stencil holds a value >= 2^100 are
+    evaluated on the stencil scaled by 2^(40 - exponent) with eps scaled by its square (kept >= 2^-240)."""
     v = np.asarray(v, dtype=np.float64)
     nc = v.shape[-1]
     if k == 1:
@@ -274,19 +276,30 @@ def reconstruct_fast(v, k=3, eps=1e-6):
     pad = [(0, 0)] * (v.ndim - 1) + [(g, g)]
     vext = np.pad(v, pad, mode="edge")
 
-    def s(off):
+    def raw(off):
         return vext[..., g + off : g + off + nc]
+
+    # per-cell power-of-two scale (1 for stencils of ordinary magnitude)
+    m = np.max(np.stack([np.abs(raw(o)) for o in range(-g, g + 1)]), axis=0)
+    big = m >= 2.0**100
+    with np.errstate(divide="ignore", invalid="ignore"):
+        ex = np.where(big, np.floor(np.log2(np.where(big, m, 1.0))) - 40.0, 0.0)
+    sdn, sup = np.exp2(-ex), np.exp2(ex)
+    epsc = np.where(big, np.maximum(eps * sdn * sdn, 2.0**-240), eps)
+
+    def s(off):
+        return raw(off) * sdn
 
     def d1(off):  # v[c+off+1] - v[c+off]
         return s(off + 1) - s(off)
 
     if k == 2:
-        den0 = (eps + d1(0) ** 2) ** 2
-        den1 = (eps + d1(-1) ** 2) ** 2
+        den0 = (epsc + d1(0) ** 2) ** 2
+        den1 = (epsc + d1(-1) ** 2) ** 2
         h = 0.5 * (d1(0) - d1(-1))
         vr = (s(0) + 0.5 * d1(0)) - (den0 * h) / (2 * den1 + den0)
         vl = (s(0) - 0.5 * d1(-1)) - (den1 * h) / (2 * den0 + den1)
-        return vl, vr
+        return vl * sup, vr * sup
 
     def d2(off):
         return d1(off) - d1(off - 1)
@@ -294,7 +307,7 @@ def reconstruct_fast(v, k=3, eps=1e-6):
     def d3(off):
         return d2(off + 1) - d2(off)
 
-    eps4 = 4.0 * eps
+    eps4 = 4.0 * epsc
     e0 = (d1(1) - 3 * d1(0)) ** 2 + ((13.0 / 3) * d2(1) ** 2 + eps4)
     e1 = (d1(-1) + d1(0)) ** 2 + ((13.0 / 3) * d2(0) ** 2 + eps4)
     e2 = (d1(-2) - 3 * d1(-1)) ** 2 + ((13.0 / 3) * d2(-1) ** 2 + eps4)
@@ -306,4 +319,4 @@ def reconstruct_fast(v, k=3, eps=1e-6):
     vlr1 = s(0) - (2 * d1(-1) + d1(0)) / 6
     vr = vrr1 - (1.5 * x + y) / (6 * p0 + a)
     vl = vlr1 + (x + 1.5 * y) / (6 * p2 + a)
-    return vl, vr
+    return vl * sup, vr * sup

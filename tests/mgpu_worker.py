@@ -131,6 +131,42 @@ def main():
         print(f"[rank {rank}] FAIL adaptive alpha: {alpha!r} vs {float(np.max(np.abs(u0)))!r}", flush=True)
     dist.barrier()
 
+    # ---- host-pointer integrate on slabs: per-slab chunk pipeline on the slab extended by the wide halos (exchanged once
+    # per call through the IPC-mapped mailboxes), no per-stage traffic; forced at a small size by a small chunk --------
+    os.environ["HRWENO_PIPE_CHUNK_TILES"] = "29"
+    for mode, order in [(pkg._abi.MODE_STRICT, 3), (pkg._abi.MODE_STRICT, 1), (FAST, 3)]:
+        nglob = world * 140000 + 777
+        off, n = pkg.slab.partition(nglob, world, rank)
+        g = pkg.hrweno_grids.grid1().linear(-5.0, 5.0, nglob)
+        u0 = ex1_ic(g.center) + 1e-3 * np.random.default_rng(world + order).standard_normal(nglob)
+        fv = pkg.fv.FV(pkg.fv.make_desc(n, k=3, linear=(-5.0, 5.0), mode=mode, rank=rank, nranks=world, global_n=nglob, global_offset=off))
+        pkg.slab.connect(fv, rank, world, gather)
+        ode = pkg.hrweno_tvdode.rktvd(fv, n, order)
+        ref.set_threads(max(1, ref.max_threads() // world))
+        rode = ref.rktvd(ref.FV(pkg.fv.make_desc(nglob, k=3, width=[g.width])), order)
+        u, ur, t, tr = np.ascontiguousarray(u0[off:off + n]), u0.copy(), 0.0, 0.0
+        dt = 0.2 * 10.0 / nglob
+        l0 = ode.launches
+        for nsteps in (6, 1, 11):
+            tt, ttr = t, tr
+            for _ in range(nsteps - 1):
+                tt, ttr = tt + dt, ttr + dt
+            t = ode.integrate(u, t, tt, dt)
+            tr = rode.integrate(ur, tr, ttr, dt)
+            if mode == FAST:
+                ok = t == tr and np.max(np.abs(u - ur[off:off + n])) / np.max(np.abs(ur)) < 1e-12
+            else:
+                ok = t == tr and np.array_equal(u, ur[off:off + n])
+            if not ok:
+                fails += 1
+                print(f"[rank {rank}] FAIL slab host pipeline mode={mode} order={order} nsteps={nsteps}: max|d|={np.max(np.abs(u - ur[off:off + n])):.3e}", flush=True)
+        if ode.launches - l0 <= 3 * 18 * order:
+            fails += 1
+            print(f"[rank {rank}] FAIL slab host pipeline not taken: {ode.launches - l0} launches", flush=True)
+        ref.set_threads(1)
+        dist.barrier()
+    del os.environ["HRWENO_PIPE_CHUNK_TILES"]
+
     tot = torch.tensor([fails], device="cuda")
     dist.all_reduce(tot)
     if rank == 0:

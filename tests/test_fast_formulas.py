@@ -42,3 +42,20 @@ def test_fast_formulas_weights_are_scale_consistent():
     fl, fr = o.reconstruct_fast(v, 3, 1e-6)
     gl, gr = o.reconstruct_fast(8.0 * v, 3, 64.0 * 1e-6)
     assert np.array_equal(gl, 8.0 * fl) and np.array_equal(gr, 8.0 * fr)
+
+
+@pytest.mark.parametrize("k", [2, 3])
+@pytest.mark.parametrize("scale", [1e30, 1e33, 1e34, 1e40, 1e60, 1e70])
+def test_fast_formulas_stay_finite_and_accurate_at_large_magnitudes(k, scale):
+    """the division-light weights form products ~v^9; beyond |v| ~ 1e33 they overflowed while the reference
+    (which only forms (eps+beta)^2 ~ v^4) stays finite up to ~1e76.  With the magnitude guard the fast formulas are
+    evaluated on a stencil scaled by a power of two and stay within a few ULP of the reference order."""
+    rng = np.random.default_rng(11)
+    for v in (rng.standard_normal(300), np.where(np.arange(300) < 150, 1.0, -0.5), np.full(64, 0.7),
+              np.concatenate([rng.standard_normal(100), 1e-30 * rng.standard_normal(100)])):
+        v = v * scale
+        vl, vr = o.reconstruct(v, k, 1e-6)
+        fl, fr = o.reconstruct_fast(v, k, 1e-6)
+        assert np.all(np.isfinite(fl)) and np.all(np.isfinite(fr))
+        tol = 4 * EPS * np.max(np.abs(v))
+        assert np.max(np.abs(vl - fl)) <= tol and np.max(np.abs(vr - fr)) <= tol
