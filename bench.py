@@ -528,12 +528,16 @@ def main():
         return n_global * 3 * k / (m["ms"] * 1e-3), stage_ms, achieved
 
     value, stage_ms, achieved = derive(main_m, K)
-    traffic = None
+    # DRAM bytes per launch from the committed ncu capture of the same kernels (profiles/traffic.json): the AVERAGE over
+    # the three RK3 stage launches, the same averaging as algorithmic_bytes_per_launch next to it -- "from profile", not live
+    traffic, traffic_src = None, None
     tp = os.path.join(ROOT, "profiles", "traffic.json")
     if os.path.exists(tp):
         tj = json.load(open(tp)).get(args.mode, {})
         if tj.get("log2_cells") == args.log2_cells:
             traffic = tj.get("dram_bytes_per_launch")
+            traffic_src = {"from": "profile (ncu --set full, not measured in this run)", "file": "profiles/traffic.json",
+                           "per_stage_ratio_to_algorithmic": {k: v["ratio"] for k, v in tj.get("per_stage", {}).items()}}
     line = {
         "metric": "WENO5+RK3 cell-updates/s", "value": value, "unit": "cell-updates/s", "n_gpus": world, "steps": K,
         "warmup": args.warmup, "ms_per_step": main_m["ms"] / K, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
@@ -551,7 +555,7 @@ def main():
         "gpu_launches": main_m["launches"],
         "clocks": main_m["clocks"],
         "roofline": {
-            "bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": traffic,
+            "bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": traffic, "traffic_source": traffic_src,
             "kernel": "fv1d_stage_kernel<K=3> (average of the 3 RK3 stage instantiations; 16/24/24 algorithmic B per cell)",
             "algorithmic_bytes_per_launch": n * RK3_BYTES_PER_CELL_STEP / 3, "avg_launch_ms": stage_ms, "peak_source": peak_src,
             "note": "fp64 WENO5 is bound by fp64 instruction issue on B200, not by HBM (DESIGN.md section 5)",

@@ -128,6 +128,9 @@ PROTOTYPES = {
     "hrweno_mgpu_destroy": (None, [C.c_void_p]),
     "hrweno_mgpu_ngpus": (C.c_int, [C.c_void_p]),
     "hrweno_mgpu_slab": (C.c_int, [C.c_void_p, C.c_int, C.POINTER(C.c_int), C.POINTER(C.c_int64), C.POINTER(C.c_int64)]),
+    "hrweno_mgpu_set_xedges": (C.c_int, [C.c_void_p, C.c_int, C.c_void_p]),
+    "hrweno_mgpu_set_flux_coef": (C.c_int, [C.c_void_p, C.c_int, C.c_void_p, C.c_void_p]),
+    "hrweno_mgpu_set_flux_time_fn": (C.c_int, [C.c_void_p, TIME_FN, C.c_void_p]),
     "hrweno_mgpu_rktvd": (C.c_int, [C.c_void_p, C.c_int]),
     "hrweno_mgpu_mstvd": (C.c_int, [C.c_void_p]),
     "hrweno_mgpu_integrate": (C.c_int, [C.c_void_p, C.c_void_p, C.POINTER(C.c_double), C.c_double, C.c_double, C.c_int]),

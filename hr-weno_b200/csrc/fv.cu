@@ -4,6 +4,7 @@
 
 #include <float.h>
 
+#include <algorithm>
 #include <cstring>
 #include <string>
 #include <new>
@@ -37,7 +38,7 @@ Fv::~Fv() {
    cudaFree(d_wtab);
    cudaFree(d_widx);
    for (int a = 0; a < 2; ++a) {
-      cudaFree(d_cnu[a]);
+      cudaFree(d_cnu_base[a]);
       cudaFree(d_fcoef[a]);
       cudaFree(d_ccoef[a]);
    }
@@ -250,7 +251,7 @@ static int upload_doubles(const double *host, int64_t n, double **dev) {
 }
 
 static int fv_enable_general(Fv *fv, const char *who) {
-   if (fv->d.nranks > 1) return fail(HRWENO_EINVAL, std::string(who) + ": the general path runs on one GPU (nranks == 1)");
+   (void)who;
    if (fv->d.ndim == 1 && !fv->d_width[0]) { // the 1D widths live in the dictionary: the general kernel reads a plain array
       double *w = nullptr;
       HRW_CUDA(cudaMalloc(&w, (size_t)(fv->n0 + PAD) * sizeof(double)));
@@ -276,9 +277,28 @@ int fv_set_xedges(Fv *fv, int axis, const double *xedges) {
    std::lock_guard<std::mutex> lock(fv->mtx);
    HRW_TRY(fv_enable_general(fv, "hrweno_fv_set_xedges"));
    const int64_t n = axis == 0 ? fv->n0 : fv->n1;
-   std::vector<double> cnu;
-   weno_calc_cnu_host(n, fv->d.k, xedges, cnu);
-   return upload_doubles(cnu.data(), (int64_t)cnu.size(), &fv->d_cnu[axis]);
+   const int k = fv->d.k, KK = k * (k + 1);
+   // Tables of the local cells plus one ghost cell on either side (the faces on a slab interface need the neighbour's edge
+   // cell reconstructed with ITS table).  On the decomposed axis of a slab, xedges is the GLOBAL edge array: the tables of
+   // cells [lo, hi) are computed from the global edges around them (a table reaches k+1 edges beyond its cell, so a
+   // window cut k+2 cells away from the cells we keep gives the very same arithmetic as the whole grid); beyond the
+   // global ends weno_calc_cnu's own linear ghost edges apply (weno.f90:242-255).
+   const bool decomposed = fv->d.nranks > 1 && axis == fv->d.ndim - 1;
+   const int64_t gn = decomposed ? fv->d.global_n : n, off = decomposed ? fv->d.global_offset : 0;
+   const int64_t lo = std::max<int64_t>(0, off - (k + 2)), hi = std::min<int64_t>(gn, off + n + (k + 2));
+   std::vector<double> win;
+   weno_calc_cnu_host(hi - lo, k, xedges + lo, win);
+   std::vector<double> cnu((size_t)(n + 2) * KK);
+   for (int64_t c = -1; c <= n; ++c) {
+      int64_t gc = off + c; // global cell; ghost tables beyond the global ends replicate the end cell's (never used: boundary rule)
+      gc = gc < 0 ? 0 : (gc > gn - 1 ? gn - 1 : gc);
+      std::memcpy(&cnu[(size_t)(c + 1) * KK], &win[(size_t)(gc - lo) * KK], sizeof(double) * (size_t)KK);
+   }
+   cudaFree(fv->d_cnu_base[axis]);
+   fv->d_cnu_base[axis] = fv->d_cnu[axis] = nullptr;
+   HRW_TRY(upload_doubles(cnu.data(), (int64_t)cnu.size(), &fv->d_cnu_base[axis]));
+   fv->d_cnu[axis] = fv->d_cnu_base[axis] + KK;
+   return HRWENO_OK;
 }
 
 // f(v, x) = (model(v)*cross[i_other])*face[i_face] for the faces along `axis`; nullptr = factor absent
@@ -476,7 +496,7 @@ void fv_tiling_1d(const Fv *fv, int *tile_cells, int *tiles_per_row) {
 
 static int fv_stage_impl(Fv *fv, int combine, const StageArgs &args, const HaloIO *io, cudaStream_t st) {
    const hrweno_fv_desc &d = fv->d;
-   if (fv->general) { // non-uniform grid and/or x-dependent flux: the general kernel, reference operation order
+   if (fv->general && d.ndim == 1) { // non-uniform grid and/or x-/t-dependent flux in 1D: the general kernel, reference operation order
       HRW_TRY(fvgen_stage(fv, combine, args, st));
       fv->launches++;
       return HRWENO_OK;
@@ -514,6 +534,11 @@ int fv_stage(Fv *fv, int combine, const StageArgs &args, cudaStream_t st) { retu
 
 int fv_stage_halo(Fv *fv, int combine, const StageArgs &args, bool halo_out, cudaStream_t st) {
    if (fv->d.nranks <= 1) return fv_stage_impl(fv, combine, args, nullptr, st);
+   if (fv->general) { // the general kernels take their ghost cells from the padded state: exchange after the stage
+      HRW_TRY(fv_stage_impl(fv, combine, args, nullptr, st));
+      if (halo_out && !args.out_dense) HRW_TRY(fv_exchange(fv, args.out, st));
+      return HRWENO_OK;
+   }
    HaloIO io;
    HRW_TRY(fv_halo_io(fv, args.vin, args.out, halo_out && !args.out_dense, &io));
    if (io.edge_first) return fv_stage_impl(fv, combine, args, &io, st); // halo traffic inside the stage kernel

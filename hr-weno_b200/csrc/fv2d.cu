@@ -30,7 +30,54 @@ struct Fv2dGeom {
    FluxCfg flux1, flux2;
    int bc;
    int phys_lo, phys_hi; // x2 ends are physical boundaries (x1 ends always are)
+   // general operator (GEN = 1): per-cell reconstruction tables cnu(:,:,i) per axis (weno.f90:100-112,177) and the flux
+   // coefficients f = ((model(v)*cross)*face)*g(t) (fluxes.f90:12-18; example2:100-101,109-110,140,153); nullptr = absent
+   const double *cnu0, *cnu1;
+   const double *fc0, *fc1, *cc0, *cc1;
+   int has_ts;
+   double ts;
 };
+
+// reconstruction of a run of R cells of a line whose first cell has index i0 on its axis (n cells): uniform tables, or the
+// per-cell tables of weno(ncells, k, eps, xedges) at `cnu` (indices clamped to the axis: cells beyond it are never used)
+template <int K, int R, class M>
+__device__ __forceinline__ void run2d(const double *w /* window, cell j at w[2 + j] */, const WenoK &kc, const double *cnu, int64_t i0,
+                                      int64_t n, double *vl, double *vr) {
+   if (cnu == nullptr) {
+      weno_run<K, R, M>(w + (2 - (K - 1)), kc, vl, vr);
+   } else {
+      constexpr int KK = K * (K + 1);
+#pragma unroll
+      for (int j = 0; j < R; ++j) {
+         int64_t i = i0 + j; // the tables carry one ghost cell on either side (a slab neighbour's edge cell)
+         i = i < -1 ? -1 : (i > n ? n : i);
+         double ci[KK]; // K(K+1) is even and the table is cudaMalloc'ed: 16-B loads
+         const double2 *c2 = reinterpret_cast<const double2 *>(cnu + i * KK);
+#pragma unroll
+         for (int q = 0; q < KK / 2; ++q) {
+            const double2 t = __ldg(c2 + q);
+            ci[2 * q] = t.x;
+            ci[2 * q + 1] = t.y;
+         }
+         weno_cell_nonuniform<K, Strict>(ci, w + 2 + j, kc.eps, vl[j], vr[j]);
+      }
+   }
+}
+
+// numerical flux at one face with the general operator's coefficients, reference operation order (fvgen.cu: same expressions)
+__device__ __forceinline__ double gen2d_phys(const FluxCfg &c, double v, const double *cc, const double *fc, int has_ts, double ts) {
+   double f = phys_flux<Strict>(c, v);
+   if (cc) f = __dmul_rn(f, *cc);
+   if (fc) f = __dmul_rn(f, *fc);
+   if (has_ts) f = __dmul_rn(f, ts);
+   return f;
+}
+__device__ __forceinline__ double gen2d_face(const FluxCfg &c, double vm, double vp, const double *cc, const double *fc, int has_ts, double ts) {
+   const double fm = gen2d_phys(c, vm, cc, fc, has_ts, ts), fp = gen2d_phys(c, vp, cc, fc, has_ts, ts);
+   if (c.scheme == HRWENO_SCHEME_LAX_FRIEDRICHS) return __dmul_rn(__dsub_rn(__dadd_rn(fm, fp), __dmul_rn(c.alpha, __dsub_rn(vp, vm))), 0.5);
+   const double lo = fm < fp ? fm : fp, hi = fm > fp ? fm : fp; // fluxes.f90:70-74
+   return vm <= vp ? lo : hi;
+}
 
 template <int TX, int TY, int UPW = 0>
 struct Tile2d {
@@ -87,7 +134,7 @@ __device__ __forceinline__ double face2d(const FluxCfg &c, double vm, double vp)
 }
 
 // phase B for one thread = (column lx, run of R rows).  INTERIOR: the tile touches no domain edge and is complete.
-template <int K, int COMBINE, class M, int UPW, int TX, int TY, bool INTERIOR>
+template <int K, int COMBINE, class M, int UPW, int TX, int TY, bool INTERIOR, int GEN = 0>
 __device__ __forceinline__ void fv2d_phase_b(const Fv2dGeom &g, const StageArgs &s, const double *s_v, const double *s_vlx,
                                              const double *s_vrx, const double *s_wd /* staged widths */, const double *s_ops,
                                              const double *vmY /* vr below face j, j = 0..R */,
@@ -103,7 +150,14 @@ __device__ __forceinline__ void fv2d_phase_b(const Fv2dGeom &g, const StageArgs 
    // x2-faces gy0 .. gy0+R of column gx: face f lies between rows f-1 and f
    double F2[R + 1];
 #pragma unroll
-   for (int j = 0; j <= R; ++j) F2[j] = face2d<UPW, M>(g.flux2, vmY[j], UPW ? 0.0 : vpY[j]);
+   for (int j = 0; j <= R; ++j) {
+      if constexpr (GEN) { // x2 face gy0 + j of column gx: [center1(i), right2(j)] (example2:109-110)
+         const int64_t f = gy0 + j > g.n1 ? g.n1 : gy0 + j, c = gx < g.n0 ? gx : g.n0 - 1;
+         F2[j] = gen2d_face(g.flux2, vmY[j], vpY[j], g.cc1 ? g.cc1 + c : nullptr, g.fc1 ? g.fc1 + f : nullptr, g.has_ts, g.ts);
+      } else {
+         F2[j] = face2d<UPW, M>(g.flux2, vmY[j], UPW ? 0.0 : vpY[j]);
+      }
+   }
    if constexpr (!INTERIOR) {
       if (g.phys_lo && gy0 == 0) F2[0] = copy ? F2[1] : 0.0;
       if (g.phys_hi) {
@@ -137,8 +191,16 @@ __device__ __forceinline__ void fv2d_phase_b(const Fv2dGeom &g, const StageArgs 
       const int ly = ly0 + j;
       // x1-faces gx and gx+1 of row gy
       const double *vlx = s_vlx + ly * T::XP + R + lx, *vrx = s_vrx + ly * T::XP + R + lx;
-      double Fl = face2d<UPW, M>(g.flux1, vrx[-1], UPW ? 0.0 : vlx[0]);
-      double Fr = face2d<UPW, M>(g.flux1, vrx[0], UPW ? 0.0 : vlx[1]);
+      double Fl, Fr;
+      if constexpr (GEN) { // x1 faces gx, gx+1 of row gy: [right1(i), center2(j)] (example2:100-101)
+         const int64_t gyc = gy0 + j < g.n1 ? gy0 + j : g.n1 - 1, f0 = gx < g.n0 ? gx : g.n0 - 1;
+         const double *cc = g.cc0 ? g.cc0 + gyc : nullptr;
+         Fl = gen2d_face(g.flux1, vrx[-1], vlx[0], cc, g.fc0 ? g.fc0 + f0 : nullptr, g.has_ts, g.ts);
+         Fr = gen2d_face(g.flux1, vrx[0], vlx[1], cc, g.fc0 ? g.fc0 + f0 + 1 : nullptr, g.has_ts, g.ts);
+      } else {
+         Fl = face2d<UPW, M>(g.flux1, vrx[-1], UPW ? 0.0 : vlx[0]);
+         Fr = face2d<UPW, M>(g.flux1, vrx[0], UPW ? 0.0 : vlx[1]);
+      }
       if constexpr (!INTERIOR) {
          if (copy) { // fedges(0) = fedges(1), fedges(nc) = fedges(nc-1)
             if (gx == 0) Fl = Fr;
@@ -224,7 +286,7 @@ constexpr int fv2d_min_blocks() {
    return NT > 256 ? HRW_MINB2_BIG : ((UPW && !M::strict) ? 3 : 2) * (256 / NT);
 }
 
-template <int K, int COMBINE, class M, int UPW, int TX, int TY, int NT>
+template <int K, int COMBINE, class M, int UPW, int TX, int TY, int NT, int GEN = 0>
 __global__ void __launch_bounds__(NT, fv2d_min_blocks<M, UPW, NT>())
    fv2d_stage_kernel(const Fv2dGeom g, const StageArgs s, const __grid_constant__ CUtensorMap tm_v, const __grid_constant__ CUtensorMap tm_a,
                      const __grid_constant__ CUtensorMap tm_b) {
@@ -315,7 +377,7 @@ __global__ void __launch_bounds__(NT, fv2d_min_blocks<M, UPW, NT>())
          w[j + 1] = t.y;
       }
       double vl[R], vr[R];
-      weno_run<K, R, M>(w + (2 - (K - 1)), g.kc, vl, vr);
+      run2d<K, R, M>(w, g.kc, GEN ? g.cnu0 : nullptr, x0 + rx * R, g.n0, vl, vr);
 #pragma unroll
       for (int j = 0; j < R; ++j) {
          if constexpr (!UPW) s_vlx[oidx + j] = vl[j]; // upwind: the left side is never used and is eliminated
@@ -331,23 +393,27 @@ __global__ void __launch_bounds__(NT, fv2d_min_blocks<M, UPW, NT>())
       const double *base;
       int stride;
       double *dst;
+      const double *tab = nullptr; // GEN: the table of this cell's axis
+      int64_t ci = 0, cn = 1;
       if (q < TY) { // x1 line q
          const int cx = high ? TX : -1;
          base = s_vt + (q + H) * T::SP + (H + cx);
          stride = 1;
          dst = (high ? s_vlx : s_vrx) + q * T::XP + R + cx;
+         if constexpr (GEN) tab = g.cnu0, ci = x0 + cx, cn = g.n0;
       } else { // x2 line
          const int lx = q - TY;
          const int cy = high ? TY : -1;
          base = s_vt + (H + cy) * T::SP + (lx + H);
          stride = T::SP;
          dst = high ? s_vle + T::RY * TX + lx : s_vre + lx;
+         if constexpr (GEN) tab = g.cnu1, ci = y0 + cy, cn = g.n1;
       }
       double w[5];
 #pragma unroll
       for (int j = 0; j < 5; ++j) w[j] = base[(j - 2) * stride];
       double vl1[1], vr1[1];
-      weno_run<K, 1, M>(w + (2 - (K - 1)), g.kc, vl1, vr1);
+      run2d<K, 1, M>(w, g.kc, tab, ci, cn, vl1, vr1);
       *dst = high ? vl1[0] : vr1[0];
    }
    // x2-sweep: item (column lx, run ry) is also this thread's phase-B item, so vl / vr stay in registers; the values the
@@ -362,7 +428,7 @@ __global__ void __launch_bounds__(NT, fv2d_min_blocks<M, UPW, NT>())
       double w[R + 4];
 #pragma unroll
       for (int j = 0; j < R + 4; ++j) w[j] = base[(j - 2) * T::SP];
-      weno_run<K, R, M>(w + (2 - (K - 1)), g.kc, vlY[q], vrY[q]);
+      run2d<K, R, M>(w, g.kc, GEN ? g.cnu1 : nullptr, y0 + ry * R, g.n1, vlY[q], vrY[q]);
       s_vre[(ry + 1) * TX + lx] = vrY[q][R - 1];
       if constexpr (!UPW) s_vle[ry * TX + lx] = vlY[q][0];
    }
@@ -385,9 +451,9 @@ __global__ void __launch_bounds__(NT, fv2d_min_blocks<M, UPW, NT>())
       }
       vpY[R] = UPW ? 0.0 : s_vle[(ry + 1) * TX + lx];
       if (interior)
-         fv2d_phase_b<K, COMBINE, M, UPW, TX, TY, true>(g, s, s_vt, s_vlx, s_vrx, s_wd, s_ops, vmY, vpY, x0, y0, lx, ry * R);
+         fv2d_phase_b<K, COMBINE, M, UPW, TX, TY, true, GEN>(g, s, s_vt, s_vlx, s_vrx, s_wd, s_ops, vmY, vpY, x0, y0, lx, ry * R);
       else
-         fv2d_phase_b<K, COMBINE, M, UPW, TX, TY, false>(g, s, s_vt, s_vlx, s_vrx, s_wd, s_ops, vmY, vpY, x0, y0, lx, ry * R);
+         fv2d_phase_b<K, COMBINE, M, UPW, TX, TY, false, GEN>(g, s, s_vt, s_vlx, s_vrx, s_wd, s_ops, vmY, vpY, x0, y0, lx, ry * R);
    }
    } // tile loop
 }
@@ -401,12 +467,12 @@ constexpr int TX2 = HRW_TX2, TY2 = HRW_TY2, NT2 = HRW_NT2;   // large grids
 constexpr int NT2F = 2 * HRW_NT2;                            // threads per tile in fast mode
 constexpr int TX2S = 32, TY2S = 16, NT2S = 128; // small grids (e.g. example2's 250x250): enough tiles to occupy every SM
 
-template <int K, int COMBINE, class M, int UPW, int TX2, int TY2, int NT2>
+template <int K, int COMBINE, class M, int UPW, int TX2, int TY2, int NT2, int GEN = 0>
 static int launch2d_t(Fv *fv, const Fv2dGeom &g, const StageArgs &a, cudaStream_t st) {
    using T = Tile2d<TX2, TY2, UPW>;
    constexpr int NSTG = fv2d_nstaged(COMBINE, UPW);
    constexpr size_t BYTES = T::bytes(NSTG);
-   auto kern = fv2d_stage_kernel<K, COMBINE, M, UPW, TX2, TY2, NT2>;
+   auto kern = fv2d_stage_kernel<K, COMBINE, M, UPW, TX2, TY2, NT2, GEN>;
    static bool configured[64] = {}; // one flag per instantiation and device (function attributes are per device)
    int dev = 0;
    cudaGetDevice(&dev);
@@ -454,8 +520,18 @@ static int launch2d_u(Fv *fv, const Fv2dGeom &g, const StageArgs &a, cudaStream_
    return launch2d_t<K, COMBINE, M, UPW, TX2, TY2, NT2>(fv, g, a, st);
 }
 
+// general operator: reference operation order (Strict), two-sided fluxes, per-cell tables / coefficients where present
+template <int K, int COMBINE>
+static int launch2d_gen(Fv *fv, const Fv2dGeom &g, const StageArgs &a, cudaStream_t st) {
+   if (g.small_tiles) return launch2d_t<K, COMBINE, Strict, 0, TX2S, TY2S, NT2S, 1>(fv, g, a, st);
+   return launch2d_t<K, COMBINE, Strict, 0, TX2, TY2, NT2, 1>(fv, g, a, st);
+}
+
 template <int K, int COMBINE, class M>
 static int launch2d(Fv *fv, const Fv2dGeom &g, const StageArgs &a, cudaStream_t st) {
+   if constexpr (M::strict) {
+      if (fv->general) return launch2d_gen<K, COMBINE>(fv, g, a, st);
+   }
    const bool upw = g.flux1.model == HRWENO_FLUX_LINEAR && g.flux1.scheme == HRWENO_SCHEME_GODUNOV && g.flux1.coef >= 0.0 && g.flux2.coef >= 0.0;
    return upw ? launch2d_u<K, COMBINE, M, 1>(fv, g, a, st) : launch2d_u<K, COMBINE, M, 0>(fv, g, a, st);
 }
@@ -502,8 +578,18 @@ int fv2d_stage(Fv *fv, int combine, const StageArgs &args, cudaStream_t st) {
    g.bc = d.bc;
    g.phys_lo = d.rank == 0;
    g.phys_hi = d.rank == d.nranks - 1;
+   if (fv->general) { // non-uniform grids / x- or t-dependent fluxes: the same tile kernel in the reference's operation order
+      g.cnu0 = fv->d_cnu[0];
+      g.cnu1 = fv->d_cnu[1];
+      g.fc0 = fv->d_fcoef[0];
+      g.fc1 = fv->d_fcoef[1];
+      g.cc0 = fv->d_ccoef[0];
+      g.cc1 = fv->d_ccoef[1];
+      g.has_ts = fv->tfn != nullptr;
+      g.ts = fv->tfn ? fv->tfn(fv->tfn_ctx, args.t) : 1.0;
+   }
    if ((int64_t)g.tiles_x * g.tiles_y > 2000000000LL) return fail(HRWENO_EINVAL, "2D grid too large for one launch");
-   if (d.mode == HRWENO_MODE_STRICT) return launch2d_k<Strict>(fv, d.k, combine, g, args, st);
+   if (d.mode == HRWENO_MODE_STRICT || fv->general) return launch2d_k<Strict>(fv, d.k, combine, g, args, st);
    return launch2d_k<Fast>(fv, d.k, combine, g, args, st);
 }
 

@@ -20,7 +20,8 @@
 // 2D: 1120 items, 2.19 reconstructions per cell).  Phase B: a thread owns one (1D) or two (2D) cells: two faces per
 // direction from shared memory, boundary rule, divergence, combination, store.  HBM-bound by the 8k(k+1) B/cell of coefficient traffic per
 // non-uniform axis (96 B/cell at k=3) on top of the stage's 16-40 B/cell.
-// Single GPU only (nranks == 1): per-cell tables of a slab would need the neighbour's edges.
+// Slabs: the frame cells beyond a slab interface are the neighbour's edge cells (ghost cells of the padded state, filled by
+// fv_exchange after every stage); their tables come with the slab's own (fv.cu: fv_set_xedges takes the global edges).
 #include "fv2d.cuh"
 #include "internal.hpp"
 #include "weno_core.cuh"
@@ -37,6 +38,7 @@ struct GenGeom {
    const double *cc0, *cc1;   // cross coefficient: cc0[j] for x1 faces of row j, cc1[i] for x2 faces of column i, or nullptr
    WenoK kc;
    FluxCfg fx0, fx1;
+   int phys_l, phys_r; // the row ends are physical boundaries (else slab interfaces: ghost cells hold the neighbour's cells)
    int has_ts;  // the flux carries a time factor g(t) (fluxes.f90:12-18 passes t to the flux)
    double ts;   // its value at this evaluation's time, computed on the host
 };
@@ -47,11 +49,11 @@ struct GenGeom {
 // table cnu(:,:,i) at `ctab` or the uniform tables.
 template <int K, bool UNIT, bool CLAMP>
 __device__ __forceinline__ void gen_recon(const double *cell, int64_t inc, int64_t i, int64_t n, bool has_tab, const double *ctab,
-                                          const WenoK &kc, double &l, double &r) {
+                                          const WenoK &kc, double &l, double &r, bool phys_l = true, bool phys_r = true) {
    int lo = -(K - 1), hi = K - 1;
-   if constexpr (CLAMP) { // edge replicas (weno.f90:171-173): offsets clamped to the row, in 32 bits
-      lo = -(int)(i < K - 1 ? i : K - 1);
-      hi = (int)(n - 1 - i < K - 1 ? n - 1 - i : K - 1);
+   if constexpr (CLAMP) { // edge replicas (weno.f90:171-173): offsets clamped to the row at PHYSICAL ends, in 32 bits
+      if (phys_l) lo = -(int)(i < K - 1 ? i : K - 1);
+      if (phys_r) hi = (int)(n - 1 - i < K - 1 ? n - 1 - i : K - 1);
    }
    double w[2 * K - 1];
 #pragma unroll
@@ -99,10 +101,10 @@ __device__ __forceinline__ double gen_face_flux(const FluxCfg &c, double vm, dou
 }
 
 // boundary rule on the two faces of cell i of a row of n cells: interior faces are given in fl (i > 0) and fr (i < n-1)
-__device__ __forceinline__ void gen_bc(int bc, int64_t i, int64_t n, double &fl, double &fr) {
+__device__ __forceinline__ void gen_bc(int bc, int64_t i, int64_t n, double &fl, double &fr, bool phys_l = true, bool phys_r = true) {
    const bool zero = bc == HRWENO_BC_ZERO_FLUX;
-   if (i == 0) fl = zero ? 0.0 : fr;     // fedges(0) = fedges(1) (example1:103) | 0 (example2:117,119); copy needs n >= 2
-   if (i == n - 1) fr = zero ? 0.0 : fl; // fedges(nc) = fedges(nc-1) (example1:104) | 0 (example2:118,120)
+   if (i == 0 && phys_l) fl = zero ? 0.0 : fr;     // fedges(0) = fedges(1) (example1:103) | 0 (example2:117,119); copy needs n >= 2
+   if (i == n - 1 && phys_r) fr = zero ? 0.0 : fl; // fedges(nc) = fedges(nc-1) (example1:104) | 0 (example2:118,120)
 }
 
 // tile of one CTA: 2D 32x16 cells (two per thread in phase B), 1D 254 cells (threads 1..254 own one; 0 and 255 only
@@ -136,10 +138,11 @@ __device__ __forceinline__ void gen_tile(const GenGeom &g, const StageArgs &a, c
       if (q < N1) { // N1 is a multiple of 32: the branch is warp-uniform
          const int iy = q / SX, ix = q - iy * SX - 1; // cell (i0 + ix, j0 + iy), ix = -1 .. TX
          const int64_t i = i0 + ix, j = j0 + iy;
-         if (INTERIOR || (i >= 0 && i < g.n0 && j < g.n1)) {
+         // at a slab interface the frame cell beyond the row end is the neighbour's edge cell (a ghost cell of the padded state)
+         if (INTERIOR || (i >= (g.phys_l ? 0 : -1) && i < g.n0 + (g.phys_r ? 0 : 1) && j < g.n1)) {
             double l, r;
-            gen_recon<K, true, !INTERIOR>(vt + (int64_t)iy * g.ld + ix, 1, i, g.n0, has0, t0 + ix * KK, g.kc, l,
-                                          r); // example1:93, example2:98 (contiguous row)
+            gen_recon<K, true, !INTERIOR>(vt + (int64_t)iy * g.ld + ix, 1, i, g.n0, has0, t0 + ix * KK, g.kc, l, r, g.phys_l != 0,
+                                          g.phys_r != 0); // example1:93, example2:98 (contiguous row)
             s_l1[q] = l;
             s_r1[q] = r;
          }
@@ -176,9 +179,9 @@ __device__ __forceinline__ void gen_tile(const GenGeom &g, const StageArgs &a, c
       const double cc0 = hc0 ? g.cc0[j] : 1.0;
       const int c1 = lx + 1 + ly * SX; // shared index of cell (i, j) in the x1 arrays
       double fl = 0.0, fr = 0.0;
-      if (INTERIOR || i > 0) fl = gen_face_flux(g.fx0, s_r1[c1 - 1], s_l1[c1], hc0, cc0, hf0, hf0 ? g.fc0[i] : 1.0, ts);
-      if (INTERIOR || i < g.n0 - 1) fr = gen_face_flux(g.fx0, s_r1[c1], s_l1[c1 + 1], hc0, cc0, hf0, hf0 ? g.fc0[i + 1] : 1.0, ts);
-      if constexpr (!INTERIOR) gen_bc(g.bc, i, g.n0, fl, fr);
+      if (INTERIOR || i > 0 || !g.phys_l) fl = gen_face_flux(g.fx0, s_r1[c1 - 1], s_l1[c1], hc0, cc0, hf0, hf0 ? g.fc0[i] : 1.0, ts);
+      if (INTERIOR || i < g.n0 - 1 || !g.phys_r) fr = gen_face_flux(g.fx0, s_r1[c1], s_l1[c1 + 1], hc0, cc0, hf0, hf0 ? g.fc0[i + 1] : 1.0, ts);
+      if constexpr (!INTERIOR) gen_bc(g.bc, i, g.n0, fl, fr, g.phys_l != 0, g.phys_r != 0);
       double L = -__ddiv_rn(__dsub_rn(fr, fl), g.w0[i]); // -(fedges(i) - fedges(i-1))/width(i)   example1:107, example2:125
       if constexpr (TWO_D) {
          const bool hc1 = g.cc1 != nullptr, hf1 = g.fc1 != nullptr;
@@ -235,15 +238,14 @@ __global__ void __launch_bounds__(GEN_NT, gen_minb<TWO_D>()) fvgen_stage_kernel(
 
 template <int K>
 static void fvgen_launch(bool two_d, unsigned blocks, const GenGeom &g, const StageArgs &a, int combine, cudaStream_t st) {
-   if (two_d)
-      fvgen_stage_kernel<K, true><<<blocks, GEN_NT, 0, st>>>(g, a, combine);
-   else
-      fvgen_stage_kernel<K, false><<<blocks, GEN_NT, 0, st>>>(g, a, combine);
+   (void)two_d; // 2D general operators run on the tile kernel of fv2d.cu (GEN = 1) since round 2: 1D rows only here
+   fvgen_stage_kernel<K, false><<<blocks, GEN_NT, 0, st>>>(g, a, combine);
 }
 
 int fvgen_stage(Fv *fv, int combine, const StageArgs &args, cudaStream_t st) {
    const hrweno_fv_desc &d = fv->d;
-   const bool two_d = d.ndim == 2;
+   if (d.ndim == 2) return fail(HRWENO_EINVAL, "general stage: 2D operators take the tile kernel (fv2d.cu)");
+   const bool two_d = false;
    GenGeom g{};
    g.n0 = fv->n0;
    g.n1 = two_d ? fv->n1 : fv->rows;
@@ -260,6 +262,8 @@ int fvgen_stage(Fv *fv, int combine, const StageArgs &args, cudaStream_t st) {
    g.kc = make_wenok(d.eps);
    g.fx0 = FluxCfg{d.flux_model, d.flux_scheme, d.flux_coef[0], d.alpha};
    g.fx1 = FluxCfg{d.flux_model, d.flux_scheme, d.flux_coef[1], d.alpha};
+   g.phys_l = d.rank == 0;
+   g.phys_r = d.rank == d.nranks - 1;
    g.has_ts = fv->tfn != nullptr;
    g.ts = fv->tfn ? fv->tfn(fv->tfn_ctx, args.t) : 1.0; // the caller's g(t) at this evaluation's time
    if (!g.w0 || (two_d && !g.w1)) return fail(HRWENO_EINVAL, "general stage: width arrays missing");

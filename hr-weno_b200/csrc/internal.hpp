@@ -92,7 +92,9 @@ struct Fv {
    double rx = 0.0;              // GRID_LINEAR: (xmax-xmin)/global_n
    // general path (fvgen.cu, K7), switched on by hrweno_fv_set_xedges / hrweno_fv_set_flux_coef
    bool general = false;
-   double *d_cnu[2] = {nullptr, nullptr};   // cnu(0:k-1,-1:k-1,1:n[a]) of weno(ncells,k,eps,xedges)  (weno.f90:41,100-112)
+   double *d_cnu[2] = {nullptr, nullptr};   // cnu(0:k-1,-1:k-1,1:n[a]) of weno(ncells,k,eps,xedges)  (weno.f90:41,100-112): pointer at the
+                                            // table of cell 0; one ghost table on either side (the neighbour slab's edge cell, or a replica)
+   double *d_cnu_base[2] = {nullptr, nullptr}; // their allocations
    double *d_fcoef[2] = {nullptr, nullptr}; // face coefficient along axis a, index 0..n[a] like edges(0:n)
    double *d_ccoef[2] = {nullptr, nullptr}; // cross coefficient for the faces of axis a, index = cell along the other axis
    hrweno_time_fn tfn = nullptr;            // time factor g(t) of the flux (hrweno_fv_set_flux_time_fn), evaluated on the host per stage

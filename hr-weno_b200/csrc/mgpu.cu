@@ -32,6 +32,8 @@ struct Mgpu {
    std::vector<double *> u;             // resident dense state of each slab
    std::vector<double *> part;          // per-device scalar (partial maximum)
    std::vector<int64_t> off, len;       // offset / length of each slab in the caller's global vector (unknowns)
+   std::vector<int64_t> soff, slen;     // offset / length of each slab along the decomposed axis (cells or rows)
+   int ndim = 1;
    std::vector<cudaEvent_t> ev;
    double **d_ptrs = nullptr;           // device 0: table of the partial-maximum pointers
    double *d_max = nullptr;             // device 0: the reduced value
@@ -100,6 +102,7 @@ static int mgpu_create(Mgpu **out, const hrweno_fv_desc *desc, int ngpus, const 
    const int64_t nsplit = rows_mode ? desc->rows : desc->n[desc->ndim - 1];
    if (nsplit < ngpus) return fail(HRWENO_EINVAL, "hrweno_mgpu_create: fewer cells (rows) along the decomposed axis than GPUs");
    m->n = ngpus;
+   m->ndim = desc->ndim;
    m->split_rows = rows_mode;
    for (int r = 0; r < ngpus; ++r) m->dev.push_back(devices ? devices[r] : r);
    // peer access between neighbouring slabs (and from device 0 to everyone for the reduction)
@@ -127,6 +130,8 @@ static int mgpu_create(Mgpu **out, const hrweno_fv_desc *desc, int ngpus, const 
       const int64_t nloc = base + (r < rem ? 1 : 0), o = (int64_t)r * base + std::min<int64_t>(r, rem);
       m->off.push_back(o * unit);
       m->len.push_back(nloc * unit);
+      m->soff.push_back(o);
+      m->slen.push_back(nloc);
       hrweno_fv_desc d = *desc;
       if (rows_mode) {
          d.rows = nloc;
@@ -159,6 +164,33 @@ static int mgpu_create(Mgpu **out, const hrweno_fv_desc *desc, int ngpus, const 
    HRW_CUDA(cudaMemcpy(m->d_ptrs, m->part.data(), (size_t)ngpus * sizeof(double *), cudaMemcpyHostToDevice));
    HRW_CUDA(cudaMalloc(&m->d_max, sizeof(double)));
    *out = m.release();
+   return HRWENO_OK;
+}
+
+// general operators on slabs: the global arrays are cut like the grid.  Along the decomposed axis a slab takes the GLOBAL
+// edge array (fv_set_xedges derives the tables of its cells and of the two neighbour cells from it) and its own part of the
+// face / cross coefficients; arrays along the other axis are shared.
+static int mgpu_set_xedges(Mgpu *m, int axis, const double *xedges) {
+   if (!m || !xedges) return fail(HRWENO_EINVAL, "hrweno_mgpu_set_xedges: null argument");
+   for (int r = 0; r < m->n; ++r) {
+      HRW_CUDA(cudaSetDevice(m->dev[r]));
+      const bool dec = !m->split_rows && axis == m->ndim - 1;
+      // nranks > 1: global edges on the decomposed axis; a single slab (or rows mode) has local == global
+      (void)dec;
+      HRW_TRY(fv_set_xedges(m->fv[r], axis, xedges));
+   }
+   return HRWENO_OK;
+}
+
+static int mgpu_set_flux_coef(Mgpu *m, int axis, const double *face, const double *cross) {
+   if (!m) return fail(HRWENO_EINVAL, "null mgpu handle");
+   for (int r = 0; r < m->n; ++r) {
+      HRW_CUDA(cudaSetDevice(m->dev[r]));
+      const bool dec_axis = !m->split_rows && axis == m->ndim - 1;        // faces of the decomposed axis: this slab's n+1 faces
+      const bool dec_cross = !m->split_rows && m->ndim == 2 && axis == 0; // cross index runs along the decomposed axis (x2 cells)
+      HRW_TRY(fv_set_flux_coef(m->fv[r], axis, face ? face + (dec_axis ? m->soff[r] : 0) : nullptr,
+                               cross ? cross + (dec_cross ? m->soff[r] : 0) : nullptr));
+   }
    return HRWENO_OK;
 }
 
@@ -254,6 +286,29 @@ int hrweno_mgpu_slab(const hrweno_mgpu *h, int rank, int *device, int64_t *offse
    if (device) *device = m->dev[rank];
    if (offset) *offset = m->off[rank];
    if (count) *count = m->len[rank];
+   return HRWENO_OK;
+}
+int hrweno_mgpu_set_xedges(hrweno_mgpu *h, int axis, const double *xedges) {
+   int prev = 0;
+   cudaGetDevice(&prev);
+   const int st = mgpu_set_xedges(reinterpret_cast<Mgpu *>(h), axis, xedges);
+   cudaSetDevice(prev);
+   return st;
+}
+int hrweno_mgpu_set_flux_coef(hrweno_mgpu *h, int axis, const double *face_coef, const double *cross_coef) {
+   int prev = 0;
+   cudaGetDevice(&prev);
+   const int st = mgpu_set_flux_coef(reinterpret_cast<Mgpu *>(h), axis, face_coef, cross_coef);
+   cudaSetDevice(prev);
+   return st;
+}
+int hrweno_mgpu_set_flux_time_fn(hrweno_mgpu *h, hrweno_time_fn g, void *ctx) {
+   Mgpu *m = reinterpret_cast<Mgpu *>(h);
+   if (!m) return fail(HRWENO_EINVAL, "null mgpu handle");
+   for (int r = 0; r < m->n; ++r) {
+      cudaSetDevice(m->dev[r]);
+      HRW_TRY(fv_set_flux_time_fn(m->fv[r], g, ctx));
+   }
    return HRWENO_OK;
 }
 int hrweno_mgpu_rktvd(hrweno_mgpu *h, int order) {

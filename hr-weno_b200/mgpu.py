@@ -36,6 +36,27 @@ class MultiGPU:
         _abi.check(_abi.lib().hrweno_mgpu_slab(self._h, rank, C.byref(dev), C.byref(off), C.byref(cnt)))
         return dev.value, off.value, cnt.value
 
+    # general operators: GLOBAL arrays, cut like the grid inside the library
+    def set_xedges(self, axis, xedges):
+        xe = np.ascontiguousarray(xedges, dtype=np.float64)
+        if xe.size != self.desc.n[axis] + 1:  # weno.f90:101-108
+            raise _abi.HrwenoError(_abi.EINVAL, "Invalid input 'xedges'. Valid range: size(xedges) = ncells + 1.")
+        _abi.check(_abi.lib().hrweno_mgpu_set_xedges(self._h, axis, xe.ctypes.data))
+
+    def set_flux_coef(self, axis, face=None, cross=None):
+        f = None if face is None else np.ascontiguousarray(face, dtype=np.float64)
+        c = None if cross is None else np.ascontiguousarray(cross, dtype=np.float64)
+        if f is not None and f.size != self.desc.n[axis] + 1:
+            raise _abi.HrwenoError(_abi.EINVAL, "face coefficients: size must be ncells + 1 (indexed like edges(0:n))")
+        if c is not None and (self.desc.ndim != 2 or c.size != self.desc.n[1 - axis]):
+            raise _abi.HrwenoError(_abi.EINVAL, "cross coefficients: ndim == 2 and one value per cell of the other axis")
+        _abi.check(_abi.lib().hrweno_mgpu_set_flux_coef(self._h, axis, None if f is None else f.ctypes.data,
+                                                        None if c is None else c.ctypes.data))
+
+    def set_flux_time_fn(self, g):
+        self._tfn = _abi.TIME_FN(lambda _ctx, t: float(g(t))) if g is not None else C.cast(None, _abi.TIME_FN)
+        _abi.check(_abi.lib().hrweno_mgpu_set_flux_time_fn(self._h, self._tfn, None))
+
     def rktvd(self, order=3):
         _abi.check(_abi.lib().hrweno_mgpu_rktvd(self._h, int(order)))
         return self

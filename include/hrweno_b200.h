@@ -167,7 +167,9 @@ int hrweno_fv_rhs_dev(hrweno_fv *fv, double t, const double *v_dev, double *vdot
  * cnu(:,:,i) of `weno(ncells, k, eps, xedges)` (weno.f90:100-112, 177, 221-297) instead of c1/c2/c3.  xedges[0..n[axis]]
  * (host) are the cell edges of that axis (grid1%edges, grids.f90:232-250; any grid1 kind).  The cell widths stay the
  * ones of the descriptor.  Call after hrweno_fv_create and before the first rhs / integrate call; from then on this
- * operator runs the general stage kernel (reference operation order in both modes, one GPU). */
+ * operator runs the general stage kernels (reference operation order in both modes).  Slabs (nranks > 1): along the
+ * DECOMPOSED axis pass the GLOBAL edge array xedges[0..global_n] -- the tables of a slab's first and last cells, and of
+ * the neighbour cells its interface faces need, depend on edges beyond the slab; other axes: the local (= global) edges. */
 int hrweno_fv_set_xedges(hrweno_fv *fv, int axis, const double *xedges);
 /* x-dependent fluxes in the fused path.  The reference hands the face coordinates to the flux callback
  * (`f(u, x(:), t)`, fluxes.f90:12-18; example2:100-101 passes [right1(i), center2(j)], :109-110 [center1(i), right2(j)])
@@ -219,6 +221,11 @@ void hrweno_mgpu_destroy(hrweno_mgpu *m);
 int hrweno_mgpu_ngpus(const hrweno_mgpu *m);
 /* slab `rank`: its device, and offset / count of its unknowns inside the global vector */
 int hrweno_mgpu_slab(const hrweno_mgpu *m, int rank, int *device, int64_t *offset, int64_t *count);
+/* general operators on the slabs, GLOBAL arrays (the library cuts them like the grid): hrweno_fv_set_xedges /
+ * _set_flux_coef / _set_flux_time_fn for the whole problem */
+int hrweno_mgpu_set_xedges(hrweno_mgpu *m, int axis, const double *xedges);
+int hrweno_mgpu_set_flux_coef(hrweno_mgpu *m, int axis, const double *face_coef, const double *cross_coef);
+int hrweno_mgpu_set_flux_time_fn(hrweno_mgpu *m, hrweno_time_fn g, void *ctx);
 int hrweno_mgpu_rktvd(hrweno_mgpu *m, int order); /* rktvd(fu, neq, order) with the fused rhs, tvdode.f90:69-95 */
 int hrweno_mgpu_mstvd(hrweno_mgpu *m);            /* mstvd(fu, neq), tvdode.f90:180-201 */
 /* integrate with the global HOST vector u (copied to the slabs and back inside the call) */

@@ -158,3 +158,62 @@ def test_mgpu_host_pipeline_on_slabs_bitwise(gpu_lib, pkg, ref, order, monkeypat
         finally:
             ref.set_threads(1)
         del m
+
+
+def _g_of_t(t):
+    return 1.0 + 0.5 * np.sin(3.0 * t) + 0.25 * t
+
+
+def test_mgpu_general_operators_on_slabs_bitwise(gpu_lib, pkg, ref):
+    """non-uniform grids (per-cell tables from the GLOBAL edges), x- and t-dependent fluxes on slabs: the general kernels read
+    the neighbour's cells from the exchanged ghost cells and reconstruct them with the neighbour's tables"""
+    # 1D: geometric grid, face coefficient, time factor, rktvd3 and mstvd
+    nglob = 20011
+    g = pkg.hrweno_grids.grid1().geometric(-5.0, 5.0, 1.0002, nglob)
+    u0 = ex1_ic(g.center) + 1e-3 * np.random.default_rng(4).standard_normal(nglob)
+    fc = 1.0 + 0.1 * np.cos(g.edges)
+    for kind in ("rk3", "ms"):
+        rfv = ref.FV(pkg.fv.make_desc(nglob, k=3, width=[g.width]))
+        rfv.set_xedges(0, g.edges)
+        rfv.set_flux_coef(0, fc, None)
+        rfv.set_flux_time_fn(_g_of_t)
+        rode = ref.mstvd(rfv) if kind == "ms" else ref.rktvd(rfv, 3)
+        ur, dt = u0.copy(), 2e-5
+        tr = rode.integrate(ur, 0.0, _steps_to(0.0, dt, 9), dt)
+        for world in _counts(gpu_lib):
+            m = pkg.mgpu.MultiGPU(pkg.fv.make_desc(nglob, k=3, width=[g.width]), world)
+            m.set_xedges(0, g.edges)
+            m.set_flux_coef(0, fc, None)
+            m.set_flux_time_fn(_g_of_t)
+            m.mstvd() if kind == "ms" else m.rktvd(3)
+            u = u0.copy()
+            t = m.integrate(u, 0.0, _steps_to(0.0, dt, 9), dt)
+            assert t == tr and np.array_equal(u, ur), f"1D general {kind} world={world}: {np.max(np.abs(u - ur)):.3e}"
+            del m
+    # 2D: example2 on geometric x geometric grids with the growth terms of example2:140,153 and a time factor
+    n1, n2 = 150, 131
+    g1, g2 = pkg.hrweno_grids.grid1().geometric(0.0, 10.0, 1.01, n1), pkg.hrweno_grids.grid1().geometric(0.0, 10.0, 1.007, n2)
+    v0 = (ex2_ic(g1.center, g2.center) + 1e-3 * np.random.default_rng(6).standard_normal((n2, n1))).reshape(-1)
+    kw = dict(flux_model=1, bc=1, width=[g1.width, g2.width])
+
+    def setup(f):
+        f.set_xedges(0, g1.edges)
+        f.set_xedges(1, g2.edges)
+        f.set_flux_coef(0, g1.edges**2, 1.0 + 0.01 * g2.center)
+        f.set_flux_coef(1, g2.edges, g1.center)
+        f.set_flux_time_fn(_g_of_t)
+
+    for kind in ("ms", "rk3"):
+        rfv = ref.FV(pkg.fv.make_desc((n1, n2), **kw))
+        setup(rfv)
+        rode = ref.mstvd(rfv) if kind == "ms" else ref.rktvd(rfv, 3)
+        vr, dt = v0.copy(), 1e-4
+        tr = rode.integrate(vr, 0.0, _steps_to(0.0, dt, 8), dt)
+        for world in _counts(gpu_lib):
+            m = pkg.mgpu.MultiGPU(pkg.fv.make_desc((n1, n2), **kw), world)
+            setup(m)
+            m.mstvd() if kind == "ms" else m.rktvd(3)
+            v = v0.copy()
+            t = m.integrate(v, 0.0, _steps_to(0.0, dt, 8), dt)
+            assert t == tr and np.array_equal(v, vr), f"2D general {kind} world={world}: {np.max(np.abs(v - vr)):.3e}"
+            del m
