@@ -103,6 +103,94 @@ module hrweno_b200_c
          type(c_ptr), value :: face_coef, cross_coef
          integer(c_int) :: st
       end function
+      ! t-dependent flux f = ((model(v)*cross)*face)*g(t); g is a bind(C) function `real(c_double) function g(ctx, t)` passed
+      ! with c_funloc (c_null_funptr removes the factor)
+      function hrweno_fv_set_flux_time_fn(fv, g, ctx) bind(c, name="hrweno_fv_set_flux_time_fn") result(st)
+         import :: c_ptr, c_funptr, c_int
+         type(c_ptr), value :: fv
+         type(c_funptr), value :: g
+         type(c_ptr), value :: ctx
+         integer(c_int) :: st
+      end function
+      ! ---- one process, N GPUs: the GLOBAL descriptor, slabs / halos / alpha reduction inside the library ----
+      function hrweno_mgpu_create(out, desc, ngpus, devices) bind(c, name="hrweno_mgpu_create") result(st)
+         import :: c_ptr, c_int, hrweno_fv_desc
+         type(c_ptr), intent(out) :: out
+         type(hrweno_fv_desc), intent(in) :: desc
+         integer(c_int), value :: ngpus          ! <= 0: all visible devices
+         type(c_ptr), value :: devices           ! c_null_ptr: devices 0 .. ngpus-1
+         integer(c_int) :: st
+      end function
+      subroutine hrweno_mgpu_destroy(m) bind(c, name="hrweno_mgpu_destroy")
+         import :: c_ptr
+         type(c_ptr), value :: m
+      end subroutine
+      function hrweno_mgpu_ngpus(m) bind(c, name="hrweno_mgpu_ngpus") result(n)
+         import :: c_ptr, c_int
+         type(c_ptr), value :: m
+         integer(c_int) :: n
+      end function
+      function hrweno_mgpu_rktvd(m, order) bind(c, name="hrweno_mgpu_rktvd") result(st)
+         import :: c_ptr, c_int
+         type(c_ptr), value :: m
+         integer(c_int), value :: order
+         integer(c_int) :: st
+      end function
+      function hrweno_mgpu_mstvd(m) bind(c, name="hrweno_mgpu_mstvd") result(st)
+         import :: c_ptr, c_int
+         type(c_ptr), value :: m
+         integer(c_int) :: st
+      end function
+      function hrweno_mgpu_integrate(m, u, t, tout, dt, itask) bind(c, name="hrweno_mgpu_integrate") result(st)
+         import :: c_ptr, c_int, c_double
+         type(c_ptr), value :: m
+         real(c_double), intent(inout) :: u(*)   ! the global vector, storage order of example2:50
+         real(c_double), intent(inout) :: t
+         real(c_double), value :: tout, dt
+         integer(c_int), value :: itask
+         integer(c_int) :: st
+      end function
+      function hrweno_mgpu_upload(m, u) bind(c, name="hrweno_mgpu_upload") result(st)
+         import :: c_ptr, c_int, c_double
+         type(c_ptr), value :: m
+         real(c_double), intent(in) :: u(*)
+         integer(c_int) :: st
+      end function
+      function hrweno_mgpu_integrate_resident(m, t, tout, dt, itask) bind(c, name="hrweno_mgpu_integrate_resident") result(st)
+         import :: c_ptr, c_int, c_double
+         type(c_ptr), value :: m
+         real(c_double), intent(inout) :: t
+         real(c_double), value :: tout, dt
+         integer(c_int), value :: itask
+         integer(c_int) :: st
+      end function
+      function hrweno_mgpu_download(m, u) bind(c, name="hrweno_mgpu_download") result(st)
+         import :: c_ptr, c_int, c_double
+         type(c_ptr), value :: m
+         real(c_double), intent(inout) :: u(*)
+         integer(c_int) :: st
+      end function
+      function hrweno_mgpu_max_wavespeed(m, alpha, install) bind(c, name="hrweno_mgpu_max_wavespeed") result(st)
+         import :: c_ptr, c_int, c_double
+         type(c_ptr), value :: m
+         real(c_double), intent(out) :: alpha
+         integer(c_int), value :: install
+         integer(c_int) :: st
+      end function
+      function hrweno_mgpu_set_xedges(m, axis, xedges) bind(c, name="hrweno_mgpu_set_xedges") result(st)
+         import :: c_ptr, c_int, c_double
+         type(c_ptr), value :: m
+         integer(c_int), value :: axis
+         real(c_double), intent(in) :: xedges(*) ! global edges(0:n(axis))
+         integer(c_int) :: st
+      end function
+      function hrweno_mgpu_set_flux_coef(m, axis, face_coef, cross_coef) bind(c, name="hrweno_mgpu_set_flux_coef") result(st)
+         import :: c_ptr, c_int
+         type(c_ptr), value :: m
+         integer(c_int), value :: axis
+         type(c_ptr), value :: face_coef, cross_coef
+         integer(c_int) :: st
+      end function
       function hrweno_rktvd_create_fused(out, fv, order) bind(c, name="hrweno_rktvd_create_fused") result(st)
          import :: c_ptr, c_int
          type(c_ptr), intent(out) :: out

@@ -114,9 +114,18 @@ static int mgpu_create(Mgpu **out, const hrweno_fv_desc *desc, int ngpus, const 
          int can = 0;
          HRW_CUDA(cudaDeviceCanAccessPeer(&can, m->dev[r], m->dev[q]));
          if (!can) return fail(HRWENO_ECOMM, "hrweno_mgpu_create: no peer access between devices " + std::to_string(m->dev[r]) + " and " + std::to_string(m->dev[q]));
-         cudaError_t e = cudaDeviceEnablePeerAccess(m->dev[q], 0);
-         if (e == cudaErrorPeerAccessAlreadyEnabled) cudaGetLastError();
-         else if (e != cudaSuccess) return cuda_fail(e, "cudaDeviceEnablePeerAccess", __FILE__, __LINE__);
+         {  // peer access is a per-process, per-pair switch: enable each pair once (a second group reuses it)
+            static std::mutex pm;
+            static std::vector<std::pair<int, int>> enabled;
+            std::lock_guard<std::mutex> lock(pm);
+            const std::pair<int, int> pr(m->dev[r], m->dev[q]);
+            if (std::find(enabled.begin(), enabled.end(), pr) == enabled.end()) {
+               cudaError_t e = cudaDeviceEnablePeerAccess(m->dev[q], 0);
+               if (e == cudaErrorPeerAccessAlreadyEnabled) cudaGetLastError(); // enabled by the caller's own code
+               else if (e != cudaSuccess) return cuda_fail(e, "cudaDeviceEnablePeerAccess", __FILE__, __LINE__);
+               enabled.push_back(pr);
+            }
+         }
       }
    }
    const int64_t base = nsplit / ngpus, rem = nsplit % ngpus;

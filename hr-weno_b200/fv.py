@@ -88,7 +88,11 @@ class FV:
     def set_xedges(self, axis, xedges):
         """weno(ncells, k, eps, xedges) for the sweep along `axis` (weno.f90:100-112): per-cell tables cnu"""
         xe = np.ascontiguousarray(xedges, dtype=np.float64)
-        if xe.size != self.desc.n[axis] + 1:  # weno.f90:101-108
+        # slabs: along the decomposed (slowest) axis the GLOBAL edges are passed (the tables of the slab's edge cells and of
+        # the neighbour cells its interface faces need depend on edges beyond the slab)
+        dec = self.desc.nranks > 1 and axis == self.desc.ndim - 1
+        want = (self.desc.global_n if dec else self.desc.n[axis]) + 1
+        if xe.size != want:  # weno.f90:101-108
             raise _abi.HrwenoError(_abi.EINVAL, "Invalid input 'xedges'. Valid range: size(xedges) = ncells + 1.")
         _abi.check(_abi.lib().hrweno_fv_set_xedges(self._h, axis, xe.ctypes.data))
 
