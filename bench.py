@@ -140,7 +140,8 @@ def run_reference(args, rank, world):
         t = ode.integrate(u, t, 1e9, dt, itask=2)
     el = time.perf_counter() - t0
     value = n * 3 * args.steps / el
-    sample = f"2^24 cells x {args.steps} RK3 steps per run (1/16 of the 2^28-cell workload), OpenMP over cells"
+    sample = (f"2^24 cells x {args.steps} RK3 steps per run (1/16 of the 2^28-cell workload; a per-cell rate: u, ui, udot are 128 MiB "
+              f"each, beyond the host's last-level cache, like the full size), OpenMP over cells on {cores} threads")
     print(json.dumps({
         "impl": "reference", "metric": "WENO5+RK3 cell-updates/s", "value": value, "unit": "cell-updates/s",
         "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * el / args.steps,
@@ -202,7 +203,8 @@ def cpu_baseline_leg(pkg):
         t = ode.integrate(u, t, 1e9, dt, itask=2)
     el = time.perf_counter() - t0
     return {"value": n * 3 * steps / el, "unit": "cell-updates/s", "cores": 1, "kind": "port",
-            "sample": f"2^22 cells x {steps} RK3 steps, 1 thread (C restatement of the reference, not gfortran)"}
+            "sample": f"2^22 cells x {steps} RK3 steps, 1 thread (C restatement of the reference, not gfortran); u, ui, udot are 32 MiB "
+                      "each: a streaming working set at or beyond the host's last-level cache, as at the full 2^28 cells"}
 
 
 def main():
