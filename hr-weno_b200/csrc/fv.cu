@@ -5,6 +5,7 @@
 #include <float.h>
 
 #include <algorithm>
+#include <cstdlib>
 #include <cstring>
 #include <string>
 #include <new>
@@ -482,6 +483,7 @@ static int fv1d_flux_kind(const hrweno_fv_desc &d) {
 // when it covers the row with fewer (partly idle) thread runs, e.g. 4096-cell rows: 9 x 504 instead of 5 x 1016
 static int fv1d_half_tile(const Fv *fv) {
    if (fv1d_flux_kind(fv->d) != FK_BURGERS_GODUNOV || !fv->width_dict) return 0;
+   if (const char *e = std::getenv("HRWENO_FORCE_HALF_TILE")) return std::atoi(e) != 0; // tuning A/B only
    const int64_t t0 = fv1d_tile_cells(fv->d.mode, 0), t1 = fv1d_tile_cells(fv->d.mode, 1);
    const double slots0 = (double)((fv->n0 + t0 - 1) / t0) * (double)fv1d_tile_slots(fv->d.mode, 0);
    const double slots1 = (double)((fv->n0 + t1 - 1) / t1) * (double)fv1d_tile_slots(fv->d.mode, 1);

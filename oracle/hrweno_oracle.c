@@ -11,15 +11,26 @@
  *
  * Every routine cites the reference lines it follows (paths relative to /root/reference).
  */
-#include "hrweno_oracle.h"
-
 #include <float.h>
 #include <math.h>
+#include <stdint.h>
 #include <stdlib.h>
 #include <string.h>
 #ifdef _OPENMP
 #include <omp.h>
 #endif
+
+/* REAL32 build (src/hrweno_kinds.F90:9-17: `rk` is a compile-time switch of the WHOLE reference).  The same source with
+ * every `double` of this file AND of the two headers below read as `float`, built with -fsingle-precision-constant so that
+ * a literal like 11.0/6 is the float quotient `11.0_rk/6` is for rk = real32 (x86-64 SSE evaluates float expressions in
+ * float: FLT_EVAL_METHOD == 0).  The system headers above keep their prototypes; copysign's detour through double only
+ * carries a sign.  -> oracle/libhrweno_oracle_f32.so, same symbol names, float in every signature and in hrweno_fv_desc. */
+#ifdef HRW_REAL32
+#define double float
+#undef DBL_EPSILON
+#define DBL_EPSILON FLT_EPSILON
+#endif
+#include "hrweno_oracle.h"
 
 static int g_threads = 1;
 
