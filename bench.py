@@ -532,13 +532,55 @@ def main():
                 "parity_check": {"rows": prow, "steps": kw + ksteps, "max_normwise": worst, "tolerance": 1e-12, "ok": bool(worst <= 1e-12),
                                  "what": "first rows of every (k, order) run vs the CPU oracle"}}
 
+    def extra_f32():
+        """REAL32 build of the path (hrweno_kinds.F90:9-17): cfg3's problem at 2^26 cells in float32 on the general kernels
+        (reference order, not the tuned TMA kernels) -- a coverage number, never the headline"""
+        if rank != 0:
+            return None
+        nf = 1 << 26
+        e = (np.float32(XMIN) + (np.float32(XMAX) - np.float32(XMIN)) / np.float32(nf) * np.arange(nf + 1, dtype=np.float32)).astype(np.float32)
+        x = (e[:-1] + e[1:]) / np.float32(2)
+        u0 = (np.clip(1.0 + (-1.5 / 6.0) * (x.astype(np.float64) + 4.0), -0.5, 1.0) + 1e-3 * np.random.default_rng(12345).standard_normal(nf)).astype(np.float32)
+        ode = pkg.real32.rktvd(pkg.real32.FV(pkg.real32.make_desc(nf, k=3, eps=1e-6, linear=(XMIN, XMAX))), 3)
+        ud = torch.from_numpy(u0).cuda()
+        dtf = 0.1 * (XMAX - XMIN) / nf
+        kw, ks = 2, 10
+        t = ode.integrate_dev(ud.data_ptr(), 0.0, steps_to(0.0, dtf, kw), dtf, 1, stream)
+        tw = t
+        l0 = ode.launches
+        sec, clocks = timed_max(lambda: ode.integrate_dev(ud.data_ptr(), tw, float(np.float32(tw) + np.float32(ks - 0.5) * np.float32(dtf)), dtf, 1, stream))
+        launches = ode.launches - l0
+        ksteps = launches // 3
+        gbs = nf * 32.0 * ksteps / sec / 1e9  # fp32 halves the bytes: 8 / 12 / 12 B per cell-stage (SURVEY 8d)
+        res = {"workload": "cfg3's problem in REAL32 (rk = real32): 1D Burgers WENO5+Godunov+rktvd(3), 2^26 cells, general kernels (reference order)",
+               "dtype": "f32", "value": nf * 3 * ksteps / sec, "unit": "cell-updates/s", "steps": int(ksteps), "gpu_launches": int(launches),
+               "roofline": {"bound": "hbm", "achieved": gbs, "peak": peaks()[0], "unit": "GB/s", "frac": gbs / peaks()[0], "traffic": None,
+                            "kernel": "fvgen_stage_kernel<3, false, float> (8 / 12 / 12 algorithmic B per cell for the three RK3 stages + 4 B width)"},
+               "clocks": clocks}
+        # parity: the head of the state against the REAL32 oracle on the same initial data for the same steps
+        from oracle import ref32
+        m, mh = 1 << 16, (1 << 16) + 9 * (kw + int(ksteps)) + 32
+        rx = (np.float32(XMAX) - np.float32(XMIN)) / np.float32(nf)
+        eh = (np.float32(XMIN) + rx * np.arange(mh + 1, dtype=np.float32)).astype(np.float32)
+        rode = ref32.rktvd(ref32.FV(pkg.real32.make_desc(mh, k=3, eps=1e-6, width=[(eh[1:] - eh[:-1]).astype(np.float32)])), 3)
+        ur, tr = u0[:mh].copy(), 0.0
+        tr = rode.integrate(ur, tr, steps_to(0.0, dtf, kw), dtf)
+        tr = rode.integrate(ur, tr, float(np.float32(tr) + np.float32(ks - 0.5) * np.float32(dtf)), dtf)
+        got = ud[:m].cpu().numpy()
+        res["parity_check"] = {"cells": m, "steps": kw + int(ksteps), "bit_identical": bool(np.array_equal(got, ur[:m])),
+                               "max_normwise": float(np.max(np.abs(got - ur[:m])) / np.max(np.abs(ur[:m]))),
+                               "what": "first cells of the timed state vs the REAL32 build of the CPU oracle"}
+        del ode, ud
+        torch.cuda.empty_cache()
+        return res
+
     K = args.steps
     main_m = measure(args.mode, K, args.warmup, True)
     other = "strict" if args.mode == "fast" else "fast"
     other_m = measure(other, max(2, min(K, 5)), 3, False) if not args.single_mode else None
     extra = None
     if not args.no_extra_configs:
-        extra = {"cfg4": extra_cfg4(args.mode), "cfg5": extra_cfg5(args.mode)}
+        extra = {"cfg4": extra_cfg4(args.mode), "cfg5": extra_cfg5(args.mode), "real32": extra_f32()}
 
     if rank != 0:
         if world > 1:

@@ -9,12 +9,13 @@ Module names follow the reference's Fortran modules:
     hrweno_tvdode  (src/hrweno_tvdode.f90)  -> rktvd, mstvd
     hrweno_grids   (src/hrweno_grids.f90)   -> grid1 (host side, like the reference)
     fv                                      -> the example `rhs` as a fused device operator
+    real32                                  -> the REAL32 build of the path (hrweno_kinds.F90:9-17): weno, FV, rktvd, mstvd on float32
     mgpu                                    -> the same over the GPUs of one box from ONE process (hrweno_mgpu_*)
 All compute goes through the C ABI into CUDA kernels; nothing here computes on the CPU
 except grid set-up, which the north star keeps on the host.
 """
 from . import _abi
 from ._abi import HrwenoError, lib
-from . import hrweno_grids, hrweno_weno, hrweno_fluxes, hrweno_tvdode, fv, slab, mgpu
+from . import hrweno_grids, hrweno_weno, hrweno_fluxes, hrweno_tvdode, fv, slab, mgpu, real32
 
-__all__ = ["_abi", "HrwenoError", "lib", "hrweno_grids", "hrweno_weno", "hrweno_fluxes", "hrweno_tvdode", "fv", "slab", "mgpu"]
+__all__ = ["_abi", "HrwenoError", "lib", "hrweno_grids", "hrweno_weno", "hrweno_fluxes", "hrweno_tvdode", "fv", "slab", "mgpu", "real32"]

@@ -52,6 +52,34 @@ class FvDesc(C.Structure):
     ]
 
 
+class FvDesc32(C.Structure):
+    """struct hrweno_fv_desc_f32 (include/hrweno_b200.h): the descriptor of the REAL32 build (hrweno_kinds.F90:9-17)."""
+
+    _fields_ = [
+        ("abi_version", C.c_int32),
+        ("ndim", C.c_int32),
+        ("n", C.c_int64 * 2),
+        ("rows", C.c_int64),
+        ("k", C.c_int32),
+        ("flux_model", C.c_int32),
+        ("flux_scheme", C.c_int32),
+        ("bc", C.c_int32),
+        ("grid_kind", C.c_int32),
+        ("mode", C.c_int32),
+        ("eps", C.c_float),
+        ("flux_coef", C.c_float * 2),
+        ("alpha", C.c_float),
+        ("xmin", C.c_float),
+        ("xmax", C.c_float),
+        ("width", C.POINTER(C.c_float) * 2),
+        ("rank", C.c_int32),
+        ("nranks", C.c_int32),
+        ("global_n", C.c_int64),
+        ("global_offset", C.c_int64),
+    ]
+
+
+TIME_FN32 = C.CFUNCTYPE(C.c_float, C.c_void_p, C.c_float)
 FLUX_FN = C.CFUNCTYPE(C.c_double, C.c_void_p, C.c_double, c_double_p, C.c_int, C.c_double)
 RHS_FN = C.CFUNCTYPE(None, C.c_void_p, C.c_double, C.c_int64, C.c_void_p, C.c_void_p, C.c_void_p)
 RHS_HOST_FN = C.CFUNCTYPE(None, C.c_void_p, C.c_double, C.c_int64, c_double_p, c_double_p)
@@ -141,6 +169,32 @@ PROTOTYPES = {
     "hrweno_mgpu_set_alpha": (C.c_int, [C.c_void_p, C.c_double]),
     "hrweno_mgpu_fevals": (C.c_int64, [C.c_void_p]),
     "hrweno_mgpu_launches": (C.c_int64, [C.c_void_p]),
+    "hrweno_weno_f32_create": (C.c_int, [C.POINTER(C.c_void_p), C.c_int64, C.c_int, C.c_float, C.c_void_p]),
+    "hrweno_weno_f32_destroy": (None, [C.c_void_p]),
+    "hrweno_weno_f32_reconstruct": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),
+    "hrweno_weno_f32_reconstruct_dev": (
+        C.c_int,
+        [C.c_void_p, C.c_int64, C.c_void_p, C.c_int64, C.c_int64, C.c_void_p, C.c_void_p, C.c_int64, C.c_void_p],
+    ),
+    "hrweno_fv_f32_create": (C.c_int, [C.POINTER(C.c_void_p), C.POINTER(FvDesc32)]),
+    "hrweno_fv_f32_destroy": (None, [C.c_void_p]),
+    "hrweno_fv_f32_neq": (C.c_int64, [C.c_void_p]),
+    "hrweno_fv_f32_rhs": (C.c_int, [C.c_void_p, C.c_float, C.c_void_p, C.c_void_p]),
+    "hrweno_fv_f32_rhs_dev": (C.c_int, [C.c_void_p, C.c_float, C.c_void_p, C.c_void_p, C.c_void_p]),
+    "hrweno_fv_f32_set_xedges": (C.c_int, [C.c_void_p, C.c_int, C.c_void_p]),
+    "hrweno_fv_f32_set_flux_coef": (C.c_int, [C.c_void_p, C.c_int, C.c_void_p, C.c_void_p]),
+    "hrweno_fv_f32_set_flux_time_fn": (C.c_int, [C.c_void_p, TIME_FN32, C.c_void_p]),
+    "hrweno_rktvd_f32_create_fused": (C.c_int, [C.POINTER(C.c_void_p), C.c_void_p, C.c_int]),
+    "hrweno_mstvd_f32_create_fused": (C.c_int, [C.POINTER(C.c_void_p), C.c_void_p]),
+    "hrweno_ode_f32_destroy": (None, [C.c_void_p]),
+    "hrweno_ode_f32_integrate": (C.c_int, [C.c_void_p, C.c_void_p, C.POINTER(C.c_float), C.c_float, C.c_float, C.c_int]),
+    "hrweno_ode_f32_integrate_dev": (
+        C.c_int,
+        [C.c_void_p, C.c_void_p, C.POINTER(C.c_float), C.c_float, C.c_float, C.c_int, C.c_void_p],
+    ),
+    "hrweno_ode_f32_fevals": (C.c_int64, [C.c_void_p]),
+    "hrweno_ode_f32_istate": (C.c_int, [C.c_void_p]),
+    "hrweno_ode_f32_launches": (C.c_int64, [C.c_void_p]),
     "hrweno_host_alloc": (C.c_int, [C.POINTER(C.c_void_p), C.c_int64]),
     "hrweno_host_free": (None, [C.c_void_p]),
 }

@@ -289,6 +289,51 @@ int64_t hrweno_ode_neq(const hrweno_ode *ode);
 /* number of kernels launched by this object so far (bench bookkeeping) */
 int64_t hrweno_ode_launches(const hrweno_ode *ode);
 
+/* ---- REAL32 (src/hrweno_kinds.F90:9-17) -------------------------------------------------------------------------
+ * `rk` is a compile-time switch of the whole reference: built with -DREAL32 every real of the path (state, widths, tables,
+ * eps, t, dt) is single precision.  These entry points are that build of the path: same semantics as their fp64
+ * counterparts above with float in every signature.  One GPU; the reference's operation order in separately rounded float
+ * operations (the general kernels instantiated for float), bit-identical to the REAL32 build of the oracle; the
+ * integrators work in place on the caller's dense vector.  (REAL128 has no GPU type.) */
+typedef struct hrweno_fv_desc_f32 {
+   int32_t abi_version, ndim;
+   int64_t n[2];
+   int64_t rows;
+   int32_t k, flux_model, flux_scheme, bc, grid_kind, mode; /* mode is ignored: always the reference order */
+   float eps;
+   float flux_coef[2];
+   float alpha;
+   float xmin, xmax;
+   const float *width[2];
+   int32_t rank, nranks; /* must describe one GPU (nranks <= 1) */
+   int64_t global_n, global_offset;
+} hrweno_fv_desc_f32;
+typedef struct hrweno_weno_f32 hrweno_weno_f32;
+typedef struct hrweno_fv_f32 hrweno_fv_f32;
+typedef struct hrweno_ode_f32 hrweno_ode_f32;
+typedef float (*hrweno_time_fn_f32)(void *ctx, float t);
+int hrweno_weno_f32_create(hrweno_weno_f32 **out, int64_t ncells, int k, float eps, const float *xedges); /* weno.f90:54-127 */
+void hrweno_weno_f32_destroy(hrweno_weno_f32 *w);
+int hrweno_weno_f32_reconstruct(const hrweno_weno_f32 *w, const float *v, float *vl, float *vr);          /* weno.f90:129-219, host */
+int hrweno_weno_f32_reconstruct_dev(const hrweno_weno_f32 *w, int64_t rows, const float *v_dev, int64_t ldv, int64_t incv,
+                                    float *vl_dev, float *vr_dev, int64_t ldo, void *stream);
+int hrweno_fv_f32_create(hrweno_fv_f32 **out, const hrweno_fv_desc_f32 *desc);
+void hrweno_fv_f32_destroy(hrweno_fv_f32 *fv);
+int64_t hrweno_fv_f32_neq(const hrweno_fv_f32 *fv);
+int hrweno_fv_f32_rhs(hrweno_fv_f32 *fv, float t, const float *v, float *vdot); /* example1:72-109 / example2:73-129, host */
+int hrweno_fv_f32_rhs_dev(hrweno_fv_f32 *fv, float t, const float *v_dev, float *vdot_dev, void *stream);
+int hrweno_fv_f32_set_xedges(hrweno_fv_f32 *fv, int axis, const float *xedges);
+int hrweno_fv_f32_set_flux_coef(hrweno_fv_f32 *fv, int axis, const float *face_coef, const float *cross_coef);
+int hrweno_fv_f32_set_flux_time_fn(hrweno_fv_f32 *fv, hrweno_time_fn_f32 g, void *ctx);
+int hrweno_rktvd_f32_create_fused(hrweno_ode_f32 **out, hrweno_fv_f32 *fv, int order); /* tvdode.f90:69-95 */
+int hrweno_mstvd_f32_create_fused(hrweno_ode_f32 **out, hrweno_fv_f32 *fv);            /* tvdode.f90:180-201 */
+void hrweno_ode_f32_destroy(hrweno_ode_f32 *ode);
+int hrweno_ode_f32_integrate(hrweno_ode_f32 *ode, float *u, float *t, float tout, float dt, int itask); /* tvdode.f90:97-178, 203-271 */
+int hrweno_ode_f32_integrate_dev(hrweno_ode_f32 *ode, float *u_dev, float *t, float tout, float dt, int itask, void *stream);
+int64_t hrweno_ode_f32_fevals(const hrweno_ode_f32 *ode);
+int hrweno_ode_f32_istate(const hrweno_ode_f32 *ode);
+int64_t hrweno_ode_f32_launches(const hrweno_ode_f32 *ode);
+
 /* ---- pinned host memory helpers (so host-buffer calls reach PCIe speed) ---- */
 int hrweno_host_alloc(void **out, int64_t bytes);
 void hrweno_host_free(void *p);

@@ -14,6 +14,23 @@ import math
 
 import numpy as np
 
+def _real(a):
+    """kind of the computation: real32 when the data are float32 (the REAL32 build, hrweno_kinds.F90:9-17), else real64"""
+    return np.float32 if getattr(a, "dtype", None) == np.float32 else np.float64
+
+
+def tables(k, T=np.float64):
+    """d and c(:, r) of weno.f90:12-21 as literals of kind T: 11.0_rk/6 is the quotient of T, 0.3_rk the nearest T"""
+    q = lambda a, b: T(a) / T(b)  # noqa: E731
+    d = {1: [T(1)], 2: [q(2, 3), q(1, 3)], 3: [T(0.3), T(0.6), T(0.1)]}[k]
+    c = {
+        1: [[T(1)], [T(1)]],
+        2: [[q(3, 2), q(-1, 2)], [q(1, 2), q(1, 2)], [q(-1, 2), q(3, 2)]],
+        3: [[q(11, 6), q(-7, 6), q(1, 3)], [q(1, 3), q(5, 6), q(-1, 6)], [q(-1, 6), q(5, 6), q(1, 3)], [q(1, 3), q(-7, 6), q(11, 6)]],
+    }[k]
+    return np.array(d, dtype=T), np.array(c, dtype=T)
+
+
 # src/hrweno_weno.f90:12-21 -- c[k][r+1] is the column c(:, r)
 D = {1: np.array([1.0]), 2: np.array([2.0 / 3, 1.0 / 3]), 3: np.array([0.3, 0.6, 0.1])}
 C = {
@@ -32,12 +49,13 @@ C = {
 
 def calc_cnu(xedges, k):
     """src/hrweno_weno.f90:221-297; returns cnu[i-1, r+1, j]."""
-    xedges = np.asarray(xedges, dtype=np.float64)
+    T = _real(np.asarray(xedges))
+    xedges = np.asarray(xedges, dtype=T)
     nc = len(xedges) - 1
     ng = k + 1
     xext = {}
     for i in range(nc + 1):
-        xext[i] = float(xedges[i])
+        xext[i] = T(xedges[i])  # NumPy scalars of kind T: every operation below is rounded to T
     dx = xext[1] - xext[0]
     for i in range(-1, -ng - 1, -1):
         xext[i] = xext[i + 1] - dx
@@ -46,22 +64,22 @@ def calc_cnu(xedges, k):
         xext[i] = xext[i - 1] + dx
     xl = lambda m: xext[m - 1]  # noqa: E731
     xr = lambda m: xext[m]  # noqa: E731
-    cnu = np.zeros((nc, k + 1, k))
+    cnu = np.zeros((nc, k + 1, k), dtype=T)
     for i in range(1, nc + 1):
         for r in range(-1, k):
             for j in range(k):
-                sum2 = 0.0
+                sum2 = T(0)
                 for m in range(j + 1, k + 1):
-                    prod2 = 1.0
+                    prod2 = T(1)
                     for l in range(k + 1):
                         if l == m:
                             continue
                         prod2 = prod2 * (xl(i - r + m) - xl(i - r + l))
-                    sum1 = 0.0
+                    sum1 = T(0)
                     for l in range(k + 1):
                         if l == m:
                             continue
-                        prod1 = 1.0
+                        prod1 = T(1)
                         for q in range(k + 1):
                             if q == m or q == l:
                                 continue
@@ -73,8 +91,12 @@ def calc_cnu(xedges, k):
 
 
 def reconstruct(v, k=3, eps=1e-6, cnu=None):
-    """src/hrweno_weno.f90:129-219, vectorised over cells; returns (vl, vr)."""
-    v = np.asarray(v, dtype=np.float64)
+    """src/hrweno_weno.f90:129-219, vectorised over cells; returns (vl, vr).  float32 data: the REAL32 build."""
+    T = _real(np.asarray(v))
+    v = np.asarray(v, dtype=T)
+    eps = T(eps)
+    if cnu is not None:
+        cnu = np.asarray(cnu, dtype=T)
     nc = v.shape[-1]
     g = k - 1
     pad = [(0, 0)] * (v.ndim - 1) + [(g, g)]
@@ -83,14 +105,15 @@ def reconstruct(v, k=3, eps=1e-6, cnu=None):
     def s(off):  # vext(i+off) for all cells i
         return vext[..., g + off : g + off + nc]
 
-    d = D[k]
+    d, ctab = (D[k], C[k]) if T is np.float64 else tables(k, T)
+    c1312, c14 = T(13) / T(12), T(1) / T(4)
     vrr, vlr = [], []
     for r in range(k):
         sr = np.zeros_like(v)
         sl = np.zeros_like(v)
         for j in range(k):
             if cnu is None:
-                cr, cl = C[k][r + 1][j], C[k][r][j]
+                cr, cl = ctab[r + 1][j], ctab[r][j]
             else:
                 cr, cl = cnu[:, r + 1, j], cnu[:, r, j]
             sr = sr + cr * s(-r + j)  # :179
@@ -103,9 +126,9 @@ def reconstruct(v, k=3, eps=1e-6, cnu=None):
         beta = [(s(1) - s(0)) ** 2, (s(0) - s(-1)) ** 2]
     else:
         beta = [
-            13.0 / 12 * ((s(0) - 2 * s(1)) + s(2)) ** 2 + 1.0 / 4 * ((3 * s(0) - 4 * s(1)) + s(2)) ** 2,
-            13.0 / 12 * ((s(-1) - 2 * s(0)) + s(1)) ** 2 + 1.0 / 4 * (s(-1) - s(1)) ** 2,
-            13.0 / 12 * ((s(-2) - 2 * s(-1)) + s(0)) ** 2 + 1.0 / 4 * ((s(-2) - 4 * s(-1)) + 3 * s(0)) ** 2,
+            c1312 * ((s(0) - 2 * s(1)) + s(2)) ** 2 + c14 * ((3 * s(0) - 4 * s(1)) + s(2)) ** 2,
+            c1312 * ((s(-1) - 2 * s(0)) + s(1)) ** 2 + c14 * (s(-1) - s(1)) ** 2,
+            c1312 * ((s(-2) - 2 * s(-1)) + s(0)) ** 2 + c14 * ((s(-2) - 4 * s(-1)) + 3 * s(0)) ** 2,
         ]
     den = [(eps + b) ** 2 for b in beta]
     alfa = [d[r] / den[r] for r in range(k)]
@@ -211,6 +234,8 @@ class RK:
         self.fu, self.order, self.fevals, self.istate = fu, order, 0, 1
 
     def integrate(self, u, t, tout, dt, itask=1):
+        T = _real(np.asarray(u))
+        t, tout, dt = T(t), T(tout), T(dt)  # real(rk) :: t, tout, dt (tvdode.f90:107-110)
         if self.istate < 1 or is_done(t, tout, dt):
             return u, t
         fu = self.fu
@@ -240,6 +265,8 @@ class MS:
         self.uold, self.udotold = [None] * 4, [None] * 4
 
     def integrate(self, u, t, tout, dt):
+        T = _real(np.asarray(u))
+        t, tout, dt = T(t), T(tout), T(dt)
         if self.istate < 1 or is_done(t, tout, dt):
             return u, t
         if self.istate == 1:
