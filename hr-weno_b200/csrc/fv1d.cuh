@@ -32,6 +32,11 @@
 #ifndef HRW_STAGE_W
 #define HRW_STAGE_W 1 // 1: the width indices of the tile travel with the tile's bulk copies (0: global loads per thread)
 #endif
+#ifndef HRW_NBUF
+#define HRW_NBUF 2 // staged-tile buffers of the TMA pipeline: tile it + NBUF - 1 is in flight while tile it is computed.
+                   // Measured with 3 (profiles/r2o_k2_three_tile_buffers_ab.txt): no gain for k = 3 (0.794 vs 0.797) nor for the
+                   // pure streaming k = 1 / rktvd1 stage (0.59 vs 0.60): the prefetch depth is not what limits either
+#endif
 #ifndef HRW_WARP_TILES
 #define HRW_WARP_TILES 0 // 1: every warp overlaps its neighbours by one thread run and exchanges by shuffles (no CTA barrier per
                          // tile).  Measured (profiles/r1_variant_sweeps.txt): the barrier stall disappears but 11 % more instructions
@@ -358,15 +363,17 @@ __global__ void __launch_bounds__(NT, HRW_MINB) fv1d_stage_kernel(const Fv1dGeom
    constexpr bool STAGE_A = NEED_A && HRW_STAGE_A;
    constexpr bool STAGE_W = WK == WK_DICT && HRW_STAGE_W;
    constexpr int WROW = ((TILE + 15) / 16) * 16 + 16 + (R % 4 ? 16 : 0); // staged index bytes per tile: from the 16-B boundary at or below its first cell
-   __shared__ __align__(128) double s_v[2][SM_N];
-   __shared__ __align__(128) double s_a[STAGE_A ? 2 : 1][STAGE_A ? TILE : 2];
-   __shared__ __align__(16) unsigned char s_wi[STAGE_W ? 2 : 1][STAGE_W ? WROW : 16];
+   constexpr int NBUF = WT ? 2 : HRW_NBUF; // (the warp-tile variant keeps its two "consumed" barriers)
+   static_assert(NBUF >= 2 && NBUF <= 4, "two to four staged tiles");
+   __shared__ __align__(128) double s_v[NBUF][SM_N];
+   __shared__ __align__(128) double s_a[STAGE_A ? NBUF : 1][STAGE_A ? TILE : 2];
+   __shared__ __align__(16) unsigned char s_wi[STAGE_W ? NBUF : 1][STAGE_W ? WROW : 16];
    __shared__ double s_vr[WT ? 1 : 2][WT ? 1 : NT];
    __shared__ double s_vl[WT ? 1 : 2][WT ? 1 : NT];
    (void)s_vr;
    (void)s_vl;
    __shared__ __align__(16) double2 s_wtab[WK == WK_DICT ? 256 : 1];
-   __shared__ __align__(8) unsigned long long s_bar[4]; // [0], [1]: tile buffer full (TMA complete_tx); [2], [3]: tile buffer consumed
+   __shared__ __align__(8) unsigned long long s_bar[NBUF + 2]; // [0 .. NBUF): tile buffer full (TMA complete_tx); then two "consumed" barriers (warp tiles)
 
    // let the next kernel of the stream be scheduled as soon as SM resources free up (it waits for this grid to
    // complete before reading or writing global data, see griddepcontrol.wait below)
@@ -408,7 +415,7 @@ __global__ void __launch_bounds__(NT, HRW_MINB) fv1d_stage_kernel(const Fv1dGeom
       if constexpr (STAGE_W) tma_bulk_g2s(sw_u32 + (uint32_t)(buf * WROW), g.widx + (c0 & ~15), (uint32_t)WROW, bar_u32 + 8u * buf);
    };
 
-   for (int idx = tid; idx < 2 * SM_N; idx += NT) (&s_v[0][0])[idx] = 0.0; // parts a clipped copy never writes
+   for (int idx = tid; idx < NBUF * SM_N; idx += NT) (&s_v[0][0])[idx] = 0.0; // parts a clipped copy never writes
    // stage coefficient with the sign of the divergence and, for Burgers/Godunov, the flux's exact 1/2 folded in:
    // dt*L = dt*(-(1/2) q) = (-dt/2)*q bit for bit (power-of-two scaling commutes with rounding)
    const double lscale = FK == FK_BURGERS_GODUNOV ? -0.5 : -1.0;
@@ -423,10 +430,9 @@ __global__ void __launch_bounds__(NT, HRW_MINB) fv1d_stage_kernel(const Fv1dGeom
       }
    asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); // order the generic-proxy zero fill before async-proxy writes
    if (tid == 0) {
-      mbar_init(&s_bar[0], 1);
-      mbar_init(&s_bar[1], 1);
-      mbar_init(&s_bar[2], WARPS);
-      mbar_init(&s_bar[3], WARPS);
+      for (int b = 0; b < NBUF; ++b) mbar_init(&s_bar[b], 1);
+      mbar_init(&s_bar[NBUF], WARPS);
+      mbar_init(&s_bar[NBUF + 1], WARPS);
       asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
    }
    __syncthreads();
@@ -441,31 +447,49 @@ __global__ void __launch_bounds__(NT, HRW_MINB) fv1d_stage_kernel(const Fv1dGeom
    // slabs: the two edge tiles are walked first (logical tile 1 <-> last tile), so the boundary cells reach the
    // neighbour GPU while the bulk of the stage is still being computed
    auto remap = [&](int tc) { return (!g.halo.edge_first || tpr < 3) ? tc : (tc == 1 ? tpr - 1 : (tc == tpr - 1 ? 1 : tc)); };
-   if (tid == 0 && lin < tile_end) issue(row, remap(tcol), 0);
-
-   for (int it = 0; lin < tile_end; ++it, lin += nblk) {
-      const int buf = it & 1;
-      int nrow = row + step_rows, ntcol = tcol + step_cols;
-      if (ntcol >= tpr) {
-         ntcol -= tpr;
-         ++nrow;
+   // (row, tile) of the tile PD iterations ahead: the prefetch cursor.  The first PD tiles are issued before the loop.
+   constexpr int PD = NBUF - 1;
+   int prow = row, ptcol = tcol;
+   auto advance = [&](int &r, int &c) {
+      r += step_rows;
+      c += step_cols;
+      if (c >= tpr) {
+         c -= tpr;
+         ++r;
       }
+   };
+   if (tid == 0) {
+#pragma unroll
+      for (int d = 0; d < PD; ++d) {
+         if (lin + d * nblk < tile_end) issue(prow, remap(ptcol), d);
+         advance(prow, ptcol);
+      }
+   } else {
+#pragma unroll
+      for (int d = 0; d < PD; ++d) advance(prow, ptcol);
+   }
+
+   int buf = 0, pbuf = PD % NBUF; // buffer of this iteration's tile / of the tile the prefetch of this iteration fills
+   uint32_t bphase = 0;           // phase parity of this iteration's buffer (flips every time the ring wraps)
+   for (int it = 0; lin < tile_end; ++it, lin += nblk) {
+      int nrow = row, ntcol = tcol;
+      advance(nrow, ntcol);
       // prefetch the next tile into the other buffer once every warp has taken the previous tile out of it: with the
       // exchange barrier, every thread passed last iteration's barrier after its loads; with warp tiles, each warp
       // arrives on the buffer's "consumed" barrier after its loads
       // The producer (thread 0) never blocks its warp early: it tests the "consumed" barrier here, again after the
       // reconstruction, and waits only at the end of the iteration.
-      bool pending = tid == 0 && lin + nblk < tile_end;
+      bool pending = tid == 0 && lin + PD * nblk < tile_end;
       auto try_issue = [&](bool block) {
          if (!pending) return;
          if (WT && it > 0) {
-            const uint32_t eb = bar_u32 + 16u + 8u * (buf ^ 1), ep = (uint32_t)(((it - 1) >> 1) & 1);
+            const uint32_t eb = bar_u32 + 8u * NBUF + 8u * (buf ^ 1), ep = (uint32_t)(((it - 1) >> 1) & 1);
             if (block)
                mbar_wait(eb, ep);
             else if (!mbar_test(eb, ep))
                return;
          }
-         issue(nrow, remap(ntcol), buf ^ 1);
+         issue(prow, remap(ptcol), pbuf);
          pending = false;
       };
       try_issue(false);
@@ -514,7 +538,7 @@ __global__ void __launch_bounds__(NT, HRW_MINB) fv1d_stage_kernel(const Fv1dGeom
          }
       }
 
-      mbar_wait(bar_u32 + 8u * buf, (uint32_t)((it >> 1) & 1));
+      mbar_wait(bar_u32 + 8u * buf, bphase);
 
       // staged operands of this thread's run (overlap runs own no cells: their slots are never used)
       if (!skip && !edge) {
@@ -584,7 +608,7 @@ __global__ void __launch_bounds__(NT, HRW_MINB) fv1d_stage_kernel(const Fv1dGeom
             for (int j = 0; j < R; ++j) asm volatile("" : "+d"(pf.av[j]));
          }
          __syncwarp();
-         if (lane == 0) mbar_arrive(bar_u32 + 16u + 8u * buf);
+         if (lane == 0) mbar_arrive(bar_u32 + 8u * NBUF + 8u * buf);
       }
       double vl[R], vr[R];
       weno_run<K, R, M>(w + (2 - (K - 1)), g.kc, vl, vr);
@@ -597,11 +621,12 @@ __global__ void __launch_bounds__(NT, HRW_MINB) fv1d_stage_kernel(const Fv1dGeom
       } else {
          // exchange arrays are double buffered by iteration parity: a slot is rewritten two iterations later, after
          // the barrier of the iteration in between, which every reader of the old value has passed
-         s_vr[buf][tid] = vr[R - 1];
-         s_vl[buf][tid] = vl[0];
+         const int xb = it & 1;
+         s_vr[xb][tid] = vr[R - 1];
+         s_vl[xb][tid] = vl[0];
          __syncthreads();
-         vr_left = s_vr[buf][tid > 0 ? tid - 1 : 0];
-         vl_right = s_vl[buf][tid < NT - 1 ? tid + 1 : tid];
+         vr_left = s_vr[xb][tid > 0 ? tid - 1 : 0];
+         vl_right = s_vl[xb][tid < NT - 1 ? tid + 1 : tid];
       }
       if (!skip) {
          if (!edge)
@@ -634,6 +659,12 @@ __global__ void __launch_bounds__(NT, HRW_MINB) fv1d_stage_kernel(const Fv1dGeom
       }
       row = nrow;
       tcol = ntcol;
+      advance(prow, ptcol);
+      if (++buf == NBUF) {
+         buf = 0;
+         bphase ^= 1u;
+      }
+      if (++pbuf == NBUF) pbuf = 0;
    }
 }
 
