@@ -40,22 +40,22 @@ struct Fv2dGeom {
 
 // reconstruction of a run of R cells of a line whose first cell has index i0 on its axis (n cells): uniform tables, or the
 // per-cell tables of weno(ncells, k, eps, xedges) at `cnu` (indices clamped to the axis: cells beyond it are never used)
+// `tab` = the table of the run's first cell inside the per-tile copy of the axis tables in shared memory (cells -1 .. T of
+// the tile, staged by TMA with the tile; consecutive cells KK doubles apart), or nullptr for the uniform tables.
 template <int K, int R, class M>
-__device__ __forceinline__ void run2d(const double *w /* window, cell j at w[2 + j] */, const WenoK &kc, const double *cnu, int64_t i0,
-                                      int64_t n, double *vl, double *vr) {
-   if (cnu == nullptr) {
+__device__ __forceinline__ void run2d(const double *w /* window, cell j at w[2 + j] */, const WenoK &kc, const double *tab, double *vl,
+                                      double *vr) {
+   if (tab == nullptr) {
       weno_run<K, R, M>(w + (2 - (K - 1)), kc, vl, vr);
    } else {
       constexpr int KK = K * (K + 1);
 #pragma unroll
       for (int j = 0; j < R; ++j) {
-         int64_t i = i0 + j; // the tables carry one ghost cell on either side (a slab neighbour's edge cell)
-         i = i < -1 ? -1 : (i > n ? n : i);
-         double ci[KK]; // K(K+1) is even and the table is cudaMalloc'ed: 16-B loads
-         const double2 *c2 = reinterpret_cast<const double2 *>(cnu + i * KK);
+         double ci[KK]; // K(K+1) is even, the staged tables are 16-B aligned
+         const double2 *c2 = reinterpret_cast<const double2 *>(tab + j * KK);
 #pragma unroll
          for (int q = 0; q < KK / 2; ++q) {
-            const double2 t = __ldg(c2 + q);
+            const double2 t = c2[q];
             ci[2 * q] = t.x;
             ci[2 * q + 1] = t.y;
          }
@@ -299,8 +299,12 @@ __global__ void __launch_bounds__(NT, fv2d_min_blocks<M, UPW, NT>())
    double *s_vre = smem + T::OFF_VRE, *s_vle = smem + T::OFF_VLE;
    double *s_wd = smem + T::OFF_W1;
    double *s_ops = smem + T::OFF_OPS;
+   // GEN: per-tile copies of the axis tables cnu(:,:,i), cells -1 .. TX (x1) and -1 .. TY (x2) of the tile
+   constexpr int KK = K * (K + 1);
+   double *s_tab0 = smem + T::OFF_OPS + NSTG * T::OP_DOUBLES, *s_tab1 = s_tab0 + (TX + 2) * KK;
+   (void)s_tab1;
 
-   __shared__ __align__(8) unsigned long long s_bar[3]; // [0], [1]: tile buffer full; [2]: staged operands of this tile full
+   __shared__ __align__(8) unsigned long long s_bar[4]; // [0], [1]: tile buffer full; [2]: staged operands; [3]: staged tables (GEN)
    asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); // the next kernel may be scheduled as SMs free up
    const int tid = threadIdx.x;
    const int total_tiles = g.tiles_x * g.tiles_y;
@@ -322,15 +326,34 @@ __global__ void __launch_bounds__(NT, fv2d_min_blocks<M, UPW, NT>())
       }
    };
 
+   // GEN: the tables of the tile's columns / rows (one ghost cell on either side), two TMA bulk copies; issued for the NEXT
+   // tile right behind the phase barrier of this one (phase B does not read them), so they never sit in front of their use
+   const bool has_tab = GEN && (g.cnu0 != nullptr || g.cnu1 != nullptr);
+   auto issue_tabs = [&](int tile_id) {
+      if constexpr (GEN) {
+         const int ty = tile_id / g.tiles_x, tx = tile_id - ty * g.tiles_x;
+         const int64_t x0 = (int64_t)tx * TX, y0 = (int64_t)ty * TY;
+         const int64_t hx = x0 + TX < g.n0 ? x0 + TX : g.n0, hy = y0 + TY < g.n1 ? y0 + TY : g.n1; // last staged cell (<= n: the ghost table)
+         const uint32_t b0 = g.cnu0 ? (uint32_t)(hx - x0 + 2) * KK * 8u : 0u, b1 = g.cnu1 ? (uint32_t)(hy - y0 + 2) * KK * 8u : 0u;
+         mbar_expect_tx(&s_bar[3], b0 + b1);
+         if (b0) tma_bulk_g2s(s_tab0, g.cnu0 + (x0 - 1) * KK, b0, &s_bar[3]);
+         if (b1) tma_bulk_g2s(s_tab1, g.cnu1 + (y0 - 1) * KK, b1, &s_bar[3]);
+      }
+   };
+
    if (tid == 0) {
       mbar_init(&s_bar[0], 1);
       mbar_init(&s_bar[1], 1);
       mbar_init(&s_bar[2], 1);
+      mbar_init(&s_bar[3], 1);
       asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
    }
    __syncthreads();
    asm volatile("griddepcontrol.wait;" ::: "memory"); // state vectors written by earlier kernels are complete from here on
-   if (tid == 0 && (int)blockIdx.x < total_tiles) issue(blockIdx.x, 0);
+   if (tid == 0 && (int)blockIdx.x < total_tiles) {
+      issue(blockIdx.x, 0);
+      if (has_tab) issue_tabs(blockIdx.x);
+   }
 
    int it_n = 0;
    for (int tile_id = blockIdx.x; tile_id < total_tiles; tile_id += gridDim.x, ++it_n) {
@@ -358,13 +381,48 @@ __global__ void __launch_bounds__(NT, fv2d_min_blocks<M, UPW, NT>())
    }
    double *s_vt = s_v + buf * T::TILE_DOUBLES; // this tile
    mbar_wait(&s_bar[buf], (uint32_t)((it_n >> 1) & 1));
+   if (has_tab) mbar_wait(&s_bar[3], (uint32_t)(it_n & 1));
+   const double *tabx = (GEN && g.cnu0) ? s_tab0 + KK : nullptr; // table of the tile's cell 0 along x1 / x2
+   const double *taby = (GEN && g.cnu1) ? s_tab1 + KK : nullptr;
 
    // ---- phase A: reconstruction items ------------------------------------------------------------------
    // x1-sweep: runs of R cells of a tile row -> shared memory (phase B reads them from other threads)
    constexpr int NXR = (TX / R) * TY, NYR = TX * (TY / R);
    constexpr int YI = NYR / NT; // x2-items (= phase-B items) per thread
    static_assert(NYR % NT == 0, "every thread owns the same number of x2-runs");
-   for (int it = tid; it < NXR; it += NT) {
+   if constexpr (GEN) {
+      // general operators: a thread takes R rows of ONE column, so the column's table is read once per R cells (and by
+      // consecutive lanes for consecutive columns); results land where phase B expects them
+      for (int it = tid; it < TX * (TY / R); it += NT) {
+         const int rb = it / TX, lx = it - rb * TX;
+         double ci[KK];
+         if (tabx) {
+            const double2 *c2 = reinterpret_cast<const double2 *>(tabx + lx * KK);
+#pragma unroll
+            for (int q = 0; q < KK / 2; ++q) {
+               const double2 t = c2[q];
+               ci[2 * q] = t.x;
+               ci[2 * q + 1] = t.y;
+            }
+         }
+#pragma unroll
+         for (int j = 0; j < R; ++j) {
+            const int ly = rb * R + j;
+            const double *cell = s_vt + (ly + H) * T::SP + (H + lx);
+            double w5[5];
+#pragma unroll
+            for (int q = 0; q < 5; ++q) w5[q] = cell[q - 2];
+            double l, r;
+            if (tabx)
+               weno_cell_nonuniform<K, Strict>(ci, w5 + 2, g.kc.eps, l, r);
+            else
+               weno_run<K, 1, M>(w5 + (2 - (K - 1)), g.kc, &l, &r);
+            s_vlx[ly * T::XP + R + lx] = l;
+            s_vrx[ly * T::XP + R + lx] = r;
+         }
+      }
+   }
+   for (int it = tid; it < (GEN ? 0 : NXR); it += NT) {
       const int ly = it / (TX / R);
       const int rx = it - ly * (TX / R);
       const double *base = s_vt + (ly + H) * T::SP + (H + rx * R); // first cell of the run
@@ -377,7 +435,7 @@ __global__ void __launch_bounds__(NT, fv2d_min_blocks<M, UPW, NT>())
          w[j + 1] = t.y;
       }
       double vl[R], vr[R];
-      run2d<K, R, M>(w, g.kc, GEN ? g.cnu0 : nullptr, x0 + rx * R, g.n0, vl, vr);
+      run2d<K, R, M>(w, g.kc, nullptr, vl, vr);
 #pragma unroll
       for (int j = 0; j < R; ++j) {
          if constexpr (!UPW) s_vlx[oidx + j] = vl[j]; // upwind: the left side is never used and is eliminated
@@ -393,27 +451,26 @@ __global__ void __launch_bounds__(NT, fv2d_min_blocks<M, UPW, NT>())
       const double *base;
       int stride;
       double *dst;
-      const double *tab = nullptr; // GEN: the table of this cell's axis
-      int64_t ci = 0, cn = 1;
+      const double *tab = nullptr; // GEN: the staged table of this cell
       if (q < TY) { // x1 line q
          const int cx = high ? TX : -1;
          base = s_vt + (q + H) * T::SP + (H + cx);
          stride = 1;
          dst = (high ? s_vlx : s_vrx) + q * T::XP + R + cx;
-         if constexpr (GEN) tab = g.cnu0, ci = x0 + cx, cn = g.n0;
+         if constexpr (GEN) tab = tabx ? tabx + cx * KK : nullptr;
       } else { // x2 line
          const int lx = q - TY;
          const int cy = high ? TY : -1;
          base = s_vt + (H + cy) * T::SP + (lx + H);
          stride = T::SP;
          dst = high ? s_vle + T::RY * TX + lx : s_vre + lx;
-         if constexpr (GEN) tab = g.cnu1, ci = y0 + cy, cn = g.n1;
+         if constexpr (GEN) tab = taby ? taby + cy * KK : nullptr;
       }
       double w[5];
 #pragma unroll
       for (int j = 0; j < 5; ++j) w[j] = base[(j - 2) * stride];
       double vl1[1], vr1[1];
-      run2d<K, 1, M>(w, g.kc, tab, ci, cn, vl1, vr1);
+      run2d<K, 1, M>(w, g.kc, tab, vl1, vr1);
       *dst = high ? vl1[0] : vr1[0];
    }
    // x2-sweep: item (column lx, run ry) is also this thread's phase-B item, so vl / vr stay in registers; the values the
@@ -428,11 +485,12 @@ __global__ void __launch_bounds__(NT, fv2d_min_blocks<M, UPW, NT>())
       double w[R + 4];
 #pragma unroll
       for (int j = 0; j < R + 4; ++j) w[j] = base[(j - 2) * T::SP];
-      run2d<K, R, M>(w, g.kc, GEN ? g.cnu1 : nullptr, y0 + ry * R, g.n1, vlY[q], vrY[q]);
+      run2d<K, R, M>(w, g.kc, taby ? taby + ry * R * KK : nullptr, vlY[q], vrY[q]);
       s_vre[(ry + 1) * TX + lx] = vrY[q][R - 1];
       if constexpr (!UPW) s_vle[ry * TX + lx] = vlY[q][0];
    }
    __syncthreads();
+   if (has_tab && tid == 0 && tile_id + (int)gridDim.x < total_tiles) issue_tabs(tile_id + gridDim.x);
    if constexpr (NSTG > 0) mbar_wait(&s_bar[2], (uint32_t)(it_n & 1));
 
    // ---- phase B: fluxes, divergence, combination ---------------------------------------------------------
@@ -465,13 +523,14 @@ __global__ void __launch_bounds__(NT, fv2d_min_blocks<M, UPW, NT>())
 #endif
 constexpr int TX2 = HRW_TX2, TY2 = HRW_TY2, NT2 = HRW_NT2;   // large grids
 constexpr int NT2F = 2 * HRW_NT2;                            // threads per tile in fast mode
+constexpr int TX2G = 32, TY2G = 32;                          // general operators on large grids
 constexpr int TX2S = 32, TY2S = 16, NT2S = 128; // small grids (e.g. example2's 250x250): enough tiles to occupy every SM
 
 template <int K, int COMBINE, class M, int UPW, int TX2, int TY2, int NT2, int GEN = 0>
 static int launch2d_t(Fv *fv, const Fv2dGeom &g, const StageArgs &a, cudaStream_t st) {
    using T = Tile2d<TX2, TY2, UPW>;
    constexpr int NSTG = fv2d_nstaged(COMBINE, UPW);
-   constexpr size_t BYTES = T::bytes(NSTG);
+   constexpr size_t BYTES = T::bytes(NSTG) + (GEN ? (size_t)((TX2 + 2) + (TY2 + 2)) * K * (K + 1) * sizeof(double) : 0);
    auto kern = fv2d_stage_kernel<K, COMBINE, M, UPW, TX2, TY2, NT2, GEN>;
    static bool configured[64] = {}; // one flag per instantiation and device (function attributes are per device)
    int dev = 0;
@@ -524,7 +583,9 @@ static int launch2d_u(Fv *fv, const Fv2dGeom &g, const StageArgs &a, cudaStream_
 template <int K, int COMBINE>
 static int launch2d_gen(Fv *fv, const Fv2dGeom &g, const StageArgs &a, cudaStream_t st) {
    if (g.small_tiles) return launch2d_t<K, COMBINE, Strict, 0, TX2S, TY2S, NT2S, 1>(fv, g, a, st);
-   return launch2d_t<K, COMBINE, Strict, 0, TX2, TY2, NT2, 1>(fv, g, a, st);
+   // 32x32 tiles, 256 threads: one column item and one x2-run per thread, ~66 KB of shared memory with the staged tables
+   // (the 64x32 tile of the uniform path would need 119 KB and leave one CTA per SM)
+   return launch2d_t<K, COMBINE, Strict, 0, TX2G, TY2G, NT2, 1>(fv, g, a, st);
 }
 
 template <int K, int COMBINE, class M>
@@ -561,8 +622,9 @@ int fv2d_stage(Fv *fv, int combine, const StageArgs &args, cudaStream_t st) {
    g.n0 = fv->n0;
    g.n1 = fv->n1;
    g.pitch = fv->pitch;
-   g.tiles_x = (int)((fv->n0 + TX2 - 1) / TX2);
-   g.tiles_y = (int)((fv->n1 + TY2 - 1) / TY2);
+   const int txl = fv->general ? TX2G : TX2, tyl = fv->general ? TY2G : TY2; // large-grid tile of this operator
+   g.tiles_x = (int)((fv->n0 + txl - 1) / txl);
+   g.tiles_y = (int)((fv->n1 + tyl - 1) / tyl);
    g.small_tiles = (int64_t)g.tiles_x * g.tiles_y < 2 * 148; // fewer large tiles than two per SM: use the small ones
    if (g.small_tiles) {
       g.tiles_x = (int)((fv->n0 + TX2S - 1) / TX2S);
