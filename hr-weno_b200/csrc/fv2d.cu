@@ -59,7 +59,7 @@ __device__ __forceinline__ void run2d(const double *w /* window, cell j at w[2 +
             ci[2 * q] = t.x;
             ci[2 * q + 1] = t.y;
          }
-         weno_cell_nonuniform<K, Strict>(ci, w + 2 + j, kc.eps, vl[j], vr[j]);
+         weno_cell_nonuniform<K, M>(ci, w + 2 + j, kc.eps, vl[j], vr[j]);
       }
    }
 }
@@ -414,7 +414,7 @@ __global__ void __launch_bounds__(NT, fv2d_min_blocks<M, UPW, NT>())
             for (int q = 0; q < 5; ++q) w5[q] = cell[q - 2];
             double l, r;
             if (tabx)
-               weno_cell_nonuniform<K, Strict>(ci, w5 + 2, g.kc.eps, l, r);
+               weno_cell_nonuniform<K, M>(ci, w5 + 2, g.kc.eps, l, r);
             else
                weno_run<K, 1, M>(w5 + (2 - (K - 1)), g.kc, &l, &r);
             s_vlx[ly * T::XP + R + lx] = l;
@@ -579,20 +579,19 @@ static int launch2d_u(Fv *fv, const Fv2dGeom &g, const StageArgs &a, cudaStream_
    return launch2d_t<K, COMBINE, M, UPW, TX2, TY2, NT2>(fv, g, a, st);
 }
 
-// general operator: reference operation order (Strict), two-sided fluxes, per-cell tables / coefficients where present
-template <int K, int COMBINE>
+// general operator: two-sided fluxes, per-cell tables / coefficients where present.  STRICT: the reference's operation order
+// (bit-identical to the oracle).  FAST: division-light weights and FMA contraction (1e-12 normwise, like the uniform fast path).
+template <int K, int COMBINE, class M>
 static int launch2d_gen(Fv *fv, const Fv2dGeom &g, const StageArgs &a, cudaStream_t st) {
-   if (g.small_tiles) return launch2d_t<K, COMBINE, Strict, 0, TX2S, TY2S, NT2S, 1>(fv, g, a, st);
+   if (g.small_tiles) return launch2d_t<K, COMBINE, M, 0, TX2S, TY2S, NT2S, 1>(fv, g, a, st);
    // 32x32 tiles, 256 threads: one column item and one x2-run per thread, ~66 KB of shared memory with the staged tables
    // (the 64x32 tile of the uniform path would need 119 KB and leave one CTA per SM)
-   return launch2d_t<K, COMBINE, Strict, 0, TX2G, TY2G, NT2, 1>(fv, g, a, st);
+   return launch2d_t<K, COMBINE, M, 0, TX2G, TY2G, NT2, 1>(fv, g, a, st);
 }
 
 template <int K, int COMBINE, class M>
 static int launch2d(Fv *fv, const Fv2dGeom &g, const StageArgs &a, cudaStream_t st) {
-   if constexpr (M::strict) {
-      if (fv->general) return launch2d_gen<K, COMBINE>(fv, g, a, st);
-   }
+   if (fv->general) return launch2d_gen<K, COMBINE, M>(fv, g, a, st);
    const bool upw = g.flux1.model == HRWENO_FLUX_LINEAR && g.flux1.scheme == HRWENO_SCHEME_GODUNOV && g.flux1.coef >= 0.0 && g.flux2.coef >= 0.0;
    return upw ? launch2d_u<K, COMBINE, M, 1>(fv, g, a, st) : launch2d_u<K, COMBINE, M, 0>(fv, g, a, st);
 }
@@ -651,7 +650,7 @@ int fv2d_stage(Fv *fv, int combine, const StageArgs &args, cudaStream_t st) {
       g.ts = fv->tfn ? fv->tfn(fv->tfn_ctx, args.t) : 1.0;
    }
    if ((int64_t)g.tiles_x * g.tiles_y > 2000000000LL) return fail(HRWENO_EINVAL, "2D grid too large for one launch");
-   if (d.mode == HRWENO_MODE_STRICT || fv->general) return launch2d_k<Strict>(fv, d.k, combine, g, args, st);
+   if (d.mode == HRWENO_MODE_STRICT) return launch2d_k<Strict>(fv, d.k, combine, g, args, st);
    return launch2d_k<Fast>(fv, d.k, combine, g, args, st);
 }
 

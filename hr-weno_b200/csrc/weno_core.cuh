@@ -384,8 +384,8 @@ __device__ __forceinline__ void weno_run(const double *w_in, const WenoK &kc, do
 // ci[j + K*(r+1)] = c(j,r); ve points at vext(i).
 // ------------------------------------------------------------------------------------------------
 template <int K, class M>
-__device__ __forceinline__ void weno_cell_nonuniform(const double *ci, const double *ve /* [-(K-1)..K-1] */,
-                                                     double eps, double &vl, double &vr) {
+__device__ __forceinline__ void weno_cell_nonuniform_core(const double *ci, const double *ve /* [-(K-1)..K-1] */,
+                                                          double eps, double &vl, double &vr) {
    double vrr[K], vlr[K], beta[K];
 #pragma unroll
    for (int r = 0; r < K; ++r) {
@@ -459,30 +459,65 @@ __device__ __forceinline__ void weno_cell_nonuniform(const double *ci, const dou
          xr = f.y;
       }
    } else {
-      double al[K], at[K];
+      // FAST mode with per-cell tables (2D general operators, fv2d.cu GEN): division-light weights as in the uniform fast
+      // path -- alfa_r ~ d_r * prod_{s != r} (eps+beta_s)^2, one reciprocal per side -- with FMA contraction; the candidates
+      // and smoothness indicators above are the reference's expressions (contracted).  Within the north-star tolerance of
+      // the reference order (a few ULP per reconstruction), not bit-identical.  Products grow like v^8..v^9: cells whose
+      // stencil holds |v| >= 2^100 are evaluated on the stencil scaled by an exact power of two (as weno_run does).
+      double den[K];
 #pragma unroll
       for (int r = 0; r < K; ++r) {
-         const double e = M::add(eps, beta[r]);
-         const double den = M::mul(e, e);
-         al[r] = M::div(d[r], den);
-         at[r] = M::div(d[K - 1 - r], den);
+         const double e = eps + beta[r];
+         den[r] = e * e;
       }
-      double s = al[0], st = at[0];
-#pragma unroll
-      for (int r = 1; r < K; ++r) {
-         s = M::add(s, al[r]);
-         st = M::add(st, at[r]);
-      }
-      xr = M::mul(M::div(al[0], s), vrr[0]);
-      xl = M::mul(M::div(at[0], st), vlr[0]);
-#pragma unroll
-      for (int r = 1; r < K; ++r) {
-         xr = M::add(xr, M::mul(M::div(al[r], s), vrr[r]));
-         xl = M::add(xl, M::mul(M::div(at[r], st), vlr[r]));
+      if constexpr (K == 1) { // w = alfa/alfa = 1 (weno.f90:186,207-214)
+         xr = vrr[0];
+         xl = vlr[0];
+      } else if constexpr (K == 2) {
+         const double a0 = d[0] * den[1], a1 = d[1] * den[0];
+         const double t0 = d[1] * den[1], t1 = d[0] * den[0];
+         xr = fma(a1, vrr[1], a0 * vrr[0]) * rcp3(a0 + a1);
+         xl = fma(t1, vlr[1], t0 * vlr[0]) * rcp3(t0 + t1);
+      } else {
+         const double p0 = den[1] * den[K - 1], p1 = den[0] * den[K - 1], p2 = den[0] * den[1];
+         const double a0 = 0.3 * p0, a1 = 0.6 * p1, a2 = 0.1 * p2;
+         const double t0 = 0.1 * p0, t2 = 0.3 * p2; // alfatilde_1 == alfa_1
+         xr = fma(a2, vrr[K - 1], fma(a1, vrr[1], a0 * vrr[0])) * fast_rcp((a0 + a1) + a2);
+         xl = fma(t2, vlr[K - 1], fma(a1, vlr[1], t0 * vlr[0])) * fast_rcp((t0 + a1) + t2);
       }
    }
    vr = xr;
    vl = xl;
+}
+
+template <int K, class M>
+__device__ __forceinline__ void weno_cell_nonuniform(const double *ci, const double *ve /* [-(K-1)..K-1] */, double eps, double &vl,
+                                                     double &vr) {
+   if constexpr (M::strict || K == 1) {
+      weno_cell_nonuniform_core<K, M>(ci, ve, eps, vl, vr);
+   } else {
+      // magnitude guard of the division-light weights (see weno_run): rare, predicated rescaling of the stencil in registers
+      constexpr int N = 2 * K - 1;
+      const float mhi = fast_window_maxhi<N>(ve - (K - 1));
+      double vv[N];
+#pragma unroll
+      for (int j = 0; j < N; ++j) vv[j] = ve[j - (K - 1)];
+      double epsv = eps, sup = 1.0;
+      const bool big = !(mhi < __int_as_float(FAST_RANGE_HI));
+      if (big) {
+         const int e = ((__float_as_int(mhi) >> 20) & 0x7ff) - 1023 - 40;
+         const double sdn = __hiloint2double((1023 - e) << 20, 0);
+         sup = __hiloint2double((1023 + e) << 20, 0);
+#pragma unroll
+         for (int j = 0; j < N; ++j) vv[j] *= sdn;
+         epsv = fmax(eps * sdn * sdn, 0x1p-240);
+      }
+      weno_cell_nonuniform_core<K, M>(ci, vv + (K - 1), epsv, vl, vr);
+      if (big) {
+         vl *= sup;
+         vr *= sup;
+      }
+   }
 }
 
 } // namespace hrw

@@ -167,7 +167,9 @@ int hrweno_fv_rhs_dev(hrweno_fv *fv, double t, const double *v_dev, double *vdot
  * cnu(:,:,i) of `weno(ncells, k, eps, xedges)` (weno.f90:100-112, 177, 221-297) instead of c1/c2/c3.  xedges[0..n[axis]]
  * (host) are the cell edges of that axis (grid1%edges, grids.f90:232-250; any grid1 kind).  The cell widths stay the
  * ones of the descriptor.  Call after hrweno_fv_create and before the first rhs / integrate call; from then on this
- * operator runs the general stage kernels (reference operation order in both modes).  Slabs (nranks > 1): along the
+ * operator runs the general stage kernels: the reference operation order in MODE_STRICT (bit-identical to the oracle);
+ * MODE_FAST keeps the reference order in 1D and uses division-light weights with FMA contraction in 2D (1e-12 normwise per
+ * output time, like the uniform fast path).  Slabs (nranks > 1): along the
  * DECOMPOSED axis pass the GLOBAL edge array xedges[0..global_n] -- the tables of a slab's first and last cells, and of
  * the neighbour cells its interface faces need, depend on edges beyond the slab; other axes: the local (= global) edges. */
 int hrweno_fv_set_xedges(hrweno_fv *fv, int axis, const double *xedges);

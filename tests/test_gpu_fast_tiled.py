@@ -207,3 +207,40 @@ def test_fast_drift_vs_grid_example2(gpu_lib, pkg, ref, threads):
     curve = _example2_drift(pkg, ref, 1000, 1.25e-3, 1.25, 10)
     _log("example2 1000^2 (fevals, drift): " + " ".join(f"({f},{d:.2e})" for f, d in curve))
     assert max(d for _, d in curve) <= TOL, curve
+
+
+# ---- 2D general operators (per-cell tables, growth fluxes, time factor) in FAST mode ---------------------------------------
+@pytest.mark.parametrize("n,integrator", [(640, "ms"), (640, "rk3"), (300, "ms")])
+def test_fast_general_2d_vs_oracle(gpu_lib, pkg, ref, threads, n, integrator):
+    """non-uniform grids + growth terms (example2:140,153) + time factor on the tile kernel with division-light weights
+    (fv2d.cu GEN, weno_core.cuh: weno_cell_nonuniform fast branch): <= 1e-12 normwise of the oracle at every output;
+    640^2 takes the 32x32 tiles, 300^2 the small ones"""
+    import math
+
+    g1 = pkg.hrweno_grids.grid1().geometric(0.0, 10.0, 1.003, n)
+    g2 = pkg.hrweno_grids.grid1().geometric(0.0, 10.0, 1.002, n)
+    u0 = (ex2_ic(g1.center, g2.center) + 1e-3 * np.random.default_rng(8).standard_normal((n, n))).reshape(-1)
+    kw = dict(n=(n, n), k=3, flux_model=1, bc=1, width=[g1.width, g2.width])
+    fv, rfv = pkg.fv.FV(pkg.fv.make_desc(mode=pkg._abi.MODE_FAST, **kw)), ref.FV(pkg.fv.make_desc(**kw))
+    gt = lambda t: 1.0 + 0.3 * math.sin(2.0 * t)  # noqa: E731
+    for f in (fv, rfv):
+        f.set_xedges(0, g1.edges)
+        f.set_xedges(1, g2.edges)
+        f.set_flux_coef(0, 0.01 * g1.edges**2, None)
+        f.set_flux_coef(1, 0.1 * g2.edges, 0.1 * g1.center)
+        f.set_flux_time_fn(gt)
+    if integrator == "ms":
+        ode, rode = pkg.hrweno_tvdode.mstvd(fv, n * n), ref.mstvd(rfv)
+    else:
+        ode, rode = pkg.hrweno_tvdode.rktvd(fv, n * n, 3), ref.rktvd(rfv, 3)
+    u, ur, t, tr, dt = u0.copy(), u0.copy(), 0.0, 0.0, 2e-3
+    worst = 0.0
+    for nsteps in (1, 9, 20):
+        tt = t
+        for _ in range(nsteps - 1):
+            tt = tt + dt
+        t, tr = ode.integrate(u, t, tt, dt), rode.integrate(ur, tr, tt, dt)
+        assert t == tr
+        worst = max(worst, normwise(u, ur))
+    _log(f"general 2D fast {n}^2 {integrator} steps=30: {worst:.3e}")
+    assert 0.0 < worst <= 1e-12  # > 0: the fast arithmetic really ran

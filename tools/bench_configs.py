@@ -146,20 +146,23 @@ if args.only == "general":
     gbs = nc * (64.0 + 3 * (96.0 + 8.0)) * K / el / 1e9  # 64 B/cell-step of state + per stage 96 B cnu + 8 B width
     print(f"general 1D 2^22 cells geometric grid WENO5+rktvd3 (K7, reference order): {nc*3*K/el:.3e} cell-stages/s, {gbs:.0f} GB/s algorithmic (64 + 3*104 B/cell-step) = {gbs/PEAK:.3f} of measured HBM peak")
     del ode, fv, ud
-    # 2D geometric x geometric with the growth terms of example2:140,153; the per-axis tables (4096 cells each) stay in cache
+    # 2D geometric x geometric with the growth terms of example2:140,153: tile kernel in GEN mode, strict (reference order,
+    # bit-identical) and fast (division-light weights, 1e-12)
     n = 4096
     g1 = pkg.hrweno_grids.grid1().geometric(0.0, 10.0, 1.0005, n)
     g2 = pkg.hrweno_grids.grid1().geometric(0.0, 10.0, 1.0003, n)
-    fv = pkg.fv.FV(pkg.fv.make_desc((n, n), flux_model=1, bc=1, width=[g1.width, g2.width]))
-    fv.set_xedges(0, g1.edges)
-    fv.set_xedges(1, g2.edges)
-    fv.set_flux_coef(0, g1.edges**2, None)
-    fv.set_flux_coef(1, g2.edges, g1.center)
-    ode = pkg.hrweno_tvdode.mstvd(fv, n * n)
     u = ex2_ic(g1.center, g2.center) + 1e-3 * np.random.default_rng(12345).standard_normal((n, n))
-    ud = torch.from_numpy(u.reshape(-1)).cuda()
-    dt = 1e-6
-    t = ode.integrate_dev(ud.data_ptr(), 0.0, steps_to(0.0, dt, 6), dt, 1, stream)
-    el = timed(lambda: ode.integrate_dev(ud.data_ptr(), t, steps_to(t, dt, K), dt, 1, stream))
-    gbs = n * n * 40.0 * K / el / 1e9
-    print(f"general 2D {n}x{n} geometric grids + growth fluxes WENO5+mstvd (K7, reference order): {n*n*K/el:.3e} cell-steps/s, {gbs:.0f} GB/s algorithmic (40 B/cell-step) = {gbs/PEAK:.3f} of measured HBM peak")
+    for mname, m in (("reference order (strict)", pkg._abi.MODE_STRICT), ("fast", pkg._abi.MODE_FAST)):
+        fv = pkg.fv.FV(pkg.fv.make_desc((n, n), flux_model=1, bc=1, width=[g1.width, g2.width], mode=m))
+        fv.set_xedges(0, g1.edges)
+        fv.set_xedges(1, g2.edges)
+        fv.set_flux_coef(0, g1.edges**2, None)
+        fv.set_flux_coef(1, g2.edges, g1.center)
+        ode = pkg.hrweno_tvdode.mstvd(fv, n * n)
+        ud = torch.from_numpy(u.reshape(-1)).cuda()
+        dt = 1e-6
+        t = ode.integrate_dev(ud.data_ptr(), 0.0, steps_to(0.0, dt, 6), dt, 1, stream)
+        el = timed(lambda: ode.integrate_dev(ud.data_ptr(), t, steps_to(t, dt, K), dt, 1, stream))
+        gbs = n * n * 40.0 * K / el / 1e9
+        print(f"general 2D {n}x{n} geometric grids + growth fluxes WENO5+mstvd (tile kernel GEN, {mname}): {n*n*K/el:.3e} cell-steps/s, {gbs:.0f} GB/s algorithmic (40 B/cell-step) = {gbs/PEAK:.3f} of measured HBM peak")
+        del ode, fv, ud
