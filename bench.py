@@ -583,7 +583,15 @@ def main():
     other_m = measure(other, max(2, min(K, 5)), 3, False) if not args.single_mode else None
     extra = None
     if not args.no_extra_configs:
-        extra = {"cfg4": extra_cfg4(args.mode), "cfg5": extra_cfg5(args.mode), "real32": extra_f32()}
+        def guarded(fn, *a):
+            """an extra configuration must never cost the headline line: report its failure instead (all ranks take the same path)"""
+            try:
+                return fn(*a)
+            except Exception as e:  # noqa: BLE001
+                torch.cuda.empty_cache()
+                return {"error": repr(e)} if rank == 0 else None
+
+        extra = {"cfg4": guarded(extra_cfg4, args.mode), "cfg5": guarded(extra_cfg5, args.mode), "real32": guarded(extra_f32)}
 
     if rank != 0:
         if world > 1:
