@@ -147,7 +147,10 @@ __device__ __forceinline__ double face_flux_k(const FluxCfg &c, double vm, doubl
       // same bits (where the two squares round to the same value either choice gives it)
       const bool up = vm <= vp, lt = fabs(vm) < fabs(vp);
       const double q = (up == lt) ? vm : vp;
-      return M::mul(q, q);
+      // a separately rounded product in BOTH modes: left to the compiler, fast mode would contract q*q with the flux
+      // difference into an FMA in the interior instantiation but not in the boundary one, and a cell's value would depend
+      // on where the slab / tile edges fall (caught by the slab == single-domain bit-identity test of tests/mgpu_worker.py)
+      return __dmul_rn(q, q);
    } else {
       return face_flux<M>(c, vm, vp);
    }

@@ -449,7 +449,7 @@ static int pipeline_operator(Ode *o, int64_t G, Fv **P, double **B, int64_t *HL,
    }
    constexpr int64_t H = Halo::WIDE_H;
    if (fv->d.grid_kind != HRWENO_GRID_LINEAR || !fv->halo.ready || !fv->halo.wide_off) return HRWENO_OK;
-   if ((int64_t)fv->d.k * G > H || fv->n0 < 4 * H) return HRWENO_OK;
+   if ((int64_t)fv->d.k * G > H) return HRWENO_OK; // (slab sizes were checked by the caller on the smallest slab)
    const int64_t hl = fv->d.rank > 0 ? H : 0, hr = fv->d.rank < fv->d.nranks - 1 ? H : 0;
    if (!o->fv_ext) {
       hrweno_fv_desc d = fv->d; // same rank / nranks / global grid: physical-boundary flags and widths follow the global indices
@@ -490,14 +490,20 @@ static int rk_integrate_pipelined(Ode *o, double *u, double *t, double tout, dou
    }
    const int order = o->order;
    const int64_t G = (int64_t)order * nsteps;
+   if (G > 1000000) return HRWENO_OK; // (the same on every rank)
    // the operator the pipeline runs on: this one (single GPU) or the slab extended by the wide halos
    Fv *P = nullptr;
    double *B[3] = {nullptr, nullptr, nullptr}; // U, T1, T2 at cell 0 of P
    int64_t HL = 0, HR = 0;
    {
+      // slabs: every rank must take the same decision (a rank on the plain path would wait for per-stage halos its
+      // neighbours never send), so the size tests use the smallest slab, floor(global_n / nranks), not this rank's own
       int tile0 = 0, tpr0 = 0;
       fv_tiling_1d(fv, &tile0, &tpr0);
-      if ((tpr0 + chunk_tiles - 1) / chunk_tiles < 4) return HRWENO_OK; // fewer than four chunks: nothing to overlap
+      const int64_t nmin = fv->d.nranks > 1 ? fv->d.global_n / fv->d.nranks : fv->n0;
+      const int64_t tiles_min = (nmin + tile0 - 1) / tile0;
+      if ((tiles_min + chunk_tiles - 1) / chunk_tiles < 4) return HRWENO_OK; // fewer than four chunks: nothing to overlap
+      if (fv->d.nranks > 1 && nmin < 4 * (int64_t)Halo::WIDE_H + 1) return HRWENO_OK;
    }
    HRW_TRY(pipeline_operator(o, G, &P, B, &HL, &HR));
    if (!P) return HRWENO_OK;
@@ -507,8 +513,7 @@ static int rk_integrate_pipelined(Ode *o, double *u, double *t, double tout, dou
    std::vector<int> cb(1, 0);
    while (cb.back() < tpr) cb.push_back(std::min(tpr, cb.back() + chunk_tiles));
    const int C = (int)cb.size() - 1;
-   if (C < 4) return HRWENO_OK;
-   if (G + C > 2000000) return HRWENO_OK;
+   if (C < 2) return HRWENO_OK; // cannot happen after the size tests above
    const int64_t n = fv->n0;      // this slab's cells: u[0..n) <-> cells [HL, HL+n) of P
    const int64_t np = P->n0;      // = HL + n + HR
    const int64_t launches0 = P->launches;
