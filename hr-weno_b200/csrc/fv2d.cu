@@ -127,7 +127,10 @@ __device__ __forceinline__ void tma_tensor_2d_g2s(uint32_t dst_smem, const CUten
 template <int UPW, class M>
 __device__ __forceinline__ double face2d(const FluxCfg &c, double vm, double vp) {
    if constexpr (UPW) {
-      return M::mul(c.coef, vm);
+      // a separately rounded product in both modes: a plain a*vm could be contracted with the flux difference that follows
+      // in one variant of phase B (interior / edge tiles) and not in the other, and fast-mode results would depend on
+      // where the tile and slab edges fall (see fv1d.cuh: face_flux_k)
+      return __dmul_rn(c.coef, vm);
    } else {
       return face_flux<M>(c, vm, vp);
    }
