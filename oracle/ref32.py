@@ -15,6 +15,9 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(HERE, "libhrweno_oracle_f32.so")
 F32 = np.float32
 _lib = None
+# the callback types of hrweno_oracle.h / hrweno_b200.h as the REAL32 build reads them (every `double` a `float`)
+FLUX_FN32 = C.CFUNCTYPE(C.c_float, C.c_void_p, C.c_float, C.POINTER(C.c_float), C.c_int, C.c_float)
+RHS_FN32 = C.CFUNCTYPE(None, C.c_void_p, C.c_float, C.c_int64, C.POINTER(C.c_float), C.POINTER(C.c_float))
 
 
 def lib():
@@ -42,6 +45,12 @@ def lib():
         "hrweno_ref_ode_integrate": (i32, [vp, vp, C.POINTER(f32), f32, f32, i32]),
         "hrweno_ref_ode_fevals": (i64, [vp]),
         "hrweno_ref_ode_istate": (i32, [vp]),
+        "hrweno_ref_lax_friedrichs": (f32, [FLUX_FN32, vp, f32, f32, vp, i32, f32, f32]),
+        "hrweno_ref_godunov": (f32, [FLUX_FN32, vp, f32, f32, vp, i32, f32]),
+        "hrweno_ref_face_flux": (f32, [i32, i32, f32, f32, f32, f32]),
+        "hrweno_ref_rktvd_create": (i32, [C.POINTER(vp), RHS_FN32, vp, i64, i32]),
+        "hrweno_ref_mstvd_create": (i32, [C.POINTER(vp), RHS_FN32, vp, i64]),
+        "hrweno_ref_is_done": (i32, [f32, f32, f32]),
     }
     for name, (res, args) in protos.items():
         fn = getattr(L, name)
@@ -125,15 +134,57 @@ class _ode:
         return tt.value
 
 
+def _wrap_rhs(fu):
+    def cb(_ctx, t, neq, up, dp):
+        u = np.ctypeslib.as_array(up, shape=(neq,))
+        d = np.ctypeslib.as_array(dp, shape=(neq,))
+        d[:] = fu(F32(t), u)
+
+    return RHS_FN32(cb)
+
+
 class rktvd(_ode):
-    def __init__(self, fv, order):
+    """rktvd(fu, order): fu is an oracle FV or a callable fu(t, u) -> udot on float32 (host)"""
+
+    def __init__(self, fv, order, neq=None):
         super().__init__()
-        self._fv = fv
-        _ok(lib().hrweno_ref_rktvd_create_fv(C.byref(self._h), fv._h, order))
+        if isinstance(fv, FV):
+            self._fv = fv
+            _ok(lib().hrweno_ref_rktvd_create_fv(C.byref(self._h), fv._h, order))
+        else:
+            self._cb = _wrap_rhs(fv)
+            _ok(lib().hrweno_ref_rktvd_create(C.byref(self._h), self._cb, None, neq, order))
 
 
 class mstvd(_ode):
-    def __init__(self, fv):
+    def __init__(self, fv, neq=None):
         super().__init__()
-        self._fv = fv
-        _ok(lib().hrweno_ref_mstvd_create_fv(C.byref(self._h), fv._h))
+        if isinstance(fv, FV):
+            self._fv = fv
+            _ok(lib().hrweno_ref_mstvd_create_fv(C.byref(self._h), fv._h))
+        else:
+            self._cb = _wrap_rhs(fv)
+            _ok(lib().hrweno_ref_mstvd_create(C.byref(self._h), self._cb, None, neq))
+
+
+def _wrap_flux(f):
+    return FLUX_FN32(lambda _ctx, u, xptr, nx, t: float(f(F32(u), np.ctypeslib.as_array(xptr, shape=(nx,)), F32(t))))
+
+
+def lax_friedrichs(f, vm, vp, x, t, alpha):
+    x = _f32(np.atleast_1d(x))
+    return F32(lib().hrweno_ref_lax_friedrichs(_wrap_flux(f), None, vm, vp, x.ctypes.data, x.size, t, alpha))
+
+
+def godunov(f, vm, vp, x, t):
+    x = _f32(np.atleast_1d(x))
+    return F32(lib().hrweno_ref_godunov(_wrap_flux(f), None, vm, vp, x.ctypes.data, x.size, t))
+
+
+def face_flux(scheme, model, coef, alpha, vm, vp):
+    f = lib().hrweno_ref_face_flux
+    return np.array([f(scheme, model, coef, alpha, a, b) for a, b in zip(np.ravel(vm), np.ravel(vp))], dtype=F32)
+
+
+def is_done(t, tout, dt):
+    return bool(lib().hrweno_ref_is_done(t, tout, dt))

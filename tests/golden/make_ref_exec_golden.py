@@ -16,6 +16,7 @@ with no contraction or re-association (gfortran on x86-64 without -ffast-math / 
 output (libm's exp/log in grid1%log, and any compiler-specific transformation, remain outside).
 
     python tests/golden/make_ref_exec_golden.py [--quick]      # --quick skips the two long runs (example2 fixtures)
+    python tests/golden/make_ref_exec_golden.py --real32       # the REAL32 build of the same source -> ref_exec_f32_*.npz
 """
 import os
 import sys
@@ -53,8 +54,18 @@ def load(example=None, patch=None):
     return P.build()
 
 
+def R(x):
+    """a harness-side real scalar of the kind being run (np.float32 in a REAL32 run, a Python float otherwise)"""
+    return f90py.rl(x)
+
+
+def A(x):
+    """a harness-side real array of the kind being run"""
+    return np.asarray(x, dtype=f90py.rdtype())
+
+
 def pulse(nc=30):  # test/test_hrweno.f90:45-46
-    v = np.zeros(nc)
+    v = np.zeros(nc, dtype=f90py.rdtype())
     v[nc // 3 - 1 : 2 * nc // 3] = 1.0
     return v
 
@@ -64,16 +75,16 @@ def gen_reconstruct(ns):
     out = {}
     rng = np.random.default_rng(20260102)
     nc = 30
-    out["v_pulse"], out["v_rand"] = pulse(nc), rng.standard_normal(nc)
-    out["xe_uniform"] = np.array([0.0 + 3.0 * i / nc for i in range(nc + 1)])   # test_hrweno.f90:87-93 style
-    out["xe_cubic"] = np.array([i / nc for i in range(nc + 1)]) ** 3            # test_hrweno.f90:128-135 style
+    out["v_pulse"], out["v_rand"] = pulse(nc), A(rng.standard_normal(nc))
+    out["xe_uniform"] = A([0.0 + 3.0 * i / nc for i in range(nc + 1)])   # test_hrweno.f90:87-93 style
+    out["xe_cubic"] = A(np.array([i / nc for i in range(nc + 1)]) ** 3)  # test_hrweno.f90:128-135 style
     for k in (1, 2, 3):
         for gname in ("none", "uniform", "cubic"):
-            w = ns["weno"](nc, k, 1e-6) if gname == "none" else ns["weno"](nc, k, 1e-6, FArr(out["xe_" + gname], (0,)))
+            w = ns["weno"](nc, k, R(1e-6)) if gname == "none" else ns["weno"](nc, k, R(1e-6), FArr(out["xe_" + gname], (0,)))
             if gname != "none":
                 out[f"cnu_{gname}_k{k}"] = np.ascontiguousarray(np.transpose(w.cnu.a, (2, 1, 0)))  # [i-1, r+1, j]
             for vname in ("pulse", "rand"):
-                vl, vr = np.zeros(nc), np.zeros(nc)
+                vl, vr = A(np.zeros(nc)), A(np.zeros(nc))
                 callm(w, "reconstruct", out["v_" + vname], vl, vr)
                 out[f"vl_{gname}_{vname}_k{k}"], out[f"vr_{gname}_{vname}_k{k}"] = vl, vr
     return out
@@ -82,17 +93,17 @@ def gen_reconstruct(ns):
 def gen_fluxes(ns):
     """lax_friedrichs / godunov (fluxes.f90:22-76) with Burgers' flux of example1:111-122"""
     rng = np.random.default_rng(20260103)
-    vm, vp = rng.standard_normal(200), rng.standard_normal(200)
+    vm, vp = A(rng.standard_normal(200)), A(rng.standard_normal(200))
     vm[:20] = vp[:20]  # h(a,a) = h(a) cases (test_fluxes.f90:41-47)
     x = FArr.from_list([3.0])
-    god = np.array([ns["godunov"](ns["flux"], float(a), float(b), x, 5.0) for a, b in zip(vm, vp)])
-    lf = np.array([ns["lax_friedrichs"](ns["flux"], float(a), float(b), x, 5.0, 1.3) for a, b in zip(vm, vp)])
-    return dict(vm=vm, vp=vp, godunov=god, lax_friedrichs=lf, alpha=1.3)
+    god = A([ns["godunov"](ns["flux"], R(a), R(b), x, R(5.0)) for a, b in zip(vm, vp)])
+    lf = A([ns["lax_friedrichs"](ns["flux"], R(a), R(b), x, R(5.0), R(1.3)) for a, b in zip(vm, vp)])
+    return dict(vm=vm, vp=vp, godunov=god, lax_friedrichs=lf, alpha=R(1.3))
 
 
 def gen_tvdode(ns):
     """rktvd orders 1-3 and mstvd (tvdode.f90:69-271) on the linear test ODE of test/test_tvdode.f90:107-111"""
-    a = np.array([-1.0 + float(ii - 1) * 4 / (10 - 1) for ii in range(1, 11)])  # test_tvdode.f90:15
+    a = A([-1.0 + float(ii - 1) * 4 / (10 - 1) for ii in range(1, 11)])  # test_tvdode.f90:15
 
     def fu(t, u, udot):  # udot = a*u
         FArr.wrap(udot).assign(FArr(a) * FArr.wrap(u))
@@ -100,15 +111,15 @@ def gen_tvdode(ns):
     out = {"a": a}
     for order in (1, 2, 3):
         ode = ns["rktvd"](fu, 10, order)
-        u, t = FArr(np.ones(10)), Ref(0.0)
+        u, t = FArr(A(np.ones(10))), Ref(R(0.0))
         for tout in (0.0, 0.1, 0.1, 0.35):
-            callm(ode, "integrate", u, t, tout, 1e-2)
-        callm(ode, "integrate", u, t, 99.0, 1e-2, itask=2)  # single step
+            callm(ode, "integrate", u, t, R(tout), R(1e-2))
+        callm(ode, "integrate", u, t, R(99.0), R(1e-2), itask=2)  # single step
         out[f"rk{order}_u"], out[f"rk{order}_t"], out[f"rk{order}_fevals"] = u.a.copy(), t.v, ode.fevals
     ode = ns["mstvd"](fu, 10)
-    u, t = FArr(np.ones(10)), Ref(0.0)
+    u, t = FArr(A(np.ones(10))), Ref(R(0.0))
     for tout in (0.0, 0.1, 0.1, 0.35):
-        callm(ode, "integrate", u, t, tout, 1e-2)
+        callm(ode, "integrate", u, t, R(tout), R(1e-2))
     out["ms_u"], out["ms_t"], out["ms_fevals"] = u.a.copy(), t.v, ode.fevals
     return out
 
@@ -180,6 +191,8 @@ def run_example1(npts=100, snaps=(0, 1, 50, 100), k=3, order=3, nc=100, extra_pa
     out = run_program(ns, "main_example1_burgers_1d_fv", npts, snaps)
     gx = ns["gx"]
     out.update(edges=gx.edges.a.copy(), width=gx.width.a.copy(), center=gx.center.a.copy())
+    if f90py.rkind() == 4:  # the initial state as the program's own `ic` gives it (example1:49; output 0 is one step later)
+        out["ic"] = ns["ic"](gx.center).a.copy()
     return out
 
 
@@ -208,6 +221,9 @@ def run_example2(n, npts, snaps, dt=5e-3, time_end=5.0, grids="linear", nonunifo
     ns = load("example2_pbe_2d_fv.f90", patch=p)
     out = run_program(ns, "main_example_pbe_2d_fv", npts, snaps)
     out.update(edges1=ns["gx"][1].edges.a.copy(), edges2=ns["gx"][2].edges.a.copy())
+    if f90py.rkind() == 4:  # example2:48-52
+        c1, c2 = ns["gx"][1].center, ns["gx"][2].center
+        out["ic"] = A([ns["ic"](FArr.from_list([c1[ii], c2[jj]])) for jj in range(1, n2 + 1) for ii in range(1, n + 1)])
     return out
 
 
@@ -219,7 +235,46 @@ LAX_FRIEDRICHS = [("fedges(i) = godunov(flux, vr(i), vl(i + 1), [gx%right(i)], t
 GROWTH = [("flux1 = v !*x(1)**2", "flux1 = v*x(1)**2"), ("flux2 = v !*x(1)*x(2)", "flux2 = v*x(1)*x(2)")]
 
 
+def main32():
+    """the REAL32 build of the reference (src/hrweno_kinds.F90:9-10, -DREAL32: rk = real32): the same source lines
+    translated and executed with every real entity a binary32 value (f90py.real_kind(4)) -> ref_exec_f32_*.npz.
+    Smaller than the binary64 set (NumPy float32 scalars are slow): it pins the REAL32 oracle
+    (oracle/libhrweno_oracle_f32.so), which is the checker of the hrweno_*_f32 entry points."""
+    t0 = time.time()
+    with f90py.real_kind(4):
+        ns1 = load("example1_burgers_1d_fv.f90")
+        np.savez(os.path.join(OUT, "ref_exec_f32_reconstruct.npz"), **gen_reconstruct(ns1))
+        np.savez(os.path.join(OUT, "ref_exec_f32_fluxes.npz"), **gen_fluxes(ns1))
+        np.savez(os.path.join(OUT, "ref_exec_f32_tvdode.npz"), **gen_tvdode(ns1))
+        g = ns1["new_grid1"]()
+        callm(g, "linear", R(-5.0), R(5.0), 100)
+        grids = {"linear": g.edges.a.copy(), "linear_center": g.center.a.copy(), "linear_width": g.width.a.copy()}
+        callm(g, "geometric", R(1e1), R(1e3), R(1.1), 100)
+        grids.update(geometric=g.edges.a.copy(), geometric_width=g.width.a.copy())
+        np.savez(os.path.join(OUT, "ref_exec_f32_grids.npz"), **grids)
+        print(f"real32: reconstruct / fluxes / tvdode / grids done ({time.time() - t0:.0f} s)", flush=True)
+        np.savez(os.path.join(OUT, "ref_exec_f32_example1.npz"), **run_example1(npts=100, snaps=(0, 1, 10, 50, 100)))
+        print(f"real32: example1 as shipped, 101 outputs done ({time.time() - t0:.0f} s)", flush=True)
+        sweep = {}
+        for k in (1, 2, 3):
+            for order in (1, 2, 3):
+                r = run_example1(npts=10, snaps=(0, 10), k=k, order=order)
+                sweep["ic"] = r["ic"]
+                sweep[f"u_k{k}_o{order}"], sweep[f"t_k{k}_o{order}"], sweep[f"fevals_k{k}_o{order}"] = r["u_10"], r["times"], r["fevals"]
+        np.savez(os.path.join(OUT, "ref_exec_f32_example1_sweep.npz"), **sweep)
+        np.savez(os.path.join(OUT, "ref_exec_f32_example1_lf.npz"),
+                 **run_example1(npts=20, snaps=(0, 10, 20), extra_patch=LAX_FRIEDRICHS))
+        print(f"real32: example1 k x order sweep and Lax-Friedrichs variant done ({time.time() - t0:.0f} s)", flush=True)
+        np.savez(os.path.join(OUT, "ref_exec_f32_example2_growth.npz"),
+                 **run_example2(24, 20, (0, 10, 20), dt=2.5e-4, time_end=0.5, grids="geometric", nonuniform=True, n2=18, growth=True))
+        print(f"real32: example2 + growth on geometric 24x18 done ({time.time() - t0:.0f} s)", flush=True)
+        np.savez(os.path.join(OUT, "ref_exec_f32_example2_40.npz"), **run_example2(40, 10, (0, 1, 5, 10)))
+        print(f"real32: example2 at 40x40, outputs 0..10 done ({time.time() - t0:.0f} s)", flush=True)
+
+
 def main():
+    if "--real32" in sys.argv:
+        return main32()
     quick = "--quick" in sys.argv
     t0 = time.time()
     ns1 = load("example1_burgers_1d_fv.f90")

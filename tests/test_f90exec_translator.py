@@ -287,3 +287,75 @@ def test_main_program_with_host_association_and_object_arrays(tmp_path):
     assert [s[0] for s in seen] == [0.5, 1.0, 1.5, 2.0]
     assert np.array_equal(seen[-1][1], np.arange(1, 7) * 3.0 + 12.0)
     assert ns["b"][1].w == 1.5 and ns["b"][2].w == 3.0
+
+
+# ---- rk = real32 (the reference's -DREAL32 build) ---------------------------------------------------------------------
+F = np.float32
+
+
+def test_real32_every_operation_rounds_to_binary32(tmp_path):
+    """literals (with or without _rk), mixed real/integer arithmetic, integer powers, `sum()` and array expressions are
+    binary32 operations; the expected values are written operation by operation with np.float32"""
+    with f90py.real_kind(4):
+        ns = build(tmp_path, """
+            module m
+            contains
+               pure real(rk) function f(a, b, n)
+                  real(rk), intent(in) :: a, b
+                  integer, intent(in) :: n
+                  f = 13.0_rk/12*a + 0.1*b - a**3/n + 1e-6_rk
+               end function
+               subroutine s(v, out)
+                  real(rk), intent(in) :: v(:)
+                  real(rk), intent(out) :: out(:)
+                  real(rk) :: w(0:2), acc
+                  integer :: i
+                  w = v(1:3)*2.5_rk + v(4:6)/3
+                  out(1) = sum(w)
+                  acc = 0
+                  do i = 0, 2
+                     acc = acc + w(i)**2
+                  end do
+                  out(2) = acc
+                  out(3) = sqrt(abs(w(0))) + max(w(1), w(2), 0.25_rk) + sign(1.0_rk, -w(0))
+                  out(4) = real(size(w), rk)/7 + epsilon(1.0_rk)
+               end subroutine
+            end module
+        """)
+        a, b = F(0.7), F(1.3)
+        r = ns["f"](a, b, 3)
+        assert isinstance(r, np.float32)
+        assert r == ((F(13.0) / F(12)) * a + F(0.1) * b) - ((a * a) * a) / F(3) + F(1e-6)
+        assert float(r) != (13.0 / 12) * 0.7 + 0.1 * 1.3 - 0.7**3 / 3 + 1e-6  # not the binary64 value rounded late
+        v, out = np.array([0.3, -1.7, 2.9, 0.11, 5.3, -0.77], dtype=F), np.zeros(4, dtype=F)
+        ns["s"](v, out)
+        w = v[:3] * F(2.5) + v[3:] / F(3)
+        assert w.dtype == F and out.dtype == F
+        assert out[0] == ((F(0) + w[0]) + w[1]) + w[2]
+        assert out[1] == ((F(0) + w[0] * w[0]) + w[1] * w[1]) + w[2] * w[2]
+        assert out[2] == (np.sqrt(np.abs(w[0])) + max(w[1], w[2], F(0.25))) + np.copysign(F(1), -w[0])
+        assert out[3] == F(3) / F(7) + np.finfo(F).eps
+    assert f90py.rkind() == 8  # the context restores binary64
+
+
+def test_real32_a_binary64_value_cannot_slip_in(tmp_path):
+    with f90py.real_kind(4):
+        ns = build(tmp_path, """
+            module m
+            contains
+               subroutine s(x, v)
+                  real(rk), intent(in) :: x
+                  real(rk), intent(inout) :: v(:)
+                  v(1) = x
+               end subroutine
+            end module
+        """)
+        v = np.zeros(2, dtype=F)
+        ns["s"](F(0.1), v)
+        assert v[0] == F(0.1)
+        with pytest.raises(TypeError, match="binary64"):
+            ns["s"](0.1, v)  # a Python float (binary64) reaching a store
+        with pytest.raises(TypeError, match="binary64"):
+            ns["s"](F(0.1), np.zeros(2))  # a float64 array as an actual argument
+        with pytest.raises(TypeError, match="binary64"):
+            FArr(np.zeros(3))

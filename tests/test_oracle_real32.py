@@ -1,8 +1,9 @@
 """REAL32 (src/hrweno_kinds.F90:9-17: rk = real32 is a compile-time switch of the whole reference).  The fp32 oracle is
 oracle/hrweno_oracle.c compiled with every `double` read as `float` and single-precision literals
-(oracle/libhrweno_oracle_f32.so).  No executed-reference-source fixture exists in float32 (tools/f90exec evaluates in
-real64), so its pin is a second, independently written restatement: oracle/np_oracle.py evaluated on float32 arrays
-(NumPy rounds every float32 operation to float32) must agree with it bit for bit -- tables, cnu, reconstruct, both
+(oracle/libhrweno_oracle_f32.so).  Its first pin is the reference's source executed as its REAL32 build
+(tests/test_reference_source_exec_real32.py, fixtures ref_exec_f32_*.npz).  This file is the second one, at sizes and on
+inputs the fixtures do not hold: an independently written restatement, oracle/np_oracle.py evaluated on float32 arrays
+(NumPy rounds every float32 operation to float32), must agree with it bit for bit -- tables, cnu, reconstruct, both
 example right-hand sides, rktvd and mstvd including the step counts the float32 time accumulation produces."""
 import numpy as np
 import pytest

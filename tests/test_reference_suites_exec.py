@@ -40,7 +40,7 @@ def check(error, actual, expected=None, message=None, more=None, thr=None, rel=F
         if a.shape != e.shape and a.size != 1 and e.size != 1:
             ok = False
         elif thr is None:
-            ok = bool(np.all(a == e)) if a.dtype.kind in "iub" else bool(np.all(np.abs(a - e) <= np.finfo(np.float64).eps))
+            ok = bool(np.all(a == e)) if a.dtype.kind in "iub" else bool(np.all(np.abs(a - e) <= np.finfo(f90py.rdtype()).eps))
         else:
             ok = bool(np.all(np.abs(a - e) <= (thr * np.abs(e) if rel else thr)))
     if not ok:
@@ -74,6 +74,17 @@ def test_reference_suite_passes_on_the_executed_reference_source(suite, test):
     assert test in ns, f"{test} not found in {suite}"
     err = ErrorBox()
     ns[test](err)
+    assert err.msg is None, err.msg
+
+
+@pytest.mark.parametrize("suite,test", [(s, t) for s, ts in SUITES.items() for t in ts])
+def test_reference_suite_passes_on_the_executed_reference_source_real32(suite, test):
+    """the same ten tests on the REAL32 build of the library (hrweno_kinds.F90:9-10): suites and library translated and
+    executed with rk = real32 -- the execution that produced tests/golden/ref_exec_f32_*.npz"""
+    with f90py.real_kind(4):
+        ns = load(suite)
+        err = ErrorBox()
+        ns[test](err)
     assert err.msg is None, err.msg
 
 

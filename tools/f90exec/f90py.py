@@ -10,7 +10,10 @@ lower bounds, pointer bounds remapping, optional arguments and the control flow 
 Arithmetic model (what a gfortran x86-64 build without -ffast-math / -march=native does): every + - * / is one
 correctly rounded binary64 operation (CPython floats and NumPy float64 element-wise operations), no FMA contraction, no
 re-association; `x**n` with an integer n is binary exponentiation (libgcc __powidf2), so `x**2 == x*x`; integer/integer
-division truncates; array expressions are evaluated element by element.
+division truncates; array expressions are evaluated element by element.  `with real_kind(4):` translates and executes
+the same source as the reference's REAL32 build (src/hrweno_kinds.F90:9-10): every real literal, scalar and array
+element is then a binary32 value (np.float32), every operation one correctly rounded binary32 operation, and a binary64
+value that reaches a store raises instead of being converted.
 
 Supported subset (enough for src/hrweno_{weno,fluxes,tvdode,grids}.f90 and the `rhs`/`flux`/`ic` procedures of the two
 examples): modules and programs with `contains`, derived types with default component values, type extension,
@@ -35,6 +38,51 @@ import numpy as np
 
 class FortranStop(RuntimeError):
     """`error stop`"""
+
+
+# The kind of `real(rk)` (src/hrweno_kinds.F90:9-17 selects it at compile time: -DREAL32 / -DREAL64).  8: scalars are
+# CPython floats, arrays float64.  4: scalars are np.float32, arrays float32 -- every NumPy float32 operation is one
+# correctly rounded binary32 operation, Python ints and the (few) Python floats that enter are "weak" operands (NEP 50)
+# that take the float32 kind exactly as an integer / a default-real operand does in Fortran.  A binary64 value stored
+# into a REAL32 run is a translator error and raises (`_store_check`).  Process-global: use `real_kind(4)` as a context.
+_KIND = [8]
+
+
+def rkind():
+    return _KIND[0]
+
+
+def rdtype():
+    return np.float32 if _KIND[0] == 4 else np.float64
+
+
+def rl(x):
+    """a real literal / `real(x, rk)` of the current kind"""
+    return np.float32(x) if _KIND[0] == 4 else float(x)
+
+
+class real_kind:
+    """`with real_kind(4): ...` -- translate AND execute inside the block (the translation writes real literals for the
+    kind, the run-time allocates arrays of it)"""
+
+    def __init__(self, kind):
+        if kind not in (4, 8):
+            raise NotImplementedError(f"real kind {kind}")
+        self.kind = kind
+
+    def __enter__(self):
+        self.prev, _KIND[0] = _KIND[0], self.kind
+        return self
+
+    def __exit__(self, *exc):
+        _KIND[0] = self.prev
+        return False
+
+
+def _store_check(value):
+    if _KIND[0] == 4 and (isinstance(value, float) or (isinstance(value, np.ndarray) and value.dtype == np.float64)):
+        raise TypeError(f"a binary64 value ({value!r}) reached a store in a REAL32 run")
+    return value
 
 
 class FS:
@@ -69,11 +117,14 @@ class FArr:
     __slots__ = ("a", "lb")
 
     def __init__(self, a, lb=None):
+        if _KIND[0] == 4 and a.dtype == np.float64:
+            raise TypeError("a binary64 array appeared in a REAL32 run")
         self.a = a
         self.lb = tuple(lb) if lb is not None else (1,) * a.ndim
 
     @staticmethod
-    def alloc(bounds, dtype=np.float64):
+    def alloc(bounds, dtype=None):
+        dtype = rdtype() if dtype is None else dtype
         shape = tuple(max(0, hi - lo + 1) for lo, hi in bounds)
         return FArr(np.zeros(shape, dtype=dtype, order="F"), tuple(lo for lo, _ in bounds))
 
@@ -85,8 +136,10 @@ class FArr:
         if isinstance(x, FArr):
             return FArr(x.a, lb if lb is not None else (1,) * x.a.ndim)
         a = np.asarray(x)
-        if a.dtype != np.float64 and a.dtype.kind == "f":
-            a = a.astype(np.float64)
+        if a.dtype != rdtype() and a.dtype.kind == "f":
+            if _KIND[0] == 4:  # a silent copy would also swallow what the callee writes into an intent(out) dummy
+                raise TypeError("a binary64 array was passed to a procedure in a REAL32 run")
+            a = a.astype(rdtype())
         return FArr(a, lb if lb is not None else (1,) * a.ndim)
 
     @staticmethod
@@ -97,7 +150,7 @@ class FArr:
                 flat.extend(it.a.ravel(order="F").tolist())
             else:
                 flat.append(it)
-        return FArr(np.array(flat, dtype=np.float64), (1,))
+        return FArr(np.array(flat, dtype=rdtype()), (1,))
 
     def copy(self):
         return FArr(np.array(self.a, order="F", copy=True), self.lb)
@@ -137,11 +190,13 @@ class FArr:
         r = self.a[k]
         if sec:
             return FArr(r)  # a section has lower bounds 1
+        if isinstance(r, np.float32):
+            return r  # REAL32: the scalar keeps its kind
         return r.item() if isinstance(r, np.generic) else r
 
     def __setitem__(self, key, value):
         k, _ = self._key(key)
-        self.a[k] = value.a if isinstance(value, FArr) else value
+        self.a[k] = value.a if isinstance(value, FArr) else _store_check(value)
 
     def assign(self, value):
         if isinstance(value, FArr):
@@ -149,7 +204,7 @@ class FArr:
                 raise ValueError(f"shape mismatch in array assignment: {self.a.shape} <- {value.a.shape}")
             self.a[...] = value.a
         else:
-            self.a[...] = value
+            self.a[...] = _store_check(value)
 
     # -- element-wise arithmetic (each NumPy float64 operation is one correctly rounded IEEE operation) ---------------
     @staticmethod
@@ -203,14 +258,14 @@ def assign(cur, value):
     """`lhs = rhs` for a whole variable: arrays are assigned in place (dummy arguments, pointer targets), an unallocated
     allocatable is allocated to the shape of the right-hand side, scalars are rebound"""
     if isinstance(cur, Ref):
-        cur.v = val(value)
+        cur.v = _store_check(val(value))
         return cur
     if isinstance(cur, FArr):
         cur.assign(value)
         return cur
     if isinstance(value, FArr):
         return value.copy()
-    return val(value)
+    return _store_check(val(value))
 
 
 def assign_alloc(cur, value):
@@ -243,6 +298,8 @@ def fpow(x, n):
         return 1.0 / y if n < 0 else y
     if isinstance(x, FArr):
         return FArr(np.power(x.a, FArr._u(n)))
+    if _KIND[0] == 4:
+        return np.power(np.float32(x), np.float32(n))
     return math.pow(x, n)
 
 
@@ -255,7 +312,8 @@ def _seq_sum(x):
     if not isinstance(x, FArr):
         return x
     s = 0 if x.a.dtype.kind in "iu" else 0.0  # sum() accumulates from zero in array element order
-    for e in x.a.ravel(order="F").tolist():
+    flat = x.a.ravel(order="F")
+    for e in (flat if flat.dtype == np.float32 else flat.tolist()):  # float32 elements keep their kind (0.0 is weak)
         s = s + e
     return s
 
@@ -273,6 +331,8 @@ def _ubound(x, dim):
 
 
 def _sign(a, b):
+    if isinstance(a, np.float32) or isinstance(b, np.float32):
+        return np.copysign(np.abs(np.float32(a)), np.float32(b))
     return math.copysign(abs(a), b) if isinstance(a, float) or isinstance(b, float) else (abs(a) if b >= 0 else -abs(a))
 
 
@@ -296,7 +356,7 @@ def _minmax(fn):
             r = FArr._u(args[0])
             for a in args[1:]:
                 r = fn(r, FArr._u(a))
-            return FArr(np.asarray(r, dtype=np.float64))
+            return FArr(np.asarray(r, dtype=rdtype()))
         r = args[0]
         for a in args[1:]:
             r = a if (fn is np.minimum and a < r) or (fn is np.maximum and a > r) else r
@@ -306,7 +366,7 @@ def _minmax(fn):
 
 
 def _elementwise(fn):
-    return lambda x: FArr(fn(x.a)) if isinstance(x, FArr) else float(fn(x))
+    return lambda x: FArr(fn(x.a)) if isinstance(x, FArr) else rl(fn(rl(x)))
 
 
 def _reshape(x, shape):
@@ -316,7 +376,7 @@ def _reshape(x, shape):
 
 INTRINSICS = {
     "reshape": _reshape,
-    "product": lambda x: (int(np.prod(x.a)) if x.a.dtype.kind in "iu" else float(np.prod(x.a))) if isinstance(x, FArr) else x,
+    "product": lambda x: (int(np.prod(x.a)) if x.a.dtype.kind in "iu" else rl(np.prod(x.a))) if isinstance(x, FArr) else x,
     "sum": _seq_sum,
     "size": _size,
     "lbound": _lbound,
@@ -326,14 +386,14 @@ INTRINSICS = {
     "min": _minmax(np.minimum),
     "max": _minmax(np.maximum),
     "abs": lambda x: FArr(np.abs(x.a)) if isinstance(x, FArr) else abs(x),
-    "epsilon": lambda x: float(np.finfo(np.float64).eps),
+    "epsilon": lambda x: rl(np.finfo(rdtype()).eps),
     "any": lambda x: bool(np.any(FArr._u(x))),
     "all": lambda x: bool(np.all(FArr._u(x))),
     "present": lambda x: x is not None,
     "allocated": lambda x: x is not None,
     "associated": lambda x: x is not None,
     "optval": lambda x, default: default if x is None else val(x),  # fortran-lang/stdlib (the reference's only use of it)
-    "real": lambda x, kind=None: float(x),
+    "real": lambda x, kind=None: rl(x),
     "int": lambda x, kind=None: int(x),
     "exp": _elementwise(np.exp),
     "log": _elementwise(np.log),
@@ -547,6 +607,8 @@ class ExprTranslator:
         if k == "num":
             v = re.sub(r"_\w+$", "", v)
             v = re.sub(r"[dD]", "e", v)
+            if _KIND[0] == 4 and re.search(r"[.eE]", v):
+                return f"rl({v})"  # REAL32: a real literal (default real or _rk) is a binary32 value
             return v
         if k == "str":
             return repr(v[1:-1])
@@ -941,7 +1003,7 @@ class Program:
                     emit(1, f"{scope.rename(nm)} = new_{tm.group(1).lower()}()")
             elif dims is not None and not info["pointer"] and not info["allocatable"] and ":" not in [d.strip() for d in split_top(dims)]:
                 bs = ", ".join(f"({lo}, {hi})" for lo, hi in self._bounds(dims, scope))
-                dt = "np.int64" if info["base"].startswith("integer") else "np.float64"
+                dt = "np.int64" if info["base"].startswith("integer") else "None"
                 emit(1, f"{scope.rename(nm)} = FArr.alloc([{bs}], {dt})")
                 if init is not None:
                     emit(1, f"{scope.rename(nm)}.assign({self.ex(init, scope)})")
@@ -1144,7 +1206,8 @@ class Program:
         """translate everything and exec it into the namespace; returns the namespace"""
         ns = self.ns
         ns["np"] = np
-        ns.setdefault("rk", 8)  # the kind parameter of hrweno_kinds (real64); only ever used as a kind argument
+        ns.setdefault("rk", rkind())  # the kind parameter of hrweno_kinds; only ever used as a kind argument
+        ns["rl"] = rl
         dummy = Scope({"proc_dummies": set()}, self)
         # derived types -> Python classes with the declared default component values
         for tname, td in self.types.items():
@@ -1180,7 +1243,7 @@ class Program:
                         order = [int(x) for x in split_top(m.group(3))] if m.group(3) else list(range(1, len(bnds) + 1))
                         shape = [int(x) for x in split_top(m.group(2))]
                         perm_shape = [shape[o - 1] for o in order]  # element order varies fastest along order(1)
-                        tmp = np.array(vals, dtype=np.float64).reshape(perm_shape, order="F")
+                        tmp = np.array(vals, dtype=rdtype()).reshape(perm_shape, order="F")
                         arr.a[...] = np.transpose(tmp, np.argsort([o - 1 for o in order]))
                     else:
                         v = eval(self.ex(init, dummy), ns)
@@ -1231,7 +1294,7 @@ def _elemental(fn):
             out = np.empty_like(x.a)
             flat_in, flat_out = x.a.ravel(order="K"), out.ravel(order="K")
             for i in range(flat_in.size):
-                flat_out[i] = fn(float(flat_in[i]), *rest)
+                flat_out[i] = fn(flat_in[i] if flat_in.dtype == np.float32 else float(flat_in[i]), *rest)
             return FArr(out.reshape(x.a.shape), x.lb)
         return fn(x, *rest)
 
