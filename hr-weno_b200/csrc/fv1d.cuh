@@ -37,6 +37,22 @@
                    // Measured with 3 (profiles/r2o_k2_three_tile_buffers_ab.txt): no gain for k = 3 (0.794 vs 0.797) nor for the
                    // pure streaming k = 1 / rktvd1 stage (0.59 vs 0.60): the prefetch depth is not what limits either
 #endif
+#ifndef HRW_CST
+// results leave through a warp-private staging area as coalesced stores (see CST in fv1d_stage_kernel): 0 never, 1 the
+// k = 1 instantiations, 2 every k.  Measured on one box (profiles/r2ac_k1_coalesced_stores_ab.txt, r2ad_coalesced_stores_all_k.txt):
+// k = 1 ensemble rktvd1 / 2 / 3 0.72 / 0.80 / 0.84 -> 0.86 / 0.92 / 0.93 of the HBM roofline; k = 3 (issue-bound) 0.801 -> 0.797 on one
+// long row and 0.66 -> 0.64 on the ensemble, k = 2 no gain either: the ten extra shared-memory instructions per run cost what
+// the store path gives back.  Results are bit-identical with and without (480 cases, tools/lib_checksums.py).
+#define HRW_CST 1
+#endif
+#ifndef HRW_WIDX_LDS
+#define HRW_WIDX_LDS HRW_CST // staged width indices are read with ld.shared instead of generic loads: 0 / 1 (k = 1) / 2 (every k)
+#endif
+#ifndef HRW_K1_NOX
+// 1: the k = 1 instantiations run without the exchange barrier (see NOX in fv1d_stage_kernel).  Measured
+// (profiles/r2aa_k1_no_exchange_barrier_ab.txt): rktvd1 +2 %, rktvd3 -1 % -- the barrier is not what limits k = 1; off.
+#define HRW_K1_NOX 0
+#endif
 #ifndef HRW_WARP_TILES
 #define HRW_WARP_TILES 0 // 1: every warp overlaps its neighbours by one thread run and exchanges by shuffles (no CTA barrier per
                          // tile).  Measured (profiles/r1_variant_sweeps.txt): the barrier stall disappears but 11 % more instructions
@@ -171,6 +187,36 @@ struct Prefetched {
 // the R one-byte width indices of a run starting at p (global or shared), packed four per word.  Runs of a multiple of
 // four cells start on a 4-B boundary; other (even) run lengths start on a 2-B boundary and are assembled from the aligned
 // words around them (the index arrays are padded, fv.cu).
+// shared-memory accesses with the state space spelled out (a pointer that went through an integer cast compiles to a
+// generic LD, which takes the long-scoreboard path: profiles/r2ab_k2_k1_euler_hotspots.txt)
+__device__ __forceinline__ uint32_t lds_u32(uint32_t addr) {
+   uint32_t v;
+   asm volatile("ld.shared.u32 %0, [%1];" : "=r"(v) : "r"(addr) : "memory");
+   return v;
+}
+__device__ __forceinline__ void sts_f64x2(uint32_t addr, double a, double b) {
+   asm volatile("st.shared.v2.f64 [%0], {%1, %2};" ::"r"(addr), "d"(a), "d"(b) : "memory");
+}
+__device__ __forceinline__ double2 lds_f64x2(uint32_t addr) {
+   double2 v;
+   asm volatile("ld.shared.v2.f64 {%0, %1}, [%2];" : "=d"(v.x), "=d"(v.y) : "r"(addr) : "memory");
+   return v;
+}
+
+// load_widx for a run whose indices were staged in shared memory (byte address `a` in the shared window)
+template <int R>
+__device__ __forceinline__ void load_widx_shared(uint32_t a, uint32_t *out) {
+   constexpr int NW = (R + 3) / 4;
+   constexpr int NL = R % 4 == 0 ? NW : (R + 2 + 3) / 4;
+   const uint32_t q = a & ~3u, sh = (a & 3u) * 8u;
+   uint32_t wd[NL + 1];
+#pragma unroll
+   for (int i = 0; i < NL; ++i) wd[i] = lds_u32(q + 4u * i);
+   wd[NL] = 0u;
+#pragma unroll
+   for (int i = 0; i < NW; ++i) out[i] = R % 4 == 0 ? wd[i] : __funnelshift_r(wd[i], wd[i + 1 < NL ? i + 1 : NL], sh);
+}
+
 template <int R>
 __device__ __forceinline__ void load_widx(const unsigned char *p, uint32_t *out) {
    constexpr int NW = (R + 3) / 4;
@@ -192,10 +238,13 @@ __device__ __forceinline__ void load_widx(const unsigned char *p, uint32_t *out)
    }
 }
 
-template <int K, int COMBINE, class M, int FK, int WK, int R, bool EDGE>
+// STAGE_OUT (interior threads only): the R results go to the shared-memory address `stage` (this thread's slot of its
+// warp's staging area) instead of global memory; the warp writes them out together afterwards.
+template <int K, int COMBINE, class M, int FK, int WK, int R, bool EDGE, bool STAGE_OUT = false>
 __device__ __forceinline__ void fv1d_finish(const Fv1dGeom &g, const StageArgs &s, const double2 *s_wtab, int64_t row, int i0,
                                             const double *w /* window, cell j at w[2+j] */, const double *vl, const double *vr,
-                                            double vr_left, double vl_right, double cL, double lscale, const Prefetched<R> &pf) {
+                                            double vr_left, double vl_right, double cL, double lscale, const Prefetched<R> &pf,
+                                            uint32_t stage = 0u) {
    const int n = (int)g.n;
    // numerical flux at the R+1 faces i0 .. i0+R (face f lies between cells f-1 and f)
    double F[R + 1];
@@ -316,8 +365,13 @@ __device__ __forceinline__ void fv1d_finish(const Fv1dGeom &g, const StageArgs &
 
    double *orow = s.out + row * s.ld_out + i0;
    if constexpr (!EDGE) {
+      if constexpr (STAGE_OUT) {
 #pragma unroll
-      for (int j = 0; j < R; j += 2) *reinterpret_cast<double2 *>(orow + j) = make_double2(res[j], res[j + 1]);
+         for (int j = 0; j < R; j += 2) sts_f64x2(stage + 8u * j, res[j], res[j + 1]);
+      } else {
+#pragma unroll
+         for (int j = 0; j < R; j += 2) *reinterpret_cast<double2 *>(orow + j) = make_double2(res[j], res[j + 1]);
+      }
       if constexpr (COMBINE == C_MS) {
          double *lrow = s.out2 + row * g.ld + i0;
 #pragma unroll
@@ -370,14 +424,33 @@ __global__ void __launch_bounds__(NT, HRW_MINB) fv1d_stage_kernel(const Fv1dGeom
    constexpr bool STAGE_W = WK == WK_DICT && HRW_STAGE_W;
    constexpr int WROW = ((TILE + 15) / 16) * 16 + 16 + (R % 4 ? 16 : 0); // staged index bytes per tile: from the 16-B boundary at or below its first cell
    constexpr int NBUF = WT ? 2 : HRW_NBUF; // (the warp-tile variant keeps its two "consumed" barriers)
+   // k = 1: vl = vr = v (weno.f90:186), so the neighbouring run's edge values are cells of this thread's own register
+   // window and nothing has to be exchanged between threads.  Without the exchange barrier the tile loop has no CTA
+   // barrier at all: each warp releases the staged tile with one arrival on the buffer's "consumed" barrier once its
+   // window is in registers (the protocol of the warp-tile variant), and the producer waits on that barrier before it
+   // refills the buffer.  Warps then drift apart by up to one tile and cover each other's load and store phases, which is
+   // all a stage without arithmetic has to hide.
+   constexpr bool NOX = !WT && K == 1 && NBUF == 2 && HRW_K1_NOX != 0;
+   constexpr bool REL = WT || NOX; // per-warp release of the tile buffers instead of a CTA barrier
+   // k = 1 has no arithmetic to hide the store path under, and the direct stores are its worst part: a thread owns R
+   // consecutive cells, so one warp-wide 16-B store touches 32 pieces 80 B apart (20 lines, 32 half-written sectors) and
+   // the five of them keep the LSU busy five times longer than the 2560 contiguous bytes need; the next iteration then
+   // waits for the stores to take their source registers (profiles/r2ab_k2_k1_euler_hotspots.txt: lg/mio throttle, 7.7 % of the
+   // samples on that register hand-over).  CST: interior threads put their run into a warp-private staging area (16-B
+   // shared stores at the same 80-B stride are conflict-free) and the warp writes its 2560 B as five fully coalesced 16-B
+   // stores per lane.  Lanes on the edge path (row ends, dense output) keep their own scalar stores; their cells are
+   // masked out of the warp's stores.
+   constexpr bool CST = !WT && (HRW_CST == 2 || (HRW_CST == 1 && K == 1));
    static_assert(NBUF >= 2 && NBUF <= 4, "two to four staged tiles");
    __shared__ __align__(128) double s_v[NBUF][SM_N];
    __shared__ __align__(128) double s_a[STAGE_A ? NBUF : 1][STAGE_A ? TILE : 2];
    __shared__ __align__(16) unsigned char s_wi[STAGE_W ? NBUF : 1][STAGE_W ? WROW : 16];
-   __shared__ double s_vr[WT ? 1 : 2][WT ? 1 : NT];
-   __shared__ double s_vl[WT ? 1 : 2][WT ? 1 : NT];
+   __shared__ double s_vr[REL ? 1 : 2][REL ? 1 : NT];
+   __shared__ double s_vl[REL ? 1 : 2][REL ? 1 : NT];
    (void)s_vr;
    (void)s_vl;
+   __shared__ __align__(16) double s_st[CST ? NT * R : 2]; // staging area: warp w owns [32*w*R, 32*(w+1)*R)
+   (void)s_st;
    __shared__ __align__(16) double2 s_wtab[WK == WK_DICT ? 256 : 1];
    __shared__ __align__(8) unsigned long long s_bar[NBUF + 2]; // [0 .. NBUF): tile buffer full (TMA complete_tx); then two "consumed" barriers (warp tiles)
 
@@ -488,7 +561,7 @@ __global__ void __launch_bounds__(NT, HRW_MINB) fv1d_stage_kernel(const Fv1dGeom
       bool pending = tid == 0 && lin + PD * nblk < tile_end;
       auto try_issue = [&](bool block) {
          if (!pending) return;
-         if (WT && it > 0) {
+         if (REL && it > 0) {
             const uint32_t eb = bar_u32 + 8u * NBUF + 8u * (buf ^ 1), ep = (uint32_t)(((it - 1) >> 1) & 1);
             if (block)
                mbar_wait(eb, ep);
@@ -558,7 +631,10 @@ __global__ void __launch_bounds__(NT, HRW_MINB) fv1d_stage_kernel(const Fv1dGeom
          }
          if constexpr (STAGE_W) {
             const int woff = (ptc * TILE) & 15;
-            load_widx<R>(&s_wi[buf][woff + (slot - 1) * R], pf.idx4);
+            if constexpr (HRW_WIDX_LDS == 2 || (HRW_WIDX_LDS == 1 && K == 1))
+               load_widx_shared<R>(sw_u32 + (uint32_t)(buf * WROW + woff + (slot - 1) * R), pf.idx4);
+            else
+               load_widx<R>(&s_wi[buf][woff + (slot - 1) * R], pf.idx4);
          }
       }
 
@@ -600,7 +676,7 @@ __global__ void __launch_bounds__(NT, HRW_MINB) fv1d_stage_kernel(const Fv1dGeom
          w[j] = t.x;
          w[j + 1] = t.y;
       }
-      if constexpr (WT) {
+      if constexpr (REL) {
          // this warp has its part of the tile in registers (the empty asm makes the loads' results a dependency of what
          // follows): release the buffer, one arrival per warp
 #pragma unroll
@@ -624,6 +700,9 @@ __global__ void __launch_bounds__(NT, HRW_MINB) fv1d_stage_kernel(const Fv1dGeom
       if constexpr (WT) {
          vr_left = __shfl_up_sync(0xffffffffu, vr[R - 1], 1);
          vl_right = __shfl_down_sync(0xffffffffu, vl[0], 1);
+      } else if constexpr (NOX) {
+         vr_left = w[1];      // cell i0-1: vr of the last cell of the run to the left
+         vl_right = w[R + 2]; // cell i0+R: vl of the first cell of the run to the right
       } else {
          // exchange arrays are double buffered by iteration parity: a slot is rewritten two iterations later, after
          // the barrier of the iteration in between, which every reader of the old value has passed
@@ -634,7 +713,34 @@ __global__ void __launch_bounds__(NT, HRW_MINB) fv1d_stage_kernel(const Fv1dGeom
          vr_left = s_vr[xb][tid > 0 ? tid - 1 : 0];
          vl_right = s_vl[xb][tid < NT - 1 ? tid + 1 : tid];
       }
-      if (!skip) {
+      if constexpr (CST) {
+         // (the ballot is also the point every lane passes before the staging area is written again: the reads of the
+         // previous iteration are complete)
+         const unsigned okm = __ballot_sync(0xffffffffu, !skip && !edge); // lanes that stage their run
+         const uint32_t st_w = smem_u32(&s_st[(tid & ~31) * R]);
+         if (!skip) {
+            if (!edge)
+               fv1d_finish<K, COMBINE, M, FK, WK, R, false, true>(g, s, s_wtab, row, i0, w, vl, vr, vr_left, vl_right, cL, lscale, pf,
+                                                                  st_w + (uint32_t)(lane * R) * 8u);
+            else
+               fv1d_finish<K, COMBINE, M, FK, WK, R, true>(g, s, s_wtab, row, i0, w, vl, vr, vr_left, vl_right, cL, lscale, pf);
+         }
+         if (okm != 0u) { // warp-uniform
+            __syncwarp();
+            // the warp's runs are consecutive: lane l owns cells [i0w + l*R, i0w + (l+1)*R) of the row
+            const int i0w = __shfl_sync(0xffffffffu, i0, 0);
+            double *ow = s.out + (int64_t)row * s.ld_out + i0w;
+#pragma unroll
+            for (int q = 0; q < R / 2; ++q) {
+               const int c = lane + 32 * q; // 16-B piece of the warp's span; it belongs to the run of lane c / (R/2)
+               if ((okm >> (c / (R / 2))) & 1u) {
+                  const double2 t = lds_f64x2(st_w + 16u * c);
+                  *reinterpret_cast<double2 *>(ow + 2 * c) = t;
+               }
+            }
+            __syncwarp(); // the staging area is rewritten in the next iteration
+         }
+      } else if (!skip) {
          if (!edge)
             fv1d_finish<K, COMBINE, M, FK, WK, R, false>(g, s, s_wtab, row, i0, w, vl, vr, vr_left, vl_right, cL, lscale, pf);
          else
