@@ -188,3 +188,28 @@ def test_real32_fixtures_are_reproducible_and_oracle_equals_live_execution(ref32
                 cnu = None if edges is None else ref32.calc_cnu(edges, k)
                 a = ref32.reconstruct(v, k, 1e-6, cnu=cnu)
                 assert np.array_equal(a[0], vl) and np.array_equal(a[1], vr), (nc, k, edges is None)
+
+
+@pytest.mark.skipif(not os.path.isdir(os.path.join(REFERENCE, "src")), reason="the reference tree is not on this machine")
+def test_real32_oracle_equals_executed_example_programs_on_small_grids(pkg, ref32):
+    """both example programs executed from source in real32 at grid sizes the fixtures do not hold (down to 2 cells,
+    n1 /= n2, every WENO order and RK order, with and without geometric grids + xedges + growth terms): the REAL32 oracle's
+    fused rhs + integrators, bit for bit, including t and fevals"""
+    sys.path.insert(0, os.path.join(ROOT, "tests", "golden"))
+    import make_ref_exec_golden as m
+    from f90py import real_kind
+
+    with real_kind(4):
+        for nc, k, order in [(2, 3, 3), (3, 2, 2), (4, 3, 1), (5, 1, 3), (7, 3, 3), (17, 2, 3), (33, 3, 2)]:
+            live = m.run_example1(npts=4, snaps=(4,), k=k, order=order, nc=nc)
+            assert np.array_equal(_grid32(-5.0, 5.0, nc)[2], live["width"])
+            ode = ref32.rktvd(ref32.FV(pkg.real32.make_desc(nc, k=k, eps=1e-6, width=[live["width"]])), order)
+            u, t = live["ic"].copy(), 0.0
+            for ii in range(5):
+                t = ode.integrate(u, t, F(12.0) * F(ii) / F(100), 1e-2)
+                assert F(t) == live["times"][ii], (nc, k, order, ii)
+            assert np.array_equal(u, live["u_4"]) and ode.fevals == live["fevals"], (nc, k, order)
+        for n1, n2, growth in [(2, 2, False), (3, 5, False), (7, 4, False), (5, 3, True), (9, 11, True)]:
+            kw = dict(grids="geometric", nonuniform=True, dt=2.5e-4, time_end=0.5, growth=True) if growth else {}
+            live = m.run_example2(n1, 2, (0, 2), n2=n2, **kw)
+            _example2(pkg, ref32, live, n1, n2, kw.get("dt", 5e-3), kw.get("time_end", 5.0), growth=growth)
