@@ -7,6 +7,9 @@
 //   namespace hrweno::hrweno_weno    { class weno }                     src/hrweno_weno.f90:23-50
 //   namespace hrweno::hrweno_fluxes  { godunov, lax_friedrichs }        src/hrweno_fluxes.f90:22,47
 //   namespace hrweno::hrweno_tvdode  { class rktvd, class mstvd }       src/hrweno_tvdode.f90:36-48
+//   namespace hrweno::hrweno_fv      { class fv }                       the example `rhs` as one fused device operator
+//   namespace hrweno::hrweno_multi   { class mgpu }                     the same operator + integrators on all GPUs of the box
+//   namespace hrweno::real32         { weno, fv, rktvd, mstvd }         the REAL32 build (src/hrweno_kinds.F90:9-10)
 // Errors: where the reference executes `error stop msg`, these throw hrweno::error carrying the same message.
 #pragma once
 
@@ -207,6 +210,19 @@ class fv {
    void set_flux_coef(int axis, const double *face, const double *cross = nullptr) {
       hrweno::check(hrweno_fv_set_flux_coef(h_, axis, face, cross));
    }
+   // t-dependent flux f(v, x, t) = f(v, x)*g(t) (fluxes.f90:12-18 passes t to the flux); an empty function removes it
+   void set_flux_time_fn(std::function<double(double)> g) {
+      tfn_ = std::move(g);
+      hrweno::check(hrweno_fv_set_flux_time_fn(h_, tfn_ ? &fv::tramp_time : nullptr, this));
+   }
+   // device-resident callers
+   void rhs_dev(double t, const double *v_dev, double *vdot_dev, void *stream = nullptr) {
+      hrweno::check(hrweno_fv_rhs_dev(h_, t, v_dev, vdot_dev, stream));
+   }
+   void max_wavespeed_dev(const double *v_dev, double *out_dev, void *stream = nullptr) {
+      hrweno::check(hrweno_fv_max_wavespeed_dev(h_, v_dev, out_dev, stream));
+   }
+   void set_alpha(double alpha) { hrweno::check(hrweno_fv_set_alpha(h_, alpha)); } // lax_friedrichs' alpha, fluxes.f90:22-45
    ::hrweno_fv *handle() const { return h_; }
    static hrweno_fv_desc desc1d(int64_t nc, int k, double eps, const double *width) {
       hrweno_fv_desc d{};
@@ -225,6 +241,8 @@ class fv {
    }
  private:
    ::hrweno_fv *h_ = nullptr;
+   std::function<double(double)> tfn_;
+   static double tramp_time(void *ctx, double t) { return static_cast<fv *>(ctx)->tfn_(t); }
 };
 } // namespace hrweno_fv
 
@@ -241,6 +259,18 @@ class tvdode { // tvdode.f90:14-34
    int order() const { return hrweno_ode_order(h_); }
    int64_t fevals() const { return hrweno_ode_fevals(h_); }
    int istate() const { return h_ ? hrweno_ode_istate(h_) : -1; }
+   int64_t launches() const { return hrweno_ode_launches(h_); }
+   // device-resident state: u_dev is a dense device vector, integrated in place
+   void integrate_dev(double *u_dev, double &t, double tout, double dt, int itask = 1, void *stream = nullptr) {
+      hrweno::check(hrweno_ode_integrate_dev(h_, u_dev, &t, tout, dt, itask, stream));
+   }
+   // fused integrators: hand the state over once, integrate from output time to output time without the dense <-> padded
+   // copies of every call, fetch it when output is due
+   void attach(const double *u_dev, void *stream = nullptr) { hrweno::check(hrweno_ode_attach(h_, u_dev, stream)); }
+   void integrate_attached(double &t, double tout, double dt, int itask = 1, void *stream = nullptr) {
+      hrweno::check(hrweno_ode_integrate_attached(h_, &t, tout, dt, itask, stream));
+   }
+   void fetch(double *u_dev, void *stream = nullptr) { hrweno::check(hrweno_ode_fetch(h_, u_dev, stream)); }
    tvdode(const tvdode &) = delete;
    tvdode &operator=(const tvdode &) = delete;
    virtual ~tvdode() { hrweno_ode_destroy(h_); }
@@ -302,4 +332,157 @@ class mstvd : public tvdode { // mstvd(fu, neq), tvdode.f90:180-201
    }
 };
 } // namespace hrweno_tvdode
+
+namespace hrweno_multi {
+// The fused operator and its integrator on every GPU of the box from ONE process (hrweno_mgpu_*): the grid is cut into
+// slabs (1D: along x; 2D: along x2; ensembles: rows), u is the caller's global vector in the reference's storage order.
+class mgpu {
+ public:
+   // ngpus <= 0: all visible devices; devices == nullptr: 0 .. ngpus-1
+   explicit mgpu(const hrweno_fv_desc &d, int ngpus = 0, const int *devices = nullptr) {
+      hrweno::check(hrweno_mgpu_create(&h_, &d, ngpus, devices));
+   }
+   mgpu(const mgpu &) = delete;
+   mgpu &operator=(const mgpu &) = delete;
+   ~mgpu() { hrweno_mgpu_destroy(h_); }
+   int ngpus() const { return hrweno_mgpu_ngpus(h_); }
+   struct slab_info {
+      int device;
+      int64_t offset, count; // unknowns [offset, offset + count) of the global vector
+   };
+   slab_info slab(int rank) const {
+      slab_info s{};
+      hrweno::check(hrweno_mgpu_slab(h_, rank, &s.device, &s.offset, &s.count));
+      return s;
+   }
+   // general operators, GLOBAL arrays (weno(..., xedges); example2:140,153; fluxes.f90:12-18)
+   void set_xedges(int axis, const double *xedges) { hrweno::check(hrweno_mgpu_set_xedges(h_, axis, xedges)); }
+   void set_flux_coef(int axis, const double *face, const double *cross = nullptr) {
+      hrweno::check(hrweno_mgpu_set_flux_coef(h_, axis, face, cross));
+   }
+   void set_flux_time_fn(std::function<double(double)> g) {
+      tfn_ = std::move(g);
+      hrweno::check(hrweno_mgpu_set_flux_time_fn(h_, tfn_ ? &mgpu::tramp_time : nullptr, this));
+   }
+   void rktvd(int order) { hrweno::check(hrweno_mgpu_rktvd(h_, order)); } // ode = rktvd(rhs, neq, order), tvdode.f90:69-95
+   void mstvd() { hrweno::check(hrweno_mgpu_mstvd(h_)); }                 // ode = mstvd(rhs, neq), tvdode.f90:180-201
+   // call ode%integrate(u, t, tout, dt [, itask]) with the global host vector
+   void integrate(double *u, double &t, double tout, double dt, int itask = 1) {
+      hrweno::check(hrweno_mgpu_integrate(h_, u, &t, tout, dt, itask));
+   }
+   // state resident on the GPUs between output times
+   void upload(const double *u) { hrweno::check(hrweno_mgpu_upload(h_, u)); }
+   void integrate_resident(double &t, double tout, double dt, int itask = 1) {
+      hrweno::check(hrweno_mgpu_integrate_resident(h_, &t, tout, dt, itask));
+   }
+   void download(double *u) { hrweno::check(hrweno_mgpu_download(h_, u)); }
+   // alpha = max |f'(u)| over all slabs of the resident state; install: also the Lax-Friedrichs alpha from the next stage on
+   double max_wavespeed(bool install = false) {
+      double a = 0.0;
+      hrweno::check(hrweno_mgpu_max_wavespeed(h_, &a, install ? 1 : 0));
+      return a;
+   }
+   void set_alpha(double alpha) { hrweno::check(hrweno_mgpu_set_alpha(h_, alpha)); }
+   int64_t fevals() const { return hrweno_mgpu_fevals(h_); }
+   int64_t launches() const { return hrweno_mgpu_launches(h_); }
+ private:
+   ::hrweno_mgpu *h_ = nullptr;
+   std::function<double(double)> tfn_;
+   static double tramp_time(void *ctx, double t) { return static_cast<mgpu *>(ctx)->tfn_(t); }
+};
+} // namespace hrweno_multi
+
+// The REAL32 build of the reference (src/hrweno_kinds.F90:9-10: -DREAL32 makes rk = real32 for the whole library): the
+// same types with float in every position, over the hrweno_*_f32 entry points.  One GPU, the reference's operation order.
+namespace real32 {
+class weno { // weno.f90:23-50 with rk = real32
+ public:
+   int64_t ncells = 0;
+   int k = 3;
+   float eps = 1e-6f;
+   weno(int64_t ncells_, int k_ = 3, float eps_ = 1e-6f, const std::vector<float> *xedges = nullptr) : ncells(ncells_), k(k_), eps(eps_) {
+      if (xedges && (int64_t)xedges->size() != ncells_ + 1) throw hrweno::error(HRWENO_EINVAL, "Invalid input 'xedges': size(xedges) /= ncells + 1.");
+      hrweno::check(hrweno_weno_f32_create(&h_, ncells_, k_, eps_, xedges ? xedges->data() : nullptr));
+   }
+   weno(const weno &) = delete;
+   weno &operator=(const weno &) = delete;
+   ~weno() { hrweno_weno_f32_destroy(h_); }
+   void reconstruct(const float *v, float *vl, float *vr) const { hrweno::check(hrweno_weno_f32_reconstruct(h_, v, vl, vr)); } // weno.f90:129-219
+ private:
+   ::hrweno_weno_f32 *h_ = nullptr;
+};
+
+class fv { // the example `rhs` (example1:72-109, example2:73-129) with rk = real32
+ public:
+   explicit fv(const hrweno_fv_desc_f32 &d) { hrweno::check(hrweno_fv_f32_create(&h_, &d)); }
+   fv(const fv &) = delete;
+   fv &operator=(const fv &) = delete;
+   ~fv() { hrweno_fv_f32_destroy(h_); }
+   int64_t neq() const { return hrweno_fv_f32_neq(h_); }
+   void rhs(float t, const float *v, float *vdot) { hrweno::check(hrweno_fv_f32_rhs(h_, t, v, vdot)); }
+   void rhs_dev(float t, const float *v_dev, float *vdot_dev, void *stream = nullptr) {
+      hrweno::check(hrweno_fv_f32_rhs_dev(h_, t, v_dev, vdot_dev, stream));
+   }
+   void set_xedges(int axis, const float *xedges) { hrweno::check(hrweno_fv_f32_set_xedges(h_, axis, xedges)); }
+   void set_flux_coef(int axis, const float *face, const float *cross = nullptr) {
+      hrweno::check(hrweno_fv_f32_set_flux_coef(h_, axis, face, cross));
+   }
+   void set_flux_time_fn(std::function<float(float)> g) {
+      tfn_ = std::move(g);
+      hrweno::check(hrweno_fv_f32_set_flux_time_fn(h_, tfn_ ? &fv::tramp_time : nullptr, this));
+   }
+   ::hrweno_fv_f32 *handle() const { return h_; }
+   static hrweno_fv_desc_f32 desc1d(int64_t nc, int k, float eps, const float *width) {
+      hrweno_fv_desc_f32 d{};
+      d.abi_version = HRWENO_ABI_VERSION;
+      d.ndim = 1; d.n[0] = nc; d.n[1] = 1; d.rows = 1; d.k = k; d.eps = eps;
+      d.flux_model = HRWENO_FLUX_BURGERS; d.flux_scheme = HRWENO_SCHEME_GODUNOV; d.bc = HRWENO_BC_COPY_NEIGHBOUR;
+      d.grid_kind = HRWENO_GRID_WIDTH_ARRAY; d.mode = HRWENO_MODE_STRICT; d.flux_coef[0] = d.flux_coef[1] = 1.0f; d.alpha = 1.0f;
+      d.width[0] = width; d.nranks = 1;
+      return d;
+   }
+   static hrweno_fv_desc_f32 desc2d(int64_t nc1, int64_t nc2, int k, float eps, const float *w1, const float *w2) {
+      hrweno_fv_desc_f32 d = desc1d(nc1, k, eps, w1);
+      d.ndim = 2; d.n[1] = nc2; d.width[1] = w2;
+      d.flux_model = HRWENO_FLUX_LINEAR; d.bc = HRWENO_BC_ZERO_FLUX;
+      return d;
+   }
+ private:
+   ::hrweno_fv_f32 *h_ = nullptr;
+   std::function<float(float)> tfn_;
+   static float tramp_time(void *ctx, float t) { return static_cast<fv *>(ctx)->tfn_(t); }
+};
+
+class tvdode { // tvdode.f90:14-34 with rk = real32
+ public:
+   int64_t fevals() const { return hrweno_ode_f32_fevals(h_); }
+   int istate() const { return h_ ? hrweno_ode_f32_istate(h_) : -1; }
+   int64_t launches() const { return hrweno_ode_f32_launches(h_); }
+   // call ode%integrate(u, t, tout, dt [, itask])  (tvdode.f90:97-178, 203-271): t = t + dt accumulates in real32
+   void integrate(float *u, float &t, float tout, float dt, int itask = 1) { hrweno::check(hrweno_ode_f32_integrate(h_, u, &t, tout, dt, itask)); }
+   void integrate_dev(float *u_dev, float &t, float tout, float dt, int itask = 1, void *stream = nullptr) {
+      hrweno::check(hrweno_ode_f32_integrate_dev(h_, u_dev, &t, tout, dt, itask, stream));
+   }
+   tvdode(const tvdode &) = delete;
+   tvdode &operator=(const tvdode &) = delete;
+   virtual ~tvdode() { hrweno_ode_f32_destroy(h_); }
+ protected:
+   tvdode() = default;
+   ::hrweno_ode_f32 *h_ = nullptr;
+};
+class rktvd : public tvdode { // rktvd(rhs, neq, order), tvdode.f90:69-95
+ public:
+   rktvd(fv &rhs, int64_t neq, int order) {
+      if (neq != rhs.neq()) throw hrweno::error(HRWENO_EINVAL, "neq does not match the finite-volume operator");
+      hrweno::check(hrweno_rktvd_f32_create_fused(&h_, rhs.handle(), order));
+   }
+};
+class mstvd : public tvdode { // mstvd(rhs, neq), tvdode.f90:180-201
+ public:
+   mstvd(fv &rhs, int64_t neq) {
+      if (neq != rhs.neq()) throw hrweno::error(HRWENO_EINVAL, "neq does not match the finite-volume operator");
+      hrweno::check(hrweno_mstvd_f32_create_fused(&h_, rhs.handle()));
+   }
+};
+} // namespace real32
 } // namespace hrweno
