@@ -10,7 +10,13 @@ import numpy as np
 
 
 class grid1:
-    def __init__(self):
+    """`grid1()` evaluates in real64; `grid1(np.float32)` is the type of the reference's REAL32 build (hrweno_kinds.F90:9-10):
+    every scalar and array of the set-up is a float32 and every operation rounds to float32."""
+
+    def __init__(self, dtype=np.float64):
+        self.dtype = np.dtype(dtype)
+        if self.dtype not in (np.dtype(np.float64), np.dtype(np.float32)):
+            raise ValueError("grid1: real64 or real32")
         self.ncells = 0
         self.scale = ""
         self.name = ""
@@ -18,10 +24,10 @@ class grid1:
 
     def _compute(self, xedges, name):  # grids.f90:232-250
         self.ncells = len(xedges) - 1
-        self.edges = np.ascontiguousarray(xedges, dtype=np.float64)
+        self.edges = np.ascontiguousarray(xedges, dtype=self.dtype)
         self.left = self.edges[:-1]
         self.right = self.edges[1:]
-        self.center = (self.left + self.right) / 2
+        self.center = (self.left + self.right) / self.dtype.type(2)
         self.width = self.right - self.left
         self.name = name
 
@@ -30,9 +36,11 @@ class grid1:
             raise ValueError("Invalid input 'xmin', 'xmax'. Valid range: xmax > xmin.")
         if ncells < 1:
             raise ValueError("Invalid input 'ncells'. Valid range: ncells > 1.")
-        rx = (xmax - xmin) / ncells
+        T = self.dtype.type
+        xmin, xmax = T(xmin), T(xmax)
+        rx = (xmax - xmin) / T(ncells)
         self.scale = "linear"
-        self._compute(xmin + rx * np.arange(ncells + 1, dtype=np.float64), name)
+        self._compute(xmin + rx * np.arange(ncells + 1, dtype=self.dtype), name)
         return self
 
     def bilinear(self, xmin, xcross, xmax, ncells, name=""):  # grids.f90:86-136
@@ -42,10 +50,12 @@ class grid1:
             raise ValueError("Invalid input 'xcross', 'xmax'. Valid range: xmax > xcross.")
         if min(ncells) < 1:
             raise ValueError("Invalid input 'ncells'. Valid range: ncells(i) >= 1.")
-        rx1 = (xcross - xmin) / ncells[0]
-        rx2 = (xmax - xcross) / ncells[1]
-        e1 = xmin + rx1 * np.arange(ncells[0] + 1, dtype=np.float64)
-        e2 = xcross + rx2 * np.arange(1, ncells[1] + 1, dtype=np.float64)
+        T = self.dtype.type
+        xmin, xcross, xmax = T(xmin), T(xcross), T(xmax)
+        rx1 = (xcross - xmin) / T(ncells[0])
+        rx2 = (xmax - xcross) / T(ncells[1])
+        e1 = xmin + rx1 * np.arange(ncells[0] + 1, dtype=self.dtype)
+        e2 = xcross + rx2 * np.arange(1, ncells[1] + 1, dtype=self.dtype)
         self.scale = "bilinear"
         self._compute(np.concatenate([e1, e2]), name)
         return self
@@ -57,9 +67,11 @@ class grid1:
             raise ValueError("Invalid input 'xmin', 'xmax'. Valid range: xmax > xmin.")
         if ncells < 1:
             raise ValueError("Invalid input 'ncells'. Valid range: ncells > 1.")
-        rx = np.log(xmax / xmin) / ncells
+        T = self.dtype.type
+        xmin, xmax = T(xmin), T(xmax)
+        rx = np.log(xmax / xmin) / T(ncells)
         self.scale = "log"
-        self._compute(np.exp(np.log(xmin) + rx * np.arange(ncells + 1, dtype=np.float64)), name)
+        self._compute(np.exp(np.log(xmin) + rx * np.arange(ncells + 1, dtype=self.dtype)), name)
         return self
 
     def geometric(self, xmin, xmax, ratio, ncells, name=""):  # grids.f90:182-230
@@ -69,21 +81,24 @@ class grid1:
             raise ValueError("Invalid input 'ratio'. Valid range: ratio > 0")
         if ncells < 1:
             raise ValueError("Invalid input 'ncells'. Valid range: ncells > 1")
-        a = (xmax - xmin) / (float(_powi(ratio, np.array([ncells]))[0]) - 1.0)
+        T = self.dtype.type
+        xmin, xmax, ratio = T(xmin), T(xmax), T(ratio)
+        a = (xmax - xmin) / (_powi(ratio, np.array([ncells]))[0] - T(1))
         self.scale = "geometric"
-        self._compute(xmin + a * (_powi(ratio, np.arange(ncells + 1)) - 1), name)
+        self._compute(xmin + a * (_powi(ratio, np.arange(ncells + 1)) - T(1)), name)
         return self
 
 
 def _powi(x, m):
     """real**integer as gfortran evaluates `ratio**i` (grids.f90:223-225): binary exponentiation, low bit first
     (libgcc __powidf2 / libgfortran pow_r8_i4), vectorised over the non-negative integer exponents m"""
+    T = type(x) if isinstance(x, np.floating) else np.float64  # the kind of x: products round to it
     n = np.asarray(m, dtype=np.int64).copy()
-    y = np.where(n & 1, float(x), 1.0)
-    xx = float(x)
+    xx = T(x)
+    y = np.where(n & 1, xx, T(1)).astype(T)
     n >>= 1
     while np.any(n):
         xx = xx * xx
-        y = np.where(n & 1, y * xx, y)
+        y = np.where(n & 1, y * xx, y).astype(T)
         n >>= 1
     return y

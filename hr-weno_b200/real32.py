@@ -18,6 +18,13 @@ def _f32(a):
     return np.ascontiguousarray(a, dtype=F32)
 
 
+def grid1():
+    """type(grid1) of the REAL32 build (grids.f90:10-37 with rk = real32): edges / center / width evaluated in float32"""
+    from .hrweno_grids import grid1 as _grid1
+
+    return _grid1(F32)
+
+
 def make_desc(n, k=3, eps=1e-6, rows=1, flux_model=_abi.FLUX_BURGERS, flux_scheme=_abi.SCHEME_GODUNOV, flux_coef=(1.0, 1.0), alpha=1.0,
               bc=_abi.BC_COPY_NEIGHBOUR, width=None, linear=None):
     """hrweno_fv_desc_f32; `width` = per-axis float32 arrays (grid1 evaluated in real32), or `linear` = (xmin, xmax)"""

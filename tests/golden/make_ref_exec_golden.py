@@ -251,7 +251,15 @@ def main32():
         grids = {"linear": g.edges.a.copy(), "linear_center": g.center.a.copy(), "linear_width": g.width.a.copy()}
         callm(g, "geometric", R(1e1), R(1e3), R(1.1), 100)
         grids.update(geometric=g.edges.a.copy(), geometric_width=g.width.a.copy())
+        callm(g, "geometric", R(0.0), R(10.0), R(1.02), 24)  # the grids of the example2 + growth fixture
+        grids["geometric_24"] = g.edges.a.copy()
+        callm(g, "bilinear", R(0.0), R(1e1), R(1e3), FArr(np.array([124, 365], dtype=np.int64)))  # test_grid.f90:128-160
+        grids.update(bilinear=g.edges.a.copy(), bilinear_center=g.center.a.copy())
+        callm(g, "log", R(1e-1), R(1e3), 1000)
+        grids["log"] = g.edges.a.copy()
         np.savez(os.path.join(OUT, "ref_exec_f32_grids.npz"), **grids)
+        if "--only-grids" in sys.argv:
+            return
         print(f"real32: reconstruct / fluxes / tvdode / grids done ({time.time() - t0:.0f} s)", flush=True)
         np.savez(os.path.join(OUT, "ref_exec_f32_example1.npz"), **run_example1(npts=100, snaps=(0, 1, 10, 50, 100)))
         print(f"real32: example1 as shipped, 101 outputs done ({time.time() - t0:.0f} s)", flush=True)

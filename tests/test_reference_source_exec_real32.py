@@ -92,6 +92,26 @@ def test_real32_linear_grid_mirror_equals_reference_source():
     assert np.array_equal(e, g["linear"]) and np.array_equal(c, g["linear_center"]) and np.array_equal(w, g["linear_width"])
 
 
+def test_real32_grid1_mirror_equals_reference_source(pkg):
+    """hrweno_b200.real32.grid1 (the host-side set-up a REAL32 caller uses) against grid1 executed from source in real32:
+    linear / geometric / bilinear bit for bit, log to 2 ulp of float32 (libm's logf / expf are not the path)"""
+    g = gold("grids")
+    G = pkg.real32.grid1
+    lin = G().linear(-5.0, 5.0, 100)
+    assert lin.edges.dtype == F and lin.center.dtype == F and lin.width.dtype == F
+    assert np.array_equal(lin.edges, g["linear"]) and np.array_equal(lin.center, g["linear_center"]) and np.array_equal(lin.width, g["linear_width"])
+    geo = G().geometric(1e1, 1e3, 1.1, 100)
+    assert np.array_equal(geo.edges, g["geometric"]) and np.array_equal(geo.width, g["geometric_width"])
+    assert np.array_equal(G().geometric(0.0, 10.0, 1.02, 24).edges, g["geometric_24"])
+    bil = G().bilinear(0.0, 1e1, 1e3, [124, 365])
+    assert np.array_equal(bil.edges, g["bilinear"]) and np.array_equal(bil.center, g["bilinear_center"])
+    lg = G().log(1e-1, 1e3, 1000)
+    assert lg.edges.dtype == F and np.max(np.abs(lg.edges / g["log"] - F(1))) <= 2 * np.finfo(F).eps
+    # the example2 + growth fixture's grids are these
+    g2 = gold("example2_growth")
+    assert np.array_equal(G().geometric(0.0, 10.0, 1.02, 24).edges, g2["edges1"]) and np.array_equal(G().geometric(0.0, 10.0, 1.03, 18).edges, g2["edges2"])
+
+
 def _example1(pkg, ref32, g_times, u0, width, k, order, scheme, snaps, final=None):
     """example1's driver loop (example1:55-65) in real32: time_out = time_end*ii/num_time_points in binary32.  `ref32` is
     the module that provides FV / rktvd / mstvd: the oracle here, the CUDA path (pkg.real32) in the GPU tests"""
