@@ -1,7 +1,12 @@
 !> ISO_C_BINDING shim: the reference's module / type / procedure names on top of libhrweno_b200.so.
 !!
-!! NOT COMPILED IN THIS REPOSITORY'S CI: the build image has no Fortran compiler (see DESIGN.md).  It is
-!! the binding a maintainer adds to HR-WENO so that example1/example2 re-link against the B200 library:
+!! NOT COMPILED IN THIS REPOSITORY'S CI: the build image has no Fortran compiler (see DESIGN.md).  What the CI does
+!! instead: tools/f90exec (f90py.py + f90c.py) EXECUTES this file statement by statement, with every `bind(c)` interface
+!! body below marshalled from its own dummy declarations (F2018 18.3.6) into a real call of the shared library, under the
+!! reference's unmodified example programs and test suites (tests/test_fortran_shim_exec.py) -- and, on the GPU box, against
+!! libhrweno_b200.so itself (tests/test_zzzz_gpu_fortran_shim_exec.py).  That is an interpreter, not a compiler: syntax a
+!! compiler would reject and the interpreter accepts remains possible.
+!! It is the binding a maintainer adds to HR-WENO so that example1/example2 re-link against the B200 library:
 !!     gfortran -c hrweno_b200_shim.f90 && gfortran example1.f90 hrweno_b200_shim.o -lhrweno_b200
 !! `hrweno_kinds` and `hrweno_grids` are used unchanged from the reference (grids, set-up and I/O stay
 !! on the host); this file replaces hrweno_weno, hrweno_fluxes (re-exported unchanged: pointwise host
@@ -69,6 +74,15 @@ module hrweno_b200_c
          real(c_double), intent(out) :: vl(*), vr(*)
          integer(c_int) :: st
       end function
+      ! the same call in subroutine form: a pure FUNCTION may not have intent(out) dummies, a pure subroutine may, and
+      ! `reconstruct` has to stay pure for the reference's `pure subroutine rhs` (example1:72,93) to compile
+      pure subroutine hrweno_weno_reconstruct_s(w, v, vl, vr, st) bind(c, name="hrweno_weno_reconstruct_s")
+         import :: c_ptr, c_int, c_double
+         type(c_ptr), value :: w
+         real(c_double), intent(in) :: v(*)
+         real(c_double), intent(out) :: vl(*), vr(*)
+         integer(c_int), intent(out) :: st
+      end subroutine
       function hrweno_fv_create(out, desc) bind(c, name="hrweno_fv_create") result(st)
          import :: c_ptr, c_int, hrweno_fv_desc
          type(c_ptr), intent(out) :: out
@@ -282,7 +296,8 @@ end module hrweno_b200_c
 
 module hrweno_weno
 !! Drop-in for src/hrweno_weno.f90: same public names (weno, c1, c2, c3), same constructor and
-!! reconstruct signatures (weno.f90:44,48-50,54,129).  `reconstruct` is no longer `pure`: it calls C.
+!! reconstruct signatures (weno.f90:44,48-50,54,129).  `reconstruct` stays `pure` (the C entry point is declared pure
+!! in its interface body: it defines nothing but vl, vr and its status); `error stop` in a pure procedure is F2018.
    use, intrinsic :: iso_c_binding
    use hrweno_kinds, only: rk
    use hrweno_b200_c
@@ -347,13 +362,13 @@ contains
       end if
    end function weno_init
 
-   subroutine weno_reconstruct(self, v, vl, vr)
+   pure subroutine weno_reconstruct(self, v, vl, vr)
       class(weno), intent(in) :: self
       real(rk), intent(in), contiguous :: v(:)   ! strided actuals (example2:107) are copied in by the compiler
       real(rk), intent(out), contiguous :: vl(:), vr(:)
       integer(c_int) :: st
-      st = hrweno_weno_reconstruct(self%handle, v, vl, vr)
-      if (st /= 0) error stop last_error_string()
+      call hrweno_weno_reconstruct_s(self%handle, v, vl, vr, st)
+      if (st /= 0) error stop "hrweno_weno_reconstruct failed (hrweno_last_error() has the text)"
    end subroutine weno_reconstruct
 
    subroutine weno_destroy(self)
@@ -407,12 +422,12 @@ module hrweno_tvdode
    type, abstract :: tvdode
       integer :: neq
       integer :: order
+      integer :: fevals = 0   ! tvdode.f90:22-23: public components; mirrored from the C object after every call,
+      integer :: istate = 0   ! so `ode%fevals` / `ode%istate` of the reference's programs and tests compile unchanged
       character(:), allocatable :: msg
       type(c_ptr) :: handle = c_null_ptr
       type(integrand_holder), pointer :: holder => null()
    contains
-      procedure, pass(self) :: fevals => tvdode_fevals   ! a function now: the counter lives in the C object
-      procedure, pass(self) :: istate => tvdode_istate
       procedure, pass(self) :: integrate => tvdode_integrate
       procedure, pass(self) :: destroy => tvdode_destroy
    end type tvdode
@@ -497,8 +512,16 @@ contains
       integer(c_int), intent(in) :: st
       if (st /= 0) then
          self%msg = last_error_string()   ! tvdode.f90:83,89 texts
+         self%istate = -1
          error stop self%msg
       end if
+      call mirror(self)
+   end subroutine
+
+   subroutine mirror(self)
+      class(tvdode), intent(inout) :: self
+      self%fevals = int(hrweno_ode_fevals(self%handle))
+      self%istate = int(hrweno_ode_istate(self%handle))
    end subroutine
 
    subroutine tvdode_integrate(self, u, t, tout, dt, itask)
@@ -512,18 +535,12 @@ contains
       itask_ = 1
       if (present(itask)) itask_ = int(itask, c_int)
       st = hrweno_ode_integrate(self%handle, u, t, tout, dt, itask_)
-      if (st /= 0) error stop last_error_string()
+      call mirror(self)
+      if (st /= 0) then
+         self%msg = last_error_string()
+         error stop self%msg
+      end if
    end subroutine
-
-   integer function tvdode_fevals(self) result(n)
-      class(tvdode), intent(in) :: self
-      n = int(hrweno_ode_fevals(self%handle))
-   end function
-
-   integer function tvdode_istate(self) result(n)
-      class(tvdode), intent(in) :: self
-      n = int(hrweno_ode_istate(self%handle))
-   end function
 
    subroutine tvdode_destroy(self)
       class(tvdode), intent(inout) :: self

@@ -99,6 +99,7 @@ PROTOTYPES = {
     "hrweno_weno_get_cnu": (C.c_int, [C.c_void_p, C.c_void_p]),
     "hrweno_weno_set_mode": (C.c_int, [C.c_void_p, C.c_int]),
     "hrweno_weno_reconstruct": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),
+    "hrweno_weno_reconstruct_s": (None, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),
     "hrweno_weno_reconstruct_batch": (
         C.c_int,
         [C.c_void_p, C.c_int64, C.c_void_p, C.c_int64, C.c_int64, C.c_void_p, C.c_void_p, C.c_int64],

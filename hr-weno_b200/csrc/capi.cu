@@ -148,6 +148,11 @@ int hrweno_weno_reconstruct(const hrweno_weno *h, const double *v, double *vl, d
    return hrweno_weno_reconstruct_batch(h, 1, v, w->ncells, 1, vl, vr, w->ncells);
 }
 
+void hrweno_weno_reconstruct_s(const hrweno_weno *h, const double *v, double *vl, double *vr, int *status) {
+   const int st = hrweno_weno_reconstruct(h, v, vl, vr);
+   if (status) *status = st;
+}
+
 // ---- fluxes ----------------------------------------------------------------------------------------
 double hrweno_lax_friedrichs(hrweno_flux_fn f, void *ctx, double vm, double vp, const double *x, int nx, double t,
                              double alpha) {

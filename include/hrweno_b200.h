@@ -112,6 +112,11 @@ int hrweno_weno_get_cnu(const hrweno_weno *w, double *cnu_host);
 /* weno_reconstruct (weno.f90:129-219): v(ncells) -> vl(ncells), vr(ncells), host memory.
  * Re-entrant for one handle (the reference procedure is pure with intent(in) self). */
 int hrweno_weno_reconstruct(const hrweno_weno *w, const double *v, double *vl, double *vr);
+/* The same call in subroutine form (status through the last argument).  The reference's `reconstruct` is `pure`
+ * (weno.f90:129) and is called from `pure subroutine rhs` (example1:72,93): Fortran lets an interface body promise
+ * `pure` for a C procedure, but a pure FUNCTION may not have intent(out) arguments, so the Fortran shim binds this one
+ * as `pure subroutine` and the reference's programs keep their `pure` prefixes. */
+void hrweno_weno_reconstruct_s(const hrweno_weno *w, const double *v, double *vl, double *vr, int *status);
 /* `rows` independent rows of ncells cells; element (row, i) of v at v[row*ldv + i*incv]
  * (incv > 1 expresses the strided sections of example2:107); outputs at [row*ldo + i]. */
 int hrweno_weno_reconstruct_batch(const hrweno_weno *w, int64_t rows, const double *v, int64_t ldv,

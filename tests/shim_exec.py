@@ -1,0 +1,107 @@
+"""Shared harness of the Fortran-shim execution tests (TEST INFRASTRUCTURE).
+
+fortran/hrweno_b200_shim.f90 is the binding a Fortran host uses; no Fortran compiler exists in this image, so the tests
+EXECUTE its source through tools/f90exec (f90py.py translates the statements, f90c.py turns every `bind(c)` interface body
+into a real call of a shared library, marshalled from the Fortran declarations alone).  The library is
+  * on a machine without a GPU: tests/cpp/abi_on_oracle.c -- the product's C ABI implemented on the CPU oracle, built here
+    into a temporary directory (the tests are the only thing that ever loads it);
+  * on the GPU box: hr-weno_b200/lib/libhrweno_b200.so itself.
+"""
+import ctypes
+import os
+import subprocess
+import sys
+
+import numpy as np
+
+from conftest import ROOT
+
+sys.path.insert(0, os.path.join(ROOT, "tools", "f90exec"))
+import f90py  # noqa: E402
+
+SHIM = os.path.join(ROOT, "fortran", "hrweno_b200_shim.f90")
+PROGRAMS = os.path.join(ROOT, "fortran", "examples")
+REFERENCE = os.environ.get("HRWENO_REFERENCE", "/root/reference")
+GOLDEN = os.path.join(ROOT, "tests", "golden")
+
+
+def build_abi_on_oracle(outdir):
+    """gcc tests/cpp/abi_on_oracle.c against oracle/libhrweno_oracle.so -> <outdir>/libhrweno_abi_on_oracle.so"""
+    so = os.path.join(str(outdir), "libhrweno_abi_on_oracle.so")
+    odir = os.path.join(ROOT, "oracle")
+    cmd = ["gcc", "-O2", "-std=c11", "-fPIC", "-shared", "-Wall", "-Wextra", "-Werror", "-I", os.path.join(ROOT, "include"), "-I", odir,
+           os.path.join(ROOT, "tests", "cpp", "abi_on_oracle.c"), "-o", so, "-L", odir, "-lhrweno_oracle", f"-Wl,-rpath,{odir}",
+           "-Wl,-Bsymbolic"]  # the product library is loaded RTLD_GLOBAL in the same process and exports the same names: this
+    #                           library's own calls between its entry points must bind to its own definitions
+    proc = subprocess.run(cmd, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)
+    assert proc.returncode == 0, proc.stdout
+    return ctypes.CDLL(so)
+
+
+def program_on_shim(lib, sources, skip=(), reference_modules=(), skip_io=False):
+    """translate: [reference modules that stay on the host] + the shim + `sources`; bind(c) calls go to `lib`"""
+    P = f90py.Program(skip_io=skip_io)
+    for f in reference_modules:
+        P.add_source(os.path.join(REFERENCE, f))
+    P.add_source(SHIM)
+    for path in sources:
+        P.add_source(path, skip=skip)
+    P.clib = lib
+    return P
+
+
+def run_own_program(lib, name):
+    """one of fortran/examples/*.f90 (self-contained programs written for this repository); returns its variables"""
+    P = program_on_shim(lib, [os.path.join(PROGRAMS, name + ".f90")])
+    ns = P.build()
+    ns["main_" + name]()
+    return ns, P
+
+
+def assert_history_equals_fixture(ns, fixture, snaps):
+    """`history(:, io)`, the output times and the fevals counter of a program against an executed-reference-source fixture"""
+    g = np.load(os.path.join(GOLDEN, fixture))
+    h = ns["history"].a
+    for i in snaps:
+        assert np.array_equal(h[:, i], g[f"u_{i}"]), f"{fixture}: output {i} differs (max {np.max(np.abs(h[:, i] - g[f'u_{i}'])):.3e})"
+    assert np.array_equal(ns["tgrid"].a, g["times"]), "output times differ"
+    assert int(ns["nfev"]) == int(g["fevals"])
+
+
+# what each self-contained program reproduces: (fixture, outputs held by the fixture, C entry points it must have gone through)
+OWN_PROGRAMS = {
+    "burgers_fused": ("ref_exec_example1.npz", (0, 1, 50, 100), {"hrweno_fv_create", "hrweno_rktvd_create_fused", "hrweno_ode_integrate"}),
+    "burgers_host_rhs": ("ref_exec_example1_lf.npz", (0, 50, 100),
+                         {"hrweno_weno_create", "hrweno_rktvd_create_host", "hrweno_ode_integrate", "hrweno_weno_reconstruct_s"}),
+    "pbe2d_fused": ("ref_exec_example2_40.npz", (0, 1, 50, 100), {"hrweno_fv_create", "hrweno_mstvd_create_fused", "hrweno_ode_integrate"}),
+}
+
+
+def check_weno_type(lib, ref):
+    """type(weno) of the shim against the oracle (shared by the CPU and the GPU test)"""
+    P = program_on_shim(lib, [])
+    ns = P.build()
+    nc, k = 37, 3
+    rng = np.random.default_rng(7)
+    xe = np.concatenate([[0.0], np.cumsum(rng.uniform(0.5, 1.5, nc))])
+    w = ns["weno"](nc, k, 1e-6, f90py.FArr(xe, (0,)))
+    assert w.ierr == 0 and w.ncells == nc and w.k == k and w.eps == 1e-6
+    assert w.cnu.a.shape == (k, k + 1, nc) and w.cnu.lb == (0, -1, 1)  # cnu(0:k-1, -1:k-1, 1:ncells), weno.f90:41
+    cnu = ref.calc_cnu(xe, k)  # [i-1, r+1, j]
+    assert np.array_equal(np.transpose(w.cnu.a, (2, 1, 0)), cnu)
+    big = rng.standard_normal(3 * nc)
+    for v in (np.ascontiguousarray(big[:nc]), big[::3]):
+        vl, vr = np.zeros(nc), np.zeros(nc)
+        f90py.callm(w, "reconstruct", f90py.FArr(v), f90py.FArr(vl), f90py.FArr(vr))
+        rl, rr = ref.reconstruct(np.ascontiguousarray(v), k, 1e-6, cnu=cnu)
+        assert np.array_equal(vl, rl) and np.array_equal(vr, rr)
+    f90py.callm(w, "destroy")
+    assert w.handle == 0
+    # uniform tables (no xedges): cnu stays unallocated, weno.f90:110-112
+    w = ns["weno"](nc)
+    assert w.cnu is None and w.k == 3
+    vl, vr = np.zeros(nc), np.zeros(nc)
+    f90py.callm(w, "reconstruct", f90py.FArr(big[:nc].copy()), f90py.FArr(vl), f90py.FArr(vr))
+    rl, rr = ref.reconstruct(big[:nc].copy(), 3, 1e-6)
+    assert np.array_equal(vl, rl) and np.array_equal(vr, rr)
+    f90py.callm(w, "destroy")

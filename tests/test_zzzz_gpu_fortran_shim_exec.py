@@ -1,0 +1,50 @@
+"""The Fortran shim EXECUTED against libhrweno_b200.so on the GPU (see tests/test_fortran_shim_exec.py for the method and for
+the same runs on the CPU stand-in of the C ABI).  The reference tree does not exist on the GPU box, so these tests run the
+self-contained programs of fortran/examples/ -- the fused 1D and 2D operators and a caller's own `pure` Fortran rhs -- through
+fortran/hrweno_b200_shim.f90 into the CUDA library, and hold their outputs, bit for bit at every output the fixtures hold, to
+the reference's source executed for the same problems (tests/golden/ref_exec_*.npz).  Strict mode: bit-identical is the bar."""
+import ctypes
+import os
+
+import numpy as np
+import pytest
+
+import shim_exec
+from shim_exec import OWN_PROGRAMS, f90py
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def cuda_abi(gpu_lib, pkg):
+    """a ctypes handle of its own on the product library: the interop layer sets argtypes from the FORTRAN declarations, which
+    must not overwrite the prototypes the package put on its own handle"""
+    path = os.path.join(os.path.dirname(pkg.__file__), "lib", "libhrweno_b200.so")
+    lib = ctypes.CDLL(path)
+    assert lib is not gpu_lib
+    return lib
+
+
+@pytest.mark.parametrize("name", sorted(OWN_PROGRAMS))
+def test_own_fortran_program_on_the_shim_and_the_cuda_library(cuda_abi, name):
+    fixture, snaps, must_call = OWN_PROGRAMS[name]
+    ns, P = shim_exec.run_own_program(cuda_abi, name)
+    shim_exec.assert_history_equals_fixture(ns, fixture, snaps)
+    assert must_call <= set(P.interop.calls)
+
+
+def test_error_stops_through_the_shim_carry_the_reference_messages(cuda_abi):
+    P = shim_exec.program_on_shim(cuda_abi, [])
+    ns = P.build()
+    with pytest.raises(f90py.FortranStop, match="Invalid input 'ncells'. Valid range: ncells > 0."):  # weno.f90:75
+        ns["weno"](0)
+    with pytest.raises(f90py.FortranStop, match="Invalid input 'k'. Valid range: 1 <= k <= 3."):  # weno.f90:84
+        ns["weno"](10, 4)
+    with pytest.raises(f90py.FortranStop, match="Invalid input 'order' in 'rktvd'"):  # tvdode.f90:89
+        ns["rktvd"](lambda t, u, udot: None, 10, 4)
+
+
+def test_weno_type_of_the_shim_on_the_gpu(cuda_abi, ref):
+    """type(weno) of the shim: the constructor with xedges fills the public `cnu` component (weno.f90:41,100-112); reconstruct
+    of contiguous and strided actuals (example2:98,107) equals the oracle bit for bit; destroy() releases the handle"""
+    shim_exec.check_weno_type(cuda_abi, ref)

@@ -641,6 +641,29 @@ class ExprTranslator:
             raise NotImplementedError(f"unexpected token {v!r} in {self.t}")
         return self.designator(v.lower())
 
+    def c_actuals(self, name, args):
+        """actual arguments of a bind(c) procedure: a scalar dummy without VALUE that the callee may define receives a
+        reference to the actual (a component, a main-program variable, or an existing by-reference dummy)"""
+        proto = self.scope.program.cprotos[name]
+        out = []
+        for pos, a in enumerate(args):
+            kw, expr = (a.split("=", 1) if re.match(r"^\w+=[^=]", a) else (None, a))
+            dummy = kw if kw else (proto["args"][pos] if pos < len(proto["args"]) else None)
+            d = proto["decls"].get(dummy)
+            if d and d["dims"] is None and not d["value"] and d["intent"] in ("out", "inout") and not re.match(r"^type\((?!c_ptr|c_funptr)", d["base"]):
+                if re.match(r"^[A-Za-z_]\w*(\.\w+)+$", expr) and not expr.endswith(".v"):
+                    obj, comp = expr.rsplit(".", 1)
+                    expr = f"AttrRef({obj}, {comp!r})"
+                elif re.match(r"^[A-Za-z_]\w*$", expr) and expr not in self.scope.refs and expr not in getattr(self.scope, "byref_tmp", {}).values():
+                    unit = self.scope.unit
+                    if unit.get("kind") == "program" or expr in unit.get("host", ()) and expr not in self.scope.locals:
+                        expr = f"GRef(globals(), {expr!r})"
+                    else:
+                        raise NotImplementedError(f"{name}: local variable {expr} as an intent({d['intent']}) actual inside an expression "
+                                                  "(use it in a CALL statement, or make it a component / program variable)")
+            out.append(f"{kw}={expr}" if kw else expr)
+        return out
+
     def designator(self, name):
         cur = self.scope.rename(name)
         first = True
@@ -649,6 +672,8 @@ class ExprTranslator:
                 self.take()
                 is_call = first and self.scope.is_callable(name)  # decided before the arguments are translated
                 args = self.arglist(")")
+                if is_call and name in getattr(self.scope.program, "cprotos", {}):
+                    args = self.c_actuals(name, args)
                 if is_call:
                     cur = f"{cur}({', '.join(args)})"
                 else:
@@ -693,7 +718,8 @@ class Scope:
     def is_callable(self, name):
         if name in self.locals and name not in self.unit["proc_dummies"]:
             return False
-        return name in INTRINSICS or name in self.program.procs or name in self.program.generics or name in self.unit["proc_dummies"]
+        return (name in INTRINSICS or name in self.program.procs or name in self.program.generics or name in self.unit["proc_dummies"]
+                or name in self.program.cprotos or name in C_INTRINSICS)
 
     def is_method(self, comp):
         return comp in self.program.methods
@@ -703,13 +729,15 @@ def PY_RESERVED_SAFE(name):
     return name + "_" if name in PY_RESERVED else name
 
 
+C_INTRINSICS = {"c_loc", "c_funloc", "c_associated", "transfer"}  # ISO_C_BINDING (+ transfer), supplied by f90c.install
+
 PY_RESERVED = {"lambda", "from", "in", "is", "not", "pass", "def", "class", "global", "with", "as", "del", "try"}
 
 DECL = re.compile(r"^(real|integer|logical|character|type|class|procedure)\b", re.I)
 UNIT_HEAD = re.compile(
     r"^(?P<prefix>(?:(?:pure|elemental|impure|recursive|module)\s+|(?:real|integer|logical|type|class)\s*\([^)]*\)\s+|"
     r"(?:logical|integer|real)\s+)*)(?P<kind>subroutine|function)\s+(?P<name>\w+)\s*(?:\((?P<args>[^)]*)\))?\s*"
-    r"(?:result\s*\(\s*(?P<res>\w+)\s*\))?\s*$",
+    r"(?P<bind1>bind\s*\([^)]*\))?\s*(?:result\s*\(\s*(?P<res>\w+)\s*\))?\s*(?P<bind2>bind\s*\([^)]*\))?\s*$",
     re.I,
 )
 
@@ -754,6 +782,20 @@ class Program:
             "frange": frange, "callm": callm, "FortranStop": FortranStop, **INTRINSICS,
         }
         self.sources = {}
+        self.cprotos = {}    # bind(c) interface bodies: Fortran name -> prototype (see f90c.py)
+        self.absifaces = {}  # abstract interface bodies, same form
+        import f90c
+
+        self.interop = f90c.install(self)  # ISO_C_BINDING: kinds, c_loc / c_funloc / c_f_pointer, bind(c) calls
+
+    @property
+    def clib(self):
+        return self.interop.lib
+
+    @clib.setter
+    def clib(self, lib):
+        """the shared library (ctypes.CDLL) the program's bind(c) interfaces resolve against"""
+        self.interop.lib = lib
 
     # -- parsing ----------------------------------------------------------------------------------------------------
     def add_source(self, path, skip=()):
@@ -778,10 +820,14 @@ class Program:
                 gen = low.split()[1] if len(low.split()) > 1 and not low.startswith("abstract") else None
                 i += 1
                 while not lines[i][1].lower().startswith("end interface"):
-                    mm = re.match(r"^module\s+procedure\s*(?:::)?\s*(\w+)", lines[i][1], re.I)
-                    if gen and mm:
-                        self.generics[gen] = mm.group(1).lower()
-                    i += 1
+                    mm = re.match(r"^module\s+procedure\s*(?:::)?\s*(.*)$", lines[i][1], re.I)
+                    if gen and mm:  # one specific: an alias; several: resolved by the kind of the actual arguments at the call
+                        self.generics.setdefault(gen, []).extend(x.strip().lower() for x in mm.group(1).split(","))
+                        i += 1
+                    elif (mh := UNIT_HEAD.match(lines[i][1])) and not gen:
+                        i = self._parse_interface_body(path, lines, i, mh, low.startswith("abstract"))
+                    else:
+                        i += 1
                 i += 1
             elif re.match(r"^type\s*(,[^:]*)?(::)?\s*\w+$", low) and not low.startswith("type("):
                 i = self._parse_type(lines, i)
@@ -799,7 +845,8 @@ class Program:
         head = lines[i][1]
         name = re.split(r"::|\s", head.strip())[-1].lower()
         mext = re.search(r"extends\s*\(\s*(\w+)\s*\)", head, re.I)
-        td = {"parent": mext.group(1).lower() if mext else None, "comps": [], "bindings": {}}
+        td = {"parent": mext.group(1).lower() if mext else None, "comps": [], "bindings": {}, "cspec": {},
+              "bindc": bool(re.search(r"bind\s*\(\s*c\s*\)", head, re.I))}
         i += 1
         in_contains = False
         while not re.match(r"^end\s*type", lines[i][1], re.I):
@@ -824,6 +871,7 @@ class Program:
                     if mm.group(3) == "=>" or default is None:
                         default = None
                     td["comps"].append((cname, default))
+                    td["cspec"][cname] = (split_top(spec)[0].strip(), mm.group(2)[1:-1] if mm.group(2) else None)
                     if spec.lower().startswith("procedure"):
                         self.methods.add(cname)
             i += 1
@@ -859,7 +907,7 @@ class Program:
         args = [a.strip().lower() for a in (m.group("args") or "").split(",") if a.strip()]
         unit = {"name": name, "kind": m.group("kind").lower(), "args": args, "res": (m.group("res") or name).lower(),
                 "prefix": (m.group("prefix") or "").lower(), "decls": [], "body": [], "path": path, "proc_dummies": set(),
-                "host": set(getattr(self, "_host", ()))}
+                "host": set(getattr(self, "_host", ())), "bindc": bool(m.group("bind1") or m.group("bind2"))}
         i += 1
         depth = 0
         while True:
@@ -880,6 +928,39 @@ class Program:
             self.procs[name] = unit
         return i + 1
 
+    def _parse_interface_body(self, path, lines, i, m, abstract):
+        """one interface body: the dummy declarations are the prototype (nothing is executed).  bind(c, name="x") bodies
+        become callables into the attached library at build time; abstract ones are kept for reference."""
+        name = m.group("name").lower()
+        bind = m.group("bind1") or m.group("bind2")
+        args = [a.strip().lower() for a in (m.group("args") or "").split(",") if a.strip()]
+        proto = {"name": name, "kind": m.group("kind").lower(), "args": args, "res": (m.group("res") or name).lower(), "decls": {},
+                 "cname": None, "path": path, "line": lines[i][0], "prefix": (m.group("prefix") or "").lower()}
+        if bind:
+            mn = re.search(r"name\s*=\s*[\"']([^\"']*)[\"']", bind)
+            proto["cname"] = mn.group(1) if mn else name
+        i += 1
+        while not re.match(rf"^end\s*({proto['kind']})?(\s+{name})?$", lines[i][1].lower()):
+            ln = lines[i][1]
+            if DECL.match(ln) and "::" in ln:
+                proto["decls"].update(self._cdecls(ln))
+            i += 1
+        missing = [a for a in args if a not in proto["decls"]]
+        if missing:
+            raise NotImplementedError(f"{path}:{proto['line']}: interface body {name}: dummies without a declaration: {missing}")
+        if abstract or not bind:
+            self.absifaces[name] = proto
+        else:
+            self.cprotos[name] = proto
+        return i + 1
+
+    def _cdecls(self, ln):
+        """declaration line -> {name: dict(base, dims, value, intent)} (what interoperability needs to know)"""
+        out = {}
+        for nm, dims, _, info in self._decl_entities(ln):
+            out[nm] = {"base": re.sub(r"\s", "", info["base"]), "dims": dims, "value": info["value"], "intent": info["intent"]}
+        return out
+
     # -- code generation ----------------------------------------------------------------------------------------------
     def ex(self, src, scope):
         tr = ExprTranslator(tokenize(src), scope)
@@ -893,7 +974,7 @@ class Program:
         attrs = [a.strip() for a in split_top(spec)]
         base = attrs[0].lower()
         info = {"base": base, "intent": None, "optional": False, "dims": None, "parameter": False, "pointer": False,
-                "allocatable": False}
+                "allocatable": False, "value": False}
         for a in attrs[1:]:
             al = a.lower()
             if al.startswith("intent"):
@@ -908,6 +989,8 @@ class Program:
                 info["pointer"] = True
             elif al == "allocatable":
                 info["allocatable"] = True
+            elif al == "value":
+                info["value"] = True
         out = []
         for ent in split_top(ents):
             mm = re.match(r"^(\w+)\s*(?:\((.*?)\))?\s*(?:=\s*(.*))?$", ent, re.S)
@@ -933,7 +1016,9 @@ class Program:
     def _bounds(self, dims, scope):
         b = []
         for d in split_top(dims):
-            if ":" in d:
+            if d.strip() == "*":  # assumed size: lower bound 1, the extent is the actual's
+                b.append(("1", None))
+            elif ":" in d:
                 lo, hi = d.split(":", 1)
                 b.append((self.ex(lo, scope) if lo.strip() else None, self.ex(hi, scope) if hi.strip() else None))
             else:
@@ -953,6 +1038,10 @@ class Program:
                 scope.locals.add(nm)
                 if info["base"].startswith("procedure") and nm in args:
                     unit["proc_dummies"].add(nm)
+        if unit.get("bindc"):
+            unit["cdecls"] = {}
+            for no, ln in unit["decls"]:
+                unit["cdecls"].update(self._cdecls(ln))
         for nm, (dims, init, info, no) in decls.items():
             if nm not in args and dims is None and not info["parameter"] and info["base"].startswith(("real", "integer", "logical")):
                 scope.scalar_locals.add(nm)
@@ -1013,6 +1102,20 @@ class Program:
         emit(1, "return res_" if is_fn else "return None")
         return "\n".join(py)
 
+    def _entity_type(self, designator, unit):
+        """declared type specifier (lower case, no blanks) of `name` or of the last component of `a%b%c`"""
+        last = designator.split("%")[-1].strip()
+        last = re.sub(r"\(.*\)$", "", last)
+        if "%" not in designator:
+            for _, ln in unit["decls"]:
+                for nm, _, _, info in self._decl_entities(ln):
+                    if nm == last:
+                        return re.sub(r"\s", "", info["base"])
+        found = {re.sub(r"\s", "", td["cspec"][last][0].lower()) for td in self.types.values() if last in td["cspec"]}
+        if len(found) != 1:
+            raise NotImplementedError(f"cannot determine the declared type of {designator!r}: {sorted(found)}")
+        return found.pop()
+
     def _assignment(self, ln, scope):
         """split `lhs = rhs` / `lhs => rhs` at the top-level operator"""
         depth, q = 0, None
@@ -1048,6 +1151,12 @@ class Program:
         if low.startswith("error stop"):
             arg = ln[10:].strip()
             return emit(ind, f"raise FortranStop({self.ex(arg, scope) if arg else repr('error stop')})")
+        if m := re.match(r"^call\s+c_f_pointer\s*\((.*)\)$", ln, re.I):  # the pointer is defined by the call
+            a = split_top(m.group(1))
+            what = self._entity_type(a[1].strip().lower(), unit)
+            kind = "obj" if what.startswith(("type", "class")) else ("char" if what.startswith("character") else what.split("(")[0])
+            shape = self.ex(a[2], scope) if len(a) > 2 else "None"
+            return emit(ind, f"{self.ex(a[1], scope)} = c_f_pointer_({self.ex(a[0], scope)}, {kind!r}, {shape})")
         if low.startswith("call "):
             target = ln[5:].strip()
             if "(" not in target:
@@ -1075,7 +1184,22 @@ class Program:
             return None
         if low.startswith("allocate"):
             inner = ln[ln.index("(") + 1 : ln.rindex(")")]
+            tspec = None
+            if "::" in inner:  # allocate (character(n) :: msg)
+                tspec, inner = [x.strip() for x in inner.split("::", 1)]
+                if not tspec.lower().startswith("character"):
+                    raise NotImplementedError(f"{unit['path']}:{no}: typed allocation of {tspec}")
             for ent in split_top(inner):
+                if tspec:
+                    emit(ind, f"{self.ex(ent, scope)} = ''")
+                    continue
+                if not ent.rstrip().endswith(")"):  # a scalar pointer / allocatable of derived type
+                    what = self._entity_type(ent.strip().lower(), unit)
+                    tm = re.match(r"^(?:type|class)\s*\(\s*(\w+)\s*\)", what)
+                    if not tm:
+                        raise NotImplementedError(f"{unit['path']}:{no}: allocate of scalar {ent} ({what})")
+                    emit(ind, f"{self.ex(ent, scope)} = new_{tm.group(1)}()")
+                    continue
                 # the allocation shape is the last parenthesised group
                 depth, k = 0, len(ent) - 1
                 while k >= 0:
@@ -1221,11 +1345,19 @@ class Program:
                 bindings.update(t["bindings"])
             cls = type(tname, (), {"_bindings": bindings, "_scope": ns, "_comps": comps})
 
-            def make(cls=cls, comps=comps):
+            cspec = {}
+            for t in reversed(chain):
+                cspec.update(t.get("cspec", {}))
+
+            def make(cls=cls, comps=comps, cspec=cspec):
                 def new():
                     o = cls()
                     for cname, default in comps:
-                        setattr(o, cname, eval(self.ex(default, dummy), ns) if default is not None else None)
+                        v = eval(self.ex(default, dummy), ns) if default is not None else None
+                        spec = cspec.get(cname, ("", None))[0].lower()
+                        if isinstance(v, FArr) and re.match(r"^(integer|type\s*\(\s*c_(fun)?ptr)", spec):
+                            v = FArr(v.a.astype(np.int64), v.lb)  # integer / c_ptr array components hold integers
+                        setattr(o, cname, v)
                     return o
 
                 return new
@@ -1257,11 +1389,17 @@ class Program:
             src = self.gen_unit(unit)
             code[name] = src
             exec(compile(src, f"<f90py:{unit['path']}:{name}>", "exec"), ns)
+            ns[name]._f90unit = unit
             if "elemental" in unit["prefix"]:
                 ns[name] = _elemental(ns[name])
-        for gen, spec in self.generics.items():
-            if spec in ns:
-                ns[gen] = ns[spec]
+        for name, proto in self.cprotos.items():
+            ns[name] = self.interop.cfunc(proto)
+        for gen, specs in self.generics.items():
+            specs = [sp for sp in specs if sp in ns]
+            if len(specs) == 1:
+                ns[gen] = ns[specs[0]]
+            elif specs:
+                ns[gen] = _generic(gen, [(ns[sp], self.procs[sp]) for sp in specs])
         self.code = code
         return ns
 
@@ -1273,6 +1411,7 @@ class CallScope:
         self._s = scope
         self.refs = scope.refs
         self.byref_tmp = scope.byref_tmp
+        self.program, self.unit, self.locals = scope.program, scope.unit, scope.locals
         self._first = True
 
     def rename(self, name):
@@ -1286,6 +1425,26 @@ class CallScope:
 
     def is_method(self, comp):
         return self._s.is_method(comp)
+
+
+def _generic(gen, specs):
+    """a generic interface with several specific procedures: the specific whose dummies agree with the actual arguments in
+    number and in being a procedure or a data object (what distinguishes rktvd(fu, neq, order) from rktvd(fv, neq, order))"""
+
+    def call(*args, **kw):
+        hits = []
+        for fn, unit in specs:
+            names = unit["args"]
+            if len(args) + len(kw) > len(names) or any(k not in names[len(args):] for k in kw):
+                continue
+            actual = {**dict(zip(names, args)), **kw}
+            if all((nm in unit["proc_dummies"]) == callable(a) for nm, a in actual.items()):
+                hits.append(fn)
+        if len(hits) != 1:
+            raise TypeError(f"generic {gen}: {len(hits)} specific procedures match the actual arguments")
+        return hits[0](*args, **kw)
+
+    return call
 
 
 def _elemental(fn):
