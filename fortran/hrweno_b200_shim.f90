@@ -205,6 +205,33 @@ module hrweno_b200_c
          type(c_ptr), value :: face_coef, cross_coef
          integer(c_int) :: st
       end function
+      function hrweno_mgpu_set_flux_time_fn(m, g, ctx) bind(c, name="hrweno_mgpu_set_flux_time_fn") result(st)
+         import :: c_ptr, c_funptr, c_int
+         type(c_ptr), value :: m
+         type(c_funptr), value :: g
+         type(c_ptr), value :: ctx
+         integer(c_int) :: st
+      end function
+      function hrweno_mgpu_set_alpha(m, alpha) bind(c, name="hrweno_mgpu_set_alpha") result(st)
+         import :: c_ptr, c_int, c_double
+         type(c_ptr), value :: m
+         real(c_double), value :: alpha
+         integer(c_int) :: st
+      end function
+      ! slab `rank` (0-based) holds unknowns [offset, offset + count) of the global vector on CUDA device `device`
+      function hrweno_mgpu_slab(m, rank, device, offset, count) bind(c, name="hrweno_mgpu_slab") result(st)
+         import :: c_ptr, c_int, c_int64_t
+         type(c_ptr), value :: m
+         integer(c_int), value :: rank
+         integer(c_int), intent(out) :: device
+         integer(c_int64_t), intent(out) :: offset, count
+         integer(c_int) :: st
+      end function
+      function hrweno_mgpu_fevals(m) bind(c, name="hrweno_mgpu_fevals") result(n)
+         import :: c_ptr, c_int64_t
+         type(c_ptr), value :: m
+         integer(c_int64_t) :: n
+      end function
       function hrweno_rktvd_create_fused(out, fv, order) bind(c, name="hrweno_rktvd_create_fused") result(st)
          import :: c_ptr, c_int
          type(c_ptr), intent(out) :: out

@@ -116,3 +116,59 @@ int hrweno_ode_integrate(hrweno_ode *ode, double *u, double *t, double tout, dou
 }
 int64_t hrweno_ode_fevals(const hrweno_ode *ode) { return hrweno_ref_ode_fevals((const hrweno_ref_ode *)ode); }
 int hrweno_ode_istate(const hrweno_ode *ode) { return hrweno_ref_ode_istate((const hrweno_ref_ode *)ode); }
+
+/* ---- one process, N GPUs (hrweno_mgpu_*): on the oracle there is one domain and no slabs ---- */
+struct hrweno_mgpu {
+   hrweno_ref_fv *fv;
+   hrweno_ref_ode *ode;
+   int64_t neq;
+   double *state; /* resident state between upload and download */
+};
+
+int hrweno_mgpu_create(hrweno_mgpu **out, const hrweno_fv_desc *desc, int ngpus, const int *devices) {
+   (void)ngpus, (void)devices;
+   if (!out || !desc) return fail(HRWENO_EINVAL, "null argument");
+   hrweno_mgpu *m = (hrweno_mgpu *)calloc(1, sizeof *m);
+   if (!m) return fail(HRWENO_ENOMEM, "out of memory");
+   const int st = hrweno_ref_fv_create(&m->fv, desc);
+   if (st) {
+      free(m);
+      return fail(st, "hrweno_mgpu_create: invalid descriptor");
+   }
+   m->neq = hrweno_ref_fv_neq(m->fv);
+   *out = m;
+   return HRWENO_OK;
+}
+void hrweno_mgpu_destroy(hrweno_mgpu *m) {
+   if (!m) return;
+   hrweno_ref_ode_destroy(m->ode), hrweno_ref_fv_destroy(m->fv), free(m->state), free(m);
+}
+int hrweno_mgpu_ngpus(const hrweno_mgpu *m) { return m ? 1 : 0; }
+int hrweno_mgpu_rktvd(hrweno_mgpu *m, int order) {
+   hrweno_ref_ode_destroy(m->ode), m->ode = NULL;
+   return hrweno_ref_rktvd_create_fv(&m->ode, m->fv, order);
+}
+int hrweno_mgpu_mstvd(hrweno_mgpu *m) {
+   hrweno_ref_ode_destroy(m->ode), m->ode = NULL;
+   return hrweno_ref_mstvd_create_fv(&m->ode, m->fv);
+}
+int hrweno_mgpu_integrate(hrweno_mgpu *m, double *u, double *t, double tout, double dt, int itask) {
+   if (!m->ode) return fail(HRWENO_EINVAL, "hrweno_mgpu_integrate: no integrator (call hrweno_mgpu_rktvd / _mstvd first)");
+   return hrweno_ref_ode_integrate(m->ode, u, t, tout, dt, itask);
+}
+int hrweno_mgpu_upload(hrweno_mgpu *m, const double *u) {
+   if (!m->state) m->state = (double *)malloc(sizeof(double) * (size_t)m->neq);
+   if (!m->state) return fail(HRWENO_ENOMEM, "out of memory");
+   memcpy(m->state, u, sizeof(double) * (size_t)m->neq);
+   return HRWENO_OK;
+}
+int hrweno_mgpu_integrate_resident(hrweno_mgpu *m, double *t, double tout, double dt, int itask) {
+   if (!m->ode || !m->state) return fail(HRWENO_EINVAL, "hrweno_mgpu_integrate_resident: no integrator or no resident state");
+   return hrweno_ref_ode_integrate(m->ode, m->state, t, tout, dt, itask);
+}
+int hrweno_mgpu_download(hrweno_mgpu *m, double *u) {
+   if (!m->state) return fail(HRWENO_EINVAL, "hrweno_mgpu_download: no resident state");
+   memcpy(u, m->state, sizeof(double) * (size_t)m->neq);
+   return HRWENO_OK;
+}
+int64_t hrweno_mgpu_fevals(const hrweno_mgpu *m) { return m->ode ? hrweno_ref_ode_fevals(m->ode) : 0; }

@@ -77,6 +77,25 @@ OWN_PROGRAMS = {
 }
 
 
+def check_multi_gpu_program(lib, ref, pkg):
+    """fortran/examples/burgers_multi_gpu.f90 (hrweno_mgpu_* from Fortran, resident state) against the oracle on the program's
+    OWN widths and initial state; returns the number of GPUs the program found"""
+    ns, P = run_own_program(lib, "burgers_multi_gpu")
+    n = 40000
+    dx, u0 = ns["dx"].a.copy(), ns["q0"].a.copy()
+    dt = 0.2 * 10.0 / n
+    rode = ref.rktvd(ref.FV(pkg.fv.make_desc(n, k=3, width=[dx])), 3)
+    u, t = u0.copy(), 0.0
+    for io, tout in enumerate((0.0, 10 * dt, 25 * dt)):
+        t = rode.integrate(u, t, tout, dt)
+        assert ns["tgrid"].a[io] == t
+        assert np.array_equal(ns["history"].a[:, io], u), f"output {io}: max diff {np.max(np.abs(ns['history'].a[:, io] - u)):.3e}"
+    assert int(ns["nfev"]) == rode.fevals
+    assert {"hrweno_mgpu_create", "hrweno_mgpu_rktvd", "hrweno_mgpu_upload", "hrweno_mgpu_integrate_resident", "hrweno_mgpu_download",
+            "hrweno_mgpu_destroy"} <= set(P.interop.calls)
+    return int(ns["ngpu"])
+
+
 def check_weno_type(lib, ref):
     """type(weno) of the shim against the oracle (shared by the CPU and the GPU test)"""
     P = program_on_shim(lib, [])

@@ -205,6 +205,11 @@ def test_reference_suite_passes_on_the_shim(abi, suite, test):
     assert any(c.startswith(("hrweno_weno_create", "hrweno_rktvd_create_host", "hrweno_mstvd_create_host")) for c in P.interop.calls)
 
 
+def test_multi_gpu_fortran_program_on_the_shim(abi, ref, pkg):
+    """hrweno_mgpu_* driven from Fortran (on the CPU stand-in there is one domain; on the GPU box: every visible device)"""
+    assert shim_exec.check_multi_gpu_program(abi, ref, pkg) == 1
+
+
 def test_weno_type_of_the_shim(abi, ref):
     shim_exec.check_weno_type(abi, ref)
 

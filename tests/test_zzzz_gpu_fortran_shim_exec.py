@@ -48,3 +48,9 @@ def test_weno_type_of_the_shim_on_the_gpu(cuda_abi, ref):
     """type(weno) of the shim: the constructor with xedges fills the public `cnu` component (weno.f90:41,100-112); reconstruct
     of contiguous and strided actuals (example2:98,107) equals the oracle bit for bit; destroy() releases the handle"""
     shim_exec.check_weno_type(cuda_abi, ref)
+
+
+def test_multi_gpu_fortran_program_on_every_visible_device(cuda_abi, gpu_lib, ref, pkg):
+    """fortran/examples/burgers_multi_gpu.f90: ONE Fortran process, hrweno_mgpu_create(..., 0, c_null_ptr) = all visible GPUs,
+    state resident between outputs; slabs + halos inside the library; bit-identical to the single-domain oracle"""
+    assert shim_exec.check_multi_gpu_program(cuda_abi, ref, pkg) == gpu_lib.hrweno_device_count()
