@@ -73,6 +73,8 @@ OWN_PROGRAMS = {
     "burgers_fused": ("ref_exec_example1.npz", (0, 1, 50, 100), {"hrweno_fv_create", "hrweno_rktvd_create_fused", "hrweno_ode_integrate"}),
     "burgers_host_rhs": ("ref_exec_example1_lf.npz", (0, 50, 100),
                          {"hrweno_weno_create", "hrweno_rktvd_create_host", "hrweno_ode_integrate", "hrweno_weno_reconstruct_s"}),
+    "pbe2d_growth_fused": ("ref_exec_example2_growth.npz", (0, 10, 20),
+                           {"hrweno_fv_create", "hrweno_fv_set_xedges", "hrweno_fv_set_flux_coef", "hrweno_mstvd_create_fused"}),
     "pbe2d_fused": ("ref_exec_example2_40.npz", (0, 1, 50, 100), {"hrweno_fv_create", "hrweno_mstvd_create_fused", "hrweno_ode_integrate"}),
 }
 
@@ -94,6 +96,33 @@ def check_multi_gpu_program(lib, ref, pkg):
     assert {"hrweno_mgpu_create", "hrweno_mgpu_rktvd", "hrweno_mgpu_upload", "hrweno_mgpu_integrate_resident", "hrweno_mgpu_download",
             "hrweno_mgpu_destroy"} <= set(P.interop.calls)
     return int(ns["ngpu"])
+
+
+def check_time_factor_program(lib, ref, pkg):
+    """fortran/examples/pbe2d_growth_time_factor.f90 (x- and t-dependent fluxes, g(t) a bind(c) Fortran function the library
+    calls back) against the oracle on the program's OWN grids and initial state with the same g in Python"""
+    ns, P = run_own_program(lib, "pbe2d_growth_time_factor")
+    n1, n2, dt = 130, 97, 1e-4
+    e1, e2, c1 = ns["e1"].a.copy(), ns["e2"].a.copy(), ns["c1x"].a.copy()
+    rfv = ref.FV(pkg.fv.make_desc((n1, n2), flux_model=1, bc=1, width=[ns["dx1"].a.copy(), ns["dx2"].a.copy()]))
+    rfv.set_xedges(0, e1)
+    rfv.set_flux_coef(0, ns["g1face"].a.copy(), None)
+    rfv.set_flux_coef(1, e2, c1)
+    rfv.set_flux_time_fn(lambda t: 1.0 + 0.25 * t)
+    rode = ref.rktvd(rfv, 3)
+    u, t = ns["q0"].a.copy(), 0.0
+    assert u.sum() > 0
+    for io, tout in enumerate((0.0, 4.5 * dt, 10.5 * dt)):
+        t = rode.integrate(u, t, tout, dt)
+        assert ns["tgrid"].a[io] == t
+        assert np.array_equal(ns["history"].a[:, io], u), f"output {io}: max diff {np.max(np.abs(ns['history'].a[:, io] - u)):.3e}"
+    assert int(ns["nfev"]) == rode.fevals == 33
+    assert {"hrweno_fv_set_xedges", "hrweno_fv_set_flux_coef", "hrweno_fv_set_flux_time_fn", "hrweno_rktvd_create_fused"} <= set(P.interop.calls)
+    # and the time factor matters: the same run without it differs
+    rfv.set_flux_time_fn(None)
+    u2 = ns["q0"].a.copy()
+    ref.rktvd(rfv, 3).integrate(u2, 0.0, 10.5 * dt, dt)
+    assert not np.array_equal(u2, u)
 
 
 def check_weno_type(lib, ref):

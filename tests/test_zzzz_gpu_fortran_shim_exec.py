@@ -54,3 +54,8 @@ def test_multi_gpu_fortran_program_on_every_visible_device(cuda_abi, gpu_lib, re
     """fortran/examples/burgers_multi_gpu.f90: ONE Fortran process, hrweno_mgpu_create(..., 0, c_null_ptr) = all visible GPUs,
     state resident between outputs; slabs + halos inside the library; bit-identical to the single-domain oracle"""
     assert shim_exec.check_multi_gpu_program(cuda_abi, ref, pkg) == gpu_lib.hrweno_device_count()
+
+
+def test_time_dependent_growth_fortran_program_on_the_gpu(cuda_abi, ref, pkg):
+    """fortran/examples/pbe2d_growth_time_factor.f90: the library calls the program's bind(c) g(t) back at every stage time"""
+    shim_exec.check_time_factor_program(cuda_abi, ref, pkg)
