@@ -21,8 +21,14 @@ type-bound procedures, procedure-pointer components, generic interfaces naming o
 functions (`result()`, `pure`/`elemental`, typed prefixes), optional and keyword arguments, explicit-shape / assumed-
 shape / automatic arrays with arbitrary lower bounds, allocatable and pointer arrays, `associate`, `do`, `do concurrent`,
 `if`, `select case`, `exit`, `cycle`, `return`, `error stop`, `allocate`, pointer assignment with bounds remapping,
-array constructors, sections with strides, and the intrinsics listed in `INTRINSICS`.
+array constructors, sections with strides, and the intrinsics listed in `INTRINSICS`.  ISO_C_BINDING (f90c.py): interface
+bodies with `bind(c, name=)` become calls into a shared library (`Program.clib`) marshalled from their own dummy
+declarations, `bind(c)` procedures can be handed to C with `c_funloc`, plus `c_loc`, `c_f_pointer`, `c_associated`,
+interoperable derived types, assumed-size dummies, typed and scalar `allocate`, generic interfaces with several specific
+procedures (resolved by the number of actual arguments and by their being procedures or data) -- what it takes to execute
+fortran/hrweno_b200_shim.f90 under the reference's programs (tests/test_fortran_shim_exec.py).
 Anything else raises `NotImplementedError` with the offending line -- it never guesses.
+`sum`, `eoshift` and `real**integer` are held to gfortran's own runtime library in tests/test_gfortran_runtime_pins.py.
 """
 from __future__ import annotations
 
