@@ -3,13 +3,14 @@
 No Fortran compiler exists in this image, but two pieces of the GNU Fortran implementation do: libgcc (`__powidf2`, what
 gfortran calls for `real**integer`) and libgfortran.so.5 (shipped inside the NumPy / SciPy wheels), which holds the library
 versions of the array intrinsics.  tools/f90exec/f90py.py -- whose execution of the reference's source pins the oracle --
-restates three semantics by hand that the reference's hot path depends on; each is checked here against the real thing,
+restates four semantics by hand that the reference's hot path depends on; each is checked here against the real thing,
 bit for bit, through hand-built gfortran array descriptors (GCC >= 8 layout):
 
   * `x**n`, integer n  (example1:120 `v**2`; grids.f90:222-224 `ratio**i`)          libgcc __powidf2, libgfortran pow_r8_i8
   * `sum(a)` accumulates from the first element to the last  (weno.f90:179-214)      libgfortran sum_r8
   * `eoshift(a, shift=-1, dim=2)` moves towards higher indices, zero-fills            libgfortran eoshift0_4
     (the multi-step history shift, tvdode.f90:262-263)
+  * `reshape(source, shape, order=)` of the coefficient tables c1 / c2 / c3 (weno.f90:16-21)   libgfortran reshape_r8
 
 What this does not pin: code gfortran generates inline at a given optimisation level (it expands rank-1 `sum` and small
 integer powers itself; without -ffast-math it may not re-associate them, which is the standard's and GCC's documented rule,
@@ -136,3 +137,45 @@ def test_eoshift_equals_libgfortran(shift, dim):
     assert np.array_equal(ret, f90py._eoshift(f90py.FArr(u), shift, dim).a)
     if (shift, dim) == (-1, 2):
         assert np.array_equal(ret[:, 1:], u[:, :-1]) and np.all(ret[:, 0] == 0.0)
+
+
+def _int_descriptor(vals):
+    """shape_type: a rank-1 array of index_type (BT_INTEGER = 1)"""
+    a = np.array(vals, dtype=np.int64)
+
+    class D(C.Structure):
+        _fields_ = [("base_addr", C.c_void_p), ("offset", C.c_size_t), ("dtype", _DType), ("span", C.c_ssize_t), ("dim", _Dim * 1)]
+
+    d = D()
+    d.base_addr, d.dtype, d.span, d.offset = a.ctypes.data, _DType(8, 0, 1, 1, 0), 8, (-1) % (1 << 64)
+    d.dim[0] = _Dim(1, 1, a.size)
+    d._keep = a
+    return d
+
+
+@needs_gf
+@pytest.mark.parametrize("order", [None, (1, 2), (2, 1)])
+def test_reshape_of_the_coefficient_tables_equals_libgfortran(tmp_path, order):
+    """weno.f90:16-21 builds c1 / c2 / c3 with `reshape([...], [k, k+1], order=[1, 2])`: element order of the source, the
+    column-major fill and the ORDER= permutation as the translator reads a module-level parameter, against reshape_r8"""
+    vals = [float(v) for v in np.random.default_rng(4).standard_normal(12)]
+    lits = ", ".join(f"{v!r}_rk" for v in vals)
+    src = tmp_path / "m.f90"
+    src.write_text(f"""
+        module m
+           real(rk), parameter :: c(0:2, -1:2) = reshape([{lits}], [3, 4]{'' if order is None else f', order=[{order[0]}, {order[1]}]'})
+        end module
+    """)
+    ns = f90py.Program().add_source(str(src)).build()
+    got = ns["c"]
+    assert got.lb == (0, -1) and got.a.shape == (3, 4)
+    ret = np.zeros((3, 4), order="F")
+    source = np.array(vals)
+    GF._gfortran_reshape_r8(C.byref(_descriptor(ret)), C.byref(_descriptor(source)), C.byref(_int_descriptor([3, 4])), None,
+                            C.byref(_int_descriptor(order)) if order else None)
+    assert np.array_equal(got.a, ret)
+    if order != (2, 1):
+        assert np.array_equal(got.a, np.reshape(source, (3, 4), order="F"))  # c(j, r) at source[j + 3*(r+1)]
+        # the run-time intrinsic (test_hrweno.f90:105-106 flattens cnu(:, :, i) with it)
+        flat = f90py.INTRINSICS["reshape"](got, f90py.FArr.from_list([12]))
+        assert np.array_equal(flat.a, source)
