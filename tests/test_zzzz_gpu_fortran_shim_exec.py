@@ -6,7 +6,6 @@ the reference's source executed for the same problems (tests/golden/ref_exec_*.n
 import ctypes
 import os
 
-import numpy as np
 import pytest
 
 import shim_exec
