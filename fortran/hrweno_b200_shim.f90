@@ -4,7 +4,7 @@
 !! instead: tools/f90exec (f90py.py + f90c.py) EXECUTES this file statement by statement, with every `bind(c)` interface
 !! body below marshalled from its own dummy declarations (F2018 18.3.6) into a real call of the shared library, under the
 !! reference's unmodified example programs and test suites (tests/test_fortran_shim_exec.py) -- and, on the GPU box, against
-!! libhrweno_b200.so itself (tests/test_zzzz_gpu_fortran_shim_exec.py).  That is an interpreter, not a compiler: syntax a
+!! libhrweno_b200.so itself (tests/test_zzzz_gpu_fortran_shim_exec.py; profiles/r2af_fortran_shim_on_b200.txt).  That is an interpreter, not a compiler: syntax a
 !! compiler would reject and the interpreter accepts remains possible.
 !! It is the binding a maintainer adds to HR-WENO so that example1/example2 re-link against the B200 library:
 !!     gfortran -c hrweno_b200_shim.f90 && gfortran example1.f90 hrweno_b200_shim.o -lhrweno_b200
@@ -38,7 +38,7 @@ module hrweno_b200_c
       real(c_double) :: flux_coef(2) = [1.0_c_double, 1.0_c_double]
       real(c_double) :: alpha = 1.0_c_double
       real(c_double) :: xmin = 0.0_c_double, xmax = 1.0_c_double
-      type(c_ptr) :: width(2) = [c_null_ptr, c_null_ptr]
+      type(c_ptr) :: width(2) = c_null_ptr
       integer(c_int32_t) :: rank = 0, nranks = 1
       integer(c_int64_t) :: global_n = 0, global_offset = 0
    end type
@@ -362,9 +362,10 @@ contains
       integer, intent(in) :: ncells
       integer, intent(in), optional :: k
       real(rk), intent(in), optional :: eps
-      real(rk), intent(in), optional, target :: xedges(0:)
+      real(rk), intent(in), optional, contiguous, target :: xedges(0:)   ! contiguous: its address goes to C
       integer(c_int) :: st
       type(c_ptr) :: xe
+      if (rk /= c_double) error stop "hrweno_b200_shim: built for rk = real64 (the REAL32 entry points are hrweno_*_f32)"
       self%ncells = ncells
       if (present(k)) self%k = k
       if (present(eps)) self%eps = eps
@@ -489,54 +490,66 @@ contains
       !! tvdode.f90:69-95, same argument list
       procedure(integrand) :: fu
       integer, intent(in) :: neq, order
+      integer(c_int) :: st
       self%neq = neq; self%order = order
       allocate (self%holder)
       self%holder%fu => fu
-      call created(self, hrweno_rktvd_create_host(self%handle, c_funloc(host_trampoline), c_loc(self%holder), &
-                                                  int(neq, c_int64_t), int(order, c_int)))
+      st = hrweno_rktvd_create_host(self%handle, c_funloc(host_trampoline), c_loc(self%holder), int(neq, c_int64_t), int(order, c_int))
+      call created(self, st)
    end function
 
    type(rktvd) function rktvd_dev(fu, neq, order) result(self)
       procedure(integrand_dev) :: fu
       integer, intent(in) :: neq, order
+      integer(c_int) :: st
       self%neq = neq; self%order = order
-      call created(self, hrweno_rktvd_create(self%handle, c_funloc(fu), c_null_ptr, int(neq, c_int64_t), int(order, c_int)))
+      st = hrweno_rktvd_create(self%handle, c_funloc(fu), c_null_ptr, int(neq, c_int64_t), int(order, c_int))
+      call created(self, st)
    end function
 
    type(rktvd) function rktvd_init_fused(fv, neq, order) result(self)
       type(c_ptr), intent(in) :: fv
       integer, intent(in) :: neq, order
+      integer(c_int) :: st
       self%neq = neq; self%order = order
-      call created(self, hrweno_rktvd_create_fused(self%handle, fv, int(order, c_int)))
+      st = hrweno_rktvd_create_fused(self%handle, fv, int(order, c_int))
+      call created(self, st)
    end function
 
    type(mstvd) function mstvd_init(fu, neq) result(self)
       !! tvdode.f90:180-201, same argument list
       procedure(integrand) :: fu
       integer, intent(in) :: neq
+      integer(c_int) :: st
       self%neq = neq; self%order = 3
       allocate (self%holder)
       self%holder%fu => fu
-      call created(self, hrweno_mstvd_create_host(self%handle, c_funloc(host_trampoline), c_loc(self%holder), int(neq, c_int64_t)))
+      st = hrweno_mstvd_create_host(self%handle, c_funloc(host_trampoline), c_loc(self%holder), int(neq, c_int64_t))
+      call created(self, st)
    end function
 
    type(mstvd) function mstvd_dev(fu, neq) result(self)
       procedure(integrand_dev) :: fu
       integer, intent(in) :: neq
+      integer(c_int) :: st
       self%neq = neq; self%order = 3
-      call created(self, hrweno_mstvd_create(self%handle, c_funloc(fu), c_null_ptr, int(neq, c_int64_t)))
+      st = hrweno_mstvd_create(self%handle, c_funloc(fu), c_null_ptr, int(neq, c_int64_t))
+      call created(self, st)
    end function
 
    type(mstvd) function mstvd_init_fused(fv, neq) result(self)
       type(c_ptr), intent(in) :: fv
       integer, intent(in) :: neq
+      integer(c_int) :: st
       self%neq = neq; self%order = 3
-      call created(self, hrweno_mstvd_create_fused(self%handle, fv))
+      st = hrweno_mstvd_create_fused(self%handle, fv)
+      call created(self, st)
    end function
 
    subroutine created(self, st)
       class(tvdode), intent(inout) :: self
       integer(c_int), intent(in) :: st
+      if (rk /= c_double) error stop "hrweno_b200_shim: built for rk = real64 (the REAL32 entry points are hrweno_*_f32)"
       if (st /= 0) then
          self%msg = last_error_string()   ! tvdode.f90:83,89 texts
          self%istate = -1

@@ -1360,7 +1360,13 @@ class Program:
                     o = cls()
                     for cname, default in comps:
                         v = eval(self.ex(default, dummy), ns) if default is not None else None
-                        spec = cspec.get(cname, ("", None))[0].lower()
+                        spec, cdims = cspec.get(cname, ("", None))
+                        spec = spec.lower()
+                        if v is not None and not isinstance(v, FArr) and cdims is not None and ":" not in cdims:
+                            arr = FArr.alloc([(int(eval(lo, ns)), int(eval(hi, ns))) for lo, hi in self._bounds(cdims, dummy)],
+                                             np.int64 if isinstance(v, int) and not isinstance(v, bool) else None)
+                            arr.assign(v)  # a scalar default of an explicit-shape array component is broadcast
+                            v = arr
                         if isinstance(v, FArr) and re.match(r"^(integer|type\s*\(\s*c_(fun)?ptr)", spec):
                             v = FArr(v.a.astype(np.int64), v.lb)  # integer / c_ptr array components hold integers
                         setattr(o, cname, v)
