@@ -196,7 +196,7 @@ def run_example1(npts=100, snaps=(0, 1, 50, 100), k=3, order=3, nc=100, extra_pa
     return out
 
 
-def run_example2(n, npts, snaps, dt=5e-3, time_end=5.0, grids="linear", nonuniform=False, n2=None, growth=False):
+def run_example2(n, npts, snaps, dt=5e-3, time_end=5.0, grids="linear", nonuniform=False, n2=None, growth=False, growth_patch=None):
     """program example_pbe_2d_fv from the source; `n`, `dt`, `time_end` patch its literals (lines 28, 57-58); grids =
     "geometric" swaps the two `linear` calls for `geometric` ones and hands the edges to `weno(...)` (what a user of
     non-uniform grids writes, weno.f90:100-112); growth removes the comment markers of lines 140, 153"""
@@ -217,7 +217,7 @@ def run_example2(n, npts, snaps, dt=5e-3, time_end=5.0, grids="linear", nonunifo
             p.append((f"myweno({i}) = weno(ncells=nc({i}), k=k, eps=1e-6_rk)",
                       f"myweno({i}) = weno(ncells=nc({i}), k=k, eps=1e-6_rk, xedges=gx({i})%edges)"))
     if growth:
-        p += GROWTH
+        p += growth_patch or GROWTH
     ns = load("example2_pbe_2d_fv.f90", patch=p)
     out = run_program(ns, "main_example_pbe_2d_fv", npts, snaps)
     out.update(edges1=ns["gx"][1].edges.a.copy(), edges2=ns["gx"][2].edges.a.copy())
@@ -233,6 +233,24 @@ def run_example2(n, npts, snaps, dt=5e-3, time_end=5.0, grids="linear", nonunifo
 LAX_FRIEDRICHS = [("fedges(i) = godunov(flux, vr(i), vl(i + 1), [gx%right(i)], t)",
                    "fedges(i) = lax_friedrichs(flux, vr(i), vl(i + 1), [gx%right(i)], t, alpha=1.0_rk)")]
 GROWTH = [("flux1 = v !*x(1)**2", "flux1 = v*x(1)**2"), ("flux2 = v !*x(1)*x(2)", "flux2 = v*x(1)*x(2)")]
+# t-dependent fluxes: the flux functions receive the evaluation time from the integrators through `rhs` (fluxes.f90:12-18,
+# example1:99, example2:100-110) and ignore it as shipped; these patches multiply the shipped expressions by
+# g(t) = 1 + t/4, which makes the stage times of tvdode.f90:162-166 (t, t + dt, t + dt/2) and :256 (t) visible in the result
+TFACTOR1 = [("flux = (v**2)/2", "flux = (v**2)/2*(1.0_rk + 0.25_rk*t)")]
+GROWTH_T = [("flux1 = v !*x(1)**2", "flux1 = v*x(1)**2*(1.0_rk + 0.25_rk*t)"), ("flux2 = v !*x(1)*x(2)", "flux2 = v*x(1)*x(2)*(1.0_rk + 0.25_rk*t)")]
+
+
+def tfactor_fixtures():
+    """ref_exec_example1_tfactor.npz / ref_exec_example2_growth_tfactor.npz: both programs with g(t) = 1 + t/4 on their fluxes"""
+    out = {}
+    for order in (1, 2, 3):
+        r = run_example1(npts=20, snaps=(0, 10, 20), order=order, extra_patch=TFACTOR1)
+        for key in ("u_0", "u_10", "u_20", "times", "fevals"):
+            out[f"{key}_o{order}"] = r[key]
+    np.savez(os.path.join(OUT, "ref_exec_example1_tfactor.npz"), **out)
+    np.savez(os.path.join(OUT, "ref_exec_example2_growth_tfactor.npz"),
+             **run_example2(24, 20, (0, 10, 20), dt=2.5e-4, time_end=0.5, grids="geometric", nonuniform=True, n2=18, growth=True,
+                            growth_patch=GROWTH_T))
 
 
 def main32():
@@ -283,6 +301,8 @@ def main32():
 def main():
     if "--real32" in sys.argv:
         return main32()
+    if "--only-tfactor" in sys.argv:
+        return tfactor_fixtures()
     quick = "--quick" in sys.argv
     t0 = time.time()
     ns1 = load("example1_burgers_1d_fv.f90")
@@ -306,6 +326,8 @@ def main():
     np.savez(os.path.join(OUT, "ref_exec_example2_growth.npz"),
              **run_example2(24, 20, (0, 10, 20), dt=2.5e-4, time_end=0.5, grids="geometric", nonuniform=True, n2=18, growth=True))
     print(f"example2 + growth on geometric 24x18 done ({time.time() - t0:.0f} s)", flush=True)
+    tfactor_fixtures()
+    print(f"t-dependent fluxes (example1 x rktvd 1-3, example2 + growth x mstvd) done ({time.time() - t0:.0f} s)", flush=True)
     if quick:
         return
     np.savez(os.path.join(OUT, "ref_exec_example2_40.npz"), **run_example2(40, 100, (0, 1, 50, 100)))

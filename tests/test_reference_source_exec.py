@@ -106,6 +106,11 @@ def test_oracle_example1_equals_reference_source(pkg, ref):
     assert ode.fevals == int(g["fevals"]) == 3603 and repr(float(g["times"][-1])) == "12.009999999999788"
 
 
+def g_of_t(t):
+    """the time factor of the *_tfactor fixtures (make_ref_exec_golden.py: TFACTOR1, GROWTH_T)"""
+    return 1.0 + 0.25 * t
+
+
 def _example1_variant(pkg, make_ode, g_times, g_u, k, order, scheme=0, upto=10, snaps=None):
     grid = pkg.hrweno_grids.grid1().linear(-5.0, 5.0, 100)
     ode = make_ode(pkg.fv.make_desc(100, k=k, eps=1e-6, width=[grid.width], flux_scheme=scheme, alpha=1.0), order)
@@ -137,7 +142,7 @@ def test_oracle_example1_lax_friedrichs_equals_reference_source(pkg, ref):
     assert ode.fevals == int(g["fevals"]) == 3603
 
 
-def _example2(pkg, make_ode, g, n1, n2, dt, time_end, growth=False, mod=None):
+def _example2(pkg, make_ode, g, n1, n2, dt, time_end, growth=False, mod=None, time_fn=None):
     e1, e2 = g["edges1"], g["edges2"]
     w1, w2, c1, c2 = e1[1:] - e1[:-1], e2[1:] - e2[:-1], (e1[:-1] + e1[1:]) / 2, (e2[:-1] + e2[1:]) / 2
     fv = mod.FV(pkg.fv.make_desc((n1, n2), k=3, eps=1e-6, flux_model=1, bc=1, width=[w1, w2]))
@@ -146,6 +151,8 @@ def _example2(pkg, make_ode, g, n1, n2, dt, time_end, growth=False, mod=None):
         fv.set_xedges(1, e2)
         fv.set_flux_coef(0, e1 * e1, None)  # flux1 = v*x(1)**2,   x = [right1(i), center2(j)]   example2:100-101,140
         fv.set_flux_coef(1, e2, c1)         # flux2 = v*x(1)*x(2), x = [center1(i), right2(j)]  example2:109-110,153
+    if time_fn:
+        fv.set_flux_time_fn(time_fn)        # ... *g(t): the flux functions' third argument, fluxes.f90:12-18
     ode = make_ode(fv)
     u, t = ex2_ic(c1, c2).reshape(-1), 0.0
     for ii in range(len(g["times"])):
@@ -179,6 +186,45 @@ def test_oracle_example2_growth_on_geometric_grids_equals_reference_source(pkg, 
     assert np.array_equal(g["edges1"], pkg.hrweno_grids.grid1().geometric(0.0, 10.0, 1.02, 24).edges)
     assert np.array_equal(g["edges2"], pkg.hrweno_grids.grid1().geometric(0.0, 10.0, 1.03, 18).edges)
     _example2(pkg, ref.mstvd, g, 24, 18, 2.5e-4, 0.5, growth=True, mod=ref)
+
+
+def _example1_tfactor(pkg, FV, make_ode, order):
+    """example1 with flux = (v**2)/2*g(t): the closed-set form model(v)*g(t) through set_flux_time_fn"""
+    g = gold("example1_tfactor")
+    grid = pkg.hrweno_grids.grid1().linear(-5.0, 5.0, 100)
+    fv = FV(pkg.fv.make_desc(100, k=3, eps=1e-6, width=[grid.width]))
+    fv.set_flux_time_fn(g_of_t)
+    ode = make_ode(fv, order)
+    u, t = np.clip(1.0 + (-1.5 / 6.0) * (grid.center + 4.0), -0.5, 1.0), 0.0
+    for ii in range(21):
+        t = ode.integrate(u, t, 12.0 * ii / 100, 1e-2)
+        assert t == g[f"times_o{order}"][ii]
+        if ii in (0, 10, 20):
+            assert np.array_equal(u, g[f"u_{ii}_o{order}"]), f"order {order} output {ii}: max diff {np.max(np.abs(u - g[f'u_{ii}_o{order}'])):.3e}"
+    assert ode.fevals == int(g[f"fevals_o{order}"])
+    return u
+
+
+@pytest.mark.parametrize("order", [1, 2, 3])
+def test_oracle_time_dependent_flux_example1_equals_reference_source(pkg, ref, order):
+    """t-dependent fluxes (SURVEY 8f-4): the reference's integrators hand t, t + dt and t + dt/2 to the rhs (tvdode.f90:162-166);
+    example1 executed from source with its flux multiplied by g(t) = 1 + t/4 pins the stage times at which the oracle (and
+    through it the CUDA path) evaluates the separable factor of hrweno_fv_set_flux_time_fn"""
+    u = _example1_tfactor(pkg, ref.FV, lambda fv, o: ref.rktvd(fv, o), order)
+    assert not np.array_equal(u, gold("example1")["u_0"])
+    if order == 3:  # the factor matters: without it the state at output 20 is example1's own
+        plain = ref.rktvd(ref.FV(pkg.fv.make_desc(100, k=3, eps=1e-6, width=[pkg.hrweno_grids.grid1().linear(-5.0, 5.0, 100).width])), 3)
+        v, t = np.clip(1.0 + (-1.5 / 6.0) * (pkg.hrweno_grids.grid1().linear(-5.0, 5.0, 100).center + 4.0), -0.5, 1.0), 0.0
+        for ii in range(21):
+            t = plain.integrate(v, t, 12.0 * ii / 100, 1e-2)
+        assert not np.array_equal(u, v)
+
+
+def test_oracle_time_dependent_growth_example2_equals_reference_source(pkg, ref):
+    """example2 on geometric grids with v*x(1)**2*g(t) and v*x(1)*x(2)*g(t), multi-step integrator (rhs at t, tvdode.f90:256;
+    start-up by four RK3 single steps, :236-247)"""
+    _example2(pkg, ref.mstvd, gold("example2_growth_tfactor"), 24, 18, 2.5e-4, 0.5, growth=True, mod=ref, time_fn=g_of_t)
+    assert not np.array_equal(gold("example2_growth_tfactor")["u_20"], gold("example2_growth")["u_20"])
 
 
 # ---- live re-execution where the reference tree is present ---------------------------------------------------------
