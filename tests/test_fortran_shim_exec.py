@@ -169,6 +169,18 @@ def test_reference_example1_unmodified_runs_on_the_shim_bit_identical(abi):
 
 
 @needs_reference
+def test_reference_example1_with_a_time_dependent_flux_on_the_shim(abi):
+    """the evaluation time crosses the boundary: the library hands t, t + dt, t + dt/2 (tvdode.f90:162-166) to the shim's
+    bind(c) trampoline, which hands them to the program's `rhs`, whose flux now depends on t (the fixture's one-line patch)"""
+    g = np.load(os.path.join(GOLDEN, "ref_exec_example1_tfactor.npz"))
+    ns, P, rec = _run_reference_program(abi, "example1_burgers_1d_fv.f90", "main_example1_burgers_1d_fv", 20, (0, 10, 20),
+                                        patch=[("flux = (v**2)/2", "flux = (v**2)/2*(1.0_rk + 0.25_rk*t)")])
+    for i in (0, 10, 20):
+        assert np.array_equal(rec[i], g[f"u_{i}_o3"]), i
+    assert np.array_equal(np.array(rec["times"]), g["times_o3"])
+
+
+@needs_reference
 def test_reference_example2_unmodified_runs_on_the_shim_bit_identical(abi):
     """example/example2_pbe_2d_fv.f90 with only `nc(2) = [250, 250]` patched to 40 x 40 (the fixture's size): `mstvd(rhs,
     size(u))`, an array of two weno objects, row sections and STRIDED column sections `v(i:i+(nc(2)-1)*nc(1):nc(1))` as
