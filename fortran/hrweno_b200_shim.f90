@@ -7,7 +7,8 @@
 !! libhrweno_b200.so itself (tests/test_zzzz_gpu_fortran_shim_exec.py; profiles/r2af_fortran_shim_on_b200.txt).  That is an interpreter, not a compiler: syntax a
 !! compiler would reject and the interpreter accepts remains possible.
 !! It is the binding a maintainer adds to HR-WENO so that example1/example2 re-link against the B200 library:
-!!     gfortran -c hrweno_b200_shim.f90 && gfortran example1.f90 hrweno_b200_shim.o -lhrweno_b200
+!!     gfortran -cpp -DREAL64 -c hrweno_b200_shim.f90 && gfortran example1.f90 hrweno_b200_shim.o -lhrweno_b200
+!! (preprocessed like the reference's hrweno_kinds.F90: -DREAL32 selects the hrweno_*_f32 entry points, see `crk` below)
 !! `hrweno_kinds` and `hrweno_grids` are used unchanged from the reference (grids, set-up and I/O stay
 !! on the host); this file replaces hrweno_weno, hrweno_fluxes (re-exported unchanged: pointwise host
 !! helpers) and hrweno_tvdode.
@@ -23,6 +24,51 @@ module hrweno_b200_c
    integer(c_int), parameter :: GRID_WIDTH_ARRAY = 0, GRID_LINEAR = 1
    integer(c_int), parameter :: MODE_STRICT = 0, MODE_FAST = 1
 
+   ! The kind of the reference is a compile-time switch of the whole library (src/hrweno_kinds.F90:9-17: -DREAL32 / -DREAL64).
+   ! Compile this file with the same switch: `crk` is the C kind of `rk`, and the bind(c) names below select the fp64 entry
+   ! points or their REAL32 counterparts (hrweno_*_f32: float in every position, include/hrweno_b200.h).  The REAL32 build
+   ! has the fused operators and integrators and type(weno); the host-integrand constructors rktvd(fu, ...) / mstvd(fu, ...),
+   ! the device-integrand ones and hrweno_mgpu_* exist for REAL64 only.
+#ifdef REAL32
+   integer, parameter :: crk = c_float
+#define N_WENO_CREATE "hrweno_weno_f32_create"
+#define N_WENO_DESTROY "hrweno_weno_f32_destroy"
+#define N_WENO_GET_CNU "hrweno_weno_f32_get_cnu"
+#define N_WENO_RECONSTRUCT "hrweno_weno_f32_reconstruct"
+#define N_WENO_RECONSTRUCT_S "hrweno_weno_f32_reconstruct_s"
+#define N_FV_CREATE "hrweno_fv_f32_create"
+#define N_FV_DESTROY "hrweno_fv_f32_destroy"
+#define N_FV_RHS "hrweno_fv_f32_rhs"
+#define N_FV_SET_XEDGES "hrweno_fv_f32_set_xedges"
+#define N_FV_SET_FLUX_COEF "hrweno_fv_f32_set_flux_coef"
+#define N_FV_SET_FLUX_TIME_FN "hrweno_fv_f32_set_flux_time_fn"
+#define N_RKTVD_CREATE_FUSED "hrweno_rktvd_f32_create_fused"
+#define N_MSTVD_CREATE_FUSED "hrweno_mstvd_f32_create_fused"
+#define N_ODE_DESTROY "hrweno_ode_f32_destroy"
+#define N_ODE_INTEGRATE "hrweno_ode_f32_integrate"
+#define N_ODE_FEVALS "hrweno_ode_f32_fevals"
+#define N_ODE_ISTATE "hrweno_ode_f32_istate"
+#else
+   integer, parameter :: crk = c_double
+#define N_WENO_CREATE "hrweno_weno_create"
+#define N_WENO_DESTROY "hrweno_weno_destroy"
+#define N_WENO_GET_CNU "hrweno_weno_get_cnu"
+#define N_WENO_RECONSTRUCT "hrweno_weno_reconstruct"
+#define N_WENO_RECONSTRUCT_S "hrweno_weno_reconstruct_s"
+#define N_FV_CREATE "hrweno_fv_create"
+#define N_FV_DESTROY "hrweno_fv_destroy"
+#define N_FV_RHS "hrweno_fv_rhs"
+#define N_FV_SET_XEDGES "hrweno_fv_set_xedges"
+#define N_FV_SET_FLUX_COEF "hrweno_fv_set_flux_coef"
+#define N_FV_SET_FLUX_TIME_FN "hrweno_fv_set_flux_time_fn"
+#define N_RKTVD_CREATE_FUSED "hrweno_rktvd_create_fused"
+#define N_MSTVD_CREATE_FUSED "hrweno_mstvd_create_fused"
+#define N_ODE_DESTROY "hrweno_ode_destroy"
+#define N_ODE_INTEGRATE "hrweno_ode_integrate"
+#define N_ODE_FEVALS "hrweno_ode_fevals"
+#define N_ODE_ISTATE "hrweno_ode_istate"
+#endif
+
    type, bind(c) :: hrweno_fv_desc
       integer(c_int32_t) :: abi_version = HRWENO_ABI_VERSION
       integer(c_int32_t) :: ndim = 1
@@ -34,10 +80,10 @@ module hrweno_b200_c
       integer(c_int32_t) :: bc = BC_COPY_NEIGHBOUR
       integer(c_int32_t) :: grid_kind = GRID_WIDTH_ARRAY
       integer(c_int32_t) :: mode = MODE_STRICT
-      real(c_double) :: eps = 1e-6_c_double
-      real(c_double) :: flux_coef(2) = [1.0_c_double, 1.0_c_double]
-      real(c_double) :: alpha = 1.0_c_double
-      real(c_double) :: xmin = 0.0_c_double, xmax = 1.0_c_double
+      real(crk) :: eps = 1e-6_crk
+      real(crk) :: flux_coef(2) = [1.0_crk, 1.0_crk]
+      real(crk) :: alpha = 1.0_crk
+      real(crk) :: xmin = 0.0_crk, xmax = 1.0_crk
       type(c_ptr) :: width(2) = c_null_ptr
       integer(c_int32_t) :: rank = 0, nranks = 1
       integer(c_int64_t) :: global_n = 0, global_offset = 0
@@ -48,69 +94,69 @@ module hrweno_b200_c
          import :: c_ptr
          type(c_ptr) :: p
       end function
-      function hrweno_weno_create(out, ncells, k, eps, xedges) bind(c, name="hrweno_weno_create") result(st)
-         import :: c_ptr, c_int, c_int64_t, c_double
+      function hrweno_weno_create(out, ncells, k, eps, xedges) bind(c, name=N_WENO_CREATE) result(st)
+         import :: c_ptr, c_int, c_int64_t, crk
          type(c_ptr), intent(out) :: out
          integer(c_int64_t), value :: ncells
          integer(c_int), value :: k
-         real(c_double), value :: eps
+         real(crk), value :: eps
          type(c_ptr), value :: xedges
          integer(c_int) :: st
       end function
-      subroutine hrweno_weno_destroy(w) bind(c, name="hrweno_weno_destroy")
+      subroutine hrweno_weno_destroy(w) bind(c, name=N_WENO_DESTROY)
          import :: c_ptr
          type(c_ptr), value :: w
       end subroutine
-      function hrweno_weno_get_cnu(w, cnu) bind(c, name="hrweno_weno_get_cnu") result(st)
-         import :: c_ptr, c_int, c_double
+      function hrweno_weno_get_cnu(w, cnu) bind(c, name=N_WENO_GET_CNU) result(st)
+         import :: c_ptr, c_int, crk
          type(c_ptr), value :: w
-         real(c_double), intent(out) :: cnu(*)
+         real(crk), intent(out) :: cnu(*)
          integer(c_int) :: st
       end function
-      function hrweno_weno_reconstruct(w, v, vl, vr) bind(c, name="hrweno_weno_reconstruct") result(st)
-         import :: c_ptr, c_int, c_double
+      function hrweno_weno_reconstruct(w, v, vl, vr) bind(c, name=N_WENO_RECONSTRUCT) result(st)
+         import :: c_ptr, c_int, crk
          type(c_ptr), value :: w
-         real(c_double), intent(in) :: v(*)
-         real(c_double), intent(out) :: vl(*), vr(*)
+         real(crk), intent(in) :: v(*)
+         real(crk), intent(out) :: vl(*), vr(*)
          integer(c_int) :: st
       end function
       ! the same call in subroutine form: a pure FUNCTION may not have intent(out) dummies, a pure subroutine may, and
       ! `reconstruct` has to stay pure for the reference's `pure subroutine rhs` (example1:72,93) to compile
-      pure subroutine hrweno_weno_reconstruct_s(w, v, vl, vr, st) bind(c, name="hrweno_weno_reconstruct_s")
-         import :: c_ptr, c_int, c_double
+      pure subroutine hrweno_weno_reconstruct_s(w, v, vl, vr, st) bind(c, name=N_WENO_RECONSTRUCT_S)
+         import :: c_ptr, c_int, crk
          type(c_ptr), value :: w
-         real(c_double), intent(in) :: v(*)
-         real(c_double), intent(out) :: vl(*), vr(*)
+         real(crk), intent(in) :: v(*)
+         real(crk), intent(out) :: vl(*), vr(*)
          integer(c_int), intent(out) :: st
       end subroutine
-      function hrweno_fv_create(out, desc) bind(c, name="hrweno_fv_create") result(st)
+      function hrweno_fv_create(out, desc) bind(c, name=N_FV_CREATE) result(st)
          import :: c_ptr, c_int, hrweno_fv_desc
          type(c_ptr), intent(out) :: out
          type(hrweno_fv_desc), intent(in) :: desc
          integer(c_int) :: st
       end function
-      subroutine hrweno_fv_destroy(fv) bind(c, name="hrweno_fv_destroy")
+      subroutine hrweno_fv_destroy(fv) bind(c, name=N_FV_DESTROY)
          import :: c_ptr
          type(c_ptr), value :: fv
       end subroutine
-      function hrweno_fv_rhs(fv, t, v, vdot) bind(c, name="hrweno_fv_rhs") result(st)
-         import :: c_ptr, c_int, c_double
+      function hrweno_fv_rhs(fv, t, v, vdot) bind(c, name=N_FV_RHS) result(st)
+         import :: c_ptr, c_int, crk
          type(c_ptr), value :: fv
-         real(c_double), value :: t
-         real(c_double), intent(in) :: v(*)
-         real(c_double), intent(out) :: vdot(*)
+         real(crk), value :: t
+         real(crk), intent(in) :: v(*)
+         real(crk), intent(out) :: vdot(*)
          integer(c_int) :: st
       end function
       ! weno(ncells,k,eps,xedges) inside the fused operator: per-cell tables for the sweep along `axis` (0-based)
-      function hrweno_fv_set_xedges(fv, axis, xedges) bind(c, name="hrweno_fv_set_xedges") result(st)
-         import :: c_ptr, c_int, c_double
+      function hrweno_fv_set_xedges(fv, axis, xedges) bind(c, name=N_FV_SET_XEDGES) result(st)
+         import :: c_ptr, c_int, crk
          type(c_ptr), value :: fv
          integer(c_int), value :: axis
-         real(c_double), intent(in) :: xedges(*)
+         real(crk), intent(in) :: xedges(*)
          integer(c_int) :: st
       end function
       ! x-dependent flux f = (model(v)*cross(c))*face(f) along `axis`; pass c_null_ptr for an absent factor
-      function hrweno_fv_set_flux_coef(fv, axis, face_coef, cross_coef) bind(c, name="hrweno_fv_set_flux_coef") result(st)
+      function hrweno_fv_set_flux_coef(fv, axis, face_coef, cross_coef) bind(c, name=N_FV_SET_FLUX_COEF) result(st)
          import :: c_ptr, c_int
          type(c_ptr), value :: fv
          integer(c_int), value :: axis
@@ -119,13 +165,14 @@ module hrweno_b200_c
       end function
       ! t-dependent flux f = ((model(v)*cross)*face)*g(t); g is a bind(C) function `real(c_double) function g(ctx, t)` passed
       ! with c_funloc (c_null_funptr removes the factor)
-      function hrweno_fv_set_flux_time_fn(fv, g, ctx) bind(c, name="hrweno_fv_set_flux_time_fn") result(st)
+      function hrweno_fv_set_flux_time_fn(fv, g, ctx) bind(c, name=N_FV_SET_FLUX_TIME_FN) result(st)
          import :: c_ptr, c_funptr, c_int
          type(c_ptr), value :: fv
          type(c_funptr), value :: g
          type(c_ptr), value :: ctx
          integer(c_int) :: st
       end function
+#ifndef REAL32
       ! ---- one process, N GPUs: the GLOBAL descriptor, slabs / halos / alpha reduction inside the library ----
       function hrweno_mgpu_create(out, desc, ngpus, devices) bind(c, name="hrweno_mgpu_create") result(st)
          import :: c_ptr, c_int, hrweno_fv_desc
@@ -232,19 +279,21 @@ module hrweno_b200_c
          type(c_ptr), value :: m
          integer(c_int64_t) :: n
       end function
-      function hrweno_rktvd_create_fused(out, fv, order) bind(c, name="hrweno_rktvd_create_fused") result(st)
+#endif
+      function hrweno_rktvd_create_fused(out, fv, order) bind(c, name=N_RKTVD_CREATE_FUSED) result(st)
          import :: c_ptr, c_int
          type(c_ptr), intent(out) :: out
          type(c_ptr), value :: fv
          integer(c_int), value :: order
          integer(c_int) :: st
       end function
-      function hrweno_mstvd_create_fused(out, fv) bind(c, name="hrweno_mstvd_create_fused") result(st)
+      function hrweno_mstvd_create_fused(out, fv) bind(c, name=N_MSTVD_CREATE_FUSED) result(st)
          import :: c_ptr, c_int
          type(c_ptr), intent(out) :: out
          type(c_ptr), value :: fv
          integer(c_int) :: st
       end function
+#ifndef REAL32
       function hrweno_rktvd_create(out, fu, ctx, neq, order) bind(c, name="hrweno_rktvd_create") result(st)
          import :: c_ptr, c_funptr, c_int, c_int64_t
          type(c_ptr), intent(out) :: out
@@ -279,25 +328,26 @@ module hrweno_b200_c
          integer(c_int64_t), value :: neq
          integer(c_int) :: st
       end function
-      subroutine hrweno_ode_destroy(ode) bind(c, name="hrweno_ode_destroy")
+#endif
+      subroutine hrweno_ode_destroy(ode) bind(c, name=N_ODE_DESTROY)
          import :: c_ptr
          type(c_ptr), value :: ode
       end subroutine
-      function hrweno_ode_integrate(ode, u, t, tout, dt, itask) bind(c, name="hrweno_ode_integrate") result(st)
-         import :: c_ptr, c_int, c_double
+      function hrweno_ode_integrate(ode, u, t, tout, dt, itask) bind(c, name=N_ODE_INTEGRATE) result(st)
+         import :: c_ptr, c_int, crk
          type(c_ptr), value :: ode
-         real(c_double), intent(inout) :: u(*)
-         real(c_double), intent(inout) :: t
-         real(c_double), value :: tout, dt
+         real(crk), intent(inout) :: u(*)
+         real(crk), intent(inout) :: t
+         real(crk), value :: tout, dt
          integer(c_int), value :: itask
          integer(c_int) :: st
       end function
-      function hrweno_ode_fevals(ode) bind(c, name="hrweno_ode_fevals") result(n)
+      function hrweno_ode_fevals(ode) bind(c, name=N_ODE_FEVALS) result(n)
          import :: c_ptr, c_int64_t
          type(c_ptr), value :: ode
          integer(c_int64_t) :: n
       end function
-      function hrweno_ode_istate(ode) bind(c, name="hrweno_ode_istate") result(n)
+      function hrweno_ode_istate(ode) bind(c, name=N_ODE_ISTATE) result(n)
          import :: c_ptr, c_int
          type(c_ptr), value :: ode
          integer(c_int) :: n
@@ -365,7 +415,7 @@ contains
       real(rk), intent(in), optional, contiguous, target :: xedges(0:)   ! contiguous: its address goes to C
       integer(c_int) :: st
       type(c_ptr) :: xe
-      if (rk /= c_double) error stop "hrweno_b200_shim: built for rk = real64 (the REAL32 entry points are hrweno_*_f32)"
+      if (rk /= crk) error stop "hrweno_b200_shim: compile the shim with the same -DREAL32 / -DREAL64 as hrweno_kinds"
       self%ncells = ncells
       if (present(k)) self%k = k
       if (present(eps)) self%eps = eps
@@ -378,7 +428,7 @@ contains
          end if
          xe = c_loc(xedges)
       end if
-      st = hrweno_weno_create(self%handle, int(ncells, c_int64_t), int(self%k, c_int), real(self%eps, c_double), xe)
+      st = hrweno_weno_create(self%handle, int(ncells, c_int64_t), int(self%k, c_int), real(self%eps, crk), xe)
       if (st /= 0) then
          self%msg = last_error_string()   ! same texts as weno.f90:75,84,94
          self%ierr = 1
@@ -420,7 +470,10 @@ module hrweno_tvdode
    use hrweno_b200_c
    implicit none
    private
-   public :: rktvd, mstvd, rktvd_dev, mstvd_dev, integrand, integrand_dev
+   public :: rktvd, mstvd, integrand, integrand_dev
+#ifndef REAL32
+   public :: rktvd_dev, mstvd_dev
+#endif
 
    abstract interface
       subroutine integrand(t, u, udot)
@@ -465,15 +518,26 @@ module hrweno_tvdode
    type, extends(tvdode) :: mstvd
    end type
 
+#ifdef REAL32
+   ! the REAL32 entry points have the fused constructors only (no host-integrand / device-integrand integrators in float)
+   interface rktvd
+      module procedure :: rktvd_init_fused
+   end interface
+   interface mstvd
+      module procedure :: mstvd_init_fused
+   end interface
+#else
    interface rktvd
       module procedure :: rktvd_init, rktvd_init_fused
    end interface
    interface mstvd
       module procedure :: mstvd_init, mstvd_init_fused
    end interface
+#endif
 
 contains
 
+#ifndef REAL32
    subroutine host_trampoline(ctx, t, neq, u, udot) bind(c)
       !! hrweno_rhs_host_fn: hands the library's pinned staging arrays to the user's assumed-shape integrand
       type(c_ptr), value :: ctx
@@ -507,6 +571,8 @@ contains
       call created(self, st)
    end function
 
+#endif
+
    type(rktvd) function rktvd_init_fused(fv, neq, order) result(self)
       type(c_ptr), intent(in) :: fv
       integer, intent(in) :: neq, order
@@ -516,6 +582,7 @@ contains
       call created(self, st)
    end function
 
+#ifndef REAL32
    type(mstvd) function mstvd_init(fu, neq) result(self)
       !! tvdode.f90:180-201, same argument list
       procedure(integrand) :: fu
@@ -537,6 +604,8 @@ contains
       call created(self, st)
    end function
 
+#endif
+
    type(mstvd) function mstvd_init_fused(fv, neq) result(self)
       type(c_ptr), intent(in) :: fv
       integer, intent(in) :: neq
@@ -549,7 +618,7 @@ contains
    subroutine created(self, st)
       class(tvdode), intent(inout) :: self
       integer(c_int), intent(in) :: st
-      if (rk /= c_double) error stop "hrweno_b200_shim: built for rk = real64 (the REAL32 entry points are hrweno_*_f32)"
+      if (rk /= crk) error stop "hrweno_b200_shim: compile the shim with the same -DREAL32 / -DREAL64 as hrweno_kinds"
       if (st /= 0) then
          self%msg = last_error_string()   ! tvdode.f90:83,89 texts
          self%istate = -1

@@ -173,6 +173,8 @@ PROTOTYPES = {
     "hrweno_weno_f32_create": (C.c_int, [C.POINTER(C.c_void_p), C.c_int64, C.c_int, C.c_float, C.c_void_p]),
     "hrweno_weno_f32_destroy": (None, [C.c_void_p]),
     "hrweno_weno_f32_reconstruct": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),
+    "hrweno_weno_f32_reconstruct_s": (None, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),
+    "hrweno_weno_f32_get_cnu": (C.c_int, [C.c_void_p, C.c_void_p]),
     "hrweno_weno_f32_reconstruct_dev": (
         C.c_int,
         [C.c_void_p, C.c_int64, C.c_void_p, C.c_int64, C.c_int64, C.c_void_p, C.c_void_p, C.c_int64, C.c_void_p],

@@ -406,6 +406,18 @@ int hrweno_weno_f32_reconstruct(const hrweno_weno_f32 *h, const float *v, float 
    return st;
 }
 
+void hrweno_weno_f32_reconstruct_s(const hrweno_weno_f32 *h, const float *v, float *vl, float *vr, int *status) {
+   const int st = hrweno_weno_f32_reconstruct(h, v, vl, vr);
+   if (status) *status = st;
+}
+int hrweno_weno_f32_get_cnu(const hrweno_weno_f32 *h, float *cnu_host) {
+   const Weno32 *w = reinterpret_cast<const Weno32 *>(h);
+   if (!w || !cnu_host) return fail(HRWENO_EINVAL, "null argument");
+   if (!w->d_cnu) return fail(HRWENO_EINVAL, "hrweno_weno_f32_get_cnu: uniform-grid object has no cnu (weno.f90:110-112)");
+   HRW_CUDA(cudaMemcpy(cnu_host, w->d_cnu, (size_t)w->ncells * (size_t)(w->k * (w->k + 1)) * sizeof(float), cudaMemcpyDeviceToHost));
+   return HRWENO_OK;
+}
+
 int hrweno_fv_f32_create(hrweno_fv_f32 **out, const hrweno_fv_desc_f32 *desc) { return fv32_create(reinterpret_cast<Fv32 **>(out), desc); }
 void hrweno_fv_f32_destroy(hrweno_fv_f32 *fv) { delete reinterpret_cast<Fv32 *>(fv); }
 int64_t hrweno_fv_f32_neq(const hrweno_fv_f32 *fv) { return fv ? reinterpret_cast<const Fv32 *>(fv)->neq : 0; }

@@ -322,6 +322,8 @@ typedef float (*hrweno_time_fn_f32)(void *ctx, float t);
 int hrweno_weno_f32_create(hrweno_weno_f32 **out, int64_t ncells, int k, float eps, const float *xedges); /* weno.f90:54-127 */
 void hrweno_weno_f32_destroy(hrweno_weno_f32 *w);
 int hrweno_weno_f32_reconstruct(const hrweno_weno_f32 *w, const float *v, float *vl, float *vr);          /* weno.f90:129-219, host */
+void hrweno_weno_f32_reconstruct_s(const hrweno_weno_f32 *w, const float *v, float *vl, float *vr, int *status); /* subroutine form (a `pure` Fortran binding), like hrweno_weno_reconstruct_s */
+int hrweno_weno_f32_get_cnu(const hrweno_weno_f32 *w, float *cnu_host); /* weno%cnu (weno.f90:41): cnu(j,r,i) at j + k*((r+1) + (k+1)*(i-1)) */
 int hrweno_weno_f32_reconstruct_dev(const hrweno_weno_f32 *w, int64_t rows, const float *v_dev, int64_t ldv, int64_t incv,
                                     float *vl_dev, float *vr_dev, int64_t ldo, void *stream);
 int hrweno_fv_f32_create(hrweno_fv_f32 **out, const hrweno_fv_desc_f32 *desc);

@@ -22,7 +22,7 @@ import numpy as np
 import pytest
 
 import shim_exec
-from shim_exec import GOLDEN, OWN_PROGRAMS, REFERENCE, f90py
+from shim_exec import GOLDEN, OWN_PROGRAMS, OWN_PROGRAMS_REAL32, REFERENCE, f90py
 
 import f90c  # noqa: E402  (tools/f90exec is on sys.path through shim_exec)
 
@@ -33,6 +33,15 @@ needs_reference = pytest.mark.skipif(not os.path.isdir(os.path.join(REFERENCE, "
 def abi(ref, tmp_path_factory):
     """the product's C ABI on the CPU oracle (`ref` makes sure the oracle is built)"""
     return shim_exec.build_abi_on_oracle(tmp_path_factory.mktemp("abi_on_oracle"))
+
+
+@pytest.fixture(scope="module")
+def abi32(ref, tmp_path_factory):
+    """the REAL32 entry points (hrweno_*_f32) on the REAL32 build of the CPU oracle"""
+    from oracle import ref32
+
+    ref32.lib()  # builds oracle/libhrweno_oracle_f32.so if need be
+    return shim_exec.build_abi_on_oracle(tmp_path_factory.mktemp("abi_f32_on_oracle"), real32=True)
 
 
 # ---- the shim's declarations against the C header ----------------------------------------------------------------------
@@ -55,39 +64,51 @@ def _cls(ct):
     raise AssertionError(f"unclassified ctypes type {ct}")
 
 
-def _shim():
-    P = f90py.Program()
+def _shim(defines=None):
+    P = f90py.Program(defines=defines)
     P.add_source(shim_exec.SHIM)
     return P
 
 
-def test_every_interface_body_of_the_shim_matches_the_c_header(pkg):
-    P = _shim()
+@pytest.mark.parametrize("build", ["REAL64", "REAL32"])
+def test_every_interface_body_of_the_shim_matches_the_c_header(pkg, build):
+    """both builds of the shim (the reference's kind is a compile-time switch, hrweno_kinds.F90:9-17): with -DREAL32 the same
+    interface bodies bind the hrweno_*_f32 entry points with float in every real position"""
+    P = _shim({build: "1"})
+    P.build()
     protos = pkg._abi.PROTOTYPES
-    assert len(P.cprotos) >= 30
+    assert len(P.cprotos) >= (30 if build == "REAL64" else 17)
     for name, proto in P.cprotos.items():
-        assert proto["cname"] == name, f"{name}: bind(c, name=) differs from the Fortran name"
-        assert name in protos, f"{name} is not an entry point of include/hrweno_b200.h"
-        res, args = protos[name]
+        cname = proto["cname"]
+        if build == "REAL64":
+            assert cname == name, f"{name}: bind(c, name=) differs from the Fortran name"
+        elif name != "hrweno_last_error":
+            assert "_f32_" in cname and cname.replace("_f32_", "_") == name, (name, cname)
+        assert cname in protos, f"{cname} is not an entry point of include/hrweno_b200.h"
+        res, args = protos[cname]
         sig = P.interop._arg_types(proto["args"], proto["decls"])
         got = [_cls(ct) if kind == "value" else "ptr" for _, kind, ct, _ in sig]
-        assert got == [_cls(a) for a in args], f"{name}: Fortran passes {got}, C expects {[_cls(a) for a in args]}"
-        fres = f90c.ctype_of(proto["decls"][proto["res"]]["base"]) if proto["kind"] == "function" else None
-        assert _cls(fres) == _cls(res), f"{name}: result {fres} vs {res}"
+        assert got == [_cls(a) for a in args], f"{cname}: Fortran passes {got}, C expects {[_cls(a) for a in args]}"
+        fres = f90c.ctype_of(proto["decls"][proto["res"]]["base"], P.ns) if proto["kind"] == "function" else None
+        assert _cls(fres) == _cls(res), f"{cname}: result {fres} vs {res}"
+        if build == "REAL32":  # no double left in a REAL32 signature
+            assert "f64" not in got and _cls(fres) != "f64", cname
 
 
-def test_interoperable_descriptor_type_has_the_layout_of_the_c_struct(pkg):
-    P = _shim()
+@pytest.mark.parametrize("build", ["REAL64", "REAL32"])
+def test_interoperable_descriptor_type_has_the_layout_of_the_c_struct(pkg, build):
+    P = _shim({build: "1"})
     P.build()
     S = P.interop.struct_type("hrweno_fv_desc")
-    D = pkg._abi.FvDesc if hasattr(pkg._abi, "FvDesc") else pkg._abi.hrweno_fv_desc
+    D = pkg._abi.FvDesc if build == "REAL64" else pkg._abi.FvDesc32
     assert C.sizeof(S) == C.sizeof(D)
     want = {n: (getattr(D, n).offset, getattr(D, n).size) for n, _ in D._fields_}
     got = {n: (getattr(S, n).offset, getattr(S, n).size) for n, _ in S._fields_}
     assert got == want
     # the defaults a Fortran program starts from are a valid single-GPU descriptor header
     s = P.interop.to_struct("hrweno_fv_desc", P.ns["new_hrweno_fv_desc"]())
-    assert (s.abi_version, s.ndim, s.k, s.rank, s.nranks, s.eps) == (pkg._abi.ABI_VERSION if hasattr(pkg._abi, "ABI_VERSION") else 1, 1, 3, 0, 1, 1e-6)
+    assert (s.abi_version, s.ndim, s.k, s.rank, s.nranks) == (pkg._abi.ABI_VERSION, 1, 3, 0, 1)
+    assert s.eps == (1e-6 if build == "REAL64" else float(np.float32(1e-6)))
 
 
 def test_the_shims_callback_has_the_signature_of_hrweno_rhs_host_fn(pkg):
@@ -111,6 +132,22 @@ def test_own_fortran_program_on_the_shim_reproduces_the_executed_reference(abi, 
     shim_exec.assert_history_equals_fixture(ns, fixture, snaps)
     assert must_call <= set(P.interop.calls)
     assert P.interop.calls[-1] in ("hrweno_fv_destroy", "hrweno_weno_destroy")  # handles released by the explicit destroy()
+
+
+@pytest.mark.parametrize("name", sorted(OWN_PROGRAMS_REAL32))
+def test_own_fortran_program_on_the_real32_build_of_the_shim(abi32, name):
+    """shim and program as `-DREAL32` compiles them (rk = real32, src/hrweno_kinds.F90:9-10), executed in binary32: the
+    hrweno_*_f32 entry points, against the reference's source executed in real32 for the same problems"""
+    fixture, snaps, must_call = OWN_PROGRAMS_REAL32[name]
+    ns, P = shim_exec.run_own_program(abi32, name, real32=True)
+    shim_exec.assert_history_equals_fixture(ns, fixture, snaps)
+    assert must_call <= set(P.interop.calls) and not any("f32" not in c for c in P.interop.calls if c != "hrweno_last_error")
+
+
+def test_weno_type_of_the_real32_build_of_the_shim(abi32):
+    from oracle import ref32
+
+    shim_exec.check_weno_type_real32(abi32, ref32)
 
 
 # ---- the reference's own programs, unmodified, on the shim ---------------------------------------------------------------------

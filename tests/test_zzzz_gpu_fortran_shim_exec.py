@@ -9,7 +9,7 @@ import os
 import pytest
 
 import shim_exec
-from shim_exec import OWN_PROGRAMS, f90py
+from shim_exec import OWN_PROGRAMS, OWN_PROGRAMS_REAL32, f90py
 
 pytestmark = pytest.mark.gpu
 
@@ -58,3 +58,18 @@ def test_multi_gpu_fortran_program_on_every_visible_device(cuda_abi, gpu_lib, re
 def test_time_dependent_growth_fortran_program_on_the_gpu(cuda_abi, ref, pkg):
     """fortran/examples/pbe2d_growth_time_factor.f90: the library calls the program's bind(c) g(t) back at every stage time"""
     shim_exec.check_time_factor_program(cuda_abi, ref, pkg)
+
+
+@pytest.mark.parametrize("name", sorted(OWN_PROGRAMS_REAL32))
+def test_own_fortran_program_on_the_real32_build_of_the_shim_and_the_cuda_library(cuda_abi, name):
+    """the shim compiled with -DREAL32 binds hrweno_*_f32: the same programs in binary32 against the REAL32 executed-source fixtures"""
+    fixture, snaps, must_call = OWN_PROGRAMS_REAL32[name]
+    ns, P = shim_exec.run_own_program(cuda_abi, name, real32=True)
+    shim_exec.assert_history_equals_fixture(ns, fixture, snaps)
+    assert must_call <= set(P.interop.calls)
+
+
+def test_weno_type_of_the_real32_build_of_the_shim_on_the_gpu(cuda_abi):
+    from oracle import ref32
+
+    shim_exec.check_weno_type_real32(cuda_abi, ref32)

@@ -43,13 +43,20 @@ class CInteropError(TypeError):
     """an actual argument that a Fortran compiler would have rejected (kind / type / rank mismatch)"""
 
 
-def ctype_of(spec):
-    """`integer(c_int)`, `real(c_double)`, `type(c_ptr)`, `type(c_funptr)`, `character(kind=c_char)` -> ctypes scalar type"""
+def ctype_of(spec, ns=None):
+    """`integer(c_int)`, `real(c_double)`, `type(c_ptr)`, `type(c_funptr)`, `character(kind=c_char)` -> ctypes scalar type.
+    A kind given by a named constant of the program (`real(crk)` with `integer, parameter :: crk = c_float`) is looked up
+    in `ns`, the program's namespace."""
     s = re.sub(r"\s", "", spec.lower())
     m = re.match(r"^(integer|real|type|character|logical)\((?:kind=)?(\w+)\)$", s)
     if not m:
         raise NotImplementedError(f"not an interoperable type specifier: {spec!r}")
     base, kind = m.groups()
+    if base in ("integer", "real") and kind not in _INT and kind not in _REAL and ns is not None and isinstance(ns.get(kind), int):
+        value = ns[kind]
+        table = {("real", 4): C.c_float, ("real", 8): C.c_double, ("integer", 4): C.c_int, ("integer", 8): C.c_int64}
+        if (base, value) in table:
+            return table[(base, value)]
     if base == "integer" and kind in _INT:
         return _INT[kind]
     if base == "real" and kind in _REAL:
@@ -198,7 +205,7 @@ class Interop:
         fields = []
         for cname, _ in td["comps"]:
             spec, dims = td["cspec"][cname]
-            ct = ctype_of(spec)
+            ct = ctype_of(spec, self.program.ns)
             if dims is not None:
                 ct = ct * int(eval(dims, self.program.ns))
             fields.append((cname, ct))
@@ -258,7 +265,7 @@ class Interop:
             if d["dims"] is not None:
                 if d["dims"].strip() != "*":
                     raise NotImplementedError(f"dummy {a}({d['dims']}): only assumed-size arrays are interoperable here")
-                out.append((a, "array", ctype_of(base), d["intent"]))
+                out.append((a, "array", ctype_of(base, self.program.ns), d["intent"]))
                 continue
             m = re.match(r"^type\s*\(\s*(\w+)\s*\)$", base)
             if m and m.group(1) not in ("c_ptr", "c_funptr"):
@@ -266,7 +273,7 @@ class Interop:
                     raise NotImplementedError("struct by value")
                 out.append((a, "struct", m.group(1), d["intent"]))
                 continue
-            out.append((a, "value" if d["value"] else "ref", ctype_of(base), d["intent"]))
+            out.append((a, "value" if d["value"] else "ref", ctype_of(base, self.program.ns), d["intent"]))
         return out
 
     def _callback(self, f, unit):
@@ -276,7 +283,7 @@ class Interop:
         decls = unit["cdecls"]
         sig = self._arg_types(unit["args"], decls)
         if unit["kind"] == "function":
-            res = ctype_of(decls[unit["res"]]["base"])
+            res = ctype_of(decls[unit["res"]]["base"], self.program.ns)
         else:
             res = None
         ctypes_args = []
@@ -291,14 +298,14 @@ class Interop:
                 pyargs, refs = [], []
                 for (name, kind, ct, intent), ca in zip(sig, cargs):
                     if kind == "value":
-                        pyargs.append(int(ca or 0) if ct is C.c_void_p else ca)
+                        pyargs.append(int(ca or 0) if ct is C.c_void_p else (np.float32(ca) if ct is C.c_float else ca))
                     elif kind == "array":
                         arr = np.ctypeslib.as_array(ca, shape=(HUGE,))
                         pyargs.append(FArr(arr))
                     elif kind == "ref":
                         from f90py import Ref
 
-                        r = Ref(ca[0])
+                        r = Ref(np.float32(ca[0]) if ct is C.c_float else ca[0])
                         refs.append((r, ca))
                         pyargs.append(r)
                     else:
@@ -321,7 +328,7 @@ class CFunc:
         self.io, self.proto = interop, proto
         self.name = proto["name"]
         self.sig = interop._arg_types(proto["args"], proto["decls"])
-        self.res = ctype_of(proto["decls"][proto["res"]]["base"]) if proto["kind"] == "function" else None
+        self.res = ctype_of(proto["decls"][proto["res"]]["base"], interop.program.ns) if proto["kind"] == "function" else None
         self._fn = None
 
     def _bind(self):
@@ -404,10 +411,10 @@ class CFunc:
                 target[...] = holder
             else:
                 v = holder.value
-                target.v = int(v or 0) if ct is C.c_void_p else v
+                target.v = int(v or 0) if ct is C.c_void_p else (np.float32(v) if ct is C.c_float else v)
         if self.res is C.c_void_p:
             return int(out or 0)
-        return out
+        return np.float32(out) if self.res is C.c_float else out
 
 
 def install(program):

@@ -420,8 +420,76 @@ def callm(obj, name, /, *args, **kw):
 # ------------------------------------------------------------------------------------------------------------------
 
 
-def logical_lines(text):
+def preprocess(text, defines=None):
+    """the C-preprocessor subset Fortran sources use (`gfortran -cpp -DNAME`, src/hrweno_kinds.F90:9-17): #ifdef / #ifndef /
+    #if NAME / #elif NAME / #else / #endif, #define NAME [text] / #undef, object-like macro substitution outside character
+    literals.  Lines that are dropped (and the directives) become empty lines, so line numbers stay those of the file."""
+    macros = dict(defines or {})
+    stack, out = [], []  # stack entries: [a branch of this group has been taken, this branch is active]
+
+    def truth(expr):
+        expr = expr.strip()
+        m = re.match(r"^defined\s*\(?\s*(\w+)\s*\)?$", expr)
+        if m:
+            return m.group(1) in macros
+        if re.match(r"^\w+$", expr):
+            return str(macros.get(expr, "0")).strip() not in ("0", "")
+        raise NotImplementedError(f"preprocessor expression {expr!r}")
+
+    def substitute(line):
+        if not macros:
+            return line
+        res, q, word = "", None, ""
+        for ch in line + "\0":
+            if q is None and (ch.isalnum() or ch == "_"):
+                word += ch
+                continue
+            if word:
+                res += str(macros[word]) if word in macros and macros[word] is not True else word
+                word = ""
+            if ch == "\0":
+                break
+            if q:
+                q = None if ch == q else q
+            elif ch in "'\"":
+                q = ch
+            res += ch
+        return res
+
+    for raw in text.splitlines():
+        st = raw.strip()
+        if st.startswith("#"):
+            m = re.match(r"^#\s*(ifdef|ifndef|if|elif|else|endif|define|undef)\b\s*(.*)$", st)
+            if not m:
+                raise NotImplementedError(f"preprocessor directive {st!r}")
+            d, arg = m.groups()
+            outer = all(b[1] for b in stack)
+            if d in ("ifdef", "ifndef", "if"):
+                on = outer and ((arg.strip() in macros) == (d == "ifdef") if d != "if" else truth(arg))
+                stack.append([on, on])
+            elif d in ("elif", "else"):
+                outer = all(b[1] for b in stack[:-1])
+                on = outer and not stack[-1][0] and (True if d == "else" else truth(arg))
+                stack[-1] = [stack[-1][0] or on, on]
+            elif d == "endif":
+                stack.pop()
+            elif outer and d == "define":
+                parts = arg.split(None, 1)
+                macros[parts[0]] = parts[1].strip() if len(parts) > 1 else "1"
+            elif outer and d == "undef":
+                macros.pop(arg.strip(), None)
+            out.append("")
+            continue
+        out.append(substitute(raw) if all(b[1] for b in stack) else "")
+    if stack:
+        raise NotImplementedError("unterminated #if")
+    return "\n".join(out)
+
+
+def logical_lines(text, defines=None):
     """comment-free logical lines (continuations joined) with the 1-based number of their first physical line"""
+    if defines is not None or re.search(r"^\s*#", text, re.M):
+        text = preprocess(text, defines)
     out, buf, start = [], "", None
     for no, raw in enumerate(text.splitlines(), 1):
         line, q, i = "", None, 0
@@ -776,8 +844,9 @@ def split_top(s, sep=","):
 class Program:
     """all program units of a set of source files, translated into one Python namespace"""
 
-    def __init__(self, skip_io=False):
+    def __init__(self, skip_io=False, defines=None):
         self.skip_io = skip_io  # `write` / `print` statements become no-ops (test programs print diagnostics)
+        self.defines = defines  # preprocessor symbols ({"REAL32": "1"} = gfortran -cpp -DREAL32)
         self.procs = {}     # name -> unit
         self.generics = {}  # generic interface name -> specific procedure
         self.types = {}     # type name -> dict(parent, comps=[(name, default_src)], bindings={})
@@ -809,7 +878,7 @@ class Program:
         self._skip = {x.lower() for x in skip}
         self._host = set()
         text = open(path).read()
-        lines = logical_lines(text)
+        lines = logical_lines(text, self.defines)
         self.sources[path] = lines
         i, n = 0, len(lines)
         stack = []  # enclosing module / program / procedures
