@@ -61,6 +61,16 @@ class weno:
             raise _abi.HrwenoError(_abi.EINVAL, "Invalid input 'xedges': size(xedges) /= ncells + 1.")
         _abi.check(_abi.lib().hrweno_weno_f32_create(C.byref(self._h), int(ncells), int(k), float(eps), None if xe is None else xe.ctypes.data))
         self.ncells, self.k = int(ncells), int(k)
+        self.uniform_grid = xe is None
+
+    @property
+    def cnu(self):
+        """cnu(0:k-1, -1:k-1, 1:ncells) as a float32 array [i-1, r+1, j] (weno.f90:41); None on a uniform grid (:110-112)"""
+        if self.uniform_grid:
+            return None
+        out = np.empty((self.ncells, self.k + 1, self.k), dtype=F32)
+        _abi.check(_abi.lib().hrweno_weno_f32_get_cnu(self._h, out.ctypes.data))
+        return out
 
     def __del__(self):
         try:
