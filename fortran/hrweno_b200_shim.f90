@@ -39,6 +39,7 @@ module hrweno_b200_c
 #define N_FV_CREATE "hrweno_fv_f32_create"
 #define N_FV_DESTROY "hrweno_fv_f32_destroy"
 #define N_FV_RHS "hrweno_fv_f32_rhs"
+#define N_FV_RHS_DEV "hrweno_fv_f32_rhs_dev"
 #define N_FV_SET_XEDGES "hrweno_fv_f32_set_xedges"
 #define N_FV_SET_FLUX_COEF "hrweno_fv_f32_set_flux_coef"
 #define N_FV_SET_FLUX_TIME_FN "hrweno_fv_f32_set_flux_time_fn"
@@ -58,6 +59,7 @@ module hrweno_b200_c
 #define N_FV_CREATE "hrweno_fv_create"
 #define N_FV_DESTROY "hrweno_fv_destroy"
 #define N_FV_RHS "hrweno_fv_rhs"
+#define N_FV_RHS_DEV "hrweno_fv_rhs_dev"
 #define N_FV_SET_XEDGES "hrweno_fv_set_xedges"
 #define N_FV_SET_FLUX_COEF "hrweno_fv_set_flux_coef"
 #define N_FV_SET_FLUX_TIME_FN "hrweno_fv_set_flux_time_fn"
@@ -145,6 +147,14 @@ module hrweno_b200_c
          real(crk), value :: t
          real(crk), intent(in) :: v(*)
          real(crk), intent(out) :: vdot(*)
+         integer(c_int) :: st
+      end function
+      ! the same on device pointers, asynchronous on `stream` (what a device integrand of rktvd_dev / mstvd_dev calls)
+      function hrweno_fv_rhs_dev(fv, t, v_dev, vdot_dev, stream) bind(c, name=N_FV_RHS_DEV) result(st)
+         import :: c_ptr, c_int, crk
+         type(c_ptr), value :: fv
+         real(crk), value :: t
+         type(c_ptr), value :: v_dev, vdot_dev, stream
          integer(c_int) :: st
       end function
       ! weno(ncells,k,eps,xedges) inside the fused operator: per-cell tables for the sweep along `axis` (0-based)

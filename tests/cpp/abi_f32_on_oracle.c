@@ -75,6 +75,10 @@ int hrweno_fv_f32_create(hrweno_fv_f32 **out, const hrweno_fv_desc_f32 *desc) {
 void hrweno_fv_f32_destroy(hrweno_fv_f32 *fv) { hrweno_ref_fv_destroy((hrweno_ref_fv *)fv); }
 int64_t hrweno_fv_f32_neq(const hrweno_fv_f32 *fv) { return hrweno_ref_fv_neq((const hrweno_ref_fv *)fv); }
 int hrweno_fv_f32_rhs(hrweno_fv_f32 *fv, float t, const float *v, float *vdot) { return hrweno_ref_fv_rhs((hrweno_ref_fv *)fv, t, v, vdot); }
+int hrweno_fv_f32_rhs_dev(hrweno_fv_f32 *fv, float t, const float *v_dev, float *vdot_dev, void *stream) {
+   (void)stream;
+   return hrweno_ref_fv_rhs((hrweno_ref_fv *)fv, t, v_dev, vdot_dev);
+}
 int hrweno_fv_f32_set_xedges(hrweno_fv_f32 *fv, int axis, const float *xedges) {
    return hrweno_ref_fv_set_xedges((hrweno_ref_fv *)fv, axis, xedges);
 }

@@ -83,6 +83,11 @@ int64_t hrweno_fv_neq(const hrweno_fv *fv) { return hrweno_ref_fv_neq((const hrw
 int hrweno_fv_rhs(hrweno_fv *fv, double t, const double *v, double *vdot) {
    return hrweno_ref_fv_rhs((hrweno_ref_fv *)fv, t, v, vdot);
 }
+/* "device" pointers are host pointers here, the stream is ignored */
+int hrweno_fv_rhs_dev(hrweno_fv *fv, double t, const double *v_dev, double *vdot_dev, void *stream) {
+   (void)stream;
+   return hrweno_ref_fv_rhs((hrweno_ref_fv *)fv, t, v_dev, vdot_dev);
+}
 int hrweno_fv_set_xedges(hrweno_fv *fv, int axis, const double *xedges) {
    return hrweno_ref_fv_set_xedges((hrweno_ref_fv *)fv, axis, xedges);
 }
@@ -102,6 +107,26 @@ int hrweno_rktvd_create_host(hrweno_ode **out, hrweno_rhs_host_fn fu, void *ctx,
 int hrweno_mstvd_create_host(hrweno_ode **out, hrweno_rhs_host_fn fu, void *ctx, int64_t neq) {
    if (!(neq > 0)) return fail(HRWENO_EINVAL, "Invalid input 'neq'. Valid range: neq >= 1.");
    return hrweno_ref_mstvd_create((hrweno_ref_ode **)out, (hrweno_ref_rhs_fn)fu, ctx, neq);
+}
+/* device-integrand constructors: hrweno_rhs_fn has a stream argument the oracle's callback type lacks */
+struct dev_adapter {
+   hrweno_rhs_fn fu;
+   void *ctx;
+};
+static void dev_trampoline(void *p, double t, int64_t neq, const double *u, double *udot) {
+   struct dev_adapter *a = (struct dev_adapter *)p;
+   a->fu(a->ctx, t, neq, u, udot, NULL);
+}
+int hrweno_rktvd_create(hrweno_ode **out, hrweno_rhs_fn fu, void *ctx, int64_t neq, int order) {
+   if (!(order >= 1 && order <= 3)) return fail(HRWENO_EINVAL, "Invalid input 'order' in 'rktvd'. Valid range: 1 <= k <= 3.");
+   struct dev_adapter *a = (struct dev_adapter *)malloc(sizeof *a); /* lives as long as the process: test infrastructure */
+   a->fu = fu, a->ctx = ctx;
+   return hrweno_ref_rktvd_create((hrweno_ref_ode **)out, dev_trampoline, a, neq, order);
+}
+int hrweno_mstvd_create(hrweno_ode **out, hrweno_rhs_fn fu, void *ctx, int64_t neq) {
+   struct dev_adapter *a = (struct dev_adapter *)malloc(sizeof *a);
+   a->fu = fu, a->ctx = ctx;
+   return hrweno_ref_mstvd_create((hrweno_ref_ode **)out, dev_trampoline, a, neq);
 }
 int hrweno_rktvd_create_fused(hrweno_ode **out, hrweno_fv *fv, int order) {
    if (!(order >= 1 && order <= 3)) return fail(HRWENO_EINVAL, "Invalid input 'order' in 'rktvd'. Valid range: 1 <= k <= 3.");

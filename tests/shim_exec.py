@@ -173,6 +173,24 @@ def check_time_factor_program(lib, ref, pkg):
     assert not np.array_equal(u2, u)
 
 
+def check_device_integrand_program(lib, ref, pkg):
+    """fortran/examples/burgers_device_rhs.f90: rktvd_dev / mstvd_dev with a bind(c) integrand on device pointers that applies
+    hrweno_fv_rhs_dev; against the oracle's fused integrators on the program's own widths and initial state"""
+    ns, P = run_own_program(lib, "burgers_device_rhs")
+    n, dt = 200, 5e-3
+    dx, u0 = ns["dx"].a.copy(), ns["q0"].a.copy()
+    for which, make in enumerate((lambda fv: ref.rktvd(fv, 3), lambda fv: ref.mstvd(fv))):
+        rode = make(ref.FV(pkg.fv.make_desc(n, k=3, width=[dx])))
+        u, t = u0.copy(), 0.0
+        for io, tout in enumerate((0.0, 0.1, 0.3)):
+            t = rode.integrate(u, t, tout, dt)
+            assert ns["tgrid"].a[io, which] == t
+            assert np.array_equal(ns["history"].a[:, io, which], u), (which, io)
+        assert int(ns["nfev"].a[which]) == rode.fevals
+    assert list(ns["asked"].a) == [0.0, 0.005, 0.0025]  # stage times t, t + dt, t + dt/2 (tvdode.f90:162-166)
+    assert {"hrweno_rktvd_create", "hrweno_mstvd_create", "hrweno_fv_rhs_dev"} <= set(P.interop.calls)
+
+
 def check_weno_type(lib, ref):
     """type(weno) of the shim against the oracle (shared by the CPU and the GPU test)"""
     P = program_on_shim(lib, [])

@@ -360,3 +360,53 @@ def test_real32_a_binary64_value_cannot_slip_in(tmp_path):
             ns["s"](F(0.1), np.zeros(2))  # a float64 array as an actual argument
         with pytest.raises(TypeError, match="binary64"):
             FArr(np.zeros(3))
+
+
+def test_preprocessor_subset_and_module_variables(tmp_path):
+    """`gfortran -cpp -DNAME` as src/hrweno_kinds.F90 uses it (#ifdef / #elif / #else / #endif, object-like #define), and
+    module variables with an initial value that the module's procedures define"""
+    src = """
+        module counters
+           implicit none
+        #ifdef WIDE
+           integer, parameter :: width = 8
+        #define LABEL "wide"
+        #elif NARROW
+           integer, parameter :: width = 4
+        #define LABEL "narrow"
+        #else
+           integer, parameter :: width = 0
+        #define LABEL "none"
+        #endif
+           integer :: ncalls = 0
+           real(rk) :: seen(3) = -1.0_rk
+        contains
+           subroutine touch(x)
+              real(rk), intent(in) :: x
+              ncalls = ncalls + 1
+              if (ncalls <= 3) seen(ncalls) = x*width
+           end subroutine
+           function label() result(s)
+              character(:), allocatable :: s
+              s = LABEL // "LABEL"
+           end function
+        #ifndef WIDE
+           integer function only_without_wide()
+              only_without_wide = 1
+           end function
+        #endif
+        end module
+    """
+    p = tmp_path / "c.f90"
+    p.write_text(textwrap.dedent(src))
+    for defines, width, label in (({"WIDE": "1"}, 8, "wide"), ({"NARROW": "1"}, 4, "narrow"), ({}, 0, "none")):
+        ns = f90py.Program(defines=defines).add_source(str(p)).build()
+        assert ns["width"] == width and ns["label"]() == label + "LABEL"
+        assert ("only_without_wide" in ns) == ("WIDE" not in defines)
+        for x in (1.5, 2.5):
+            ns["touch"](x)
+        assert ns["ncalls"] == 2 and list(ns["seen"].a) == [1.5 * width, 2.5 * width, -1.0]
+    with pytest.raises(NotImplementedError):
+        f90py.preprocess("#if A && B\nx\n#endif\n", {"A": "1"})
+    with pytest.raises(NotImplementedError):
+        f90py.preprocess("#ifdef A\nx\n", {})

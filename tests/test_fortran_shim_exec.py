@@ -263,6 +263,10 @@ def test_time_dependent_growth_fortran_program_on_the_shim(abi, ref, pkg):
     shim_exec.check_time_factor_program(abi, ref, pkg)
 
 
+def test_device_integrand_fortran_program_on_the_shim(abi, ref, pkg):
+    shim_exec.check_device_integrand_program(abi, ref, pkg)
+
+
 def test_weno_type_of_the_shim(abi, ref):
     shim_exec.check_weno_type(abi, ref)
 

@@ -73,3 +73,9 @@ def test_weno_type_of_the_real32_build_of_the_shim_on_the_gpu(cuda_abi):
     from oracle import ref32
 
     shim_exec.check_weno_type_real32(cuda_abi, ref32)
+
+
+def test_device_integrand_fortran_program_on_the_gpu(cuda_abi, ref, pkg):
+    """fortran/examples/burgers_device_rhs.f90: rktvd_dev / mstvd_dev, the bind(c) integrand enqueues hrweno_fv_rhs_dev on the
+    integrator's stream; equals the fused integrators (and the oracle) bit for bit"""
+    shim_exec.check_device_integrand_program(cuda_abi, ref, pkg)

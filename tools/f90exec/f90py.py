@@ -593,11 +593,18 @@ class ExprTranslator:
            ".le.": "<=", ".gt.": ">", ".ge.": ">="}
 
     def rel(self):
-        left = self.add()
+        left = self.concat()
         v = self.peek()[1]
         if v is not None and v.lower() in self.REL:
             self.take()
-            return f"({left} {self.REL[v.lower()]} {self.add()})"
+            return f"({left} {self.REL[v.lower()]} {self.concat()})"
+        return left
+
+    def concat(self):
+        left = self.add()
+        while self.at("//"):  # character concatenation: below + -, above the relational operators
+            self.take()
+            left = f"({left} + {self.add()})"
         return left
 
     def add(self):
@@ -911,8 +918,10 @@ class Program:
             elif low.startswith("end ") or low == "end" or low == "contains":
                 i += 1
             else:
-                if DECL.match(ln) and "parameter" in low.split("::")[0]:
-                    self.params.append((path, no, ln))
+                if DECL.match(ln) and "::" in ln and ("parameter" in low.split("::")[0] or (stack and "=" in ln.split("::", 1)[1])):
+                    self.params.append((path, no, ln))  # named constants, and module variables with an initial value
+                    if "parameter" not in low.split("::")[0]:  # module variables: the module's procedures may define them
+                        self._host = set(self._host) | {nm for nm, _, _, _ in self._decl_entities(ln)}
                 i += 1
         return self
 
