@@ -4,7 +4,7 @@ Bar: bit-identical (strict mode / the general kernel).  Sorted last on purpose (
 import numpy as np
 import pytest
 
-from test_reference_source_exec import _example1, _example1_tfactor, _example1_variant, _example2, g_of_t, gold
+from test_reference_source_exec import _example1, _example1_variant, _example2, gold
 
 @pytest.mark.gpu
 def test_gpu_example1_equals_reference_source(gpu_lib, pkg):
@@ -23,20 +23,6 @@ def test_gpu_example2_equals_reference_source(gpu_lib, pkg):
 def test_gpu_general_path_equals_reference_source(gpu_lib, pkg):
     _example2(pkg, lambda fv: pkg.hrweno_tvdode.mstvd(fv, 24 * 18), gold("example2_growth"), 24, 18, 2.5e-4, 0.5, growth=True,
               mod=pkg.fv)
-
-
-@pytest.mark.gpu
-@pytest.mark.parametrize("order", [1, 2, 3])
-def test_gpu_time_dependent_flux_example1_equals_reference_source(gpu_lib, pkg, order):
-    """example1 executed from source with flux = (v**2)/2*(1 + t/4): the fused stage with the separable time factor, g called on
-    the host at the reference's stage times"""
-    _example1_tfactor(pkg, pkg.fv.FV, lambda fv, o: pkg.hrweno_tvdode.rktvd(fv, 100, o), order)
-
-
-@pytest.mark.gpu
-def test_gpu_time_dependent_growth_example2_equals_reference_source(gpu_lib, pkg):
-    _example2(pkg, lambda fv: pkg.hrweno_tvdode.mstvd(fv, 24 * 18), gold("example2_growth_tfactor"), 24, 18, 2.5e-4, 0.5, growth=True,
-              mod=pkg.fv, time_fn=g_of_t)
 
 
 @pytest.mark.gpu
