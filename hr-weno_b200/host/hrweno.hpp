@@ -408,6 +408,11 @@ class weno { // weno.f90:23-50 with rk = real32
    weno &operator=(const weno &) = delete;
    ~weno() { hrweno_weno_f32_destroy(h_); }
    void reconstruct(const float *v, float *vl, float *vr) const { hrweno::check(hrweno_weno_f32_reconstruct(h_, v, vl, vr)); } // weno.f90:129-219
+   std::vector<float> cnu() const { // cnu(0:k-1,-1:k-1,1:ncells), weno.f90:41 (objects built with xedges)
+      std::vector<float> c((size_t)(k * (k + 1) * ncells));
+      hrweno::check(hrweno_weno_f32_get_cnu(h_, c.data()));
+      return c;
+   }
  private:
    ::hrweno_weno_f32 *h_ = nullptr;
 };

@@ -51,6 +51,7 @@ static int exercise() {
    std::vector<float> wf(64, 10.0f / 64), vf(64, 1.0f), lf(64), rf(64);
    real32::weno w32(64, 3, 1e-6f);
    w32.reconstruct(vf.data(), lf.data(), rf.data());
+   f += (double)w32.cnu().size();
    hrweno_fv_desc_f32 d32 = real32::fv::desc1d(64, 3, 1e-6f, wf.data());
    real32::fv op32(d32);
    op32.set_xedges(0, wf.data());
