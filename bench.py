@@ -358,6 +358,14 @@ def main():
             e2e_call(steps)
             barrier()
             (out["e2e_s"],) = allmax(time.perf_counter() - w0)
+            # the same API used one step per call (every step pays H2D + D2H of the whole state): the un-amortised figure
+            ks = max(1, min(int(steps), 5))
+            barrier()
+            w1 = time.perf_counter()
+            for _ in range(ks):
+                e2e_call(1)
+            barrier()
+            (out["e2e_step_s"],) = allmax((time.perf_counter() - w1) / ks)
             # the ceiling the host side puts on e2e: pinned H2D and D2H of this rank's u, all ranks copying at once
             # (both directions at once as well, as the chunk pipeline does), CUDA events, slowest rank
             d_tmp = torch.empty(n, dtype=torch.float64, device="cuda")
@@ -659,6 +667,12 @@ def main():
             "note": "one hrweno_ode_integrate call with a pinned host u advancing K steps: H2D u (8n B), 3K fused stages, D2H u (8n B); "
                     "time-skewed chunk pipeline (slabs: on the slab extended by wide halos exchanged once per call)",
             "seconds_per_call": main_m["e2e_s"], "host_copy_ceiling": main_m.get("pcie"), "host_placement": numa,
+            "one_call_per_step": {
+                "value": n_global * 3 / main_m["e2e_step_s"], "unit": "cell-updates/s", "seconds_per_call": main_m["e2e_step_s"],
+                "h2d_bytes_per_step": n * 8, "d2h_bytes_per_step": n * 8,
+                "note": "hrweno_ode_integrate called once PER STEP with the pinned host u (itask-free: tout one step ahead): every step "
+                        "pays the H2D and the D2H of the whole state, nothing is amortised; bound by host_copy_ceiling.copy_floor_s per call",
+            },
         },
     }
     def parity_of(m):
