@@ -1,5 +1,6 @@
 // capi.cu -- the extern "C" boundary declared in include/hrweno_b200.h.
 #include <cstring>
+#include <limits>
 #include <new>
 #include <string>
 
@@ -156,10 +157,18 @@ void hrweno_weno_reconstruct_s(const hrweno_weno *h, const double *v, double *vl
 // ---- fluxes ----------------------------------------------------------------------------------------
 double hrweno_lax_friedrichs(hrweno_flux_fn f, void *ctx, double vm, double vp, const double *x, int nx, double t,
                              double alpha) {
+   if (!f) { // the reference's dummy procedure cannot be absent; a C caller's pointer can
+      fail(HRWENO_EINVAL, "hrweno_lax_friedrichs: null flux callback");
+      return std::numeric_limits<double>::quiet_NaN();
+   }
    return (f(ctx, vm, x, nx, t) + f(ctx, vp, x, nx, t) - alpha * (vp - vm)) / 2; // fluxes.f90:43
 }
 
 double hrweno_godunov(hrweno_flux_fn f, void *ctx, double vm, double vp, const double *x, int nx, double t) {
+   if (!f) {
+      fail(HRWENO_EINVAL, "hrweno_godunov: null flux callback");
+      return std::numeric_limits<double>::quiet_NaN();
+   }
    const double fm = f(ctx, vm, x, nx, t), fp = f(ctx, vp, x, nx, t); // fluxes.f90:67-68
    if (vm <= vp) return fm < fp ? fm : fp;                             // :70-74
    return fm > fp ? fm : fp;
