@@ -240,15 +240,16 @@ TFACTOR1 = [("flux = (v**2)/2", "flux = (v**2)/2*(1.0_rk + 0.25_rk*t)")]
 GROWTH_T = [("flux1 = v !*x(1)**2", "flux1 = v*x(1)**2*(1.0_rk + 0.25_rk*t)"), ("flux2 = v !*x(1)*x(2)", "flux2 = v*x(1)*x(2)*(1.0_rk + 0.25_rk*t)")]
 
 
-def tfactor_fixtures():
-    """ref_exec_example1_tfactor.npz / ref_exec_example2_growth_tfactor.npz: both programs with g(t) = 1 + t/4 on their fluxes"""
+def tfactor_fixtures(prefix="ref_exec_"):
+    """ref_exec_example1_tfactor.npz / ref_exec_example2_growth_tfactor.npz: both programs with g(t) = 1 + t/4 on their fluxes
+    (prefix "ref_exec_f32_" inside `with f90py.real_kind(4)`: the REAL32 build of the same patched sources)"""
     out = {}
     for order in (1, 2, 3):
         r = run_example1(npts=20, snaps=(0, 10, 20), order=order, extra_patch=TFACTOR1)
         for key in ("u_0", "u_10", "u_20", "times", "fevals"):
             out[f"{key}_o{order}"] = r[key]
-    np.savez(os.path.join(OUT, "ref_exec_example1_tfactor.npz"), **out)
-    np.savez(os.path.join(OUT, "ref_exec_example2_growth_tfactor.npz"),
+    np.savez(os.path.join(OUT, prefix + "example1_tfactor.npz"), **out)
+    np.savez(os.path.join(OUT, prefix + "example2_growth_tfactor.npz"),
              **run_example2(24, 20, (0, 10, 20), dt=2.5e-4, time_end=0.5, grids="geometric", nonuniform=True, n2=18, growth=True,
                             growth_patch=GROWTH_T))
 
@@ -294,6 +295,8 @@ def main32():
         np.savez(os.path.join(OUT, "ref_exec_f32_example2_growth.npz"),
                  **run_example2(24, 20, (0, 10, 20), dt=2.5e-4, time_end=0.5, grids="geometric", nonuniform=True, n2=18, growth=True))
         print(f"real32: example2 + growth on geometric 24x18 done ({time.time() - t0:.0f} s)", flush=True)
+        tfactor_fixtures("ref_exec_f32_")
+        print(f"real32: t-dependent fluxes done ({time.time() - t0:.0f} s)", flush=True)
         np.savez(os.path.join(OUT, "ref_exec_f32_example2_40.npz"), **run_example2(40, 10, (0, 1, 5, 10)))
         print(f"real32: example2 at 40x40, outputs 0..10 done ({time.time() - t0:.0f} s)", flush=True)
 
@@ -303,6 +306,9 @@ def main():
         return main32()
     if "--only-tfactor" in sys.argv:
         return tfactor_fixtures()
+    if "--only-tfactor32" in sys.argv:
+        with f90py.real_kind(4):
+            return tfactor_fixtures("ref_exec_f32_")
     quick = "--quick" in sys.argv
     t0 = time.time()
     ns1 = load("example1_burgers_1d_fv.f90")

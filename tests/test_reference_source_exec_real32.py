@@ -154,7 +154,37 @@ def test_real32_oracle_example1_lax_friedrichs_equals_reference_source(pkg, ref3
     assert ode.fevals == int(g["fevals"])
 
 
-def _example2(pkg, ref32, g, n1, n2, dt, time_end, growth=False):
+def g_of_t32(t):
+    """the time factor of the REAL32 *_tfactor fixtures, 1.0_rk + 0.25_rk*t evaluated in binary32"""
+    return float(F(1.0) + F(0.25) * F(t))
+
+
+@pytest.mark.parametrize("order", [1, 2, 3])
+def test_real32_oracle_time_dependent_flux_example1_equals_reference_source(pkg, ref32, order):
+    """example1 executed in real32 with flux = (v**2)/2*(1 + t/4): stage times and the separable factor of the REAL32 oracle"""
+    _example1_tfactor32(pkg, ref32, order)
+
+
+def _example1_tfactor32(pkg, ref32, order):
+    g = gold("example1_tfactor")
+    fv = ref32.FV(pkg.real32.make_desc(100, k=3, eps=1e-6, width=[_grid32(-5.0, 5.0, 100)[2]]))
+    fv.set_flux_time_fn(g_of_t32)
+    ode = ref32.rktvd(fv, order)
+    u, t = gold("example1")["ic"].copy(), 0.0
+    for ii in range(21):
+        t = ode.integrate(u, t, F(12.0) * F(ii) / F(100), 1e-2)
+        assert F(t) == g[f"times_o{order}"][ii]
+        if ii in (0, 10, 20):
+            assert np.array_equal(u, g[f"u_{ii}_o{order}"]), f"order {order} output {ii}"
+    assert ode.fevals == int(g[f"fevals_o{order}"])
+
+
+def test_real32_oracle_time_dependent_growth_example2_equals_reference_source(pkg, ref32):
+    _example2(pkg, ref32, gold("example2_growth_tfactor"), 24, 18, 2.5e-4, 0.5, growth=True, time_fn=g_of_t32)
+    assert not np.array_equal(gold("example2_growth_tfactor")["u_20"], gold("example2_growth")["u_20"])
+
+
+def _example2(pkg, ref32, g, n1, n2, dt, time_end, growth=False, time_fn=None):
     """example2's driver (example2:57-66) in real32, from the state its own `ic` gives (example2:48-52)"""
     e1, e2 = g["edges1"], g["edges2"]
     w1, w2, c1 = e1[1:] - e1[:-1], e2[1:] - e2[:-1], (e1[:-1] + e1[1:]) / F(2)
@@ -164,6 +194,8 @@ def _example2(pkg, ref32, g, n1, n2, dt, time_end, growth=False):
         fv.set_xedges(1, e2)
         fv.set_flux_coef(0, e1 * e1, None)  # flux1 = v*x(1)**2,   x = [right1(i), center2(j)]   example2:100-101,140
         fv.set_flux_coef(1, e2, c1)         # flux2 = v*x(1)*x(2), x = [center1(i), right2(j)]  example2:109-110,153
+    if time_fn:
+        fv.set_flux_time_fn(time_fn)
     ode = ref32.mstvd(fv)
     u, t = g["ic"].copy(), 0.0
     for ii in range(len(g["times"])):

@@ -19,3 +19,19 @@ def test_gpu_time_dependent_flux_example1_equals_reference_source(gpu_lib, pkg, 
 def test_gpu_time_dependent_growth_example2_equals_reference_source(gpu_lib, pkg):
     _example2(pkg, lambda fv: pkg.hrweno_tvdode.mstvd(fv, 24 * 18), gold("example2_growth_tfactor"), 24, 18, 2.5e-4, 0.5, growth=True,
               mod=pkg.fv, time_fn=g_of_t)
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("order", [1, 2, 3])
+def test_gpu_real32_time_dependent_flux_example1_equals_reference_source(gpu_lib, pkg, order):
+    """the REAL32 entry points against example1 executed in real32 with the same patched flux line"""
+    import test_reference_source_exec_real32 as r32
+
+    r32._example1_tfactor32(pkg, pkg.real32, order)
+
+
+@pytest.mark.gpu
+def test_gpu_real32_time_dependent_growth_example2_equals_reference_source(gpu_lib, pkg):
+    import test_reference_source_exec_real32 as r32
+
+    r32._example2(pkg, pkg.real32, r32.gold("example2_growth_tfactor"), 24, 18, 2.5e-4, 0.5, growth=True, time_fn=r32.g_of_t32)
